@@ -1,0 +1,225 @@
+/*
+ * ptb200.h — C-ABI of the B200-native radiance loop for nbonneel/pathtracer.
+ *
+ * The reference has no plugin/FFI interface: its callers reach the hot path through C++ member
+ * calls on a by-value `Raytracer` (reference mainApp.h:768, mainApp.cpp:39-47).  This header is the
+ * boundary a maintainer binds instead.  Each entry point names the reference interface it replaces
+ * (file:line into the reference tree).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns PTB_OK (0) or a negative error code; ptb_last_error() gives the text.
+ *     (the reference reports nothing: failures there are crashes or silent garbage.)
+ *   - the caller owns all input arrays; the library copies what it needs before returning.
+ *   - one ptb_ctx is bound to one CUDA device and is used from one host thread at a time.
+ *   - object ids are assigned in call order exactly like Scene::addObject (Geometry.cpp:249-252):
+ *     id 0 is the spherical light, id 1 the environment dome (Raytracer.cpp:1257-1266, hard-wired
+ *     in getColor at Raytracer.cpp:275, 303).
+ *   - images use the reference's row convention: pixel (i,j) of the camera lands in row (H-1-i)
+ *     (Raytracer.cpp:1651).
+ *
+ * The same declarations, with the prefix `ref_` / `orc_` instead of `ptb_`, are exported by the two
+ * CPU checkers under oracle/ (test infrastructure only): oracle/_ref (the reference's own sources
+ * compiled headless) and oracle/port (plain-C restatement).
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_OK                0
+#define PTB_ERR_INVALID      -1   /* bad argument */
+#define PTB_ERR_STATE        -2   /* call order (e.g. render before commit) */
+#define PTB_ERR_CUDA         -3   /* CUDA runtime / launch failure */
+#define PTB_ERR_NOMEM        -4
+#define PTB_ERR_UNSUPPORTED  -5
+
+typedef struct ptb_ctx ptb_ctx;
+
+/* Texture slot == reference `Texture` {values, W, H, multiplier} (BRDF.h:252-426).
+ * texels are the POST-LOAD float values, W*H*3, in Texture::values order: colour maps already
+ * /255 and ^2.2 (BRDF.h:393-404), normal maps already (v-128) normalised (BRDF.h:406-419), rows
+ * already flipped by load_image (utils.cpp:98-170).  W==0 (or texels==NULL) is a constant slot
+ * whose value is `mult` (Texture::getVec else-branch, BRDF.h:306-308). */
+typedef struct ptb_tex {
+    const float* texels;
+    int32_t      W, H;
+    float        mult[3];
+} ptb_tex;
+
+/* Which per-group slots exist.  Object::queryMaterial (Geometry.h:399-445) falls back to
+ * Kd=1, Ks=0, Ne=1, opaque, refr 1.3 when `idx >= slot.size()`; an absent bit selects that. */
+#define PTB_SLOT_KD      (1u << 0)   /* Object::textures         */
+#define PTB_SLOT_KS      (1u << 1)   /* Object::specularmap      */
+#define PTB_SLOT_NE      (1u << 2)   /* Object::roughnessmap     */
+#define PTB_SLOT_TRANSP  (1u << 3)   /* Object::transparent_map  (transparent iff value < 0.5) */
+#define PTB_SLOT_REFR    (1u << 4)   /* Object::refr_index_map   */
+#define PTB_SLOT_NORMAL  (1u << 5)   /* Object::normal_map       */
+#define PTB_SLOT_ALPHA   (1u << 6)   /* Object::alphamap (hit rejected in traversal iff value < 0.5,
+                                        TriangleMesh.cpp:1198-1205, 1298-1305) */
+
+typedef struct ptb_material {
+    uint32_t present;               /* PTB_SLOT_* mask */
+    ptb_tex  Kd, Ks, Ne, transp, refr, normal, alpha;
+} ptb_material;
+
+/* Object placement == the fields Object::build_matrix reads (Geometry.h:322-360). */
+typedef struct ptb_xform {
+    float scale;                    /* Object::scale            */
+    float rotation[9];              /* Object::mat_rotation, row-major */
+    float rotation_center[3];       /* Object::rotation_center  */
+    float translation[3];           /* Object::max_translation  */
+} ptb_xform;
+
+#define PTB_OBJ_MIRROR        (1 << 0)   /* Object::miroir        */
+#define PTB_OBJ_FLIP_NORMALS  (1 << 1)   /* Object::flip_normals  */
+#define PTB_OBJ_FLAT_NORMALS  (1 << 2)   /* !TriMesh::interp_normals (default interpolates) */
+
+#define PTB_BRDF_PHONG 0                 /* PhongBRDF   (BRDF.h:37-97), the Object default */
+#define PTB_BRDF_MERL  1                 /* IsoMERLBRDF (BRDF.h:192-248) */
+
+/* Triangle mesh as TriMesh::init receives it from a reader (TriangleMesh.cpp:718-841): arrays in
+ * FILE order and FILE axes.  The library applies what init applies: axis swap (x,y,z)->(-z,y,x) on
+ * vertices and normals (742-751), optional centre + normalise to `scaling` (760-770), per-vertex
+ * tangents (601-711).  tri is nTri x 10 int32: {vtx i,j,k, uv i,j,k, normal i,j,k, group}
+ * (TriangleIndices, TriangleMesh.h:53-65; -1 = absent).  Triangle ids reported back are indices
+ * into this array (the reference's own-BVH path reports BVH-permuted ids, mapped back through
+ * permuted_triangle_index, TriangleMesh.cpp:1113). */
+typedef struct ptb_mesh {
+    const float*   vertices;  int32_t n_vertices;   /* n x 3 */
+    const float*   normals;   int32_t n_normals;    /* n x 3 (mandatory for defined shading) */
+    const float*   uvs;       int32_t n_uvs;        /* n x 2 */
+    const int32_t* tri;       int32_t n_tri;        /* n x 10 */
+    float          scaling;                         /* TriMesh ctor `scaling` */
+    float          offset[3];                       /* TriMesh ctor `offset`  */
+    int32_t        center;                          /* TriMesh ctor `center`  */
+} ptb_mesh;
+
+/* Camera == the fields Camera::generateDirection reads (Vector.h:792-825), non-lenticular branch. */
+typedef struct ptb_camera {
+    float position[3], direction[3], up[3];
+    float fov;              /* radians */
+    float focus_distance;
+    float aperture;
+} ptb_camera;
+
+/* Frame parameters == the Raytracer fields render_image_nopreviz reads (Raytracer.h:73-111). */
+typedef struct ptb_params {
+    int32_t  W, H;
+    int32_t  nrays;          /* samples per pixel            */
+    int32_t  nb_bounces;     /* path depth                   */
+    float    sigma_filter;   /* Gaussian splat sigma         */
+    float    gamma;          /* display gamma                */
+    uint32_t seed;           /* global seed of the per-(pixel,sample) pcg32 streams (DESIGN.md "RNG") */
+    int32_t  shard_rank;     /* image tiles with (tile_id % shard_count) == shard_rank are rendered */
+    int32_t  shard_count;    /* 1 = whole frame */
+    int32_t  tile_size;      /* tile edge in pixels for sharding; 0 = default 64 */
+} ptb_params;
+
+typedef struct ptb_stats {
+    uint64_t samples;        /* camera samples traced                                */
+    uint64_t rays_closest;   /* Scene::intersection-equivalent queries               */
+    uint64_t rays_shadow;    /* Scene::intersection_shadow-equivalent queries        */
+    uint64_t node_visits;    /* wide-node visits   (only when the ctx counts, see ptb_set_option) */
+    uint64_t tri_tests;      /* triangle tests     (idem) */
+    double   ms_device;      /* CUDA-event time of the render on the device          */
+    double   ms_wall;        /* host steady_clock around the call                    */
+    uint64_t kernel_launches;
+} ptb_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* replaces: `Raytracer` construction (Raytracer.h:28-41) + Scene() (Geometry.h:1240-1281). */
+int  ptb_create(int device_id, ptb_ctx** out);
+void ptb_destroy(ptb_ctx*);
+const char* ptb_last_error(const ptb_ctx*);          /* ctx may be NULL: last error of a failed create */
+const char* ptb_version(void);
+
+/* ---- scene ingestion (all before ptb_commit) -------------------------------------------------- */
+/* replaces: `new Sphere(O,R)` + Scene::addObject (Geometry.h:852-873, Geometry.cpp:249-252). */
+int ptb_add_sphere(ptb_ctx*, const float O[3], float R, const ptb_xform*, int flags, int* out_id);
+/* replaces: `new Plane(A,N)` + addObject (Geometry.h:1130-1140). */
+int ptb_add_plane(ptb_ctx*, const float A[3], const float N[3], const ptb_xform*, int flags, int* out_id);
+/* replaces: `new TriMesh(scene, file, scaling, offset, mirror, NULL, false, center)` + addObject
+ * (TriangleMesh.cpp:714-841), with the reader's arrays passed in memory. */
+int ptb_add_mesh(ptb_ctx*, const ptb_mesh*, const ptb_xform*, int flags, int* out_id);
+/* replaces: Object::{add,set}_{col_,}{texture,specular,roughness,transp,refr,alpha,normalmap}
+ * (Geometry.cpp:56-245) for slot index `group` of object `obj`. */
+int ptb_set_group_material(ptb_ctx*, int obj, int group, const ptb_material*);
+/* replaces: `obj->brdf = new IsoMERLBRDF(path)` (mainApp.cpp:2436) / the PhongBRDF default. */
+int ptb_set_brdf(ptb_ctx*, int obj, int brdf_kind, int merl_id);
+/* replaces: read_brdf (MERLBRDFRead.cpp:212-235): table = 3 x (90*90*180) doubles as stored in the file. */
+int ptb_add_merl(ptb_ctx*, const double* table, int* out_merl_id);
+/* replaces: Sphere::load_envmap on object 1 (Geometry.h:912-916): 8-bit RGB, rows as load_image returns them. */
+int ptb_set_envmap(ptb_ctx*, const uint8_t* rgb, int W, int H);
+/* replaces: Scene::intensite_lumiere / Scene::envmap_intensity (Raytracer.cpp:1270-1271). */
+int ptb_set_light(ptb_ctx*, float intensite_lumiere, float envmap_intensity);
+
+/* replaces: TriMesh::build_bvh (TriangleMesh.cpp:878-885, 1029-1130) + Scene::prepare_render
+ * (Geometry.cpp:280-308): builds the wide BVH over all meshes and uploads the scene to the device. */
+int ptb_commit(ptb_ctx*);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+/* replaces: Raytracer::render_image_nopreviz (Raytracer.cpp:1565-1798) up to and including the
+ * tonemap.  HOST outputs, any may be NULL:
+ *   imagedouble  W*H*3 float  linear radiance / weight     (Raytracer::imagedouble, 1687-1694)
+ *   sample_count W*H   float  filter weight sum            (Raytracer::sample_count)
+ *   image        W*H*3 uint8  tonemapped                   (Raytracer::image, 1701-1708)  */
+int ptb_render(ptb_ctx*, const ptb_camera*, const ptb_params*,
+               float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats);
+
+/* Sharded form for one-process-per-GPU runs: adds this shard's un-normalised sums into a DEVICE
+ * buffer d_rgbw (W*H float4 = {sum r, sum g, sum b, sum weight}, reference row convention) owned
+ * by the caller (e.g. a torch tensor, so NCCL can move it).  The buffer is NOT cleared. */
+int ptb_render_accum(ptb_ctx*, const ptb_camera*, const ptb_params*, float* d_rgbw, ptb_stats* stats);
+/* Normalise + tonemap a DEVICE rgbw buffer into HOST outputs (the tail of render_image_nopreviz,
+ * Raytracer.cpp:1687-1708).  Outputs may be NULL. */
+int ptb_resolve(ptb_ctx*, const float* d_rgbw, int W, int H, float gamma,
+                float* imagedouble, float* sample_count, uint8_t* image);
+/* Tile gather support (multi-GPU): pack / unpack-add the tiles owned by a shard, each with a
+ * ceil(2*sigma) apron, between a full-frame DEVICE rgbw buffer and a dense DEVICE staging buffer.
+ * ptb_shard_pack_size gives the staging size in floats for a shard. */
+int ptb_shard_pack_size(const ptb_params*, int shard_rank, int64_t* out_floats);
+int ptb_shard_pack(ptb_ctx*, const ptb_params*, int shard_rank, const float* d_rgbw, float* d_packed);
+int ptb_shard_unpack_add(ptb_ctx*, const ptb_params*, int shard_rank, const float* d_packed, float* d_rgbw);
+
+/* replaces: the picking query (mainApp.h:686-692): pixel-centre rays
+ * cam.generateDirection(0,i,j,0,0,0,0,0,W,H) + Scene::intersection.  HOST outputs W*H each, row i,
+ * column j at [i*W+j] (camera order, not flipped); obj_id -1 = miss; tri_id -1 = not a mesh. */
+int ptb_primary_ids(ptb_ctx*, const ptb_camera*, int W, int H,
+                    int32_t* obj_id, int32_t* tri_id, float* t);
+
+/* ---- options and introspection ----------------------------------------------------------------- */
+#define PTB_OPT_COUNT_TRAVERSAL  1   /* 1: count node visits / triangle tests (instrumented kernels) */
+#define PTB_OPT_POOL_PATHS       2   /* paths in flight per pass (default 1<<24) */
+int ptb_set_option(ptb_ctx*, int option, int64_t value);
+
+typedef struct ptb_scene_info {
+    int64_t n_triangles, n_bvh_nodes, bytes_nodes, bytes_triangles, bytes_attributes, bytes_textures;
+    int32_t n_objects, bvh_depth;
+    double  ms_bvh_build, ms_upload;
+} ptb_scene_info;
+int ptb_get_scene_info(const ptb_ctx*, ptb_scene_info*);
+
+/* Function-level probes used by the parity tests: run the DEVICE implementation of one building
+ * block on n inputs.  `which` selects the block, in/out layouts are documented in DESIGN.md §KAT. */
+#define PTB_KAT_PCG32          1   /* in: u64 {state_seed, stream} x n  -> out: 4 x u32 draws as double */
+#define PTB_KAT_LATTICE        2   /* in: k                    -> out: x, y                  (Raytracer.cpp:1311-1319) */
+#define PTB_KAT_CAMERA         3   /* in: i,j,dx,dy,ax,ay      -> out: o[3], d[3]            (Vector.h:792-825) */
+#define PTB_KAT_RANDOM_COS     4   /* in: N[3], r1, r2         -> out: v[3]                  (Vector.h:581-589) */
+#define PTB_KAT_RANDOM_PHONG   5   /* in: R[3], n, r1, r2      -> out: v[3]                  (BRDF.h:41-61) */
+#define PTB_KAT_PHONG_EVAL     6   /* in: Kd3,Ks3,Ne3,wi3,wo3,N3 -> out: f[3]                (BRDF.h:88-96) */
+#define PTB_KAT_MERL_EVAL      7   /* in: wi3,wo3,N3 (merl id 0) -> out: f[3]                (BRDF.h:204-246) */
+#define PTB_KAT_FAST_EXP       8   /* in: y                    -> out: fast_exp(y)           (Raytracer.cpp:1294-1299) */
+#define PTB_KAT_FAST_NORMALIZE 9   /* in: v[3]                 -> out: v[3]                  (Vector.h:294-309, 376-382) */
+#define PTB_KAT_RANDOM_PER_PIXEL 10 /* in: pixel index p       -> out: randomPerPixel[p].x,.y (Raytracer.cpp:1341-1344) */
+#define PTB_KAT_FILTER_RATIO   11  /* in: i,j,W,H,sigma        -> out: ratio                 (Raytracer.cpp:1604-1608) */
+int ptb_kat(ptb_ctx*, int which, const ptb_camera* cam, int W, int H,
+            const double* in, int n, int in_stride, double* out, int out_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

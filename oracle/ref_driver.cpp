@@ -1,0 +1,404 @@
+// oracle/ref_driver.cpp — TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Headless driver over the REFERENCE's own classes (Raytracer, Scene, TriMesh, Sphere, Plane,
+// PhongBRDF, IsoMERLBRDF ...).  It is #included at the end of the unity translation unit that
+// oracle/build_ref.py writes, after the reference's patched .cpp files, so every symbol used below
+// is the reference's.  It exports the ABI of include/ptb200.h under the prefix ref_ so the parity
+// tests can feed one scene description to the reference and to the CUDA path.
+//
+// Scene construction follows SURVEY.md App. B (in-memory route, no .scn/.obj files):
+//   meshes : `new TriMesh()`, fill vertices/normals/uvs/indices, `init(scene,"synthetic",...)`
+//            (TriangleMesh.cpp:718-841 skips the file readers for names without .obj/.off/.wrl)
+//   slots  : Texture objects pushed into Object::{textures,specularmap,...} (Geometry.h:672)
+//   envmap : Sphere::{envtex,envW,envH,has_envmap} filled directly (Geometry.h:1096-1101)
+//   MERL   : IsoMERLBRDF with `data` pointed at the caller's table (BRDF.h:247)
+#define ORACLE_PREFIX ref_
+#include "prefix.h"
+#include "ptb200.h"
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+uint32_t ptb_ref_global_seed = 0;
+unsigned long long ptb_ref_cnt[64][8];
+
+struct ptb_ctx {
+    Raytracer* rt;
+    std::string err;
+    std::vector<double*> merl;
+    bool committed;
+    int threads;
+    double ms_build;
+    long long n_tri;
+};
+
+static std::string g_create_err;
+
+static void apply_xform(Object* o, const ptb_xform* xf, bool is_mesh) {
+    if (!xf) return;
+    o->scale = xf->scale;
+    for (int i = 0; i < 9; i++) o->mat_rotation[i] = xf->rotation[i];
+    o->max_translation = Vector(xf->translation[0], xf->translation[1], xf->translation[2]);
+    if (!(xf->rotation_center[0] != xf->rotation_center[0]))  // NaN keeps the object's own centre
+        o->rotation_center = Vector(xf->rotation_center[0], xf->rotation_center[1], xf->rotation_center[2]);
+}
+
+static void apply_flags(Object* o, int flags) {
+    o->miroir = (flags & PTB_OBJ_MIRROR) != 0;
+    o->flip_normals = (flags & PTB_OBJ_FLIP_NORMALS) != 0;
+    o->ghost = false;
+}
+
+static Texture make_tex(const ptb_tex& t, int type) {
+    Texture tex;  // W=H=0, multiplier (1,1,1), type 0
+    tex.type = type;
+    tex.multiplier = Vector(t.mult[0], t.mult[1], t.mult[2]);
+    tex.filename = "Null";
+    if (t.texels && t.W > 0 && t.H > 0) {
+        tex.W = t.W;
+        tex.H = t.H;
+        tex.values.assign(t.texels, t.texels + (size_t)t.W * t.H * 3);
+    }
+    return tex;
+}
+
+static void set_slot(std::vector<Texture>& slot, int group, const Texture& t) {
+    if ((int)slot.size() <= group) slot.resize(group + 1);
+    slot[group] = t;
+}
+
+extern "C" {
+
+const char* ptb_version(void) { return "ptb-oracle-ref (reference sources, own BVH, headless)"; }
+
+const char* ptb_last_error(const ptb_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int ptb_create(int device_id, ptb_ctx** out) {
+    (void)device_id;
+    if (!out) return PTB_ERR_INVALID;
+    ptb_ctx* c = new ptb_ctx();
+    c->rt = new Raytracer();  // heap: contribsArray is ~0.6 MB
+    Raytracer* rt = c->rt;
+    rt->W = 64; rt->H = 64; rt->nrays = 1; rt->nb_bounces = 5;
+    rt->last_nrays = -1; rt->lastfilter = -1;
+    rt->sigma_filter = 0.5f; rt->gamma = 2.2f;
+    rt->autosave = false; rt->has_denoiser = false; rt->is_recording = false;
+    rt->sphereEnv = NULL;
+    Scene& s = rt->s;
+    s.fog_density = s.fog_absorption = s.fog_density_decay = s.fog_absorption_decay = 0;
+    s.fog_type = s.fog_phase_type = 0; s.phase_aniso = 0; s.nbframes = 1;
+    s.lumiere = NULL; s.intensite_lumiere = 0; s.envmap_intensity = 1;
+    c->committed = false;
+    c->threads = 0;
+    c->ms_build = 0;
+    c->n_tri = 0;
+    *out = c;
+    return PTB_OK;
+}
+
+void ptb_destroy(ptb_ctx* c) {
+    if (!c) return;
+    c->rt->s.clear();
+    delete c->rt;
+    for (size_t i = 0; i < c->merl.size(); i++) free(c->merl[i]);
+    delete c;
+}
+
+int ptb_add_sphere(ptb_ctx* c, const float O[3], float R, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !O) return PTB_ERR_INVALID;
+    Sphere* sp = new Sphere(Vector(O[0], O[1], O[2]), R);  // rotation_center = O (Geometry.h:869)
+    apply_flags(sp, flags);
+    apply_xform(sp, xf, false);
+    c->rt->s.addObject(sp);
+    int id = (int)c->rt->s.objects.size() - 1;
+    if (id == 0) c->rt->s.lumiere = sp;  // Raytracer.cpp:1269
+    if (out_id) *out_id = id;
+    return PTB_OK;
+}
+
+int ptb_add_plane(ptb_ctx* c, const float A[3], const float N[3], const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !A || !N) return PTB_ERR_INVALID;
+    Plane* p = new Plane(Vector(A[0], A[1], A[2]), Vector(N[0], N[1], N[2]));
+    apply_flags(p, flags);
+    apply_xform(p, xf, false);
+    c->rt->s.addObject(p);
+    if (out_id) *out_id = (int)c->rt->s.objects.size() - 1;
+    return PTB_OK;
+}
+
+int ptb_add_mesh(ptb_ctx* c, const ptb_mesh* m, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !m || !m->vertices || !m->tri || m->n_tri <= 0) return PTB_ERR_INVALID;
+    auto t0 = std::chrono::steady_clock::now();
+    TriMesh* g = new TriMesh();
+    g->vertices.resize(m->n_vertices);
+    for (int i = 0; i < m->n_vertices; i++) g->vertices[i] = Vector(m->vertices[3 * i], m->vertices[3 * i + 1], m->vertices[3 * i + 2]);
+    g->normals.resize(m->n_normals);
+    for (int i = 0; i < m->n_normals; i++) g->normals[i] = Vector(m->normals[3 * i], m->normals[3 * i + 1], m->normals[3 * i + 2]);
+    g->uvs.resize(m->n_uvs);
+    for (int i = 0; i < m->n_uvs; i++) g->uvs[i] = Vector(m->uvs[2 * i], m->uvs[2 * i + 1], 0.f);
+    g->indices.resize(m->n_tri);
+    for (int i = 0; i < m->n_tri; i++) {
+        const int32_t* t = m->tri + 10 * (size_t)i;
+        // ctor order: vtx i,j,k, ni,nj,nk, uvi,uvj,uvk, group (TriangleMesh.h:55)
+        g->indices[i] = TriangleIndices(t[0], t[1], t[2], t[6], t[7], t[8], t[3], t[4], t[5], t[9]);
+    }
+    g->bvh_depth = 0;
+    g->init(&c->rt->s, "synthetic", m->scaling, Vector(m->offset[0], m->offset[1], m->offset[2]),
+            (flags & PTB_OBJ_MIRROR) != 0, NULL, false, false, m->center != 0);
+    apply_flags(g, flags);
+    g->interp_normals = (flags & PTB_OBJ_FLAT_NORMALS) == 0;
+    apply_xform(g, xf, true);
+    c->rt->s.addObject(g);
+    c->ms_build += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->n_tri += m->n_tri;
+    if (out_id) *out_id = (int)c->rt->s.objects.size() - 1;
+    return PTB_OK;
+}
+
+int ptb_set_group_material(ptb_ctx* c, int obj, int group, const ptb_material* m) {
+    if (!c || !m || obj < 0 || obj >= (int)c->rt->s.objects.size() || group < 0) return PTB_ERR_INVALID;
+    Object* o = c->rt->s.objects[obj];
+    if (m->present & PTB_SLOT_KD) set_slot(o->textures, group, make_tex(m->Kd, 0));
+    if (m->present & PTB_SLOT_KS) set_slot(o->specularmap, group, make_tex(m->Ks, 1));
+    if (m->present & PTB_SLOT_NE) set_slot(o->roughnessmap, group, make_tex(m->Ne, 4));
+    if (m->present & PTB_SLOT_TRANSP) set_slot(o->transparent_map, group, make_tex(m->transp, 5));
+    if (m->present & PTB_SLOT_REFR) set_slot(o->refr_index_map, group, make_tex(m->refr, 6));
+    if (m->present & PTB_SLOT_NORMAL) set_slot(o->normal_map, group, make_tex(m->normal, 2));
+    if (m->present & PTB_SLOT_ALPHA) set_slot(o->alphamap, group, make_tex(m->alpha, 3));
+    return PTB_OK;
+}
+
+int ptb_add_merl(ptb_ctx* c, const double* table, int* out_merl_id) {
+    if (!c || !table) return PTB_ERR_INVALID;
+    const size_t n = (size_t)3 * 90 * 90 * 180;
+    double* copy = (double*)malloc(n * sizeof(double));
+    memcpy(copy, table, n * sizeof(double));
+    c->merl.push_back(copy);
+    if (out_merl_id) *out_merl_id = (int)c->merl.size() - 1;
+    return PTB_OK;
+}
+
+int ptb_set_brdf(ptb_ctx* c, int obj, int kind, int merl_id) {
+    if (!c || obj < 0 || obj >= (int)c->rt->s.objects.size()) return PTB_ERR_INVALID;
+    Object* o = c->rt->s.objects[obj];
+    if (kind == PTB_BRDF_PHONG) {
+        o->brdf = new PhongBRDF();
+    } else if (kind == PTB_BRDF_MERL) {
+        if (merl_id < 0 || merl_id >= (int)c->merl.size()) return PTB_ERR_INVALID;
+        IsoMERLBRDF* b = new IsoMERLBRDF(std::string(""));  // read_brdf fails on "", leaves data unset
+        b->data = c->merl[merl_id];
+        o->brdf = b;
+    } else {
+        return PTB_ERR_UNSUPPORTED;
+    }
+    return PTB_OK;
+}
+
+int ptb_set_envmap(ptb_ctx* c, const uint8_t* rgb, int W, int H) {
+    if (!c || c->rt->s.objects.size() < 2) return PTB_ERR_STATE;
+    Sphere* dome = dynamic_cast<Sphere*>(c->rt->s.objects[1]);
+    if (!dome) return PTB_ERR_STATE;
+    if (!rgb || W <= 0 || H <= 0) { dome->has_envmap = false; return PTB_OK; }
+    dome->envtex.assign(rgb, rgb + (size_t)W * H * 3);
+    dome->envW = W; dome->envH = H;
+    dome->has_envmap = true;
+    return PTB_OK;
+}
+
+int ptb_set_light(ptb_ctx* c, float intensite_lumiere, float envmap_intensity) {
+    if (!c) return PTB_ERR_INVALID;
+    c->rt->s.intensite_lumiere = intensite_lumiere;
+    c->rt->s.envmap_intensity = envmap_intensity;
+    return PTB_OK;
+}
+
+int ptb_commit(ptb_ctx* c) {
+    if (!c) return PTB_ERR_INVALID;
+    if (c->rt->s.objects.size() < 2 || !c->rt->s.lumiere) { c->err = "need light (id 0) and dome (id 1)"; return PTB_ERR_STATE; }
+    c->committed = true;
+    return PTB_OK;
+}
+
+static void set_camera(Raytracer* rt, const ptb_camera* cam) {
+    rt->cam = Camera(Vector(cam->position[0], cam->position[1], cam->position[2]),
+                     Vector(cam->direction[0], cam->direction[1], cam->direction[2]),
+                     Vector(cam->up[0], cam->up[1], cam->up[2]));
+    rt->cam.fov = cam->fov;
+    rt->cam.focus_distance = cam->focus_distance;
+    rt->cam.aperture = cam->aperture;
+}
+
+static int setup_frame(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p) {
+    if (!c || !cam || !p || p->W <= 0 || p->H <= 0 || p->nrays <= 0) return PTB_ERR_INVALID;
+    if (!c->committed) return PTB_ERR_STATE;
+    Raytracer* rt = c->rt;
+    set_camera(rt, cam);
+    rt->W = p->W; rt->H = p->H; rt->nrays = p->nrays; rt->nb_bounces = p->nb_bounces;
+    rt->sigma_filter = p->sigma_filter; rt->gamma = p->gamma;
+    rt->s.double_frustum_start_t = 0; rt->s.current_frame = 0;
+    ptb_ref_global_seed = p->seed;
+    int nt = c->threads > 0 ? c->threads : omp_get_num_procs();
+    if (nt > 64) nt = 64;  // engine[64], contribsArray[64] (Vector.h:29, Raytracer.h:114-115)
+    omp_set_num_threads(nt);
+    return PTB_OK;
+}
+
+int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p,
+               float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats) {
+    int rc = setup_frame(c, cam, p);
+    if (rc) return rc;
+    if (p->shard_count > 1) return PTB_ERR_UNSUPPORTED;
+    Raytracer* rt = c->rt;
+    memset(ptb_ref_cnt, 0, sizeof(ptb_ref_cnt));
+    auto t0 = std::chrono::steady_clock::now();
+    rt->render_image_nopreviz();
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    size_t n = (size_t)p->W * p->H;
+    if (imagedouble) memcpy(imagedouble, &rt->imagedouble[0], n * 3 * sizeof(float));
+    if (sample_count) memcpy(sample_count, &rt->sample_count[0], n * sizeof(float));
+    if (image) memcpy(image, &rt->image[0], n * 3);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->samples = (uint64_t)n * p->nrays;
+        for (int t = 0; t < 64; t++) { stats->rays_closest += ptb_ref_cnt[t][0]; stats->rays_shadow += ptb_ref_cnt[t][1]; }
+        stats->ms_wall = ms;
+        stats->ms_device = 0;
+    }
+    return PTB_OK;
+}
+
+int ptb_render_accum(ptb_ctx*, const ptb_camera*, const ptb_params*, float*, ptb_stats*) { return PTB_ERR_UNSUPPORTED; }
+int ptb_resolve(ptb_ctx*, const float*, int, int, float, float*, float*, uint8_t*) { return PTB_ERR_UNSUPPORTED; }
+int ptb_shard_pack_size(const ptb_params*, int, int64_t*) { return PTB_ERR_UNSUPPORTED; }
+int ptb_shard_pack(ptb_ctx*, const ptb_params*, int, const float*, float*) { return PTB_ERR_UNSUPPORTED; }
+int ptb_shard_unpack_add(ptb_ctx*, const ptb_params*, int, const float*, float*) { return PTB_ERR_UNSUPPORTED; }
+
+int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* obj_id, int32_t* tri_id, float* tout) {
+    if (!c || !cam || W <= 0 || H <= 0) return PTB_ERR_INVALID;
+    if (!c->committed) return PTB_ERR_STATE;
+    Raytracer* rt = c->rt;
+    set_camera(rt, cam);
+    rt->s.current_frame = 0;
+    rt->s.prepare_render(false);
+    // the picking query, mainApp.h:686-692
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int i = 0; i < H; i++) {
+        for (int j = 0; j < W; j++) {
+            Ray r = rt->cam.generateDirection(0, i, j, 0, 0, 0, 0, 0, W, H);
+            Vector P; MaterialValues mat; int id = -1, tri = -1; float t;
+            bool hit = rt->s.intersection(r, P, id, t, mat, tri);
+            int32_t oid = -1, tid = -1;
+            if (hit) {
+                oid = id;
+                TriMesh* g = rt->s.castToMesh[id];
+                if (g && tri >= 0) tid = g->permuted_triangle_index[tri];
+            }
+            if (obj_id) obj_id[(size_t)i * W + j] = oid;
+            if (tri_id) tri_id[(size_t)i * W + j] = tid;
+            if (tout) tout[(size_t)i * W + j] = hit ? t : -1.f;
+        }
+    }
+    return PTB_OK;
+}
+
+int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
+    if (!c) return PTB_ERR_INVALID;
+    if (option == ORC_OPT_THREADS) { c->threads = (int)value; return PTB_OK; }
+    return PTB_OK;  // GPU-only options are ignored
+}
+
+int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
+    if (!c || !info) return PTB_ERR_INVALID;
+    memset(info, 0, sizeof(*info));
+    info->n_triangles = c->n_tri;
+    info->n_objects = (int)c->rt->s.objects.size();
+    info->ms_bvh_build = c->ms_build;
+    for (size_t i = 0; i < c->rt->s.objects.size(); i++) {
+        TriMesh* g = c->rt->s.castToMesh[i];
+        if (g) { info->n_bvh_nodes += g->bvh.nodes.size(); if (g->bvh_depth > info->bvh_depth) info->bvh_depth = g->bvh_depth; }
+    }
+    info->bytes_nodes = info->n_bvh_nodes * (int64_t)sizeof(BVHNodes);
+    info->bytes_triangles = info->n_triangles * (int64_t)sizeof(Triangle);
+    return PTB_OK;
+}
+
+int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H,
+            const double* in, int n, int is, double* out, int os) {
+    if (!c || !in || !out) return PTB_ERR_INVALID;
+    Raytracer* rt = c->rt;
+    if (cam) set_camera(rt, cam);
+    if (which == PTB_KAT_RANDOM_PER_PIXEL || which == PTB_KAT_FILTER_RATIO) {
+        if (!c->committed) return PTB_ERR_STATE;
+        rt->W = W; rt->H = H;
+        if (which == PTB_KAT_FILTER_RATIO) { rt->sigma_filter = (float)in[2]; rt->lastfilter = -1; }
+        rt->prepare_render(0);
+    }
+    for (int k = 0; k < n; k++) {
+        const double* a = in + (size_t)k * is;
+        double* o = out + (size_t)k * os;
+        switch (which) {
+        case PTB_KAT_PCG32: {
+            pcg32 e((uint64_t)a[0], (uint64_t)a[1]);
+            for (int q = 0; q < 4; q++) o[q] = (double)e();
+        } break;
+        case PTB_KAT_LATTICE: {
+            Vector v = extensibleLattice2d((uint32_t)a[0]);
+            o[0] = v[0]; o[1] = v[1];
+        } break;
+        case PTB_KAT_CAMERA: {
+            Ray r = rt->cam.generateDirection(0, (int)a[0], (int)a[1], 0, (float)a[2], (float)a[3], (float)a[4], (float)a[5], W, H);
+            for (int q = 0; q < 3; q++) { o[q] = r.origin[q]; o[3 + q] = r.direction[q]; }
+        } break;
+        case PTB_KAT_RANDOM_COS: {
+            Vector v = random_cos(Vector((float)a[0], (float)a[1], (float)a[2]), (float)a[3], (float)a[4]);
+            for (int q = 0; q < 3; q++) o[q] = v[q];
+        } break;
+        case PTB_KAT_RANDOM_PHONG: {
+            Vector v = PhongBRDF::random_Phong(Vector((float)a[0], (float)a[1], (float)a[2]), (float)a[3], (float)a[4], (float)a[5]);
+            for (int q = 0; q < 3; q++) o[q] = v[q];
+        } break;
+        case PTB_KAT_PHONG_EVAL: {
+            MaterialValues m;
+            m.Kd = Vector((float)a[0], (float)a[1], (float)a[2]);
+            m.Ks = Vector((float)a[3], (float)a[4], (float)a[5]);
+            m.Ne = Vector((float)a[6], (float)a[7], (float)a[8]);
+            PhongBRDF b;
+            Vector v = b.eval(m, Vector((float)a[9], (float)a[10], (float)a[11]), Vector((float)a[12], (float)a[13], (float)a[14]),
+                              Vector((float)a[15], (float)a[16], (float)a[17]));
+            for (int q = 0; q < 3; q++) o[q] = v[q];
+        } break;
+        case PTB_KAT_MERL_EVAL: {
+            if (c->merl.empty()) return PTB_ERR_STATE;
+            IsoMERLBRDF b(std::string(""));
+            b.data = c->merl[0];
+            MaterialValues m;
+            Vector v = b.eval(m, Vector((float)a[0], (float)a[1], (float)a[2]), Vector((float)a[3], (float)a[4], (float)a[5]),
+                              Vector((float)a[6], (float)a[7], (float)a[8]));
+            for (int q = 0; q < 3; q++) o[q] = v[q];
+        } break;
+        case PTB_KAT_FAST_EXP: o[0] = fast_exp(a[0]); break;
+        case PTB_KAT_FAST_NORMALIZE: {
+            Vector v((float)a[0], (float)a[1], (float)a[2]);
+            v.fast_normalize();
+            for (int q = 0; q < 3; q++) o[q] = v[q];
+        } break;
+        case PTB_KAT_RANDOM_PER_PIXEL: {
+            size_t p = (size_t)a[0];
+            o[0] = rt->randomPerPixel[p][0]; o[1] = rt->randomPerPixel[p][1];
+        } break;
+        case PTB_KAT_FILTER_RATIO: {
+            int i = (int)a[0], j = (int)a[1];
+            int fs = rt->filter_size, ftw = rt->filter_total_width;
+            int bmin_i = std::max(0, i - fs), bmax_i = std::min(i + fs, H - 1);
+            int bmin_j = std::max(0, j - fs), bmax_j = std::min(j + fs, W - 1);
+            float ratio = 1.f / sum_area_table(&rt->filter_integral[0], ftw, bmin_i - i + fs, bmax_i - i + fs, bmin_j - j + fs, bmax_j - j + fs);
+            o[0] = ratio;
+        } break;
+        default: return PTB_ERR_UNSUPPORTED;
+        }
+    }
+    return PTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+"""ctypes mirror of include/ptb200.h.
+
+`Lib(cdll, prefix)` binds the C-ABI entry points of one shared library.  The product binds
+libptb200.so with prefix "ptb_" (see pathtracer_b200/__init__.py); the tests bind the CPU checkers
+under oracle/ with their own prefixes through the same class, so one scene description can be fed
+to each implementation unchanged.
+"""
+import ctypes as C
+
+import numpy as np
+
+OK = 0
+SLOT_KD, SLOT_KS, SLOT_NE, SLOT_TRANSP, SLOT_REFR, SLOT_NORMAL, SLOT_ALPHA = (1 << i for i in range(7))
+OBJ_MIRROR, OBJ_FLIP_NORMALS, OBJ_FLAT_NORMALS = 1, 2, 4
+BRDF_PHONG, BRDF_MERL = 0, 1
+OPT_COUNT_TRAVERSAL, OPT_POOL_PATHS = 1, 2
+ORC_OPT_THREADS = 100
+(KAT_PCG32, KAT_LATTICE, KAT_CAMERA, KAT_RANDOM_COS, KAT_RANDOM_PHONG, KAT_PHONG_EVAL, KAT_MERL_EVAL,
+ KAT_FAST_EXP, KAT_FAST_NORMALIZE, KAT_RANDOM_PER_PIXEL, KAT_FILTER_RATIO) = range(1, 12)
+KAT_SHAPES = {  # which -> (n_in, n_out)
+    KAT_PCG32: (2, 4), KAT_LATTICE: (1, 2), KAT_CAMERA: (6, 6), KAT_RANDOM_COS: (5, 3),
+    KAT_RANDOM_PHONG: (6, 3), KAT_PHONG_EVAL: (18, 3), KAT_MERL_EVAL: (9, 3), KAT_FAST_EXP: (1, 1),
+    KAT_FAST_NORMALIZE: (3, 3), KAT_RANDOM_PER_PIXEL: (1, 2), KAT_FILTER_RATIO: (3, 1),
+}
+
+_fp = C.POINTER(C.c_float)
+
+
+class Tex(C.Structure):
+    _fields_ = [("texels", _fp), ("W", C.c_int32), ("H", C.c_int32), ("mult", C.c_float * 3)]
+
+
+class Material(C.Structure):
+    _fields_ = [("present", C.c_uint32), ("Kd", Tex), ("Ks", Tex), ("Ne", Tex), ("transp", Tex),
+                ("refr", Tex), ("normal", Tex), ("alpha", Tex)]
+
+
+class Xform(C.Structure):
+    _fields_ = [("scale", C.c_float), ("rotation", C.c_float * 9), ("rotation_center", C.c_float * 3),
+                ("translation", C.c_float * 3)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("vertices", _fp), ("n_vertices", C.c_int32), ("normals", _fp), ("n_normals", C.c_int32),
+                ("uvs", _fp), ("n_uvs", C.c_int32), ("tri", C.POINTER(C.c_int32)), ("n_tri", C.c_int32),
+                ("scaling", C.c_float), ("offset", C.c_float * 3), ("center", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("direction", C.c_float * 3), ("up", C.c_float * 3),
+                ("fov", C.c_float), ("focus_distance", C.c_float), ("aperture", C.c_float)]
+
+
+class Params(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("nrays", C.c_int32), ("nb_bounces", C.c_int32),
+                ("sigma_filter", C.c_float), ("gamma", C.c_float), ("seed", C.c_uint32),
+                ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("tile_size", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
+                ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("ms_device", C.c_double),
+                ("ms_wall", C.c_double), ("kernel_launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("n_triangles", C.c_int64), ("n_bvh_nodes", C.c_int64), ("bytes_nodes", C.c_int64),
+                ("bytes_triangles", C.c_int64), ("bytes_attributes", C.c_int64), ("bytes_textures", C.c_int64),
+                ("n_objects", C.c_int32), ("bvh_depth", C.c_int32), ("ms_bvh_build", C.c_double),
+                ("ms_upload", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/ptb200.h declares (tests check the product library exports all of them)
+SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_mesh",
+           "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "commit", "render",
+           "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
+           "set_option", "get_scene_info", "kat"]
+
+
+class PtbError(RuntimeError):
+    pass
+
+
+class Lib:
+    """Bound entry points of one implementation of the ptb200 C-ABI."""
+
+    def __init__(self, cdll, prefix="ptb_"):
+        self.cdll, self.prefix = cdll, prefix
+        vp, ip = C.c_void_p, C.POINTER(C.c_int)
+        sig = {
+            "create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+            "destroy": (None, [vp]),
+            "last_error": (C.c_char_p, [vp]),
+            "version": (C.c_char_p, []),
+            "add_sphere": (C.c_int, [vp, _fp, C.c_float, C.POINTER(Xform), C.c_int, ip]),
+            "add_plane": (C.c_int, [vp, _fp, _fp, C.POINTER(Xform), C.c_int, ip]),
+            "add_mesh": (C.c_int, [vp, C.POINTER(Mesh), C.POINTER(Xform), C.c_int, ip]),
+            "set_group_material": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(Material)]),
+            "set_brdf": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+            "add_merl": (C.c_int, [vp, C.POINTER(C.c_double), ip]),
+            "set_envmap": (C.c_int, [vp, C.POINTER(C.c_uint8), C.c_int, C.c_int]),
+            "set_light": (C.c_int, [vp, C.c_float, C.c_float]),
+            "commit": (C.c_int, [vp]),
+            "render": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), _fp, _fp, C.POINTER(C.c_uint8), C.POINTER(Stats)]),
+            "render_accum": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), vp, C.POINTER(Stats)]),
+            "resolve": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_float, _fp, _fp, C.POINTER(C.c_uint8)]),
+            "shard_pack_size": (C.c_int, [C.POINTER(Params), C.c_int, C.POINTER(C.c_int64)]),
+            "shard_pack": (C.c_int, [vp, C.POINTER(Params), C.c_int, vp, vp]),
+            "shard_unpack_add": (C.c_int, [vp, C.POINTER(Params), C.c_int, vp, vp]),
+            "primary_ids": (C.c_int, [vp, C.POINTER(Camera), C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _fp]),
+            "set_option": (C.c_int, [vp, C.c_int, C.c_int64]),
+            "get_scene_info": (C.c_int, [vp, C.POINTER(SceneInfo)]),
+            "kat": (C.c_int, [vp, C.c_int, C.POINTER(Camera), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
+                              C.POINTER(C.c_double), C.c_int]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(cdll, prefix + name)  # AttributeError if the symbol is missing: loud by design
+            fn.restype, fn.argtypes = res, args
+            setattr(self, name, fn)
+
+    def check(self, rc, ctx=None):
+        if rc != OK:
+            msg = self.last_error(ctx)
+            raise PtbError(f"{self.prefix}* call failed rc={rc}: {msg.decode() if msg else ''}")
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def fptr(a):
+    return a.ctypes.data_as(_fp) if a is not None else None

@@ -1,0 +1,307 @@
+"""Host-side mirror of the reference's operator surface for the radiance loop.
+
+Names and argument meaning follow the reference (`Raytracer`, `Scene`, `Sphere`, `Plane`, `TriMesh`,
+`Camera`; Raytracer.h:25-121, Geometry.h:849-1217, TriangleMesh.h:113-255, Vector.h:720-840) so the
+parity tests read like reference code.  Everything here is description + plumbing: the objects only
+record what the reference's objects hold and hand it to a C-ABI implementation (`_abi.Lib`) — the
+CUDA library for the product, a CPU checker in the tests.  No rendering arithmetic lives in Python.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _abi
+from ._abi import f32, fptr
+
+
+class Camera:
+    """Vector.h:720-840 (non-lenticular).  rotate() follows Camera::rotate (738-765)."""
+
+    def __init__(self, position=(0, 0, 50), direction=(0, 0, -1), up=(0, 1, 0)):
+        self.position = np.array(position, np.float32)
+        self.direction = np.array(direction, np.float32)
+        self.up = np.array(up, np.float32)
+        self.fov = np.float32(35 * math.pi / 180)
+        self.focus_distance = np.float32(50)
+        self.aperture = np.float32(0.1)
+
+    def rotate(self, angle_x, angle_y, time):
+        ax, ay = np.float32(time * angle_x), np.float32(time * angle_y)
+        cx, sx, cy, sy = (np.float32(f(a)) for f, a in ((math.cos, ax), (math.sin, ax), (math.cos, ay), (math.sin, ay)))
+
+        def rot(v):
+            t = np.array([v[0], cy * v[1] - sy * v[2], sy * v[1] + cy * v[2]], np.float32)
+            return np.array([cx * t[0] - sx * t[2], t[1], sx * t[0] + cx * t[2]], np.float32)
+
+        self.direction, self.up = rot(self.direction), rot(self.up)
+
+    def c_struct(self):
+        c = _abi.Camera()
+        c.position[:] = [float(x) for x in self.position]
+        c.direction[:] = [float(x) for x in self.direction]
+        c.up[:] = [float(x) for x in self.up]
+        c.fov, c.focus_distance, c.aperture = float(self.fov), float(self.focus_distance), float(self.aperture)
+        return c
+
+
+class Texture:
+    """BRDF.h:252-426: `values` (H,W,3) float32 post-load, or a constant `multiplier`."""
+
+    def __init__(self, multiplier=(1, 1, 1), values=None):
+        self.multiplier = tuple(float(x) for x in (multiplier if np.ndim(multiplier) else (multiplier,) * 3))
+        self.values = None if values is None else f32(values)
+
+    def c_struct(self):
+        t = _abi.Tex()
+        t.mult[:] = self.multiplier
+        if self.values is not None:
+            h, w, _ = self.values.shape
+            t.texels, t.W, t.H = fptr(self.values), w, h
+        return t
+
+
+_SLOTS = [("Kd", _abi.SLOT_KD), ("Ks", _abi.SLOT_KS), ("Ne", _abi.SLOT_NE), ("transp", _abi.SLOT_TRANSP),
+          ("refr", _abi.SLOT_REFR), ("normal", _abi.SLOT_NORMAL), ("alpha", _abi.SLOT_ALPHA)]
+
+
+class Object:
+    """Geometry.h:240-672: placement, flags, BRDF pointer and per-group texture slots."""
+
+    def __init__(self):
+        self.scale = 1.0
+        self.mat_rotation = np.eye(3, dtype=np.float32)
+        self.rotation_center = None            # None -> the object's own default
+        self.max_translation = np.zeros(3, np.float32)
+        self.miroir = False
+        self.flip_normals = False
+        self.interp_normals = True
+        self.brdf = ("phong", None)            # or ("merl", table ndarray float64 of 3*90*90*180)
+        self.materials = {}                    # group -> {slot name: Texture}
+
+    def set_material(self, group=0, **slots):
+        """e.g. set_material(0, Kd=Texture((.5,.5,.5)), Ks=Texture(.2), Ne=Texture(50))"""
+        self.materials.setdefault(group, {}).update(slots)
+        return self
+
+    def _flags(self):
+        return ((_abi.OBJ_MIRROR if self.miroir else 0) | (_abi.OBJ_FLIP_NORMALS if self.flip_normals else 0)
+                | (0 if self.interp_normals else _abi.OBJ_FLAT_NORMALS))
+
+    def _xform(self):
+        x = _abi.Xform()
+        x.scale = float(self.scale)
+        x.rotation[:] = [float(v) for v in np.asarray(self.mat_rotation, np.float32).reshape(9)]
+        rc = self.rotation_center if self.rotation_center is not None else (float("nan"),) * 3
+        x.rotation_center[:] = [float(v) for v in rc]
+        x.translation[:] = [float(v) for v in self.max_translation]
+        return x
+
+
+class Sphere(Object):
+    def __init__(self, O, R, mirror=False, normal_swapped=False):
+        super().__init__()
+        self.O, self.R = np.array(O, np.float32), float(R)
+        self.miroir, self.flip_normals = mirror, normal_swapped
+        self.envmap = None                     # (H,W,3) uint8 on the dome (object 1)
+
+
+class Plane(Object):
+    def __init__(self, A, N, mirror=False):
+        super().__init__()
+        self.A, self.vecN = np.array(A, np.float32), np.array(N, np.float32)
+        self.miroir = mirror
+
+
+class TriMesh(Object):
+    """In-memory equivalent of `new TriMesh(scene, file, scaling, offset, mirror, NULL, false, center)`
+    (TriangleMesh.cpp:714-841): arrays as a file reader would have produced them."""
+
+    def __init__(self, vertices, normals, uvs, tri, scaling=1.0, offset=(0, 0, 0), mirror=False, center=True):
+        super().__init__()
+        self.vertices, self.normals = f32(vertices).reshape(-1, 3), f32(normals).reshape(-1, 3)
+        self.uvs = f32(uvs).reshape(-1, 2)
+        self.tri = np.ascontiguousarray(tri, np.int32).reshape(-1, 10)
+        self.scaling, self.offset, self.center = float(scaling), tuple(float(x) for x in offset), bool(center)
+        self.miroir = mirror
+
+
+class Scene:
+    """Geometry.h:1238-1400: object list; ids 0/1 are the light and the dome."""
+
+    def __init__(self):
+        self.objects = []
+        self.intensite_lumiere = 0.0
+        self.envmap_intensity = 1.0
+
+    def addObject(self, o):
+        self.objects.append(o)
+        return len(self.objects) - 1
+
+
+class Raytracer:
+    """Raytracer.h:25-121.  Fill the public fields, then `render_image_nopreviz()`; outputs land in
+    `imagedouble`, `sample_count`, `image` like the reference's public buffers."""
+
+    def __init__(self, lib, device=0):
+        self.lib = lib
+        self.device = device
+        self.W, self.H, self.nrays, self.nb_bounces = 1000, 800, 100, 3
+        self.sigma_filter, self.gamma = 0.5, 2.2
+        self.seed = 0
+        self.cam = Camera()
+        self.s = Scene()
+        self.imagedouble = self.sample_count = self.image = None
+        self.stats = None
+        self._ctx = None
+        self._keep = []
+
+    # ---- Raytracer::loadScene (Raytracer.cpp:1238-1274) ----
+    def loadScene(self):
+        self.W, self.H, self.nrays, self.nb_bounces = 1000, 800, 100, 3
+        self.cam = Camera((0, 0, 50), (0, 0, -1), (0, 1, 0))
+        self.cam.fov, self.cam.focus_distance, self.cam.aperture = np.float32(35 * math.pi / 180), np.float32(50), np.float32(0.1)
+        self.sigma_filter = 0.5
+        self.s = Scene()
+        slum = Sphere((10, 23, 15), 10)
+        s2 = Sphere((0, 0, 0), 1000000, normal_swapped=True)
+        plane = Plane((0, 0, 0), (0, 1, 0))
+        plane.max_translation = np.array((0, -27.3, 0), np.float32)
+        for o in (slum, s2, plane):
+            self.s.addObject(o)
+        self.s.intensite_lumiere = float(np.float32(1000000000 * 4. * math.pi / (4. * math.pi * slum.R * slum.R * math.pi)))
+        self.s.envmap_intensity = 1.0
+        self.cam.rotate(0, -22 * math.pi / 180, 1)
+        return self
+
+    # ---- scene hand-over -------------------------------------------------------------------------
+    def commit(self):
+        L = self.lib
+        self.close()
+        ctx = C.c_void_p()
+        L.check(L.create(self.device, C.byref(ctx)))
+        self._ctx = ctx
+        merl_ids = {}
+        for o in self.s.objects:
+            oid = C.c_int(-1)
+            xf = o._xform()
+            if isinstance(o, Sphere):
+                L.check(L.add_sphere(ctx, fptr(f32(o.O)), o.R, C.byref(xf), o._flags(), C.byref(oid)), ctx)
+            elif isinstance(o, Plane):
+                L.check(L.add_plane(ctx, fptr(f32(o.A)), fptr(f32(o.vecN)), C.byref(xf), o._flags(), C.byref(oid)), ctx)
+            elif isinstance(o, TriMesh):
+                m = _abi.Mesh()
+                m.vertices, m.n_vertices = fptr(o.vertices), len(o.vertices)
+                m.normals, m.n_normals = fptr(o.normals), len(o.normals)
+                m.uvs, m.n_uvs = fptr(o.uvs), len(o.uvs)
+                m.tri, m.n_tri = o.tri.ctypes.data_as(C.POINTER(C.c_int32)), len(o.tri)
+                m.scaling, m.center = o.scaling, int(o.center)
+                m.offset[:] = o.offset
+                L.check(L.add_mesh(ctx, C.byref(m), C.byref(xf), o._flags(), C.byref(oid)), ctx)
+            else:
+                raise TypeError(type(o))
+            for group, slots in sorted(o.materials.items()):
+                mat = _abi.Material()
+                for name, bit in _SLOTS:
+                    if name in slots:
+                        mat.present |= bit
+                        setattr(mat, name, slots[name].c_struct())
+                L.check(L.set_group_material(ctx, oid.value, group, C.byref(mat)), ctx)
+            if o.brdf[0] == "merl":
+                key = id(o.brdf[1])
+                if key not in merl_ids:
+                    tab = np.ascontiguousarray(o.brdf[1], np.float64).reshape(-1)
+                    assert tab.size == 3 * 90 * 90 * 180
+                    mid = C.c_int(-1)
+                    L.check(L.add_merl(ctx, tab.ctypes.data_as(C.POINTER(C.c_double)), C.byref(mid)), ctx)
+                    merl_ids[key] = mid.value
+                L.check(L.set_brdf(ctx, oid.value, _abi.BRDF_MERL, merl_ids[key]), ctx)
+        dome = self.s.objects[1]
+        if getattr(dome, "envmap", None) is not None:
+            env = np.ascontiguousarray(dome.envmap, np.uint8)
+            L.check(L.set_envmap(ctx, env.ctypes.data_as(C.POINTER(C.c_uint8)), env.shape[1], env.shape[0]), ctx)
+        L.check(L.set_light(ctx, float(self.s.intensite_lumiere), float(self.s.envmap_intensity)), ctx)
+        L.check(L.commit(ctx), ctx)
+        return self
+
+    def params(self, shard_rank=0, shard_count=1, tile_size=0):
+        p = _abi.Params()
+        p.W, p.H, p.nrays, p.nb_bounces = self.W, self.H, self.nrays, self.nb_bounces
+        p.sigma_filter, p.gamma, p.seed = self.sigma_filter, self.gamma, self.seed
+        p.shard_rank, p.shard_count, p.tile_size = shard_rank, shard_count, tile_size
+        return p
+
+    # ---- Raytracer::render_image_nopreviz (Raytracer.cpp:1565-1798) ----
+    def render_image_nopreviz(self, want_image=True):
+        L, ctx = self.lib, self._ctx
+        if ctx is None:
+            self.commit()
+            ctx = self._ctx
+        n = self.W * self.H
+        self.imagedouble = np.empty((self.H, self.W, 3), np.float32)
+        self.sample_count = np.empty((self.H, self.W), np.float32)
+        self.image = np.empty((self.H, self.W, 3), np.uint8) if want_image else None
+        st, cam, p = _abi.Stats(), self.cam.c_struct(), self.params()
+        L.check(L.render(ctx, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count),
+                         self.image.ctypes.data_as(C.POINTER(C.c_uint8)) if want_image else None, C.byref(st)), ctx)
+        self.stats = st.as_dict()
+        return self.imagedouble
+
+    def render_accum(self, d_rgbw_ptr, shard_rank=0, shard_count=1, tile_size=0):
+        """Sharded form: add this shard's sums into a caller-owned DEVICE float4 buffer."""
+        L, ctx = self.lib, self._ctx
+        st, cam, p = _abi.Stats(), self.cam.c_struct(), self.params(shard_rank, shard_count, tile_size)
+        L.check(L.render_accum(ctx, C.byref(cam), C.byref(p), C.c_void_p(d_rgbw_ptr), C.byref(st)), ctx)
+        self.stats = st.as_dict()
+        return self.stats
+
+    def resolve(self, d_rgbw_ptr, want_image=True):
+        L, ctx = self.lib, self._ctx
+        self.imagedouble = np.empty((self.H, self.W, 3), np.float32)
+        self.sample_count = np.empty((self.H, self.W), np.float32)
+        self.image = np.empty((self.H, self.W, 3), np.uint8) if want_image else None
+        L.check(L.resolve(ctx, C.c_void_p(d_rgbw_ptr), self.W, self.H, self.gamma, fptr(self.imagedouble), fptr(self.sample_count),
+                          self.image.ctypes.data_as(C.POINTER(C.c_uint8)) if want_image else None), ctx)
+        return self.imagedouble
+
+    def primary_ids(self, W=None, H=None):
+        """The picking query (mainApp.h:686-692) over the whole frame."""
+        L, ctx = self.lib, self._ctx
+        W, H = W or self.W, H or self.H
+        obj = np.empty((H, W), np.int32)
+        tri = np.empty((H, W), np.int32)
+        t = np.empty((H, W), np.float32)
+        cam = self.cam.c_struct()
+        i32 = C.POINTER(C.c_int32)
+        L.check(L.primary_ids(ctx, C.byref(cam), W, H, obj.ctypes.data_as(i32), tri.ctypes.data_as(i32), fptr(t)), ctx)
+        return obj, tri, t
+
+    def kat(self, which, inputs, W=None, H=None):
+        L, ctx = self.lib, self._ctx
+        n_in, n_out = _abi.KAT_SHAPES[which]
+        a = np.ascontiguousarray(inputs, np.float64).reshape(-1, n_in)
+        out = np.zeros((len(a), n_out), np.float64)
+        cam = self.cam.c_struct()
+        dp = C.POINTER(C.c_double)
+        L.check(L.kat(ctx, which, C.byref(cam), W or self.W, H or self.H, a.ctypes.data_as(dp), len(a), n_in,
+                      out.ctypes.data_as(dp), n_out), ctx)
+        return out
+
+    def set_option(self, option, value):
+        self.lib.check(self.lib.set_option(self._ctx, option, int(value)), self._ctx)
+
+    def scene_info(self):
+        info = _abi.SceneInfo()
+        self.lib.check(self.lib.get_scene_info(self._ctx, C.byref(info)), self._ctx)
+        return info.as_dict()
+
+    def close(self):
+        if self._ctx is not None:
+            self.lib.destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,174 @@
+"""Closed-form synthetic inputs for the benchmark configurations (BASELINE.json).
+
+No RNG anywhere, so every implementation (CUDA path, oracle/_ref, oracle/port) regenerates
+bit-identical arrays from the same parameters.  Meshes are handed over as a file reader would have
+produced them (file axes, file order); TriMesh::init semantics (axis swap, centre/normalise) are the
+receiving implementation's job.
+"""
+import math
+
+import numpy as np
+
+from .api import Plane, Raytracer, Sphere, Texture, TriMesh
+
+
+def displaced_torus(nv):
+    """4*nv^2 triangles.  Closed genus-1 surface without poles (a UV sphere's sliver pole triangles
+    produce NaN barycentrics that crash the reference's alpha lookup)."""
+    nu = 2 * nv
+    i = np.arange(nu + 1, dtype=np.float64)[None, :]
+    j = np.arange(nv + 1, dtype=np.float64)[:, None]
+    u = 2 * math.pi * i / nu
+    v = 2 * math.pi * j / nv
+    n = np.stack([np.cos(v) * np.cos(u), np.sin(v) * np.ones_like(u), np.cos(v) * np.sin(u)], -1)
+    rho = 0.4 * (1 + 0.15 * np.sin(9 * u) * np.sin(7 * v) + 0.04 * np.sin(40 * u + 3) * np.sin(33 * v))
+    ring = np.stack([np.cos(u) * np.ones_like(v), np.zeros_like(u * v), np.sin(u) * np.ones_like(v)], -1)
+    p = ring + rho[..., None] * n
+    uv = np.stack([(i / nu) * np.ones_like(j), (j / nv) * np.ones_like(i)], -1)
+    vertices = p.reshape(-1, 3).astype(np.float32)
+    normals = n.reshape(-1, 3).astype(np.float32)
+    uvs = uv.reshape(-1, 2).astype(np.float32)
+    jj, ii = np.meshgrid(np.arange(nv), np.arange(nu), indexing="ij")
+    a = (jj * (nu + 1) + ii).reshape(-1)
+    b, c = a + 1, a + nu + 1
+    d = c + 1
+    t1 = np.stack([a, b, c], -1)
+    t2 = np.stack([b, d, c], -1)
+    vt = np.stack([t1, t2], 1).reshape(-1, 3).astype(np.int32)
+    tri = np.concatenate([vt, vt, vt, np.zeros((len(vt), 1), np.int32)], 1)  # vtx, uv, normal share indices; group 0
+    return vertices, normals, uvs, tri
+
+
+def sky_envmap(W=2048, H=1024):
+    """8-bit procedural sky: 40+60*max(0,N.y), plus a 5 degree sun disc (255) at elevation 40, azimuth 30.
+    Texel (r,c) <-> direction through the reference's lookup (Geometry.h:963-977):
+    theta = 1-acos(N.y)/pi = r/(H-1), phi = (atan2(-N.z,N.x)+pi)/(2pi) = c/(W-1)."""
+    r = np.arange(H, dtype=np.float64)[:, None] / (H - 1)
+    c = np.arange(W, dtype=np.float64)[None, :] / (W - 1)
+    ny = np.cos(math.pi * (1 - r))
+    s = np.sqrt(np.maximum(0, 1 - ny * ny))
+    ang = 2 * math.pi * c - math.pi
+    nx, nz = s * np.cos(ang), -s * np.sin(ang)
+    el, az = math.radians(40), math.radians(30)
+    sun = np.array([math.cos(el) * math.cos(az), math.sin(el), math.cos(el) * math.sin(az)])
+    cosang = nx * sun[0] + ny * sun[1] + nz * sun[2]
+    val = 40 + 60 * np.maximum(0, ny) * np.ones_like(c)
+    val = np.where(cosang > math.cos(math.radians(5)), 255.0, val)
+    img = np.clip(np.floor(val), 0, 255).astype(np.uint8)
+    return np.repeat(img[..., None], 3, -1).copy()
+
+
+def merl_table(n=60.0):
+    """Synthetic MERL-format table (3 x 90 x 90 x 180 doubles): Lambert 0.2/pi + normalised Blinn-like lobe
+    0.5*(n+2)/(2pi)*cos(theta_h)^n at each bin centre, divided by the channel scale so RGB come out equal
+    (MERLBRDFRead.h:3-8; theta_h bins are non-linear: idx = 90*sqrt(theta_h/(pi/2)), MERLBRDFRead.cpp:130-142)."""
+    ih = (np.arange(90, dtype=np.float64) + 0.5) / 90
+    theta_h = ih * ih * (math.pi / 2)
+    val = 0.2 / math.pi + 0.5 * (n + 2) / (2 * math.pi) * np.cos(theta_h) ** n
+    tab = np.broadcast_to(val[:, None, None], (90, 90, 180))
+    scales = (1.0 / 1500.0, 1.15 / 1500.0, 1.66 / 1500.0)
+    return np.stack([tab / s for s in scales], 0).astype(np.float64).copy()
+
+
+def wave_normal_map(size=1024):
+    """Post-load normal map values: normalize(0.3 sin(40 pi u), 0.3 sin(40 pi v), 1)."""
+    t = (np.arange(size, dtype=np.float64) + 0.0) / (size - 1)
+    x = 0.3 * np.sin(40 * math.pi * t)[None, :] * np.ones((size, 1))
+    y = 0.3 * np.sin(40 * math.pi * t)[:, None] * np.ones((1, size))
+    z = np.ones((size, size))
+    n = np.stack([x, y, z], -1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    return n.astype(np.float32)
+
+
+def checker_alpha_map(size=1024):
+    """Alpha 0 where (floor(16u)+floor(16v)) % 8 == 0, else 1 (post-load float RGB)."""
+    t = np.arange(size, dtype=np.float64) / (size - 1)
+    k = np.minimum(np.floor(16 * t), 15).astype(np.int64)
+    a = ((k[None, :] + k[:, None]) % 8 != 0).astype(np.float32)
+    return np.repeat(a[..., None], 3, -1).copy()
+
+
+def _place_like_gui(mesh, scale=30.0, ground_y=-27.3):
+    """mainApp.cpp:2402-2410: scale, then rest the bbox on the ground plane.  After TriMesh::init with
+    center=true the mesh spans a unit max-extent box centred at 0; min.y follows from the vertex data."""
+    v = mesh.vertices.astype(np.float32)
+    # init: (x,y,z)->(-z,y,x), then (v-c)/s*scaling+offset, all float32 (TriangleMesh.cpp:742-770)
+    sw = np.stack([-v[:, 2], v[:, 1], v[:, 0]], -1)
+    lo, hi = sw.min(0), sw.max(0)
+    s = np.float32(max(hi - lo))
+    c = (lo + hi) * np.float32(0.5)
+    miny = np.float32(((sw[:, 1] - c[1]) / s * np.float32(mesh.scaling) + np.float32(mesh.offset[1])).min())
+    mesh.scale = float(scale)
+    mesh.max_translation = np.array([0, np.float32(ground_y) - miny * np.float32(scale), 0], np.float32)
+    return mesh
+
+
+def phong(Kd, Ks, Ne, **extra):
+    d = dict(Kd=Texture(Kd), Ks=Texture(Ks), Ne=Texture(Ne), alpha=Texture(1.0), refr=Texture(1.3),
+             transp=Texture(1.0), normal=Texture((0, 0, 1)))
+    d.update(extra)
+    return d
+
+
+def base(lib, W, H, spp, depth=5, device=0):
+    rt = Raytracer(lib, device).loadScene()
+    rt.W, rt.H, rt.nrays, rt.nb_bounces = W, H, spp, depth
+    return rt
+
+
+def config_C1(lib, W=512, H=512, spp=64, device=0):
+    """Default parametric scene + two Phong spheres."""
+    rt = base(lib, W, H, spp, device=device)
+    s1 = Sphere((0, -17.3, 0), 10).set_material(0, **phong((.8, .3, .3), 0.0, 1.0))
+    s2 = Sphere((-15, -20.3, 5), 7).set_material(0, **phong((.3, .8, .3), 0.3, 50.0))
+    rt.s.addObject(s1)
+    rt.s.addObject(s2)
+    return rt
+
+
+def config_C2(lib, W=1024, H=1024, spp=256, nv=500, env=(2048, 1024), device=0):
+    """1M-triangle Phong torus + 8-bit sky envmap."""
+    rt = base(lib, W, H, spp, device=device)
+    m = _place_like_gui(TriMesh(*displaced_torus(nv)))
+    m.set_material(0, **phong((.5, .5, .5), (.2, .2, .2), 50.0))
+    rt.s.addObject(m)
+    rt.s.objects[1].envmap = sky_envmap(*env)
+    return rt
+
+
+def config_C3(lib, W=1920, H=1080, spp=512, nv=791, tex=1024, device=0):
+    """2.5M-triangle fully transparent torus (refr 1.5) + normal and alpha maps."""
+    rt = base(lib, W, H, spp, device=device)
+    m = _place_like_gui(TriMesh(*displaced_torus(nv)))
+    m.set_material(0, **phong((.5, .5, .5), (.2, .2, .2), 50.0, transp=Texture(0.0), refr=Texture(1.5),
+                              normal=Texture((0, 0, 1), wave_normal_map(tex)), alpha=Texture(1.0, checker_alpha_map(tex))))
+    rt.s.addObject(m)
+    return rt
+
+
+def config_C4(lib, W=1024, H=1024, spp=1024, nv=255, device=0):
+    """260k-triangle MERL torus with depth of field."""
+    rt = base(lib, W, H, spp, device=device)
+    rt.cam.aperture, rt.cam.focus_distance = np.float32(1.0), np.float32(50)
+    m = _place_like_gui(TriMesh(*displaced_torus(nv)))
+    m.set_material(0, **phong((.5, .5, .5), 0.0, 1.0))
+    m.brdf = ("merl", merl_table())
+    rt.s.addObject(m)
+    return rt
+
+
+def config_C5(lib, W=3840, H=2160, spp=1024, nv=866, device=0):
+    """8 tori (24M triangles at nv=866) on a 4x2 grid, scale 15, Phong, no envmap."""
+    rt = base(lib, W, H, spp, device=device)
+    geo = displaced_torus(nv)
+    for k in range(8):
+        m = _place_like_gui(TriMesh(*geo), scale=15.0)
+        gx, gz = k % 4, k // 4
+        m.max_translation = m.max_translation + np.array([(gx - 1.5) * 17.5, 0, (gz - 0.5) * 17.5 - 10], np.float32)
+        m.set_material(0, **phong((.5, .5, .5), (.2, .2, .2), 50.0))
+        rt.s.addObject(m)
+    return rt
+
+
+CONFIGS = {"C1": config_C1, "C2": config_C2, "C3": config_C3, "C4": config_C4, "C5": config_C5}
