@@ -1,0 +1,269 @@
+// bvh8_build.cpp — host builder of the compressed 8-wide BVH (ptb_bvh8.h) over world-space triangles.
+//
+// Replaces TriMesh::build_bvh / build_bvh_recur (reference TriangleMesh.cpp:878-885, 1029-1130: one
+// binary BVH per mesh, 16 candidate planes on the longest centroid axis, <=4 triangles per leaf).
+// Here: one BVH over ALL meshes' triangles baked to world space (scenes are static during a render,
+// SURVEY §3.4), binned SAH on all three axes (16 bins), leaves of <=3 triangles, then a greedy
+// surface-area collapse to 8-wide nodes, octant-ordered child slots and 8-bit quantised child boxes.
+// The result is only an acceleration structure: which triangle a ray hits is decided by the triangle
+// test, so parity with the reference does not depend on reproducing its tree.
+#include "ptb_host.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+
+namespace ptb {
+
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int k = 0; k < 3; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; } }
+    void grow(const float* p) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+    void grow(const Box& b) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0.f;
+        return 2.f * (dx * dy + dx * dz + dy * dz);
+    }
+};
+
+struct BNode {   // binary node: leaf iff count > 0
+    Box box;
+    int32_t left, right;   // children (internal)
+    int32_t first, count;  // range in the index array (leaf)
+};
+
+struct Builder {
+    const float* verts;            // 9 floats per triangle
+    int64_t n;
+    std::vector<Box> pbox;
+    std::vector<float> pcen;       // 3 per prim
+    std::vector<uint32_t> idx;
+    std::vector<BNode> nodes;
+    std::atomic<int64_t> n_nodes{0};
+
+    int64_t alloc2() { return n_nodes.fetch_add(2); }
+
+    void build(int64_t node, int64_t b, int64_t e, int depth);
+};
+
+constexpr int NBINS = 16;
+constexpr float C_TRAV = 0.5f;   // binary nodes mostly vanish in the collapse
+
+void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
+    BNode& nd = nodes[node];
+    Box box, cb;
+    box.reset(); cb.reset();
+    for (int64_t i = b; i < e; i++) { box.grow(pbox[idx[i]]); cb.grow(&pcen[3 * (size_t)idx[i]]); }
+    nd.box = box;
+    const int64_t cnt = e - b;
+    auto make_leaf = [&]() { nd.left = nd.right = -1; nd.first = (int32_t)b; nd.count = (int32_t)cnt; };
+    if (cnt == 1) { make_leaf(); return; }
+
+    // binned SAH over the three axes
+    float best_cost = INFINITY;
+    int best_axis = -1, best_bin = -1;
+    for (int ax = 0; ax < 3; ax++) {
+        const float lo = cb.lo[ax], ext = cb.hi[ax] - cb.lo[ax];
+        if (!(ext > 0)) continue;
+        Box bb[NBINS]; int64_t bc[NBINS];
+        for (int k = 0; k < NBINS; k++) { bb[k].reset(); bc[k] = 0; }
+        const float scale = NBINS / ext;
+        for (int64_t i = b; i < e; i++) {
+            const uint32_t p = idx[i];
+            int k = (int)((pcen[3 * (size_t)p + ax] - lo) * scale);
+            k = k < 0 ? 0 : (k >= NBINS ? NBINS - 1 : k);
+            bb[k].grow(pbox[p]); bc[k]++;
+        }
+        float ra[NBINS]; int64_t rc[NBINS];
+        Box acc; acc.reset(); int64_t c = 0;
+        for (int k = NBINS - 1; k > 0; k--) { acc.grow(bb[k]); c += bc[k]; ra[k] = acc.area(); rc[k] = c; }
+        acc.reset(); c = 0;
+        for (int k = 0; k < NBINS - 1; k++) {
+            acc.grow(bb[k]); c += bc[k];
+            if (c == 0 || rc[k + 1] == 0) continue;
+            const float cost = acc.area() * (float)c + ra[k + 1] * (float)rc[k + 1];
+            if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = k; }
+        }
+    }
+    int64_t mid;
+    if (best_axis < 0) {
+        if (cnt <= 3) { make_leaf(); return; }
+        mid = b + cnt / 2;  // coincident centroids: split by index
+    } else {
+        if (cnt <= 3) {
+            const float A = box.area();
+            if (!(C_TRAV * A + best_cost < (float)cnt * A)) { make_leaf(); return; }
+        }
+        const float lo = cb.lo[best_axis], scale = NBINS / (cb.hi[best_axis] - cb.lo[best_axis]);
+        auto it = std::partition(idx.begin() + b, idx.begin() + e, [&](uint32_t p) {
+            int k = (int)((pcen[3 * (size_t)p + best_axis] - lo) * scale);
+            k = k < 0 ? 0 : (k >= NBINS ? NBINS - 1 : k);
+            return k <= best_bin;
+        });
+        mid = it - idx.begin();
+        if (mid == b || mid == e) mid = b + cnt / 2;
+    }
+    const int64_t c0 = alloc2();
+    nd.left = (int32_t)c0; nd.right = (int32_t)(c0 + 1); nd.first = 0; nd.count = 0;
+    if (cnt > 4096 && depth < 24) {
+#pragma omp task default(shared) firstprivate(c0, b, mid, depth)
+        build(c0, b, mid, depth + 1);
+#pragma omp task default(shared) firstprivate(c0, mid, e, depth)
+        build(c0 + 1, mid, e, depth + 1);
+#pragma omp taskwait
+    } else {
+        build(c0, b, mid, depth + 1);
+        build(c0 + 1, mid, e, depth + 1);
+    }
+}
+
+inline uint8_t exponent_byte(float extent) {
+    // smallest e with extent <= 255 * 2^e (a little slack keeps the rounded-up far planes inside 255)
+    int e;
+    if (!(extent > 0)) e = -100;
+    else {
+        e = (int)std::ceil(std::log2((double)extent * 1.0001 / 255.0));
+        if (e < -100) e = -100;
+        if (e > 100) e = 100;
+    }
+    return (uint8_t)(e + 127);
+}
+
+}  // namespace
+
+void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_nodes, std::vector<uint32_t>& leaf_order, Bvh8Stats& stats) {
+    out_nodes.clear(); leaf_order.clear();
+    stats = Bvh8Stats();
+    if (n_tri <= 0) return;
+    Builder B;
+    B.verts = verts9; B.n = n_tri;
+    B.pbox.resize(n_tri); B.pcen.resize(3 * (size_t)n_tri); B.idx.resize(n_tri);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_tri; i++) {
+        Box bx; bx.reset();
+        const float* v = verts9 + 9 * (size_t)i;
+        bx.grow(v); bx.grow(v + 3); bx.grow(v + 6);
+        B.pbox[i] = bx;
+        for (int k = 0; k < 3; k++) B.pcen[3 * (size_t)i + k] = 0.5f * (bx.lo[k] + bx.hi[k]);
+        B.idx[i] = (uint32_t)i;
+    }
+    B.nodes.resize(2 * (size_t)n_tri + 2);
+    B.n_nodes = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        B.build(0, 0, n_tri, 0);
+    }
+
+    // ---- collapse to 8-wide, breadth first so that a node's internal children are contiguous ----
+    struct Work { int32_t bnode; uint32_t wide; int depth; };
+    std::vector<Work> queue;
+    out_nodes.reserve((size_t)n_tri / 3 + 16);
+    leaf_order.reserve(n_tri);
+    out_nodes.emplace_back();
+    queue.push_back({0, 0, 1});
+    size_t head = 0;
+    while (head < queue.size()) {
+        const Work w = queue[head++];
+        stats.depth = std::max(stats.depth, w.depth);
+        int32_t ch[8]; int nc = 0;
+        const BNode& root = B.nodes[w.bnode];
+        if (root.count > 0) ch[nc++] = w.bnode;           // a leaf root: one leaf child
+        else { ch[nc++] = root.left; ch[nc++] = root.right; }
+        while (nc < 8) {
+            int best = -1; float best_area = -1.f;
+            for (int i = 0; i < nc; i++) {
+                const BNode& c = B.nodes[ch[i]];
+                if (c.count > 0) continue;
+                const float a = c.box.area();
+                if (a > best_area) { best_area = a; best = i; }
+            }
+            if (best < 0) break;
+            const BNode& c = B.nodes[ch[best]];
+            ch[best] = c.left; ch[nc++] = c.right;
+        }
+        // node box
+        Box nb; nb.reset();
+        for (int i = 0; i < nc; i++) nb.grow(B.nodes[ch[i]].box);
+        // ---- assign children to slots: slot s prefers the child lying towards corner s (bit2=+x, bit1=+y, bit0=+z)
+        float ncx[3]; for (int k = 0; k < 3; k++) ncx[k] = 0.5f * (nb.lo[k] + nb.hi[k]);
+        float cost[8][8];
+        for (int i = 0; i < nc; i++) {
+            const Box& cbx = B.nodes[ch[i]].box;
+            float off[3]; for (int k = 0; k < 3; k++) off[k] = 0.5f * (cbx.lo[k] + cbx.hi[k]) - ncx[k];
+            for (int s = 0; s < 8; s++)
+                cost[i][s] = ((s & 4) ? off[0] : -off[0]) + ((s & 2) ? off[1] : -off[1]) + ((s & 1) ? off[2] : -off[2]);
+        }
+        int slot_child[8]; for (int s = 0; s < 8; s++) slot_child[s] = -1;
+        bool child_done[8] = {false, false, false, false, false, false, false, false};
+        for (int it = 0; it < nc; it++) {
+            float bestc = -INFINITY; int bi = -1, bs = -1;
+            for (int i = 0; i < nc; i++) {
+                if (child_done[i]) continue;
+                for (int s = 0; s < 8; s++) {
+                    if (slot_child[s] >= 0) continue;
+                    if (cost[i][s] > bestc) { bestc = cost[i][s]; bi = i; bs = s; }
+                }
+            }
+            slot_child[bs] = bi; child_done[bi] = true;
+        }
+        // ---- emit
+        Node8 nd;
+        memset(&nd, 0, sizeof(nd));
+        nd.ex = exponent_byte(nb.hi[0] - nb.lo[0]);
+        nd.ey = exponent_byte(nb.hi[1] - nb.lo[1]);
+        nd.ez = exponent_byte(nb.hi[2] - nb.lo[2]);
+        const float cell[3] = {std::ldexp(1.f, (int)nd.ex - 127), std::ldexp(1.f, (int)nd.ey - 127), std::ldexp(1.f, (int)nd.ez - 127)};
+        // conservative slack: a thousandth of a cell plus a few ulps of the coordinate
+        float eps[3], p[3];
+        for (int k = 0; k < 3; k++) {
+            eps[k] = cell[k] * 1e-3f + 4e-7f * std::max(std::fabs(nb.lo[k]), std::fabs(nb.hi[k]));
+            p[k] = nb.lo[k] - eps[k];
+        }
+        nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
+        nd.child_base = (uint32_t)out_nodes.size();
+        nd.tri_base = (uint32_t)leaf_order.size();
+        uint32_t n_internal = 0, tri_off = 0;
+        for (int s = 0; s < 8; s++) {
+            const int i = slot_child[s];
+            if (i < 0) continue;
+            const BNode& c = B.nodes[ch[i]];
+            uint8_t* ql[3] = {nd.qlox, nd.qloy, nd.qloz};
+            uint8_t* qh[3] = {nd.qhix, nd.qhiy, nd.qhiz};
+            for (int k = 0; k < 3; k++) {
+                float lo = std::floor((c.box.lo[k] - eps[k] - p[k]) / cell[k]);
+                float hi = std::ceil((c.box.hi[k] + eps[k] - p[k]) / cell[k]);
+                lo = std::min(std::max(lo, 0.f), 255.f);
+                hi = std::min(std::max(hi, 0.f), 255.f);
+                ql[k][s] = (uint8_t)lo; qh[k][s] = (uint8_t)hi;
+            }
+            if (c.count > 0) {
+                const uint32_t unary = (c.count == 1) ? 1u : (c.count == 2 ? 3u : 7u);
+                nd.meta[s] = (uint8_t)((unary << 5) | tri_off);
+                for (int t = 0; t < c.count; t++) leaf_order.push_back(B.idx[c.first + t]);
+                tri_off += (uint32_t)c.count;
+                stats.leaves++;
+            } else {
+                nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+                nd.imask |= (uint8_t)(1u << s);
+                n_internal++;
+            }
+        }
+        // allocate the internal children contiguously, in slot order
+        for (int s = 0; s < 8; s++) {
+            const int i = slot_child[s];
+            if (i < 0 || B.nodes[ch[i]].count > 0) continue;
+            queue.push_back({ch[i], (uint32_t)out_nodes.size(), w.depth + 1});
+            out_nodes.emplace_back();
+        }
+        out_nodes[w.wide] = nd;
+    }
+    stats.n_nodes = (int64_t)out_nodes.size();
+    stats.n_binary_nodes = B.n_nodes.load();
+}
+
+}  // namespace ptb

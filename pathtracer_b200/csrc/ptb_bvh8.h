@@ -1,0 +1,227 @@
+// ptb_bvh8.h — compressed 8-wide BVH: node layout and ray traversal (closest hit and any hit).
+//
+// Replaces the reference's binary BVH (`BVHNodesT`, TriangleMesh.h:6-28; traversal
+// TriangleMesh.cpp:1133-1319; slab tests Geometry.h:114-204; `Triangle::intersection`
+// TriangleMesh.h:82-104).  Layout after Ylitie, Karras, Laine 2017 ("Efficient Incoherent Ray
+// Traversal on GPUs Through Compressed Wide BVHs"): one 80-byte node = 5 x 16-byte loads holds 8
+// child boxes quantised to 8 bits on a per-node power-of-two grid.
+//
+//   bytes  0-11  p        float3 grid origin (node box min)
+//         12-14  e        int8 exponents: cell size 2^e per axis
+//            15  imask    bit s set <=> slot s holds an internal node
+//         16-19  child_base   index of the first internal child (children are contiguous, slot order)
+//         20-23  tri_base     index of the node's first triangle (leaf children contiguous)
+//         24-31  meta[8]  empty: 0; internal: (1<<5) | (24+slot); leaf: (unary count in top 3 bits) | first-triangle offset
+//         32-79  qlo_x[8] qlo_y[8] qlo_z[8] qhi_x[8] qhi_y[8] qhi_z[8]
+//
+// Triangles are stored in leaf order as 3 x float4 = 48 bytes {v0, e1 = v1-v0, e2 = v2-v0}; the .w
+// lanes carry flags.  Semantics mirrored from the reference: two-sided, barycentrics >= 0 inclusive,
+// t >= 0 accepted, strictly nearer than the current best wins (TriangleMesh.h:82-104,
+// TriangleMesh.cpp:1196-1209); alpha-mapped hits are rejected inside traversal (1198-1205).
+#pragma once
+#include "ptb_core.h"
+
+namespace ptb {
+
+struct alignas(16) Node8 {
+    float px, py, pz;
+    uint8_t ex, ey, ez, imask;
+    uint32_t child_base, tri_base;
+    uint8_t meta[8];
+    uint8_t qlox[8], qloy[8], qloz[8], qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+
+#define PTB_TRI_FLAG_ALPHA 1u  /* tri.w0 bit: this triangle's group has an alpha map that can reject */
+
+struct Hit {
+    float t, b1, b2;   // distance, barycentric of v1 (beta), of v2 (gamma)
+    int32_t prim;      // triangle index in leaf order, -1 none
+};
+
+PTB_HD uint32_t highest_bit(uint32_t v) {  // index of the highest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+    return 31u - (uint32_t)__clz((int)v);
+#else
+    return 31u - (uint32_t)__builtin_clz(v);
+#endif
+}
+PTB_HD uint32_t popcount32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+
+#if defined(__CUDA_ARCH__)
+#define PTB_LDG_F4(p) __ldg(reinterpret_cast<const float4*>(p))
+#else
+struct float4_host { float x, y, z, w; };
+#define PTB_LDG_F4(p) (*reinterpret_cast<const ptb::float4_host*>(p))
+#endif
+
+// Per-ray constants of the slab test in quantised space.
+struct RayPrep {
+    V3 o, d, idir;
+    uint32_t oct_inv4;  // (7 - octant) replicated in 4 bytes; octant bit set <=> direction component negative
+};
+PTB_HD RayPrep ray_prep(V3 o, V3 d) {
+    RayPrep r;
+    r.o = o; r.d = d;
+    const float eps = 1e-30f;
+    r.idir.x = 1.f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
+    r.idir.y = 1.f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
+    r.idir.z = 1.f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+    r.oct_inv4 = ((d.x < 0 ? 0u : 0x04040404u) | (d.y < 0 ? 0u : 0x02020202u) | (d.z < 0 ? 0u : 0x01010101u));
+    return r;
+}
+
+// Alpha callback data: uv + group + object of a triangle, and the material table (see ptb_scene.h).
+struct AlphaCtx;
+PTB_HD bool alpha_rejects(const AlphaCtx* ctx, int prim, float b1, float b2);
+
+// Tests the 8 children of `n` against the ray; returns the hit mask in traversal-priority order:
+// bits 31..24 internal children (bit 24 + (slot ^ (7-oct))), bits 23..0 triangles of hit leaves.
+PTB_HD uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4& n3, const F4& n4, const RayPrep& r, float tmax) {
+    const uint32_t e_imask = f2u(n0.w);
+    const float sx = u2f(((e_imask >> 0) & 0xffu) << 23), sy = u2f(((e_imask >> 8) & 0xffu) << 23), sz = u2f(((e_imask >> 16) & 0xffu) << 23);
+    const float adx = sx * r.idir.x, ady = sy * r.idir.y, adz = sz * r.idir.z;
+    const float box = (n0.x - r.o.x) * r.idir.x, boy = (n0.y - r.o.y) * r.idir.y, boz = (n0.z - r.o.z) * r.idir.z;
+    const uint32_t meta_lo = f2u(n1.z), meta_hi = f2u(n1.w);
+    const uint32_t qlox_lo = f2u(n2.x), qlox_hi = f2u(n2.y), qloy_lo = f2u(n2.z), qloy_hi = f2u(n2.w);
+    const uint32_t qloz_lo = f2u(n3.x), qloz_hi = f2u(n3.y), qhix_lo = f2u(n3.z), qhix_hi = f2u(n3.w);
+    const uint32_t qhiy_lo = f2u(n4.x), qhiy_hi = f2u(n4.y), qhiz_lo = f2u(n4.z), qhiz_hi = f2u(n4.w);
+    const bool negx = r.d.x < 0, negy = r.d.y < 0, negz = r.d.z < 0;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t meta4 = half ? meta_hi : meta_lo;
+        const uint32_t lox = half ? qlox_hi : qlox_lo, loy = half ? qloy_hi : qloy_lo, loz = half ? qloz_hi : qloz_lo;
+        const uint32_t hix = half ? qhix_hi : qhix_lo, hiy = half ? qhiy_hi : qhiy_lo, hiz = half ? qhiz_hi : qhiz_lo;
+        // entry plane is lo for positive direction, hi for negative
+        const uint32_t nx = negx ? hix : lox, fx = negx ? lox : hix;
+        const uint32_t ny = negy ? hiy : loy, fy = negy ? loy : hiy;
+        const uint32_t nz = negz ? hiz : loz, fz = negz ? loz : hiz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t sh = 8u * j;
+            const float tnx = (float)((nx >> sh) & 0xffu) * adx + box;
+            const float tny = (float)((ny >> sh) & 0xffu) * ady + boy;
+            const float tnz = (float)((nz >> sh) & 0xffu) * adz + boz;
+            const float tfx = (float)((fx >> sh) & 0xffu) * adx + box;
+            const float tfy = (float)((fy >> sh) & 0xffu) * ady + boy;
+            const float tfz = (float)((fz >> sh) & 0xffu) * adz + boz;
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+            if (tn <= tf) {
+                const uint32_t meta = (meta4 >> sh) & 0xffu;
+                // internal children carry 0b001 in the top bits and 24+slot below: reorder them by octant
+                const uint32_t is_inner = ((meta & 0x18u) == 0x18u) ? 0xffu : 0u;
+                const uint32_t bit_index = (meta ^ (r.oct_inv4 & is_inner)) & 0x1fu;
+                hitmask |= (meta >> 5) << bit_index;
+            }
+        }
+    }
+    return hitmask;
+}
+
+// Möller–Trumbore on {v0,e1,e2}; two-sided; accepts b1,b2 >= 0, b1+b2 <= 1, 0 <= t < tbest.
+PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, float tbest, float& t, float& b1, float& b2) {
+    const V3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
+    const V3 pvec = cross(r.d, e2);
+    const float det = dot(e1, pvec);
+    const float inv = 1.f / det;
+    const V3 tvec = r.o - v0;
+    const float u = dot(tvec, pvec) * inv;
+    const V3 qvec = cross(tvec, e1);
+    const float v = dot(r.d, qvec) * inv;
+    const float tt = dot(e2, qvec) * inv;
+    // written so that NaN (degenerate triangle, det == 0) fails every test
+    if (!(u >= 0.f) || !(v >= 0.f) || !(1.f - u - v >= 0.f) || !(tt >= 0.f) || !(tt < tbest)) return false;
+    t = tt; b1 = u; b2 = v;
+    return true;
+}
+
+#define PTB_STACK 32
+
+struct TraverseCounters {
+    uint32_t nodes, tris;
+};
+
+// ANY_HIT: returns at the first accepted triangle with t < tmax (Scene::intersection_shadow semantics:
+// the caller passes tmax = 0.999*dist_light, TriangleMesh.cpp:1239-1319 + Geometry.cpp:735).
+template <bool ANY_HIT, bool COUNT>
+PTB_HD bool traverse(const F4* __restrict__ nodes, const F4* __restrict__ tris, const AlphaCtx* actx, V3 o, V3 d, float tmax,
+                     Hit& hit, TraverseCounters* cnt) {
+    const RayPrep r = ray_prep(o, d);
+    U2 stack[PTB_STACK];
+    int sp = 0;
+    U2 ngroup, tgroup;
+    // the root enters as a one-child group: bit 31 set, no imask bits -> relative index 0
+    ngroup.x = 0; ngroup.y = 0x80000000u;
+    bool found = false;
+    float tbest = tmax;
+    for (;;) {
+        // invariant: ngroup has at least one pending internal child (a bit in 31..24)
+        {
+            const uint32_t hits_imask = ngroup.y;
+            const uint32_t child_bit = highest_bit(hits_imask);
+            const uint32_t child_base = ngroup.x;
+            ngroup.y &= ~(1u << child_bit);
+            if (ngroup.y > 0x00ffffffu) {
+                if (sp < PTB_STACK) stack[sp++] = ngroup;
+            }
+            const uint32_t slot = (child_bit - 24u) ^ (r.oct_inv4 & 0xffu);
+            const uint32_t rel = popcount32(hits_imask & ~(0xffffffffu << slot));
+            const uint32_t child_index = child_base + rel;
+            const F4* np = nodes + (size_t)child_index * 5;
+            F4 n0, n1, n2, n3, n4;
+            {
+                auto l0 = PTB_LDG_F4(np + 0); auto l1 = PTB_LDG_F4(np + 1); auto l2 = PTB_LDG_F4(np + 2);
+                auto l3 = PTB_LDG_F4(np + 3); auto l4 = PTB_LDG_F4(np + 4);
+                n0.x = l0.x; n0.y = l0.y; n0.z = l0.z; n0.w = l0.w;
+                n1.x = l1.x; n1.y = l1.y; n1.z = l1.z; n1.w = l1.w;
+                n2.x = l2.x; n2.y = l2.y; n2.z = l2.z; n2.w = l2.w;
+                n3.x = l3.x; n3.y = l3.y; n3.z = l3.z; n3.w = l3.w;
+                n4.x = l4.x; n4.y = l4.y; n4.z = l4.z; n4.w = l4.w;
+            }
+            if (COUNT) cnt->nodes++;
+            const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, tbest);
+            const uint32_t imask = f2u(n0.w) >> 24;
+            ngroup.x = f2u(n1.x);
+            tgroup.x = f2u(n1.y);
+            ngroup.y = (hm & 0xff000000u) | imask;
+            tgroup.y = hm & 0x00ffffffu;
+        }
+        while (tgroup.y != 0) {
+            const uint32_t ti = highest_bit(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            const uint32_t prim = tgroup.x + ti;
+            const F4* tp = tris + (size_t)prim * 3;
+            F4 a, b, c;
+            {
+                auto l0 = PTB_LDG_F4(tp + 0); auto l1 = PTB_LDG_F4(tp + 1); auto l2 = PTB_LDG_F4(tp + 2);
+                a.x = l0.x; a.y = l0.y; a.z = l0.z; a.w = l0.w;
+                b.x = l1.x; b.y = l1.y; b.z = l1.z; b.w = l1.w;
+                c.x = l2.x; c.y = l2.y; c.z = l2.z; c.w = l2.w;
+            }
+            if (COUNT) cnt->tris++;
+            float t, b1, b2;
+            if (tri_test(a, b, c, r, tbest, t, b1, b2)) {
+                if ((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(actx, (int)prim, b1, b2)) continue;
+                tbest = t;
+                hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = (int32_t)prim;
+                found = true;
+                if (ANY_HIT) return true;
+            }
+        }
+        if (ngroup.y <= 0x00ffffffu) {
+            if (sp > 0) ngroup = stack[--sp];
+            else break;
+        }
+    }
+    return found;
+}
+
+}  // namespace ptb

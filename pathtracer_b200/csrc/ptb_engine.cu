@@ -1,0 +1,706 @@
+// ptb_engine.cu — CUDA kernels (sm_100a) of the wavefront radiance loop, their launch schedule, and the
+// C-ABI of include/ptb200.h.
+//
+// One render = passes over the shard's pixels; one pass keeps `pool` paths in flight in HBM (SoA, ptb_scene.h
+// PoolDev) and runs, on one stream with no host synchronisation:
+//     k_raygen -> [ k_extend -> k_shade -> k_shadow ] x nb_bounces -> k_splat
+// Queues are index lists compacted with warp ballots + one atomic per warp (k_shade); every kernel reads
+// its element count from device memory, so the host never waits for a count.
+// There is no CPU implementation behind this ABI: a missing device or a failed launch is an error code.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ptb_host.h"
+
+using namespace ptb;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return PTB_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+// counters layout (uint32): [2*b] = paths queued for bounce b, [2*b+1] = shadow rays of bounce b
+#define PTB_MAX_BOUNCES 64
+// 64-bit totals: 0 closest rays, 1 shadow rays, 2 node visits, 3 triangle tests
+#define PTB_N_TOTALS 4
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(256) k_rpp(float* rpp, int n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float x, y;
+    random_per_pixel((uint32_t)p, x, y);
+    rpp[2 * p] = x;
+    rpp[2 * p + 1] = y;
+}
+
+__global__ void __launch_bounds__(256) k_raygen(FrameDev f, PoolDev p, int n_paths) {
+    const int path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= n_paths) return;
+    raygen_one(f, p, path);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
+                                                int n_static, unsigned long long* totals) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = count ? (int)*count : n_static;
+    TraverseCounters tc;
+    tc.nodes = 0; tc.tris = 0;
+    if (tid < n) {
+        const int path = queue ? (int)queue[tid] : tid;
+        if (p.pixel[path] != 0xffffffffu) extend_one<COUNT>(sc, p, path, &tc);
+        else { F4 q; q.x = INFINITY; q.y = 0; q.z = 0; q.w = u2f((uint32_t)PTB_HIT_MISS); p.hit[path] = q; }
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) { tc.nodes += __shfl_down_sync(0xffffffffu, tc.nodes, o); tc.tris += __shfl_down_sync(0xffffffffu, tc.tris, o); }
+        if ((threadIdx.x & 31) == 0 && (tc.nodes | tc.tris)) { atomicAdd(&totals[2], (unsigned long long)tc.nodes); atomicAdd(&totals[3], (unsigned long long)tc.tris); }
+    }
+}
+
+// warp-aggregated append: one atomic per warp, lanes take consecutive slots
+__device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool want) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0) return 0;
+    const uint32_t lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(128) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
+                                               const uint32_t* __restrict__ count, int n_static, uint32_t* __restrict__ next_queue,
+                                               uint32_t* next_count, uint32_t* shadow_count) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = count ? (int)*count : n_static;
+    ShadeOut out;
+    out.cont = false; out.shadow = false;
+    int path = 0;
+    if (tid < n) {
+        path = queue ? (int)queue[tid] : tid;
+        shade_one(sc, f, p, path, out);
+    }
+    const uint32_t qi = warp_push(next_count, out.cont);
+    if (out.cont) next_queue[qi] = (uint32_t)path;
+    const uint32_t si = warp_push(shadow_count, out.shadow);
+    if (out.shadow) { p.sh_o[si] = out.sh_o; p.sh_d[si] = out.sh_d; p.sh_c[si] = out.sh_c; }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow(SceneDev sc, PoolDev p, const uint32_t* __restrict__ count, unsigned long long* totals) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (int)*count;
+    TraverseCounters tc;
+    tc.nodes = 0; tc.tris = 0;
+    if (tid < n) shadow_one<COUNT>(sc, p, tid, &tc);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) { tc.nodes += __shfl_down_sync(0xffffffffu, tc.nodes, o); tc.tris += __shfl_down_sync(0xffffffffu, tc.tris, o); }
+        if ((threadIdx.x & 31) == 0 && (tc.nodes | tc.tris)) { atomicAdd(&totals[2], (unsigned long long)tc.nodes); atomicAdd(&totals[3], (unsigned long long)tc.tris); }
+    }
+}
+
+struct RedAddV4 {
+    __device__ __forceinline__ void operator()(F4* addr, const F4& v) const {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+};
+
+__global__ void __launch_bounds__(128) k_splat(FrameDev f, PoolDev p, F4* accum) {
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ps >= f.n_pixel_slots) return;
+    splat_pixel(f, p, ps, accum, RedAddV4());
+}
+
+__global__ void k_totals(const uint32_t* counters, int nb, unsigned long long valid_paths, unsigned long long* totals) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long closest = valid_paths, shadow = 0;
+    for (int b = 0; b < nb; b++) { if (b > 0) closest += counters[2 * b]; shadow += counters[2 * b + 1]; }
+    totals[0] += closest;
+    totals[1] += shadow;
+}
+
+__global__ void __launch_bounds__(256) k_resolve(const F4* accum, size_t n, float gamma, float* imagedouble, float* sample_count, uint8_t* image) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    resolve_pixel(accum, idx, gamma, imagedouble, sample_count, image);
+}
+
+__global__ void __launch_bounds__(128) k_primary(SceneDev sc, CameraDev cam, int W, int H, int32_t* obj_id, int32_t* tri_id, float* tout) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= W * H) return;
+    const int i = idx / W, j = idx - i * W;
+    V3 o, d;
+    camera_ray(cam, i, j, 0.f, 0.f, 0.f, 0.f, o, d);
+    Hit h;
+    int32_t id;
+    extend_ray<false>(sc, o, d, h, id, nullptr);
+    int32_t oid = -1, tid = -1;
+    if (id >= 0) { oid = sc.tri_uv[id].object_has_uv & 0x7fffffff; tid = sc.tri_shade[id].orig; }
+    else if (id != PTB_HIT_MISS) oid = -2 - id;
+    if (obj_id) obj_id[idx] = oid;
+    if (tri_id) tri_id[idx] = tid;
+    if (tout) tout[idx] = (id == PTB_HIT_MISS) ? -1.f : h.t;
+}
+
+// tile pack / unpack-add with apron (multi-GPU gather).  One thread per packed texel.
+__global__ void __launch_bounds__(256) k_shard_pack(const F4* rgbw, F4* packed, int W, int H, int tile, int apron, int tiles_x, int n_tiles_total,
+                                                    int rank, int count, long long n_packed, int unpack) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_packed) return;
+    const int side = tile + 2 * apron;
+    const long long per = (long long)side * side;
+    const int lt = (int)(idx / per);
+    const int r = (int)(idx - (long long)lt * per);
+    const int tile_id = rank + lt * count;
+    if (tile_id >= n_tiles_total) return;
+    const int ty = tile_id / tiles_x, tx = tile_id - ty * tiles_x;
+    const int i = ty * tile - apron + r / side, j = tx * tile - apron + r % side;
+    const bool inside = i >= 0 && i < H && j >= 0 && j < W;
+    if (!unpack) {
+        F4 z; z.x = z.y = z.z = z.w = 0;
+        packed[idx] = inside ? rgbw[(size_t)(H - 1 - i) * W + j] : z;
+    } else if (inside) {
+        const F4 v = packed[idx];
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) RedAddV4()(const_cast<F4*>(rgbw) + (size_t)(H - 1 - i) * W + j, v);
+    }
+}
+
+__global__ void k_kat(int which, SceneDev sc, CameraDev cam, FilterDev filt, int W, int H, const double* in, int n, int is, double* out, int os) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* a = in + (size_t)k * is;
+    double* o = out + (size_t)k * os;
+    switch (which) {
+    case PTB_KAT_PCG32: { Pcg32 e = pcg32_seed((uint64_t)a[0], (uint64_t)a[1]); for (int q = 0; q < 4; q++) o[q] = (double)pcg32_next(e); } break;
+    case PTB_KAT_LATTICE: { float x, y; extensible_lattice_2d((uint32_t)a[0], x, y); o[0] = x; o[1] = y; } break;
+    case PTB_KAT_CAMERA: { V3 ro, rd; camera_ray(cam, (int)a[0], (int)a[1], (float)a[2], (float)a[3], (float)a[4], (float)a[5], ro, rd);
+        o[0] = ro.x; o[1] = ro.y; o[2] = ro.z; o[3] = rd.x; o[4] = rd.y; o[5] = rd.z; } break;
+    case PTB_KAT_RANDOM_COS: { V3 v = random_cos(v3((float)a[0], (float)a[1], (float)a[2]), (float)a[3], (float)a[4]); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+    case PTB_KAT_RANDOM_PHONG: { V3 v = random_phong(v3((float)a[0], (float)a[1], (float)a[2]), (float)a[3], (float)a[4], (float)a[5]); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+    case PTB_KAT_PHONG_EVAL: { V3 v = phong_eval(v3((float)a[0], (float)a[1], (float)a[2]), v3((float)a[3], (float)a[4], (float)a[5]), v3((float)a[6], (float)a[7], (float)a[8]),
+                                               v3((float)a[9], (float)a[10], (float)a[11]), v3((float)a[12], (float)a[13], (float)a[14]), v3((float)a[15], (float)a[16], (float)a[17]));
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+    case PTB_KAT_MERL_EVAL: { V3 v = merl_eval(sc.merl, v3((float)a[0], (float)a[1], (float)a[2]), v3((float)a[3], (float)a[4], (float)a[5]), v3((float)a[6], (float)a[7], (float)a[8]));
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+    case PTB_KAT_FAST_EXP: o[0] = fast_exp(a[0]); break;
+    case PTB_KAT_FAST_NORMALIZE: { V3 v = fast_normalize(v3((float)a[0], (float)a[1], (float)a[2])); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+    case PTB_KAT_RANDOM_PER_PIXEL: { float x, y; random_per_pixel((uint32_t)a[0], x, y); o[0] = x; o[1] = y; } break;
+    case PTB_KAT_FILTER_RATIO: { int b0, b1, b2, b3; o[0] = filter_ratio(filt, (int)a[0], (int)a[1], W, H, b0, b1, b2, b3); } break;
+    default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ context
+struct ptb_ctx {
+    int device = 0;
+    std::string err;
+    HostScene host;
+    FlatScene flat;
+    bool committed = false;
+    SceneDev sc;
+    std::vector<void*> scene_allocs;
+    double ms_upload = 0;
+    int64_t bytes_nodes = 0, bytes_tris = 0, bytes_attr = 0, bytes_tex = 0;
+    // path pool
+    int64_t pool_paths = (int64_t)1 << 24, pool_cap = 0;
+    PoolDev pool;
+    uint32_t* d_queue[2] = {nullptr, nullptr};
+    uint32_t* d_counters = nullptr;
+    unsigned long long* d_totals = nullptr;
+    float* d_rpp = nullptr;
+    int64_t rpp_n = 0;
+    F4* d_accum = nullptr;
+    int64_t accum_n = 0;
+    float* d_out_img = nullptr; float* d_out_cnt = nullptr; uint8_t* d_out_u8 = nullptr;
+    int64_t out_n = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool count_traversal = false;
+};
+
+static std::string g_create_err;
+
+static void free_scene(ptb_ctx* c) {
+    for (void* p : c->scene_allocs) cudaFree(p);
+    c->scene_allocs.clear();
+}
+static void free_pool(ptb_ctx* c) {
+    void* ptrs[] = {c->pool.ray_o, c->pool.ray_d, c->pool.weight, c->pool.radiance, c->pool.hit, c->pool.rng, c->pool.pixel,
+                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1]};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    memset(&c->pool, 0, sizeof(c->pool));
+    c->d_queue[0] = c->d_queue[1] = nullptr;
+    c->pool_cap = 0;
+}
+
+template <class T>
+static int upload(ptb_ctx* c, const T* host, size_t n, const T** dev) {
+    void* d = nullptr;
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CK(cudaMalloc(&d, bytes));
+    c->scene_allocs.push_back(d);
+    if (n) CK(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *dev = (const T*)d;
+    return PTB_OK;
+}
+
+static int ensure_pool(ptb_ctx* c, int64_t paths) {
+    if (paths <= c->pool_cap) return PTB_OK;
+    free_pool(c);
+    const size_t n = (size_t)paths;
+    CK(cudaMalloc((void**)&c->pool.ray_o, n * sizeof(F4)));
+    CK(cudaMalloc((void**)&c->pool.ray_d, n * sizeof(F4)));
+    CK(cudaMalloc((void**)&c->pool.weight, n * sizeof(F4)));
+    CK(cudaMalloc((void**)&c->pool.radiance, n * sizeof(F4)));
+    CK(cudaMalloc((void**)&c->pool.hit, n * sizeof(F4)));
+    CK(cudaMalloc((void**)&c->pool.rng, n * sizeof(uint64_t)));
+    CK(cudaMalloc((void**)&c->pool.pixel, n * sizeof(uint32_t)));
+    CK(cudaMalloc((void**)&c->pool.sh_o, n * sizeof(F4)));
+    CK(cudaMalloc((void**)&c->pool.sh_d, n * sizeof(F4)));
+    CK(cudaMalloc((void**)&c->pool.sh_c, n * sizeof(F4)));
+    CK(cudaMalloc((void**)&c->d_queue[0], n * sizeof(uint32_t)));
+    CK(cudaMalloc((void**)&c->d_queue[1], n * sizeof(uint32_t)));
+    c->pool_cap = paths;
+    return PTB_OK;
+}
+
+static void camera_from_abi(CameraDev& cam, const ptb_camera* pc, int W, int H) {
+    camera_setup(cam, pc->position, pc->direction, pc->up, pc->fov, pc->focus_distance, pc->aperture, W, H);
+}
+
+// ------------------------------------------------------------------------------------------------ C-ABI
+extern "C" {
+
+const char* ptb_version(void) { return "ptb200 0.1 (sm_100a wavefront, BVH8)"; }
+
+const char* ptb_last_error(const ptb_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int ptb_create(int device_id, ptb_ctx** out) {
+    if (!out) return PTB_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)";
+        return PTB_ERR_CUDA;
+    }
+    if (device_id < 0 || device_id >= n) { g_create_err = "device id out of range"; return PTB_ERR_INVALID; }
+    ptb_ctx* c = new ptb_ctx();
+    c->device = device_id;
+    memset(&c->pool, 0, sizeof(c->pool));
+    memset(&c->sc, 0, sizeof(c->sc));
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_counters, 2 * (PTB_MAX_BOUNCES + 1) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_totals, PTB_N_TOTALS * sizeof(unsigned long long)) != cudaSuccess) {
+        g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete c;
+        return PTB_ERR_CUDA;
+    }
+    *out = c;
+    return PTB_OK;
+}
+
+void ptb_destroy(ptb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    free_pool(c);
+    void* ptrs[] = {c->d_counters, c->d_totals, c->d_rpp, c->d_accum, c->d_out_img, c->d_out_cnt, c->d_out_u8};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ptb_add_sphere(ptb_ctx* c, const float O[3], float R, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !O) return PTB_ERR_INVALID;
+    if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
+    const int id = c->host.add_sphere(O, R, xf, flags);
+    if (out_id) *out_id = id;
+    return PTB_OK;
+}
+int ptb_add_plane(ptb_ctx* c, const float A[3], const float N[3], const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !A || !N) return PTB_ERR_INVALID;
+    if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
+    const int id = c->host.add_plane(A, N, xf, flags);
+    if (out_id) *out_id = id;
+    return PTB_OK;
+}
+int ptb_add_mesh(ptb_ctx* c, const ptb_mesh* m, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c) return PTB_ERR_INVALID;
+    if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
+    const int id = c->host.add_mesh(m, xf, flags, c->err);
+    if (id < 0) return id;
+    if (out_id) *out_id = id;
+    return PTB_OK;
+}
+int ptb_set_group_material(ptb_ctx* c, int obj, int group, const ptb_material* m) {
+    if (!c) return PTB_ERR_INVALID;
+    if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
+    return c->host.set_group_material(obj, group, m, c->err);
+}
+int ptb_set_brdf(ptb_ctx* c, int obj, int kind, int merl_id) {
+    if (!c || obj < 0 || obj >= (int)c->host.objects.size()) return PTB_ERR_INVALID;
+    if (kind == PTB_BRDF_MERL && (merl_id < 0 || merl_id >= (int)c->host.merl_tables.size())) { c->err = "set_brdf: unknown merl id"; return PTB_ERR_INVALID; }
+    if (kind != PTB_BRDF_PHONG && kind != PTB_BRDF_MERL) return PTB_ERR_UNSUPPORTED;
+    c->host.objects[obj].brdf = kind;
+    c->host.objects[obj].merl = kind == PTB_BRDF_MERL ? merl_id : 0;
+    return PTB_OK;
+}
+int ptb_add_merl(ptb_ctx* c, const double* table, int* out_merl_id) {
+    if (!c || !table) return PTB_ERR_INVALID;
+    c->host.merl_tables.emplace_back(table, table + 3 * (size_t)PTB_MERL_N);
+    if (out_merl_id) *out_merl_id = (int)c->host.merl_tables.size() - 1;
+    return PTB_OK;
+}
+int ptb_set_envmap(ptb_ctx* c, const uint8_t* rgb, int W, int H) {
+    if (!c) return PTB_ERR_INVALID;
+    if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
+    if (!rgb || W <= 0 || H <= 0) { c->host.envmap.clear(); c->host.envW = c->host.envH = 0; return PTB_OK; }
+    c->host.envmap.assign(rgb, rgb + (size_t)W * H * 3);
+    c->host.envW = W; c->host.envH = H;
+    return PTB_OK;
+}
+int ptb_set_light(ptb_ctx* c, float intensite_lumiere, float envmap_intensity) {
+    if (!c) return PTB_ERR_INVALID;
+    c->host.intensite_lumiere = intensite_lumiere;
+    c->host.envmap_intensity = envmap_intensity;
+    if (c->committed) {  // light constants live in the by-value scene header: cheap to refresh
+        const float s = c->host.objects[0].xf.scale;
+        c->sc.lightPower = intensite_lumiere / (s * s);
+        c->sc.envmap_intensity = envmap_intensity;
+    }
+    return PTB_OK;
+}
+
+int ptb_commit(ptb_ctx* c) {
+    if (!c) return PTB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = c->host.flatten(c->flat, c->err);
+    if (rc) return rc;
+    free_scene(c);
+    auto t0 = std::chrono::steady_clock::now();
+    FlatScene& f = c->flat;
+    SceneDev& sc = c->sc;
+    memset(&sc, 0, sizeof(sc));
+    const Node8* dn; const F4* dt; const uint8_t* de;
+    if ((rc = upload(c, f.nodes.data(), f.nodes.size(), &dn))) return rc;
+    if ((rc = upload(c, f.tris.data(), f.tris.size(), &dt))) return rc;
+    if ((rc = upload(c, f.tri_uv.data(), f.tri_uv.size(), &sc.tri_uv))) return rc;
+    if ((rc = upload(c, f.tri_shade.data(), f.tri_shade.size(), &sc.tri_shade))) return rc;
+    if ((rc = upload(c, f.objects.data(), f.objects.size(), &sc.objects))) return rc;
+    if ((rc = upload(c, f.materials.data(), f.materials.size(), &sc.materials))) return rc;
+    if ((rc = upload(c, f.texels.data(), f.texels.size(), &sc.texels))) return rc;
+    if ((rc = upload(c, f.envmap.data(), f.envmap.size(), &de))) return rc;
+    if ((rc = upload(c, f.merl.data(), f.merl.size(), &sc.merl))) return rc;
+    sc.nodes = reinterpret_cast<const F4*>(dn);
+    sc.tris = dt;
+    sc.envmap = de;
+    sc.n_objects = (int32_t)f.objects.size();
+    sc.has_mesh = f.nodes.empty() ? 0 : 1;
+    sc.envW = f.envW; sc.envH = f.envH; sc.has_envmap = (f.envW > 0 && f.envH > 0) ? 1 : 0;
+    sc.envmap_intensity = f.envmap_intensity; sc.lightPower = f.lightPower; sc.radiusLight = f.radiusLight;
+    sc.centerLight = v3(f.centerLight[0], f.centerLight[1], f.centerLight[2]);
+    CK(cudaStreamSynchronize(c->stream));
+    c->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->bytes_nodes = (int64_t)f.nodes.size() * sizeof(Node8);
+    c->bytes_tris = (int64_t)f.tris.size() * sizeof(F4);
+    c->bytes_attr = (int64_t)f.tri_uv.size() * sizeof(TriUV) + (int64_t)f.tri_shade.size() * sizeof(TriShade);
+    c->bytes_tex = (int64_t)f.texels.size() * 4 + (int64_t)f.envmap.size() + (int64_t)f.merl.size() * 4;
+    // the host copies of the big arrays are no longer needed
+    std::vector<F4>().swap(f.tris); std::vector<TriUV>().swap(f.tri_uv); std::vector<TriShade>().swap(f.tri_shade);
+    std::vector<float>().swap(f.texels); std::vector<float>().swap(f.merl);
+    c->committed = true;
+    return PTB_OK;
+}
+
+static int frame_setup(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, FrameDev& f) {
+    if (!cam || !p || p->W <= 0 || p->H <= 0 || p->nrays <= 0 || p->nb_bounces < 0 || p->nb_bounces > PTB_MAX_BOUNCES || !(p->sigma_filter > 0)) {
+        c->err = "render: invalid parameters"; return PTB_ERR_INVALID;
+    }
+    if ((int)ceilf(p->sigma_filter * 2) > PTB_MAX_FILTER) { c->err = "render: sigma_filter too large (filter_size > 4)"; return PTB_ERR_UNSUPPORTED; }
+    if ((int64_t)p->W * p->H >= ((int64_t)1 << 31)) { c->err = "render: frame too large"; return PTB_ERR_UNSUPPORTED; }
+    memset(&f, 0, sizeof(f));
+    camera_from_abi(f.cam, cam, p->W, p->H);
+    filter_setup(f.filter, p->sigma_filter);
+    f.W = p->W; f.H = p->H; f.nb_bounces = p->nb_bounces; f.seed = p->seed;
+    f.tile = p->tile_size > 0 ? p->tile_size : 64;
+    f.tiles_x = (p->W + f.tile - 1) / f.tile; f.tiles_y = (p->H + f.tile - 1) / f.tile;
+    f.shard_count = p->shard_count > 0 ? p->shard_count : 1;
+    f.shard_rank = p->shard_rank;
+    if (f.shard_rank < 0 || f.shard_rank >= f.shard_count) { c->err = "render: shard_rank out of range"; return PTB_ERR_INVALID; }
+    const int total_tiles = f.tiles_x * f.tiles_y;
+    f.n_my_tiles = total_tiles > f.shard_rank ? (total_tiles - f.shard_rank + f.shard_count - 1) / f.shard_count : 0;
+    // randomPerPixel (prepare_render): regenerated when the frame size changes
+    const int64_t npix = (int64_t)p->W * p->H;
+    if (c->rpp_n != npix) {
+        if (c->d_rpp) cudaFree(c->d_rpp);
+        c->d_rpp = nullptr; c->rpp_n = 0;
+        CK(cudaMalloc((void**)&c->d_rpp, (size_t)npix * 2 * sizeof(float)));
+        k_rpp<<<(unsigned)((npix + 255) / 256), 256, 0, c->stream>>>(c->d_rpp, (int)npix);
+        CK(cudaGetLastError());
+        c->rpp_n = npix;
+    }
+    f.rpp = c->d_rpp;
+    return PTB_OK;
+}
+
+// the pass loop; accumulates into d_rgbw (device, W*H float4)
+static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stats* stats) {
+    auto w0 = std::chrono::steady_clock::now();
+    const int64_t pixel_slots = (int64_t)f.n_my_tiles * f.tile * f.tile;
+    uint64_t launches = 0;
+    CK(cudaMemsetAsync(c->d_totals, 0, PTB_N_TOTALS * sizeof(unsigned long long), c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    // count the shard's in-image pixels (edge tiles are partial)
+    unsigned long long valid_pixels = 0;
+    for (int lt = 0; lt < f.n_my_tiles; lt++) {
+        const int tile_id = f.shard_rank + lt * f.shard_count;
+        const int ty = tile_id / f.tiles_x, tx = tile_id % f.tiles_x;
+        const int h = std::min(f.tile, f.H - ty * f.tile), w = std::min(f.tile, f.W - tx * f.tile);
+        valid_pixels += (unsigned long long)h * w;
+    }
+    if (pixel_slots > 0) {
+        // samples per pixel per pass and pixel slots per pass
+        int64_t pool = std::max<int64_t>(c->pool_paths, 1024);
+        int spp_pass; int64_t slots_pass;
+        if (pixel_slots * nrays <= pool) { spp_pass = nrays; slots_pass = pixel_slots; }
+        else if (pixel_slots <= pool) { spp_pass = (int)std::max<int64_t>(1, pool / pixel_slots); slots_pass = pixel_slots; }
+        else { spp_pass = 1; slots_pass = (pool / (f.tile * f.tile)) * (f.tile * f.tile); if (slots_pass <= 0) slots_pass = f.tile * f.tile; }
+        int rc = ensure_pool(c, slots_pass * spp_pass);
+        if (rc) return rc;
+        const int nb = f.nb_bounces;
+        for (int64_t s0 = 0; s0 < pixel_slots; s0 += slots_pass) {
+            const int64_t ns = std::min(slots_pass, pixel_slots - s0);
+            // valid pixels in this slot range (for the ray statistics)
+            unsigned long long valid_here = 0;
+            {
+                const int tp = f.tile * f.tile;
+                for (int64_t lt = s0 / tp; lt * tp < s0 + ns; lt++) {
+                    const int tile_id = f.shard_rank + (int)lt * f.shard_count;
+                    const int ty = tile_id / f.tiles_x, tx = tile_id % f.tiles_x;
+                    const int h = std::min(f.tile, f.H - ty * f.tile), w = std::min(f.tile, f.W - tx * f.tile);
+                    valid_here += (unsigned long long)h * w;
+                }
+            }
+            for (int k0 = 0; k0 < nrays; k0 += spp_pass) {
+                f.spp_pass = std::min(spp_pass, nrays - k0);
+                f.k0 = k0;
+                f.slot0 = (int)s0;
+                f.n_pixel_slots = (int)ns;
+                const int n_paths = (int)(ns * f.spp_pass);
+                const unsigned g256 = (unsigned)((n_paths + 255) / 256), g128 = (unsigned)((n_paths + 127) / 128);
+                CK(cudaMemsetAsync(c->d_counters, 0, 2 * (PTB_MAX_BOUNCES + 1) * sizeof(uint32_t), c->stream));
+                k_raygen<<<g256, 256, 0, c->stream>>>(f, c->pool, n_paths);
+                launches++;
+                for (int b = 0; b < nb; b++) {
+                    const uint32_t* q = b == 0 ? nullptr : c->d_queue[b & 1];
+                    const uint32_t* cnt = b == 0 ? nullptr : c->d_counters + 2 * b;
+                    if (c->count_traversal) k_extend<true><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_totals);
+                    else k_extend<false><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_totals);
+                    k_shade<<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1),
+                                                         c->d_counters + 2 * b + 1);
+                    if (c->count_traversal) k_shadow<true><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, c->d_counters + 2 * b + 1, c->d_totals);
+                    else k_shadow<false><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, c->d_counters + 2 * b + 1, c->d_totals);
+                    launches += 3;
+                }
+                k_splat<<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(f, c->pool, d_rgbw);
+                k_totals<<<1, 32, 0, c->stream>>>(c->d_counters, nb, nb > 0 ? valid_here * (unsigned long long)f.spp_pass : 0ull, c->d_totals);
+                launches += 2;
+                CK(cudaGetLastError());
+            }
+        }
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (stats) {
+        unsigned long long t[PTB_N_TOTALS];
+        CK(cudaMemcpy(t, c->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        memset(stats, 0, sizeof(*stats));
+        stats->samples = valid_pixels * (unsigned long long)nrays;
+        stats->rays_closest = t[0]; stats->rays_shadow = t[1]; stats->node_visits = t[2]; stats->tri_tests = t[3];
+        stats->ms_device = ms;
+        stats->ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+        stats->kernel_launches = launches;
+    }
+    return PTB_OK;
+}
+
+int ptb_render_accum(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* d_rgbw, ptb_stats* stats) {
+    if (!c) return PTB_ERR_INVALID;
+    if (!c->committed) { c->err = "render before commit"; return PTB_ERR_STATE; }
+    if (!d_rgbw) { c->err = "render_accum: null device buffer"; return PTB_ERR_INVALID; }
+    CK(cudaSetDevice(c->device));
+    FrameDev f;
+    int rc = frame_setup(c, cam, p, f);
+    if (rc) return rc;
+    return render_passes(c, f, p->nrays, reinterpret_cast<F4*>(d_rgbw), stats);
+}
+
+static int resolve_to_host(ptb_ctx* c, const F4* d_rgbw, int W, int H, float gamma, float* imagedouble, float* sample_count, uint8_t* image) {
+    const int64_t n = (int64_t)W * H;
+    if (c->out_n < n) {
+        void* ptrs[] = {c->d_out_img, c->d_out_cnt, c->d_out_u8};
+        for (void* q : ptrs) if (q) cudaFree(q);
+        c->d_out_img = nullptr; c->d_out_cnt = nullptr; c->d_out_u8 = nullptr; c->out_n = 0;
+        CK(cudaMalloc((void**)&c->d_out_img, (size_t)n * 3 * sizeof(float)));
+        CK(cudaMalloc((void**)&c->d_out_cnt, (size_t)n * sizeof(float)));
+        CK(cudaMalloc((void**)&c->d_out_u8, (size_t)n * 3));
+        c->out_n = n;
+    }
+    k_resolve<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_rgbw, (size_t)n, gamma, imagedouble ? c->d_out_img : nullptr,
+                                                                 sample_count ? c->d_out_cnt : nullptr, image ? c->d_out_u8 : nullptr);
+    CK(cudaGetLastError());
+    if (imagedouble) CK(cudaMemcpyAsync(imagedouble, c->d_out_img, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (sample_count) CK(cudaMemcpyAsync(sample_count, c->d_out_cnt, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (image) CK(cudaMemcpyAsync(image, c->d_out_u8, (size_t)n * 3, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_resolve(ptb_ctx* c, const float* d_rgbw, int W, int H, float gamma, float* imagedouble, float* sample_count, uint8_t* image) {
+    if (!c || !d_rgbw || W <= 0 || H <= 0) return PTB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    return resolve_to_host(c, reinterpret_cast<const F4*>(d_rgbw), W, H, gamma, imagedouble, sample_count, image);
+}
+
+int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats) {
+    if (!c) return PTB_ERR_INVALID;
+    if (!c->committed) { c->err = "render before commit"; return PTB_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    auto w0 = std::chrono::steady_clock::now();
+    FrameDev f;
+    int rc = frame_setup(c, cam, p, f);
+    if (rc) return rc;
+    const int64_t n = (int64_t)p->W * p->H;
+    if (c->accum_n < n) {
+        if (c->d_accum) cudaFree(c->d_accum);
+        c->d_accum = nullptr; c->accum_n = 0;
+        CK(cudaMalloc((void**)&c->d_accum, (size_t)n * sizeof(F4)));
+        c->accum_n = n;
+    }
+    CK(cudaMemsetAsync(c->d_accum, 0, (size_t)n * sizeof(F4), c->stream));
+    rc = render_passes(c, f, p->nrays, c->d_accum, stats);
+    if (rc) return rc;
+    rc = resolve_to_host(c, c->d_accum, p->W, p->H, p->gamma, imagedouble, sample_count, image);
+    if (rc) return rc;
+    if (stats) stats->ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    return PTB_OK;
+}
+
+static void shard_geometry(const ptb_params* p, int rank, int& tile, int& apron, int& tiles_x, int& total, int& mine) {
+    tile = p->tile_size > 0 ? p->tile_size : 64;
+    apron = (int)ceilf(p->sigma_filter * 2);
+    tiles_x = (p->W + tile - 1) / tile;
+    total = tiles_x * ((p->H + tile - 1) / tile);
+    const int count = p->shard_count > 0 ? p->shard_count : 1;
+    mine = total > rank ? (total - rank + count - 1) / count : 0;
+}
+
+int ptb_shard_pack_size(const ptb_params* p, int shard_rank, int64_t* out_floats) {
+    if (!p || !out_floats || p->W <= 0 || p->H <= 0) return PTB_ERR_INVALID;
+    int tile, apron, tiles_x, total, mine;
+    shard_geometry(p, shard_rank, tile, apron, tiles_x, total, mine);
+    const int64_t side = tile + 2 * apron;
+    *out_floats = (int64_t)mine * side * side * 4;
+    return PTB_OK;
+}
+
+static int shard_move(ptb_ctx* c, const ptb_params* p, int shard_rank, const float* d_rgbw, float* d_packed, int unpack) {
+    if (!c || !p || !d_rgbw || !d_packed) return PTB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    int tile, apron, tiles_x, total, mine;
+    shard_geometry(p, shard_rank, tile, apron, tiles_x, total, mine);
+    const long long side = tile + 2 * apron, n = (long long)mine * side * side;
+    if (n == 0) return PTB_OK;
+    k_shard_pack<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const F4*>(d_rgbw), reinterpret_cast<F4*>(d_packed), p->W, p->H, tile, apron,
+                                                                    tiles_x, total, shard_rank, p->shard_count > 0 ? p->shard_count : 1, n, unpack);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+int ptb_shard_pack(ptb_ctx* c, const ptb_params* p, int shard_rank, const float* d_rgbw, float* d_packed) { return shard_move(c, p, shard_rank, d_rgbw, d_packed, 0); }
+int ptb_shard_unpack_add(ptb_ctx* c, const ptb_params* p, int shard_rank, const float* d_packed, float* d_rgbw) { return shard_move(c, p, shard_rank, d_rgbw, const_cast<float*>(d_packed), 1); }
+
+int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* obj_id, int32_t* tri_id, float* t) {
+    if (!c || !cam || W <= 0 || H <= 0) return PTB_ERR_INVALID;
+    if (!c->committed) { c->err = "primary_ids before commit"; return PTB_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    CameraDev cd;
+    camera_from_abi(cd, cam, W, H);
+    const size_t n = (size_t)W * H;
+    int32_t *d_o = nullptr, *d_t = nullptr; float* d_tt = nullptr;
+    CK(cudaMalloc((void**)&d_o, n * 4)); CK(cudaMalloc((void**)&d_t, n * 4)); CK(cudaMalloc((void**)&d_tt, n * 4));
+    k_primary<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->sc, cd, W, H, d_o, d_t, d_tt);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess && obj_id) e = cudaMemcpy(obj_id, d_o, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && tri_id) e = cudaMemcpy(tri_id, d_t, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && t) e = cudaMemcpy(t, d_tt, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_o); cudaFree(d_t); cudaFree(d_tt);
+    if (e != cudaSuccess) { c->err = std::string("primary_ids: ") + cudaGetErrorString(e); return PTB_ERR_CUDA; }
+    return PTB_OK;
+}
+
+int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
+    if (!c) return PTB_ERR_INVALID;
+    switch (option) {
+    case PTB_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return PTB_OK;
+    case PTB_OPT_POOL_PATHS: if (value < 1024) return PTB_ERR_INVALID; c->pool_paths = value; return PTB_OK;
+    default: return PTB_OK;  // unknown options (e.g. the CPU checkers' thread count) are ignored
+    }
+}
+
+int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
+    if (!c || !info) return PTB_ERR_INVALID;
+    memset(info, 0, sizeof(*info));
+    info->n_triangles = c->bytes_tris / 48;
+    info->n_bvh_nodes = c->flat.bvh.n_nodes;
+    info->bytes_nodes = c->bytes_nodes; info->bytes_triangles = c->bytes_tris; info->bytes_attributes = c->bytes_attr; info->bytes_textures = c->bytes_tex;
+    info->n_objects = (int32_t)c->host.objects.size();
+    info->bvh_depth = c->flat.bvh.depth;
+    info->ms_bvh_build = c->flat.ms_bvh; info->ms_upload = c->ms_upload;
+    return PTB_OK;
+}
+
+int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H, const double* in, int n, int is, double* out, int os) {
+    if (!c || !in || !out || n <= 0) return PTB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    if (which == PTB_KAT_MERL_EVAL && (!c->committed || c->host.merl_tables.empty())) { c->err = "kat: MERL needs a committed scene with a table"; return PTB_ERR_STATE; }
+    CameraDev cd;
+    memset(&cd, 0, sizeof(cd));
+    if (cam) camera_from_abi(cd, cam, W, H);
+    FilterDev fd;
+    memset(&fd, 0, sizeof(fd));
+    if (which == PTB_KAT_FILTER_RATIO) filter_setup(fd, (float)in[2]);
+    double *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMalloc((void**)&d_in, (size_t)n * is * 8)); CK(cudaMalloc((void**)&d_out, (size_t)n * os * 8));
+    cudaError_t e = cudaMemcpy(d_in, in, (size_t)n * is * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_out, 0, (size_t)n * os * 8);
+    if (e == cudaSuccess) {
+        k_kat<<<(n + 63) / 64, 64, 0, c->stream>>>(which, c->sc, cd, fd, W, H, d_in, n, is, d_out, os);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n * os * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) { c->err = std::string("kat: ") + cudaGetErrorString(e); return PTB_ERR_CUDA; }
+    return PTB_OK;
+}
+
+}  // extern "C"

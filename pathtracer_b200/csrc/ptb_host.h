@@ -1,0 +1,73 @@
+// ptb_host.h — host-side scene model behind the C-ABI (no CUDA types here).
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ptb200.h"
+#include "ptb_scene.h"
+
+namespace ptb {
+
+struct Bvh8Stats {
+    int64_t n_nodes = 0, n_binary_nodes = 0, leaves = 0;
+    int depth = 0;
+};
+// verts9: 9 floats per triangle (world space).  leaf_order[k] = input index of the k-th stored triangle.
+void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& nodes, std::vector<uint32_t>& leaf_order, Bvh8Stats& stats);
+
+struct HostTex {
+    float mult[3] = {1, 1, 1};
+    int W = 0, H = 0;
+    std::vector<float> texels;
+};
+struct HostMaterial {
+    uint32_t present = 0;
+    HostTex Kd, Ks, Ne, transp, refr, normal, alpha;
+};
+struct HostObject {
+    int type = OBJ_SPHERE, flags = 0, brdf = 0, merl = 0;
+    ptb_xform xf;
+    float a[3] = {0, 0, 0}, n[3] = {0, 1, 0}, R = 0;
+    std::vector<HostMaterial> groups;      // index = group
+    // mesh data AFTER TriMesh::init processing (object space)
+    std::vector<float> vertices, normals, uvs, tangents;   // tangents: per vertex
+    std::vector<int32_t> tri;              // n x 10
+    float trans[12], inv_trans[12], rot[9];
+};
+
+// Everything ptb_commit produces, ready to upload.
+struct FlatScene {
+    std::vector<Node8> nodes;
+    std::vector<F4> tris;                  // 3 per triangle, leaf order
+    std::vector<TriUV> tri_uv;
+    std::vector<TriShade> tri_shade;
+    std::vector<ObjectDev> objects;
+    std::vector<MaterialDev> materials;
+    std::vector<float> texels;
+    std::vector<uint8_t> envmap;
+    std::vector<float> merl;
+    int envW = 0, envH = 0;
+    float envmap_intensity = 1, lightPower = 0, radiusLight = 0, centerLight[3] = {0, 0, 0};
+    Bvh8Stats bvh;
+    double ms_bvh = 0;
+};
+
+struct HostScene {
+    std::vector<HostObject> objects;
+    std::vector<std::vector<double>> merl_tables;
+    std::vector<uint8_t> envmap;
+    int envW = 0, envH = 0;
+    float intensite_lumiere = 0, envmap_intensity = 1;
+
+    int add_sphere(const float O[3], float R, const ptb_xform* xf, int flags);
+    int add_plane(const float A[3], const float N[3], const ptb_xform* xf, int flags);
+    int add_mesh(const ptb_mesh* m, const ptb_xform* xf, int flags, std::string& err);
+    int set_group_material(int obj, int group, const ptb_material* m, std::string& err);
+    int flatten(FlatScene& out, std::string& err);
+};
+
+void build_matrix(HostObject& o);          // Object::build_matrix (Geometry.h:322-360)
+
+}  // namespace ptb

@@ -1,0 +1,560 @@
+// ptb_scene.h — device-side scene description and the per-path stages of the wavefront integrator.
+//
+// The stages restate Raytracer::getColor (Raytracer.cpp:196-664, fog / subsurface / ghost / background
+// branches excluded, see DESIGN.md "scope") as four per-path functions that the kernels in kernels.cu
+// call once per queue entry:
+//     raygen_one  — precomputeRayBatch + Camera::generateDirection (Raytracer.cpp:1404-1420)
+//     extend_one  — Scene::intersection (Geometry.cpp:589-688)
+//     shade_one   — getColor's per-bounce body: emission, mirror, dielectric, NEE sample, BSDF sample
+//     shadow_one  — Scene::intersection_shadow (Geometry.cpp:691-744) + the deferred direct term
+//     splat_pixel — the Gaussian splat (Raytracer.cpp:1604-1659)
+#pragma once
+#include "ptb_bvh8.h"
+
+namespace ptb {
+
+enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2 };
+enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4 };
+enum { SLOT_KD = 1, SLOT_KS = 2, SLOT_NE = 4, SLOT_TRANSP = 8, SLOT_REFR = 16, SLOT_NORMAL = 32, SLOT_ALPHA = 64 };
+
+struct ObjectDev {          // Object / Sphere / Plane fields the path reads (Geometry.h:240-672, 849-1217)
+    int32_t type, flags, brdf, merl;
+    int32_t mat_base, n_groups;   // materials[mat_base + group], group < n_groups else defaults
+    int32_t slot_mask;            // union of the slots present on the object (Geometry.h:979 test for spheres)
+    int32_t pad;
+    float trans[12], inv_trans[12], rot[9];
+    float a[3];                   // Sphere::O / Plane::A
+    float n[3];                   // Plane::vecN
+    float R, R2;
+};
+struct MaterialDev {
+    uint32_t present;
+    TexDev Kd, Ks, Ne, transp, refr, normal, alpha;
+};
+struct alignas(16) TriUV {     // what the in-traversal alpha test and the uv interpolation need (32 B)
+    float u0, v0, u1, v1, u2, v2;
+    int32_t group;             // TriangleIndices::group (-1: no uv / default material)
+    int32_t object_has_uv;     // object id | (has_uv << 31)
+};
+struct alignas(16) TriShade {  // object-space vertex normals and tangents + original triangle id (80 B)
+    float n0[3], n1[3], n2[3], t0[3], t1[3], t2[3];
+    int32_t orig;
+    int32_t pad;
+};
+
+struct SceneDev {
+    const F4* nodes;            // 5 x F4 per Node8
+    const F4* tris;             // 3 x F4 per triangle, leaf order
+    const TriUV* tri_uv;
+    const TriShade* tri_shade;
+    const ObjectDev* objects;
+    const MaterialDev* materials;
+    const float* texels;
+    const uint8_t* envmap;
+    const float* merl;          // per table 3*PTB_MERL_N floats, pre-scaled (see merl_eval)
+    int32_t n_objects, has_mesh, envW, envH, has_envmap, pad0;
+    float envmap_intensity, lightPower, radiusLight;
+    V3 centerLight;
+};
+
+struct AlphaCtx {
+    const TriUV* tri_uv;
+    const ObjectDev* objects;
+    const MaterialDev* materials;
+    const float* texels;
+};
+
+// TriangleMesh.cpp:1198-1205: reject the hit when the group's alpha map reads < 0.5 at the hit's uv
+PTB_HD bool alpha_rejects(const AlphaCtx* c, int prim, float b1, float b2) {
+#if defined(__CUDA_ARCH__)
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(c->tri_uv + prim));
+    const float4 q1 = __ldg(reinterpret_cast<const float4*>(c->tri_uv + prim) + 1);
+    TriUV tu; tu.u0 = q0.x; tu.v0 = q0.y; tu.u1 = q0.z; tu.v1 = q0.w; tu.u2 = q1.x; tu.v2 = q1.y;
+    tu.group = __float_as_int(q1.z); tu.object_has_uv = __float_as_int(q1.w);
+#else
+    const TriUV tu = c->tri_uv[prim];
+#endif
+    if (tu.group < 0 || tu.object_has_uv >= 0) return false;  // needs a group and uvs
+    const ObjectDev& ob = c->objects[tu.object_has_uv & 0x7fffffff];
+    if (tu.group >= ob.n_groups) return false;
+    const MaterialDev& m = c->materials[ob.mat_base + tu.group];
+    if (!(m.present & SLOT_ALPHA)) return false;
+    const float alpha = 1.f - b1 - b2;
+    float u = tu.u0 * alpha + tu.u1 * b1 + tu.u2 * b2;
+    float v = tu.v0 * alpha + tu.v1 * b1 + tu.v2 * b2;
+    u = tex_wrap(u); v = tex_wrap(v);
+    return tex_red(m.alpha, c->texels, u, v) < 0.5f;
+}
+
+PTB_HD V3 xf_point(const float* m, V3 v) {   // Object::apply_transformation (Geometry.h:362-368)
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3], m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7],
+              m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11]);
+}
+PTB_HD V3 xf_dir(const float* m, V3 v) {     // apply_rotation_scaling (369-375)
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+PTB_HD V3 xf_rot(const float* m, V3 v) {     // apply_rotation (376-382), 3x3
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
+}
+
+// Sphere::intersection roots (Geometry.h:943-962): object-space ray, non-unit direction
+PTB_HD bool sphere_t(const ObjectDev& ob, V3 o, V3 d, float& t) {
+    const V3 O = v3(ob.a[0], ob.a[1], ob.a[2]);
+    const V3 oc = o - O;
+    const float b = dot(d, oc);
+    const float a = norm2(d);
+    const float c = norm2(oc) - ob.R2;
+    const float delta = b * b - a * c;
+    if (delta < 0) return false;
+    const float sq = sqrtf(delta);
+    const float inva = 1.f / a;
+    const float t2 = (-b + sq) * inva;
+    if (t2 < 0) return false;
+    const float t1 = (-b - sq) * inva;
+    t = (t1 > 0) ? t1 : t2;
+    return true;
+}
+// Plane::intersection (Geometry.h:1142-1148)
+PTB_HD bool plane_t(const ObjectDev& ob, V3 o, V3 d, float& t) {
+    const V3 N = v3(ob.n[0], ob.n[1], ob.n[2]);
+    const float ddot = dot(d, N);
+    if (fabsf(ddot) < 1E-9f) return false;
+    t = dot(v3(ob.a[0], ob.a[1], ob.a[2]) - o, N) / ddot;
+    if (t <= 0.f) return false;
+    return true;
+}
+
+#define PTB_HIT_MISS (-1)
+PTB_HD int32_t hit_id_analytic(int obj) { return -2 - obj; }
+
+// Scene::intersection: nearest over analytic objects (object-space rays, world t) then the wide BVH.
+template <bool COUNT>
+PTB_HD void extend_ray(const SceneDev& sc, V3 o, V3 d, Hit& hit, int32_t& id, TraverseCounters* cnt) {
+    float tmin = INFINITY;
+    id = PTB_HIT_MISS;
+    hit.t = INFINITY; hit.b1 = 0; hit.b2 = 0; hit.prim = -1;
+    for (int i = 0; i < sc.n_objects; i++) {
+        const ObjectDev& ob = sc.objects[i];
+        if (ob.type == OBJ_MESH) continue;
+        const V3 dl = xf_dir(ob.inv_trans, d);
+        const V3 ol = xf_point(ob.inv_trans, o);
+        float t;
+        const bool h = (ob.type == OBJ_SPHERE) ? sphere_t(ob, ol, dl, t) : plane_t(ob, ol, dl, t);
+        if (h && t < tmin) { tmin = t; id = hit_id_analytic(i); }
+    }
+    if (sc.has_mesh) {
+        AlphaCtx ac; ac.tri_uv = sc.tri_uv; ac.objects = sc.objects; ac.materials = sc.materials; ac.texels = sc.texels;
+        Hit h;
+        if (traverse<false, COUNT>(sc.nodes, sc.tris, &ac, o, d, tmin, h, cnt)) { hit = h; id = h.prim; tmin = h.t; }
+    }
+    hit.t = tmin;
+}
+
+// Scene::intersection_shadow with avoid_ghosts: any object closer than 0.999*dist_light.
+template <bool COUNT>
+PTB_HD bool occluded(const SceneDev& sc, V3 o, V3 d, float dist_light, TraverseCounters* cnt) {
+    const float lim = dist_light * 0.999f;
+    for (int i = 0; i < sc.n_objects; i++) {
+        const ObjectDev& ob = sc.objects[i];
+        if (ob.type == OBJ_MESH) continue;
+        const V3 dl = xf_dir(ob.inv_trans, d);
+        const V3 ol = xf_point(ob.inv_trans, o);
+        float t;
+        const bool h = (ob.type == OBJ_SPHERE) ? sphere_t(ob, ol, dl, t) : plane_t(ob, ol, dl, t);
+        if (h && t < lim) return true;
+    }
+    if (sc.has_mesh) {
+        AlphaCtx ac; ac.tri_uv = sc.tri_uv; ac.objects = sc.objects; ac.materials = sc.materials; ac.texels = sc.texels;
+        Hit h;
+        if (traverse<true, COUNT>(sc.nodes, sc.tris, &ac, o, d, lim, h, cnt)) return true;
+    }
+    return false;
+}
+
+struct Surface {   // MaterialValues (BRDF.h:7-20) + what getColor needs about the object
+    V3 P, N, Kd, Ks, Ne, Ke;
+    float refr_index;
+    bool transp;
+    int32_t object;
+};
+
+// Object::queryMaterial (Geometry.h:399-445)
+PTB_HD void query_material(const SceneDev& sc, const ObjectDev& ob, int group, float u, float v, Surface& s) {
+    u = tex_wrap(u); v = tex_wrap(v);
+    const bool in_range = group >= 0 && group < ob.n_groups;
+    const MaterialDev* m = in_range ? &sc.materials[ob.mat_base + group] : nullptr;
+    const uint32_t present = m ? m->present : 0u;
+    s.Kd = (present & SLOT_KD) ? tex_vec(m->Kd, sc.texels, u, v) : v3(1, 1, 1);
+    s.Ks = (present & SLOT_KS) ? tex_vec(m->Ks, sc.texels, u, v) : v3(0, 0, 0);
+    s.Ne = (present & SLOT_NE) ? tex_vec(m->Ne, sc.texels, u, v) : v3(1, 1, 1);
+    s.transp = (present & SLOT_TRANSP) ? (tex_red(m->transp, sc.texels, u, v) < 0.5f) : false;
+    s.refr_index = (present & SLOT_REFR) ? tex_red(m->refr, sc.texels, u, v) : 1.3f;
+    s.Ke = v3(0, 0, 0);
+}
+
+// Rebuild the shading point of a hit: Object::intersection's material part + the tail of Scene::intersection.
+PTB_HD void surface_from_hit(const SceneDev& sc, V3 o, V3 d, const Hit& hit, int32_t id, Surface& s) {
+    V3 Nl;  // object-space shading normal before rotation
+    const ObjectDev* obp;
+    if (id >= 0) {
+        // ---- TriMesh::getMaterial (TriangleMesh.cpp:919-1026) ----
+        const TriUV tu = sc.tri_uv[id];
+        const TriShade ts = sc.tri_shade[id];
+        s.object = tu.object_has_uv & 0x7fffffff;
+        obp = &sc.objects[s.object];
+        float beta = hit.b1, gamma = hit.b2;
+        float alpha = 1.f - beta - gamma;
+        const bool has_uv = tu.object_has_uv < 0;
+        float u = 0, v = 0;
+        if (has_uv) {
+            u = tu.u0 * alpha + tu.u1 * beta + tu.u2 * gamma;
+            v = tu.v0 * alpha + tu.v1 * beta + tu.v2 * gamma;
+        }
+        query_material(sc, *obp, tu.group, u, v, s);
+        Nl = v3(ts.n0[0], ts.n0[1], ts.n0[2]) * alpha + v3(ts.n1[0], ts.n1[1], ts.n1[2]) * beta + v3(ts.n2[0], ts.n2[1], ts.n2[2]) * gamma;
+        Nl = normalize(Nl);
+        const bool in_range = tu.group >= 0 && tu.group < obp->n_groups;
+        if (has_uv && in_range && (sc.materials[obp->mat_base + tu.group].present & SLOT_NORMAL)) {
+            const MaterialDev& m = sc.materials[obp->mat_base + tu.group];
+            V3 tangent = v3(ts.t0[0], ts.t0[1], ts.t0[2]) * alpha + v3(ts.t1[0], ts.t1[1], ts.t1[2]) * beta + v3(ts.t2[0], ts.t2[1], ts.t2[2]) * gamma;
+            tangent = normalize(tangent);
+            const V3 bitangent = cross(Nl, tangent);
+            const V3 nl = tex_normal(m.normal, sc.texels, u, v);  // un-wrapped uv, as getMaterial passes them (TriangleMesh.cpp:961)
+            V3 Ns = nl.x * tangent + nl.y * bitangent + nl.z * Nl;
+            if (Ns.x == 0.f && Ns.y == 0.f && Ns.z == 0.f) Ns = Nl;
+            Nl = normalize(Ns);
+        }
+        if (obp->flags & FLAG_FLIP) Nl = -Nl;
+        s.P = o + hit.t * d;  // world-space triangles: same point as apply_transformation(o' + t d')
+    } else {
+        s.object = -2 - id;
+        obp = &sc.objects[s.object];
+        const ObjectDev& ob = *obp;
+        const V3 dl = xf_dir(ob.inv_trans, d);
+        const V3 ol = xf_point(ob.inv_trans, o);
+        const V3 Pl = ol + hit.t * dl;
+        if (ob.type == OBJ_SPHERE) {
+            V3 N = Pl - v3(ob.a[0], ob.a[1], ob.a[2]);
+            if (s.object == 1 && sc.has_envmap) {
+                // Geometry.h:963-977: the dome with an environment map
+                N = fast_normalize(N);
+                const float theta = 1.f - acosf(N.y) / PTB_PI_F;
+                const float phi = (float)(((double)atan2f(-N.z, N.x) + PTB_PI_D) / (double)(2.f * PTB_PI_F));
+                query_material(sc, ob, 0, theta, phi, s);
+                Nl = -N;
+                const int idx = 3 * ((int)(theta * ((float)sc.envH - 1.f)) * sc.envW + (int)(phi * ((float)sc.envW - 1.f)));
+                if (idx < 0 || idx >= 3 * sc.envW * sc.envH) s.Ke = v3(0, 0, 0);
+                else s.Ke = v3((float)sc.envmap[idx], (float)sc.envmap[idx + 1], (float)sc.envmap[idx + 2]) * (100000.f / 255.f);
+            } else {
+                // MaterialValues() defaults when the sphere has no slot at all (BRDF.h:9-16)
+                s.Kd = v3(.5f, .5f, .5f); s.Ks = v3(0, 0, 0); s.Ne = v3(100, 100, 100); s.transp = false; s.refr_index = 1.3f;
+                if (ob.slot_mask & (SLOT_KD | SLOT_KS | SLOT_NE | SLOT_TRANSP | SLOT_REFR)) {
+                    N = fast_normalize(N);
+                    const float theta = 1.f - acosf(N.y) / PTB_PI_F;
+                    const float phi = (atan2f(-N.z, N.x) + PTB_PI_F) / (2.f * PTB_PI_F);
+                    query_material(sc, ob, 0, theta, phi, s);
+                }
+                s.Ke = v3(0, 0, 0);
+                Nl = (ob.flags & FLAG_FLIP) ? -N : N;
+            }
+        } else {
+            Nl = v3(ob.n[0], ob.n[1], ob.n[2]);
+            query_material(sc, ob, 0, Pl.x * 0.1f, Pl.z * 0.1f, s);
+        }
+        s.P = xf_point(ob.trans, Pl);
+    }
+    s.N = fast_normalize(xf_rot(obp->rot, Nl));  // Geometry.cpp:677-684
+}
+
+// ---- path pool (structure of arrays in HBM) ---------------------------------------------------------
+struct PoolDev {
+    F4* ray_o;        // xyz origin
+    F4* ray_d;        // xyz direction
+    F4* weight;       // xyz path weight; w = bits: depth (low 16) | show_lights << 16
+    F4* radiance;     // xyz accumulated radiance of the sample
+    F4* hit;          // t, b1, b2, id bits
+    uint64_t* rng;    // pcg32 state (inc follows from pixel/sample/seed)
+    uint32_t* pixel;  // i*W + j, or 0xffffffff for an empty slot
+    F4* sh_o;         // shadow queue: xyz origin, w = dist_light
+    F4* sh_d;         // xyz direction, w = path slot bits
+    F4* sh_c;         // xyz = path weight * direct contribution
+};
+
+struct FrameDev {     // per-render constants (Raytracer fields + prepare_render results)
+    CameraDev cam;
+    FilterDev filter;
+    int32_t W, H, nb_bounces, spp_pass, k0;   // this pass traces samples k0 .. k0+spp_pass-1 of each pixel
+    uint32_t seed;
+    int32_t tile, tiles_x, tiles_y, shard_rank, shard_count, n_my_tiles;
+    int32_t slot0;                            // first pixel slot (in the shard's tile-major pixel order) of this pass
+    int32_t n_pixel_slots;                    // pixel slots in this pass
+    const float* rpp;                         // randomPerPixel, 2 floats per pixel (Raytracer.cpp:1341-1344)
+};
+
+// pixel slot (tile-major order over the shard's tiles) -> (i, j); false if outside the image
+PTB_HD bool slot_to_pixel(const FrameDev& f, int slot, int& i, int& j) {
+    const int tp = f.tile * f.tile;
+    const int lt = slot / tp, r = slot - lt * tp;
+    const int tile_id = f.shard_rank + lt * f.shard_count;
+    if (tile_id >= f.tiles_x * f.tiles_y) return false;
+    const int ty = tile_id / f.tiles_x, tx = tile_id - ty * f.tiles_x;
+    i = ty * f.tile + r / f.tile;
+    j = tx * f.tile + (r % f.tile);
+    return i < f.H && j < f.W;
+}
+
+PTB_HD uint64_t path_inc(const FrameDev& f, int path) {  // pcg32 stream increment of the path's (pixel,sample) stream
+    return (((uint64_t)(uint32_t)(f.k0 + (path % f.spp_pass)) ^ ((uint64_t)f.seed << 32)) << 1) | 1ULL;
+}
+PTB_HD uint32_t pack_state(int depth, bool show_lights) { return (uint32_t)depth | (show_lights ? 0x10000u : 0u); }
+
+// ---- stage 1: camera samples --------------------------------------------------------------------------
+PTB_HD void raygen_one(const FrameDev& f, PoolDev& p, int path) {
+    const int ps = path / f.spp_pass, s = path - ps * f.spp_pass;
+    int i, j;
+    if (!slot_to_pixel(f, f.slot0 + ps, i, j)) { p.pixel[path] = 0xffffffffu; return; }
+    const uint32_t pix = (uint32_t)(i * f.W + j);
+    const uint32_t k = (uint32_t)(f.k0 + s);
+    Pcg32 e = pcg32_for_sample(pix, k, f.seed);
+    const float dx = pcg32_uniform(e) - 0.5f;
+    const float dy = pcg32_uniform(e) - 0.5f;
+    const float ax = (pcg32_uniform(e) - 0.5f) * f.cam.aperture;
+    const float ay = (pcg32_uniform(e) - 0.5f) * f.cam.aperture;
+    V3 o, d;
+    camera_ray(f.cam, i, j, dx, dy, ax, ay, o, d);
+    F4 q;
+    q.x = o.x; q.y = o.y; q.z = o.z; q.w = 0; p.ray_o[path] = q;
+    q.x = d.x; q.y = d.y; q.z = d.z; q.w = 0; p.ray_d[path] = q;
+    q.x = 1; q.y = 1; q.z = 1; q.w = u2f(pack_state(f.nb_bounces, true)); p.weight[path] = q;
+    q.x = 0; q.y = 0; q.z = 0; q.w = 0; p.radiance[path] = q;
+    p.rng[path] = e.state;
+    p.pixel[path] = pix;
+}
+
+// ---- stage 2: closest hit ---------------------------------------------------------------------------------
+template <bool COUNT>
+PTB_HD void extend_one(const SceneDev& sc, PoolDev& p, int path, TraverseCounters* cnt) {
+    const F4 o = p.ray_o[path], d = p.ray_d[path];
+    Hit h;
+    int32_t id;
+    extend_ray<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), h, id, cnt);
+    F4 q;
+    q.x = h.t; q.y = h.b1; q.z = h.b2; q.w = u2f((uint32_t)id);
+    p.hit[path] = q;
+}
+
+// ---- stage 3: shade ---------------------------------------------------------------------------------------
+struct ShadeOut {
+    bool cont;      // the path continues: ray_o/ray_d/weight were rewritten
+    bool shadow;    // a shadow ray was produced
+    F4 sh_o, sh_d, sh_c;
+};
+
+PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path, ShadeOut& out) {
+    out.cont = false; out.shadow = false;
+    const F4 hq = p.hit[path];
+    const int32_t id = (int32_t)f2u(hq.w);
+    if (id == PTB_HIT_MISS) return;                                  // Raytracer.cpp:654-657
+    const F4 oq = p.ray_o[path], dq = p.ray_d[path], wq = p.weight[path];
+    const V3 ro = v3(oq.x, oq.y, oq.z), rd = v3(dq.x, dq.y, dq.z);
+    const V3 w = v3(wq.x, wq.y, wq.z);
+    const uint32_t st = f2u(wq.w);
+    const int depth = (int)(st & 0xffffu);
+    const bool show_lights = (st & 0x10000u) != 0;
+    Hit hit; hit.t = hq.x; hit.b1 = hq.y; hit.b2 = hq.z; hit.prim = id;
+    F4 Lq = p.radiance[path];
+    if (id == hit_id_analytic(0)) {                                  // the light, Raytracer.cpp:303-316
+        const float lp = show_lights ? sc.lightPower : 0.f;
+        Lq.x += w.x * lp; Lq.y += w.y * lp; Lq.z += w.z * lp;
+        p.radiance[path] = Lq;
+        return;
+    }
+    if (id == hit_id_analytic(1) && !sc.has_envmap) return;          // dome without a map: Ke = 0
+    Surface s;
+    surface_from_hit(sc, ro, rd, hit, id, s);
+    if (s.object == 1) {                                             // env dome, Raytracer.cpp:275-301
+        const V3 c = (w * sc.envmap_intensity) * s.Ke;
+        Lq.x += c.x; Lq.y += c.y; Lq.z += c.z;
+        p.radiance[path] = Lq;
+        return;
+    }
+    const ObjectDev& ob = sc.objects[s.object];
+    const V3 N = s.N, P = s.P;
+    V3 no, nd, nw = w;
+    bool nshow = show_lights;
+    if (ob.flags & FLAG_MIRROR) {                                    // 413-436
+        nd = reflect(rd, N);
+        no = P + 0.001f * N;
+    } else if (s.transp) {                                           // 438-489
+        float n1 = 1.f, n2 = s.refr_index;
+        V3 Nt = N;
+        bool entering = true;
+        if (dot(rd, N) > 0) { n1 = s.refr_index; n2 = 1; Nt = -N; entering = false; }
+        const float c0 = dot(Nt, rd);
+        const float radical = 1.f - (n1 / n2) * (n1 / n2) * (1.f - c0 * c0);
+        if (radical > 0) {
+            const V3 refr = (n1 / n2) * (rd - dot(rd, Nt) * Nt) - Nt * sqrtf(radical);
+            const float r0 = (n1 - n2) / (n1 + n2);
+            const float R0 = r0 * r0;
+            float R;
+            if (entering) R = R0 + (1 - R0) * powf(1.f + dot(rd, N), 5.f);
+            else R = R0 + (1 - R0) * powf(1.f - dot(refr, N), 5.f);
+            Pcg32 e; e.state = p.rng[path]; e.inc = path_inc(f, path);
+            const float u = pcg32_uniform(e);
+            p.rng[path] = e.state;
+            if (u < R) { no = P + 0.001f * Nt; nd = reflect(rd, N); }
+            else { no = P - 0.001f * Nt; nd = refr; }
+        } else {
+            no = P + 0.001f * Nt; nd = reflect(rd, N);
+        }
+    } else {                                                         // opaque, 490-649
+        Pcg32 e; e.state = p.rng[path]; e.inc = path_inc(f, path);
+        // -- next-event estimation on the spherical light (494-566)
+        const V3 axeOP = fast_normalize(P - sc.centerLight);
+        const float l1 = pcg32_uniform(e);
+        const float l2 = pcg32_uniform(e);
+        const V3 dirl = random_cos(axeOP, l1, l2);
+        const V3 xl = dirl * sc.radiusLight + sc.centerLight;
+        const V3 toL = xl - P;
+        const V3 wi = fast_normalize(toL);
+        const float d2 = norm2(toL);
+        if (!(dot(N, wi) < 0)) {
+            V3 fr;
+            if (ob.brdf == 1) fr = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, wi, -rd, N);
+            else fr = phong_eval(s.Kd, s.Ks, s.Ne, wi, -rd, N);
+            const float J = dot(dirl, -wi) / d2;
+            const float proba = (float)((double)dot(axeOP, dirl) / (PTB_PI_D * (double)(sc.radiusLight * sc.radiusLight)));
+            if (proba > 0.f) {
+                const float g = sc.lightPower * fmaxf(0.f, dot(N, wi)) * J / proba;
+                const V3 c = w * (g * fr);
+                const V3 so = P + 0.01f * wi;
+                out.shadow = true;
+                out.sh_o.x = so.x; out.sh_o.y = so.y; out.sh_o.z = so.z; out.sh_o.w = sqrtf(d2) - 0.01f;
+                out.sh_d.x = wi.x; out.sh_d.y = wi.y; out.sh_d.z = wi.z; out.sh_d.w = u2f((uint32_t)path);
+                out.sh_c.x = c.x; out.sh_c.y = c.y; out.sh_c.z = c.z; out.sh_c.w = 0;
+            } else {
+                // the reference still traces the shadow ray here; its result is unused (counted in stats)
+                out.shadow = false;
+            }
+        }
+        // -- continuation (570-632)
+        const uint32_t pix = p.pixel[path];
+        float sx, sy;
+        extensible_lattice_2d((uint32_t)(f.k0 + (path % f.spp_pass)), sx, sy);
+        const float r1 = frac_pos(f.rpp[2 * pix] + sx);
+        const float r2 = frac_pos(f.rpp[2 * pix + 1] + sy);
+        float pdf;
+        V3 dir;
+        if (ob.brdf == 1) {
+            dir = random_cos(N, r1, r2);
+            pdf = (float)((double)dot(N, dir) / PTB_PI_D);
+        } else {
+            bool diffuse;
+            const float u = pcg32_uniform(e);
+            dir = phong_sample(s.Ks, s.Ne, -rd, N, r1, r2, u, pdf, diffuse);
+        }
+        p.rng[path] = e.state;
+        if (dot(dir, N) < 0 || dot(dir, reflect(rd, N)) < 0 || pdf <= 0) return;
+        V3 fi;
+        if (ob.brdf == 1) fi = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, dir, -rd, N);
+        else fi = phong_eval(s.Kd, s.Ks, s.Ne, dir, -rd, N);
+        nw = (w * fi) * (dot(N, dir) / pdf);
+        no = P + 0.01f * dir;
+        nd = dir;
+        nshow = false;
+    }
+    const int ndepth = depth - 1;
+    // loop-top tests of the next iteration (240-241): depth exhausted or weight below 0.01
+    if (ndepth == 0 || norm2(nw) < 0.01f * 0.01f) return;
+    // NaN weights fall through `<` like the reference; keep tracing them as it does
+    F4 q;
+    q.x = no.x; q.y = no.y; q.z = no.z; q.w = 0; p.ray_o[path] = q;
+    q.x = nd.x; q.y = nd.y; q.z = nd.z; q.w = 0; p.ray_d[path] = q;
+    q.x = nw.x; q.y = nw.y; q.z = nw.z; q.w = u2f(pack_state(ndepth, nshow)); p.weight[path] = q;
+    out.cont = true;
+}
+
+// ---- stage 4: shadow rays -----------------------------------------------------------------------------------
+template <bool COUNT>
+PTB_HD void shadow_one(const SceneDev& sc, PoolDev& p, int entry, TraverseCounters* cnt) {
+    const F4 o = p.sh_o[entry], d = p.sh_d[entry];
+    if (occluded<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, cnt)) return;
+    const uint32_t path = f2u(d.w);
+    const F4 c = p.sh_c[entry];
+    F4 L = p.radiance[path];
+    L.x += c.x; L.y += c.y; L.z += c.z;
+    p.radiance[path] = L;
+}
+
+
+// ---- stage 5: Gaussian splat of a pixel's samples of this pass (Raytracer.cpp:1604-1659) --------------------------
+// ADD(addr, value) adds a float4 {r*w, g*w, b*w, w} into the frame accumulator: red.global.add.v4.f32 on the device.
+template <class ADD>
+PTB_HD void splat_pixel(const FrameDev& f, const PoolDev& p, int ps, F4* accum, ADD add) {
+    int i, j;
+    if (!slot_to_pixel(f, f.slot0 + ps, i, j)) return;
+    int bmin_i, bmax_i, bmin_j, bmax_j;
+    const float ratio = filter_ratio(f.filter, i, j, f.W, f.H, bmin_i, bmax_i, bmin_j, bmax_j);
+    const float denom1 = (float)((double)ratio / ((double)(f.filter.sigma * f.filter.sigma) * 2. * PTB_PI_D));
+    const uint32_t pix = (uint32_t)(i * f.W + j);
+    if (f.filter.size == 1) {
+        F4 acc[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) { acc[q].x = 0; acc[q].y = 0; acc[q].z = 0; acc[q].w = 0; }
+        for (int s = 0; s < f.spp_pass; s++) {
+            Pcg32 e = pcg32_for_sample(pix, (uint32_t)(f.k0 + s), f.seed);
+            const float dx = pcg32_uniform(e) - 0.5f;
+            const float dy = pcg32_uniform(e) - 0.5f;
+            const F4 L = p.radiance[ps * f.spp_pass + s];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    const float w = filter_weight(f.filter, denom1, i + a - 1, j + b - 1, i, j, dx, dy);
+                    F4& c = acc[a * 3 + b];
+                    c.x += L.x * w; c.y += L.y * w; c.z += L.z * w; c.w += w;
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const int i2 = i + a - 1, j2 = j + b - 1;
+                if (i2 < bmin_i || i2 > bmax_i || j2 < bmin_j || j2 > bmax_j) continue;
+                add(accum + ((size_t)(f.H - i2 - 1) * f.W + j2), acc[a * 3 + b]);
+            }
+    } else {
+        for (int s = 0; s < f.spp_pass; s++) {
+            Pcg32 e = pcg32_for_sample(pix, (uint32_t)(f.k0 + s), f.seed);
+            const float dx = pcg32_uniform(e) - 0.5f;
+            const float dy = pcg32_uniform(e) - 0.5f;
+            const F4 L = p.radiance[ps * f.spp_pass + s];
+            for (int i2 = bmin_i; i2 <= bmax_i; i2++)
+                for (int j2 = bmin_j; j2 <= bmax_j; j2++) {
+                    const float w = filter_weight(f.filter, denom1, i2, j2, i, j, dx, dy);
+                    F4 c; c.x = L.x * w; c.y = L.y * w; c.z = L.z * w; c.w = w;
+                    add(accum + ((size_t)(f.H - i2 - 1) * f.W + j2), c);
+                }
+        }
+    }
+}
+
+// ---- resolve: normalise by the weight and tonemap (Raytracer.cpp:1687-1708) ----------------------------------------
+PTB_HD void resolve_pixel(const F4* accum, size_t idx, float gamma, float* imagedouble, float* sample_count, uint8_t* image) {
+    const F4 a = accum[idx];
+    const float r = a.x / a.w, g = a.y / a.w, b = a.z / a.w;
+    if (imagedouble) { imagedouble[idx * 3] = r; imagedouble[idx * 3 + 1] = g; imagedouble[idx * 3 + 2] = b; }
+    if (sample_count) sample_count[idx] = a.w;
+    if (image) {
+        const double ig = (double)(1 / gamma);
+        const float c[3] = {r, g, b};
+        for (int q = 0; q < 3; q++) {
+            double v = 255. * pow((double)c[q] / 196964.7, ig);
+            v = v > 0. ? v : 0.;     // std::max(0., v): NaN -> 0
+            v = v < 255. ? v : 255.;
+            image[idx * 3 + q] = (uint8_t)v;
+        }
+    }
+}
+
+}  // namespace ptb

@@ -1,0 +1,317 @@
+// scene_host.cpp — scene ingestion behind the C-ABI: what the reference does between "a reader filled the
+// arrays" and "the render loop starts", restated for a flat, upload-once device scene.
+//   TriMesh::init        (TriangleMesh.cpp:718-841): axis swap, centre/normalise, rotation centre
+//   TriMesh::setup_tangents (601-711): per-vertex tangents (Lengyel), missing normals -> face normals
+//   Object::build_matrix (Geometry.h:322-360)
+//   Raytracer::prepare_render light constants (Raytracer.cpp:1377-1380)
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "ptb_host.h"
+
+namespace ptb {
+
+static ptb_xform identity_xform() {
+    ptb_xform x;
+    memset(&x, 0, sizeof(x));
+    x.scale = 1.f;
+    x.rotation[0] = x.rotation[4] = x.rotation[8] = 1.f;
+    x.rotation_center[0] = x.rotation_center[1] = x.rotation_center[2] = NAN;
+    return x;
+}
+
+static void take_xform(HostObject& o, const ptb_xform* xf, const float default_center[3]) {
+    o.xf = xf ? *xf : identity_xform();
+    if (o.xf.rotation_center[0] != o.xf.rotation_center[0])
+        for (int k = 0; k < 3; k++) o.xf.rotation_center[k] = default_center[k];
+}
+
+int HostScene::add_sphere(const float O[3], float R, const ptb_xform* xf, int flags) {
+    HostObject o;
+    o.type = OBJ_SPHERE; o.flags = flags;
+    for (int k = 0; k < 3; k++) o.a[k] = O[k];
+    o.R = R;
+    take_xform(o, xf, O);  // Sphere::init: rotation_center = origin (Geometry.h:869)
+    objects.push_back(std::move(o));
+    return (int)objects.size() - 1;
+}
+
+int HostScene::add_plane(const float A[3], const float N[3], const ptb_xform* xf, int flags) {
+    HostObject o;
+    o.type = OBJ_PLANE; o.flags = flags;
+    for (int k = 0; k < 3; k++) { o.a[k] = A[k]; o.n[k] = N[k]; }
+    const float zero[3] = {0, 0, 0};
+    take_xform(o, xf, zero);
+    objects.push_back(std::move(o));
+    return (int)objects.size() - 1;
+}
+
+static inline V3 V(const std::vector<float>& a, int i) { return v3(a[3 * (size_t)i], a[3 * (size_t)i + 1], a[3 * (size_t)i + 2]); }
+
+int HostScene::add_mesh(const ptb_mesh* m, const ptb_xform* xf, int flags, std::string& err) {
+    if (!m || !m->vertices || !m->tri || m->n_tri <= 0 || m->n_vertices <= 0) { err = "add_mesh: empty mesh"; return PTB_ERR_INVALID; }
+    HostObject o;
+    o.type = OBJ_MESH; o.flags = flags;
+    const int nv = m->n_vertices, nn = m->normals ? m->n_normals : 0, nuv = m->uvs ? m->n_uvs : 0, nt = m->n_tri;
+    o.vertices.assign(m->vertices, m->vertices + 3 * (size_t)nv);
+    if (nn) o.normals.assign(m->normals, m->normals + 3 * (size_t)nn);
+    if (nuv) o.uvs.assign(m->uvs, m->uvs + 2 * (size_t)nuv);
+    o.tri.assign(m->tri, m->tri + 10 * (size_t)nt);
+    for (int i = 0; i < nt; i++) {
+        const int32_t* t = &o.tri[10 * (size_t)i];
+        for (int k = 0; k < 3; k++) {
+            if (t[k] < 0 || t[k] >= nv) { err = "add_mesh: vertex index out of range"; return PTB_ERR_INVALID; }
+            if (t[3 + k] >= nuv || t[6 + k] >= nn) { err = "add_mesh: uv/normal index out of range"; return PTB_ERR_INVALID; }
+        }
+    }
+    // (x,y,z) -> (-z,y,x) on vertices and normals (TriangleMesh.cpp:742-751)
+    for (int i = 0; i < nv; i++) { float* v = &o.vertices[3 * (size_t)i]; std::swap(v[0], v[2]); v[0] = -v[0]; }
+    for (int i = 0; i < nn; i++) { float* v = &o.normals[3 * (size_t)i]; std::swap(v[0], v[2]); v[0] = -v[0]; }
+    float lo[3] = {1E9f, 1E9f, 1E9f}, hi[3] = {-1E9f, -1E9f, -1E9f};
+    for (int i = 0; i < nv; i++)
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], o.vertices[3 * (size_t)i + k]); hi[k] = std::max(hi[k], o.vertices[3 * (size_t)i + k]); }
+    if (m->center) {  // 760-770
+        const float s = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+        float c[3];
+        for (int k = 0; k < 3; k++) c[k] = (lo[k] + hi[k]) * 0.5f;
+        for (int i = 0; i < nv; i++)
+            for (int k = 0; k < 3; k++) {
+                float& v = o.vertices[3 * (size_t)i + k];
+                v = (v - c[k]) / s * m->scaling + m->offset[k];
+            }
+    }
+    // bbox over referenced vertices -> default rotation centre (build_bbox 844-860, 831-835)
+    float blo[3], bhi[3];
+    for (int k = 0; k < 3; k++) blo[k] = bhi[k] = o.vertices[3 * (size_t)o.tri[0] + k];
+    for (int i = 0; i < nt; i++)
+        for (int c = 0; c < 3; c++)
+            for (int k = 0; k < 3; k++) {
+                const float v = o.vertices[3 * (size_t)o.tri[10 * (size_t)i + c] + k];
+                blo[k] = std::min(blo[k], v); bhi[k] = std::max(bhi[k], v);
+            }
+    float rc[3];
+    for (int k = 0; k < 3; k++) rc[k] = (blo[k] + bhi[k]) * 0.5f;
+    take_xform(o, xf, rc);
+
+    // ---- setup_tangents (601-711) ----
+    std::vector<V3> tan1(nv, v3(0, 0, 0)), tan2(nv, v3(0, 0, 0));
+    for (int i = 0; i < nt; i++) {
+        const int32_t* t = &o.tri[10 * (size_t)i];
+        if (t[3] == -1 || t[4] == -1 || t[5] == -1) continue;
+        const int a = t[0], b = t[1], c = t[2];
+        const V3 vA = V(o.vertices, b) - V(o.vertices, a), vB = V(o.vertices, c) - V(o.vertices, a);
+        const float sA0 = o.uvs[2 * (size_t)t[4]] - o.uvs[2 * (size_t)t[3]], sA1 = o.uvs[2 * (size_t)t[4] + 1] - o.uvs[2 * (size_t)t[3] + 1];
+        const float sB0 = o.uvs[2 * (size_t)t[5]] - o.uvs[2 * (size_t)t[3]], sB1 = o.uvs[2 * (size_t)t[5] + 1] - o.uvs[2 * (size_t)t[3] + 1];
+        const float det = (sA0 * sB1 - sB0 * sA1);
+        V3 sdir, tdir;
+        if (det != 0) { sdir = (sB1 * vA - sA1 * vB) / det; tdir = (sA0 * vB - sB0 * vA) / det; }
+        else { sdir = vA * 0.00001f; tdir = vB * 0.00001f; }
+        tan1[a] = tan1[a] + sdir; tan1[b] = tan1[b] + sdir; tan1[c] = tan1[c] + sdir;
+        tan2[a] = tan2[a] + tdir; tan2[b] = tan2[b] + tdir; tan2[c] = tan2[c] + tdir;
+    }
+    // missing normal indices -> a fresh face normal (649-668)
+    for (int i = 0; i < nt; i++) {
+        int32_t* t = &o.tri[10 * (size_t)i];
+        if (t[6] != -1 && t[7] != -1 && t[8] != -1) continue;
+        const V3 fn = normalize(cross(V(o.vertices, t[1]) - V(o.vertices, t[0]), V(o.vertices, t[2]) - V(o.vertices, t[0])));
+        o.normals.push_back(fn.x); o.normals.push_back(fn.y); o.normals.push_back(fn.z);
+        const int id = (int)(o.normals.size() / 3) - 1;
+        for (int k = 6; k < 9; k++) if (t[k] == -1) t[k] = id;
+    }
+    std::vector<int> vtn(nv, 0);
+    for (int i = 0; i < nt; i++) { const int32_t* t = &o.tri[10 * (size_t)i]; vtn[t[0]] = t[6]; vtn[t[1]] = t[7]; vtn[t[2]] = t[8]; }
+    o.tangents.resize(3 * (size_t)nv);
+    for (int i = 0; i < nv; i++) {
+        const V3 N = normalize(V(o.normals, vtn[i]));
+        const V3 tg = normalize(tan1[i] - N * dot(tan1[i], N));
+        o.tangents[3 * (size_t)i] = tg.x; o.tangents[3 * (size_t)i + 1] = tg.y; o.tangents[3 * (size_t)i + 2] = tg.z;
+    }
+    if (nn == 0) o.flags |= FLAG_FLAT;  // no vertex normals in the input: face normals (the reference yields NaN here, App. D#12)
+    objects.push_back(std::move(o));
+    return (int)objects.size() - 1;
+}
+
+static void take_tex(HostTex& d, const ptb_tex& s) {
+    for (int k = 0; k < 3; k++) d.mult[k] = s.mult[k];
+    if (s.texels && s.W > 0 && s.H > 0) { d.W = s.W; d.H = s.H; d.texels.assign(s.texels, s.texels + (size_t)s.W * s.H * 3); }
+    else { d.W = d.H = 0; d.texels.clear(); }
+}
+
+int HostScene::set_group_material(int obj, int group, const ptb_material* m, std::string& err) {
+    if (obj < 0 || obj >= (int)objects.size() || group < 0 || !m) { err = "set_group_material: bad object/group"; return PTB_ERR_INVALID; }
+    HostObject& o = objects[obj];
+    if ((int)o.groups.size() <= group) o.groups.resize(group + 1);
+    HostMaterial& g = o.groups[group];
+    g.present |= m->present;
+    if (m->present & PTB_SLOT_KD) take_tex(g.Kd, m->Kd);
+    if (m->present & PTB_SLOT_KS) take_tex(g.Ks, m->Ks);
+    if (m->present & PTB_SLOT_NE) take_tex(g.Ne, m->Ne);
+    if (m->present & PTB_SLOT_TRANSP) take_tex(g.transp, m->transp);
+    if (m->present & PTB_SLOT_REFR) take_tex(g.refr, m->refr);
+    if (m->present & PTB_SLOT_NORMAL) take_tex(g.normal, m->normal);
+    if (m->present & PTB_SLOT_ALPHA) take_tex(g.alpha, m->alpha);
+    return PTB_OK;
+}
+
+void build_matrix(HostObject& o) {
+    const float* m = o.xf.rotation;
+    float mt[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) mt[j * 3 + i] = m[i * 3 + j];
+    const float s = o.xf.scale;
+    const float* tr = o.xf.translation;
+    const float* rc = o.xf.rotation_center;
+    for (int i = 0; i < 3; i++) {
+        float v2[3] = {m[0 * 3 + i], m[1 * 3 + i], m[2 * 3 + i]};
+        o.trans[0 * 4 + i] = v2[0] * s; o.trans[1 * 4 + i] = v2[1] * s; o.trans[2 * 4 + i] = v2[2] * s;
+        o.rot[0 * 3 + i] = v2[0]; o.rot[1 * 3 + i] = v2[1]; o.rot[2 * 3 + i] = v2[2];
+        float w2[3] = {mt[0 * 3 + i], mt[1 * 3 + i], mt[2 * 3 + i]};
+        o.inv_trans[0 * 4 + i] = w2[0] / s; o.inv_trans[1 * 4 + i] = w2[1] / s; o.inv_trans[2 * 4 + i] = w2[2] / s;
+    }
+    auto mul = [](const float* M, const float* b, float* r) {
+        for (int i = 0; i < 3; i++) { float v = 0; for (int j = 0; j < 3; j++) v += M[i * 3 + j] * b[j]; r[i] = v; }
+    };
+    float nrc[3] = {-rc[0], -rc[1], -rc[2]}, v2[3];
+    mul(m, nrc, v2);
+    for (int k = 0; k < 3; k++) o.trans[k * 4 + 3] = v2[k] * s + rc[k] + tr[k];
+    float b[3] = {-rc[0] - tr[0], -rc[1] - tr[1], -rc[2] - tr[2]};
+    mul(mt, b, v2);
+    for (int k = 0; k < 3; k++) o.inv_trans[k * 4 + 3] = v2[k] / s + rc[k];
+}
+
+static TexDev put_tex(const HostTex& t, std::vector<float>& pool) {
+    TexDev d;
+    for (int k = 0; k < 3; k++) d.mult[k] = t.mult[k];
+    d.W = t.W; d.H = t.H; d.offset = 0;
+    if (t.W > 0) { d.offset = (uint32_t)pool.size(); pool.insert(pool.end(), t.texels.begin(), t.texels.end()); }
+    return d;
+}
+
+int HostScene::flatten(FlatScene& out, std::string& err) {
+    if (objects.size() < 2 || objects[0].type != OBJ_SPHERE || objects[1].type != OBJ_SPHERE) {
+        err = "commit: object 0 must be the spherical light and object 1 the environment dome (Raytracer.cpp:1257-1266)";
+        return PTB_ERR_STATE;
+    }
+    out = FlatScene();
+    int64_t n_tri = 0;
+    for (auto& o : objects) {
+        build_matrix(o);
+        ObjectDev d;
+        memset(&d, 0, sizeof(d));
+        d.type = o.type; d.flags = o.flags; d.brdf = o.brdf; d.merl = o.merl;
+        d.mat_base = (int32_t)out.materials.size(); d.n_groups = (int32_t)o.groups.size();
+        for (auto& g : o.groups) {
+            MaterialDev m;
+            memset(&m, 0, sizeof(m));
+            m.present = g.present;
+            m.Kd = put_tex(g.Kd, out.texels); m.Ks = put_tex(g.Ks, out.texels); m.Ne = put_tex(g.Ne, out.texels);
+            m.transp = put_tex(g.transp, out.texels); m.refr = put_tex(g.refr, out.texels);
+            m.normal = put_tex(g.normal, out.texels); m.alpha = put_tex(g.alpha, out.texels);
+            out.materials.push_back(m);
+            d.slot_mask |= (int32_t)g.present;
+        }
+        memcpy(d.trans, o.trans, sizeof(d.trans)); memcpy(d.inv_trans, o.inv_trans, sizeof(d.inv_trans)); memcpy(d.rot, o.rot, sizeof(d.rot));
+        for (int k = 0; k < 3; k++) { d.a[k] = o.a[k]; d.n[k] = o.n[k]; }
+        d.R = o.R; d.R2 = o.R * o.R;
+        out.objects.push_back(d);
+        if (o.type == OBJ_MESH) n_tri += (int64_t)o.tri.size() / 10;
+    }
+    if (out.texels.size() >= (size_t)4294967295u) { err = "commit: texture pool exceeds 2^32 floats"; return PTB_ERR_UNSUPPORTED; }
+    if (out.materials.empty()) out.materials.emplace_back();  // keep pointers valid
+    if (out.texels.empty()) out.texels.push_back(0.f);
+    // light constants (Raytracer.cpp:1377-1380)
+    {
+        const HostObject& L = objects[0];
+        const V3 c = xf_point(L.trans, v3(L.a[0], L.a[1], L.a[2]));
+        out.centerLight[0] = c.x; out.centerLight[1] = c.y; out.centerLight[2] = c.z;
+        out.radiusLight = L.xf.scale * L.R;
+        out.lightPower = intensite_lumiere / (L.xf.scale * L.xf.scale);
+        out.envmap_intensity = envmap_intensity;
+    }
+    out.envmap = envmap; out.envW = envW; out.envH = envH;
+    // MERL tables: channel scales folded in, narrowed exactly like `result[c] = r` (BRDF.h:240-243)
+    for (auto& t : merl_tables) {
+        const double scale[3] = {1.0 / 1500.0, 1.15 / 1500.0, 1.66 / 1500.0};
+        const size_t base = out.merl.size();
+        out.merl.resize(base + 3 * (size_t)PTB_MERL_N);
+        for (int c = 0; c < 3; c++)
+            for (size_t i = 0; i < (size_t)PTB_MERL_N; i++) out.merl[base + c * (size_t)PTB_MERL_N + i] = (float)(t[c * (size_t)PTB_MERL_N + i] * scale[c]);
+    }
+    if (out.merl.empty()) out.merl.push_back(0.f);
+
+    // ---- world-space triangle soup over all meshes ----
+    if (n_tri > 0) {
+        struct Src { int obj; int tri; };
+        std::vector<float> verts9(9 * (size_t)n_tri);
+        std::vector<Src> src(n_tri);
+        int64_t w = 0;
+        for (int oi = 0; oi < (int)objects.size(); oi++) {
+            const HostObject& o = objects[oi];
+            if (o.type != OBJ_MESH) continue;
+            const int nt = (int)(o.tri.size() / 10);
+            for (int i = 0; i < nt; i++, w++) {
+                const int32_t* t = &o.tri[10 * (size_t)i];
+                for (int c = 0; c < 3; c++) {
+                    const V3 p = xf_point(o.trans, V(o.vertices, t[c]));
+                    verts9[9 * (size_t)w + 3 * c] = p.x; verts9[9 * (size_t)w + 3 * c + 1] = p.y; verts9[9 * (size_t)w + 3 * c + 2] = p.z;
+                }
+                src[w].obj = oi; src[w].tri = i;
+            }
+        }
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<uint32_t> order;
+        build_bvh8(verts9.data(), n_tri, out.nodes, order, out.bvh);
+        out.ms_bvh = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        out.tris.resize(3 * (size_t)n_tri); out.tri_uv.resize(n_tri); out.tri_shade.resize(n_tri);
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < n_tri; k++) {
+            const uint32_t in = order[k];
+            const HostObject& o = objects[src[in].obj];
+            const int32_t* t = &o.tri[10 * (size_t)src[in].tri];
+            const float* v = &verts9[9 * (size_t)in];
+            const int group = t[9];
+            const bool uv_all = !o.uvs.empty() && t[3] >= 0 && t[4] >= 0 && t[5] >= 0;
+            const bool has_uv = !o.uvs.empty() && group >= 0 && t[3] >= 0;      // TriangleMesh.cpp:928
+            uint32_t flags = 0;
+            if (uv_all && group >= 0 && group < (int)o.groups.size() && (o.groups[group].present & SLOT_ALPHA)) {
+                const HostTex& a = o.groups[group].alpha;
+                if (a.W > 0 || a.mult[0] < 0.5f) flags |= PTB_TRI_FLAG_ALPHA;  // a constant >= 0.5 can never reject
+            }
+            F4 q;
+            q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = u2f(flags); out.tris[3 * (size_t)k] = q;
+            q.x = v[3] - v[0]; q.y = v[4] - v[1]; q.z = v[5] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 1] = q;
+            q.x = v[6] - v[0]; q.y = v[7] - v[1]; q.z = v[8] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 2] = q;
+            TriUV tu;
+            memset(&tu, 0, sizeof(tu));
+            auto uvc = [&](int idx, float& u, float& vv) {
+                if (idx >= 0 && !o.uvs.empty()) { u = o.uvs[2 * (size_t)idx]; vv = o.uvs[2 * (size_t)idx + 1]; } else { u = 0; vv = 0; }
+            };
+            uvc(t[3], tu.u0, tu.v0); uvc(t[4], tu.u1, tu.v1); uvc(t[5], tu.u2, tu.v2);
+            tu.group = group;
+            tu.object_has_uv = src[in].obj | (has_uv ? (int32_t)0x80000000 : 0);
+            out.tri_uv[k] = tu;
+            TriShade ts;
+            memset(&ts, 0, sizeof(ts));
+            if (o.flags & FLAG_FLAT) {
+                const V3 fn = normalize(cross(V(o.vertices, t[1]) - V(o.vertices, t[0]), V(o.vertices, t[2]) - V(o.vertices, t[0])));
+                for (int c = 0; c < 3; c++) { float* d = c == 0 ? ts.n0 : (c == 1 ? ts.n1 : ts.n2); d[0] = fn.x; d[1] = fn.y; d[2] = fn.z; }
+            } else {
+                for (int c = 0; c < 3; c++) {
+                    float* d = c == 0 ? ts.n0 : (c == 1 ? ts.n1 : ts.n2);
+                    const V3 nn = V(o.normals, t[6 + c]);
+                    d[0] = nn.x; d[1] = nn.y; d[2] = nn.z;
+                }
+            }
+            for (int c = 0; c < 3; c++) {
+                float* d = c == 0 ? ts.t0 : (c == 1 ? ts.t1 : ts.t2);
+                const V3 tg = V(o.tangents, t[c]);
+                d[0] = tg.x; d[1] = tg.y; d[2] = tg.z;
+            }
+            ts.orig = src[in].tri;
+            out.tri_shade[k] = ts;
+        }
+    }
+    return PTB_OK;
+}
+
+}  // namespace ptb

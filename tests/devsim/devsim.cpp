@@ -1,0 +1,168 @@
+// tests/devsim/devsim.cpp — TEST-ONLY host-compiled stepping of the DEVICE code.
+//
+// The CUDA kernels in pathtracer_b200/csrc/ptb_engine.cu are thin wrappers over the PTB_HD per-path
+// functions of ptb_core.h / ptb_bvh8.h / ptb_scene.h.  This file compiles those same headers with g++ and
+// runs the same stage order in plain loops, so the device logic (BVH8 traversal, shading, splat) can be
+// debugged against the oracles in a container without a GPU.  It is NOT part of libptb200.so, is never
+// loaded by the product, and no parity claim rests on it: the `-m gpu` tests run the real kernels.
+#define ORACLE_PREFIX sim_
+#include "../../oracle/prefix.h"
+#include "../../pathtracer_b200/csrc/ptb_host.h"
+
+#include <chrono>
+#include <cstring>
+
+using namespace ptb;
+
+struct ptb_ctx {
+    std::string err;
+    HostScene host;
+    FlatScene flat;
+    SceneDev sc;
+    bool committed = false;
+    bool count = false;
+};
+static std::string g_err;
+
+struct PlainAdd {
+    void operator()(F4* a, const F4& v) const { a->x += v.x; a->y += v.y; a->z += v.z; a->w += v.w; }
+};
+
+extern "C" {
+const char* ptb_version(void) { return "ptb200 devsim (host-stepped device code, test only)"; }
+const char* ptb_last_error(const ptb_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+int ptb_create(int, ptb_ctx** out) { *out = new ptb_ctx(); memset(&(*out)->sc, 0, sizeof(SceneDev)); return PTB_OK; }
+void ptb_destroy(ptb_ctx* c) { delete c; }
+int ptb_add_sphere(ptb_ctx* c, const float O[3], float R, const ptb_xform* xf, int flags, int* id) { int i = c->host.add_sphere(O, R, xf, flags); if (id) *id = i; return PTB_OK; }
+int ptb_add_plane(ptb_ctx* c, const float A[3], const float N[3], const ptb_xform* xf, int flags, int* id) { int i = c->host.add_plane(A, N, xf, flags); if (id) *id = i; return PTB_OK; }
+int ptb_add_mesh(ptb_ctx* c, const ptb_mesh* m, const ptb_xform* xf, int flags, int* id) { int i = c->host.add_mesh(m, xf, flags, c->err); if (i < 0) return i; if (id) *id = i; return PTB_OK; }
+int ptb_set_group_material(ptb_ctx* c, int obj, int group, const ptb_material* m) { return c->host.set_group_material(obj, group, m, c->err); }
+int ptb_set_brdf(ptb_ctx* c, int obj, int kind, int merl) { c->host.objects[obj].brdf = kind; c->host.objects[obj].merl = merl; return PTB_OK; }
+int ptb_add_merl(ptb_ctx* c, const double* t, int* id) { c->host.merl_tables.emplace_back(t, t + 3 * (size_t)PTB_MERL_N); if (id) *id = (int)c->host.merl_tables.size() - 1; return PTB_OK; }
+int ptb_set_envmap(ptb_ctx* c, const uint8_t* rgb, int W, int H) { c->host.envmap.assign(rgb, rgb + (size_t)W * H * 3); c->host.envW = W; c->host.envH = H; return PTB_OK; }
+int ptb_set_light(ptb_ctx* c, float a, float b) { c->host.intensite_lumiere = a; c->host.envmap_intensity = b; return PTB_OK; }
+int ptb_commit(ptb_ctx* c) {
+    int rc = c->host.flatten(c->flat, c->err);
+    if (rc) return rc;
+    FlatScene& f = c->flat; SceneDev& sc = c->sc;
+    sc.nodes = reinterpret_cast<const F4*>(f.nodes.data()); sc.tris = f.tris.data(); sc.tri_uv = f.tri_uv.data(); sc.tri_shade = f.tri_shade.data();
+    sc.objects = f.objects.data(); sc.materials = f.materials.data(); sc.texels = f.texels.data(); sc.envmap = f.envmap.data(); sc.merl = f.merl.data();
+    sc.n_objects = (int)f.objects.size(); sc.has_mesh = f.nodes.empty() ? 0 : 1; sc.envW = f.envW; sc.envH = f.envH; sc.has_envmap = f.envW > 0;
+    sc.envmap_intensity = f.envmap_intensity; sc.lightPower = f.lightPower; sc.radiusLight = f.radiusLight;
+    sc.centerLight = v3(f.centerLight[0], f.centerLight[1], f.centerLight[2]);
+    c->committed = true;
+    return PTB_OK;
+}
+
+int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats) {
+    if (!c->committed) return PTB_ERR_STATE;
+    auto t0 = std::chrono::steady_clock::now();
+    FrameDev f; memset(&f, 0, sizeof(f));
+    camera_setup(f.cam, cam->position, cam->direction, cam->up, cam->fov, cam->focus_distance, cam->aperture, p->W, p->H);
+    filter_setup(f.filter, p->sigma_filter);
+    f.W = p->W; f.H = p->H; f.nb_bounces = p->nb_bounces; f.seed = p->seed;
+    f.tile = p->tile_size > 0 ? p->tile_size : 64;
+    f.tiles_x = (p->W + f.tile - 1) / f.tile; f.tiles_y = (p->H + f.tile - 1) / f.tile;
+    f.shard_count = p->shard_count > 0 ? p->shard_count : 1; f.shard_rank = p->shard_rank;
+    const int total = f.tiles_x * f.tiles_y;
+    f.n_my_tiles = total > f.shard_rank ? (total - f.shard_rank + f.shard_count - 1) / f.shard_count : 0;
+    const size_t npix = (size_t)p->W * p->H;
+    std::vector<float> rpp(2 * npix);
+    for (size_t i = 0; i < npix; i++) random_per_pixel((uint32_t)i, rpp[2 * i], rpp[2 * i + 1]);
+    f.rpp = rpp.data();
+    f.spp_pass = p->nrays; f.k0 = 0; f.slot0 = 0; f.n_pixel_slots = f.n_my_tiles * f.tile * f.tile;
+    const size_t P = (size_t)f.n_pixel_slots * f.spp_pass;
+    std::vector<F4> ray_o(P), ray_d(P), weight(P), radiance(P), hit(P), sh_o(P), sh_d(P), sh_c(P), accum(npix);
+    std::vector<uint64_t> rng(P); std::vector<uint32_t> pixel(P), q0, q1;
+    memset(accum.data(), 0, npix * sizeof(F4));
+    PoolDev pool{ray_o.data(), ray_d.data(), weight.data(), radiance.data(), hit.data(), rng.data(), pixel.data(), sh_o.data(), sh_d.data(), sh_c.data()};
+    unsigned long long closest = 0, shadow = 0, nodes = 0, tris = 0, samples = 0;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)P; i++) raygen_one(f, pool, (int)i);
+    for (size_t i = 0; i < P; i++) if (pixel[i] != 0xffffffffu) { q0.push_back((uint32_t)i); }
+    samples = q0.size();
+    for (int b = 0; b < f.nb_bounces; b++) {
+        closest += q0.size();
+        const long long n = (long long)q0.size();
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, tris)
+        for (long long i = 0; i < n; i++) { TraverseCounters tc{0, 0}; extend_one<true>(c->sc, pool, (int)q0[i], &tc); nodes += tc.nodes; tris += tc.tris; }
+        std::vector<ShadeOut> outs(n);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long long i = 0; i < n; i++) shade_one(c->sc, f, pool, (int)q0[i], outs[i]);
+        q1.clear();
+        size_t ns = 0;
+        for (long long i = 0; i < n; i++) {
+            if (outs[i].cont) q1.push_back(q0[i]);
+            if (outs[i].shadow) { sh_o[ns] = outs[i].sh_o; sh_d[ns] = outs[i].sh_d; sh_c[ns] = outs[i].sh_c; ns++; }
+        }
+        shadow += ns;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, tris)
+        for (long long i = 0; i < (long long)ns; i++) { TraverseCounters tc{0, 0}; shadow_one<true>(c->sc, pool, (int)i, &tc); nodes += tc.nodes; tris += tc.tris; }
+        q0.swap(q1);
+    }
+    for (int ps = 0; ps < f.n_pixel_slots; ps++) splat_pixel(f, pool, ps, accum.data(), PlainAdd());
+    for (size_t i = 0; i < npix; i++) resolve_pixel(accum.data(), i, p->gamma, imagedouble, sample_count, image);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->samples = samples; stats->rays_closest = closest; stats->rays_shadow = shadow; stats->node_visits = nodes; stats->tri_tests = tris;
+        stats->ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return PTB_OK;
+}
+int ptb_render_accum(ptb_ctx*, const ptb_camera*, const ptb_params*, float*, ptb_stats*) { return PTB_ERR_UNSUPPORTED; }
+int ptb_resolve(ptb_ctx*, const float*, int, int, float, float*, float*, uint8_t*) { return PTB_ERR_UNSUPPORTED; }
+int ptb_shard_pack_size(const ptb_params*, int, int64_t*) { return PTB_ERR_UNSUPPORTED; }
+int ptb_shard_pack(ptb_ctx*, const ptb_params*, int, const float*, float*) { return PTB_ERR_UNSUPPORTED; }
+int ptb_shard_unpack_add(ptb_ctx*, const ptb_params*, int, const float*, float*) { return PTB_ERR_UNSUPPORTED; }
+
+int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* obj_id, int32_t* tri_id, float* tout) {
+    if (!c->committed) return PTB_ERR_STATE;
+    CameraDev cd; camera_setup(cd, cam->position, cam->direction, cam->up, cam->fov, cam->focus_distance, cam->aperture, W, H);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int idx = 0; idx < W * H; idx++) {
+        const int i = idx / W, j = idx - i * W;
+        V3 o, d; camera_ray(cd, i, j, 0, 0, 0, 0, o, d);
+        Hit h; int32_t id;
+        extend_ray<false>(c->sc, o, d, h, id, nullptr);
+        int32_t oid = -1, tid = -1;
+        if (id >= 0) { oid = c->sc.tri_uv[id].object_has_uv & 0x7fffffff; tid = c->sc.tri_shade[id].orig; }
+        else if (id != PTB_HIT_MISS) oid = -2 - id;
+        if (obj_id) obj_id[idx] = oid;
+        if (tri_id) tri_id[idx] = tid;
+        if (tout) tout[idx] = id == PTB_HIT_MISS ? -1.f : h.t;
+    }
+    return PTB_OK;
+}
+int ptb_set_option(ptb_ctx*, int, int64_t) { return PTB_OK; }
+int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
+    memset(info, 0, sizeof(*info));
+    info->n_triangles = (int64_t)c->flat.tris.size() / 3; info->n_bvh_nodes = c->flat.bvh.n_nodes; info->bvh_depth = c->flat.bvh.depth;
+    info->bytes_nodes = info->n_bvh_nodes * 80; info->bytes_triangles = info->n_triangles * 48; info->ms_bvh_build = c->flat.ms_bvh;
+    info->n_objects = (int)c->host.objects.size();
+    return PTB_OK;
+}
+int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H, const double* in, int n, int is, double* out, int os) {
+    CameraDev cd; memset(&cd, 0, sizeof(cd));
+    if (cam) camera_setup(cd, cam->position, cam->direction, cam->up, cam->fov, cam->focus_distance, cam->aperture, W, H);
+    FilterDev fd; memset(&fd, 0, sizeof(fd));
+    if (which == PTB_KAT_FILTER_RATIO) filter_setup(fd, (float)in[2]);
+    for (int k = 0; k < n; k++) {
+        const double* a = in + (size_t)k * is; double* o = out + (size_t)k * os;
+        switch (which) {
+        case PTB_KAT_PCG32: { Pcg32 e = pcg32_seed((uint64_t)a[0], (uint64_t)a[1]); for (int q = 0; q < 4; q++) o[q] = (double)pcg32_next(e); } break;
+        case PTB_KAT_LATTICE: { float x, y; extensible_lattice_2d((uint32_t)a[0], x, y); o[0] = x; o[1] = y; } break;
+        case PTB_KAT_CAMERA: { V3 ro, rd; camera_ray(cd, (int)a[0], (int)a[1], (float)a[2], (float)a[3], (float)a[4], (float)a[5], ro, rd); o[0] = ro.x; o[1] = ro.y; o[2] = ro.z; o[3] = rd.x; o[4] = rd.y; o[5] = rd.z; } break;
+        case PTB_KAT_RANDOM_COS: { V3 v = random_cos(v3((float)a[0], (float)a[1], (float)a[2]), (float)a[3], (float)a[4]); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_RANDOM_PHONG: { V3 v = random_phong(v3((float)a[0], (float)a[1], (float)a[2]), (float)a[3], (float)a[4], (float)a[5]); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_PHONG_EVAL: { V3 v = phong_eval(v3((float)a[0], (float)a[1], (float)a[2]), v3((float)a[3], (float)a[4], (float)a[5]), v3((float)a[6], (float)a[7], (float)a[8]), v3((float)a[9], (float)a[10], (float)a[11]), v3((float)a[12], (float)a[13], (float)a[14]), v3((float)a[15], (float)a[16], (float)a[17])); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_MERL_EVAL: { if (!c->committed || c->host.merl_tables.empty()) return PTB_ERR_STATE; V3 v = merl_eval(c->sc.merl, v3((float)a[0], (float)a[1], (float)a[2]), v3((float)a[3], (float)a[4], (float)a[5]), v3((float)a[6], (float)a[7], (float)a[8])); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_FAST_EXP: o[0] = fast_exp(a[0]); break;
+        case PTB_KAT_FAST_NORMALIZE: { V3 v = fast_normalize(v3((float)a[0], (float)a[1], (float)a[2])); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_RANDOM_PER_PIXEL: { float x, y; random_per_pixel((uint32_t)a[0], x, y); o[0] = x; o[1] = y; } break;
+        case PTB_KAT_FILTER_RATIO: { int b0, b1, b2, b3; o[0] = filter_ratio(fd, (int)a[0], (int)a[1], W, H, b0, b1, b2, b3); } break;
+        default: return PTB_ERR_UNSUPPORTED;
+        }
+    }
+    return PTB_OK;
+}
+}

@@ -29,3 +29,13 @@ def port_lib():
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "port"), "-s"])
         _cache["port"] = Lib(ctypes.CDLL(PORT_SO, mode=ctypes.RTLD_LOCAL), "orc_")
     return _cache["port"]
+
+DEVSIM_SO = os.path.join(ROOT, "tests", "devsim", "libptb_devsim.so")
+
+
+def devsim_lib():
+    """tests/devsim: the DEVICE headers compiled for the host (debugging aid, see devsim.cpp)."""
+    if "sim" not in _cache:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "devsim"), "-s"])
+        _cache["sim"] = Lib(ctypes.CDLL(DEVSIM_SO, mode=ctypes.RTLD_LOCAL), "sim_")
+    return _cache["sim"]
