@@ -1,0 +1,1082 @@
+/*
+ * oracle/port/oracle_port.c — TEST INFRASTRUCTURE ONLY.  Plain-C CPU restatement of the reference's
+ * radiance loop (nbonneel/pathtracer), used as the parity checker for the CUDA path and as the
+ * "port" CPU baseline of bench.py.  Nothing in pathtracer_b200/ may link, import or execute it.
+ *
+ * PINNED: this restatement is checked against oracle/_ref (the reference's own sources compiled
+ * headless, oracle/build_ref.py) by tests/test_oracle_pinning.py — function-level known answers are
+ * bit-identical and single-thread images agree bit for bit on the committed scenes — and against the
+ * golden vectors under tests/golden/ generated from oracle/_ref (tests/golden/make_golden.py).
+ *
+ * Every function cites the reference file:line it restates.  Same algorithm, same float/double
+ * evaluation order (C++ overload resolution written out: cosf vs cos, powf vs pow ...), same binary
+ * BVH (TriangleMesh.cpp:1029-1130), same traversal order, same per-(pixel,sample) pcg32 streams that
+ * oracle/build_ref.py patches into the reference copy (DESIGN.md "RNG").  Fog, subsurface, ghost and
+ * background-photo branches are outside the contract (SURVEY.md §8a last row) and are not restated.
+ */
+#define ORACLE_PREFIX orc_
+#include "../prefix.h"
+#include "../../include/ptb200.h"
+
+#include <math.h>
+#include <omp.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+#define M_TWO_PI_REF 6.28318530718 /* Vector.h:16-18 */
+
+typedef struct { float x, y, z; } vec;
+static inline vec V(float x, float y, float z) { vec r = {x, y, z}; return r; }
+static inline vec vadd(vec a, vec b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline vec vsub(vec a, vec b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline vec vneg(vec a) { return V(-a.x, -a.y, -a.z); }
+static inline vec vmul(vec a, vec b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline vec vscale(float s, vec a) { return V(s * a.x, s * a.y, s * a.z); }
+static inline vec vdiv(vec a, float s) { return V(a.x / s, a.y / s, a.z / s); }
+static inline float vdot(vec a, vec b) { return a.x * b.x + a.y * b.y + a.z * b.z; }      /* Vector.h:553-556 */
+static inline float vnorm2(vec a) { return a.x * a.x + a.y * a.y + a.z * a.z; }          /* Vector.h:367-369 */
+static inline vec vcross(vec a, vec b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static inline vec vnormalize(vec a) { float n = sqrtf(vnorm2(a)); return V(a.x / n, a.y / n, a.z / n); } /* Vector.h:371-376 */
+static inline vec vreflect(vec d, vec N) { return vsub(d, vscale(2.f * vdot(d, N), N)); } /* Vector.h:388-391 */
+static inline float vget(vec a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+
+/* Vector.h:294-309 with the 4-byte pun of the author's platform (build_ref.py patch 4) */
+static inline float inv_sq_root(float n) {
+    float y = n;
+    int32_t i;
+    memcpy(&i, &y, 4);
+    i = 0x5f3759df - (i >> 1);
+    memcpy(&y, &i, 4);
+    y = y * (1.5F - ((n * 0.5F) * y * y));
+    y = y * (1.5F - ((n * 0.5F) * y * y));
+    return y;
+}
+static inline vec vfast_normalize(vec a) { float inv = inv_sq_root(vnorm2(a)); return V(a.x * inv, a.y * inv, a.z * inv); } /* Vector.h:376-382 */
+
+/* ---- pcg32 (pcg_random.hpp:1866, 845-873, 484-501, 158-159) ------------------------------------- */
+typedef struct { uint64_t state, inc; } pcg;
+#define PCG_MULT 6364136223846793005ULL
+#define PCG_DEFAULT_INC 1442695040888963407ULL
+static inline pcg pcg_seed2(uint64_t seed, uint64_t stream) { pcg r; r.inc = (stream << 1) | 1ULL; r.state = (seed + r.inc) * PCG_MULT + r.inc; return r; }
+static inline pcg pcg_seed1(uint64_t seed) { pcg r; r.inc = PCG_DEFAULT_INC; r.state = (seed + r.inc) * PCG_MULT + r.inc; return r; }
+static inline uint32_t pcg_next(pcg* r) {
+    uint64_t old = r->state;
+    r->state = old * PCG_MULT + r->inc;
+    uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u), rot = (uint32_t)(old >> 59u);
+    return (xs >> rot) | (xs << ((32u - rot) & 31u));
+}
+static const float INVMAX = 1.f / 4294967296.f; /* 1.f/engine.max(): max() = 2^32-1 rounds to 2^32 as float (Raytracer.h:28) */
+static inline float pcg_unif(pcg* r) { return (float)pcg_next(r) * INVMAX; }
+
+/* ---- Raytracer.cpp:1294-1319 -------------------------------------------------------------------- */
+static double fast_exp(double y) {
+    int32_t hi = (int32_t)(1512775 * y + 1072632447);
+    uint64_t bits = ((uint64_t)(uint32_t)hi) << 32;
+    double d; memcpy(&d, &bits, 8); return d;
+}
+static uint32_t reverse_bits(uint32_t n) {
+    n = (n << 16) | (n >> 16);
+    n = ((n & 0x00ff00ff) << 8) | ((n & 0xff00ff00) >> 8);
+    n = ((n & 0x0f0f0f0f) << 4) | ((n & 0xf0f0f0f0) >> 4);
+    n = ((n & 0x33333333) << 2) | ((n & 0xcccccccc) >> 2);
+    n = ((n & 0x55555555) << 1) | ((n & 0xaaaaaaaa) >> 1);
+    return n;
+}
+static void lattice2d(uint32_t id, float* x, float* y) {
+    uint32_t rid = reverse_bits(id);
+    float phi = (float)(rid * pow(2.0, -32));
+    float tmp;
+    *x = modff((float)(phi * 1 + 0.456789123), &tmp);      /* modf(float,float*) overload: narrowed first */
+    *y = modff((float)(phi * 182667 + 0.123456789), &tmp);
+}
+
+/* ---- Vector.h:566-589, BRDF.h:41-97 ---------------------------------------------------------------- */
+static vec get_tangent(vec N) {
+    float ax = fabsf(N.x), ay = fabsf(N.y), az = fabsf(N.z);
+    vec t;
+    if (ax <= ay && ax <= az) t = V(0, -N.z, N.y);
+    else if (ay <= ax && ay <= az) t = V(-N.z, 0, N.x);
+    else t = V(-N.y, N.x, 0);
+    return vnormalize(t);
+}
+static vec random_cos(vec N, float r1, float r2) {
+    float sr2 = sqrtf(1.f - r2);
+    float twopi = (float)(2. * M_PI);
+    vec l = V(cosf(twopi * r1) * sr2, sinf(twopi * r1) * sr2, sqrtf(r2));
+    vec t1 = get_tangent(N), t2 = vcross(t1, N);
+    return vadd(vadd(vscale(l.z, N), vscale(l.x, t1)), vscale(l.y, t2));
+}
+static vec random_phong(vec R, float n, float r1, float r2) {
+    float facteur = sqrtf(1 - powf(r2, 2.f / (n + 1.f)));
+    vec l = V((float)(cos(2 * M_PI * r1) * facteur), (float)(sin(2 * M_PI * r1) * facteur), (float)pow(r2, 1. / (n + 1)));
+    vec t1 = get_tangent(R), t2 = vcross(t1, R);
+    return vadd(vadd(vscale(l.z, R), vscale(l.x, t1)), vscale(l.y, t2));
+}
+typedef struct { vec shadingN, Kd, Ks, Ne, Ke; int transp; float refr_index; } matvals; /* BRDF.h:7-20 */
+static matvals matvals_default(void) {
+    matvals m; m.shadingN = V(0, 1, 0); m.Kd = V(.5f, .5f, .5f); m.Ne = V(100, 100, 100); m.Ks = V(0, 0, 0); m.Ke = V(0, 0, 0);
+    m.transp = 0; m.refr_index = 1.3f; /* uninitialised in the reference; only read after queryMaterial set them */
+    return m;
+}
+static vec phong_eval(const matvals* m, vec wi, vec wo, vec N) {
+    vec refl = vreflect(vneg(wo), N);
+    float d = vdot(refl, wi);
+    if (d < 0) return vdiv(m->Kd, (float)M_PI);
+    vec lobe = V((float)(powf(d, m->Ne.x) * (m->Ne.x + 2.f) / M_TWO_PI_REF), (float)(powf(d, m->Ne.y) * (m->Ne.y + 2.f) / M_TWO_PI_REF),
+                 (float)(powf(d, m->Ne.z) * (m->Ne.z + 2.f) / M_TWO_PI_REF));
+    return vadd(vdiv(m->Kd, (float)M_PI), vmul(lobe, m->Ks));
+}
+static vec phong_sample(const matvals* m, vec wo, vec N, float* pdf, float r1, float r2, pcg* e) {
+    float avgNe = (m->Ne.x + m->Ne.y + m->Ne.z) / 3.f;
+    float p = 1 - (m->Ks.x + m->Ks.y + m->Ks.z) / 3.f;
+    vec R = vreflect(vneg(wo), N), dir;
+    if (pcg_next(e) / 4294967296.f < p) dir = random_cos(N, r1, r2);
+    else dir = random_phong(R, avgNe, r1, r2);
+    float proba_phong = (float)((avgNe + 1) / (2.f * M_PI) * powf(vdot(R, dir), avgNe));
+    *pdf = (float)(p * vdot(N, dir) / (M_PI) + (1.f - p) * proba_phong);
+    return dir;
+}
+
+/* ---- MERLBRDFRead.cpp:50-207, BRDF.h:204-246 ---------------------------------------------------- */
+static void merl_rotate(const double* v, const double* axis, double angle, double* out) {
+    double c = cos(angle), s = sin(angle), temp;
+    out[0] = v[0] * c; out[1] = v[1] * c; out[2] = v[2] * c;
+    temp = axis[0] * v[0] + axis[1] * v[1] + axis[2] * v[2];
+    temp = temp * (1.0 - c);
+    out[0] += axis[0] * temp; out[1] += axis[1] * temp; out[2] += axis[2] * temp;
+    double cr[3] = {axis[1] * v[2] - axis[2] * v[1], axis[2] * v[0] - axis[0] * v[2], axis[0] * v[1] - axis[1] * v[0]};
+    out[0] += cr[0] * s; out[1] += cr[1] * s; out[2] += cr[2] * s;
+}
+static void dnormalize(double* v) { double len = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); v[0] /= len; v[1] /= len; v[2] /= len; }
+static vec merl_eval(const double* brdf, vec wi, vec wo, vec N) {
+    const double PI = 3.1415926535897932384626433832795;
+    vec t1 = get_tangent(N), t2 = vcross(t1, N);
+    vec wil = V(vdot(wi, t1), vdot(wi, t2), vdot(wi, N)), wol = V(vdot(wo, t1), vdot(wo, t2), vdot(wo, N));
+    float thetai = acosf(wil.z);
+    if (thetai >= M_PI / 2) return V(0, 0, 0);
+    float thetao = acosf(wol.z);
+    if (thetao >= M_PI / 2) return V(0, 0, 0);
+    float phio = atan2f(wol.y, wol.x);
+    if (phio < 0) phio = (float)(phio + 2 * M_PI);
+    float phii = atan2f(wil.y, wil.x);
+    if (phii < 0) phii = (float)(phii + 2 * M_PI);
+    double theta_in = thetai, fi_in = phii, theta_out = thetao, fi_out = phio;
+    double in_z = cos(theta_in), pin = sin(theta_in), in_x = pin * cos(fi_in), in_y = pin * sin(fi_in);
+    double in[3] = {in_x, in_y, in_z};
+    dnormalize(in);
+    double out_z = cos(theta_out), pout = sin(theta_out), out_x = pout * cos(fi_out), out_y = pout * sin(fi_out);
+    double half[3] = {(in_x + out_x) / 2.0f, (in_y + out_y) / 2.0f, (in_z + out_z) / 2.0f};
+    dnormalize(half);
+    double theta_half = acos(half[2]), fi_half = atan2(half[1], half[0]);
+    const double bi_normal[3] = {0.0, 1.0, 0.0}, normal[3] = {0.0, 0.0, 1.0};
+    double temp[3], diff[3];
+    merl_rotate(in, normal, -fi_half, temp);
+    merl_rotate(temp, bi_normal, -theta_half, diff);
+    double theta_diff = acos(diff[2]), fi_diff = atan2(diff[1], diff[0]);
+    int ih, id, ip;
+    if (theta_half <= 0.0) ih = 0;
+    else { double deg = ((theta_half / (PI / 2.0)) * 90); double t = sqrt(deg * 90); ih = (int)t; if (ih < 0) ih = 0; if (ih >= 90) ih = 89; }
+    id = (int)(theta_diff / (PI * 0.5) * 90);
+    if (id < 0) id = 0; else if (id >= 89) id = 89;
+    if (fi_diff < 0.0) fi_diff += PI;
+    ip = (int)(fi_diff / PI * 360 / 2);
+    if (ip < 0) ip = 0; else if (ip >= 179) ip = 179;
+    int ind = ip + id * 360 / 2 + ih * 360 / 2 * 90;
+    double r = brdf[ind] * (1.0 / 1500.0), g = brdf[ind + 90 * 90 * 360 / 2] * (1.15 / 1500.0), b = brdf[ind + 90 * 90 * 360] * (1.66 / 1500.0);
+    return V((float)r, (float)g, (float)b);
+}
+
+/* ---- Texture (BRDF.h:252-426) --------------------------------------------------------------------- */
+typedef struct { float mult[3]; size_t W, H; float* values; } tex;
+typedef struct { tex* t; int n; } slotv; /* std::vector<Texture> */
+enum { S_KD, S_KS, S_NE, S_TRANSP, S_REFR, S_NORMAL, S_ALPHA, S_COUNT };
+static float tex_wrap(float u) { u -= (int)u; if (u < 0) u += 1; return u; }
+static size_t tex_idx(const tex* t, float u, float v) { int x = (int)(u * (t->W - 1)); int y = (int)(v * (t->H - 1)); return (y * t->W + x) * 3; }
+static vec tex_vec(const tex* t, float u, float v) {
+    if (t->W > 0) { size_t i = tex_idx(t, u, v); return V(t->values[i] * t->mult[0], t->values[i + 1] * t->mult[1], t->values[i + 2] * t->mult[2]); }
+    return V(t->mult[0], t->mult[1], t->mult[2]);
+}
+static float tex_red(const tex* t, float u, float v) { if (t->W > 0) return t->values[tex_idx(t, u, v)] * t->mult[0]; return t->mult[0]; }
+static vec tex_normal(const tex* t, float u, float v) {
+    if (t->W > 0) { size_t i = tex_idx(t, u, v); return V(t->values[i], t->values[i + 1], t->values[i + 2]); }
+    return V(0.f, 0.f, 1.f);
+}
+
+/* ---- objects --------------------------------------------------------------------------------------- */
+typedef struct { vec lo, hi; } box;
+typedef struct { int isleaf, fg, fd; box bb; } bnode;                       /* BVHNodesT, TriangleMesh.h:6-13 */
+typedef struct { int vtx[3], uv[3], n[3], group; } tindex;                  /* TriangleIndices, TriangleMesh.h:53-65 */
+typedef struct { vec A, u, v, N; float m11, m12, m22, invdetm; float uvs[3][2]; vec normals[3]; } tsoup; /* Triangle, 67-111 */
+enum { T_MESH, T_SPHERE, T_PLANE };
+typedef struct {
+    int type, miroir, flip_normals, interp_normals, brdf;
+    const double* merl;
+    float scale, rot[9]; vec rc, tr;
+    float trans[12], inv[12], rotm[9];
+    slotv slots[S_COUNT];
+    vec O; float R, R2; int has_envmap; const uint8_t* envtex; int envW, envH;   /* Sphere */
+    vec A, vecN;                                                              /* Plane */
+    int nv, nn, nuv, nt;                                                      /* TriMesh */
+    vec *vertices, *normals; float* uvs; tindex* indices; tsoup* soup; vec* tangent_soup; int* permuted;
+    bnode* nodes; int n_nodes, cap_nodes; box bvh_bbox; int bvh_depth;
+} object;
+
+struct ptb_ctx {
+    object** objs; int n_objs;
+    double** merl; int n_merl;
+    uint8_t* env; int envW, envH;
+    float intensite_lumiere, envmap_intensity;
+    int committed, threads;
+    char err[256];
+    double ms_build; long long n_tri;
+    /* frame state (Raytracer fields) */
+    int W, H, nrays, nb_bounces; float sigma_filter, gamma; uint32_t seed;
+    vec cam_pos, cam_dir, cam_up; float fov, focus_distance, aperture;
+    vec centerLight; float radiusLight, lightPower;
+    int filter_size, filter_total_width; float filter_integral[81];
+    vec* randomPerPixel; int rpp_n;
+};
+static char g_err[256];
+
+/* Object::build_matrix (Geometry.h:322-360) */
+static void build_matrix(object* o) {
+    const float* m = o->rot; float mt[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) mt[j * 3 + i] = m[i * 3 + j];
+    float s = o->scale;
+    for (int i = 0; i < 3; i++) {
+        vec v2 = V(m[0 * 3 + i], m[1 * 3 + i], m[2 * 3 + i]);
+        o->trans[0 * 4 + i] = v2.x * s; o->trans[1 * 4 + i] = v2.y * s; o->trans[2 * 4 + i] = v2.z * s;
+        o->rotm[0 * 3 + i] = v2.x; o->rotm[1 * 3 + i] = v2.y; o->rotm[2 * 3 + i] = v2.z;
+        v2 = V(mt[0 * 3 + i], mt[1 * 3 + i], mt[2 * 3 + i]);
+        o->inv[0 * 4 + i] = v2.x / s; o->inv[1 * 4 + i] = v2.y / s; o->inv[2 * 4 + i] = v2.z / s;
+    }
+    float b[3] = {-o->rc.x, -o->rc.y, -o->rc.z}, r[3];
+    for (int i = 0; i < 3; i++) { float v = 0; for (int j = 0; j < 3; j++) v += m[i * 3 + j] * b[j]; r[i] = v; }
+    o->trans[3] = r[0] * s + o->rc.x + o->tr.x; o->trans[7] = r[1] * s + o->rc.y + o->tr.y; o->trans[11] = r[2] * s + o->rc.z + o->tr.z;
+    vec q = vsub(vneg(o->rc), o->tr);
+    float b2[3] = {q.x, q.y, q.z};
+    for (int i = 0; i < 3; i++) { float v = 0; for (int j = 0; j < 3; j++) v += mt[i * 3 + j] * b2[j]; r[i] = v; }
+    o->inv[3] = r[0] / s + o->rc.x; o->inv[7] = r[1] / s + o->rc.y; o->inv[11] = r[2] / s + o->rc.z;
+}
+static vec xf_point(const float* m, vec v) { return V(m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3], m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7], m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11]); }
+static vec xf_dir(const float* m, vec v) { return V(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); }
+static vec xf_rot(const float* m, vec v) { return V(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z); }
+
+/* Object::queryMaterial (Geometry.h:399-445); idx is compared as size_t in the reference, so -1 selects the defaults */
+static void query_material(const object* o, int idx, float u, float v, matvals* m) {
+    u = tex_wrap(u); v = tex_wrap(v);
+    size_t i = (size_t)idx;
+    if (i >= (size_t)o->slots[S_KD].n) m->Kd = V(1, 1, 1); else m->Kd = tex_vec(&o->slots[S_KD].t[i], u, v);
+    if (i >= (size_t)o->slots[S_KS].n) m->Ks = V(0, 0, 0); else m->Ks = tex_vec(&o->slots[S_KS].t[i], u, v);
+    if (i >= (size_t)o->slots[S_NE].n) m->Ne = V(1, 1, 1); else m->Ne = tex_vec(&o->slots[S_NE].t[i], u, v);
+    if (i >= (size_t)o->slots[S_TRANSP].n) m->transp = 0; else m->transp = tex_red(&o->slots[S_TRANSP].t[i], u, v) < 0.5f;
+    if (i >= (size_t)o->slots[S_REFR].n) m->refr_index = 1.3f; else m->refr_index = tex_red(&o->slots[S_REFR].t[i], u, v);
+    m->Ke = V(0, 0, 0);
+}
+
+/* ---- BBox slab tests (Geometry.h:114-204) ----------------------------------------------------------- */
+typedef struct { vec o, id; } invray;
+static inline float bnd(const box* b, int hi, int k) { return vget(hi ? b->hi : b->lo, k); }
+static int box_invd(const box* b, const invray* r, const char s[3], float* t) { /* 114-141 */
+    float tmax = (bnd(b, s[0], 0) - r->o.x) * r->id.x;
+    if (tmax < 0) return 0;
+    *t = (bnd(b, 1 - s[0], 0) - r->o.x) * r->id.x;
+    float tmaxy = (bnd(b, s[1], 1) - r->o.y) * r->id.y;
+    if (tmaxy < 0) return 0;
+    float tminy = (bnd(b, 1 - s[1], 1) - r->o.y) * r->id.y;
+    if (tminy > tmax || tmaxy < *t) return 0;
+    if (tminy > *t) *t = tminy;
+    if (tmaxy < tmax) tmax = tmaxy;
+    float tmaxz = (bnd(b, s[2], 2) - r->o.z) * r->id.z;
+    if (tmaxz < 0) return 0;
+    float tminz = (bnd(b, 1 - s[2], 2) - r->o.z) * r->id.z;
+    if (*t > tmaxz || tminz > tmax) return 0;
+    if (tminz > *t) *t = tminz;
+    if (*t < 0) *t = 0;
+    return 1;
+}
+static int box_invd_x(const box* b, const invray* r, const char s[3], float* t, int positive) { /* 143-204 */
+    float tmax;
+    if (positive) { tmax = (b->hi.x - r->o.x); if (tmax < 0) return 0; tmax *= r->id.x; *t = (b->lo.x - r->o.x) * r->id.x; }
+    else { tmax = (b->lo.x - r->o.x); if (tmax > 0) return 0; tmax *= r->id.x; *t = (b->hi.x - r->o.x) * r->id.x; }
+    float tmaxy = (bnd(b, s[1], 1) - r->o.y) * r->id.y;
+    if (tmaxy < 0) return 0;
+    float tminy = (bnd(b, 1 - s[1], 1) - r->o.y) * r->id.y;
+    if (tminy > tmax || tmaxy < *t) return 0;
+    if (tminy > *t) *t = tminy;
+    if (tmaxy < tmax) tmax = tmaxy;
+    float tmaxz = (bnd(b, s[2], 2) - r->o.z) * r->id.z;
+    if (tmaxz < 0) return 0;
+    float tminz = (bnd(b, 1 - s[2], 2) - r->o.z) * r->id.z;
+    if (*t > tmaxz || tminz > tmax) return 0;
+    if (tminz > *t) *t = tminz;
+    if (*t < 0) *t = 0;
+    return 1;
+}
+
+/* Triangle ctor + Triangle::intersection (TriangleMesh.h:70-104) */
+static tsoup soup_make(vec A, vec B, vec C) {
+    tsoup s; memset(&s, 0, sizeof(s));
+    s.A = A; s.u = vsub(B, A); s.v = vsub(C, A); s.N = vcross(s.u, s.v);
+    s.m11 = vnorm2(s.u); s.m22 = vnorm2(s.v); s.m12 = vdot(s.u, s.v);
+    s.invdetm = (float)(1. / (s.m11 * s.m22 - s.m12 * s.m12));
+    return s;
+}
+static int soup_hit(const tsoup* s, vec o, vec d, vec* P, float* t, float* alpha, float* beta, float* gamma) {
+    *t = vdot(vsub(s->A, o), s->N) / vdot(d, s->N);
+    if (*t < 0 || *t != *t) return 0;
+    *P = vadd(o, vscale(*t, d));
+    vec w = vsub(*P, s->A);
+    float b11 = vdot(w, s->u), b21 = vdot(w, s->v);
+    float detb = b11 * s->m22 - b21 * s->m12;
+    *beta = detb * s->invdetm;
+    if (*beta < 0) return 0;
+    float detg = b21 * s->m11 - b11 * s->m12;
+    *gamma = detg * s->invdetm;
+    if (*gamma < 0) return 0;
+    *alpha = 1 - *beta - *gamma;
+    if (*alpha < 0) return 0;
+    return 1;
+}
+
+/* ---- binary BVH build (TriangleMesh.cpp:844-885, 1029-1130) ----------------------------------------- */
+static vec vmin3(vec a, vec b) { return V(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y, a.z < b.z ? a.z : b.z); } /* std::min(a,b): b<a?b:a */
+static vec vmax3(vec a, vec b) { return V(a.x < b.x ? b.x : a.x, a.y < b.y ? b.y : a.y, a.z < b.z ? b.z : a.z); }
+static float fminr(float a, float b) { return b < a ? b : a; } /* std::min */
+static float fmaxr(float a, float b) { return a < b ? b : a; } /* std::max */
+static box mesh_bbox(const object* g, int i0, int i1) {
+    box r; r.hi = g->vertices[g->indices[i0].vtx[0]]; r.lo = r.hi;
+    for (int i = i0; i < i1; i++)
+        for (int c = 0; c < 3; c++) { vec p = g->vertices[g->indices[i].vtx[c]]; r.lo = vmin3(r.lo, p); r.hi = vmax3(r.hi, p); }
+    return r;
+}
+static vec tri_center(const object* g, int i) {
+    const tindex* t = &g->indices[i];
+    return vdiv(vadd(vadd(g->vertices[t->vtx[0]], g->vertices[t->vtx[1]]), g->vertices[t->vtx[2]]), 3.f);
+}
+static box centers_bbox(const object* g, int i0, int i1) {
+    box r; r.hi = tri_center(g, i0); r.lo = r.hi;
+    for (int i = i0; i < i1; i++) { vec c = tri_center(g, i); r.lo = vmin3(r.lo, c); r.hi = vmax3(r.hi, c); }
+    return r;
+}
+static float box_area(const box* b) { vec s = vsub(b->hi, b->lo); return 2 * (s.x * s.y + s.x * s.z + s.y * s.z); }
+static float center_dim(const object* g, int i, int d) { /* (a+b+c)/3. : double division, narrowed */
+    const tindex* t = &g->indices[i];
+    return (float)((vget(g->vertices[t->vtx[0]], d) + vget(g->vertices[t->vtx[1]], d) + vget(g->vertices[t->vtx[2]], d)) / 3.);
+}
+static void bvh_recur(object* g, int node, int i0, int i1, int depth) {
+    if (g->n_nodes == g->cap_nodes) { g->cap_nodes *= 2; g->nodes = (bnode*)realloc(g->nodes, sizeof(bnode) * (size_t)g->cap_nodes); }
+    bnode n; n.bb = mesh_bbox(g, i0, i1); n.fg = i0; n.fd = i1; n.isleaf = 1;
+    g->nodes[g->n_nodes++] = n;
+    if (depth > g->bvh_depth) g->bvh_depth = depth;
+    box cb = centers_bbox(g, i0, i1);
+    vec diag = vsub(cb.hi, cb.lo);
+    int dim;
+    if (diag.x >= diag.y && diag.x >= diag.z) dim = 0; else if (diag.y >= diag.x && diag.y >= diag.z) dim = 1; else dim = 2;
+    float best_factor = 0.5f, best_area = INFINITY; /* 1E50 as float */
+    for (int k = 0; k < 16; k++) {
+        float f = (k + 1) / (float)(16 + 1);
+        float split = vget(cb.lo, dim) + vget(diag, dim) * f;
+        box L = {V(1E10f, 1E10f, 1E10f), V(-1E10f, -1E10f, -1E10f)}, Rb = L;
+        int nl = 0, nr = 0;
+        for (int i = i0; i < i1; i++) {
+            float c = center_dim(g, i, dim);
+            const tindex* t = &g->indices[i];
+            box* bb = (c <= split) ? &L : &Rb;
+            for (int q = 0; q < 3; q++) bb->lo = vmin3(bb->lo, g->vertices[t->vtx[q]]);
+            for (int q = 0; q < 3; q++) bb->hi = vmax3(bb->hi, g->vertices[t->vtx[q]]);
+            if (c <= split) nl++; else nr++;
+        }
+        float sum = box_area(&L) * nl + box_area(&Rb) * nr;
+        if (sum < best_area) { best_factor = f; best_area = sum; }
+    }
+    float split = vget(cb.lo, dim) + vget(diag, dim) * best_factor;
+    int pivot = i0 - 1;
+    for (int i = i0; i < i1; i++) {
+        if (center_dim(g, i, dim) <= split) {
+            pivot++;
+            tindex t = g->indices[i]; g->indices[i] = g->indices[pivot]; g->indices[pivot] = t;
+            int p = g->permuted[i]; g->permuted[i] = g->permuted[pivot]; g->permuted[pivot] = p;
+        }
+    }
+    if (pivot < i0 || pivot >= i1 - 1 || i1 <= i0 + 4) return;
+    g->nodes[node].isleaf = 0;
+    g->nodes[node].fg = g->n_nodes;
+    bvh_recur(g, g->nodes[node].fg, i0, pivot + 1, depth + 1);
+    g->nodes[node].fd = g->n_nodes;
+    bvh_recur(g, g->nodes[node].fd, pivot + 1, i1, depth + 1);
+}
+
+/* TriMesh::setup_tangents (TriangleMesh.cpp:601-711) */
+static void setup_tangents(object* g) {
+    vec* tan1 = (vec*)calloc((size_t)g->nv, sizeof(vec));
+    vec* tan2 = (vec*)calloc((size_t)g->nv, sizeof(vec));
+    for (int i = 0; i < g->nt; i++) {
+        const tindex* t = &g->indices[i];
+        if (t->uv[0] == -1 || t->uv[1] == -1 || t->uv[2] == -1) continue;
+        int a = t->vtx[0], b = t->vtx[1], c = t->vtx[2];
+        vec vA = vsub(g->vertices[b], g->vertices[a]), vB = vsub(g->vertices[c], g->vertices[a]);
+        float sA0 = g->uvs[2 * t->uv[1]] - g->uvs[2 * t->uv[0]], sA1 = g->uvs[2 * t->uv[1] + 1] - g->uvs[2 * t->uv[0] + 1];
+        float sB0 = g->uvs[2 * t->uv[2]] - g->uvs[2 * t->uv[0]], sB1 = g->uvs[2 * t->uv[2] + 1] - g->uvs[2 * t->uv[0] + 1];
+        float det = (sA0 * sB1 - sB0 * sA1);
+        vec sdir, tdir;
+        if (det != 0) { sdir = vdiv(vsub(vscale(sB1, vA), vscale(sA1, vB)), det); tdir = vdiv(vsub(vscale(sA0, vB), vscale(sB0, vA)), det); }
+        else { sdir = vscale(0.00001f, vA); tdir = vscale(0.00001f, vB); }
+        tan1[a] = vadd(tan1[a], sdir); tan1[b] = vadd(tan1[b], sdir); tan1[c] = vadd(tan1[c], sdir);
+        tan2[a] = vadd(tan2[a], tdir); tan2[b] = vadd(tan2[b], tdir); tan2[c] = vadd(tan2[c], tdir);
+    }
+    for (int i = 0; i < g->nt; i++) { /* missing normals -> face normal (649-668) */
+        tindex* t = &g->indices[i];
+        if (t->n[0] != -1 && t->n[1] != -1 && t->n[2] != -1) continue;
+        vec fn = vnormalize(vcross(vsub(g->vertices[t->vtx[1]], g->vertices[t->vtx[0]]), vsub(g->vertices[t->vtx[2]], g->vertices[t->vtx[0]])));
+        g->normals = (vec*)realloc(g->normals, sizeof(vec) * (size_t)(g->nn + 1));
+        g->normals[g->nn] = fn;
+        for (int k = 0; k < 3; k++) if (t->n[k] == -1) t->n[k] = g->nn;
+        g->nn++;
+    }
+    int* vtn = (int*)calloc((size_t)g->nv, sizeof(int));
+    for (int i = 0; i < g->nt; i++) for (int k = 0; k < 3; k++) vtn[g->indices[i].vtx[k]] = g->indices[i].n[k];
+    vec* tangents = (vec*)malloc(sizeof(vec) * (size_t)g->nv);
+    for (int i = 0; i < g->nv; i++) {
+        vec N = vnormalize(g->normals[vtn[i]]);
+        tangents[i] = vnormalize(vsub(tan1[i], vscale(vdot(tan1[i], N), N)));
+    }
+    g->tangent_soup = (vec*)malloc(sizeof(vec) * 3 * (size_t)g->nt);
+    for (int i = 0; i < g->nt; i++) for (int k = 0; k < 3; k++) g->tangent_soup[i * 3 + k] = tangents[g->indices[i].vtx[k]];
+    free(tan1); free(tan2); free(vtn); free(tangents);
+}
+
+/* TriMesh::getMaterial (TriangleMesh.cpp:919-1026) */
+static void mesh_material(const object* g, int tri, float alpha, float beta, float gamma, matvals* m) {
+    float u = 0, v = 0;
+    const tindex* t = &g->indices[tri];
+    const tsoup* s = &g->soup[tri];
+    int has_uv = 0;
+    if (g->nuv != 0 && t->group >= 0 && t->uv[0] >= 0 && !(t->uv[0] >= g->nuv)) {
+        u = (s->uvs[0][0] * alpha + s->uvs[1][0] * beta + s->uvs[2][0] * gamma);
+        v = (s->uvs[0][1] * alpha + s->uvs[1][1] * beta + s->uvs[2][1] * gamma);
+        has_uv = 1;
+    }
+    query_material(g, t->group, u, v, m);
+    if (!g->interp_normals || t->n[0] == -1) m->shadingN = s->N;
+    else m->shadingN = vadd(vadd(vscale(alpha, s->normals[0]), vscale(beta, s->normals[1])), vscale(gamma, s->normals[2]));
+    m->shadingN = vnormalize(m->shadingN);
+    if (g->slots[S_NORMAL].n != 0 && has_uv && (size_t)t->group < (size_t)g->slots[S_NORMAL].n) {
+        vec tangent = vadd(vadd(vscale(alpha, g->tangent_soup[tri * 3]), vscale(beta, g->tangent_soup[tri * 3 + 1])), vscale(gamma, g->tangent_soup[tri * 3 + 2]));
+        tangent = vnormalize(tangent);
+        vec bitangent = vcross(m->shadingN, tangent);
+        vec nl = tex_normal(&g->slots[S_NORMAL].t[t->group], u, v);
+        vec Ns = vadd(vadd(vscale(nl.x, tangent), vscale(nl.y, bitangent)), vscale(nl.z, m->shadingN));
+        if (Ns.x == 0. && Ns.y == 0 && Ns.z == 0) Ns = m->shadingN;
+        m->shadingN = vnormalize(Ns);
+    }
+    if (g->flip_normals) m->shadingN = vneg(m->shadingN);
+}
+
+/* alpha test inside traversal (TriangleMesh.cpp:1198-1205) */
+static int alpha_skip(const object* g, int i, float alpha, float beta, float gamma) {
+    const tindex* t = &g->indices[i];
+    int tid = t->group;
+    if (g->nuv > 0 && (size_t)g->slots[S_ALPHA].n > (size_t)tid && t->uv[0] >= 0 && t->uv[1] >= 0 && t->uv[2] >= 0) {
+        float u = g->uvs[2 * t->uv[0]] * alpha + g->uvs[2 * t->uv[1]] * beta + g->uvs[2 * t->uv[2]] * gamma;
+        float v = g->uvs[2 * t->uv[0] + 1] * alpha + g->uvs[2 * t->uv[1] + 1] * beta + g->uvs[2 * t->uv[2] + 1] * gamma;
+        u = tex_wrap(u); v = tex_wrap(v);
+        if (tex_red(&g->slots[S_ALPHA].t[tid], u, v) < 0.5) return 1;
+    }
+    return 0;
+}
+
+/* TriMesh::intersection (TriangleMesh.cpp:1133-1235) / intersection_shadow (1239-1319) */
+static int mesh_hit(const object* g, vec o, vec d, vec* P, float* t, matvals* mat, float cur_best_t, int* tri_id, int shadow, float dist_light) {
+    *t = cur_best_t;
+    int has = 0, best = -1;
+    float tl, tr_, lt, alpha, beta, gamma;
+    vec lp;
+    invray r; r.o = o; r.id = V((float)(1. / d.x), (float)(1. / d.y), (float)(1. / d.z));
+    char s[3] = {(char)(r.id.x >= 0 ? 1 : 0), (char)(r.id.y >= 0 ? 1 : 0), (char)(r.id.z >= 0 ? 1 : 0)};
+    if (!box_invd(&g->bvh_bbox, &r, s, &tl)) return 0;
+    if (tl > cur_best_t || (shadow && tl > dist_light)) return 0;
+    int l[50]; float tn[50]; int top = -1;
+    l[++top] = 0; tn[top] = tl;
+    while (top >= 0) {
+        if (tn[top] > *t) { top--; continue; }
+        int cur = l[top--];
+        int fg = g->nodes[cur].fg, fd = g->nodes[cur].fd;
+        if (!g->nodes[cur].isleaf) {
+            int gl, gr;
+            if (shadow) {
+                gl = box_invd(&g->nodes[fg].bb, &r, s, &tl) && tl < *t && tl < dist_light;
+                gr = box_invd(&g->nodes[fd].bb, &r, s, &tr_) && tr_ < *t && tr_ < dist_light;
+            } else {
+                gl = box_invd_x(&g->nodes[fg].bb, &r, s, &tl, s[0] == 1) && tl < *t;
+                gr = box_invd_x(&g->nodes[fd].bb, &r, s, &tr_, s[0] == 1) && tr_ < *t;
+            }
+            if (gl && gr) {
+                if (tl < tr_) { l[++top] = fd; tn[top] = tr_; l[++top] = fg; tn[top] = tl; }
+                else { l[++top] = fg; tn[top] = tl; l[++top] = fd; tn[top] = tr_; }
+            } else {
+                if (gl) { l[++top] = fg; tn[top] = tl; }
+                if (gr) { l[++top] = fd; tn[top] = tr_; }
+            }
+        } else {
+            for (int i = fg; i < fd; i++) {
+                if (soup_hit(&g->soup[i], o, d, &lp, &lt, &alpha, &beta, &gamma) && lt < *t) {
+                    if (alpha_skip(g, i, alpha, beta, gamma)) continue;
+                    has = 1; best = i; *t = lt;
+                    if (shadow && *t < dist_light * 0.999) return 1;
+                }
+            }
+        }
+    }
+    if (has && !shadow) {
+        *tri_id = best;
+        soup_hit(&g->soup[best], o, d, &lp, &lt, &alpha, &beta, &gamma);
+        if (isnan(alpha) && isnan(beta) && isnan(gamma)) { alpha = 1; beta = 0; gamma = 0; }
+        if (isnan(alpha)) alpha = 0;
+        if (isnan(beta)) beta = 0;
+        if (isnan(gamma)) gamma = 0;
+        if (isinf(alpha)) alpha = 1;
+        if (isinf(beta)) beta = 1;
+        if (isinf(gamma)) gamma = 1;
+        *P = lp;
+        mesh_material(g, best, alpha, beta, gamma, mat);
+    }
+    return has;
+}
+
+/* Sphere::intersection (Geometry.h:918-992) / intersection_shadow (1071-1094) */
+static int sphere_hit(const object* sp, vec o, vec d, vec* P, float* t, matvals* mat, int shadow) {
+    float b = vdot(d, vsub(o, sp->O));
+    float a = vnorm2(d);
+    float c = vnorm2(vsub(o, sp->O)) - sp->R2;
+    float delta = b * b - a * c;
+    if (delta < 0) return 0;
+    float sq = sqrtf(delta);
+    float inva = shadow ? (float)(1. / a) : 1.f / a;
+    float t2 = (-b + sq) * inva;
+    if (t2 < 0) return 0;
+    float t1 = (-b - sq) * inva;
+    *t = t1 > 0 ? t1 : t2;
+    if (shadow) return 1;
+    *P = vadd(o, vscale(*t, d));
+    vec N = vsub(*P, sp->O);
+    if (sp->has_envmap) {
+        N = vfast_normalize(N);
+        float theta = 1.f - acosf(N.y) / (float)M_PI;
+        float phi = (float)((atan2f(-N.z, N.x) + M_PI) / (2.f * (float)M_PI));
+        query_material(sp, 0, theta, phi, mat);
+        mat->shadingN = vneg(N);
+        int idx = 3 * ((int)(theta * (sp->envH - 1.f)) * sp->envW + (int)(phi * (sp->envW - 1.f)));
+        if (idx < 0 || idx >= 3 * sp->envW * sp->envH) mat->Ke = V(0, 0, 0);
+        else mat->Ke = vscale(100000.f / 255.f, V(sp->envtex[idx], sp->envtex[idx + 1], sp->envtex[idx + 2]));
+        return 1;
+    }
+    if (sp->slots[S_KD].n || sp->slots[S_KS].n || sp->slots[S_NE].n || sp->slots[S_TRANSP].n || sp->slots[S_REFR].n) {
+        N = vfast_normalize(N);
+        float theta = 1.f - acosf(N.y) / (float)M_PI;
+        float phi = (atan2f(-N.z, N.x) + (float)M_PI) / (2.f * (float)M_PI);
+        query_material(sp, 0, theta, phi, mat);
+    }
+    mat->shadingN = N;
+    mat->Ke = V(0, 0, 0);
+    if (sp->flip_normals) mat->shadingN = vneg(mat->shadingN);
+    return 1;
+}
+/* Plane::intersection (Geometry.h:1142-1157) / intersection_shadow (1185-1191) */
+static int plane_hit(const object* pl, vec o, vec d, vec* P, float* t, matvals* mat, int shadow) {
+    if (!shadow) mat->shadingN = pl->vecN;
+    float ddot = vdot(d, pl->vecN);
+    if (fabsf(ddot) < 1E-9) return 0;
+    *t = vdot(vsub(pl->A, o), pl->vecN) / ddot;
+    if (*t <= 0.) return 0;
+    if (shadow) return 1;
+    *P = vadd(o, vscale(*t, d));
+    query_material(pl, 0, P->x * 0.1f, P->z * 0.1f, mat);
+    return 1;
+}
+
+/* Scene::intersection (Geometry.cpp:589-688) */
+static int scene_hit(const struct ptb_ctx* c, vec o, vec d, vec* P, int* id, float* min_t, matvals* mat, int* tri_id, unsigned long long* counter) {
+    int has = 0;
+    *min_t = INFINITY; /* 1E99 as float */
+    if (counter) counter[0]++;
+    vec lp; matvals lm = matvals_default(); float t;
+    for (int i = 0; i < c->n_objs; i++) {
+        const object* ob = c->objs[i];
+        vec dl = xf_dir(ob->inv, d), ol = xf_point(ob->inv, o);
+        int h;
+        if (ob->type == T_MESH) h = mesh_hit(ob, ol, dl, &lp, &t, &lm, *min_t, tri_id, 0, 0);
+        else if (ob->type == T_SPHERE) { h = sphere_hit(ob, ol, dl, &lp, &t, &lm, 0); if (h) *tri_id = -1; }
+        else { h = plane_hit(ob, ol, dl, &lp, &t, &lm, 0); if (h) *tri_id = -1; }
+        if (h && t < *min_t) { has = 1; *min_t = t; *P = lp; *id = i; *mat = lm; }
+    }
+    if (has) { *P = xf_point(c->objs[*id]->trans, *P); mat->shadingN = xf_rot(c->objs[*id]->rotm, mat->shadingN); }
+    mat->shadingN = vfast_normalize(mat->shadingN);
+    return has;
+}
+/* Scene::intersection_shadow (Geometry.cpp:691-744) */
+static int scene_shadow(const struct ptb_ctx* c, vec o, vec d, float dist_light, unsigned long long* counter) {
+    float min_t = INFINITY;
+    if (counter) counter[1]++;
+    for (int i = 0; i < c->n_objs; i++) {
+        const object* ob = c->objs[i];
+        vec dl = xf_dir(ob->inv, d), ol = xf_point(ob->inv, o);
+        float t; int h, tid; vec P; matvals m;
+        if (ob->type == T_MESH) h = mesh_hit(ob, ol, dl, &P, &t, &m, min_t, &tid, 1, dist_light);
+        else if (ob->type == T_SPHERE) h = sphere_hit(ob, ol, dl, &P, &t, &m, 1);
+        else h = plane_hit(ob, ol, dl, &P, &t, &m, 1);
+        if (h && t < dist_light * 0.999) return 1;
+    }
+    return 0;
+}
+
+/* Camera::generateDirection (Vector.h:792-825), non-lenticular */
+static void camera_ray(const struct ptb_ctx* c, float init_t, int i, int j, float dxs, float dys, float dxa, float dya, int W, int H, vec* ro, vec* rd) {
+    float k = W / (2 * tanf(c->fov / 2));
+    vec right = vcross(c->cam_dir, c->cam_up);
+    vec dv = V((float)(j - W / 2 + 0.5 + dxs), (float)(i - H / 2 + 0.5 + dys), k);
+    dv = vnormalize(dv);
+    dv = vadd(vadd(vscale(dv.x, right), vscale(dv.y, c->cam_up)), vscale(dv.z, c->cam_dir));
+    vec dest = vadd(c->cam_pos, vscale(c->focus_distance / fabsf(vdot(dv, c->cam_dir)), dv));
+    vec no = vadd(vadd(c->cam_pos, vscale(dxa, right)), vscale(dya, c->cam_up));
+    vec nd = vnormalize(vsub(dest, no));
+    *ro = vadd(no, vdiv(vscale(init_t, nd), vdot(nd, c->cam_dir)));
+    *rd = nd;
+}
+
+/* Raytracer::getColor (Raytracer.cpp:196-664) without fog / subsurface / ghost / background */
+static vec get_color(const struct ptb_ctx* c, vec ro, vec rd, int sampleID, int pix, pcg* e, unsigned long long* counter, const vec* samples2d) {
+    vec color = V(0, 0, 0), w = V(1.f, 1.f, 1.f);
+    int depth = c->nb_bounces, show_lights = 1;
+    for (;;) {
+        if (depth == 0) break;                                      /* 240 */
+        if (vnorm2(w) < 0.01f * 0.01f) break;                       /* 241 */
+        vec P; matvals mat = matvals_default(); int id = -1, tri = -1; float t;
+        int has = scene_hit(c, ro, rd, &P, &id, &t, &mat, &tri, counter);
+        vec N = mat.shadingN;
+        if (!has) break;                                            /* 654-657 */
+        if (id == 1) { color = vadd(color, vmul(vscale(c->envmap_intensity, w), mat.Ke)); break; }          /* 275-301 */
+        if (id == 0) { float lp = show_lights ? c->lightPower : 0.f; color = vadd(color, vmul(w, V(lp, lp, lp))); break; } /* 303-316 */
+        const object* ob = c->objs[id];
+        color = vadd(color, vscale(c->envmap_intensity, vmul(w, mat.Ke)));                                  /* 411 */
+        if (ob->miroir) {                                            /* 413-436 */
+            vec nd = vreflect(rd, N);
+            ro = vadd(P, vscale(0.001f, N)); rd = nd; depth--; continue;
+        }
+        if (mat.transp) {                                            /* 438-489 */
+            float n1 = 1.f, n2 = mat.refr_index; vec Nt = N; int entering = 1;
+            if (vdot(rd, N) > 0) { n1 = mat.refr_index; n2 = 1; Nt = vneg(N); entering = 0; }
+            float c0 = vdot(Nt, rd);
+            float radical = 1.f - (n1 / n2) * (n1 / n2) * (1.f - c0 * c0);
+            vec no, nd;
+            if (radical > 0) {
+                vec refr = vsub(vscale(n1 / n2, vsub(rd, vscale(vdot(rd, Nt), Nt))), vscale(sqrtf(radical), Nt));
+                float r0 = (n1 - n2) / (n1 + n2), R0 = r0 * r0, R;
+                if (entering) R = R0 + (1 - R0) * powf(1.f + vdot(rd, N), 5.f);
+                else R = R0 + (1 - R0) * powf(1.f - vdot(refr, N), 5.f);
+                if (pcg_unif(e) < R) { no = vadd(P, vscale(0.001f, Nt)); nd = vreflect(rd, N); }
+                else { no = vsub(P, vscale(0.001f, Nt)); nd = refr; }
+            } else { no = vadd(P, vscale(0.001f, Nt)); nd = vreflect(rd, N); }
+            ro = no; rd = nd; depth--; continue;
+        }
+        /* opaque: next-event estimation (494-566) */
+        vec axeOP = vfast_normalize(vsub(P, c->centerLight));
+        float l1 = pcg_unif(e), l2 = pcg_unif(e);
+        vec dirl = random_cos(axeOP, l1, l2);
+        vec xl = vadd(vscale(c->radiusLight, dirl), c->centerLight);
+        vec wi = vfast_normalize(vsub(xl, P));
+        float d2 = vnorm2(vsub(xl, P));
+        int shadowed;
+        if (vdot(mat.shadingN, wi) < 0) shadowed = 1;
+        else shadowed = scene_shadow(c, vadd(P, vscale(0.01f, wi)), wi, sqrtf(d2) - 0.01f, counter);
+        vec contrib = V(0, 0, 0);
+        if (!shadowed) {
+            vec fr = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, wi, vneg(rd), N) : phong_eval(&mat, wi, vneg(rd), N);
+            float J = vdot(dirl, vneg(wi)) / d2;
+            float proba = (float)(vdot(axeOP, dirl) / (M_PI * c->radiusLight * c->radiusLight));
+            if (proba > 0.f) contrib = vadd(contrib, vmul(vscale(c->lightPower * fmaxr(0.f, vdot(N, wi)) * J / proba, V(1, 1, 1)), fr));
+        }
+        color = vadd(color, vmul(w, contrib));
+        /* continuation (570-632) */
+        float tmp;
+        float r1 = modff(c->randomPerPixel[pix].x + samples2d[sampleID].x, &tmp);
+        float r2 = modff(c->randomPerPixel[pix].y + samples2d[sampleID].y, &tmp);
+        float pdf; vec dir;
+        if (ob->brdf == PTB_BRDF_MERL) { dir = random_cos(N, r1, r2); pdf = (float)(vdot(N, dir) / (M_PI)); }
+        else dir = phong_sample(&mat, vneg(rd), N, &pdf, r1, r2, e);
+        if (vdot(dir, N) < 0 || vdot(dir, vreflect(rd, N)) < 0 || pdf <= 0) break;
+        vec fi = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, dir, vneg(rd), N) : phong_eval(&mat, dir, vneg(rd), N);
+        w = vscale((vdot(N, dir) / pdf), vmul(vmul(w, V(1, 1, 1)), fi));
+        ro = vadd(P, vscale(0.01f, dir)); rd = dir; depth--; show_lights = 0;
+    }
+    return color;
+}
+
+static float sat(const float* s, int w, int i0, int i1, int j0, int j1) { /* Raytracer.cpp:1276-1291 */
+    float t1 = 0, t2 = 0, t3 = 0;
+    if (i0 > 0) t1 = s[(i0 - 1) * w + j1];
+    if (j0 > 0) t2 = s[i1 * w + j0 - 1];
+    if (i0 > 0 && j0 > 0) t3 = s[(i0 - 1) * w + j0 - 1];
+    return s[i1 * w + j1] - t1 - t2 + t3;
+}
+
+/* Raytracer::prepare_render (Raytracer.cpp:1321-1391) */
+static void prepare_render(struct ptb_ctx* c) {
+    if (c->rpp_n != c->W * c->H) {
+        free(c->randomPerPixel);
+        c->rpp_n = c->W * c->H;
+        c->randomPerPixel = (vec*)malloc(sizeof(vec) * (size_t)c->rpp_n);
+        pcg e0 = pcg_seed1(0);
+        for (int i = 0; i < c->rpp_n; i++) { float a = pcg_unif(&e0); float b = pcg_unif(&e0); c->randomPerPixel[i] = V(a, b, 0); }
+    }
+    float sg = c->sigma_filter;
+    c->filter_size = (int)ceilf(sg * 2);
+    c->filter_total_width = 2 * c->filter_size + 1;
+    int fs = c->filter_size, ftw = c->filter_total_width;
+    for (int i = -fs; i <= fs; i++)
+        for (int j = -fs; j <= fs; j++) {
+            float integ = 0;
+            for (int i2 = -fs; i2 <= i; i2++)
+                for (int j2 = -fs; j2 <= j; j2++) { float w = (float)(fast_exp(-(i2 * i2 + j2 * j2) / (2. * sg * sg)) / (sg * sg * 2. * M_PI)); integ += w; }
+            c->filter_integral[(i + fs) * ftw + (j + fs)] = integ;
+        }
+    for (int i = 0; i < c->n_objs; i++) build_matrix(c->objs[i]);
+    const object* L = c->objs[0];
+    c->centerLight = xf_point(L->trans, L->O);
+    c->radiusLight = L->scale * L->R;
+    c->lightPower = c->intensite_lumiere / (L->scale * L->scale);
+}
+
+/* ---- ABI -------------------------------------------------------------------------------------------- */
+const char* ptb_version(void) { return "ptb-oracle-port (plain C restatement)"; }
+const char* ptb_last_error(const ptb_ctx* c) { return c ? c->err : g_err; }
+int ptb_create(int device_id, ptb_ctx** out) {
+    (void)device_id;
+    if (!out) return PTB_ERR_INVALID;
+    ptb_ctx* c = (ptb_ctx*)calloc(1, sizeof(ptb_ctx));
+    c->envmap_intensity = 1; c->sigma_filter = 0.5f; c->gamma = 2.2f; c->nb_bounces = 5; c->W = c->H = 64; c->nrays = 1;
+    *out = c;
+    return PTB_OK;
+}
+static void free_object(object* o) {
+    for (int s = 0; s < S_COUNT; s++) { for (int i = 0; i < o->slots[s].n; i++) free(o->slots[s].t[i].values); free(o->slots[s].t); }
+    free(o->vertices); free(o->normals); free(o->uvs); free(o->indices); free(o->soup); free(o->tangent_soup); free(o->permuted); free(o->nodes);
+    free(o);
+}
+void ptb_destroy(ptb_ctx* c) {
+    if (!c) return;
+    for (int i = 0; i < c->n_objs; i++) free_object(c->objs[i]);
+    free(c->objs);
+    for (int i = 0; i < c->n_merl; i++) free(c->merl[i]);
+    free(c->merl); free(c->env); free(c->randomPerPixel); free(c);
+}
+static object* new_object(ptb_ctx* c, int type, const ptb_xform* xf, int flags, vec default_rc) {
+    object* o = (object*)calloc(1, sizeof(object));
+    o->type = type; o->miroir = (flags & PTB_OBJ_MIRROR) != 0; o->flip_normals = (flags & PTB_OBJ_FLIP_NORMALS) != 0;
+    o->interp_normals = (flags & PTB_OBJ_FLAT_NORMALS) == 0;
+    o->scale = 1; o->rot[0] = o->rot[4] = o->rot[8] = 1; o->rc = default_rc; o->tr = V(0, 0, 0);
+    if (xf) {
+        o->scale = xf->scale; memcpy(o->rot, xf->rotation, sizeof(o->rot)); o->tr = V(xf->translation[0], xf->translation[1], xf->translation[2]);
+        if (!(xf->rotation_center[0] != xf->rotation_center[0])) o->rc = V(xf->rotation_center[0], xf->rotation_center[1], xf->rotation_center[2]);
+    }
+    c->objs = (object**)realloc(c->objs, sizeof(object*) * (size_t)(c->n_objs + 1));
+    c->objs[c->n_objs++] = o;
+    return o;
+}
+int ptb_add_sphere(ptb_ctx* c, const float O[3], float R, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !O) return PTB_ERR_INVALID;
+    object* o = new_object(c, T_SPHERE, xf, flags, V(O[0], O[1], O[2]));
+    o->O = V(O[0], O[1], O[2]); o->R = R; o->R2 = R * R;
+    if (out_id) *out_id = c->n_objs - 1;
+    return PTB_OK;
+}
+int ptb_add_plane(ptb_ctx* c, const float A[3], const float N[3], const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !A || !N) return PTB_ERR_INVALID;
+    object* o = new_object(c, T_PLANE, xf, flags, V(0, 0, 0));
+    o->A = V(A[0], A[1], A[2]); o->vecN = V(N[0], N[1], N[2]);
+    if (out_id) *out_id = c->n_objs - 1;
+    return PTB_OK;
+}
+/* TriMesh::init (TriangleMesh.cpp:718-841), in-memory route */
+int ptb_add_mesh(ptb_ctx* c, const ptb_mesh* m, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !m || !m->vertices || !m->tri || m->n_tri <= 0) return PTB_ERR_INVALID;
+    struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    object* g = new_object(c, T_MESH, NULL, flags, V(0, 0, 0));
+    g->nv = m->n_vertices; g->nn = m->normals ? m->n_normals : 0; g->nuv = m->uvs ? m->n_uvs : 0; g->nt = m->n_tri;
+    g->vertices = (vec*)malloc(sizeof(vec) * (size_t)g->nv);
+    for (int i = 0; i < g->nv; i++) g->vertices[i] = V(-m->vertices[3 * i + 2], m->vertices[3 * i + 1], m->vertices[3 * i]);   /* 742-746 */
+    g->normals = (vec*)malloc(sizeof(vec) * (size_t)(g->nn + 1));
+    for (int i = 0; i < g->nn; i++) g->normals[i] = V(-m->normals[3 * i + 2], m->normals[3 * i + 1], m->normals[3 * i]);      /* 747-750 */
+    g->uvs = (float*)malloc(sizeof(float) * 2 * (size_t)(g->nuv + 1));
+    if (g->nuv) memcpy(g->uvs, m->uvs, sizeof(float) * 2 * (size_t)g->nuv);
+    g->indices = (tindex*)malloc(sizeof(tindex) * (size_t)g->nt);
+    g->permuted = (int*)malloc(sizeof(int) * (size_t)g->nt);
+    for (int i = 0; i < g->nt; i++) {
+        const int32_t* t = m->tri + 10 * (size_t)i;
+        for (int k = 0; k < 3; k++) { g->indices[i].vtx[k] = t[k]; g->indices[i].uv[k] = t[3 + k]; g->indices[i].n[k] = t[6 + k]; }
+        g->indices[i].group = t[9];
+        g->permuted[i] = i;
+    }
+    box bb = {V(1E9f, 1E9f, 1E9f), V(-1E9f, -1E9f, -1E9f)};
+    for (int i = 0; i < g->nv; i++) {
+        bb.lo = V(fminr(bb.lo.x, g->vertices[i].x), fminr(bb.lo.y, g->vertices[i].y), fminr(bb.lo.z, g->vertices[i].z));
+        bb.hi = V(fmaxr(bb.hi.x, g->vertices[i].x), fmaxr(bb.hi.y, g->vertices[i].y), fmaxr(bb.hi.z, g->vertices[i].z));
+    }
+    if (m->center) {                                                                                                          /* 760-770 */
+        float s = fmaxr(bb.hi.x - bb.lo.x, fmaxr(bb.hi.y - bb.lo.y, bb.hi.z - bb.lo.z));
+        vec cc = vscale(0.5f, vadd(bb.lo, bb.hi));
+        for (int i = 0; i < g->nv; i++) {
+            g->vertices[i].x = (g->vertices[i].x - cc.x) / s * m->scaling + m->offset[0];
+            g->vertices[i].y = (g->vertices[i].y - cc.y) / s * m->scaling + m->offset[1];
+            g->vertices[i].z = (g->vertices[i].z - cc.z) / s * m->scaling + m->offset[2];
+        }
+    }
+    g->bvh_bbox = mesh_bbox(g, 0, g->nt);
+    g->cap_nodes = 1024; g->nodes = (bnode*)malloc(sizeof(bnode) * (size_t)g->cap_nodes); g->n_nodes = 0; g->bvh_depth = 0;
+    bvh_recur(g, 0, 0, g->nt, 0);                                                                                             /* 807-809 */
+    box obb = mesh_bbox(g, 0, g->nt);
+    g->soup = (tsoup*)malloc(sizeof(tsoup) * (size_t)g->nt);                                                                  /* 813-829 */
+    for (int i = 0; i < g->nt; i++) {
+        const tindex* t = &g->indices[i];
+        g->soup[i] = soup_make(g->vertices[t->vtx[0]], g->vertices[t->vtx[1]], g->vertices[t->vtx[2]]);
+        if (g->nn != 0) for (int k = 0; k < 3; k++) g->soup[i].normals[k] = g->normals[t->n[k]];
+        if (g->nuv != 0) for (int k = 0; k < 3; k++) { g->soup[i].uvs[k][0] = g->uvs[2 * t->uv[k]]; g->soup[i].uvs[k][1] = g->uvs[2 * t->uv[k] + 1]; }
+    }
+    g->rc = vscale(0.5f, vadd(obb.lo, obb.hi));                                                                               /* 831-835 */
+    setup_tangents(g);
+    if (xf) {
+        g->scale = xf->scale; memcpy(g->rot, xf->rotation, sizeof(g->rot)); g->tr = V(xf->translation[0], xf->translation[1], xf->translation[2]);
+        if (!(xf->rotation_center[0] != xf->rotation_center[0])) g->rc = V(xf->rotation_center[0], xf->rotation_center[1], xf->rotation_center[2]);
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    c->ms_build += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    c->n_tri += g->nt;
+    if (out_id) *out_id = c->n_objs - 1;
+    return PTB_OK;
+}
+static void put_slot(slotv* s, int group, const ptb_tex* t) {
+    if (s->n <= group) {
+        s->t = (tex*)realloc(s->t, sizeof(tex) * (size_t)(group + 1));
+        for (int i = s->n; i <= group; i++) { tex d; d.mult[0] = d.mult[1] = d.mult[2] = 1; d.W = d.H = 0; d.values = NULL; s->t[i] = d; }  /* Texture() */
+        s->n = group + 1;
+    }
+    tex* d = &s->t[group];
+    free(d->values); d->values = NULL; d->W = d->H = 0;
+    memcpy(d->mult, t->mult, sizeof(d->mult));
+    if (t->texels && t->W > 0 && t->H > 0) {
+        d->W = (size_t)t->W; d->H = (size_t)t->H;
+        d->values = (float*)malloc(sizeof(float) * 3 * d->W * d->H);
+        memcpy(d->values, t->texels, sizeof(float) * 3 * d->W * d->H);
+    }
+}
+int ptb_set_group_material(ptb_ctx* c, int obj, int group, const ptb_material* m) {
+    if (!c || !m || obj < 0 || obj >= c->n_objs || group < 0) return PTB_ERR_INVALID;
+    object* o = c->objs[obj];
+    if (m->present & PTB_SLOT_KD) put_slot(&o->slots[S_KD], group, &m->Kd);
+    if (m->present & PTB_SLOT_KS) put_slot(&o->slots[S_KS], group, &m->Ks);
+    if (m->present & PTB_SLOT_NE) put_slot(&o->slots[S_NE], group, &m->Ne);
+    if (m->present & PTB_SLOT_TRANSP) put_slot(&o->slots[S_TRANSP], group, &m->transp);
+    if (m->present & PTB_SLOT_REFR) put_slot(&o->slots[S_REFR], group, &m->refr);
+    if (m->present & PTB_SLOT_NORMAL) put_slot(&o->slots[S_NORMAL], group, &m->normal);
+    if (m->present & PTB_SLOT_ALPHA) put_slot(&o->slots[S_ALPHA], group, &m->alpha);
+    return PTB_OK;
+}
+int ptb_add_merl(ptb_ctx* c, const double* table, int* out_id) {
+    if (!c || !table) return PTB_ERR_INVALID;
+    size_t n = (size_t)3 * 90 * 90 * 180;
+    c->merl = (double**)realloc(c->merl, sizeof(double*) * (size_t)(c->n_merl + 1));
+    c->merl[c->n_merl] = (double*)malloc(n * sizeof(double));
+    memcpy(c->merl[c->n_merl], table, n * sizeof(double));
+    if (out_id) *out_id = c->n_merl;
+    c->n_merl++;
+    return PTB_OK;
+}
+int ptb_set_brdf(ptb_ctx* c, int obj, int kind, int merl_id) {
+    if (!c || obj < 0 || obj >= c->n_objs) return PTB_ERR_INVALID;
+    if (kind == PTB_BRDF_MERL) { if (merl_id < 0 || merl_id >= c->n_merl) return PTB_ERR_INVALID; c->objs[obj]->merl = c->merl[merl_id]; }
+    else if (kind != PTB_BRDF_PHONG) return PTB_ERR_UNSUPPORTED;
+    c->objs[obj]->brdf = kind;
+    return PTB_OK;
+}
+int ptb_set_envmap(ptb_ctx* c, const uint8_t* rgb, int W, int H) {
+    if (!c || c->n_objs < 2 || c->objs[1]->type != T_SPHERE) return PTB_ERR_STATE;
+    free(c->env); c->env = NULL;
+    object* dome = c->objs[1];
+    if (!rgb || W <= 0 || H <= 0) { dome->has_envmap = 0; return PTB_OK; }
+    c->env = (uint8_t*)malloc((size_t)W * H * 3);
+    memcpy(c->env, rgb, (size_t)W * H * 3);
+    dome->envtex = c->env; dome->envW = W; dome->envH = H; dome->has_envmap = 1;
+    return PTB_OK;
+}
+int ptb_set_light(ptb_ctx* c, float il, float ei) { if (!c) return PTB_ERR_INVALID; c->intensite_lumiere = il; c->envmap_intensity = ei; return PTB_OK; }
+int ptb_commit(ptb_ctx* c) {
+    if (!c) return PTB_ERR_INVALID;
+    if (c->n_objs < 2 || c->objs[0]->type != T_SPHERE || c->objs[1]->type != T_SPHERE) { snprintf(c->err, sizeof(c->err), "need light (id 0) and dome (id 1)"); return PTB_ERR_STATE; }
+    c->committed = 1;
+    return PTB_OK;
+}
+static int set_frame(ptb_ctx* c, const ptb_camera* cam, int W, int H) {
+    c->cam_pos = V(cam->position[0], cam->position[1], cam->position[2]);
+    c->cam_dir = V(cam->direction[0], cam->direction[1], cam->direction[2]);
+    c->cam_up = V(cam->up[0], cam->up[1], cam->up[2]);
+    c->fov = cam->fov; c->focus_distance = cam->focus_distance; c->aperture = cam->aperture;
+    c->W = W; c->H = H;
+    return PTB_OK;
+}
+
+/* Raytracer::render_image_nopreviz (Raytracer.cpp:1565-1708) with the per-(pixel,sample) streams of build_ref.py patch 5 */
+int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats) {
+    if (!c || !cam || !p || p->W <= 0 || p->H <= 0 || p->nrays <= 0) return PTB_ERR_INVALID;
+    if (!c->committed) return PTB_ERR_STATE;
+    if (p->shard_count > 1) return PTB_ERR_UNSUPPORTED;
+    set_frame(c, cam, p->W, p->H);
+    c->nrays = p->nrays; c->nb_bounces = p->nb_bounces; c->sigma_filter = p->sigma_filter; c->gamma = p->gamma; c->seed = p->seed;
+    if ((int)ceilf(c->sigma_filter * 2) > 4) return PTB_ERR_UNSUPPORTED;
+    int nt = c->threads > 0 ? c->threads : omp_get_num_procs();
+    if (nt > 64) nt = 64;
+    struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    prepare_render(c);
+    const int W = c->W, H = c->H, nrays = c->nrays, fs = c->filter_size, ftw = c->filter_total_width;
+    vec* samples2d = (vec*)malloc(sizeof(vec) * (size_t)nrays);
+    for (int i = 0; i < nrays; i++) { float x, y; lattice2d((uint32_t)i, &x, &y); samples2d[i] = V(x, y, 0); }
+    float denom2 = 1.f / (2.f * c->sigma_filter * c->sigma_filter);
+    const int bw = 4, bh = 4;
+    const int nbx = (int)ceilf(W / (float)bw), nby = (int)ceilf(H / (float)bh);
+    size_t npix = (size_t)W * H;
+    float* img_t = (float*)calloc(npix * 3 * (size_t)nt, sizeof(float));
+    float* cnt_t = (float*)calloc(npix * (size_t)nt, sizeof(float));
+    unsigned long long counters[64][8];
+    memset(counters, 0, sizeof(counters));
+#pragma omp parallel num_threads(nt)
+    {
+        int th = omp_get_thread_num();
+        float* img = img_t + (size_t)th * npix * 3;
+        float* cnt = cnt_t + (size_t)th * npix;
+#pragma omp for schedule(dynamic, 1)
+        for (int batch = 0; batch < nbx * nby; batch++) {
+            int bi = batch / nbx, bj = batch % nbx;
+            int bW = (W < bj * bw + bw ? W : bj * bw + bw) - bj * bw, bH = (H < bi * bh + bh ? H : bi * bh + bh) - bi * bh;
+            for (int id = 0; id < bW * bH; id++) {
+                int i = bi * bh + id / bW, j = bj * bw + id % bW;
+                int bmin_i = i - fs > 0 ? i - fs : 0, bmax_i = i + fs < H - 1 ? i + fs : H - 1;
+                int bmin_j = j - fs > 0 ? j - fs : 0, bmax_j = j + fs < W - 1 ? j + fs : W - 1;
+                float ratio = 1.f / sat(c->filter_integral, ftw, bmin_i - i + fs, bmax_i - i + fs, bmin_j - j + fs, bmax_j - j + fs);
+                float denom1 = (float)(ratio / (c->sigma_filter * c->sigma_filter * 2. * M_PI));
+                for (int k = 0; k < nrays; k++) {
+                    pcg e = pcg_seed2((uint64_t)(i * W + j), (uint64_t)k ^ ((uint64_t)c->seed << 32));
+                    float dx = pcg_unif(&e) - 0.5f, dy = pcg_unif(&e) - 0.5f;
+                    float dxa = (pcg_unif(&e) - 0.5f) * c->aperture, dya = (pcg_unif(&e) - 0.5f) * c->aperture;
+                    vec ro, rd;
+                    camera_ray(c, 0.f, i, j, dx, dy, dxa, dya, W, H, &ro, &rd);
+                    vec col = get_color(c, ro, rd, k, i * W + j, &e, counters[th], samples2d);
+                    for (int i2 = bmin_i; i2 <= bmax_i; i2++)
+                        for (int j2 = bmin_j; j2 <= bmax_j; j2++) {
+                            size_t idx = ((size_t)(H - i2 - 1) * W + j2) * 3;
+                            float a = (i2 - i - dy), b = (j2 - j - dx);
+                            float w = (float)(fast_exp(-(a * a + b * b) * denom2) * denom1);
+                            img[idx] += col.x * w; img[idx + 1] += col.y * w; img[idx + 2] += col.z * w;
+                            cnt[(size_t)(H - i2 - 1) * W + j2] += w;
+                        }
+                }
+            }
+        }
+    }
+    float* acc = (float*)calloc(npix * 3, sizeof(float));
+    float* sc = (float*)calloc(npix, sizeof(float));
+    for (int th = 0; th < nt; th++)
+        for (size_t i = 0; i < npix; i++) {
+            acc[i * 3] += img_t[(size_t)th * npix * 3 + i * 3]; acc[i * 3 + 1] += img_t[(size_t)th * npix * 3 + i * 3 + 1];
+            acc[i * 3 + 2] += img_t[(size_t)th * npix * 3 + i * 3 + 2]; sc[i] += cnt_t[(size_t)th * npix + i];
+        }
+    for (size_t i = 0; i < npix; i++) for (int q = 0; q < 3; q++) acc[i * 3 + q] /= sc[i];
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (imagedouble) memcpy(imagedouble, acc, npix * 3 * sizeof(float));
+    if (sample_count) memcpy(sample_count, sc, npix * sizeof(float));
+    if (image)
+        for (size_t i = 0; i < npix * 3; i++) {
+            double v = 255. * pow(acc[i] / 196964.7, 1 / c->gamma);
+            v = v > 0. ? v : 0.; v = v < 255. ? v : 255.;
+            image[i] = (uint8_t)v;
+        }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->samples = (uint64_t)npix * (uint64_t)nrays;
+        for (int th = 0; th < 64; th++) { stats->rays_closest += counters[th][0]; stats->rays_shadow += counters[th][1]; }
+        stats->ms_wall = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    }
+    free(acc); free(sc); free(img_t); free(cnt_t); free(samples2d);
+    return PTB_OK;
+}
+int ptb_render_accum(ptb_ctx* c, const ptb_camera* a, const ptb_params* b, float* d, ptb_stats* s) { (void)c; (void)a; (void)b; (void)d; (void)s; return PTB_ERR_UNSUPPORTED; }
+int ptb_resolve(ptb_ctx* c, const float* d, int W, int H, float g, float* a, float* b, uint8_t* e) { (void)c; (void)d; (void)W; (void)H; (void)g; (void)a; (void)b; (void)e; return PTB_ERR_UNSUPPORTED; }
+int ptb_shard_pack_size(const ptb_params* p, int r, int64_t* o) { (void)p; (void)r; (void)o; return PTB_ERR_UNSUPPORTED; }
+int ptb_shard_pack(ptb_ctx* c, const ptb_params* p, int r, const float* a, float* b) { (void)c; (void)p; (void)r; (void)a; (void)b; return PTB_ERR_UNSUPPORTED; }
+int ptb_shard_unpack_add(ptb_ctx* c, const ptb_params* p, int r, const float* a, float* b) { (void)c; (void)p; (void)r; (void)a; (void)b; return PTB_ERR_UNSUPPORTED; }
+
+/* the picking query (mainApp.h:686-692) */
+int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* obj_id, int32_t* tri_id, float* tout) {
+    if (!c || !cam || W <= 0 || H <= 0) return PTB_ERR_INVALID;
+    if (!c->committed) return PTB_ERR_STATE;
+    set_frame(c, cam, W, H);
+    for (int i = 0; i < c->n_objs; i++) build_matrix(c->objs[i]);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int i = 0; i < H; i++)
+        for (int j = 0; j < W; j++) {
+            vec ro, rd, P; matvals m = matvals_default(); int id = -1, tri = -1; float t;
+            camera_ray(c, 0, i, j, 0, 0, 0, 0, W, H, &ro, &rd);
+            int hit = scene_hit(c, ro, rd, &P, &id, &t, &m, &tri, NULL);
+            int32_t oid = -1, tid = -1;
+            if (hit) { oid = id; if (c->objs[id]->type == T_MESH && tri >= 0) tid = c->objs[id]->permuted[tri]; }
+            if (obj_id) obj_id[(size_t)i * W + j] = oid;
+            if (tri_id) tri_id[(size_t)i * W + j] = tid;
+            if (tout) tout[(size_t)i * W + j] = hit ? t : -1.f;
+        }
+    return PTB_OK;
+}
+int ptb_set_option(ptb_ctx* c, int option, int64_t value) { if (!c) return PTB_ERR_INVALID; if (option == ORC_OPT_THREADS) c->threads = (int)value; return PTB_OK; }
+int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
+    if (!c || !info) return PTB_ERR_INVALID;
+    memset(info, 0, sizeof(*info));
+    info->n_triangles = c->n_tri; info->n_objects = c->n_objs; info->ms_bvh_build = c->ms_build;
+    for (int i = 0; i < c->n_objs; i++) if (c->objs[i]->type == T_MESH) { info->n_bvh_nodes += c->objs[i]->n_nodes; if (c->objs[i]->bvh_depth > info->bvh_depth) info->bvh_depth = c->objs[i]->bvh_depth; }
+    info->bytes_nodes = info->n_bvh_nodes * (int64_t)sizeof(bnode); info->bytes_triangles = info->n_triangles * (int64_t)sizeof(tsoup);
+    return PTB_OK;
+}
+int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H, const double* in, int n, int is, double* out, int os) {
+    if (!c || !in || !out) return PTB_ERR_INVALID;
+    if (cam) set_frame(c, cam, W, H);
+    if (which == PTB_KAT_RANDOM_PER_PIXEL || which == PTB_KAT_FILTER_RATIO) {
+        if (!c->committed) return PTB_ERR_STATE;
+        c->W = W; c->H = H;
+        if (which == PTB_KAT_FILTER_RATIO) c->sigma_filter = (float)in[2];
+        prepare_render(c);
+    }
+    for (int k = 0; k < n; k++) {
+        const double* a = in + (size_t)k * is; double* o = out + (size_t)k * os;
+        switch (which) {
+        case PTB_KAT_PCG32: { pcg e = pcg_seed2((uint64_t)a[0], (uint64_t)a[1]); for (int q = 0; q < 4; q++) o[q] = (double)pcg_next(&e); } break;
+        case PTB_KAT_LATTICE: { float x, y; lattice2d((uint32_t)a[0], &x, &y); o[0] = x; o[1] = y; } break;
+        case PTB_KAT_CAMERA: { vec ro, rd; camera_ray(c, 0, (int)a[0], (int)a[1], (float)a[2], (float)a[3], (float)a[4], (float)a[5], W, H, &ro, &rd);
+            o[0] = ro.x; o[1] = ro.y; o[2] = ro.z; o[3] = rd.x; o[4] = rd.y; o[5] = rd.z; } break;
+        case PTB_KAT_RANDOM_COS: { vec v = random_cos(V((float)a[0], (float)a[1], (float)a[2]), (float)a[3], (float)a[4]); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_RANDOM_PHONG: { vec v = random_phong(V((float)a[0], (float)a[1], (float)a[2]), (float)a[3], (float)a[4], (float)a[5]); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_PHONG_EVAL: { matvals m = matvals_default(); m.Kd = V((float)a[0], (float)a[1], (float)a[2]); m.Ks = V((float)a[3], (float)a[4], (float)a[5]); m.Ne = V((float)a[6], (float)a[7], (float)a[8]);
+            vec v = phong_eval(&m, V((float)a[9], (float)a[10], (float)a[11]), V((float)a[12], (float)a[13], (float)a[14]), V((float)a[15], (float)a[16], (float)a[17])); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_MERL_EVAL: { if (c->n_merl == 0) return PTB_ERR_STATE;
+            vec v = merl_eval(c->merl[0], V((float)a[0], (float)a[1], (float)a[2]), V((float)a[3], (float)a[4], (float)a[5]), V((float)a[6], (float)a[7], (float)a[8])); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_FAST_EXP: o[0] = fast_exp(a[0]); break;
+        case PTB_KAT_FAST_NORMALIZE: { vec v = vfast_normalize(V((float)a[0], (float)a[1], (float)a[2])); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
+        case PTB_KAT_RANDOM_PER_PIXEL: { size_t p = (size_t)a[0]; o[0] = c->randomPerPixel[p].x; o[1] = c->randomPerPixel[p].y; } break;
+        case PTB_KAT_FILTER_RATIO: { int i = (int)a[0], j = (int)a[1], fs = c->filter_size, ftw = c->filter_total_width;
+            int bmin_i = i - fs > 0 ? i - fs : 0, bmax_i = i + fs < H - 1 ? i + fs : H - 1, bmin_j = j - fs > 0 ? j - fs : 0, bmax_j = j + fs < W - 1 ? j + fs : W - 1;
+            o[0] = 1.f / sat(c->filter_integral, ftw, bmin_i - i + fs, bmax_i - i + fs, bmin_j - j + fs, bmax_j - j + fs); } break;
+        default: return PTB_ERR_UNSUPPORTED;
+        }
+    }
+    return PTB_OK;
+}
