@@ -216,7 +216,7 @@ class Raytracer:
                     L.check(L.add_merl(ctx, tab.ctypes.data_as(C.POINTER(C.c_double)), C.byref(mid)), ctx)
                     merl_ids[key] = mid.value
                 L.check(L.set_brdf(ctx, oid.value, _abi.BRDF_MERL, merl_ids[key]), ctx)
-        dome = self.s.objects[1]
+        dome = self.s.objects[1] if len(self.s.objects) > 1 else None
         if getattr(dome, "envmap", None) is not None:
             env = np.ascontiguousarray(dome.envmap, np.uint8)
             L.check(L.set_envmap(ctx, env.ctypes.data_as(C.POINTER(C.c_uint8)), env.shape[1], env.shape[0]), ctx)

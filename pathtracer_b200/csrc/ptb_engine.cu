@@ -168,8 +168,10 @@ __global__ void __launch_bounds__(256) k_shard_pack(const F4* rgbw, F4* packed, 
     const int i = ty * tile - apron + r / side, j = tx * tile - apron + r % side;
     const bool inside = i >= 0 && i < H && j >= 0 && j < W;
     if (!unpack) {
+        const int tiles_y = (H + tile - 1) / tile;
+        const bool send = shard_block_sends(tile_id, i, j, W, H, tile, apron, tiles_x, tiles_y, rank, count);
         F4 z; z.x = z.y = z.z = z.w = 0;
-        packed[idx] = inside ? rgbw[(size_t)(H - 1 - i) * W + j] : z;
+        packed[idx] = send ? rgbw[(size_t)(H - 1 - i) * W + j] : z;
     } else if (inside) {
         const F4 v = packed[idx];
         if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) RedAddV4()(const_cast<F4*>(rgbw) + (size_t)(H - 1 - i) * W + j, v);

@@ -303,6 +303,25 @@ PTB_HD bool slot_to_pixel(const FrameDev& f, int slot, int& i, int& j) {
     return i < f.H && j < f.W;
 }
 
+// Tile gather: does own tile `tile_id` carry frame pixel (i,j) in its (tile + apron) block?  Every pixel a shard
+// touched must travel exactly once: inside an own tile it goes with that tile; in a foreign tile it goes with the
+// lowest-numbered own tile whose apron covers it (two own tiles can flank the same foreign pixel).
+PTB_HD bool shard_block_sends(int tile_id, int i, int j, int W, int H, int tile, int apron, int tiles_x, int tiles_y, int rank, int count) {
+    if (i < 0 || i >= H || j < 0 || j >= W) return false;
+    const int pty = i / tile, ptx = j / tile;
+    const int pid = pty * tiles_x + ptx;
+    if (pid % count == rank) return pid == tile_id;
+    for (int ty = pty - 1; ty <= pty + 1; ty++)
+        for (int tx = ptx - 1; tx <= ptx + 1; tx++) {
+            if (ty < 0 || ty >= tiles_y || tx < 0 || tx >= tiles_x) continue;
+            const int id = ty * tiles_x + tx;
+            if (id % count != rank) continue;
+            if (i < ty * tile - apron || i >= ty * tile + tile + apron || j < tx * tile - apron || j >= tx * tile + tile + apron) continue;
+            return id == tile_id;   // ids ascend in this scan order: the first covering own tile is the lowest
+        }
+    return false;
+}
+
 PTB_HD uint64_t path_inc(const FrameDev& f, int path) {  // pcg32 stream increment of the path's (pixel,sample) stream
     return (((uint64_t)(uint32_t)(f.k0 + (path % f.spp_pass)) ^ ((uint64_t)f.seed << 32)) << 1) | 1ULL;
 }

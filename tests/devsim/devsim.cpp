@@ -54,7 +54,7 @@ int ptb_commit(ptb_ctx* c) {
     return PTB_OK;
 }
 
-int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats) {
+static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F4* accum_out, ptb_stats* stats) {
     if (!c->committed) return PTB_ERR_STATE;
     auto t0 = std::chrono::steady_clock::now();
     FrameDev f; memset(&f, 0, sizeof(f));
@@ -72,9 +72,8 @@ int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* im
     f.rpp = rpp.data();
     f.spp_pass = p->nrays; f.k0 = 0; f.slot0 = 0; f.n_pixel_slots = f.n_my_tiles * f.tile * f.tile;
     const size_t P = (size_t)f.n_pixel_slots * f.spp_pass;
-    std::vector<F4> ray_o(P), ray_d(P), weight(P), radiance(P), hit(P), sh_o(P), sh_d(P), sh_c(P), accum(npix);
+    std::vector<F4> ray_o(P), ray_d(P), weight(P), radiance(P), hit(P), sh_o(P), sh_d(P), sh_c(P);
     std::vector<uint64_t> rng(P); std::vector<uint32_t> pixel(P), q0, q1;
-    memset(accum.data(), 0, npix * sizeof(F4));
     PoolDev pool{ray_o.data(), ray_d.data(), weight.data(), radiance.data(), hit.data(), rng.data(), pixel.data(), sh_o.data(), sh_d.data(), sh_c.data()};
     unsigned long long closest = 0, shadow = 0, nodes = 0, tris = 0, samples = 0;
 #pragma omp parallel for schedule(static)
@@ -100,8 +99,7 @@ int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* im
         for (long long i = 0; i < (long long)ns; i++) { TraverseCounters tc{0, 0}; shadow_one<true>(c->sc, pool, (int)i, &tc); nodes += tc.nodes; tris += tc.tris; }
         q0.swap(q1);
     }
-    for (int ps = 0; ps < f.n_pixel_slots; ps++) splat_pixel(f, pool, ps, accum.data(), PlainAdd());
-    for (size_t i = 0; i < npix; i++) resolve_pixel(accum.data(), i, p->gamma, imagedouble, sample_count, image);
+    for (int ps = 0; ps < f.n_pixel_slots; ps++) splat_pixel(f, pool, ps, accum_out, PlainAdd());
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->samples = samples; stats->rays_closest = closest; stats->rays_shadow = shadow; stats->node_visits = nodes; stats->tri_tests = tris;
@@ -109,11 +107,56 @@ int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* im
     }
     return PTB_OK;
 }
-int ptb_render_accum(ptb_ctx*, const ptb_camera*, const ptb_params*, float*, ptb_stats*) { return PTB_ERR_UNSUPPORTED; }
-int ptb_resolve(ptb_ctx*, const float*, int, int, float, float*, float*, uint8_t*) { return PTB_ERR_UNSUPPORTED; }
-int ptb_shard_pack_size(const ptb_params*, int, int64_t*) { return PTB_ERR_UNSUPPORTED; }
-int ptb_shard_pack(ptb_ctx*, const ptb_params*, int, const float*, float*) { return PTB_ERR_UNSUPPORTED; }
-int ptb_shard_unpack_add(ptb_ctx*, const ptb_params*, int, const float*, float*) { return PTB_ERR_UNSUPPORTED; }
+int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats) {
+    const size_t npix = (size_t)p->W * p->H;
+    std::vector<F4> accum(npix);
+    memset(accum.data(), 0, npix * sizeof(F4));
+    int rc = render_into(c, cam, p, accum.data(), stats);
+    if (rc) return rc;
+    for (size_t i = 0; i < npix; i++) resolve_pixel(accum.data(), i, p->gamma, imagedouble, sample_count, image);
+    return PTB_OK;
+}
+// in the sim the "device" buffers are plain host memory
+int ptb_render_accum(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* d_rgbw, ptb_stats* stats) { return render_into(c, cam, p, reinterpret_cast<F4*>(d_rgbw), stats); }
+int ptb_resolve(ptb_ctx*, const float* d_rgbw, int W, int H, float gamma, float* imagedouble, float* sample_count, uint8_t* image) {
+    for (size_t i = 0; i < (size_t)W * H; i++) resolve_pixel(reinterpret_cast<const F4*>(d_rgbw), i, gamma, imagedouble, sample_count, image);
+    return PTB_OK;
+}
+static void shard_geometry(const ptb_params* p, int rank, int& tile, int& apron, int& tiles_x, int& total, int& mine) {
+    tile = p->tile_size > 0 ? p->tile_size : 64;
+    apron = (int)ceilf(p->sigma_filter * 2);
+    tiles_x = (p->W + tile - 1) / tile;
+    total = tiles_x * ((p->H + tile - 1) / tile);
+    const int count = p->shard_count > 0 ? p->shard_count : 1;
+    mine = total > rank ? (total - rank + count - 1) / count : 0;
+}
+int ptb_shard_pack_size(const ptb_params* p, int rank, int64_t* out) {
+    int tile, apron, tiles_x, total, mine;
+    shard_geometry(p, rank, tile, apron, tiles_x, total, mine);
+    const int64_t side = tile + 2 * apron;
+    *out = (int64_t)mine * side * side * 4;
+    return PTB_OK;
+}
+static int shard_move(const ptb_params* p, int rank, F4* rgbw, F4* packed, int unpack) {
+    int tile, apron, tiles_x, total, mine;
+    shard_geometry(p, rank, tile, apron, tiles_x, total, mine);
+    const int side = tile + 2 * apron, count = p->shard_count > 0 ? p->shard_count : 1;
+    for (int lt = 0; lt < mine; lt++) {
+        const int tile_id = rank + lt * count, ty = tile_id / tiles_x, tx = tile_id % tiles_x;
+        for (int r = 0; r < side * side; r++) {
+            const int i = ty * tile - apron + r / side, j = tx * tile - apron + r % side;
+            const bool inside = i >= 0 && i < p->H && j >= 0 && j < p->W;
+            F4& q = packed[(size_t)lt * side * side + r];
+            const int tiles_y = (p->H + tile - 1) / tile;
+            const bool send = shard_block_sends(tile_id, i, j, p->W, p->H, tile, apron, tiles_x, tiles_y, rank, count);
+            if (!unpack) { F4 z; z.x = z.y = z.z = z.w = 0; q = send ? rgbw[(size_t)(p->H - 1 - i) * p->W + j] : z; }
+            else if (inside) { F4& d = rgbw[(size_t)(p->H - 1 - i) * p->W + j]; d.x += q.x; d.y += q.y; d.z += q.z; d.w += q.w; }
+        }
+    }
+    return PTB_OK;
+}
+int ptb_shard_pack(ptb_ctx*, const ptb_params* p, int rank, const float* d_rgbw, float* d_packed) { return shard_move(p, rank, (F4*)d_rgbw, (F4*)d_packed, 0); }
+int ptb_shard_unpack_add(ptb_ctx*, const ptb_params* p, int rank, const float* d_packed, float* d_rgbw) { return shard_move(p, rank, (F4*)d_rgbw, (F4*)d_packed, 1); }
 
 int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* obj_id, int32_t* tri_id, float* tout) {
     if (!c->committed) return PTB_ERR_STATE;

@@ -1,0 +1,204 @@
+"""Parity cases shared by the CPU suite (tests/devsim: the device headers host-compiled) and the GPU suite
+(the real kernels through the C-ABI).  Each case renders the same seeded scene with the implementation under
+test and with the oracle and states its tolerance next to the assertion.
+
+Tolerances (float32 paths; the oracle and the CUDA path draw the same pcg32 numbers per (pixel,sample)):
+  ID_AGREE      primary-hit (object, triangle) ids agree on >= 99.99 % of pixels (BASELINE.json north_star)
+  FRAC_1SPP     at equal seed and spp at most 0.5 % of pixels differ by more than 1e-3 relative
+                (a path changes when a rounding difference flips a branch: lobe choice, Fresnel choice, edge hit)
+  MEAN_REL      image means agree within 0.2 %
+  RRMSE_FACTOR  relRMSE(test_N, oracle_hi) <= 1.1 * relRMSE(oracle_N, oracle_hi) + 0.005  (converged-image bound)
+"""
+import numpy as np
+
+from pathtracer_b200 import _abi, scenes
+from pathtracer_b200.api import Plane, Sphere, Texture, TriMesh
+
+ID_AGREE = 0.9999
+FRAC_1SPP = 0.005
+MEAN_REL = 2e-3
+RRMSE_FACTOR = 1.1
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max(-1) / np.maximum(np.abs(a).max(-1), 1e-3 * float(np.abs(a).mean()) + 1e-30)
+
+
+def rrmse(a, ref):
+    return float(np.sqrt(np.mean((a - ref) ** 2)) / np.mean(ref))
+
+
+def check_images(img, ref, frac=FRAC_1SPP, mean_rel=MEAN_REL):
+    assert np.isfinite(img).all()
+    e = rel_err(ref, img)
+    bad = float(np.mean(e > 1e-3))
+    assert bad <= frac, f"{bad:.5f} of pixels differ by > 1e-3 relative (bound {frac})"
+    assert abs(float(img.mean()) / float(ref.mean()) - 1) <= mean_rel
+
+
+def check_ids(rt_test, rt_oracle, W=None, H=None, agree=ID_AGREE, need_mesh=True):
+    oa, ta, da = rt_oracle.primary_ids(W, H)
+    ob, tb, db = rt_test.primary_ids(W, H)
+    same = (oa == ob) & (ta == tb)
+    assert same.mean() >= agree, f"primary-hit ids agree on {same.mean():.6f} of pixels (need {agree})"
+    if need_mesh:
+        assert (ta >= 0).mean() > 0.05, "the test scene must actually show the mesh"
+    hit = same & (oa >= 0)
+    assert np.allclose(da[hit], db[hit], rtol=2e-4), "hit distances"
+
+
+def case_scene(test_lib, oracle_lib, mk, nrays=None, frac=FRAC_1SPP):
+    a, b = mk(oracle_lib).commit(), mk(test_lib).commit()
+    if nrays:
+        a.nrays = b.nrays = nrays
+    check_ids(b, a, need_mesh=len(a.s.objects) > 5 or any(hasattr(o, "tri") for o in a.s.objects))
+    ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+    check_images(ib, ia, frac)
+    assert np.allclose(a.sample_count, b.sample_count, rtol=1e-5)
+    # ray counters: identical paths except where a branch flipped
+    for k in ("rays_closest", "rays_shadow"):
+        assert abs(a.stats[k] - b.stats[k]) <= 0.002 * a.stats[k] + 8, k
+    assert b.stats["samples"] == a.stats["samples"]
+    d = np.abs(a.image.astype(int) - b.image.astype(int))
+    assert np.mean(d > 1) <= 2 * frac
+    a.close(); b.close()
+
+
+def case_converged(test_lib, oracle_lib):
+    mk = lambda L: scenes.config_C2(L, 40, 40, 8, nv=24, env=(128, 64))
+    hi = mk(oracle_lib).commit()
+    hi.nrays, hi.seed = 512, 99
+    ref_hi = hi.render_image_nopreviz().copy()
+    a, b = mk(oracle_lib).commit(), mk(test_lib).commit()
+    ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+    ea, eb = rrmse(ia, ref_hi), rrmse(ib, ref_hi)
+    assert eb <= RRMSE_FACTOR * ea + 0.005, (ea, eb)
+    assert rrmse(ib, ia) <= 0.02, "equal-seed images should be nearly the same image"
+
+
+def kat_tolerances():
+    # (rtol, atol, fraction of rows allowed outside) per building block
+    return {
+        _abi.KAT_PCG32: (0, 0, 0), _abi.KAT_LATTICE: (0, 0, 0), _abi.KAT_FAST_EXP: (0, 0, 0), _abi.KAT_RANDOM_PER_PIXEL: (0, 0, 0),
+        _abi.KAT_FILTER_RATIO: (0, 0, 0), _abi.KAT_FAST_NORMALIZE: (4e-7, 0, 0), _abi.KAT_CAMERA: (2e-6, 2e-6, 0),
+        _abi.KAT_RANDOM_COS: (2e-5, 2e-6, 0), _abi.KAT_RANDOM_PHONG: (2e-5, 2e-6, 0), _abi.KAT_PHONG_EVAL: (1e-4, 1e-7, 0),
+        _abi.KAT_MERL_EVAL: (0, 0, 0.02),   # a lookup without interpolation: bin flips at bin borders only
+    }
+
+
+def case_kats(test_lib, gold):
+    from golden_scenes import KAT_INPUTS
+    rt = scenes.config_C4(test_lib, 32, 32, 1, nv=10).commit()
+    for which, (inp, kw) in KAT_INPUTS().items():
+        rtol, atol, frac = kat_tolerances()[which]
+        got, want = rt.kat(which, inp, **kw), gold[f"out_{which}"]
+        ok = np.isclose(got, want, rtol=rtol, atol=atol).all(-1)
+        assert 1 - ok.mean() <= frac, f"KAT {which}: {(~ok).sum()} of {len(ok)} rows outside rtol={rtol} atol={atol}"
+    rt.close()
+
+
+# ---- edge cases -------------------------------------------------------------------------------------------------
+def quad_mesh(n=6, with_uv=True, with_normals=True, groups=False):
+    """A wavy (n x n)-quad sheet in file axes."""
+    g = np.linspace(-1, 1, n + 1)
+    x, z = np.meshgrid(g, g, indexing="xy")
+    y = 0.15 * np.sin(3 * x) * np.cos(2 * z)
+    v = np.stack([x, y, z], -1).reshape(-1, 3).astype(np.float32)
+    nrm = np.stack([-0.45 * np.cos(3 * x) * np.cos(2 * z), np.ones_like(x), 0.3 * np.sin(3 * x) * np.sin(2 * z)], -1).reshape(-1, 3)
+    nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    uv = np.stack([(x + 1) / 2, (z + 1) / 2], -1).reshape(-1, 2).astype(np.float32)
+    tri = []
+    for r in range(n):
+        for c in range(n):
+            a = r * (n + 1) + c
+            b, cc, d = a + 1, a + n + 1, a + n + 2
+            for t in ((a, cc, b), (b, cc, d)):
+                grp = ((r + c) % 2) if groups else 0
+                tri.append([*t, *(t if with_uv else (-1, -1, -1)), *(t if with_normals else (-1, -1, -1)), grp])
+    return v, (nrm if with_normals else np.zeros((0, 3), np.float32)), (uv if with_uv else np.zeros((0, 2), np.float32)), np.array(tri, np.int32)
+
+
+def edge_scene(L, variant, W=37, H=23, spp=3):
+    rt = scenes.base(L, W, H, spp)
+    if variant == "mirror_and_flip":
+        s = Sphere((0, -17.3, 0), 10, mirror=True).set_material(0, **scenes.phong((.8, .8, .8), 0.0, 1.0))
+        s2 = Sphere((-14, -20, 8), 6, normal_swapped=False).set_material(0, **scenes.phong((.2, .5, .9), 0.4, 20.0, transp=Texture(0.0), refr=Texture(1.4)))
+        rt.s.addObject(s); rt.s.addObject(s2)
+    elif variant == "mesh_no_uv_groups":
+        m = scenes._place_like_gui(TriMesh(*quad_mesh(with_uv=False, groups=True)))
+        m.set_material(0, **scenes.phong((.7, .2, .2), 0.1, 30.0)); m.set_material(1, **scenes.phong((.2, .7, .2), 0.0, 1.0))
+        rt.s.addObject(m)
+    elif variant == "mesh_flat":
+        m = scenes._place_like_gui(TriMesh(*quad_mesh(groups=True)))
+        m.interp_normals = False
+        m.set_material(0, **scenes.phong((.6, .6, .2), 0.2, 40.0))   # group 1 has no material: defaults Kd=1
+        rt.s.addObject(m)
+    elif variant == "textured_rotated":
+        v, n, uv, tri = quad_mesh(groups=False)
+        m = scenes._place_like_gui(TriMesh(v, n, uv, tri))
+        th = 0.6
+        m.mat_rotation = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]], np.float32)
+        yy, xx = np.mgrid[0:16, 0:16]
+        kd = np.stack([(xx % 4 < 2) * .8 + .1, (yy % 4 < 2) * .8 + .1, np.full((16, 16), .3)], -1).astype(np.float32)
+        mat = scenes.phong((1, 1, 1), 0.1, 25.0, normal=Texture((0, 0, 1), scenes.wave_normal_map(32)), alpha=Texture(1.0, scenes.checker_alpha_map(32)))
+        mat["Kd"] = Texture((1, 1, 1), kd)
+        m.set_material(0, **mat)
+        rt.s.addObject(m)
+        pl = rt.s.objects[2]
+        pl.set_material(0, Kd=Texture((1, 1, 1), kd))
+    elif variant == "wide_filter":
+        rt.sigma_filter = 1.0
+        rt.s.addObject(Sphere((0, -17.3, 0), 10).set_material(0, **scenes.phong((.8, .3, .3), 0.0, 1.0)))
+    elif variant == "depth_one":
+        rt.nb_bounces = 1
+        rt.s.addObject(Sphere((0, -17.3, 0), 10).set_material(0, **scenes.phong((.8, .3, .3), 0.3, 10.0)))
+    else:
+        raise KeyError(variant)
+    return rt
+
+
+EDGE_VARIANTS = ["mirror_and_flip", "mesh_no_uv_groups", "mesh_flat", "textured_rotated", "wide_filter", "depth_one"]
+
+
+def case_edge(test_lib, oracle_lib, variant):
+    a, b = edge_scene(oracle_lib, variant).commit(), edge_scene(test_lib, variant).commit()
+    ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+    check_images(ib, ia, frac=0.01)
+    assert np.allclose(a.sample_count, b.sample_count, rtol=1e-5)
+    oa, ta, _ = a.primary_ids(); ob, tb, _ = b.primary_ids()
+    assert ((oa == ob) & (ta == tb)).mean() >= 0.998   # 851 pixels: at most one edge pixel may flip
+
+
+def case_passes_and_shards(test_lib):
+    """Size-independent properties: splitting the work into passes or shards must not change the image."""
+    mk = lambda: scenes.config_C2(test_lib, 150, 70, 5, nv=16, env=(64, 32)).commit()
+    whole = mk()
+    ref = whole.render_image_nopreviz().copy()
+    cnt = whole.sample_count.copy()
+    small = mk()
+    small.set_option(_abi.OPT_POOL_PATHS, 4096)      # forces several slot passes and one sample per pass
+    img = small.render_image_nopreviz()
+    assert np.allclose(img, ref, rtol=2e-5, atol=1e-3) and np.allclose(small.sample_count, cnt, rtol=2e-5)
+    assert small.stats["rays_closest"] == whole.stats["rays_closest"] and small.stats["samples"] == whole.stats["samples"]
+    return whole, ref, cnt
+
+
+def case_errors(test_lib):
+    import ctypes as C
+    from pathtracer_b200.api import Raytracer
+    rt = Raytracer(test_lib)
+    rt.s.addObject(Sphere((0, 0, 0), 1))
+    try:
+        rt.commit()
+        raised = False
+    except _abi.PtbError:
+        raised = True
+    assert raised, "commit without the dome must fail (object ids 0/1 are hard-wired)"
+    rt = scenes.base(test_lib, 8, 8, 1)
+    rt.s.addObject(TriMesh(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 2)), np.zeros((0, 10), np.int32)))
+    try:
+        rt.commit()
+        raised = False
+    except _abi.PtbError:
+        raised = True
+    assert raised, "an empty mesh is rejected"

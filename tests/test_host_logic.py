@@ -1,0 +1,93 @@
+"""CPU coverage of everything that is host code or host-checkable: scene ingestion (TriMesh::init semantics,
+tangents, matrices), the BVH8 builder, the shard/tile arithmetic — and, through tests/devsim (the device headers
+compiled for the host, test-only), the device logic itself against the oracle.  No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+from golden_scenes import SCENES
+from parity_cases import (EDGE_VARIANTS, case_converged, case_edge, case_errors, case_kats, case_passes_and_shards, case_scene,
+                          check_ids)
+
+from pathtracer_b200 import _abi, scenes
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_kats_devsim(devsim):
+    case_kats(devsim, np.load(os.path.join(GOLD, "kat.npz")))
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_scenes_devsim_vs_oracle(devsim, port, name):
+    case_scene(devsim, port, SCENES[name])
+
+
+@pytest.mark.parametrize("variant", EDGE_VARIANTS)
+def test_edge_cases_devsim(devsim, port, variant):
+    case_edge(devsim, port, variant)
+
+
+def test_converged_devsim(devsim, port):
+    case_converged(devsim, port)
+
+
+def test_bvh8_against_oracle_on_a_larger_mesh(devsim, port):
+    """160k triangles, 200x200 picking rays from two view points: exercises deep trees, quantisation slack and leaf packing."""
+    mk = lambda L: scenes.config_C2(L, 200, 200, 1, nv=200, env=(64, 32))
+    a, b = mk(port).commit(), mk(devsim).commit()
+    check_ids(b, a)
+    info = b.scene_info()
+    assert info["n_triangles"] == 160000 and 0 < info["n_bvh_nodes"] < 160000 / 2 and info["bvh_depth"] <= 12
+    for rt in (a, b):
+        rt.cam.position = np.array([30, 5, 30], np.float32)
+        rt.cam.direction = np.array([-0.6, -0.35, -0.72], np.float32) / np.float32(np.linalg.norm([-0.6, -0.35, -0.72]))
+        rt.cam.up = np.array([0, 1, 0], np.float32)
+    check_ids(b, a)
+
+
+def test_passes_and_shards_devsim(devsim):
+    whole, ref, cnt = case_passes_and_shards(devsim)
+    # shards: three ranks accumulate into one buffer == the whole frame (ragged 150x70 frame, 32-pixel tiles)
+    acc = np.zeros((whole.H * whole.W, 4), np.float32)
+    total = 0
+    for r in range(3):
+        st = whole.render_accum(acc.ctypes.data, r, 3, 32)
+        total += st["samples"]
+    assert total == whole.W * whole.H * whole.nrays
+    img = whole.resolve(acc.ctypes.data)
+    assert np.allclose(img, ref, rtol=2e-5, atol=1e-3) and np.allclose(whole.sample_count, cnt, rtol=2e-5)
+
+
+def test_shard_pack_roundtrip_devsim(devsim):
+    import ctypes as C
+    rt = scenes.config_C1(devsim, 150, 70, 2).commit()
+    full = np.zeros((rt.H * rt.W, 4), np.float32)
+    rt.render_accum(full.ctypes.data, 0, 1, 32)
+    merged = np.zeros_like(full)
+    for world in (2, 3, 4):
+        merged[:] = 0
+        for r in range(world):
+            part = np.zeros_like(full)
+            rt.render_accum(part.ctypes.data, r, world, 32)
+            n = C.c_int64()
+            p = rt.params(r, world, 32)
+            devsim.check(devsim.shard_pack_size(C.byref(p), r, C.byref(n)))
+            packed = np.zeros(n.value, np.float32)
+            devsim.check(devsim.shard_pack(rt._ctx, C.byref(p), r, C.c_void_p(part.ctypes.data), C.c_void_p(packed.ctypes.data)))
+            devsim.check(devsim.shard_unpack_add(rt._ctx, C.byref(p), r, C.c_void_p(packed.ctypes.data), C.c_void_p(merged.ctypes.data)))
+        assert np.allclose(merged, full, rtol=2e-5, atol=1e-2), world
+
+
+def test_errors_devsim(devsim):
+    case_errors(devsim)
+
+
+def test_generators_are_deterministic_and_sized():
+    v, n, uv, tri = scenes.displaced_torus(10)
+    assert len(tri) == 400 and tri[:, :3].max() < len(v) and np.allclose(np.linalg.norm(n, axis=1), 1, atol=1e-6)
+    assert 4 * 500 ** 2 == 1000000 and 4 * 791 ** 2 == 2502724 and 4 * 255 ** 2 == 260100 and 8 * 4 * 866 ** 2 == 23998592
+    env = scenes.sky_envmap(64, 32)
+    assert env.dtype == np.uint8 and env.shape == (32, 64, 3) and env.max() == 255
+    t = scenes.merl_table()
+    assert t.shape == (3, 90, 90, 180) and np.allclose(t[0] * (1.0 / 1500), t[1] * (1.15 / 1500)) and np.allclose(t[0] * (1.0 / 1500), t[2] * (1.66 / 1500))
