@@ -194,7 +194,22 @@ int ptb_primary_ids(ptb_ctx*, const ptb_camera*, int W, int H,
 /* ---- options and introspection ----------------------------------------------------------------- */
 #define PTB_OPT_COUNT_TRAVERSAL  1   /* 1: count node visits / triangle tests (instrumented kernels) */
 #define PTB_OPT_POOL_PATHS       2   /* paths in flight per pass (default 1<<24) */
+#define PTB_OPT_TIME_KERNELS     3   /* 1: bracket every kernel launch with CUDA events (see ptb_get_kernel_times) */
 int ptb_set_option(ptb_ctx*, int option, int64_t value);
+
+/* Per-kernel device time of the LAST render, measured with CUDA events on the launching stream
+ * (PTB_OPT_TIME_KERNELS).  Index: 0 raygen, 1 extend (closest hit), 2 shade, 3 shadow (any hit), 4 splat.
+ * ms[k] = summed duration of kernel k's launches, launches[k] = how many, rays[k] = queue entries processed
+ * (paths or shadow rays), node_visits/tri_tests per kernel need PTB_OPT_COUNT_TRAVERSAL. */
+#define PTB_N_KERNELS 5
+typedef struct ptb_kernel_times {
+    double   ms[PTB_N_KERNELS];
+    uint64_t launches[PTB_N_KERNELS];
+    uint64_t items[PTB_N_KERNELS];
+    uint64_t node_visits[PTB_N_KERNELS];
+    uint64_t tri_tests[PTB_N_KERNELS];
+} ptb_kernel_times;
+int ptb_get_kernel_times(const ptb_ctx*, ptb_kernel_times*);
 
 typedef struct ptb_scene_info {
     int64_t n_triangles, n_bvh_nodes, bytes_nodes, bytes_triangles, bytes_attributes, bytes_textures;

@@ -1047,6 +1047,7 @@ int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
     info->bytes_nodes = info->n_bvh_nodes * (int64_t)sizeof(bnode); info->bytes_triangles = info->n_triangles * (int64_t)sizeof(tsoup);
     return PTB_OK;
 }
+int ptb_get_kernel_times(const ptb_ctx* c, ptb_kernel_times* t) { (void)c; (void)t; return PTB_ERR_UNSUPPORTED; }
 int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H, const double* in, int n, int is, double* out, int os) {
     if (!c || !in || !out) return PTB_ERR_INVALID;
     if (cam) set_frame(c, cam, W, H);

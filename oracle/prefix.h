@@ -32,6 +32,7 @@
 #define ptb_set_option         ORC_NAME(set_option)
 #define ptb_get_scene_info     ORC_NAME(get_scene_info)
 #define ptb_kat                ORC_NAME(kat)
+#define ptb_get_kernel_times    ORC_NAME(get_kernel_times)
 /* options understood only by the CPU checkers */
 #define ORC_OPT_THREADS 100    /* OpenMP threads for render (default: all, capped at 64 like the reference) */
 #endif

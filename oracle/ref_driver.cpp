@@ -323,6 +323,7 @@ int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
     return PTB_OK;
 }
 
+int ptb_get_kernel_times(const ptb_ctx*, ptb_kernel_times*) { return PTB_ERR_UNSUPPORTED; }
 int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H,
             const double* in, int n, int is, double* out, int os) {
     if (!c || !in || !out) return PTB_ERR_INVALID;

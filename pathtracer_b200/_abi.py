@@ -13,7 +13,8 @@ OK = 0
 SLOT_KD, SLOT_KS, SLOT_NE, SLOT_TRANSP, SLOT_REFR, SLOT_NORMAL, SLOT_ALPHA = (1 << i for i in range(7))
 OBJ_MIRROR, OBJ_FLIP_NORMALS, OBJ_FLAT_NORMALS = 1, 2, 4
 BRDF_PHONG, BRDF_MERL = 0, 1
-OPT_COUNT_TRAVERSAL, OPT_POOL_PATHS = 1, 2
+OPT_COUNT_TRAVERSAL, OPT_POOL_PATHS, OPT_TIME_KERNELS = 1, 2, 3
+KERNEL_NAMES = ["raygen", "extend", "shade", "shadow", "splat"]
 ORC_OPT_THREADS = 100
 (KAT_PCG32, KAT_LATTICE, KAT_CAMERA, KAT_RANDOM_COS, KAT_RANDOM_PHONG, KAT_PHONG_EVAL, KAT_MERL_EVAL,
  KAT_FAST_EXP, KAT_FAST_NORMALIZE, KAT_RANDOM_PER_PIXEL, KAT_FILTER_RATIO) = range(1, 12)
@@ -76,11 +77,19 @@ class SceneInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class KernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 5), ("launches", C.c_uint64 * 5), ("items", C.c_uint64 * 5), ("node_visits", C.c_uint64 * 5),
+                ("tri_tests", C.c_uint64 * 5)]
+
+    def as_dict(self):
+        return {n: {k: getattr(self, k)[i] for k, _ in self._fields_} for i, n in enumerate(KERNEL_NAMES)}
+
+
 # every symbol include/ptb200.h declares (tests check the product library exports all of them)
 SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_mesh",
            "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "commit", "render",
            "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
-           "set_option", "get_scene_info", "kat"]
+           "set_option", "get_scene_info", "kat", "get_kernel_times"]
 
 
 class PtbError(RuntimeError):
@@ -116,6 +125,7 @@ class Lib:
             "primary_ids": (C.c_int, [vp, C.POINTER(Camera), C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _fp]),
             "set_option": (C.c_int, [vp, C.c_int, C.c_int64]),
             "get_scene_info": (C.c_int, [vp, C.POINTER(SceneInfo)]),
+            "get_kernel_times": (C.c_int, [vp, C.POINTER(KernelTimes)]),
             "kat": (C.c_int, [vp, C.c_int, C.POINTER(Camera), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
                               C.POINTER(C.c_double), C.c_int]),
         }

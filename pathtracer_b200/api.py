@@ -290,6 +290,11 @@ class Raytracer:
     def set_option(self, option, value):
         self.lib.check(self.lib.set_option(self._ctx, option, int(value)), self._ctx)
 
+    def kernel_times(self):
+        kt = _abi.KernelTimes()
+        self.lib.check(self.lib.get_kernel_times(self._ctx, C.byref(kt)), self._ctx)
+        return kt.as_dict()
+
     def scene_info(self):
         info = _abi.SceneInfo()
         self.lib.check(self.lib.get_scene_info(self._ctx, C.byref(info)), self._ctx)

@@ -30,8 +30,8 @@ using namespace ptb;
 
 // counters layout (uint32): [2*b] = paths queued for bounce b, [2*b+1] = shadow rays of bounce b
 #define PTB_MAX_BOUNCES 64
-// 64-bit totals: 0 closest rays, 1 shadow rays, 2 node visits, 3 triangle tests
-#define PTB_N_TOTALS 4
+// 64-bit totals: 0 closest rays, 1 shadow rays, 2/3 node visits / triangle tests of k_extend, 4/5 of k_shadow
+#define PTB_N_TOTALS 6
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) k_rpp(float* rpp, int n) {
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) k_shadow(SceneDev sc, PoolDev p, const ui
     if (tid < n) shadow_one<COUNT>(sc, p, tid, &tc);
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) { tc.nodes += __shfl_down_sync(0xffffffffu, tc.nodes, o); tc.tris += __shfl_down_sync(0xffffffffu, tc.tris, o); }
-        if ((threadIdx.x & 31) == 0 && (tc.nodes | tc.tris)) { atomicAdd(&totals[2], (unsigned long long)tc.nodes); atomicAdd(&totals[3], (unsigned long long)tc.tris); }
+        if ((threadIdx.x & 31) == 0 && (tc.nodes | tc.tris)) { atomicAdd(&totals[4], (unsigned long long)tc.nodes); atomicAdd(&totals[5], (unsigned long long)tc.tris); }
     }
 }
 
@@ -229,6 +229,10 @@ struct ptb_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool count_traversal = false;
+    bool time_kernels = false;
+    std::vector<cudaEvent_t> ev_pool;          // PTB_OPT_TIME_KERNELS: start/stop pairs, one per launch
+    std::vector<int> ev_kind;
+    ptb_kernel_times ktimes;
 };
 
 static std::string g_create_err;
@@ -323,6 +327,7 @@ void ptb_destroy(ptb_ctx* c) {
     void* ptrs[] = {c->d_counters, c->d_totals, c->d_rpp, c->d_accum, c->d_out_img, c->d_out_cnt, c->d_out_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -460,11 +465,30 @@ static int frame_setup(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     return PTB_OK;
 }
 
+// PTB_OPT_TIME_KERNELS: a start/stop event pair around one launch, on the launching stream
+struct LaunchTimer {
+    ptb_ctx* c; size_t used = 0;
+    explicit LaunchTimer(ptb_ctx* ctx) : c(ctx) { c->ev_kind.clear(); }
+    void begin(int kind) {
+        if (!c->time_kernels) return;
+        if (used + 2 > c->ev_pool.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); c->ev_pool.push_back(a); c->ev_pool.push_back(b); }
+        c->ev_kind.push_back(kind);
+        cudaEventRecord(c->ev_pool[used], c->stream);
+    }
+    void end() {
+        if (!c->time_kernels) return;
+        cudaEventRecord(c->ev_pool[used + 1], c->stream);
+        used += 2;
+    }
+};
+
 // the pass loop; accumulates into d_rgbw (device, W*H float4)
 static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stats* stats) {
     auto w0 = std::chrono::steady_clock::now();
     const int64_t pixel_slots = (int64_t)f.n_my_tiles * f.tile * f.tile;
     uint64_t launches = 0;
+    LaunchTimer lt(c);
+    memset(&c->ktimes, 0, sizeof(c->ktimes));
     CK(cudaMemsetAsync(c->d_totals, 0, PTB_N_TOTALS * sizeof(unsigned long long), c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     // count the shard's in-image pixels (edge tiles are partial)
@@ -506,20 +530,30 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                 const int n_paths = (int)(ns * f.spp_pass);
                 const unsigned g256 = (unsigned)((n_paths + 255) / 256), g128 = (unsigned)((n_paths + 127) / 128);
                 CK(cudaMemsetAsync(c->d_counters, 0, 2 * (PTB_MAX_BOUNCES + 1) * sizeof(uint32_t), c->stream));
+                lt.begin(0);
                 k_raygen<<<g256, 256, 0, c->stream>>>(f, c->pool, n_paths);
+                lt.end();
                 launches++;
                 for (int b = 0; b < nb; b++) {
                     const uint32_t* q = b == 0 ? nullptr : c->d_queue[b & 1];
                     const uint32_t* cnt = b == 0 ? nullptr : c->d_counters + 2 * b;
+                    lt.begin(1);
                     if (c->count_traversal) k_extend<true><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_totals);
                     else k_extend<false><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_totals);
+                    lt.end();
+                    lt.begin(2);
                     k_shade<<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1),
                                                          c->d_counters + 2 * b + 1);
+                    lt.end();
+                    lt.begin(3);
                     if (c->count_traversal) k_shadow<true><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, c->d_counters + 2 * b + 1, c->d_totals);
                     else k_shadow<false><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, c->d_counters + 2 * b + 1, c->d_totals);
+                    lt.end();
                     launches += 3;
                 }
+                lt.begin(4);
                 k_splat<<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(f, c->pool, d_rgbw);
+                lt.end();
                 k_totals<<<1, 32, 0, c->stream>>>(c->d_counters, nb, nb > 0 ? valid_here * (unsigned long long)f.spp_pass : 0ull, c->d_totals);
                 launches += 2;
                 CK(cudaGetLastError());
@@ -528,14 +562,26 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    unsigned long long t[PTB_N_TOTALS];
+    CK(cudaMemcpy(t, c->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
+    {
+        ptb_kernel_times& kt = c->ktimes;
+        for (size_t i = 0; i < c->ev_kind.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]);
+            kt.ms[c->ev_kind[i]] += ms;
+            kt.launches[c->ev_kind[i]]++;
+        }
+        kt.items[0] = kt.items[4] = valid_pixels * (unsigned long long)nrays;
+        kt.items[1] = kt.items[2] = t[0]; kt.items[3] = t[1];
+        kt.node_visits[1] = t[2]; kt.tri_tests[1] = t[3]; kt.node_visits[3] = t[4]; kt.tri_tests[3] = t[5];
+    }
     if (stats) {
-        unsigned long long t[PTB_N_TOTALS];
-        CK(cudaMemcpy(t, c->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         memset(stats, 0, sizeof(*stats));
         stats->samples = valid_pixels * (unsigned long long)nrays;
-        stats->rays_closest = t[0]; stats->rays_shadow = t[1]; stats->node_visits = t[2]; stats->tri_tests = t[3];
+        stats->rays_closest = t[0]; stats->rays_shadow = t[1]; stats->node_visits = t[2] + t[4]; stats->tri_tests = t[3] + t[5];
         stats->ms_device = ms;
         stats->ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
         stats->kernel_launches = launches;
@@ -664,6 +710,7 @@ int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
     switch (option) {
     case PTB_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return PTB_OK;
     case PTB_OPT_POOL_PATHS: if (value < 1024) return PTB_ERR_INVALID; c->pool_paths = value; return PTB_OK;
+    case PTB_OPT_TIME_KERNELS: c->time_kernels = value != 0; return PTB_OK;
     default: return PTB_OK;  // unknown options (e.g. the CPU checkers' thread count) are ignored
     }
 }
@@ -677,6 +724,12 @@ int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
     info->n_objects = (int32_t)c->host.objects.size();
     info->bvh_depth = c->flat.bvh.depth;
     info->ms_bvh_build = c->flat.ms_bvh; info->ms_upload = c->ms_upload;
+    return PTB_OK;
+}
+
+int ptb_get_kernel_times(const ptb_ctx* c, ptb_kernel_times* out) {
+    if (!c || !out) return PTB_ERR_INVALID;
+    *out = c->ktimes;
     return PTB_OK;
 }
 

@@ -184,6 +184,7 @@ int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
     info->n_objects = (int)c->host.objects.size();
     return PTB_OK;
 }
+int ptb_get_kernel_times(const ptb_ctx*, ptb_kernel_times*) { return PTB_ERR_UNSUPPORTED; }
 int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H, const double* in, int n, int is, double* out, int os) {
     CameraDev cd; memset(&cd, 0, sizeof(cd));
     if (cam) camera_setup(cd, cam->position, cam->direction, cam->up, cam->fov, cam->focus_distance, cam->aperture, W, H);

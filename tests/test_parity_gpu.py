@@ -1,0 +1,154 @@
+"""The parity tests proper: the CUDA kernels, called through the C-ABI, against the oracle on the same seeded
+inputs, plus size-independent properties at the benchmark configurations' full sizes.  Run on the B200 box:
+    python -m pytest tests -m gpu
+The oracle here is oracle/port (bit-identical to the reference's own code on the golden vectors, see
+tests/test_oracle_pinning.py); oracle/_ref is used as well when its prebuilt library travelled."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+from golden_scenes import SCENES
+from parity_cases import (EDGE_VARIANTS, case_converged, case_edge, case_errors, case_kats, case_passes_and_shards, case_scene,
+                          check_ids, check_images)
+
+from pathtracer_b200 import _abi, scenes
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_native_library_is_what_runs(gpu):
+    import pathtracer_b200
+    assert gpu.version().decode().startswith("ptb200")
+    maps = open("/proc/self/maps").read()
+    assert pathtracer_b200.LIB_PATH in maps, "libptb200.so must be the loaded implementation"
+
+
+def test_kats_gpu(gpu):
+    case_kats(gpu, np.load(os.path.join(GOLD, "kat.npz")))
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_scenes_gpu_vs_oracle(gpu, port, name):
+    case_scene(gpu, port, SCENES[name])
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_scenes_gpu_vs_golden_reference_images(gpu, name):
+    """Against the committed outputs of the reference itself (no oracle code involved at run time)."""
+    gold = np.load(os.path.join(GOLD, f"scene_{name}.npz"))
+    rt = SCENES[name](gpu).commit()
+    obj, tri, t = rt.primary_ids()
+    assert ((obj == gold["obj"]) & (tri == gold["tri"])).mean() >= 0.999   # 2304 pixels: at most two may flip
+    img = rt.render_image_nopreviz()
+    check_images(img, gold["imagedouble"], frac=0.01)
+    assert np.allclose(rt.sample_count, gold["sample_count"], rtol=1e-5)
+
+
+def test_scenes_gpu_vs_compiled_reference(gpu, ref):
+    case_scene(gpu, ref, lambda L: scenes.config_C3(L, 96, 96, 2, nv=40, tex=128))
+
+
+@pytest.mark.parametrize("variant", EDGE_VARIANTS)
+def test_edge_cases_gpu(gpu, port, variant):
+    case_edge(gpu, port, variant)
+
+
+def test_converged_gpu(gpu, port):
+    case_converged(gpu, port)
+
+
+def test_errors_gpu(gpu):
+    case_errors(gpu)
+    ctx = C.c_void_p()
+    assert gpu.create(10 ** 6, C.byref(ctx)) == -1            # device id out of range
+    rt = scenes.config_C1(gpu, 16, 16, 1)
+    rt.commit()
+    rt.sigma_filter = 3.0                                      # filter_size 6 > 4
+    with pytest.raises(_abi.PtbError):
+        rt.render_image_nopreviz()
+    rt.sigma_filter, rt.nrays = 0.5, 0
+    with pytest.raises(_abi.PtbError):
+        rt.render_image_nopreviz()
+
+
+def test_primary_ids_on_a_quarter_million_triangles(gpu, port):
+    """BASELINE.json north_star: primary-ray hit triangle ids agree on >= 99.99 % of pixels (C4's mesh, 512x512)."""
+    mk = lambda L: scenes.config_C4(L, 512, 512, 1)
+    a, b = mk(port).commit(), mk(gpu).commit()
+    check_ids(b, a)
+
+
+def test_passes_and_shards_gpu(gpu):
+    whole, ref, cnt = case_passes_and_shards(gpu)
+    import torch
+    acc = torch.zeros(whole.H * whole.W * 4, dtype=torch.float32, device="cuda:0")
+    total = 0
+    for r in range(3):
+        total += whole.render_accum(acc.data_ptr(), r, 3, 32)["samples"]
+    assert total == whole.W * whole.H * whole.nrays
+    img = whole.resolve(acc.data_ptr())
+    assert np.allclose(img, ref, rtol=2e-5, atol=1e-3) and np.allclose(whole.sample_count, cnt, rtol=2e-5)
+    # tile gather: pack each shard's tiles+aprons, unpack-add into a fresh frame == the whole frame
+    merged = torch.zeros_like(acc)
+    for world in (2, 4):
+        merged.zero_()
+        for r in range(world):
+            part = torch.zeros_like(acc)
+            whole.render_accum(part.data_ptr(), r, world, 32)
+            n = C.c_int64()
+            p = whole.params(r, world, 32)
+            gpu.check(gpu.shard_pack_size(C.byref(p), r, C.byref(n)))
+            packed = torch.zeros(max(n.value, 4), dtype=torch.float32, device="cuda:0")
+            gpu.check(gpu.shard_pack(whole._ctx, C.byref(p), r, C.c_void_p(part.data_ptr()), C.c_void_p(packed.data_ptr())), whole._ctx)
+            gpu.check(gpu.shard_unpack_add(whole._ctx, C.byref(p), r, C.c_void_p(packed.data_ptr()), C.c_void_p(merged.data_ptr())), whole._ctx)
+        torch.cuda.synchronize()
+        assert np.allclose(whole.resolve(merged.data_ptr()), ref, rtol=2e-5, atol=1e-3), world
+
+
+def test_determinism_and_seed(gpu):
+    mk = lambda: scenes.config_C3(gpu, 64, 64, 4, nv=24, tex=64).commit()
+    a, b = mk(), mk()
+    ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+    assert np.allclose(ia, ib, rtol=1e-5), "same seed: same image up to the order of the splat atomics"
+    assert a.stats["rays_closest"] == b.stats["rays_closest"] and a.stats["rays_shadow"] == b.stats["rays_shadow"]
+    b.seed = 1
+    ic = b.render_image_nopreviz()
+    assert not np.allclose(ia, ic, rtol=1e-3)
+
+
+# ---- full-size properties (BASELINE.json sizes; the oracle cannot run these in seconds) -----------------------------
+def test_full_size_C2_properties(gpu):
+    """1,000,000 triangles, 1024x1024: traversal counters, pass splitting and weight normalisation at full size."""
+    rt = scenes.config_C2(gpu, spp=4).commit()
+    info = rt.scene_info()
+    assert info["n_triangles"] == 1000000 and info["bytes_nodes"] == 80 * info["n_bvh_nodes"]
+    rt.set_option(_abi.OPT_COUNT_TRAVERSAL, 1)
+    img = rt.render_image_nopreviz().copy()
+    st = rt.stats
+    assert st["samples"] == 1024 * 1024 * 4 and np.isfinite(img).all() and (img >= 0).all()
+    rays = st["rays_closest"] + st["rays_shadow"]
+    assert st["samples"] <= st["rays_closest"] <= 5 * st["samples"] and st["rays_shadow"] <= st["rays_closest"]
+    assert 2 < st["node_visits"] / rays < 40 and 0.5 < st["tri_tests"] / rays < 20
+    # interior weight sums: every sample deposits the same total weight -> sample_count ~ spp * const
+    c = rt.sample_count[8:-8, 8:-8]
+    assert abs(c.mean() / 4 - rt.sample_count[0, 0] / 4 * c.mean() / rt.sample_count[0, 0]) < 1e-3 and c.std() / c.mean() < 0.2
+    # the same frame in many small passes
+    rt2 = scenes.config_C2(gpu, spp=4).commit()
+    rt2.set_option(_abi.OPT_POOL_PATHS, 1 << 19)
+    img2 = rt2.render_image_nopreviz()
+    assert np.allclose(img2, img, rtol=5e-5, atol=1e-2)
+    assert rt2.stats["rays_closest"] == st["rays_closest"] and rt2.stats["kernel_launches"] > 4 * st["kernel_launches"]
+    # primary ids: every mesh pixel reports a valid original triangle id
+    obj, tri, t = rt.primary_ids()
+    assert ((obj == 3) == (tri >= 0)).all() and tri.max() < 1000000 and (t[obj >= 0] > 0).all()
+
+
+def test_full_size_C3_roundtrip_of_transparency(gpu):
+    """2.5M-triangle dielectric: no NaN, energy bounded by the emitters, refraction actually happens (rays/sample > opaque)."""
+    rt = scenes.config_C3(gpu, spp=2).commit()
+    img = rt.render_image_nopreviz()
+    assert np.isfinite(img).all()
+    assert rt.stats["rays_closest"] / rt.stats["samples"] > 2.5
+    assert img.max() <= 3183098.75 * 1.001   # nothing brighter than looking at the light itself (lightPower)
