@@ -1,0 +1,207 @@
+// ptb_raytracer.hpp — C++ host side above the C-ABI, shaped like the reference's own classes so that code written
+// against `Raytracer` / `Scene` / `Sphere` / `Plane` / `TriMesh` / `Camera` (Raytracer.h:25-121, Geometry.h:849-1400,
+// TriangleMesh.h:113-255, Vector.h:720-840) ports by changing an include.  The objects only hold description; all
+// rendering happens in libptb200.so (CUDA).  Errors surface as ptb::Error (the reference reports nothing).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ptb200.h"
+
+namespace ptbhost {
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct Vector {
+    float v[3];
+    Vector(float x = 0, float y = 0, float z = 0) { v[0] = x; v[1] = y; v[2] = z; }
+    float& operator[](int i) { return v[i]; }
+    float operator[](int i) const { return v[i]; }
+};
+
+// Vector.h:720-840 (non-lenticular)
+struct Camera {
+    Vector position{0, 0, 50}, direction{0, 0, -1}, up{0, 1, 0};
+    float fov = 35.f * (float)M_PI / 180.f, focus_distance = 50.f, aperture = 0.1f;
+    Camera() = default;
+    Camera(const Vector& p, const Vector& d, const Vector& u) : position(p), direction(d), up(u) {}
+    void rotate(float angle_x, float angle_y, float time) {   // Camera::rotate, Vector.h:738-765
+        const float ax = time * angle_x, ay = time * angle_y;
+        auto rot = [&](Vector& d) {
+            Vector t(d[0], std::cos(ay) * d[1] - std::sin(ay) * d[2], std::sin(ay) * d[1] + std::cos(ay) * d[2]);
+            d = Vector(std::cos(ax) * t[0] - std::sin(ax) * t[2], t[1], std::sin(ax) * t[0] + std::cos(ax) * t[2]);
+        };
+        rot(direction); rot(up);
+    }
+};
+
+// BRDF.h:252-426
+struct Texture {
+    Vector multiplier{1, 1, 1};
+    int W = 0, H = 0;
+    std::vector<float> values;   // W*H*3 post-load
+    Texture() = default;
+    explicit Texture(const Vector& m) : multiplier(m) {}
+    explicit Texture(float m) : multiplier(m, m, m) {}
+};
+
+struct Material {                // one slot index of Object::textures / specularmap / ... (Geometry.h:672)
+    uint32_t present = 0;
+    Texture Kd, Ks, Ne, transp, refr, normal, alpha;
+    Material& set(uint32_t slot, const Texture& t) {
+        present |= slot;
+        switch (slot) {
+        case PTB_SLOT_KD: Kd = t; break; case PTB_SLOT_KS: Ks = t; break; case PTB_SLOT_NE: Ne = t; break;
+        case PTB_SLOT_TRANSP: transp = t; break; case PTB_SLOT_REFR: refr = t; break;
+        case PTB_SLOT_NORMAL: normal = t; break; case PTB_SLOT_ALPHA: alpha = t; break;
+        default: throw Error("unknown slot");
+        }
+        return *this;
+    }
+};
+
+enum ObjectType { OT_TRIMESH, OT_SPHERE, OT_PLANE };
+
+struct Object {                  // Geometry.h:240-672
+    ObjectType type;
+    bool miroir = false, flip_normals = false, interp_normals = true;
+    float scale = 1.f;
+    float mat_rotation[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    Vector rotation_center{NAN, NAN, NAN};   // NaN: the object's own default
+    Vector max_translation;
+    int brdf_kind = PTB_BRDF_PHONG;
+    std::shared_ptr<std::vector<double>> merl;   // IsoMERLBRDF::data
+    std::vector<Material> materials;             // index = group
+    explicit Object(ObjectType t) : type(t) {}
+    virtual ~Object() = default;
+};
+struct Sphere : Object {
+    Vector O; float R;
+    std::vector<uint8_t> envtex; int envW = 0, envH = 0;   // Sphere::load_envmap (object 1 only)
+    Sphere(const Vector& origin, float rayon, bool mirror = false, bool normal_swapped = false) : Object(OT_SPHERE), O(origin), R(rayon) {
+        miroir = mirror; flip_normals = normal_swapped;
+    }
+};
+struct Plane : Object {
+    Vector A, vecN;
+    Plane(const Vector& a, const Vector& n, bool mirror = false) : Object(OT_PLANE), A(a), vecN(n) { miroir = mirror; }
+};
+struct TriMesh : Object {        // arrays as a reader fills them (TriangleMesh.cpp:240-569), before init's processing
+    std::vector<float> vertices, normals, uvs;   // x3, x3, x2
+    std::vector<int32_t> indices;                // x10: vtx ijk, uv ijk, normal ijk, group
+    float scaling = 1.f; Vector offset; bool center = true;
+    TriMesh() : Object(OT_TRIMESH) {}
+};
+
+struct Scene {                   // Geometry.h:1238-1400
+    std::vector<std::shared_ptr<Object>> objects;
+    float intensite_lumiere = 0.f, envmap_intensity = 1.f;
+    int addObject(std::shared_ptr<Object> o) { objects.push_back(std::move(o)); return (int)objects.size() - 1; }
+};
+
+class Raytracer {                // Raytracer.h:25-121
+public:
+    int W = 1000, H = 800, nrays = 100, nb_bounces = 3;
+    Camera cam;
+    float sigma_filter = 0.5f, gamma = 2.2f;
+    uint32_t seed = 0;
+    Scene s;
+    std::vector<unsigned char> image;     // W*H*3
+    std::vector<float> imagedouble;       // W*H*3 linear
+    std::vector<float> sample_count;      // W*H
+    ptb_stats stats{};
+
+    explicit Raytracer(int device = 0) : device_(device) {}
+    ~Raytracer() { if (ctx_) ptb_destroy(ctx_); }
+    Raytracer(const Raytracer&) = delete;
+
+    void loadScene() {               // Raytracer.cpp:1238-1274
+        W = 1000; H = 800; nrays = 100; nb_bounces = 3;
+        cam = Camera(Vector(0, 0, 50), Vector(0, 0, -1), Vector(0, 1, 0));
+        cam.fov = (float)(35 * M_PI / 180); cam.focus_distance = 50; cam.aperture = 0.1f; sigma_filter = 0.5f;
+        s = Scene();
+        auto slum = std::make_shared<Sphere>(Vector(10, 23, 15), 10.f);
+        auto s2 = std::make_shared<Sphere>(Vector(0, 0, 0), 1000000.f, false, true);
+        auto plane = std::make_shared<Plane>(Vector(0, 0, 0), Vector(0, 1, 0));
+        plane->max_translation = Vector(0, -27.3f, 0);
+        s.addObject(slum); s.addObject(s2); s.addObject(plane);
+        s.intensite_lumiere = (float)(1000000000 * 4. * M_PI / (4. * M_PI * slum->R * slum->R * M_PI));
+        s.envmap_intensity = 1;
+        cam.rotate(0, (float)(-22 * M_PI / 180), 1);
+    }
+
+    // hands the scene to the device: TriMesh::init + build_bvh + Scene::prepare_render equivalents
+    void commit() {
+        if (ctx_) { ptb_destroy(ctx_); ctx_ = nullptr; }
+        if (ptb_create(device_, &ctx_) != PTB_OK) throw Error(std::string("ptb_create: ") + ptb_last_error(nullptr));
+        std::vector<std::pair<const std::vector<double>*, int>> merl_ids;
+        for (auto& op : s.objects) {
+            Object& o = *op;
+            ptb_xform xf;
+            xf.scale = o.scale; std::memcpy(xf.rotation, o.mat_rotation, sizeof(xf.rotation));
+            for (int k = 0; k < 3; k++) { xf.rotation_center[k] = o.rotation_center[k]; xf.translation[k] = o.max_translation[k]; }
+            const int flags = (o.miroir ? PTB_OBJ_MIRROR : 0) | (o.flip_normals ? PTB_OBJ_FLIP_NORMALS : 0) | (o.interp_normals ? 0 : PTB_OBJ_FLAT_NORMALS);
+            int id = -1;
+            if (o.type == OT_SPHERE) { auto& sp = static_cast<Sphere&>(o); ck(ptb_add_sphere(ctx_, sp.O.v, sp.R, &xf, flags, &id)); }
+            else if (o.type == OT_PLANE) { auto& pl = static_cast<Plane&>(o); ck(ptb_add_plane(ctx_, pl.A.v, pl.vecN.v, &xf, flags, &id)); }
+            else {
+                auto& g = static_cast<TriMesh&>(o);
+                ptb_mesh m;
+                m.vertices = g.vertices.data(); m.n_vertices = (int)g.vertices.size() / 3;
+                m.normals = g.normals.data(); m.n_normals = (int)g.normals.size() / 3;
+                m.uvs = g.uvs.data(); m.n_uvs = (int)g.uvs.size() / 2;
+                m.tri = g.indices.data(); m.n_tri = (int)g.indices.size() / 10;
+                m.scaling = g.scaling; m.center = g.center ? 1 : 0;
+                for (int k = 0; k < 3; k++) m.offset[k] = g.offset[k];
+                ck(ptb_add_mesh(ctx_, &m, &xf, flags, &id));
+            }
+            for (size_t gi = 0; gi < o.materials.size(); gi++) {
+                const Material& mm = o.materials[gi];
+                ptb_material pm;
+                std::memset(&pm, 0, sizeof(pm));
+                pm.present = mm.present;
+                auto tex = [](const Texture& t) { ptb_tex r; r.texels = t.W > 0 ? t.values.data() : nullptr; r.W = t.W; r.H = t.H; for (int k = 0; k < 3; k++) r.mult[k] = t.multiplier[k]; return r; };
+                pm.Kd = tex(mm.Kd); pm.Ks = tex(mm.Ks); pm.Ne = tex(mm.Ne); pm.transp = tex(mm.transp); pm.refr = tex(mm.refr); pm.normal = tex(mm.normal); pm.alpha = tex(mm.alpha);
+                ck(ptb_set_group_material(ctx_, id, (int)gi, &pm));
+            }
+            if (o.brdf_kind == PTB_BRDF_MERL && o.merl) {
+                int mid = -1;
+                for (auto& pr : merl_ids) if (pr.first == o.merl.get()) mid = pr.second;
+                if (mid < 0) { ck(ptb_add_merl(ctx_, o.merl->data(), &mid)); merl_ids.push_back({o.merl.get(), mid}); }
+                ck(ptb_set_brdf(ctx_, id, PTB_BRDF_MERL, mid));
+            }
+        }
+        if (s.objects.size() > 1 && s.objects[1]->type == OT_SPHERE) {
+            auto& dome = static_cast<Sphere&>(*s.objects[1]);
+            if (dome.envW > 0) ck(ptb_set_envmap(ctx_, dome.envtex.data(), dome.envW, dome.envH));
+        }
+        ck(ptb_set_light(ctx_, s.intensite_lumiere, s.envmap_intensity));
+        ck(ptb_commit(ctx_));
+    }
+
+    // Raytracer::render_image_nopreviz (Raytracer.cpp:1565-1798): fills imagedouble / sample_count / image
+    void render_image_nopreviz() {
+        if (!ctx_) commit();
+        ptb_camera c; ptb_params p;
+        for (int k = 0; k < 3; k++) { c.position[k] = cam.position[k]; c.direction[k] = cam.direction[k]; c.up[k] = cam.up[k]; }
+        c.fov = cam.fov; c.focus_distance = cam.focus_distance; c.aperture = cam.aperture;
+        p.W = W; p.H = H; p.nrays = nrays; p.nb_bounces = nb_bounces; p.sigma_filter = sigma_filter; p.gamma = gamma; p.seed = seed;
+        p.shard_rank = 0; p.shard_count = 1; p.tile_size = 0;
+        image.resize((size_t)W * H * 3); imagedouble.resize((size_t)W * H * 3); sample_count.resize((size_t)W * H);
+        ck(ptb_render(ctx_, &c, &p, imagedouble.data(), sample_count.data(), image.data(), &stats));
+    }
+
+    ptb_ctx* ctx() { return ctx_; }
+
+private:
+    void ck(int rc) { if (rc != PTB_OK) throw Error(std::string("ptb error ") + std::to_string(rc) + ": " + ptb_last_error(ctx_)); }
+    int device_;
+    ptb_ctx* ctx_ = nullptr;
+};
+
+}  // namespace ptbhost
