@@ -3,7 +3,7 @@
 //
 // One render = passes over the shard's pixels; one pass keeps `pool` paths in flight in HBM (SoA, ptb_scene.h
 // PoolDev) and runs, on one stream with no host synchronisation:
-//     k_raygen -> [ k_extend -> k_shade -> k_shadow ] x nb_bounces -> k_splat
+//     k_raygen -> [ k_trace<closest> -> k_shade -> k_trace<any-hit> ] x nb_bounces -> k_splat
 // Queues are index lists compacted with warp ballots + one atomic per warp (k_shade); every kernel reads
 // its element count from device memory, so the host never waits for a count.
 // There is no CPU implementation behind this ABI: a missing device or a failed launch is an error code.
@@ -28,9 +28,15 @@ using namespace ptb;
         }                                                                                                \
     } while (0)
 
-// counters layout (uint32): [2*b] = paths queued for bounce b, [2*b+1] = shadow rays of bounce b
+// counters layout (uint32), zeroed at the start of every pass:
+//   [2*b] paths queued for bounce b          [2*b+1] shadow rays queued for the BVH at bounce b
+//   [CUR + 2*b] / [CUR + 2*b+1]  work cursors of the persistent trace kernels (closest / any-hit) of bounce b
+//   [SQ + b]  intersection_shadow-equivalent queries made at bounce b (ray statistics)
 #define PTB_MAX_BOUNCES 64
-// 64-bit totals: 0 closest rays, 1 shadow rays, 2/3 node visits / triangle tests of k_extend, 4/5 of k_shadow
+#define PTB_CNT_CUR (2 * (PTB_MAX_BOUNCES + 1))
+#define PTB_CNT_SQ (4 * (PTB_MAX_BOUNCES + 1))
+#define PTB_N_COUNTERS (5 * (PTB_MAX_BOUNCES + 1))
+// 64-bit totals: 0 closest rays, 1 shadow rays, 2/3 node visits / triangle tests of the closest-hit trace, 4/5 of the any-hit trace
 #define PTB_N_TOTALS 6
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -43,27 +49,147 @@ __global__ void __launch_bounds__(256) k_rpp(float* rpp, int n) {
     rpp[2 * p + 1] = y;
 }
 
-__global__ void __launch_bounds__(256) k_raygen(FrameDev f, PoolDev p, int n_paths) {
+__global__ void __launch_bounds__(256) k_raygen(SceneDev sc, FrameDev f, PoolDev p, int n_paths) {
     const int path = blockIdx.x * blockDim.x + threadIdx.x;
     if (path >= n_paths) return;
-    raygen_one(f, p, path);
+    raygen_one(sc, f, p, path);
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
-                                                int n_static, unsigned long long* totals) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = count ? (int)*count : n_static;
-    TraverseCounters tc;
-    tc.nodes = 0; tc.tris = 0;
-    if (tid < n) {
-        const int path = queue ? (int)queue[tid] : tid;
-        if (p.pixel[path] != 0xffffffffu) extend_one<COUNT>(sc, p, path, &tc);
-        else { F4 q; q.x = INFINITY; q.y = 0; q.z = 0; q.w = u2f((uint32_t)PTB_HIT_MISS); p.hit[path] = q; }
+// ---- BVH8 traversal: persistent warps, dynamic ray fetch, postponed triangle tests -------------------------------------
+// Replaces TriMesh::intersection / intersection_shadow (TriangleMesh.cpp:1133-1319).  One thread per ray diverges badly
+// (ncu on the 2.5M-triangle scene: 7-10 of 32 lanes active per instruction), so the warp is kept busy instead:
+//   * a lane whose ray has finished pulls the next queue entry (one atomic per warp) once fewer than `refill_below`
+//     lanes are live (Aila & Laine 2009, persistent threads);
+//   * every iteration of the warp loop is: [stack pop or finish] -> [ONE node step for lanes with node work] ->
+//     [triangle steps while at least a quarter of the live lanes take part]; triangles left over are postponed by pushing
+//     the triangle group on the traversal stack (Ylitie et al. 2017, sec. 4).
+// ANY_HIT = shadow rays (queue = shadow entries, first accepted triangle ends the ray; an unoccluded ray adds its deferred
+// direct term to the path's radiance).  Closest-hit results overwrite the analytic hit record the ray's producer wrote.
+template <bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
+                                               int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = count ? *count : (uint32_t)n_static;
+    const AlphaCtx ac = alpha_ctx(sc);
+    const F4* __restrict__ nodes = sc.nodes;
+    const F4* __restrict__ tris = sc.tris;
+    bool live = false, exhausted = false;
+    uint32_t item = 0, entry = 0;
+    RayPrep r;
+    float tbest = 0.f, hb1 = 0.f, hb2 = 0.f;
+    int32_t hprim = -1;
+    U2 ngroup, tgroup, stack[PTB_STACK];
+    int sp = 0;
+    ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
+    uint32_t cn = 0, ct = 0;
+    r.o = r.d = r.idir = v3(0, 0, 0); r.oct_inv4 = 0;
+    for (;;) {
+        // ---- refill idle lanes from the queue
+        const uint32_t live_mask = __ballot_sync(FULL, live);
+        if (!exhausted && __popc(live_mask) < refill_below) {
+            const uint32_t idle = ~live_mask;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (!live) {
+                const uint32_t qi = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                if (qi < n) {
+                    F4 o, d;
+                    float tmax;
+                    bool ok = true;
+                    if (ANY_HIT) { entry = qi; o = p.sh_o[qi]; d = p.sh_d[qi]; tmax = o.w; }
+                    else {
+                        item = queue ? queue[qi] : qi;
+                        ok = p.pixel[item] != 0xffffffffu;
+                        o = p.ray_o[item]; d = p.ray_d[item]; tmax = p.hit[item].x;
+                    }
+                    if (ok) {
+                        r = ray_prep(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
+                        tbest = tmax; hprim = -1; sp = 0;
+                        ngroup.x = 0; ngroup.y = 0x80000000u; tgroup.x = 0; tgroup.y = 0;
+                        if (ANY_HIT) item = f2u(d.w);   // the path the shadow ray belongs to
+                        live = true;
+                    }
+                }
+            }
+            if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
+        }
+        if (__ballot_sync(FULL, live) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- pop / finish: lanes with neither node nor triangle work
+        if (live && ngroup.y <= 0x00ffffffu && tgroup.y == 0) {
+            if (sp > 0) {
+                const U2 e = stack[--sp];
+                if (e.y > 0x00ffffffu) ngroup = e; else tgroup = e;
+            } else {
+                if (ANY_HIT) {   // unoccluded: deliver the deferred direct term (Raytracer.cpp:545-566)
+                    const F4 c = p.sh_c[entry];
+                    F4 L = p.radiance[item];
+                    L.x += c.x; L.y += c.y; L.z += c.z;
+                    p.radiance[item] = L;
+                } else if (hprim >= 0) {
+                    F4 q; q.x = tbest; q.y = hb1; q.z = hb2; q.w = u2f((uint32_t)hprim);
+                    p.hit[item] = q;
+                }
+                live = false;
+            }
+        }
+        // ---- node phase: ONE node step
+        if (live && ngroup.y > 0x00ffffffu) {
+            if (tgroup.y != 0) { if (sp < PTB_STACK) stack[sp++] = tgroup; tgroup.y = 0; }   // postpone leftover triangles
+            const uint32_t hits_imask = ngroup.y;
+            const uint32_t child_bit = highest_bit(hits_imask);
+            const uint32_t child_base = ngroup.x;
+            ngroup.y &= ~(1u << child_bit);
+            if (ngroup.y > 0x00ffffffu) { if (sp < PTB_STACK) stack[sp++] = ngroup; }
+            const uint32_t slot = (child_bit - 24u) ^ (r.oct_inv4 & 0xffu);
+            const uint32_t rel = popcount32(hits_imask & ~(0xffffffffu << slot));
+            const float4* np = reinterpret_cast<const float4*>(nodes) + (size_t)(child_base + rel) * 5;
+            const float4 l0 = __ldg(np), l1 = __ldg(np + 1), l2 = __ldg(np + 2), l3 = __ldg(np + 3), l4 = __ldg(np + 4);
+            F4 n0, n1, n2, n3, n4;
+            n0.x = l0.x; n0.y = l0.y; n0.z = l0.z; n0.w = l0.w; n1.x = l1.x; n1.y = l1.y; n1.z = l1.z; n1.w = l1.w;
+            n2.x = l2.x; n2.y = l2.y; n2.z = l2.z; n2.w = l2.w; n3.x = l3.x; n3.y = l3.y; n3.z = l3.z; n3.w = l3.w;
+            n4.x = l4.x; n4.y = l4.y; n4.z = l4.z; n4.w = l4.w;
+            if (COUNT) cn++;
+            const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, tbest);
+            ngroup.x = f2u(n1.x);
+            tgroup.x = f2u(n1.y);
+            ngroup.y = (hm & 0xff000000u) | (f2u(n0.w) >> 24);
+            tgroup.y = hm & 0x00ffffffu;
+        }
+        // ---- triangle phase: at least one step, more while a quarter of the live lanes take part
+        uint32_t tm = __ballot_sync(FULL, live && tgroup.y != 0);
+        if (tm != 0) {
+            const int live_n = __popc(__ballot_sync(FULL, live));
+            do {
+                if (live && tgroup.y != 0) {
+                    const uint32_t ti = highest_bit(tgroup.y);
+                    tgroup.y &= ~(1u << ti);
+                    const uint32_t prim = tgroup.x + ti;
+                    const float4* tp = reinterpret_cast<const float4*>(tris) + (size_t)prim * 3;
+                    const float4 l0 = __ldg(tp), l1 = __ldg(tp + 1), l2 = __ldg(tp + 2);
+                    F4 a, b, c;
+                    a.x = l0.x; a.y = l0.y; a.z = l0.z; a.w = l0.w; b.x = l1.x; b.y = l1.y; b.z = l1.z; b.w = l1.w;
+                    c.x = l2.x; c.y = l2.y; c.z = l2.z; c.w = l2.w;
+                    if (COUNT) ct++;
+                    float t, b1, b2;
+                    if (tri_test(a, b, c, r, tbest, t, b1, b2)) {
+                        if (!((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(&ac, (int)prim, b1, b2))) {
+                            tbest = t; hb1 = b1; hb2 = b2; hprim = (int32_t)prim;
+                            if (ANY_HIT) { live = false; tgroup.y = 0; }   // occluded: nothing to deliver
+                        }
+                    }
+                }
+                tm = __ballot_sync(FULL, live && tgroup.y != 0);
+            } while (__popc(tm) * 4 >= live_n && tm != 0);
+        }
     }
     if (COUNT) {
-        for (int o = 16; o > 0; o >>= 1) { tc.nodes += __shfl_down_sync(0xffffffffu, tc.nodes, o); tc.tris += __shfl_down_sync(0xffffffffu, tc.tris, o); }
-        if ((threadIdx.x & 31) == 0 && (tc.nodes | tc.tris)) { atomicAdd(&totals[2], (unsigned long long)tc.nodes); atomicAdd(&totals[3], (unsigned long long)tc.tris); }
+        for (int o = 16; o > 0; o >>= 1) { cn += __shfl_down_sync(FULL, cn, o); ct += __shfl_down_sync(FULL, ct, o); }
+        if (lane == 0 && (cn | ct)) { atomicAdd(&totals[ANY_HIT ? 4 : 2], (unsigned long long)cn); atomicAdd(&totals[ANY_HIT ? 5 : 3], (unsigned long long)ct); }
     }
 }
 
@@ -81,11 +207,11 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool want) {
 
 __global__ void __launch_bounds__(128) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
                                                const uint32_t* __restrict__ count, int n_static, uint32_t* __restrict__ next_queue,
-                                               uint32_t* next_count, uint32_t* shadow_count) {
+                                               uint32_t* next_count, uint32_t* shadow_count, uint32_t* shadow_queries) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = count ? (int)*count : n_static;
     ShadeOut out;
-    out.cont = false; out.shadow = false;
+    out.cont = false; out.shadow = false; out.shadow_query = false;
     int path = 0;
     if (tid < n) {
         path = queue ? (int)queue[tid] : tid;
@@ -95,19 +221,8 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, FrameDev f, PoolDev 
     if (out.cont) next_queue[qi] = (uint32_t)path;
     const uint32_t si = warp_push(shadow_count, out.shadow);
     if (out.shadow) { p.sh_o[si] = out.sh_o; p.sh_d[si] = out.sh_d; p.sh_c[si] = out.sh_c; }
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow(SceneDev sc, PoolDev p, const uint32_t* __restrict__ count, unsigned long long* totals) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = (int)*count;
-    TraverseCounters tc;
-    tc.nodes = 0; tc.tris = 0;
-    if (tid < n) shadow_one<COUNT>(sc, p, tid, &tc);
-    if (COUNT) {
-        for (int o = 16; o > 0; o >>= 1) { tc.nodes += __shfl_down_sync(0xffffffffu, tc.nodes, o); tc.tris += __shfl_down_sync(0xffffffffu, tc.tris, o); }
-        if ((threadIdx.x & 31) == 0 && (tc.nodes | tc.tris)) { atomicAdd(&totals[4], (unsigned long long)tc.nodes); atomicAdd(&totals[5], (unsigned long long)tc.tris); }
-    }
+    const uint32_t sq = __ballot_sync(0xffffffffu, out.shadow_query);
+    if ((threadIdx.x & 31) == 0 && sq) atomicAdd(shadow_queries, (uint32_t)__popc(sq));
 }
 
 struct RedAddV4 {
@@ -125,7 +240,7 @@ __global__ void __launch_bounds__(128) k_splat(FrameDev f, PoolDev p, F4* accum)
 __global__ void k_totals(const uint32_t* counters, int nb, unsigned long long valid_paths, unsigned long long* totals) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned long long closest = valid_paths, shadow = 0;
-    for (int b = 0; b < nb; b++) { if (b > 0) closest += counters[2 * b]; shadow += counters[2 * b + 1]; }
+    for (int b = 0; b < nb; b++) { if (b > 0) closest += counters[2 * b]; shadow += counters[PTB_CNT_SQ + b]; }
     totals[0] += closest;
     totals[1] += shadow;
 }
@@ -230,6 +345,8 @@ struct ptb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool count_traversal = false;
     bool time_kernels = false;
+    int trace_blocks = 148 * 8;                // persistent grid of k_trace, set from the occupancy query in ptb_create
+    int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
     std::vector<cudaEvent_t> ev_pool;          // PTB_OPT_TIME_KERNELS: start/stop pairs, one per launch
     std::vector<int> ev_kind;
     ptb_kernel_times ktimes;
@@ -308,11 +425,17 @@ int ptb_create(int device_id, ptb_ctx** out) {
     memset(&c->sc, 0, sizeof(c->sc));
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaMalloc((void**)&c->d_counters, 2 * (PTB_MAX_BOUNCES + 1) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_counters, PTB_N_COUNTERS * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc((void**)&c->d_totals, PTB_N_TOTALS * sizeof(unsigned long long)) != cudaSuccess) {
         g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
         delete c;
         return PTB_ERR_CUDA;
+    }
+    {
+        int sms = 148, per_sm = 8;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, false>, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 8;
+        c->trace_blocks = sms * per_sm;
     }
     *out = c;
     return PTB_OK;
@@ -529,27 +652,36 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                 f.n_pixel_slots = (int)ns;
                 const int n_paths = (int)(ns * f.spp_pass);
                 const unsigned g256 = (unsigned)((n_paths + 255) / 256), g128 = (unsigned)((n_paths + 127) / 128);
-                CK(cudaMemsetAsync(c->d_counters, 0, 2 * (PTB_MAX_BOUNCES + 1) * sizeof(uint32_t), c->stream));
+                CK(cudaMemsetAsync(c->d_counters, 0, PTB_N_COUNTERS * sizeof(uint32_t), c->stream));
                 lt.begin(0);
-                k_raygen<<<g256, 256, 0, c->stream>>>(f, c->pool, n_paths);
+                k_raygen<<<g256, 256, 0, c->stream>>>(c->sc, f, c->pool, n_paths);
                 lt.end();
                 launches++;
                 for (int b = 0; b < nb; b++) {
                     const uint32_t* q = b == 0 ? nullptr : c->d_queue[b & 1];
                     const uint32_t* cnt = b == 0 ? nullptr : c->d_counters + 2 * b;
-                    lt.begin(1);
-                    if (c->count_traversal) k_extend<true><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_totals);
-                    else k_extend<false><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_totals);
-                    lt.end();
+                    const bool mesh = c->sc.has_mesh != 0;
+                    // persistent grid: as many blocks as are resident at once, but no more than the queue can feed
+                    const unsigned gt = (unsigned)std::max(1, std::min<int>(c->trace_blocks, (n_paths + 127) / 128));
+                    if (mesh) {
+                        lt.begin(1);
+                        if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below);
+                        else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below);
+                        lt.end();
+                        launches++;
+                    }
                     lt.begin(2);
                     k_shade<<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1),
-                                                         c->d_counters + 2 * b + 1);
+                                                         c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b);
                     lt.end();
-                    lt.begin(3);
-                    if (c->count_traversal) k_shadow<true><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, c->d_counters + 2 * b + 1, c->d_totals);
-                    else k_shadow<false><<<g128, 128, 0, c->stream>>>(c->sc, c->pool, c->d_counters + 2 * b + 1, c->d_totals);
-                    lt.end();
-                    launches += 3;
+                    launches++;
+                    if (mesh) {
+                        lt.begin(3);
+                        if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below);
+                        else k_trace<true, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below);
+                        lt.end();
+                        launches++;
+                    }
                 }
                 lt.begin(4);
                 k_splat<<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(f, c->pool, d_rgbw);
@@ -711,6 +843,8 @@ int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
     case PTB_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return PTB_OK;
     case PTB_OPT_POOL_PATHS: if (value < 1024) return PTB_ERR_INVALID; c->pool_paths = value; return PTB_OK;
     case PTB_OPT_TIME_KERNELS: c->time_kernels = value != 0; return PTB_OK;
+    case PTB_OPT_REFILL_BELOW: if (value < 1 || value > 33) return PTB_ERR_INVALID; c->refill_below = (int)value; return PTB_OK;
+    case PTB_OPT_TRACE_BLOCKS: if (value < 1) return PTB_ERR_INVALID; c->trace_blocks = (int)value; return PTB_OK;
     default: return PTB_OK;  // unknown options (e.g. the CPU checkers' thread count) are ignored
     }
 }

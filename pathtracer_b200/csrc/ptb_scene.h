@@ -127,12 +127,11 @@ PTB_HD bool plane_t(const ObjectDev& ob, V3 o, V3 d, float& t) {
 #define PTB_HIT_MISS (-1)
 PTB_HD int32_t hit_id_analytic(int obj) { return -2 - obj; }
 
-// Scene::intersection: nearest over analytic objects (object-space rays, world t) then the wide BVH.
-template <bool COUNT>
-PTB_HD void extend_ray(const SceneDev& sc, V3 o, V3 d, Hit& hit, int32_t& id, TraverseCounters* cnt) {
-    float tmin = INFINITY;
+// Nearest hit over the analytic objects (Sphere / Plane) of Scene::intersection's loop (Geometry.cpp:601-626):
+// object-space rays, world t.  Meshes are handled by the wide BVH afterwards.
+PTB_HD void analytic_closest(const SceneDev& sc, V3 o, V3 d, float& tmin, int32_t& id) {
+    tmin = INFINITY;
     id = PTB_HIT_MISS;
-    hit.t = INFINITY; hit.b1 = 0; hit.b2 = 0; hit.prim = -1;
     for (int i = 0; i < sc.n_objects; i++) {
         const ObjectDev& ob = sc.objects[i];
         if (ob.type == OBJ_MESH) continue;
@@ -142,18 +141,10 @@ PTB_HD void extend_ray(const SceneDev& sc, V3 o, V3 d, Hit& hit, int32_t& id, Tr
         const bool h = (ob.type == OBJ_SPHERE) ? sphere_t(ob, ol, dl, t) : plane_t(ob, ol, dl, t);
         if (h && t < tmin) { tmin = t; id = hit_id_analytic(i); }
     }
-    if (sc.has_mesh) {
-        AlphaCtx ac; ac.tri_uv = sc.tri_uv; ac.objects = sc.objects; ac.materials = sc.materials; ac.texels = sc.texels;
-        Hit h;
-        if (traverse<false, COUNT>(sc.nodes, sc.tris, &ac, o, d, tmin, h, cnt)) { hit = h; id = h.prim; tmin = h.t; }
-    }
-    hit.t = tmin;
 }
-
-// Scene::intersection_shadow with avoid_ghosts: any object closer than 0.999*dist_light.
-template <bool COUNT>
-PTB_HD bool occluded(const SceneDev& sc, V3 o, V3 d, float dist_light, TraverseCounters* cnt) {
-    const float lim = dist_light * 0.999f;
+// Analytic part of Scene::intersection_shadow (Geometry.cpp:721-741): any object closer than 0.999*dist_light
+PTB_HD bool analytic_occluded(const SceneDev& sc, V3 o, V3 d, float dist_light) {
+    const double lim = (double)dist_light * 0.999;
     for (int i = 0; i < sc.n_objects; i++) {
         const ObjectDev& ob = sc.objects[i];
         if (ob.type == OBJ_MESH) continue;
@@ -161,14 +152,27 @@ PTB_HD bool occluded(const SceneDev& sc, V3 o, V3 d, float dist_light, TraverseC
         const V3 ol = xf_point(ob.inv_trans, o);
         float t;
         const bool h = (ob.type == OBJ_SPHERE) ? sphere_t(ob, ol, dl, t) : plane_t(ob, ol, dl, t);
-        if (h && t < lim) return true;
-    }
-    if (sc.has_mesh) {
-        AlphaCtx ac; ac.tri_uv = sc.tri_uv; ac.objects = sc.objects; ac.materials = sc.materials; ac.texels = sc.texels;
-        Hit h;
-        if (traverse<true, COUNT>(sc.nodes, sc.tris, &ac, o, d, lim, h, cnt)) return true;
+        if (h && (double)t < lim) return true;
     }
     return false;
+}
+PTB_HD AlphaCtx alpha_ctx(const SceneDev& sc) {
+    AlphaCtx ac; ac.tri_uv = sc.tri_uv; ac.objects = sc.objects; ac.materials = sc.materials; ac.texels = sc.texels;
+    return ac;
+}
+
+// Scene::intersection: analytic objects, then the wide BVH with the analytic t as the upper bound.
+template <bool COUNT>
+PTB_HD void extend_ray(const SceneDev& sc, V3 o, V3 d, Hit& hit, int32_t& id, TraverseCounters* cnt) {
+    float tmin;
+    analytic_closest(sc, o, d, tmin, id);
+    hit.b1 = 0; hit.b2 = 0; hit.prim = -1;
+    if (sc.has_mesh) {
+        const AlphaCtx ac = alpha_ctx(sc);
+        Hit h;
+        if (traverse<false, COUNT>(sc.nodes, sc.tris, &ac, o, d, tmin, h, cnt)) { hit = h; id = h.prim; tmin = h.t; }
+    }
+    hit.t = tmin;
 }
 
 struct Surface {   // MaterialValues (BRDF.h:7-20) + what getColor needs about the object
@@ -328,10 +332,15 @@ PTB_HD uint64_t path_inc(const FrameDev& f, int path) {  // pcg32 stream increme
 PTB_HD uint32_t pack_state(int depth, bool show_lights) { return (uint32_t)depth | (show_lights ? 0x10000u : 0u); }
 
 // ---- stage 1: camera samples --------------------------------------------------------------------------
-PTB_HD void raygen_one(const FrameDev& f, PoolDev& p, int path) {
+PTB_HD void raygen_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path) {
     const int ps = path / f.spp_pass, s = path - ps * f.spp_pass;
     int i, j;
-    if (!slot_to_pixel(f, f.slot0 + ps, i, j)) { p.pixel[path] = 0xffffffffu; return; }
+    if (!slot_to_pixel(f, f.slot0 + ps, i, j)) {   // slot of an edge tile that lies outside the frame: an empty path
+        p.pixel[path] = 0xffffffffu;
+        F4 m; m.x = INFINITY; m.y = 0; m.z = 0; m.w = u2f((uint32_t)PTB_HIT_MISS);
+        p.hit[path] = m;
+        return;
+    }
     const uint32_t pix = (uint32_t)(i * f.W + j);
     const uint32_t k = (uint32_t)(f.k0 + s);
     Pcg32 e = pcg32_for_sample(pix, k, f.seed);
@@ -346,31 +355,37 @@ PTB_HD void raygen_one(const FrameDev& f, PoolDev& p, int path) {
     q.x = d.x; q.y = d.y; q.z = d.z; q.w = 0; p.ray_d[path] = q;
     q.x = 1; q.y = 1; q.z = 1; q.w = u2f(pack_state(f.nb_bounces, true)); p.weight[path] = q;
     q.x = 0; q.y = 0; q.z = 0; q.w = 0; p.radiance[path] = q;
+    float ta; int32_t ida;
+    analytic_closest(sc, o, d, ta, ida);        // the analytic half of Scene::intersection rides with the ray producer
+    q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
     p.rng[path] = e.state;
     p.pixel[path] = pix;
 }
 
-// ---- stage 2: closest hit ---------------------------------------------------------------------------------
+// ---- stage 2: closest hit in the wide BVH (the analytic objects were tested by the ray's producer) ----------------
 template <bool COUNT>
 PTB_HD void extend_one(const SceneDev& sc, PoolDev& p, int path, TraverseCounters* cnt) {
     const F4 o = p.ray_o[path], d = p.ray_d[path];
+    const F4 h0 = p.hit[path];
+    const AlphaCtx ac = alpha_ctx(sc);
     Hit h;
-    int32_t id;
-    extend_ray<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), h, id, cnt);
-    F4 q;
-    q.x = h.t; q.y = h.b1; q.z = h.b2; q.w = u2f((uint32_t)id);
-    p.hit[path] = q;
+    if (traverse<false, COUNT>(sc.nodes, sc.tris, &ac, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), h0.x, h, cnt)) {
+        F4 q;
+        q.x = h.t; q.y = h.b1; q.z = h.b2; q.w = u2f((uint32_t)h.prim);
+        p.hit[path] = q;
+    }
 }
 
 // ---- stage 3: shade ---------------------------------------------------------------------------------------
 struct ShadeOut {
-    bool cont;      // the path continues: ray_o/ray_d/weight were rewritten
-    bool shadow;    // a shadow ray was produced
+    bool cont;          // the path continues: ray_o/ray_d/weight/hit were rewritten
+    bool shadow;        // a shadow ray must still be traced through the BVH
+    bool shadow_query;  // an intersection_shadow-equivalent query was made (ray statistics)
     F4 sh_o, sh_d, sh_c;
 };
 
 PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path, ShadeOut& out) {
-    out.cont = false; out.shadow = false;
+    out.cont = false; out.shadow = false; out.shadow_query = false;
     const F4 hq = p.hit[path];
     const int32_t id = (int32_t)f2u(hq.w);
     if (id == PTB_HIT_MISS) return;                                  // Raytracer.cpp:654-657
@@ -447,13 +462,23 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
                 const float g = sc.lightPower * fmaxf(0.f, dot(N, wi)) * J / proba;
                 const V3 c = w * (g * fr);
                 const V3 so = P + 0.01f * wi;
-                out.shadow = true;
-                out.sh_o.x = so.x; out.sh_o.y = so.y; out.sh_o.z = so.z; out.sh_o.w = sqrtf(d2) - 0.01f;
-                out.sh_d.x = wi.x; out.sh_d.y = wi.y; out.sh_d.z = wi.z; out.sh_d.w = u2f((uint32_t)path);
-                out.sh_c.x = c.x; out.sh_c.y = c.y; out.sh_c.z = c.z; out.sh_c.w = 0;
+                const float dist = sqrtf(d2) - 0.01f;
+                out.shadow_query = true;
+                // analytic occluders (incl. the light itself and the dome, App. D#8) are tested here, coherently;
+                // only rays they do not block go on to the BVH
+                if (!analytic_occluded(sc, so, wi, dist)) {
+                    if (sc.has_mesh) {
+                        out.shadow = true;
+                        out.sh_o.x = so.x; out.sh_o.y = so.y; out.sh_o.z = so.z; out.sh_o.w = (float)((double)dist * 0.999);
+                        out.sh_d.x = wi.x; out.sh_d.y = wi.y; out.sh_d.z = wi.z; out.sh_d.w = u2f((uint32_t)path);
+                        out.sh_c.x = c.x; out.sh_c.y = c.y; out.sh_c.z = c.z; out.sh_c.w = 0;
+                    } else {
+                        Lq.x += c.x; Lq.y += c.y; Lq.z += c.z;
+                        p.radiance[path] = Lq;
+                    }
+                }
             } else {
-                // the reference still traces the shadow ray here; its result is unused (counted in stats)
-                out.shadow = false;
+                out.shadow_query = true;   // the reference traces this ray too; its result is unused
             }
         }
         // -- continuation (570-632)
@@ -490,21 +515,25 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
     q.x = no.x; q.y = no.y; q.z = no.z; q.w = 0; p.ray_o[path] = q;
     q.x = nd.x; q.y = nd.y; q.z = nd.z; q.w = 0; p.ray_d[path] = q;
     q.x = nw.x; q.y = nw.y; q.z = nw.z; q.w = u2f(pack_state(ndepth, nshow)); p.weight[path] = q;
+    float ta; int32_t ida;
+    analytic_closest(sc, no, nd, ta, ida);
+    q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
     out.cont = true;
 }
 
-// ---- stage 4: shadow rays -----------------------------------------------------------------------------------
+// ---- stage 4: shadow rays through the wide BVH; unoccluded ones deliver the deferred direct term -----------------------
 template <bool COUNT>
 PTB_HD void shadow_one(const SceneDev& sc, PoolDev& p, int entry, TraverseCounters* cnt) {
     const F4 o = p.sh_o[entry], d = p.sh_d[entry];
-    if (occluded<COUNT>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, cnt)) return;
+    const AlphaCtx ac = alpha_ctx(sc);
+    Hit h;
+    if (traverse<true, COUNT>(sc.nodes, sc.tris, &ac, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, h, cnt)) return;
     const uint32_t path = f2u(d.w);
     const F4 c = p.sh_c[entry];
     F4 L = p.radiance[path];
     L.x += c.x; L.y += c.y; L.z += c.z;
     p.radiance[path] = L;
 }
-
 
 // ---- stage 5: Gaussian splat of a pixel's samples of this pass (Raytracer.cpp:1604-1659) --------------------------
 // ADD(addr, value) adds a float4 {r*w, g*w, b*w, w} into the frame accumulator: red.global.add.v4.f32 on the device.

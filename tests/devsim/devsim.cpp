@@ -77,14 +77,14 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     PoolDev pool{ray_o.data(), ray_d.data(), weight.data(), radiance.data(), hit.data(), rng.data(), pixel.data(), sh_o.data(), sh_d.data(), sh_c.data()};
     unsigned long long closest = 0, shadow = 0, nodes = 0, tris = 0, samples = 0;
 #pragma omp parallel for schedule(static)
-    for (long long i = 0; i < (long long)P; i++) raygen_one(f, pool, (int)i);
+    for (long long i = 0; i < (long long)P; i++) raygen_one(c->sc, f, pool, (int)i);
     for (size_t i = 0; i < P; i++) if (pixel[i] != 0xffffffffu) { q0.push_back((uint32_t)i); }
     samples = q0.size();
     for (int b = 0; b < f.nb_bounces; b++) {
         closest += q0.size();
         const long long n = (long long)q0.size();
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, tris)
-        for (long long i = 0; i < n; i++) { TraverseCounters tc{0, 0}; extend_one<true>(c->sc, pool, (int)q0[i], &tc); nodes += tc.nodes; tris += tc.tris; }
+        for (long long i = 0; i < n; i++) { TraverseCounters tc{0, 0}; if (c->sc.has_mesh) extend_one<true>(c->sc, pool, (int)q0[i], &tc); nodes += tc.nodes; tris += tc.tris; }
         std::vector<ShadeOut> outs(n);
 #pragma omp parallel for schedule(dynamic, 256)
         for (long long i = 0; i < n; i++) shade_one(c->sc, f, pool, (int)q0[i], outs[i]);
@@ -93,8 +93,8 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
         for (long long i = 0; i < n; i++) {
             if (outs[i].cont) q1.push_back(q0[i]);
             if (outs[i].shadow) { sh_o[ns] = outs[i].sh_o; sh_d[ns] = outs[i].sh_d; sh_c[ns] = outs[i].sh_c; ns++; }
+            if (outs[i].shadow_query) shadow++;
         }
-        shadow += ns;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, tris)
         for (long long i = 0; i < (long long)ns; i++) { TraverseCounters tc{0, 0}; shadow_one<true>(c->sc, pool, (int)i, &tc); nodes += tc.nodes; tris += tc.tris; }
         q0.swap(q1);
