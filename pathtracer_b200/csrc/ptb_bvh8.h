@@ -20,6 +20,9 @@
 // TriangleMesh.cpp:1196-1209); alpha-mapped hits are rejected inside traversal (1198-1205).
 #pragma once
 #include "ptb_core.h"
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 namespace ptb {
 
@@ -83,7 +86,53 @@ PTB_HD bool alpha_rejects(const AlphaCtx* ctx, int prim, float b1, float b2);
 
 // Tests the 8 children of `n` against the ray; returns the hit mask in traversal-priority order:
 // bits 31..24 internal children (bit 24 + (slot ^ (7-oct))), bits 23..0 triangles of hit leaves.
-PTB_HD uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4& n3, const F4& n4, const RayPrep& r, float tmax) {
+#if defined(__CUDA_ARCH__)
+// Device form.  ncu on the straightforward form showed the XU pipe (48 I2F.U8 per node) as the busiest pipe, so the
+// quantised planes are turned into floats on the ALU + FMA pipes instead: one PRMT drops two plane bytes into the
+// mantissas of a half2 {1024+q0, 1024+q1} (0x6400 | q), HADD2.F32 widens them, and the bias is folded into the FFMA
+// constant: t = (1024+q)*ad + (bo - 1024*ad).  The fold costs at most 2^-24 * 1024 cells (6e-5 of a cell) of rounding,
+// well inside the builder's 1e-3-cell conservative slack.  The meta bytes are decoded four at a time (Ylitie et al. 2017).
+__device__ __forceinline__ void planes4(uint32_t w, float ad, float bo, float& t0, float& t1, float& t2, float& t3) {
+    const uint32_t h01 = __byte_perm(w, 0x64646464u, 0x4140), h23 = __byte_perm(w, 0x64646464u, 0x4342);
+    const __half2 a = *reinterpret_cast<const __half2*>(&h01), b = *reinterpret_cast<const __half2*>(&h23);
+    t0 = fmaf(__low2float(a), ad, bo); t1 = fmaf(__high2float(a), ad, bo);
+    t2 = fmaf(__low2float(b), ad, bo); t3 = fmaf(__high2float(b), ad, bo);
+}
+__device__ __forceinline__ uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4& n3, const F4& n4, const RayPrep& r, float tmax) {
+    const uint32_t e_imask = f2u(n0.w);
+    const float sx = u2f(((e_imask >> 0) & 0xffu) << 23), sy = u2f(((e_imask >> 8) & 0xffu) << 23), sz = u2f(((e_imask >> 16) & 0xffu) << 23);
+    const float adx = sx * r.idir.x, ady = sy * r.idir.y, adz = sz * r.idir.z;
+    const float box = fmaf(-1024.f, adx, (n0.x - r.o.x) * r.idir.x), boy = fmaf(-1024.f, ady, (n0.y - r.o.y) * r.idir.y),
+                boz = fmaf(-1024.f, adz, (n0.z - r.o.z) * r.idir.z);
+    const bool negx = r.d.x < 0, negy = r.d.y < 0, negz = r.d.z < 0;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t meta4 = f2u(half ? n1.w : n1.z);
+        const uint32_t lox = f2u(half ? n2.y : n2.x), loy = f2u(half ? n2.w : n2.z), loz = f2u(half ? n3.y : n3.x);
+        const uint32_t hix = f2u(half ? n3.w : n3.z), hiy = f2u(half ? n4.y : n4.x), hiz = f2u(half ? n4.w : n4.z);
+        float tnx[4], tny[4], tnz[4], tfx[4], tfy[4], tfz[4];
+        planes4(negx ? hix : lox, adx, box, tnx[0], tnx[1], tnx[2], tnx[3]);
+        planes4(negx ? lox : hix, adx, box, tfx[0], tfx[1], tfx[2], tfx[3]);
+        planes4(negy ? hiy : loy, ady, boy, tny[0], tny[1], tny[2], tny[3]);
+        planes4(negy ? loy : hiy, ady, boy, tfy[0], tfy[1], tfy[2], tfy[3]);
+        planes4(negz ? hiz : loz, adz, boz, tnz[0], tnz[1], tnz[2], tnz[3]);
+        planes4(negz ? loz : hiz, adz, boz, tfz[0], tfz[1], tfz[2], tfz[3]);
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = __byte_perm(is_inner4 << 3, 0u, 0xba98);          // per byte: 0xff iff internal child
+        const uint32_t bit_index4 = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float tn = fmaxf(fmaxf(tnx[j], tny[j]), fmaxf(tnz[j], 0.f));
+            const float tf = fminf(fminf(tfx[j], tfy[j]), fminf(tfz[j], tmax));
+            if (tn <= tf) hitmask |= ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
+        }
+    }
+    return hitmask;
+}
+#else
+inline uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4& n3, const F4& n4, const RayPrep& r, float tmax) {
     const uint32_t e_imask = f2u(n0.w);
     const float sx = u2f(((e_imask >> 0) & 0xffu) << 23), sy = u2f(((e_imask >> 8) & 0xffu) << 23), sz = u2f(((e_imask >> 16) & 0xffu) << 23);
     const float adx = sx * r.idir.x, ady = sy * r.idir.y, adz = sz * r.idir.z;
@@ -94,7 +143,6 @@ PTB_HD uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4&
     const uint32_t qhiy_lo = f2u(n4.x), qhiy_hi = f2u(n4.y), qhiz_lo = f2u(n4.z), qhiz_hi = f2u(n4.w);
     const bool negx = r.d.x < 0, negy = r.d.y < 0, negz = r.d.z < 0;
     uint32_t hitmask = 0;
-#pragma unroll
     for (int half = 0; half < 2; half++) {
         const uint32_t meta4 = half ? meta_hi : meta_lo;
         const uint32_t lox = half ? qlox_hi : qlox_lo, loy = half ? qloy_hi : qloy_lo, loz = half ? qloz_hi : qloz_lo;
@@ -103,7 +151,6 @@ PTB_HD uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4&
         const uint32_t nx = negx ? hix : lox, fx = negx ? lox : hix;
         const uint32_t ny = negy ? hiy : loy, fy = negy ? loy : hiy;
         const uint32_t nz = negz ? hiz : loz, fz = negz ? loz : hiz;
-#pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t sh = 8u * j;
             const float tnx = (float)((nx >> sh) & 0xffu) * adx + box;
@@ -125,6 +172,7 @@ PTB_HD uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4&
     }
     return hitmask;
 }
+#endif
 
 // Möller–Trumbore on {v0,e1,e2}; two-sided; accepts b1,b2 >= 0, b1+b2 <= 1, 0 <= t < tbest.
 PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, float tbest, float& t, float& b1, float& b2) {

@@ -61,13 +61,13 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev sc, FrameDev f, PoolDev
 //   * a lane whose ray has finished pulls the next queue entry (one atomic per warp) once fewer than `refill_below`
 //     lanes are live (Aila & Laine 2009, persistent threads);
 //   * every iteration of the warp loop is: [stack pop or finish] -> [ONE node step for lanes with node work] ->
-//     [triangle steps while at least a quarter of the live lanes take part]; triangles left over are postponed by pushing
+//     [triangle steps while at least 1/tri_den of the live lanes take part]; triangles left over are postponed by pushing
 //     the triangle group on the traversal stack (Ylitie et al. 2017, sec. 4).
 // ANY_HIT = shadow rays (queue = shadow entries, first accepted triangle ends the ray; an unoccluded ray adds its deferred
 // direct term to the path's radiance).  Closest-hit results overwrite the analytic hit record the ray's producer wrote.
 template <bool ANY_HIT, bool COUNT>
 __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
-                                               int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below) {
+                                               int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below, int tri_den) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n = count ? *count : (uint32_t)n_static;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
                     }
                 }
                 tm = __ballot_sync(FULL, live && tgroup.y != 0);
-            } while (__popc(tm) * 4 >= live_n && tm != 0);
+            } while (__popc(tm) * tri_den >= live_n && tm != 0);
         }
     }
     if (COUNT) {
@@ -347,6 +347,7 @@ struct ptb_ctx {
     bool time_kernels = false;
     int trace_blocks = 148 * 8;                // persistent grid of k_trace, set from the occupancy query in ptb_create
     int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
+    int tri_den = 4;                           // triangle steps repeat while >= 1/tri_den of the live lanes take part
     std::vector<cudaEvent_t> ev_pool;          // PTB_OPT_TIME_KERNELS: start/stop pairs, one per launch
     std::vector<int> ev_kind;
     ptb_kernel_times ktimes;
@@ -526,6 +527,7 @@ int ptb_commit(ptb_ctx* c) {
     FlatScene& f = c->flat;
     SceneDev& sc = c->sc;
     memset(&sc, 0, sizeof(sc));
+    scene_header(sc, f);        // before the upload: it tags objects that do not fit the inline table
     const Node8* dn; const F4* dt; const uint8_t* de;
     if ((rc = upload(c, f.nodes.data(), f.nodes.size(), &dn))) return rc;
     if ((rc = upload(c, f.tris.data(), f.tris.size(), &dt))) return rc;
@@ -539,11 +541,6 @@ int ptb_commit(ptb_ctx* c) {
     sc.nodes = reinterpret_cast<const F4*>(dn);
     sc.tris = dt;
     sc.envmap = de;
-    sc.n_objects = (int32_t)f.objects.size();
-    sc.has_mesh = f.nodes.empty() ? 0 : 1;
-    sc.envW = f.envW; sc.envH = f.envH; sc.has_envmap = (f.envW > 0 && f.envH > 0) ? 1 : 0;
-    sc.envmap_intensity = f.envmap_intensity; sc.lightPower = f.lightPower; sc.radiusLight = f.radiusLight;
-    sc.centerLight = v3(f.centerLight[0], f.centerLight[1], f.centerLight[2]);
     CK(cudaStreamSynchronize(c->stream));
     c->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     c->bytes_nodes = (int64_t)f.nodes.size() * sizeof(Node8);
@@ -665,8 +662,8 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     const unsigned gt = (unsigned)std::max(1, std::min<int>(c->trace_blocks, (n_paths + 127) / 128));
                     if (mesh) {
                         lt.begin(1);
-                        if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below);
-                        else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below);
+                        if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den);
+                        else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den);
                         lt.end();
                         launches++;
                     }
@@ -677,8 +674,8 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     launches++;
                     if (mesh) {
                         lt.begin(3);
-                        if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below);
-                        else k_trace<true, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below);
+                        if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den);
+                        else k_trace<true, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den);
                         lt.end();
                         launches++;
                     }
@@ -844,6 +841,7 @@ int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
     case PTB_OPT_POOL_PATHS: if (value < 1024) return PTB_ERR_INVALID; c->pool_paths = value; return PTB_OK;
     case PTB_OPT_TIME_KERNELS: c->time_kernels = value != 0; return PTB_OK;
     case PTB_OPT_REFILL_BELOW: if (value < 1 || value > 33) return PTB_ERR_INVALID; c->refill_below = (int)value; return PTB_OK;
+    case PTB_OPT_TRI_FRACTION: if (value < 1 || value > 64) return PTB_ERR_INVALID; c->tri_den = (int)value; return PTB_OK;
     case PTB_OPT_TRACE_BLOCKS: if (value < 1) return PTB_ERR_INVALID; c->trace_blocks = (int)value; return PTB_OK;
     default: return PTB_OK;  // unknown options (e.g. the CPU checkers' thread count) are ignored
     }

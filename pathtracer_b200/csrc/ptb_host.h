@@ -70,4 +70,24 @@ struct HostScene {
 
 void build_matrix(HostObject& o);          // Object::build_matrix (Geometry.h:322-360)
 
+// Fill the by-value part of SceneDev from a flattened scene (pointers are the caller's business).
+inline void scene_header(SceneDev& sc, FlatScene& f) {
+    sc.n_objects = (int32_t)f.objects.size();
+    sc.has_mesh = f.nodes.empty() ? 0 : 1;
+    sc.envW = f.envW; sc.envH = f.envH; sc.has_envmap = (f.envW > 0 && f.envH > 0) ? 1 : 0;
+    sc.envmap_intensity = f.envmap_intensity; sc.lightPower = f.lightPower; sc.radiusLight = f.radiusLight;
+    sc.centerLight = v3(f.centerLight[0], f.centerLight[1], f.centerLight[2]);
+    sc.n_inline = 0; sc.n_extra = 0;
+    for (size_t i = 0; i < f.objects.size(); i++) {
+        ObjectDev& o = f.objects[i];
+        if (o.type == OBJ_MESH) continue;
+        if (sc.n_inline < PTB_INLINE_ANALYTIC) {
+            AnalyticDev& a = sc.analytic[sc.n_inline++];
+            a.type = o.type; a.id = (int32_t)i; a.R2 = o.R2;
+            for (int k = 0; k < 12; k++) a.inv_trans[k] = o.inv_trans[k];
+            for (int k = 0; k < 3; k++) { a.a[k] = o.a[k]; a.n[k] = o.n[k]; }
+        } else { o.flags |= FLAG_NOT_INLINE; sc.n_extra++; }
+    }
+}
+
 }  // namespace ptb

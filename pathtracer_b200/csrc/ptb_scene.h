@@ -14,7 +14,7 @@
 namespace ptb {
 
 enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2 };
-enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4 };
+enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4, FLAG_NOT_INLINE = 1 << 16 };
 enum { SLOT_KD = 1, SLOT_KS = 2, SLOT_NE = 4, SLOT_TRANSP = 8, SLOT_REFR = 16, SLOT_NORMAL = 32, SLOT_ALPHA = 64 };
 
 struct ObjectDev {          // Object / Sphere / Plane fields the path reads (Geometry.h:240-672, 849-1217)
@@ -42,6 +42,15 @@ struct alignas(16) TriShade {  // object-space vertex normals and tangents + ori
     int32_t pad;
 };
 
+// The handful of analytic objects every ray is tested against travel INSIDE the kernel parameter block (constant
+// bank, uniform loads) instead of being gathered from global memory by every thread.
+#define PTB_INLINE_ANALYTIC 8
+struct AnalyticDev {
+    int32_t type, id;           // OBJ_SPHERE / OBJ_PLANE, scene object id
+    float inv_trans[12];
+    float a[3], n[3], R2;
+};
+
 struct SceneDev {
     const F4* nodes;            // 5 x F4 per Node8
     const F4* tris;             // 3 x F4 per triangle, leaf order
@@ -55,6 +64,8 @@ struct SceneDev {
     int32_t n_objects, has_mesh, envW, envH, has_envmap, pad0;
     float envmap_intensity, lightPower, radiusLight;
     V3 centerLight;
+    int32_t n_inline, n_extra;  // analytic objects held inline below / left in `objects` (flag FLAG_NOT_INLINE)
+    AnalyticDev analytic[PTB_INLINE_ANALYTIC];
 };
 
 struct AlphaCtx {
@@ -98,12 +109,12 @@ PTB_HD V3 xf_rot(const float* m, V3 v) {     // apply_rotation (376-382), 3x3
 }
 
 // Sphere::intersection roots (Geometry.h:943-962): object-space ray, non-unit direction
-PTB_HD bool sphere_t(const ObjectDev& ob, V3 o, V3 d, float& t) {
-    const V3 O = v3(ob.a[0], ob.a[1], ob.a[2]);
+PTB_HD bool sphere_t(const float* A, float R2, V3 o, V3 d, float& t) {
+    const V3 O = v3(A[0], A[1], A[2]);
     const V3 oc = o - O;
     const float b = dot(d, oc);
     const float a = norm2(d);
-    const float c = norm2(oc) - ob.R2;
+    const float c = norm2(oc) - R2;
     const float delta = b * b - a * c;
     if (delta < 0) return false;
     const float sq = sqrtf(delta);
@@ -115,11 +126,11 @@ PTB_HD bool sphere_t(const ObjectDev& ob, V3 o, V3 d, float& t) {
     return true;
 }
 // Plane::intersection (Geometry.h:1142-1148)
-PTB_HD bool plane_t(const ObjectDev& ob, V3 o, V3 d, float& t) {
-    const V3 N = v3(ob.n[0], ob.n[1], ob.n[2]);
+PTB_HD bool plane_t(const float* A, const float* Nn, V3 o, V3 d, float& t) {
+    const V3 N = v3(Nn[0], Nn[1], Nn[2]);
     const float ddot = dot(d, N);
     if (fabsf(ddot) < 1E-9f) return false;
-    t = dot(v3(ob.a[0], ob.a[1], ob.a[2]) - o, N) / ddot;
+    t = dot(v3(A[0], A[1], A[2]) - o, N) / ddot;
     if (t <= 0.f) return false;
     return true;
 }
@@ -129,31 +140,45 @@ PTB_HD int32_t hit_id_analytic(int obj) { return -2 - obj; }
 
 // Nearest hit over the analytic objects (Sphere / Plane) of Scene::intersection's loop (Geometry.cpp:601-626):
 // object-space rays, world t.  Meshes are handled by the wide BVH afterwards.
+PTB_HD bool analytic_t(int type, const float* inv_trans, const float* A, const float* N, float R2, V3 o, V3 d, float& t) {
+    const V3 dl = xf_dir(inv_trans, d);
+    const V3 ol = xf_point(inv_trans, o);
+    return (type == OBJ_SPHERE) ? sphere_t(A, R2, ol, dl, t) : plane_t(A, N, ol, dl, t);
+}
 PTB_HD void analytic_closest(const SceneDev& sc, V3 o, V3 d, float& tmin, int32_t& id) {
     tmin = INFINITY;
     id = PTB_HIT_MISS;
-    for (int i = 0; i < sc.n_objects; i++) {
-        const ObjectDev& ob = sc.objects[i];
-        if (ob.type == OBJ_MESH) continue;
-        const V3 dl = xf_dir(ob.inv_trans, d);
-        const V3 ol = xf_point(ob.inv_trans, o);
+    int best = -1;
+    // object order matters only for exact ties (strict `t < min_t`, Geometry.cpp:615): inline objects keep scene order
+    for (int i = 0; i < sc.n_inline; i++) {
+        const AnalyticDev& ob = sc.analytic[i];
         float t;
-        const bool h = (ob.type == OBJ_SPHERE) ? sphere_t(ob, ol, dl, t) : plane_t(ob, ol, dl, t);
-        if (h && t < tmin) { tmin = t; id = hit_id_analytic(i); }
+        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && t < tmin) { tmin = t; best = ob.id; }
     }
+    if (sc.n_extra > 0)
+        for (int i = 0; i < sc.n_objects; i++) {
+            const ObjectDev& ob = sc.objects[i];
+            if (ob.type == OBJ_MESH || !(ob.flags & FLAG_NOT_INLINE)) continue;
+            float t;
+            if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (t < tmin || (t == tmin && i < best))) { tmin = t; best = i; }
+        }
+    if (best >= 0) id = hit_id_analytic(best);
 }
 // Analytic part of Scene::intersection_shadow (Geometry.cpp:721-741): any object closer than 0.999*dist_light
 PTB_HD bool analytic_occluded(const SceneDev& sc, V3 o, V3 d, float dist_light) {
     const double lim = (double)dist_light * 0.999;
-    for (int i = 0; i < sc.n_objects; i++) {
-        const ObjectDev& ob = sc.objects[i];
-        if (ob.type == OBJ_MESH) continue;
-        const V3 dl = xf_dir(ob.inv_trans, d);
-        const V3 ol = xf_point(ob.inv_trans, o);
+    for (int i = 0; i < sc.n_inline; i++) {
+        const AnalyticDev& ob = sc.analytic[i];
         float t;
-        const bool h = (ob.type == OBJ_SPHERE) ? sphere_t(ob, ol, dl, t) : plane_t(ob, ol, dl, t);
-        if (h && (double)t < lim) return true;
+        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (double)t < lim) return true;
     }
+    if (sc.n_extra > 0)
+        for (int i = 0; i < sc.n_objects; i++) {
+            const ObjectDev& ob = sc.objects[i];
+            if (ob.type == OBJ_MESH || !(ob.flags & FLAG_NOT_INLINE)) continue;
+            float t;
+            if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (double)t < lim) return true;
+        }
     return false;
 }
 PTB_HD AlphaCtx alpha_ctx(const SceneDev& sc) {

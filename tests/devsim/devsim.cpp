@@ -47,9 +47,7 @@ int ptb_commit(ptb_ctx* c) {
     FlatScene& f = c->flat; SceneDev& sc = c->sc;
     sc.nodes = reinterpret_cast<const F4*>(f.nodes.data()); sc.tris = f.tris.data(); sc.tri_uv = f.tri_uv.data(); sc.tri_shade = f.tri_shade.data();
     sc.objects = f.objects.data(); sc.materials = f.materials.data(); sc.texels = f.texels.data(); sc.envmap = f.envmap.data(); sc.merl = f.merl.data();
-    sc.n_objects = (int)f.objects.size(); sc.has_mesh = f.nodes.empty() ? 0 : 1; sc.envW = f.envW; sc.envH = f.envH; sc.has_envmap = f.envW > 0;
-    sc.envmap_intensity = f.envmap_intensity; sc.lightPower = f.lightPower; sc.radiusLight = f.radiusLight;
-    sc.centerLight = v3(f.centerLight[0], f.centerLight[1], f.centerLight[2]);
+    scene_header(sc, f);
     c->committed = true;
     return PTB_OK;
 }

@@ -146,6 +146,10 @@ def edge_scene(L, variant, W=37, H=23, spp=3):
         rt.s.addObject(m)
         pl = rt.s.objects[2]
         pl.set_material(0, Kd=Texture((1, 1, 1), kd))
+    elif variant == "many_spheres":      # more analytic objects than the kernel-parameter table holds (8)
+        for k in range(9):
+            c = (-16 + 4 * k, -22.3 + (k % 3), -6 + 3 * (k % 4))
+            rt.s.addObject(Sphere(c, 2.5 + 0.3 * (k % 3)).set_material(0, **scenes.phong((.2 + .08 * k, .5, .9 - .08 * k), 0.1 * (k % 2), 20.0)))
     elif variant == "wide_filter":
         rt.sigma_filter = 1.0
         rt.s.addObject(Sphere((0, -17.3, 0), 10).set_material(0, **scenes.phong((.8, .3, .3), 0.0, 1.0)))
@@ -157,7 +161,7 @@ def edge_scene(L, variant, W=37, H=23, spp=3):
     return rt
 
 
-EDGE_VARIANTS = ["mirror_and_flip", "mesh_no_uv_groups", "mesh_flat", "textured_rotated", "wide_filter", "depth_one"]
+EDGE_VARIANTS = ["many_spheres", "mirror_and_flip", "mesh_no_uv_groups", "mesh_flat", "textured_rotated", "wide_filter", "depth_one"]
 
 
 def case_edge(test_lib, oracle_lib, variant):
