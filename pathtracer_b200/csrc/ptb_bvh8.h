@@ -119,7 +119,7 @@ __device__ __forceinline__ uint32_t node_hitmask(const F4& n0, const F4& n1, con
         planes4(negz ? hiz : loz, adz, boz, tnz[0], tnz[1], tnz[2], tnz[3]);
         planes4(negz ? loz : hiz, adz, boz, tfz[0], tfz[1], tfz[2], tfz[3]);
         const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = __byte_perm(is_inner4 << 3, 0u, 0xba98);          // per byte: 0xff iff internal child
+        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;                          // per byte: 0xff iff internal child
         const uint32_t bit_index4 = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
         const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
