@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev sc, FrameDev f, PoolDev
 // direct term to the path's radiance).  Closest-hit results overwrite the analytic hit record the ray's producer wrote.
 template <bool ANY_HIT, bool COUNT>
 __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
-                                               int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below, int tri_den) {
+                                               int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below, int tri_den, int tri_min_pct) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n = count ? *count : (uint32_t)n_static;
@@ -119,7 +119,12 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
             if (exhausted) break;
             continue;
         }
-        // ---- pop / finish: lanes with neither node nor triangle work
+        // ---- pop / finish: lanes without node work.  A lane still holding postponed triangles swaps them for the node
+        //      group on top of its stack (if there is one) so that it keeps feeding the node phase.
+        if (live && ngroup.y <= 0x00ffffffu && tgroup.y != 0 && sp > 0) {
+            const U2 e = stack[sp - 1];
+            if (e.y > 0x00ffffffu) { stack[sp - 1] = tgroup; ngroup = e; tgroup.y = 0; }
+        }
         if (live && ngroup.y <= 0x00ffffffu && tgroup.y == 0) {
             if (sp > 0) {
                 const U2 e = stack[--sp];
@@ -160,10 +165,13 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
             ngroup.y = (hm & 0xff000000u) | (f2u(n0.w) >> 24);
             tgroup.y = hm & 0x00ffffffu;
         }
-        // ---- triangle phase: at least one step, more while a quarter of the live lanes take part
+        // ---- triangle phase: entered once enough live lanes hold triangle work (tri_min_pct) or nobody can do anything
+        //      else; repeats while >= 1/tri_den of the live lanes take part.  (ncu, r01b: run every iteration it had 6 of
+        //      32 lanes active and cost a third of the issue slots.)
         uint32_t tm = __ballot_sync(FULL, live && tgroup.y != 0);
-        if (tm != 0) {
-            const int live_n = __popc(__ballot_sync(FULL, live));
+        const uint32_t other = __ballot_sync(FULL, live && (ngroup.y > 0x00ffffffu || tgroup.y == 0));   // lanes that progress without it
+        const int live_n = __popc(__ballot_sync(FULL, live));
+        if (tm != 0 && (__popc(tm) * 100 >= tri_min_pct * live_n || other == 0)) {
             do {
                 if (live && tgroup.y != 0) {
                     const uint32_t ti = highest_bit(tgroup.y);
@@ -347,6 +355,7 @@ struct ptb_ctx {
     bool time_kernels = false;
     int trace_blocks = 148 * 8;                // persistent grid of k_trace, set from the occupancy query in ptb_create
     int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
+    int tri_min_pct = 20;                      // the triangle phase starts once this share of a warp's live lanes hold triangles
     int tri_den = 4;                           // triangle steps repeat while >= 1/tri_den of the live lanes take part
     std::vector<cudaEvent_t> ev_pool;          // PTB_OPT_TIME_KERNELS: start/stop pairs, one per launch
     std::vector<int> ev_kind;
@@ -662,8 +671,8 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     const unsigned gt = (unsigned)std::max(1, std::min<int>(c->trace_blocks, (n_paths + 127) / 128));
                     if (mesh) {
                         lt.begin(1);
-                        if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den);
-                        else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den);
+                        if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                        else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
                         lt.end();
                         launches++;
                     }
@@ -674,8 +683,8 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     launches++;
                     if (mesh) {
                         lt.begin(3);
-                        if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den);
-                        else k_trace<true, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den);
+                        if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                        else k_trace<true, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
                         lt.end();
                         launches++;
                     }
@@ -842,6 +851,7 @@ int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
     case PTB_OPT_TIME_KERNELS: c->time_kernels = value != 0; return PTB_OK;
     case PTB_OPT_REFILL_BELOW: if (value < 1 || value > 33) return PTB_ERR_INVALID; c->refill_below = (int)value; return PTB_OK;
     case PTB_OPT_TRI_FRACTION: if (value < 1 || value > 64) return PTB_ERR_INVALID; c->tri_den = (int)value; return PTB_OK;
+    case PTB_OPT_TRI_MIN_PCT: if (value < 0 || value > 100) return PTB_ERR_INVALID; c->tri_min_pct = (int)value; return PTB_OK;
     case PTB_OPT_TRACE_BLOCKS: if (value < 1) return PTB_ERR_INVALID; c->trace_blocks = (int)value; return PTB_OK;
     default: return PTB_OK;  // unknown options (e.g. the CPU checkers' thread count) are ignored
     }
