@@ -119,12 +119,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
             if (exhausted) break;
             continue;
         }
-        // ---- pop / finish: lanes without node work.  A lane still holding postponed triangles swaps them for the node
-        //      group on top of its stack (if there is one) so that it keeps feeding the node phase.
-        if (live && ngroup.y <= 0x00ffffffu && tgroup.y != 0 && sp > 0) {
-            const U2 e = stack[sp - 1];
-            if (e.y > 0x00ffffffu) { stack[sp - 1] = tgroup; ngroup = e; tgroup.y = 0; }
-        }
+        // ---- pop / finish: lanes with neither node nor triangle work
         if (live && ngroup.y <= 0x00ffffffu && tgroup.y == 0) {
             if (sp > 0) {
                 const U2 e = stack[--sp];
@@ -165,9 +160,9 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
             ngroup.y = (hm & 0xff000000u) | (f2u(n0.w) >> 24);
             tgroup.y = hm & 0x00ffffffu;
         }
-        // ---- triangle phase: entered once enough live lanes hold triangle work (tri_min_pct) or nobody can do anything
-        //      else; repeats while >= 1/tri_den of the live lanes take part.  (ncu, r01b: run every iteration it had 6 of
-        //      32 lanes active and cost a third of the issue slots.)
+        // ---- triangle phase: entered when tri_min_pct % of the live lanes hold triangle work (default 0: always; postponing
+        //      further was measured to cost more node visits than it saves issue slots) or when nobody can do anything else;
+        //      repeats while >= 1/tri_den of the live lanes take part.
         uint32_t tm = __ballot_sync(FULL, live && tgroup.y != 0);
         const uint32_t other = __ballot_sync(FULL, live && (ngroup.y > 0x00ffffffu || tgroup.y == 0));   // lanes that progress without it
         const int live_n = __popc(__ballot_sync(FULL, live));
@@ -213,6 +208,7 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool want) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+template <bool MERL>
 __global__ void __launch_bounds__(128) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
                                                const uint32_t* __restrict__ count, int n_static, uint32_t* __restrict__ next_queue,
                                                uint32_t* next_count, uint32_t* shadow_count, uint32_t* shadow_queries) {
@@ -223,7 +219,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, FrameDev f, PoolDev 
     int path = 0;
     if (tid < n) {
         path = queue ? (int)queue[tid] : tid;
-        shade_one(sc, f, p, path, out);
+        shade_one<MERL>(sc, f, p, path, out);
     }
     const uint32_t qi = warp_push(next_count, out.cont);
     if (out.cont) next_queue[qi] = (uint32_t)path;
@@ -353,9 +349,10 @@ struct ptb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool count_traversal = false;
     bool time_kernels = false;
+    bool has_merl = false;
     int trace_blocks = 148 * 8;                // persistent grid of k_trace, set from the occupancy query in ptb_create
     int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
-    int tri_min_pct = 20;                      // the triangle phase starts once this share of a warp's live lanes hold triangles
+    int tri_min_pct = 0;                       // the triangle phase starts once this share of a warp's live lanes hold triangles
     int tri_den = 4;                           // triangle steps repeat while >= 1/tri_den of the live lanes take part
     std::vector<cudaEvent_t> ev_pool;          // PTB_OPT_TIME_KERNELS: start/stop pairs, one per launch
     std::vector<int> ev_kind;
@@ -537,6 +534,8 @@ int ptb_commit(ptb_ctx* c) {
     SceneDev& sc = c->sc;
     memset(&sc, 0, sizeof(sc));
     scene_header(sc, f);        // before the upload: it tags objects that do not fit the inline table
+    c->has_merl = false;
+    for (const ObjectDev& o : f.objects) if (o.brdf == 1) c->has_merl = true;
     const Node8* dn; const F4* dt; const uint8_t* de;
     if ((rc = upload(c, f.nodes.data(), f.nodes.size(), &dn))) return rc;
     if ((rc = upload(c, f.tris.data(), f.tris.size(), &dt))) return rc;
@@ -677,8 +676,10 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         launches++;
                     }
                     lt.begin(2);
-                    k_shade<<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1),
-                                                         c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b);
+                    if (c->has_merl) k_shade<true><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1),
+                                                                               c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b);
+                    else k_shade<false><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1),
+                                                                     c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b);
                     lt.end();
                     launches++;
                     if (mesh) {

@@ -409,6 +409,9 @@ struct ShadeOut {
     F4 sh_o, sh_d, sh_c;
 };
 
+// MERL = the scene holds at least one IsoMERLBRDF object; scenes without one get a kernel free of the double-precision
+// lookup code (fewer registers, higher occupancy).
+template <bool MERL>
 PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path, ShadeOut& out) {
     out.cont = false; out.shadow = false; out.shadow_query = false;
     const F4 hq = p.hit[path];
@@ -479,10 +482,14 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
         const float d2 = norm2(toL);
         if (!(dot(N, wi) < 0)) {
             V3 fr;
-            if (ob.brdf == 1) fr = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, wi, -rd, N);
+            if (MERL && ob.brdf == 1) fr = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, wi, -rd, N);
             else fr = phong_eval(s.Kd, s.Ks, s.Ne, wi, -rd, N);
             const float J = dot(dirl, -wi) / d2;
+#if defined(__CUDA_ARCH__)
+            const float proba = dot(axeOP, dirl) / (PTB_PI_F * (sc.radiusLight * sc.radiusLight));
+#else
             const float proba = (float)((double)dot(axeOP, dirl) / (PTB_PI_D * (double)(sc.radiusLight * sc.radiusLight)));
+#endif
             if (proba > 0.f) {
                 const float g = sc.lightPower * fmaxf(0.f, dot(N, wi)) * J / proba;
                 const V3 c = w * (g * fr);
@@ -514,7 +521,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
         const float r2 = frac_pos(f.rpp[2 * pix + 1] + sy);
         float pdf;
         V3 dir;
-        if (ob.brdf == 1) {
+        if (MERL && ob.brdf == 1) {
             dir = random_cos(N, r1, r2);
             pdf = (float)((double)dot(N, dir) / PTB_PI_D);
         } else {
@@ -525,7 +532,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
         p.rng[path] = e.state;
         if (dot(dir, N) < 0 || dot(dir, reflect(rd, N)) < 0 || pdf <= 0) return;
         V3 fi;
-        if (ob.brdf == 1) fi = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, dir, -rd, N);
+        if (MERL && ob.brdf == 1) fi = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, dir, -rd, N);
         else fi = phong_eval(s.Kd, s.Ks, s.Ne, dir, -rd, N);
         nw = (w * fi) * (dot(N, dir) / pdf);
         no = P + 0.01f * dir;

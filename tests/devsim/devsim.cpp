@@ -85,7 +85,7 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
         for (long long i = 0; i < n; i++) { TraverseCounters tc{0, 0}; if (c->sc.has_mesh) extend_one<true>(c->sc, pool, (int)q0[i], &tc); nodes += tc.nodes; tris += tc.tris; }
         std::vector<ShadeOut> outs(n);
 #pragma omp parallel for schedule(dynamic, 256)
-        for (long long i = 0; i < n; i++) shade_one(c->sc, f, pool, (int)q0[i], outs[i]);
+        for (long long i = 0; i < n; i++) shade_one<true>(c->sc, f, pool, (int)q0[i], outs[i]);
         q1.clear();
         size_t ns = 0;
         for (long long i = 0; i < n; i++) {
