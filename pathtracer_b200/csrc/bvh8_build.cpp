@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace ptb {
@@ -51,7 +52,10 @@ struct Builder {
 };
 
 constexpr int NBINS = 16;
-constexpr float C_TRAV = 0.5f;   // binary nodes mostly vanish in the collapse
+// builder knobs (environment overrides are for experiments only; the defaults are what ships)
+static float env_f(const char* n, float d) { const char* v = getenv(n); return v ? (float)atof(v) : d; }
+static const float C_TRAV = env_f("PTB_BVH_CTRAV", 0.25f);   // binary nodes mostly vanish in the collapse
+static const int MAX_LEAF = (int)env_f("PTB_BVH_MAXLEAF", 3.f);
 
 void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
     BNode& nd = nodes[node];
@@ -91,10 +95,10 @@ void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
     }
     int64_t mid;
     if (best_axis < 0) {
-        if (cnt <= 3) { make_leaf(); return; }
+        if (cnt <= MAX_LEAF) { make_leaf(); return; }
         mid = b + cnt / 2;  // coincident centroids: split by index
     } else {
-        if (cnt <= 3) {
+        if (cnt <= MAX_LEAF) {
             const float A = box.area();
             if (!(C_TRAV * A + best_cost < (float)cnt * A)) { make_leaf(); return; }
         }
