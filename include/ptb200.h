@@ -193,7 +193,7 @@ int ptb_primary_ids(ptb_ctx*, const ptb_camera*, int W, int H,
 
 /* ---- options and introspection ----------------------------------------------------------------- */
 #define PTB_OPT_COUNT_TRAVERSAL  1   /* 1: count node visits / triangle tests (instrumented kernels) */
-#define PTB_OPT_POOL_PATHS       2   /* paths in flight per pass (default 1<<24) */
+#define PTB_OPT_POOL_PATHS       2   /* paths in flight per pass (default 1<<25, about 5.7 GB of HBM) */
 #define PTB_OPT_TIME_KERNELS     3   /* 1: bracket every kernel launch with CUDA events (see ptb_get_kernel_times) */
 #define PTB_OPT_REFILL_BELOW     4   /* tuning: a traversal warp refills idle lanes when fewer than this many are live (1..33) */
 #define PTB_OPT_TRI_FRACTION     6   /* tuning: triangle steps repeat while >= 1/value of a warp's live lanes have triangle work */

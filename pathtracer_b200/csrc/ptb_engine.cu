@@ -334,7 +334,7 @@ struct ptb_ctx {
     double ms_upload = 0;
     int64_t bytes_nodes = 0, bytes_tris = 0, bytes_attr = 0, bytes_tex = 0;
     // path pool
-    int64_t pool_paths = (int64_t)1 << 24, pool_cap = 0;
+    int64_t pool_paths = (int64_t)1 << 25, pool_cap = 0;   // measured: larger pools amortise the tails of the persistent kernels (tune4.log)
     PoolDev pool;
     uint32_t* d_queue[2] = {nullptr, nullptr};
     uint32_t* d_counters = nullptr;
