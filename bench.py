@@ -9,7 +9,7 @@ BVH build and upload happen once before the timed region and are reported separa
   value   whole-job Msamples/s with the scene resident in HBM and the frame left in HBM (ptb_render_accum)
   e2e     the same through the reference-shaped call Raytracer::render_image_nopreviz() with HOST buffers:
           camera + parameters go host->device, imagedouble + sample_count + 8-bit image come back every step
-  roofline  the dominant kernel (k_extend, closest-hit traversal) against the measured HBM copy bandwidth
+  roofline  the dominant kernel (k_trace, closest-hit BVH8 traversal) against the measured HBM copy bandwidth
   cpu_baseline  the reference's own CPU code (oracle/_ref) or its C restatement (oracle/port) on this box's cores
 For N > 1 (torchrun, one rank per GPU) the frame is tile-sharded and gathered once over NCCL; value = samples of
 all ranks / max-over-ranks time: strong scaling on the fixed frame.
@@ -282,9 +282,9 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get("k_extend_dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("k_trace_closest_dram_bytes_per_launch")
     step_kernel_ms = sum(v["ms"] for v in kt.values())
-    line["roofline"] = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    line["roofline"] = {"bound": "hbm", "kernel": "k_trace<closest-hit> (BVH8 traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                         "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "n_node": n_node, "n_tri": n_tri,
                         "rays_per_launch": rays_per_launch, "launch_ms": ext_launch_ms, "launches_per_step": ext["launches"],
                         "share_of_step": ext["ms"] / step_kernel_ms if step_kernel_ms else None,
