@@ -198,7 +198,6 @@ int ptb_primary_ids(ptb_ctx*, const ptb_camera*, int W, int H,
 #define PTB_OPT_REFILL_BELOW     4   /* tuning: a traversal warp refills idle lanes when fewer than this many are live (1..33) */
 #define PTB_OPT_TRI_FRACTION     6   /* tuning: triangle steps repeat while >= 1/value of a warp's live lanes have triangle work */
 #define PTB_OPT_TRI_MIN_PCT      7   /* tuning: the triangle phase of a warp starts once this % of its live lanes hold triangle work */
-#define PTB_OPT_TRACE_MINB       8   /* tuning: traversal kernel variant compiled for >= value resident blocks per SM (8, 10, 12, 16) */
 #define PTB_OPT_TRACE_BLOCKS     5   /* tuning: persistent grid size of the traversal kernels (default: SMs x resident blocks) */
 int ptb_set_option(ptb_ctx*, int option, int64_t value);
 

@@ -208,8 +208,8 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool want) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
-template <bool MERL>
-__global__ void __launch_bounds__(128) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
+template <bool MERL, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
                                                const uint32_t* __restrict__ count, int n_static, uint32_t* __restrict__ next_queue,
                                                uint32_t* next_count, uint32_t* shadow_count, uint32_t* shadow_queries) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -350,6 +350,7 @@ struct ptb_ctx {
     bool count_traversal = false;
     bool time_kernels = false;
     bool has_merl = false;
+    int shade_minb = 8;                        // k_shade variant (resident blocks/SM the compiler must allow); PTB_SHADE_MINB overrides for experiments
     int trace_blocks = 148 * 8;                // persistent grid of k_trace, set from the occupancy query in ptb_create
     int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
     int tri_min_pct = 0;                       // the triangle phase starts once this share of a warp's live lanes hold triangles
@@ -428,6 +429,7 @@ int ptb_create(int device_id, ptb_ctx** out) {
     if (device_id < 0 || device_id >= n) { g_create_err = "device id out of range"; return PTB_ERR_INVALID; }
     ptb_ctx* c = new ptb_ctx();
     c->device = device_id;
+    if (const char* e = getenv("PTB_SHADE_MINB")) c->shade_minb = atoi(e);
     memset(&c->pool, 0, sizeof(c->pool));
     memset(&c->sc, 0, sizeof(c->sc));
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -669,21 +671,24 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     // persistent grid: as many blocks as are resident at once, but no more than the queue can feed
                     const unsigned gt = (unsigned)std::max(1, std::min<int>(c->trace_blocks, (n_paths + 127) / 128));
                     if (mesh) {
-                        lt.begin(1);
+                        lt.begin(1 | (b << 8));
                         if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
                         else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
                         lt.end();
                         launches++;
                     }
-                    lt.begin(2);
-                    if (c->has_merl) k_shade<true><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1),
-                                                                               c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b);
-                    else k_shade<false><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1),
-                                                                     c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b);
+                    lt.begin(2 | (b << 8));
+#define PTB_SHADE(M, MB) k_shade<M, MB><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1), \
+                                                                    c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b)
+                    if (c->has_merl) PTB_SHADE(true, 5);
+                    else if (c->shade_minb == 8) PTB_SHADE(false, 8);
+                    else if (c->shade_minb == 10) PTB_SHADE(false, 10);
+                    else PTB_SHADE(false, 6);
+#undef PTB_SHADE
                     lt.end();
                     launches++;
                     if (mesh) {
-                        lt.begin(3);
+                        lt.begin(3 | (b << 8));
                         if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
                         else k_trace<true, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
                         lt.end();
@@ -708,8 +713,22 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
         for (size_t i = 0; i < c->ev_kind.size(); i++) {
             float ms = 0;
             cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]);
-            kt.ms[c->ev_kind[i]] += ms;
-            kt.launches[c->ev_kind[i]]++;
+            kt.ms[c->ev_kind[i] & 0xff] += ms;
+            kt.launches[c->ev_kind[i] & 0xff]++;
+        }
+        if (getenv("PTB_DEBUG_BOUNCES")) {   // per-bounce launch times of the LAST pass + its queue lengths (diagnostics only)
+            uint32_t cnt[PTB_N_COUNTERS];
+            cudaMemcpy(cnt, c->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost);
+            const size_t per_pass = 2 + 3 * (size_t)f.nb_bounces;
+            const size_t first = c->ev_kind.size() >= per_pass ? c->ev_kind.size() - per_pass : 0;
+            for (size_t i = first; i < c->ev_kind.size(); i++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]);
+                const int kind = c->ev_kind[i] & 0xff, b = c->ev_kind[i] >> 8;
+                const char* names[] = {"raygen", "closest", "shade", "anyhit", "splat"};
+                const unsigned items = kind == 3 ? cnt[2 * b + 1] : ((kind == 1 || kind == 2) ? (b == 0 ? 0u : cnt[2 * b]) : 0u);
+                fprintf(stderr, "[ptb] %-8s b=%d  %8.3f ms  items=%u\n", names[kind], b, ms, items);
+            }
         }
         kt.items[0] = kt.items[4] = valid_pixels * (unsigned long long)nrays;
         kt.items[1] = kt.items[2] = t[0]; kt.items[3] = t[1];
