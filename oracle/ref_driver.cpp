@@ -402,4 +402,179 @@ int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H,
     return PTB_OK;
 }
 
+
+// ---- the reference's own FILE READERS behind the accessor shapes of include/ptb_sceneio.h (prefix ref_) ----------------
+// Used by tests/golden/make_golden.py and tests/test_scene_io.py to pin pathtracer_b200/csrc/scene_io.cpp: the same Python
+// comparison code walks the product's handles and these.
+#include "ptb_sceneio.h"
+
+struct ref_meshfile_t { TriMesh* g; bool has_materials; std::vector<float> v, n, uv, vc; std::vector<int32_t> tri; };
+
+static void ref_copy_str(char* dst, const std::string& s) {
+    size_t n = s.size() < PTB_PATH_MAX - 1 ? s.size() : PTB_PATH_MAX - 1;
+    memcpy(dst, s.data(), n); dst[n] = 0;
+}
+static void ref_slot_from_tex(const Texture& t, ptb_slot* out) {
+    // a slot whose image did not load keeps W == 0: report it as constant ("" file) like the product's reader resolves it
+    ref_copy_str(out->file, (t.W > 0) ? t.filename : std::string());
+    for (int k = 0; k < 3; k++) out->mult[k] = t.multiplier[k];
+}
+static const std::vector<Texture>* ref_slot_vector(const Object* o, int kind) {
+    switch (kind) {
+    case PTB_KIND_KD: return &o->textures;
+    case PTB_KIND_NORMAL: return &o->normal_map;
+    case PTB_KIND_SUBSURF: return &o->subsurface;
+    case PTB_KIND_KS: return &o->specularmap;
+    case PTB_KIND_ALPHA: return &o->alphamap;
+    case PTB_KIND_NE: return &o->roughnessmap;
+    case PTB_KIND_TRANSP: return &o->transparent_map;
+    case PTB_KIND_REFR: return &o->refr_index_map;
+    }
+    return NULL;
+}
+
+int ref_image_load(const char* path, uint8_t** rgb, int32_t* W, int32_t* H) {
+    std::vector<unsigned char> v; size_t w = 0, h = 0;
+    if (!load_image(path, v, w, h)) return PTB_ERR_INVALID;
+    *rgb = (uint8_t*)malloc(v.size()); memcpy(*rgb, v.data(), v.size()); *W = (int32_t)w; *H = (int32_t)h;
+    return PTB_OK;
+}
+void ref_image_free(void* p) { free(p); }
+int ref_texture_load(const char* path, int kind, float** values, int32_t* W, int32_t* H) {
+    Texture t;
+    t.W = 0; t.H = 0;
+    if (kind == 0) t.loadColors(path); else t.loadNormals(path);
+    if (t.W == 0) return PTB_ERR_INVALID;
+    *values = (float*)malloc(t.values.size() * sizeof(float)); memcpy(*values, t.values.data(), t.values.size() * sizeof(float));
+    *W = (int32_t)t.W; *H = (int32_t)t.H;
+    return PTB_OK;
+}
+
+int ref_meshfile_read(const char* path, int load_textures, void** out) {
+    ref_meshfile_t* m = new ref_meshfile_t();
+    m->g = new TriMesh();
+    m->has_materials = load_textures != 0;
+    std::string lo(path); for (size_t i = 0; i < lo.size(); i++) lo[i] = tolower(lo[i]);
+    FILE* probe = fopen(path, "r");
+    if (!probe) { delete m; return PTB_ERR_INVALID; }
+    fclose(probe);
+    if (lo.find(".off") != std::string::npos) m->g->readOFF(path);        // TriMesh::init's dispatch (TriangleMesh.cpp:729-741)
+    else if (lo.find(".obj") != std::string::npos) m->g->readOBJ(path, load_textures != 0);
+    else { delete m; return PTB_ERR_UNSUPPORTED; }
+    TriMesh* g = m->g;
+    for (size_t i = 0; i < g->vertices.size(); i++) for (int k = 0; k < 3; k++) m->v.push_back(g->vertices[i][k]);
+    for (size_t i = 0; i < g->normals.size(); i++) for (int k = 0; k < 3; k++) m->n.push_back(g->normals[i][k]);
+    for (size_t i = 0; i < g->uvs.size(); i++) for (int k = 0; k < 2; k++) m->uv.push_back(g->uvs[i][k]);
+    for (size_t i = 0; i < g->vertexcolors.size(); i++) for (int k = 0; k < 3; k++) m->vc.push_back(g->vertexcolors[i][k]);
+    for (size_t i = 0; i < g->indices.size(); i++) {
+        const TriangleIndices& t = g->indices[i];
+        int32_t r[10] = {t.vtxi, t.vtxj, t.vtxk, t.uvi, t.uvj, t.uvk, t.ni, t.nj, t.nk, t.group};
+        m->tri.insert(m->tri.end(), r, r + 10);
+    }
+    *out = m;
+    return PTB_OK;
+}
+void ref_meshfile_free(void* h) { delete (ref_meshfile_t*)h; }
+int ref_meshfile_get(const void* h, ptb_meshfile_info* o) {
+    const ref_meshfile_t* m = (const ref_meshfile_t*)h;
+    o->vertices = m->v.data(); o->n_vertices = (int32_t)(m->v.size() / 3);
+    o->normals = m->n.data(); o->n_normals = (int32_t)(m->n.size() / 3);
+    o->uvs = m->uv.data(); o->n_uvs = (int32_t)(m->uv.size() / 2);
+    o->vertex_colors = m->vc.data(); o->n_vertex_colors = (int32_t)(m->vc.size() / 3);
+    o->tri = m->tri.data(); o->n_tri = (int32_t)(m->tri.size() / 10);
+    o->n_groups = (int32_t)m->g->groupNames.size();
+    o->has_materials = m->has_materials ? 1 : 0;
+    return PTB_OK;
+}
+int ref_meshfile_group_name(const void* h, int group, char name[PTB_PATH_MAX]) {
+    const ref_meshfile_t* m = (const ref_meshfile_t*)h;
+    for (std::map<std::string, int>::const_iterator it = m->g->groupNames.begin(); it != m->g->groupNames.end(); ++it)
+        if (it->second == group) { ref_copy_str(name, it->first); return PTB_OK; }
+    return PTB_ERR_INVALID;
+}
+int ref_meshfile_group_slot(const void* h, int group, int kind, ptb_slot* out) {
+    const ref_meshfile_t* m = (const ref_meshfile_t*)h;
+    const std::vector<Texture>* v = ref_slot_vector(m->g, kind);
+    if (!v || group < 0 || group >= (int)v->size()) return PTB_ERR_INVALID;
+    ref_slot_from_tex((*v)[group], out);
+    return PTB_OK;
+}
+
+int ref_scn_load(const char* path, const char* replaced, void** out) {
+    FILE* probe = fopen(path, "r");
+    if (!probe) return PTB_ERR_INVALID;
+    fclose(probe);
+    ptb_ctx* c = NULL;
+    ptb_create(0, &c);
+    c->rt->load_scene(path, replaced);
+    *out = c;
+    return PTB_OK;
+}
+void ref_scn_free(void* h) { ptb_destroy((ptb_ctx*)h); }
+int ref_scn_get_header(const void* hh, ptb_scn_header* h) {
+    const Raytracer* rt = ((const ptb_ctx*)hh)->rt;
+    memset(h, 0, sizeof(*h));
+    h->W = rt->W; h->H = rt->H; h->nrays = rt->nrays; h->nbframes = rt->s.nbframes; h->nb_bounces = rt->nb_bounces;
+    h->has_denoiser = rt->has_denoiser; h->is_lenticular = rt->cam.is_lenticular; h->n_objects = (int32_t)rt->s.objects.size();
+    for (int k = 0; k < 3; k++) { h->cam.position[k] = rt->cam.position[k]; h->cam.direction[k] = rt->cam.direction[k]; h->cam.up[k] = rt->cam.up[k]; }
+    h->cam.fov = rt->cam.fov; h->cam.focus_distance = rt->cam.focus_distance; h->cam.aperture = rt->cam.aperture;
+    h->sigma_filter = rt->sigma_filter; h->gamma = rt->gamma; h->intensite_lumiere = rt->s.intensite_lumiere; h->envmap_intensity = rt->s.envmap_intensity;
+    h->fog_density = rt->s.fog_density; h->fog_absorption = rt->s.fog_absorption; h->fog_density_decay = rt->s.fog_density_decay;
+    h->fog_absorption_decay = rt->s.fog_absorption_decay; h->fog_type = rt->s.fog_type; h->fog_phase_type = rt->s.fog_phase_type;
+    h->double_frustum_start_t = rt->s.double_frustum_start_t;
+    if (rt->s.backgroundW > 0) ref_copy_str(h->background, rt->s.backgroundfilename);
+    return PTB_OK;
+}
+int ref_scn_get_object(const void* hh, int i, ptb_scn_object* o) {
+    const Raytracer* rt = ((const ptb_ctx*)hh)->rt;
+    if (i < 0 || i >= (int)rt->s.objects.size()) return PTB_ERR_INVALID;
+    Object* b = rt->s.objects[i];
+    memset(o, 0, sizeof(*o));
+    o->type = b->type == OT_TRIMESH ? PTB_SCN_MESH : b->type == OT_SPHERE ? PTB_SCN_SPHERE : b->type == OT_PLANE ? PTB_SCN_PLANE : PTB_SCN_POINTSET;
+    ref_copy_str(o->name, b->name);
+    o->miroir = b->miroir; o->ghost = b->ghost; o->display_edges = b->display_edges; o->interp_normals = b->interp_normals; o->flip_normals = b->flip_normals;
+    o->n_keyframes = (int32_t)b->translation_keyframes.size();
+    o->xform.scale = b->get_scale(0, false);
+    Matrix33 R = b->get_rotation(0, false);
+    Vector T = b->get_translation(0, false);
+    for (int k = 0; k < 9; k++) o->xform.rotation[k] = R[k];
+    for (int k = 0; k < 3; k++) { o->xform.rotation_center[k] = b->rotation_center[k]; o->xform.translation[k] = T[k]; }
+    for (int k = 0; k < PTB_N_KINDS; k++) o->n_slots[k] = (int32_t)ref_slot_vector(b, k)->size();
+    if (Sphere* sp = dynamic_cast<Sphere*>(b)) {
+        o->is_envmap = sp->has_envmap; if (sp->has_envmap) ref_copy_str(o->envmap, sp->envmapfilename);
+        for (int k = 0; k < 3; k++) o->O[k] = sp->O[k];
+        o->R = sp->R;
+    } else if (Plane* pl = dynamic_cast<Plane*>(b)) {
+        for (int k = 0; k < 3; k++) { o->A[k] = pl->A[k]; o->N[k] = pl->vecN[k]; }
+    } else if (TriMesh* g = dynamic_cast<TriMesh*>(b)) {
+        o->is_centered = g->is_centered; o->has_csv = g->csv_file.size() != 0; ref_copy_str(o->csv_file, g->csv_file);
+    }
+    return PTB_OK;
+}
+int ref_scn_get_slot(const void* hh, int i, int kind, int idx, ptb_slot* out) {
+    const Raytracer* rt = ((const ptb_ctx*)hh)->rt;
+    if (i < 0 || i >= (int)rt->s.objects.size()) return PTB_ERR_INVALID;
+    const std::vector<Texture>* v = ref_slot_vector(rt->s.objects[i], kind);
+    if (!v || idx < 0 || idx >= (int)v->size()) return PTB_ERR_INVALID;
+    ref_slot_from_tex((*v)[idx], out);
+    return PTB_OK;
+}
+// Raytracer::load_scene + hand the loaded Raytracer to the render entry points of this driver
+int ref_load_scene(ptb_ctx* c, const char* path, const char* replaced, ptb_camera* cam, ptb_params* p) {
+    if (!c || !path) return PTB_ERR_INVALID;
+    FILE* probe = fopen(path, "r");
+    if (!probe) return PTB_ERR_INVALID;
+    fclose(probe);
+    Raytracer* rt = c->rt;
+    rt->load_scene(path, replaced);
+    ptb_scn_header h;
+    ref_scn_get_header(c, &h);
+    if (cam) *cam = h.cam;
+    if (p) { memset(p, 0, sizeof(*p)); p->W = h.W; p->H = h.H; p->nrays = h.nrays; p->nb_bounces = h.nb_bounces; p->sigma_filter = h.sigma_filter; p->gamma = h.gamma; p->shard_count = 1; }
+    for (size_t i = 0; i < rt->s.objects.size(); i++) if (TriMesh* g = rt->s.castToMesh[i]) c->n_tri += (long long)g->indices.size();
+    return PTB_OK;
+}
+const char* ref_sceneio_last_error(void) { return "reference reader failed (the reference reports no reason)"; }
+int ref_scn_save(const void* hh, const char* path) { ((const ptb_ctx*)hh)->rt->save_scene(path); return PTB_OK; }
+
 }  // extern "C"

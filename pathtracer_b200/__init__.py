@@ -13,6 +13,7 @@ from ._abi import Lib, PtbError  # noqa: F401
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libptb200.so")
 _lib = None
+_io = None
 
 
 def load():
@@ -24,6 +25,14 @@ def load():
                            "There is no CPU fallback.")
         _lib = Lib(ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL), "ptb_")
     return _lib
+
+
+def sceneio():
+    """Bind the scene-file readers of include/ptb_sceneio.h (same library; host code, usable without a GPU)."""
+    global _io
+    if _io is None:
+        _io = _abi.SceneIO(load().cdll, "ptb_")
+    return _io
 
 
 def Raytracer(device=0):

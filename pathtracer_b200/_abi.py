@@ -92,8 +92,80 @@ SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plan
            "set_option", "get_scene_info", "kat", "get_kernel_times"]
 
 
+# ---- include/ptb_sceneio.h -------------------------------------------------------------------------
+PATH_MAX = 512
+KIND_KD, KIND_NORMAL, KIND_SUBSURF, KIND_KS, KIND_ALPHA, KIND_NE, KIND_TRANSP, KIND_REFR = range(8)
+N_KINDS = 8
+SCN_MESH, SCN_SPHERE, SCN_PLANE, SCN_POINTSET = range(4)
+
+
+class Slot(C.Structure):
+    _fields_ = [("file", C.c_char * PATH_MAX), ("mult", C.c_float * 3)]
+
+
+class MeshfileInfo(C.Structure):
+    _fields_ = [("vertices", _fp), ("n_vertices", C.c_int32), ("normals", _fp), ("n_normals", C.c_int32), ("uvs", _fp), ("n_uvs", C.c_int32),
+                ("vertex_colors", _fp), ("n_vertex_colors", C.c_int32), ("tri", C.POINTER(C.c_int32)), ("n_tri", C.c_int32),
+                ("n_groups", C.c_int32), ("has_materials", C.c_int32)]
+
+
+class ScnHeader(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("nrays", C.c_int32), ("nbframes", C.c_int32), ("nb_bounces", C.c_int32),
+                ("has_denoiser", C.c_int32), ("is_lenticular", C.c_int32), ("n_objects", C.c_int32), ("cam", Camera),
+                ("sigma_filter", C.c_float), ("gamma", C.c_float), ("intensite_lumiere", C.c_float), ("envmap_intensity", C.c_float),
+                ("fog_density", C.c_float), ("fog_absorption", C.c_float), ("fog_density_decay", C.c_float), ("fog_absorption_decay", C.c_float),
+                ("fog_type", C.c_int32), ("fog_phase_type", C.c_int32), ("double_frustum_start_t", C.c_float), ("background", C.c_char * PATH_MAX)]
+
+
+class ScnObject(C.Structure):
+    _fields_ = [("type", C.c_int32), ("name", C.c_char * PATH_MAX), ("miroir", C.c_int32), ("ghost", C.c_int32), ("display_edges", C.c_int32),
+                ("interp_normals", C.c_int32), ("flip_normals", C.c_int32), ("n_keyframes", C.c_int32), ("xform", Xform),
+                ("n_slots", C.c_int32 * N_KINDS), ("is_envmap", C.c_int32), ("envmap", C.c_char * PATH_MAX), ("O", C.c_float * 3), ("R", C.c_float),
+                ("A", C.c_float * 3), ("N", C.c_float * 3), ("is_centered", C.c_int32), ("has_csv", C.c_int32), ("csv_file", C.c_char * PATH_MAX)]
+
+
+# every symbol include/ptb_sceneio.h declares
+SCENEIO_SYMBOLS = ["sceneio_last_error", "image_load", "image_free", "texture_load", "meshfile_read", "meshfile_free", "meshfile_get",
+                   "meshfile_group_name", "meshfile_group_slot", "scn_load", "scn_free", "scn_get_header", "scn_get_object", "scn_get_slot",
+                   "scn_save", "load_scene"]
+
+
 class PtbError(RuntimeError):
     pass
+
+
+class SceneIO:
+    """Bound entry points of include/ptb_sceneio.h (host-side readers; they need no GPU)."""
+
+    def __init__(self, cdll, prefix="ptb_"):
+        vp, ip32 = C.c_void_p, C.POINTER(C.c_int32)
+        sig = {
+            "sceneio_last_error": (C.c_char_p, []),
+            "image_load": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_uint8)), ip32, ip32]),
+            "image_free": (None, [vp]),
+            "texture_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_fp), ip32, ip32]),
+            "meshfile_read": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
+            "meshfile_free": (None, [vp]),
+            "meshfile_get": (C.c_int, [vp, C.POINTER(MeshfileInfo)]),
+            "meshfile_group_name": (C.c_int, [vp, C.c_int, C.c_char_p]),
+            "meshfile_group_slot": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(Slot)]),
+            "scn_load": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(vp)]),
+            "scn_free": (None, [vp]),
+            "scn_get_header": (C.c_int, [vp, C.POINTER(ScnHeader)]),
+            "scn_get_object": (C.c_int, [vp, C.c_int, C.POINTER(ScnObject)]),
+            "scn_get_slot": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(Slot)]),
+            "scn_save": (C.c_int, [vp, C.c_char_p]),
+            "load_scene": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.POINTER(Camera), C.POINTER(Params)]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(cdll, prefix + name)
+            fn.restype, fn.argtypes = res, args
+            setattr(self, name, fn)
+
+    def check(self, rc):
+        if rc != OK:
+            msg = self.sceneio_last_error()
+            raise PtbError(f"scene reader failed rc={rc}: {msg.decode() if msg else ''}")
 
 
 class Lib:

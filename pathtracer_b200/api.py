@@ -61,6 +61,45 @@ class Texture:
         return t
 
 
+def _io():
+    from . import sceneio
+    return sceneio()
+
+
+def load_image(path):
+    """load_image<unsigned char> (utils.cpp:98-170): (H,W,3) uint8, rows flipped like the reference keeps them."""
+    io = _io()
+    p, w, h = C.POINTER(C.c_uint8)(), C.c_int32(), C.c_int32()
+    io.check(io.image_load(str(path).encode(), C.byref(p), C.byref(w), C.byref(h)))
+    a = np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
+    io.image_free(p)
+    return a
+
+
+def load_texture_values(path, normals=False):
+    """Texture::loadColors / loadNormals (BRDF.h:393-419): (H,W,3) float32 `Texture::values`, or None if the file cannot be read
+    (the reference then keeps a constant slot)."""
+    io = _io()
+    p, w, h = C.POINTER(C.c_float)(), C.c_int32(), C.c_int32()
+    if io.texture_load(str(path).encode(), 1 if normals else 0, C.byref(p), C.byref(w), C.byref(h)) != _abi.OK:
+        return None
+    a = np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
+    io.image_free(p)
+    return a
+
+
+_KIND_NAMES = {_abi.KIND_KD: "Kd", _abi.KIND_NORMAL: "normal", _abi.KIND_SUBSURF: "Ksub", _abi.KIND_KS: "Ks", _abi.KIND_ALPHA: "alpha",
+               _abi.KIND_NE: "Ne", _abi.KIND_TRANSP: "transp", _abi.KIND_REFR: "refr"}
+
+
+def _texture_from_slot(slot, kind):
+    f = slot.file.decode()
+    vals = load_texture_values(f, kind == _abi.KIND_NORMAL) if f else None
+    t = Texture(tuple(slot.mult), vals)
+    t.filename = f or "Null"
+    return t
+
+
 _SLOTS = [("Kd", _abi.SLOT_KD), ("Ks", _abi.SLOT_KS), ("Ne", _abi.SLOT_NE), ("transp", _abi.SLOT_TRANSP),
           ("refr", _abi.SLOT_REFR), ("normal", _abi.SLOT_NORMAL), ("alpha", _abi.SLOT_ALPHA)]
 
@@ -78,6 +117,8 @@ class Object:
         self.interp_normals = True
         self.brdf = ("phong", None)            # or ("merl", table ndarray float64 of 3*90*90*180)
         self.materials = {}                    # group -> {slot name: Texture}
+        self.ghost = False
+        self.name = ""
 
     def set_material(self, group=0, **slots):
         """e.g. set_material(0, Kd=Texture((.5,.5,.5)), Ks=Texture(.2), Ne=Texture(50))"""
@@ -125,6 +166,39 @@ class TriMesh(Object):
         self.scaling, self.offset, self.center = float(scaling), tuple(float(x) for x in offset), bool(center)
         self.miroir = mirror
 
+    @classmethod
+    def from_file(cls, path, scaling=1.0, offset=(0, 0, 0), mirror=False, center=True, load_textures=True):
+        """`new TriMesh(scene, file, scaling, offset, mirror, NULL, false, center)` for an .obj (+ .mtl) or .off file
+        (TriangleMesh.cpp:714-841 with readOBJ 240-569 / readOFF 107-130)."""
+        io = _io()
+        h = C.c_void_p()
+        io.check(io.meshfile_read(str(path).encode(), int(load_textures), C.byref(h)))
+        try:
+            info = _abi.MeshfileInfo()
+            io.check(io.meshfile_get(h, C.byref(info)))
+            arr = lambda p, n, k, dt: (np.ctypeslib.as_array(p, shape=(n, k)).astype(dt, copy=True) if n else np.zeros((0, k), dt))
+            m = cls(arr(info.vertices, info.n_vertices, 3, np.float32), arr(info.normals, info.n_normals, 3, np.float32),
+                    arr(info.uvs, info.n_uvs, 2, np.float32), arr(info.tri, info.n_tri, 10, np.int32), scaling, offset, mirror, center)
+            m.vertex_colors = arr(info.vertex_colors, info.n_vertex_colors, 3, np.float32)
+            m.name = str(path)
+            m.group_names = {}
+            for g in range(info.n_groups):
+                buf = C.create_string_buffer(_abi.PATH_MAX)
+                if io.meshfile_group_name(h, g, buf) == _abi.OK:
+                    m.group_names[buf.value.decode()] = g
+            if info.has_materials:
+                n_mat = max(1, max(m.group_names.values(), default=0) + 1)
+                for g in range(n_mat):
+                    slots = {}
+                    for kind, name in _KIND_NAMES.items():
+                        sl = _abi.Slot()
+                        if io.meshfile_group_slot(h, g, kind, C.byref(sl)) == _abi.OK:
+                            slots[name] = _texture_from_slot(sl, kind)
+                    m.materials[g] = slots
+        finally:
+            io.meshfile_free(h)
+        return m
+
 
 class Scene:
     """Geometry.h:1238-1400: object list; ids 0/1 are the light and the dome."""
@@ -133,6 +207,9 @@ class Scene:
         self.objects = []
         self.intensite_lumiere = 0.0
         self.envmap_intensity = 1.0
+        self.fog_density = self.fog_absorption = self.fog_density_decay = self.fog_absorption_decay = 0.0
+        self.fog_type = self.fog_phase_type = 0
+        self.background = None                 # (H,W,3) uint8 as load_image returns it, or None
 
     def addObject(self, o):
         self.objects.append(o)
@@ -174,8 +251,105 @@ class Raytracer:
         self.cam.rotate(0, -22 * math.pi / 180, 1)
         return self
 
+    # ---- Raytracer::load_scene (Raytracer.cpp:1149-1236) ----
+    def load_scene(self, filename, replacedNames=None):
+        """Parse a .scn file written by Raytracer::save_scene, read the meshes / textures / environment map it names and
+        fill this Raytracer's fields like the reference does.  Parsing happens in the native reader (include/ptb_sceneio.h)."""
+        io = _io()
+        h = C.c_void_p()
+        io.check(io.scn_load(str(filename).encode(), replacedNames.encode() if replacedNames else None, C.byref(h)))
+        try:
+            hd = _abi.ScnHeader()
+            io.check(io.scn_get_header(h, C.byref(hd)))
+            self.W, self.H, self.nrays, self.nb_bounces = hd.W, hd.H, hd.nrays, hd.nb_bounces
+            self.sigma_filter, self.gamma, self.has_denoiser = float(hd.sigma_filter), float(hd.gamma), bool(hd.has_denoiser)
+            self.cam = Camera(tuple(hd.cam.position), tuple(hd.cam.direction), tuple(hd.cam.up))
+            self.cam.fov, self.cam.focus_distance, self.cam.aperture = np.float32(hd.cam.fov), np.float32(hd.cam.focus_distance), np.float32(hd.cam.aperture)
+            self.cam.is_lenticular = bool(hd.is_lenticular)
+            self.s = Scene()
+            s = self.s
+            s.intensite_lumiere, s.envmap_intensity = float(hd.intensite_lumiere), float(hd.envmap_intensity)
+            s.fog_density, s.fog_absorption = float(hd.fog_density), float(hd.fog_absorption)
+            s.fog_density_decay, s.fog_absorption_decay = float(hd.fog_density_decay), float(hd.fog_absorption_decay)
+            s.fog_type, s.fog_phase_type = hd.fog_type, hd.fog_phase_type
+            if hd.background:
+                s.background = load_image(hd.background.decode())
+            for i in range(hd.n_objects):
+                o = _abi.ScnObject()
+                io.check(io.scn_get_object(h, i, C.byref(o)))
+                name = o.name.decode()
+                if o.type == _abi.SCN_SPHERE:
+                    obj = Sphere(tuple(o.O), float(o.R))
+                    if o.is_envmap:
+                        obj.envmap = load_image(o.envmap.decode())
+                elif o.type == _abi.SCN_PLANE:
+                    obj = Plane(tuple(o.A), tuple(o.N))
+                elif o.type == _abi.SCN_MESH:
+                    obj = TriMesh.from_file(name, 1.0, (0, 0, 0), bool(o.miroir), bool(o.is_centered), load_textures=False)
+                else:
+                    raise _abi.PtbError(f"load_scene: object {i} ({name}): PointSet objects are not rendered")
+                obj.name = name
+                obj.miroir, obj.ghost = bool(o.miroir), bool(o.ghost)
+                obj.flip_normals, obj.interp_normals = bool(o.flip_normals), bool(o.interp_normals)
+                obj.scale = float(o.xform.scale)
+                obj.mat_rotation = np.array(o.xform.rotation, np.float32).reshape(3, 3)
+                obj.rotation_center = tuple(o.xform.rotation_center)
+                obj.max_translation = np.array(o.xform.translation, np.float32)
+                for kind, slot_name in _KIND_NAMES.items():
+                    for g in range(o.n_slots[kind]):
+                        sl = _abi.Slot()
+                        io.check(io.scn_get_slot(h, i, kind, g, C.byref(sl)))
+                        obj.materials.setdefault(g, {})[slot_name] = _texture_from_slot(sl, kind)
+                s.addObject(obj)
+        finally:
+            io.scn_free(h)
+        return self
+
+    def load_scene_native(self, filename, replacedNames=None, io=None):
+        """The C-level route a C/C++ caller takes: `ptb_load_scene` parses the file, reads meshes / textures / envmap and feeds the
+        context itself (include/ptb_sceneio.h); this object only receives the camera and frame parameters.  Commits the scene."""
+        io = io or _io()
+        L = self.lib
+        self.close()
+        ctx = C.c_void_p()
+        L.check(L.create(self.device, C.byref(ctx)))
+        self._ctx = ctx
+        cam, p = _abi.Camera(), _abi.Params()
+        io.check(io.load_scene(ctx, str(filename).encode(), replacedNames.encode() if replacedNames else None, C.byref(cam), C.byref(p)))
+        self.W, self.H, self.nrays, self.nb_bounces = p.W, p.H, p.nrays, p.nb_bounces
+        self.sigma_filter, self.gamma = float(p.sigma_filter), float(p.gamma)
+        self.cam = Camera(tuple(cam.position), tuple(cam.direction), tuple(cam.up))
+        self.cam.fov, self.cam.focus_distance, self.cam.aperture = np.float32(cam.fov), np.float32(cam.focus_distance), np.float32(cam.aperture)
+        L.check(L.commit(ctx), ctx)
+        return self
+
+    def _unsupported(self):
+        """Scene features of the reference that the CUDA path does not render: refused, never approximated."""
+        s = self.s
+        if s.fog_density > 1e-8:
+            return "participating media (fog_density > 0)"
+        if s.background is not None:
+            return "background photograph"
+        if getattr(self.cam, "is_lenticular", False):
+            return "lenticular camera"
+        for i, o in enumerate(s.objects):
+            if o.ghost:
+                return f"ghost object {i}"
+            if getattr(o, "vertex_colors", None) is not None and len(o.vertex_colors):
+                return f"per-vertex colours on object {i}"
+            if i != 1 and getattr(o, "envmap", None) is not None:
+                return f"environment map on object {i} (only the dome, object 1)"
+            for slots in o.materials.values():
+                t = slots.get("Ksub")
+                if t is not None and (t.values is not None or sum(x * x for x in t.multiplier) > 1e-8):
+                    return f"subsurface scattering on object {i}"
+        return None
+
     # ---- scene hand-over -------------------------------------------------------------------------
     def commit(self):
+        bad = self._unsupported()
+        if bad:
+            raise _abi.PtbError(f"unsupported by this renderer: {bad}")
         L = self.lib
         self.close()
         ctx = C.c_void_p()

@@ -1,6 +1,7 @@
 // ptb_cli.cpp — headless driver: the `rayTracer <scene> <out>` path of the reference (mainApp.cpp:38-49) over the
-// CUDA library, with the synthetic scenes of SURVEY.md §8d instead of .scn files (scene-file ingestion is a "next" row).
-//   ptb_cli <C1|torus> <out.ppm> [W H spp nv]
+// CUDA library: a .scn file written by Raytracer::save_scene, or the synthetic scenes of SURVEY.md §8d.
+//   ptb_cli <scene.scn> <out.ppm> [W H spp]          (0 keeps the file's value)
+//   ptb_cli <C1|torus>  <out.ppm> [W H spp nv]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,9 +32,17 @@ static std::shared_ptr<TriMesh> displaced_torus(int nv) {   // SURVEY.md §8d ge
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { std::fprintf(stderr, "usage: %s <C1|torus> <out.ppm> [W H spp nv]\n", argv[0]); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: %s <scene.scn|C1|torus> <out.ppm> [W H spp nv]\n", argv[0]); return 2; }
     try {
         Raytracer rt;
+        const size_t len = std::strlen(argv[1]);
+        const bool scn = len > 4 && !std::strcmp(argv[1] + len - 4, ".scn");
+        if (scn) {
+            rt.load_scene(argv[1]);
+            if (argc > 3 && std::atoi(argv[3]) > 0) rt.W = std::atoi(argv[3]);
+            if (argc > 4 && std::atoi(argv[4]) > 0) rt.H = std::atoi(argv[4]);
+            if (argc > 5 && std::atoi(argv[5]) > 0) rt.nrays = std::atoi(argv[5]);
+        } else {
         rt.loadScene();
         rt.W = argc > 3 ? std::atoi(argv[3]) : 512; rt.H = argc > 4 ? std::atoi(argv[4]) : 512;
         rt.nrays = argc > 5 ? std::atoi(argv[5]) : 64; rt.nb_bounces = 5;
@@ -54,6 +63,7 @@ int main(int argc, char** argv) {
             rt.s.addObject(g);
         }
         rt.commit();
+        }
         rt.render_image_nopreviz();
         std::FILE* f = std::fopen(argv[2], "wb");
         if (!f) throw Error("cannot open output");

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/ptb200.h"
+#include "../../include/ptb_sceneio.h"
 
 namespace ptbhost {
 
@@ -133,6 +134,20 @@ public:
         s.intensite_lumiere = (float)(1000000000 * 4. * M_PI / (4. * M_PI * slum->R * slum->R * M_PI));
         s.envmap_intensity = 1;
         cam.rotate(0, (float)(-22 * M_PI / 180), 1);
+    }
+
+    // Raytracer::load_scene (Raytracer.cpp:1149-1236): the native reader parses the .scn, reads the meshes / textures /
+    // environment map it names and feeds the device context; this object receives the camera and frame parameters.
+    // The scene is committed on return (`s.objects` stays empty: the description lives in the context).
+    void load_scene(const char* filename, const char* replacedNames = nullptr) {
+        if (ctx_) { ptb_destroy(ctx_); ctx_ = nullptr; }
+        if (ptb_create(device_, &ctx_) != PTB_OK) throw Error(std::string("ptb_create: ") + ptb_last_error(nullptr));
+        ptb_camera c; ptb_params p;
+        if (ptb_load_scene(ctx_, filename, replacedNames, &c, &p) != PTB_OK) throw Error(std::string("load_scene: ") + ptb_sceneio_last_error());
+        W = p.W; H = p.H; nrays = p.nrays; nb_bounces = p.nb_bounces; sigma_filter = p.sigma_filter; gamma = p.gamma;
+        cam = Camera(Vector(c.position[0], c.position[1], c.position[2]), Vector(c.direction[0], c.direction[1], c.direction[2]), Vector(c.up[0], c.up[1], c.up[2]));
+        cam.fov = c.fov; cam.focus_distance = c.focus_distance; cam.aperture = c.aperture;
+        ck(ptb_commit(ctx_));
     }
 
     // hands the scene to the device: TriMesh::init + build_bvh + Scene::prepare_render equivalents
