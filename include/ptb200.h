@@ -170,6 +170,33 @@ int ptb_commit(ptb_ctx*);
 int ptb_render(ptb_ctx*, const ptb_camera*, const ptb_params*,
                float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats);
 
+/* replaces: Raytracer::render_image_nopreviz with `has_denoiser == true` (Raytracer.cpp:1631-1645, 1676-1693), up to the hand-over
+ * to Open Image Denoise (the denoiser itself is not part of this library).  In this mode the reference does NOT splat: every
+ * sample adds its radiance and a count of 1 to its own pixel, and the first hit's albedo (mat.Kd) and shading normal are
+ * accumulated next to it (getColor, Raytracer.cpp:254-257).  HOST outputs, W*H*3 floats each (sample_count: W*H), any may be NULL:
+ *   imagedouble       mean radiance                           albedoImage   mean first-hit albedo
+ *   normalImage       what the reference stores there: it sums the COLOUR buffers instead of the normals (1680-1682) and
+ *                     normalises, i.e. the normalised radiance sum (NaN where it is zero)
+ *   first_hit_normal  the normalised sum of the first-hit shading normals, the quantity 1680-1682 was written to produce */
+int ptb_render_denoiser_inputs(ptb_ctx*, const ptb_camera*, const ptb_params*, float* imagedouble, float* sample_count,
+                               float* albedoImage, float* normalImage, float* first_hit_normal, ptb_stats* stats);
+
+/* replaces: Raytracer::render_image (Raytracer.cpp:1424-1563), the progressive renderer of the GUI thread: one sample per pixel
+ * per pass into buffers that persist between passes.  The reference interleaves each pass over 8x8 pixel phases so that a
+ * preview fills in evenly on the CPU; the order does not change what is accumulated and a pass takes about a millisecond here,
+ * so a pass is simply all pixels.  begin = prepare_render (buffers zeroed, 1382-1389); pass(n) = the next n iterations of the
+ * `realtime_ray_iter` loop (1444), fewer if `nrays` is reached; the caller checks its own `stopped` flag between calls (1452).
+ * read, HOST outputs, any may be NULL:
+ *   imagedouble         W*H*3 UN-normalised weighted sums (the progressive path never divides them, 1491-1493)
+ *   sample_count        W*H   filter weight sums (1495)
+ *   image               W*H*3 255*(imagedouble/196964.7/max(sample_count,1))^(1/gamma) (1543-1545)
+ *   imagedouble_lowres  ceil(W/16)*ceil(H/16)*3: every sample adds colour/256 to its 16x16 block (1508-1510)
+ *   current_nb_rays     passes accumulated so far (Raytracer::current_nb_rays, 1445) */
+int ptb_progressive_begin(ptb_ctx*, const ptb_camera*, const ptb_params*);
+int ptb_progressive_pass(ptb_ctx*, int n_spp, ptb_stats* stats);
+int ptb_progressive_read(ptb_ctx*, float* imagedouble, float* sample_count, uint8_t* image, float* imagedouble_lowres,
+                         int32_t* current_nb_rays);
+
 /* Sharded form for one-process-per-GPU runs: adds this shard's un-normalised sums into a DEVICE
  * buffer d_rgbw (W*H float4 = {sum r, sum g, sum b, sum weight}, reference row convention) owned
  * by the caller (e.g. a torch tensor, so NCCL can move it).  The buffer is NOT cleared. */

@@ -17,7 +17,8 @@ Patches applied to the temp copy (each must match exactly once, else the build a
                    the author's Windows build has 4-byte long; int32_t restores the intended behaviour)
   5. Raytracer.cpp per-(pixel,sample) pcg32 streams instead of per-thread engines (determinism; this
                    is the inline ray generation the author left commented at Raytracer.cpp:1613-1622,
-                   preceded by a reseed; see DESIGN.md "RNG")
+                   preceded by a reseed; see DESIGN.md "RNG"); 5c: the same reseed in front of the
+                   draws of the progressive renderer render_image (Raytracer.cpp:1462)
   6. Geometry.cpp  per-thread ray counters at the top of Scene::intersection{,_shadow} (measurement)
 Flags: -std=c++11 -O2 -fopenmp -fpermissive -include omp.h -D__forceinline=inline, unity TU.
 """
@@ -84,6 +85,12 @@ def patch(tmp):
         "Vector normal, albedo;\n"
         "Vector color = getColor(r, k, nb_bounces, i, j, normal, albedo, false, false);",
         "5b inline per-sample rays")
+    # 5c: the same per-(pixel,sample) stream in the progressive renderer (render_image, Raytracer.cpp:1459-1466)
+    r = sub_once(
+        r,
+        r"(for \(int j = j1; j < W; j \+= 8\) \{\s*)(float dx = engine\[threadid\]\(\)\*invmax - 0\.5f;)",
+        r"\1engine[threadid] = pcg32((uint64_t)(i*W + j), (uint64_t)realtime_ray_iter ^ ((uint64_t)ptb_ref_global_seed << 32));\n\2",
+        "5c progressive per-sample streams")
     wr("Raytracer.cpp", r)
 
     g = rd("Geometry.cpp")

@@ -240,6 +240,9 @@ struct ptb_ctx {
     vec centerLight; float radiusLight, lightPower;
     int filter_size, filter_total_width; float filter_integral[81];
     vec* randomPerPixel; int rpp_n;
+    /* progressive session (Raytracer::render_image): the buffers that persist between passes */
+    int prog_active, prog_iter; float* prog_img; float* prog_cnt; float* prog_lowres; vec* prog_samples2d;
+    unsigned long long prog_counters[64][8];
 };
 static char g_err[256];
 
@@ -650,7 +653,8 @@ static void camera_ray(const struct ptb_ctx* c, float init_t, int i, int j, floa
 }
 
 /* Raytracer::getColor (Raytracer.cpp:196-664) without fog / subsurface / ghost / background */
-static vec get_color(const struct ptb_ctx* c, vec ro, vec rd, int sampleID, int pix, pcg* e, unsigned long long* counter, const vec* samples2d) {
+static vec get_color(const struct ptb_ctx* c, vec ro, vec rd, int sampleID, int pix, pcg* e, unsigned long long* counter, const vec* samples2d,
+                     vec* normalValue, vec* albedoValue) {
     vec color = V(0, 0, 0), w = V(1.f, 1.f, 1.f);
     int depth = c->nb_bounces, show_lights = 1;
     for (;;) {
@@ -659,6 +663,7 @@ static vec get_color(const struct ptb_ctx* c, vec ro, vec rd, int sampleID, int 
         vec P; matvals mat = matvals_default(); int id = -1, tri = -1; float t;
         int has = scene_hit(c, ro, rd, &P, &id, &t, &mat, &tri, counter);
         vec N = mat.shadingN;
+        if (has && depth == c->nb_bounces && normalValue) { *normalValue = N; *albedoValue = mat.Kd; }   /* 254-257 */
         if (!has) break;                                            /* 654-657 */
         if (id == 1) { color = vadd(color, vmul(vscale(c->envmap_intensity, w), mat.Ke)); break; }          /* 275-301 */
         if (id == 0) { float lp = show_lights ? c->lightPower : 0.f; color = vadd(color, vmul(w, V(lp, lp, lp))); break; } /* 303-316 */
@@ -768,7 +773,9 @@ static void free_object(object* o) {
     free(o->vertices); free(o->normals); free(o->uvs); free(o->indices); free(o->soup); free(o->tangent_soup); free(o->permuted); free(o->nodes);
     free(o);
 }
+static void prog_free(ptb_ctx* c);
 void ptb_destroy(ptb_ctx* c) {
+    if (c) prog_free(c);
     if (!c) return;
     for (int i = 0; i < c->n_objs; i++) free_object(c->objs[i]);
     free(c->objs);
@@ -973,7 +980,7 @@ int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* im
                     float dxa = (pcg_unif(&e) - 0.5f) * c->aperture, dya = (pcg_unif(&e) - 0.5f) * c->aperture;
                     vec ro, rd;
                     camera_ray(c, 0.f, i, j, dx, dy, dxa, dya, W, H, &ro, &rd);
-                    vec col = get_color(c, ro, rd, k, i * W + j, &e, counters[th], samples2d);
+                    vec col = get_color(c, ro, rd, k, i * W + j, &e, counters[th], samples2d, NULL, NULL);
                     for (int i2 = bmin_i; i2 <= bmax_i; i2++)
                         for (int j2 = bmin_j; j2 <= bmax_j; j2++) {
                             size_t idx = ((size_t)(H - i2 - 1) * W + j2) * 3;
@@ -1012,6 +1019,180 @@ int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* im
     free(acc); free(sc); free(img_t); free(cnt_t); free(samples2d);
     return PTB_OK;
 }
+/* render_image_nopreviz with has_denoiser == true (Raytracer.cpp:1631-1645 accumulation, 1669-1694 merge and normalisation) */
+int ptb_render_denoiser_inputs(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, float* albedoImage,
+                               float* normalImage, float* first_hit_normal, ptb_stats* stats) {
+    if (!c || !cam || !p || p->W <= 0 || p->H <= 0 || p->nrays <= 0) return PTB_ERR_INVALID;
+    if (!c->committed) return PTB_ERR_STATE;
+    if (p->shard_count > 1) return PTB_ERR_UNSUPPORTED;
+    set_frame(c, cam, p->W, p->H);
+    c->nrays = p->nrays; c->nb_bounces = p->nb_bounces; c->sigma_filter = p->sigma_filter; c->gamma = p->gamma; c->seed = p->seed;
+    int nt = c->threads > 0 ? c->threads : omp_get_num_procs();
+    if (nt > 64) nt = 64;
+    prepare_render(c);
+    const int W = c->W, H = c->H, nrays = c->nrays;
+    vec* samples2d = (vec*)malloc(sizeof(vec) * (size_t)nrays);
+    for (int i = 0; i < nrays; i++) { float x, y; lattice2d((uint32_t)i, &x, &y); samples2d[i] = V(x, y, 0); }
+    const int bw = 4, bh = 4;
+    const int nbx = (int)ceilf(W / (float)bw), nby = (int)ceilf(H / (float)bh);
+    size_t npix = (size_t)W * H;
+    float* img_t = (float*)calloc(npix * 3 * (size_t)nt, sizeof(float));
+    float* cnt_t = (float*)calloc(npix * (size_t)nt, sizeof(float));
+    float* alb_t = (float*)calloc(npix * 3 * (size_t)nt, sizeof(float));
+    float* nrm_t = (float*)calloc(npix * 3 * (size_t)nt, sizeof(float));
+    unsigned long long counters[64][8];
+    memset(counters, 0, sizeof(counters));
+#pragma omp parallel num_threads(nt)
+    {
+        int th = omp_get_thread_num();
+        float* img = img_t + (size_t)th * npix * 3; float* cnt = cnt_t + (size_t)th * npix;
+        float* alb = alb_t + (size_t)th * npix * 3; float* nrm = nrm_t + (size_t)th * npix * 3;
+#pragma omp for schedule(dynamic, 1)
+        for (int batch = 0; batch < nbx * nby; batch++) {
+            int bi = batch / nbx, bj = batch % nbx;
+            int bW = (W < bj * bw + bw ? W : bj * bw + bw) - bj * bw, bH = (H < bi * bh + bh ? H : bi * bh + bh) - bi * bh;
+            for (int id = 0; id < bW * bH; id++) {
+                int i = bi * bh + id / bW, j = bj * bw + id % bW;
+                for (int k = 0; k < nrays; k++) {
+                    pcg e = pcg_seed2((uint64_t)(i * W + j), (uint64_t)k ^ ((uint64_t)c->seed << 32));
+                    float dx = pcg_unif(&e) - 0.5f, dy = pcg_unif(&e) - 0.5f;
+                    float dxa = (pcg_unif(&e) - 0.5f) * c->aperture, dya = (pcg_unif(&e) - 0.5f) * c->aperture;
+                    vec ro, rd, normal = V(0, 0, 0), albedo = V(0, 0, 0);          /* `Vector normal, albedo;` are zero-initialised (Vector.h:45) */
+                    camera_ray(c, 0.f, i, j, dx, dy, dxa, dya, W, H, &ro, &rd);
+                    vec col = get_color(c, ro, rd, k, i * W + j, &e, counters[th], samples2d, &normal, &albedo);
+                    size_t idx = ((size_t)(H - i - 1) * W + j) * 3;
+                    img[idx] += col.x; img[idx + 1] += col.y; img[idx + 2] += col.z;
+                    cnt[(size_t)(H - i - 1) * W + j] += 1;
+                    nrm[idx] += normal.x; nrm[idx + 1] += normal.y; nrm[idx + 2] += normal.z;
+                    alb[idx] += albedo.x; alb[idx + 1] += albedo.y; alb[idx + 2] += albedo.z;
+                }
+            }
+        }
+    }
+    float* acc = (float*)calloc(npix * 3, sizeof(float)); float* sc = (float*)calloc(npix, sizeof(float));
+    float* al = (float*)calloc(npix * 3, sizeof(float)); float* nr = (float*)calloc(npix * 3, sizeof(float)); float* fh = (float*)calloc(npix * 3, sizeof(float));
+    for (int th = 0; th < nt; th++)
+        for (size_t i = 0; i < npix; i++) {
+            sc[i] += cnt_t[(size_t)th * npix + i];
+            for (int q = 0; q < 3; q++) {
+                acc[i * 3 + q] += img_t[(size_t)th * npix * 3 + i * 3 + q];
+                al[i * 3 + q] += alb_t[(size_t)th * npix * 3 + i * 3 + q];
+                nr[i * 3 + q] += img_t[(size_t)th * npix * 3 + i * 3 + q];     /* 1680-1682: the reference adds imagedoublethreads here, not the normals */
+                fh[i * 3 + q] += nrm_t[(size_t)th * npix * 3 + i * 3 + q];     /* what that line was meant to add */
+            }
+        }
+    for (size_t i = 0; i < npix; i++) {                                         /* 1687-1694 */
+        float nn = sqrtf(nr[i * 3] * nr[i * 3] + nr[i * 3 + 1] * nr[i * 3 + 1] + nr[i * 3 + 2] * nr[i * 3 + 2]);
+        float nf = sqrtf(fh[i * 3] * fh[i * 3] + fh[i * 3 + 1] * fh[i * 3 + 1] + fh[i * 3 + 2] * fh[i * 3 + 2]);
+        for (int q = 0; q < 3; q++) { acc[i * 3 + q] /= sc[i]; al[i * 3 + q] /= sc[i]; nr[i * 3 + q] /= nn; fh[i * 3 + q] /= nf; }
+    }
+    if (imagedouble) memcpy(imagedouble, acc, npix * 3 * sizeof(float));
+    if (sample_count) memcpy(sample_count, sc, npix * sizeof(float));
+    if (albedoImage) memcpy(albedoImage, al, npix * 3 * sizeof(float));
+    if (normalImage) memcpy(normalImage, nr, npix * 3 * sizeof(float));
+    if (first_hit_normal) memcpy(first_hit_normal, fh, npix * 3 * sizeof(float));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->samples = (uint64_t)npix * (uint64_t)nrays;
+        for (int th = 0; th < 64; th++) { stats->rays_closest += counters[th][0]; stats->rays_shadow += counters[th][1]; }
+    }
+    free(acc); free(sc); free(al); free(nr); free(fh); free(img_t); free(cnt_t); free(alb_t); free(nrm_t); free(samples2d);
+    return PTB_OK;
+}
+
+/* Raytracer::render_image (Raytracer.cpp:1424-1563), a batch of passes per call; per-(pixel,sample) streams as in ptb_render */
+static void prog_free(ptb_ctx* c) { free(c->prog_img); free(c->prog_cnt); free(c->prog_lowres); free(c->prog_samples2d); c->prog_img = c->prog_cnt = c->prog_lowres = NULL; c->prog_samples2d = NULL; c->prog_active = 0; }
+int ptb_progressive_begin(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p) {
+    if (!c || !cam || !p || p->W <= 0 || p->H <= 0 || p->nrays <= 0) return PTB_ERR_INVALID;
+    if (!c->committed) return PTB_ERR_STATE;
+    prog_free(c);
+    set_frame(c, cam, p->W, p->H);
+    c->nrays = p->nrays; c->nb_bounces = p->nb_bounces; c->sigma_filter = p->sigma_filter; c->gamma = p->gamma; c->seed = p->seed;
+    if ((int)ceilf(c->sigma_filter * 2) > 4) return PTB_ERR_UNSUPPORTED;
+    prepare_render(c);                                                          /* 1441: zeroes the buffers (1382-1389) */
+    const size_t npix = (size_t)c->W * c->H;
+    const int Wlr = (int)ceilf(c->W / 16.f), Hlr = (int)ceilf(c->H / 16.f);      /* 1329-1330 */
+    c->prog_img = (float*)calloc(npix * 3, sizeof(float));
+    c->prog_cnt = (float*)calloc(npix, sizeof(float));
+    c->prog_lowres = (float*)calloc((size_t)Wlr * Hlr * 3, sizeof(float));
+    c->prog_samples2d = (vec*)malloc(sizeof(vec) * (size_t)c->nrays);
+    for (int i = 0; i < c->nrays; i++) { float x, y; lattice2d((uint32_t)i, &x, &y); c->prog_samples2d[i] = V(x, y, 0); }
+    c->prog_iter = 0; c->prog_active = 1;
+    return PTB_OK;
+}
+int ptb_progressive_pass(ptb_ctx* c, int n_spp, ptb_stats* stats) {
+    if (!c) return PTB_ERR_INVALID;
+    if (!c->prog_active) return PTB_ERR_STATE;
+    const int W = c->W, H = c->H, fs = c->filter_size, ftw = c->filter_total_width;
+    const int Wlr = (int)ceilf(W / 16.f), Hlr = (int)ceilf(H / 16.f);
+    int n = n_spp < c->nrays - c->prog_iter ? n_spp : c->nrays - c->prog_iter;
+    int nt = c->threads > 0 ? c->threads : omp_get_num_procs();
+    if (nt > 64) nt = 64;
+    float denom2 = (float)(1.f / (2. * c->sigma_filter * c->sigma_filter));      /* 1430: double arithmetic narrowed to float */
+    memset(c->prog_counters, 0, sizeof(c->prog_counters));
+    float* img = c->prog_img; float* cnt = c->prog_cnt; float* lr = c->prog_lowres;
+    for (int k = c->prog_iter; k < c->prog_iter + (n > 0 ? n : 0); k++)
+        for (int pib = 0; pib < 64; pib++) {                                     /* 1447-1449: 8x8 interleave */
+            int i1 = pib % 8, j1 = pib / 8;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+            for (int i = i1; i < H; i += 8) {
+                int th = omp_get_thread_num();
+                for (int j = j1; j < W; j += 8) {
+                    pcg e = pcg_seed2((uint64_t)(i * W + j), (uint64_t)k ^ ((uint64_t)c->seed << 32));
+                    float dx = pcg_unif(&e) - 0.5f, dy = pcg_unif(&e) - 0.5f;
+                    float dxa = (pcg_unif(&e) - 0.5f) * c->aperture, dya = (pcg_unif(&e) - 0.5f) * c->aperture;
+                    vec ro, rd;
+                    camera_ray(c, 0.f, i, j, dx, dy, dxa, dya, W, H, &ro, &rd);
+                    vec col = get_color(c, ro, rd, k, i * W + j, &e, c->prog_counters[th], c->prog_samples2d, NULL, NULL);
+                    int bmin_i = i - fs > 0 ? i - fs : 0, bmax_i = i + fs < H - 1 ? i + fs : H - 1;
+                    int bmin_j = j - fs > 0 ? j - fs : 0, bmax_j = j + fs < W - 1 ? j + fs : W - 1;
+                    float ratio = 1.f / sat(c->filter_integral, ftw, bmin_i - i + fs, bmax_i - i + fs, bmin_j - j + fs, bmax_j - j + fs);
+                    float denom1 = (float)(ratio / (c->sigma_filter * c->sigma_filter * 2. * M_PI));
+                    for (int i2 = bmin_i; i2 <= bmax_i; i2++)
+                        for (int j2 = bmin_j; j2 <= bmax_j; j2++) {
+                            size_t idx = ((size_t)(H - i2 - 1) * W + j2) * 3;
+                            float a = (i2 - i - dy), b = (j2 - j - dx);
+                            float w = (float)(fast_exp(-(a * a + b * b) * denom2) * denom1);
+                            img[idx] += col.x * w; img[idx + 1] += col.y * w; img[idx + 2] += col.z * w;
+                            cnt[(size_t)(H - i2 - 1) * W + j2] += w;
+                        }
+                    size_t li = ((size_t)(Hlr - i / 16 - 1) * Wlr + j / 16) * 3;   /* 1508-1510 (rows i and i+8 share a block: unordered adds when threaded) */
+                    for (int q = 0; q < 3; q++) {
+                        float add = (float)(vget(col, q) / 256.);
+#pragma omp atomic
+                        lr[li + q] += add;
+                    }
+                }
+            }
+        }
+    if (n > 0) c->prog_iter += n;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->samples = (uint64_t)W * H * (uint64_t)(n > 0 ? n : 0);
+        for (int th = 0; th < 64; th++) { stats->rays_closest += c->prog_counters[th][0]; stats->rays_shadow += c->prog_counters[th][1]; }
+    }
+    return PTB_OK;
+}
+int ptb_progressive_read(ptb_ctx* c, float* imagedouble, float* sample_count, uint8_t* image, float* imagedouble_lowres, int32_t* current_nb_rays) {
+    if (!c) return PTB_ERR_INVALID;
+    if (!c->prog_active) return PTB_ERR_STATE;
+    const size_t npix = (size_t)c->W * c->H;
+    const int Wlr = (int)ceilf(c->W / 16.f), Hlr = (int)ceilf(c->H / 16.f);
+    if (imagedouble) memcpy(imagedouble, c->prog_img, npix * 3 * sizeof(float));
+    if (sample_count) memcpy(sample_count, c->prog_cnt, npix * sizeof(float));
+    if (imagedouble_lowres) memcpy(imagedouble_lowres, c->prog_lowres, (size_t)Wlr * Hlr * 3 * sizeof(float));
+    if (image)                                                                   /* 1540-1547 */
+        for (size_t i = 0; i < npix; i++)
+            for (int q = 0; q < 3; q++) {
+                float d = c->prog_cnt[i] < 1.f ? 1.f : c->prog_cnt[i];           /* std::max(sample_count, 1.f) */
+                double v = 255. * pow(c->prog_img[i * 3 + q] / 196964.7 / d, 1 / c->gamma);
+                v = v > 0. ? v : 0.; v = v < 255. ? v : 255.;
+                image[i * 3 + q] = (uint8_t)v;
+            }
+    if (current_nb_rays) *current_nb_rays = c->prog_iter;
+    return PTB_OK;
+}
+
 int ptb_render_accum(ptb_ctx* c, const ptb_camera* a, const ptb_params* b, float* d, ptb_stats* s) { (void)c; (void)a; (void)b; (void)d; (void)s; return PTB_ERR_UNSUPPORTED; }
 int ptb_resolve(ptb_ctx* c, const float* d, int W, int H, float g, float* a, float* b, uint8_t* e) { (void)c; (void)d; (void)W; (void)H; (void)g; (void)a; (void)b; (void)e; return PTB_ERR_UNSUPPORTED; }
 int ptb_shard_pack_size(const ptb_params* p, int r, int64_t* o) { (void)p; (void)r; (void)o; return PTB_ERR_UNSUPPORTED; }

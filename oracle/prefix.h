@@ -33,6 +33,10 @@
 #define ptb_get_scene_info     ORC_NAME(get_scene_info)
 #define ptb_kat                ORC_NAME(kat)
 #define ptb_get_kernel_times    ORC_NAME(get_kernel_times)
+#define ptb_render_denoiser_inputs ORC_NAME(render_denoiser_inputs)
+#define ptb_progressive_begin  ORC_NAME(progressive_begin)
+#define ptb_progressive_pass   ORC_NAME(progressive_pass)
+#define ptb_progressive_read   ORC_NAME(progressive_read)
 /* options understood only by the CPU checkers */
 #define ORC_OPT_THREADS 100    /* OpenMP threads for render (default: all, capped at 64 like the reference) */
 #endif

@@ -268,6 +268,66 @@ int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p,
     return PTB_OK;
 }
 
+// render_image_nopreviz with has_denoiser = true: without OIDN compiled in, the reference stops after the normalisation loop
+// (Raytracer.cpp:1687-1694; build_ref.py patch 3 closes the brace the OIDN block would have closed)
+int ptb_render_denoiser_inputs(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, float* albedoImage,
+                               float* normalImage, float* first_hit_normal, ptb_stats* stats) {
+    int rc = setup_frame(c, cam, p);
+    if (rc) return rc;
+    Raytracer* rt = c->rt;
+    memset(ptb_ref_cnt, 0, sizeof(ptb_ref_cnt));
+    rt->has_denoiser = true;
+    rt->render_image_nopreviz();
+    rt->has_denoiser = false;
+    size_t n = (size_t)p->W * p->H;
+    if (imagedouble) memcpy(imagedouble, &rt->imagedouble[0], n * 3 * sizeof(float));
+    if (sample_count) memcpy(sample_count, &rt->sample_count[0], n * sizeof(float));
+    if (albedoImage) memcpy(albedoImage, &rt->albedoImage[0], n * 3 * sizeof(float));
+    if (normalImage) memcpy(normalImage, &rt->normalImage[0], n * 3 * sizeof(float));
+    if (first_hit_normal) for (size_t i = 0; i < n * 3; i++) first_hit_normal[i] = NAN;   // the reference never forms this quantity (1680-1682 sum colours)
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->samples = (uint64_t)n * p->nrays;
+        for (int t = 0; t < 64; t++) { stats->rays_closest += ptb_ref_cnt[t][0]; stats->rays_shadow += ptb_ref_cnt[t][1]; }
+    }
+    return PTB_OK;
+}
+
+// Raytracer::render_image cannot be paused from outside; with per-(pixel,sample) streams (build_ref.py patch 5c) the first k passes
+// of a longer render ARE a k-pass render, so a session re-renders `passes so far` on read.
+static ptb_camera g_prog_cam; static ptb_params g_prog_p; static int g_prog_iter = -1;
+int ptb_progressive_begin(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p) {
+    int rc = setup_frame(c, cam, p);
+    if (rc) return rc;
+    g_prog_cam = *cam; g_prog_p = *p; g_prog_iter = 0;
+    return PTB_OK;
+}
+int ptb_progressive_pass(ptb_ctx* c, int n_spp, ptb_stats* stats) {
+    if (!c || g_prog_iter < 0) return PTB_ERR_STATE;
+    int n = n_spp < g_prog_p.nrays - g_prog_iter ? n_spp : g_prog_p.nrays - g_prog_iter;
+    if (n > 0) g_prog_iter += n;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    return PTB_OK;
+}
+int ptb_progressive_read(ptb_ctx* c, float* imagedouble, float* sample_count, uint8_t* image, float* imagedouble_lowres, int32_t* current_nb_rays) {
+    if (!c || g_prog_iter < 0) return PTB_ERR_STATE;
+    ptb_params p = g_prog_p;
+    p.nrays = g_prog_iter > 0 ? g_prog_iter : 1;
+    int rc = setup_frame(c, &g_prog_cam, &p);
+    if (rc) return rc;
+    Raytracer* rt = c->rt;
+    if (g_prog_iter == 0) rt->nrays = 0;
+    rt->stopped = false;
+    rt->render_image();
+    size_t n = (size_t)p.W * p.H;
+    if (imagedouble) memcpy(imagedouble, &rt->imagedouble[0], n * 3 * sizeof(float));
+    if (sample_count) memcpy(sample_count, &rt->sample_count[0], n * sizeof(float));
+    if (image) memcpy(image, &rt->image[0], n * 3);
+    if (imagedouble_lowres) memcpy(imagedouble_lowres, &rt->imagedouble_lowres[0], (size_t)rt->Wlr * rt->Hlr * 3 * sizeof(float));
+    if (current_nb_rays) *current_nb_rays = g_prog_iter;
+    return PTB_OK;
+}
+
 int ptb_render_accum(ptb_ctx*, const ptb_camera*, const ptb_params*, float*, ptb_stats*) { return PTB_ERR_UNSUPPORTED; }
 int ptb_resolve(ptb_ctx*, const float*, int, int, float, float*, float*, uint8_t*) { return PTB_ERR_UNSUPPORTED; }
 int ptb_shard_pack_size(const ptb_params*, int, int64_t*) { return PTB_ERR_UNSUPPORTED; }

@@ -11,7 +11,8 @@ from . import _abi
 from ._abi import Lib, PtbError  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libptb200.so")
+# PTB_LIB_PATH: A/B measurements of another build of the same library (experiments only)
+LIB_PATH = os.environ.get("PTB_LIB_PATH") or os.path.join(_HERE, "csrc", "libptb200.so")
 _lib = None
 _io = None
 

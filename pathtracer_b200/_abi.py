@@ -89,7 +89,8 @@ class KernelTimes(C.Structure):
 SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_mesh",
            "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "commit", "render",
            "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
-           "set_option", "get_scene_info", "kat", "get_kernel_times"]
+           "set_option", "get_scene_info", "kat", "get_kernel_times", "render_denoiser_inputs", "progressive_begin", "progressive_pass",
+           "progressive_read"]
 
 
 # ---- include/ptb_sceneio.h -------------------------------------------------------------------------
@@ -198,6 +199,10 @@ class Lib:
             "set_option": (C.c_int, [vp, C.c_int, C.c_int64]),
             "get_scene_info": (C.c_int, [vp, C.POINTER(SceneInfo)]),
             "get_kernel_times": (C.c_int, [vp, C.POINTER(KernelTimes)]),
+            "render_denoiser_inputs": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), _fp, _fp, _fp, _fp, _fp, C.POINTER(Stats)]),
+            "progressive_begin": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params)]),
+            "progressive_pass": (C.c_int, [vp, C.c_int, C.POINTER(Stats)]),
+            "progressive_read": (C.c_int, [vp, _fp, _fp, C.POINTER(C.c_uint8), _fp, C.POINTER(C.c_int32)]),
             "kat": (C.c_int, [vp, C.c_int, C.POINTER(Camera), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
                               C.POINTER(C.c_double), C.c_int]),
         }

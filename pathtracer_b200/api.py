@@ -421,6 +421,62 @@ class Raytracer:
         self.stats = st.as_dict()
         return self.imagedouble
 
+    # ---- Raytracer::render_image (Raytracer.cpp:1424-1563): the progressive renderer ----
+    def render_image(self, passes_per_call=1, on_pass=None):
+        """One sample per pixel per pass until `nrays` passes are done or `self.stopped` is set by `on_pass` (the reference's GUI
+        sets `stopped` from another thread, 1452).  Fills `imagedouble` (UN-normalised sums, as the reference leaves them),
+        `sample_count`, `image`, `imagedouble_lowres` and `current_nb_rays`."""
+        L, ctx = self.lib, self._ctx
+        if ctx is None:
+            self.commit()
+            ctx = self._ctx
+        cam, p = self.cam.c_struct(), self.params()
+        L.check(L.progressive_begin(ctx, C.byref(cam), C.byref(p)), ctx)
+        self.stopped = False
+        self.current_nb_rays = 0
+        tot = {"samples": 0, "rays_closest": 0, "rays_shadow": 0, "ms_device": 0.0, "kernel_launches": 0}
+        while self.current_nb_rays < self.nrays and not self.stopped:
+            st = _abi.Stats()
+            L.check(L.progressive_pass(ctx, int(passes_per_call), C.byref(st)), ctx)
+            for k in tot:
+                tot[k] += getattr(st, k)
+            self.current_nb_rays = min(self.nrays, self.current_nb_rays + int(passes_per_call))
+            if on_pass is not None:
+                on_pass(self)
+        self.stats = tot
+        return self.read_progressive()
+
+    def read_progressive(self):
+        L, ctx = self.lib, self._ctx
+        wlr, hlr = -(-self.W // 16), -(-self.H // 16)
+        self.imagedouble = np.empty((self.H, self.W, 3), np.float32)
+        self.sample_count = np.empty((self.H, self.W), np.float32)
+        self.image = np.empty((self.H, self.W, 3), np.uint8)
+        self.imagedouble_lowres = np.empty((hlr, wlr, 3), np.float32)
+        n = C.c_int32(0)
+        L.check(L.progressive_read(ctx, fptr(self.imagedouble), fptr(self.sample_count), self.image.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                   fptr(self.imagedouble_lowres), C.byref(n)), ctx)
+        self.current_nb_rays = n.value
+        self.stopped = True                      # Raytracer.cpp:1559
+        return self.imagedouble
+
+    # ---- render_image_nopreviz with has_denoiser (Raytracer.cpp:1631-1645, 1676-1693), up to the OIDN hand-over ----
+    def render_denoiser_inputs(self):
+        """Fills `imagedouble` (mean radiance, unsplatted), `sample_count`, `albedoImage`, `normalImage` (as the reference computes it:
+        the normalised COLOUR sum) and `first_hit_normal` (the normalised sum of first-hit shading normals)."""
+        L, ctx = self.lib, self._ctx
+        if ctx is None:
+            self.commit()
+            ctx = self._ctx
+        mk = lambda: np.empty((self.H, self.W, 3), np.float32)
+        self.imagedouble, self.albedoImage, self.normalImage, self.first_hit_normal = mk(), mk(), mk(), mk()
+        self.sample_count = np.empty((self.H, self.W), np.float32)
+        st, cam, p = _abi.Stats(), self.cam.c_struct(), self.params()
+        L.check(L.render_denoiser_inputs(ctx, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count), fptr(self.albedoImage),
+                                         fptr(self.normalImage), fptr(self.first_hit_normal), C.byref(st)), ctx)
+        self.stats = st.as_dict()
+        return self.imagedouble
+
     def render_accum(self, d_rgbw_ptr, shard_rank=0, shard_count=1, tile_size=0):
         """Sharded form: add this shard's sums into a caller-owned DEVICE float4 buffer."""
         L, ctx = self.lib, self._ctx

@@ -222,10 +222,11 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
         nd.ey = exponent_byte(nb.hi[1] - nb.lo[1]);
         nd.ez = exponent_byte(nb.hi[2] - nb.lo[2]);
         const float cell[3] = {std::ldexp(1.f, (int)nd.ex - 127), std::ldexp(1.f, (int)nd.ey - 127), std::ldexp(1.f, (int)nd.ez - 127)};
-        // conservative slack: a thousandth of a cell plus a few ulps of the coordinate
+        // conservative slack: 4e-3 of a cell (covers the rounding of the traversal's folded plane bias in either form of
+        // ptb_bvh8.h planes4) plus a few ulps of the coordinate
         float eps[3], p[3];
         for (int k = 0; k < 3; k++) {
-            eps[k] = cell[k] * 1e-3f + 4e-7f * std::max(std::fabs(nb.lo[k]), std::fabs(nb.hi[k]));
+            eps[k] = cell[k] * 4e-3f + 4e-7f * std::max(std::fabs(nb.lo[k]), std::fabs(nb.hi[k]));
             p[k] = nb.lo[k] - eps[k];
         }
         nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];

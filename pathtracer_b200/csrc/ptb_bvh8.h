@@ -88,22 +88,38 @@ PTB_HD bool alpha_rejects(const AlphaCtx* ctx, int prim, float b1, float b2);
 // bits 31..24 internal children (bit 24 + (slot ^ (7-oct))), bits 23..0 triangles of hit leaves.
 #if defined(__CUDA_ARCH__)
 // Device form.  ncu on the straightforward form showed the XU pipe (48 I2F.U8 per node) as the busiest pipe, so the
-// quantised planes are turned into floats on the ALU + FMA pipes instead: one PRMT drops two plane bytes into the
-// mantissas of a half2 {1024+q0, 1024+q1} (0x6400 | q), HADD2.F32 widens them, and the bias is folded into the FFMA
-// constant: t = (1024+q)*ad + (bo - 1024*ad).  The fold costs at most 2^-24 * 1024 cells (6e-5 of a cell) of rounding,
-// well inside the builder's 1e-3-cell conservative slack.  The meta bytes are decoded four at a time (Ylitie et al. 2017).
+// quantised planes are turned into floats without any conversion instruction (see planes4 below) and the bias is folded
+// into the FFMA constant.  The meta bytes are decoded four at a time (Ylitie et al. 2017).
+// Both the fma pipe (FFMA, HADD2, IMAD) and the alu pipe (PRMT, FMNMX, LOP3, SHF, SEL, ISETP) issue one warp instruction
+// every 2 cycles per SM sub-partition; the node test is bound by the alu pipe (about 116 alu vs 96 fma instructions per node).
+#if !defined(PTB_PLANES_PRMT32)
+// default: one PRMT (alu) builds a half2 {1024+q0, 1024+q1} (0x6400 | q) for TWO planes and HADD2.F32 (fma pipe) widens each;
+// the bias folds into the FFMA constant: t = (1024+q)*ad + (bo - 1024*ad), at most 2^-24 * 1024 = 6e-5 of a cell of rounding.
+#define PTB_PLANE_BIAS 1024.f
 __device__ __forceinline__ void planes4(uint32_t w, float ad, float bo, float& t0, float& t1, float& t2, float& t3) {
     const uint32_t h01 = __byte_perm(w, 0x64646464u, 0x4140), h23 = __byte_perm(w, 0x64646464u, 0x4342);
     const __half2 a = *reinterpret_cast<const __half2*>(&h01), b = *reinterpret_cast<const __half2*>(&h23);
     t0 = fmaf(__low2float(a), ad, bo); t1 = fmaf(__high2float(a), ad, bo);
     t2 = fmaf(__low2float(b), ad, bo); t3 = fmaf(__high2float(b), ad, bo);
 }
+#else
+// measured alternative (r01e, 1.5 % SLOWER on C2/C3): one PRMT per plane drops the byte into bits 8..15 of 0x47000000 = the
+// float 32768 + q, no conversion instruction: 23 fewer instructions per node, but all 48 byte moves land on the alu pipe,
+// which is the busier one.  Fold rounding 2^-24 * 32768 = 2e-3 of a cell (builder slack: 4e-3).
+#define PTB_PLANE_BIAS 32768.f
+__device__ __forceinline__ void planes4(uint32_t w, float ad, float bo, float& t0, float& t1, float& t2, float& t3) {
+    t0 = fmaf(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7404)), ad, bo);
+    t1 = fmaf(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7414)), ad, bo);
+    t2 = fmaf(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7424)), ad, bo);
+    t3 = fmaf(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7434)), ad, bo);
+}
+#endif
 __device__ __forceinline__ uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4& n3, const F4& n4, const RayPrep& r, float tmax) {
     const uint32_t e_imask = f2u(n0.w);
     const float sx = u2f(((e_imask >> 0) & 0xffu) << 23), sy = u2f(((e_imask >> 8) & 0xffu) << 23), sz = u2f(((e_imask >> 16) & 0xffu) << 23);
     const float adx = sx * r.idir.x, ady = sy * r.idir.y, adz = sz * r.idir.z;
-    const float box = fmaf(-1024.f, adx, (n0.x - r.o.x) * r.idir.x), boy = fmaf(-1024.f, ady, (n0.y - r.o.y) * r.idir.y),
-                boz = fmaf(-1024.f, adz, (n0.z - r.o.z) * r.idir.z);
+    const float box = fmaf(-PTB_PLANE_BIAS, adx, (n0.x - r.o.x) * r.idir.x), boy = fmaf(-PTB_PLANE_BIAS, ady, (n0.y - r.o.y) * r.idir.y),
+                boz = fmaf(-PTB_PLANE_BIAS, adz, (n0.z - r.o.z) * r.idir.z);
     const bool negx = r.d.x < 0, negy = r.d.y < 0, negz = r.d.z < 0;
     uint32_t hitmask = 0;
 #pragma unroll
@@ -179,7 +195,14 @@ PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, fl
     const V3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
     const V3 pvec = cross(r.d, e2);
     const float det = dot(e1, pvec);
+#if defined(__CUDA_ARCH__) && !defined(PTB_TRI_RCP_EXACT)
+    // one MUFU.RCP instead of the IEEE division sequence (9 instructions + a slow path): the signs of u, v, t and hence every
+    // accept test but the last ulp of `1-u-v >= 0` and `t < tbest` are unaffected; |det| below 1.2e-38 flushes to a miss.
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(det));
+#else
     const float inv = 1.f / det;
+#endif
     const V3 tvec = r.o - v0;
     const float u = dot(tvec, pvec) * inv;
     const V3 qvec = cross(tvec, e1);

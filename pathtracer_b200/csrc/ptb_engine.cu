@@ -208,7 +208,7 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool want) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
-template <bool MERL, int MINB>
+template <bool MERL, int MINB, bool AOV>
 __global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
                                                const uint32_t* __restrict__ count, int n_static, uint32_t* __restrict__ next_queue,
                                                uint32_t* next_count, uint32_t* shadow_count, uint32_t* shadow_queries) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, Po
     int path = 0;
     if (tid < n) {
         path = queue ? (int)queue[tid] : tid;
-        shade_one<MERL>(sc, f, p, path, out);
+        shade_one<MERL, AOV>(sc, f, p, path, out);
     }
     const uint32_t qi = warp_push(next_count, out.cont);
     if (out.cont) next_queue[qi] = (uint32_t)path;
@@ -253,6 +253,43 @@ __global__ void __launch_bounds__(256) k_resolve(const F4* accum, size_t n, floa
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     resolve_pixel(accum, idx, gamma, imagedouble, sample_count, image);
+}
+
+// has_denoiser tail of render_image_nopreviz (Raytracer.cpp:1676-1693): colour and albedo means, and the two normal images:
+// `normalImage` as the reference computes it (it sums the COLOUR buffers there, 1680-1682, then normalises) and the normalised sum of
+// the first-hit shading normals that line was meant to produce.
+__global__ void __launch_bounds__(256) k_resolve_denoiser(const F4* accum, const F4* albedo, const F4* normal, size_t n, float* imagedouble, float* sample_count,
+                                                          float* albedoImage, float* normalImage, float* first_hit_normal) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const F4 a = accum[idx], k = albedo[idx], m = normal[idx];
+    const float nn = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z), nm = sqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
+    if (imagedouble) { imagedouble[idx * 3] = a.x / a.w; imagedouble[idx * 3 + 1] = a.y / a.w; imagedouble[idx * 3 + 2] = a.z / a.w; }
+    if (sample_count) sample_count[idx] = a.w;
+    if (albedoImage) { albedoImage[idx * 3] = k.x / a.w; albedoImage[idx * 3 + 1] = k.y / a.w; albedoImage[idx * 3 + 2] = k.z / a.w; }
+    if (normalImage) { normalImage[idx * 3] = a.x / nn; normalImage[idx * 3 + 1] = a.y / nn; normalImage[idx * 3 + 2] = a.z / nn; }
+    if (first_hit_normal) { first_hit_normal[idx * 3] = m.x / nm; first_hit_normal[idx * 3 + 1] = m.y / nm; first_hit_normal[idx * 3 + 2] = m.z / nm; }
+}
+
+// tail of the progressive Raytracer::render_image (Raytracer.cpp:1540-1547): imagedouble stays the un-normalised sums, the display
+// image divides by max(sample_count, 1)
+__global__ void __launch_bounds__(256) k_resolve_progressive(const F4* accum, size_t n, float gamma, float* imagedouble, float* sample_count, uint8_t* image) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const F4 a = accum[idx];
+    if (imagedouble) { imagedouble[idx * 3] = a.x; imagedouble[idx * 3 + 1] = a.y; imagedouble[idx * 3 + 2] = a.z; }
+    if (sample_count) sample_count[idx] = a.w;
+    if (image) {
+        const double ig = (double)(1 / gamma);
+        const float d = fmaxf(a.w, 1.f);
+        const float c[3] = {a.x, a.y, a.z};
+        for (int q = 0; q < 3; q++) {
+            double v = 255. * pow((double)c[q] / 196964.7 / (double)d, ig);
+            v = v > 0. ? v : 0.;
+            v = v < 255. ? v : 255.;
+            image[idx * 3 + q] = (uint8_t)v;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(128) k_primary(SceneDev sc, CameraDev cam, int W, int H, int32_t* obj_id, int32_t* tri_id, float* tout) {
@@ -345,6 +382,19 @@ struct ptb_ctx {
     int64_t accum_n = 0;
     float* d_out_img = nullptr; float* d_out_cnt = nullptr; uint8_t* d_out_u8 = nullptr;
     int64_t out_n = 0;
+    F4* d_aux = nullptr;                       // denoiser-input mode: albedo sums, normal sums (2 x W*H float4)
+    int64_t aux_n = 0;
+    float* d_out_aux = nullptr;                // 3 x (W*H*3) floats staged for the host: albedoImage, normalImage, first-hit normal
+    int64_t out_aux_n = 0;
+    // progressive session (Raytracer::render_image): persistent accumulator + low-resolution preview
+    bool prog_active = false;
+    FrameDev prog_f;
+    ptb_params prog_p;
+    int prog_iter = 0;
+    F4* d_prog_accum = nullptr;
+    int64_t prog_n = 0;
+    float* d_lowres = nullptr;
+    int64_t lowres_n = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool count_traversal = false;
@@ -368,7 +418,7 @@ static void free_scene(ptb_ctx* c) {
 }
 static void free_pool(ptb_ctx* c) {
     void* ptrs[] = {c->pool.ray_o, c->pool.ray_d, c->pool.weight, c->pool.radiance, c->pool.hit, c->pool.rng, c->pool.pixel,
-                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1]};
+                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1], c->pool.aov_n, c->pool.aov_kd};
     for (void* p : ptrs) if (p) cudaFree(p);
     memset(&c->pool, 0, sizeof(c->pool));
     c->d_queue[0] = c->d_queue[1] = nullptr;
@@ -386,8 +436,9 @@ static int upload(ptb_ctx* c, const T* host, size_t n, const T** dev) {
     return PTB_OK;
 }
 
-static int ensure_pool(ptb_ctx* c, int64_t paths) {
-    if (paths <= c->pool_cap) return PTB_OK;
+static int ensure_pool(ptb_ctx* c, int64_t paths, bool aov = false) {
+    if (paths <= c->pool_cap && (!aov || c->pool.aov_n)) return PTB_OK;
+    paths = std::max(paths, c->pool_cap);
     free_pool(c);
     const size_t n = (size_t)paths;
     CK(cudaMalloc((void**)&c->pool.ray_o, n * sizeof(F4)));
@@ -402,12 +453,26 @@ static int ensure_pool(ptb_ctx* c, int64_t paths) {
     CK(cudaMalloc((void**)&c->pool.sh_c, n * sizeof(F4)));
     CK(cudaMalloc((void**)&c->d_queue[0], n * sizeof(uint32_t)));
     CK(cudaMalloc((void**)&c->d_queue[1], n * sizeof(uint32_t)));
+    if (aov) {
+        CK(cudaMalloc((void**)&c->pool.aov_n, n * sizeof(F4)));
+        CK(cudaMalloc((void**)&c->pool.aov_kd, n * sizeof(F4)));
+    }
     c->pool_cap = paths;
     return PTB_OK;
 }
 
 static void camera_from_abi(CameraDev& cam, const ptb_camera* pc, int W, int H) {
     camera_setup(cam, pc->position, pc->direction, pc->up, pc->fov, pc->focus_distance, pc->aperture, W, H);
+}
+
+template <class T>
+static int grow(ptb_ctx* c, T** buf, int64_t* have, int64_t want) {
+    if (*have >= want) return PTB_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *have = 0;
+    CK(cudaMalloc((void**)buf, (size_t)want * sizeof(T)));
+    *have = want;
+    return PTB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ C-ABI
@@ -456,7 +521,7 @@ void ptb_destroy(ptb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     free_scene(c);
     free_pool(c);
-    void* ptrs[] = {c->d_counters, c->d_totals, c->d_rpp, c->d_accum, c->d_out_img, c->d_out_cnt, c->d_out_u8};
+    void* ptrs[] = {c->d_counters, c->d_totals, c->d_rpp, c->d_accum, c->d_out_img, c->d_out_cnt, c->d_out_u8, c->d_aux, c->d_out_aux, c->d_prog_accum, c->d_lowres};
     for (void* p : ptrs) if (p) cudaFree(p);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -613,7 +678,8 @@ struct LaunchTimer {
 };
 
 // the pass loop; accumulates into d_rgbw (device, W*H float4)
-static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stats* stats) {
+// samples k_first .. k_first + nrays - 1 of every pixel of the shard
+static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stats* stats, int k_first = 0) {
     auto w0 = std::chrono::steady_clock::now();
     const int64_t pixel_slots = (int64_t)f.n_my_tiles * f.tile * f.tile;
     uint64_t launches = 0;
@@ -636,7 +702,8 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
         if (pixel_slots * nrays <= pool) { spp_pass = nrays; slots_pass = pixel_slots; }
         else if (pixel_slots <= pool) { spp_pass = (int)std::max<int64_t>(1, pool / pixel_slots); slots_pass = pixel_slots; }
         else { spp_pass = 1; slots_pass = (pool / (f.tile * f.tile)) * (f.tile * f.tile); if (slots_pass <= 0) slots_pass = f.tile * f.tile; }
-        int rc = ensure_pool(c, slots_pass * spp_pass);
+        const bool aov = f.accum_albedo != nullptr;
+        int rc = ensure_pool(c, slots_pass * spp_pass, aov);
         if (rc) return rc;
         const int nb = f.nb_bounces;
         for (int64_t s0 = 0; s0 < pixel_slots; s0 += slots_pass) {
@@ -654,7 +721,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
             }
             for (int k0 = 0; k0 < nrays; k0 += spp_pass) {
                 f.spp_pass = std::min(spp_pass, nrays - k0);
-                f.k0 = k0;
+                f.k0 = k_first + k0;
                 f.slot0 = (int)s0;
                 f.n_pixel_slots = (int)ns;
                 const int n_paths = (int)(ns * f.spp_pass);
@@ -678,12 +745,13 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         launches++;
                     }
                     lt.begin(2 | (b << 8));
-#define PTB_SHADE(M, MB) k_shade<M, MB><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1), \
-                                                                    c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b)
-                    if (c->has_merl) PTB_SHADE(true, 5);
-                    else if (c->shade_minb == 8) PTB_SHADE(false, 8);
-                    else if (c->shade_minb == 10) PTB_SHADE(false, 10);
-                    else PTB_SHADE(false, 6);
+#define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1), \
+                                                                          c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b)
+                    if (aov && b == 0) { if (c->has_merl) PTB_SHADE(true, 5, true); else PTB_SHADE(false, 6, true); }   // camera rays of a denoiser-input render
+                    else if (c->has_merl) PTB_SHADE(true, 5, false);
+                    else if (c->shade_minb == 8) PTB_SHADE(false, 8, false);
+                    else if (c->shade_minb == 10) PTB_SHADE(false, 10, false);
+                    else PTB_SHADE(false, 6, false);
 #undef PTB_SHADE
                     lt.end();
                     launches++;
@@ -730,6 +798,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                 fprintf(stderr, "[ptb] %-8s b=%d  %8.3f ms  items=%u\n", names[kind], b, ms, items);
             }
         }
+        (void)k_first;
         kt.items[0] = kt.items[4] = valid_pixels * (unsigned long long)nrays;
         kt.items[1] = kt.items[2] = t[0]; kt.items[3] = t[1];
         kt.node_visits[1] = t[2]; kt.tri_tests[1] = t[3]; kt.node_visits[3] = t[4]; kt.tri_tests[3] = t[5];
@@ -806,6 +875,99 @@ int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* im
     rc = resolve_to_host(c, c->d_accum, p->W, p->H, p->gamma, imagedouble, sample_count, image);
     if (rc) return rc;
     if (stats) stats->ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    return PTB_OK;
+}
+
+// render_image_nopreviz with has_denoiser == true (Raytracer.cpp:1631-1645, 1676-1693), up to the point where the reference
+// hands the buffers to Open Image Denoise
+int ptb_render_denoiser_inputs(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, float* albedoImage,
+                               float* normalImage, float* first_hit_normal, ptb_stats* stats) {
+    if (!c) return PTB_ERR_INVALID;
+    if (!c->committed) { c->err = "render before commit"; return PTB_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    FrameDev f;
+    int rc = frame_setup(c, cam, p, f);
+    if (rc) return rc;
+    if (f.shard_count != 1) { c->err = "render_denoiser_inputs: whole frames only"; return PTB_ERR_UNSUPPORTED; }
+    const int64_t n = (int64_t)p->W * p->H;
+    if ((rc = grow(c, &c->d_accum, &c->accum_n, n))) return rc;
+    if ((rc = grow(c, &c->d_aux, &c->aux_n, 2 * n))) return rc;
+    if ((rc = grow(c, &c->d_out_aux, &c->out_aux_n, 13 * n))) return rc;
+    CK(cudaMemsetAsync(c->d_accum, 0, (size_t)n * sizeof(F4), c->stream));
+    CK(cudaMemsetAsync(c->d_aux, 0, (size_t)n * 2 * sizeof(F4), c->stream));
+    f.box_filter = 1;
+    f.accum_albedo = c->d_aux;
+    f.accum_normal = c->d_aux + n;
+    if ((rc = render_passes(c, f, p->nrays, c->d_accum, stats))) return rc;
+    float* o = c->d_out_aux;   // staged back to back: imagedouble 3n | sample_count n | albedo 3n | normal 3n | first-hit normal 3n
+    k_resolve_denoiser<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_accum, c->d_aux, c->d_aux + n, (size_t)n, o, o + 3 * n, o + 4 * n, o + 7 * n, o + 10 * n);
+    CK(cudaGetLastError());
+    struct { float* host; int64_t off, len; } out[] = {{imagedouble, 0, 3 * n}, {sample_count, 3 * n, n}, {albedoImage, 4 * n, 3 * n}, {normalImage, 7 * n, 3 * n}, {first_hit_normal, 10 * n, 3 * n}};
+    for (auto& e : out) if (e.host) CK(cudaMemcpyAsync(e.host, o + e.off, (size_t)e.len * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+// ---- progressive rendering: Raytracer::render_image (Raytracer.cpp:1424-1563) one batch of passes at a time ---------------------
+int ptb_progressive_begin(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p) {
+    if (!c) return PTB_ERR_INVALID;
+    if (!c->committed) { c->err = "render before commit"; return PTB_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    c->prog_active = false;
+    int rc = frame_setup(c, cam, p, c->prog_f);
+    if (rc) return rc;
+    if (c->prog_f.shard_count != 1) { c->err = "progressive: whole frames only"; return PTB_ERR_UNSUPPORTED; }
+    const int64_t n = (int64_t)p->W * p->H;
+    const int Wlr = (int)ceilf(p->W / 16.f), Hlr = (int)ceilf(p->H / 16.f);     // Raytracer.cpp:1329-1330
+    if ((rc = grow(c, &c->d_prog_accum, &c->prog_n, n))) return rc;
+    if ((rc = grow(c, &c->d_lowres, &c->lowres_n, (int64_t)Wlr * Hlr * 3))) return rc;
+    if ((rc = grow(c, &c->d_out_aux, &c->out_aux_n, (int64_t)Wlr * Hlr * 3))) return rc;
+    CK(cudaMemsetAsync(c->d_prog_accum, 0, (size_t)n * sizeof(F4), c->stream));    // prepare_render: 1383-1385
+    CK(cudaMemsetAsync(c->d_lowres, 0, (size_t)Wlr * Hlr * 3 * sizeof(float), c->stream));
+    c->prog_f.lowres = c->d_lowres; c->prog_f.lowresW = Wlr; c->prog_f.lowresH = Hlr;
+    c->prog_p = *p;
+    c->prog_iter = 0;
+    c->prog_active = true;
+    return PTB_OK;
+}
+
+int ptb_progressive_pass(ptb_ctx* c, int n_spp, ptb_stats* stats) {
+    if (!c) return PTB_ERR_INVALID;
+    if (!c->prog_active) { c->err = "progressive_pass before progressive_begin"; return PTB_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const int n = std::min(n_spp, c->prog_p.nrays - c->prog_iter);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n <= 0) return PTB_OK;                                   // realtime_ray_iter reached nrays: the loop of 1444 has ended
+    int rc = render_passes(c, c->prog_f, n, c->d_prog_accum, stats, c->prog_iter);
+    if (rc) return rc;
+    c->prog_iter += n;
+    return PTB_OK;
+}
+
+int ptb_progressive_read(ptb_ctx* c, float* imagedouble, float* sample_count, uint8_t* image, float* imagedouble_lowres, int32_t* current_nb_rays) {
+    if (!c) return PTB_ERR_INVALID;
+    if (!c->prog_active) { c->err = "progressive_read before progressive_begin"; return PTB_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const ptb_params& p = c->prog_p;
+    const int64_t n = (int64_t)p.W * p.H;
+    if (c->out_n < n) {   // the staging buffers of resolve_to_host, sized together
+        void* ptrs[] = {c->d_out_img, c->d_out_cnt, c->d_out_u8};
+        for (void* q : ptrs) if (q) cudaFree(q);
+        c->d_out_img = nullptr; c->d_out_cnt = nullptr; c->d_out_u8 = nullptr; c->out_n = 0;
+        CK(cudaMalloc((void**)&c->d_out_img, (size_t)n * 3 * sizeof(float)));
+        CK(cudaMalloc((void**)&c->d_out_cnt, (size_t)n * sizeof(float)));
+        CK(cudaMalloc((void**)&c->d_out_u8, (size_t)n * 3));
+        c->out_n = n;
+    }
+    k_resolve_progressive<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_prog_accum, (size_t)n, p.gamma, imagedouble ? c->d_out_img : nullptr,
+                                                                             sample_count ? c->d_out_cnt : nullptr, image ? c->d_out_u8 : nullptr);
+    CK(cudaGetLastError());
+    if (imagedouble) CK(cudaMemcpyAsync(imagedouble, c->d_out_img, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (sample_count) CK(cudaMemcpyAsync(sample_count, c->d_out_cnt, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (image) CK(cudaMemcpyAsync(image, c->d_out_u8, (size_t)n * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (imagedouble_lowres) CK(cudaMemcpyAsync(imagedouble_lowres, c->d_lowres, (size_t)c->prog_f.lowresW * c->prog_f.lowresH * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (current_nb_rays) *current_nb_rays = c->prog_iter;
     return PTB_OK;
 }
 

@@ -307,6 +307,8 @@ struct PoolDev {
     F4* sh_o;         // shadow queue: xyz origin, w = dist_light
     F4* sh_d;         // xyz direction, w = path slot bits
     F4* sh_c;         // xyz = path weight * direct contribution
+    F4* aov_n;        // first-hit shading normal (normalValue, Raytracer.cpp:254-257); null unless the denoiser-input mode renders
+    F4* aov_kd;       // first-hit albedo mat.Kd (albedoValue)
 };
 
 struct FrameDev {     // per-render constants (Raytracer fields + prepare_render results)
@@ -318,6 +320,11 @@ struct FrameDev {     // per-render constants (Raytracer fields + prepare_render
     int32_t slot0;                            // first pixel slot (in the shard's tile-major pixel order) of this pass
     int32_t n_pixel_slots;                    // pixel slots in this pass
     const float* rpp;                         // randomPerPixel, 2 floats per pixel (Raytracer.cpp:1341-1344)
+    int32_t box_filter;                       // has_denoiser accumulation: each sample adds (L, 1) to its own pixel, no splat (Raytracer.cpp:1631-1645)
+    int32_t lowresW, lowresH;                 // progressive preview grid ceil(W/16) x ceil(H/16) (Raytracer.cpp:1329-1330)
+    float* lowres;                            // imagedouble_lowres sums (Raytracer.cpp:1508-1510), or null
+    F4* accum_albedo;                         // box_filter mode: per-pixel sums of the first-hit albedo / normal, or null
+    F4* accum_normal;
 };
 
 // pixel slot (tile-major order over the shard's tiles) -> (i, j); false if outside the image
@@ -380,6 +387,7 @@ PTB_HD void raygen_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pa
     q.x = d.x; q.y = d.y; q.z = d.z; q.w = 0; p.ray_d[path] = q;
     q.x = 1; q.y = 1; q.z = 1; q.w = u2f(pack_state(f.nb_bounces, true)); p.weight[path] = q;
     q.x = 0; q.y = 0; q.z = 0; q.w = 0; p.radiance[path] = q;
+    if (f.accum_albedo) { p.aov_n[path] = q; p.aov_kd[path] = q; }   // `Vector normal, albedo;` start at zero (Vector.h:45) and stay there on a miss
     float ta; int32_t ida;
     analytic_closest(sc, o, d, ta, ida);        // the analytic half of Scene::intersection rides with the ray producer
     q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
@@ -411,7 +419,9 @@ struct ShadeOut {
 
 // MERL = the scene holds at least one IsoMERLBRDF object; scenes without one get a kernel free of the double-precision
 // lookup code (fewer registers, higher occupancy).
-template <bool MERL>
+// AOV = this launch shades the camera rays of a denoiser-input render: the first hit's shading normal and albedo are recorded
+// (`if (has_inter && nbrebonds == nb_bounces) { normalValue = N; albedoValue = mat.Kd; }`, Raytracer.cpp:254-257).
+template <bool MERL, bool AOV = false>
 PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path, ShadeOut& out) {
     out.cont = false; out.shadow = false; out.shadow_query = false;
     const F4 hq = p.hit[path];
@@ -425,6 +435,13 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
     const bool show_lights = (st & 0x10000u) != 0;
     Hit hit; hit.t = hq.x; hit.b1 = hq.y; hit.b2 = hq.z; hit.prim = id;
     F4 Lq = p.radiance[path];
+    if (AOV && depth == f.nb_bounces) {
+        Surface s0;
+        surface_from_hit(sc, ro, rd, hit, id, s0);
+        F4 q; q.w = 0;
+        q.x = s0.N.x; q.y = s0.N.y; q.z = s0.N.z; p.aov_n[path] = q;
+        q.x = s0.Kd.x; q.y = s0.Kd.y; q.z = s0.Kd.z; p.aov_kd[path] = q;
+    }
     if (id == hit_id_analytic(0)) {                                  // the light, Raytracer.cpp:303-316
         const float lp = show_lights ? sc.lightPower : 0.f;
         Lq.x += w.x * lp; Lq.y += w.y * lp; Lq.z += w.z * lp;
@@ -577,6 +594,32 @@ PTB_HD void splat_pixel(const FrameDev& f, const PoolDev& p, int ps, F4* accum, 
     const float ratio = filter_ratio(f.filter, i, j, f.W, f.H, bmin_i, bmax_i, bmin_j, bmax_j);
     const float denom1 = (float)((double)ratio / ((double)(f.filter.sigma * f.filter.sigma) * 2. * PTB_PI_D));
     const uint32_t pix = (uint32_t)(i * f.W + j);
+    if (f.box_filter) {                                  // Raytracer.cpp:1631-1645: unsplatted sums + first-hit AOVs
+        F4 c, a, n;
+        c.x = c.y = c.z = c.w = 0; a = c; n = c;
+        for (int s = 0; s < f.spp_pass; s++) {
+            const F4 L = p.radiance[ps * f.spp_pass + s];
+            c.x += L.x; c.y += L.y; c.z += L.z; c.w += 1.f;
+            if (f.accum_albedo) {
+                const F4 ka = p.aov_kd[ps * f.spp_pass + s], kn = p.aov_n[ps * f.spp_pass + s];
+                a.x += ka.x; a.y += ka.y; a.z += ka.z; n.x += kn.x; n.y += kn.y; n.z += kn.z;
+            }
+        }
+        const size_t o = (size_t)(f.H - i - 1) * f.W + j;
+        add(accum + o, c);
+        if (f.accum_albedo) { add(f.accum_albedo + o, a); add(f.accum_normal + o, n); }
+        return;
+    }
+    if (f.lowres) {                                      // Raytracer.cpp:1508-1510: every sample adds colour/256 to its 16x16 block
+        float r = 0, g = 0, b = 0;
+        for (int s = 0; s < f.spp_pass; s++) { const F4 L = p.radiance[ps * f.spp_pass + s]; r += L.x * (1.f / 256.f); g += L.y * (1.f / 256.f); b += L.z * (1.f / 256.f); }
+        float* q = f.lowres + ((size_t)(f.lowresH - i / 16 - 1) * f.lowresW + j / 16) * 3;
+#if defined(__CUDA_ARCH__)
+        atomicAdd(q, r); atomicAdd(q + 1, g); atomicAdd(q + 2, b);
+#else
+        q[0] += r; q[1] += g; q[2] += b;
+#endif
+    }
     if (f.filter.size == 1) {
         F4 acc[9];
 #pragma unroll

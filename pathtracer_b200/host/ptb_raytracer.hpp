@@ -3,6 +3,7 @@
 // TriangleMesh.h:113-255, Vector.h:720-840) ports by changing an include.  The objects only hold description; all
 // rendering happens in libptb200.so (CUDA).  Errors surface as ptb::Error (the reference reports nothing).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -203,17 +204,56 @@ public:
     void render_image_nopreviz() {
         if (!ctx_) commit();
         ptb_camera c; ptb_params p;
-        for (int k = 0; k < 3; k++) { c.position[k] = cam.position[k]; c.direction[k] = cam.direction[k]; c.up[k] = cam.up[k]; }
-        c.fov = cam.fov; c.focus_distance = cam.focus_distance; c.aperture = cam.aperture;
-        p.W = W; p.H = H; p.nrays = nrays; p.nb_bounces = nb_bounces; p.sigma_filter = sigma_filter; p.gamma = gamma; p.seed = seed;
-        p.shard_rank = 0; p.shard_count = 1; p.tile_size = 0;
+        fill(c, p);
         image.resize((size_t)W * H * 3); imagedouble.resize((size_t)W * H * 3); sample_count.resize((size_t)W * H);
         ck(ptb_render(ctx_, &c, &p, imagedouble.data(), sample_count.data(), image.data(), &stats));
+    }
+
+    // Raytracer::render_image (Raytracer.cpp:1424-1563): progressive; `stopped` may be set from `on_pass` (the GUI sets it from
+    // another thread).  imagedouble holds UN-normalised sums afterwards, like the reference's.
+    bool stopped = true;
+    int current_nb_rays = 0;
+    std::vector<float> imagedouble_lowres;   // ceil(W/16) x ceil(H/16) x 3
+    template <class F>
+    void render_image(F on_pass, int passes_per_call = 1) {
+        if (!ctx_) commit();
+        ptb_camera c; ptb_params p;
+        fill(c, p);
+        ck(ptb_progressive_begin(ctx_, &c, &p));
+        stopped = false; current_nb_rays = 0;
+        while (current_nb_rays < nrays && !stopped) {
+            ck(ptb_progressive_pass(ctx_, passes_per_call, &stats));
+            current_nb_rays = std::min(nrays, current_nb_rays + passes_per_call);
+            on_pass(*this);
+        }
+        const int Wlr = (W + 15) / 16, Hlr = (H + 15) / 16;
+        image.resize((size_t)W * H * 3); imagedouble.resize((size_t)W * H * 3); sample_count.resize((size_t)W * H); imagedouble_lowres.resize((size_t)Wlr * Hlr * 3);
+        int32_t n = 0;
+        ck(ptb_progressive_read(ctx_, imagedouble.data(), sample_count.data(), image.data(), imagedouble_lowres.data(), &n));
+        current_nb_rays = n; stopped = true;
+    }
+    void render_image() { render_image([](Raytracer&) {}); }
+
+    // render_image_nopreviz with has_denoiser (Raytracer.cpp:1631-1645, 1676-1693) up to the hand-over to the denoiser
+    std::vector<float> albedoImage, normalImage, first_hit_normal;
+    void render_denoiser_inputs() {
+        if (!ctx_) commit();
+        ptb_camera c; ptb_params p;
+        fill(c, p);
+        const size_t n = (size_t)W * H;
+        imagedouble.resize(n * 3); sample_count.resize(n); albedoImage.resize(n * 3); normalImage.resize(n * 3); first_hit_normal.resize(n * 3);
+        ck(ptb_render_denoiser_inputs(ctx_, &c, &p, imagedouble.data(), sample_count.data(), albedoImage.data(), normalImage.data(), first_hit_normal.data(), &stats));
     }
 
     ptb_ctx* ctx() { return ctx_; }
 
 private:
+    void fill(ptb_camera& c, ptb_params& p) const {
+        for (int k = 0; k < 3; k++) { c.position[k] = cam.position[k]; c.direction[k] = cam.direction[k]; c.up[k] = cam.up[k]; }
+        c.fov = cam.fov; c.focus_distance = cam.focus_distance; c.aperture = cam.aperture;
+        p.W = W; p.H = H; p.nrays = nrays; p.nb_bounces = nb_bounces; p.sigma_filter = sigma_filter; p.gamma = gamma; p.seed = seed;
+        p.shard_rank = 0; p.shard_count = 1; p.tile_size = 0;
+    }
     void ck(int rc) { if (rc != PTB_OK) throw Error(std::string("ptb error ") + std::to_string(rc) + ": " + ptb_last_error(ctx_)); }
     int device_;
     ptb_ctx* ctx_ = nullptr;

@@ -21,6 +21,12 @@ struct ptb_ctx {
     SceneDev sc;
     bool committed = false;
     bool count = false;
+    // progressive session
+    bool prog = false; ptb_camera prog_cam; ptb_params prog_p; int prog_iter = 0;
+    std::vector<F4> prog_accum; std::vector<float> prog_lowres;
+};
+struct Extras {          // what the denoiser-input and progressive modes add to a render
+    int k_first = 0; bool box = false; F4* albedo = nullptr; F4* normal = nullptr; float* lowres = nullptr;
 };
 static std::string g_err;
 
@@ -52,7 +58,7 @@ int ptb_commit(ptb_ctx* c) {
     return PTB_OK;
 }
 
-static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F4* accum_out, ptb_stats* stats) {
+static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F4* accum_out, ptb_stats* stats, const Extras& x = Extras()) {
     if (!c->committed) return PTB_ERR_STATE;
     auto t0 = std::chrono::steady_clock::now();
     FrameDev f; memset(&f, 0, sizeof(f));
@@ -68,11 +74,15 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     std::vector<float> rpp(2 * npix);
     for (size_t i = 0; i < npix; i++) random_per_pixel((uint32_t)i, rpp[2 * i], rpp[2 * i + 1]);
     f.rpp = rpp.data();
-    f.spp_pass = p->nrays; f.k0 = 0; f.slot0 = 0; f.n_pixel_slots = f.n_my_tiles * f.tile * f.tile;
+    f.spp_pass = p->nrays; f.k0 = x.k_first; f.slot0 = 0; f.n_pixel_slots = f.n_my_tiles * f.tile * f.tile;
+    f.box_filter = x.box ? 1 : 0; f.accum_albedo = x.albedo; f.accum_normal = x.normal;
+    f.lowres = x.lowres; f.lowresW = (int)ceilf(p->W / 16.f); f.lowresH = (int)ceilf(p->H / 16.f);
     const size_t P = (size_t)f.n_pixel_slots * f.spp_pass;
     std::vector<F4> ray_o(P), ray_d(P), weight(P), radiance(P), hit(P), sh_o(P), sh_d(P), sh_c(P);
     std::vector<uint64_t> rng(P); std::vector<uint32_t> pixel(P), q0, q1;
-    PoolDev pool{ray_o.data(), ray_d.data(), weight.data(), radiance.data(), hit.data(), rng.data(), pixel.data(), sh_o.data(), sh_d.data(), sh_c.data()};
+    std::vector<F4> aov_n(x.albedo ? P : 0), aov_kd(x.albedo ? P : 0);
+    PoolDev pool{ray_o.data(), ray_d.data(), weight.data(), radiance.data(), hit.data(), rng.data(), pixel.data(), sh_o.data(), sh_d.data(), sh_c.data(),
+                 x.albedo ? aov_n.data() : nullptr, x.albedo ? aov_kd.data() : nullptr};
     unsigned long long closest = 0, shadow = 0, nodes = 0, tris = 0, samples = 0;
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)P; i++) raygen_one(c->sc, f, pool, (int)i);
@@ -85,7 +95,7 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
         for (long long i = 0; i < n; i++) { TraverseCounters tc{0, 0}; if (c->sc.has_mesh) extend_one<true>(c->sc, pool, (int)q0[i], &tc); nodes += tc.nodes; tris += tc.tris; }
         std::vector<ShadeOut> outs(n);
 #pragma omp parallel for schedule(dynamic, 256)
-        for (long long i = 0; i < n; i++) shade_one<true>(c->sc, f, pool, (int)q0[i], outs[i]);
+        for (long long i = 0; i < n; i++) { if (x.albedo && b == 0) shade_one<true, true>(c->sc, f, pool, (int)q0[i], outs[i]); else shade_one<true>(c->sc, f, pool, (int)q0[i], outs[i]); }
         q1.clear();
         size_t ns = 0;
         for (long long i = 0; i < n; i++) {
@@ -112,6 +122,61 @@ int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* im
     int rc = render_into(c, cam, p, accum.data(), stats);
     if (rc) return rc;
     for (size_t i = 0; i < npix; i++) resolve_pixel(accum.data(), i, p->gamma, imagedouble, sample_count, image);
+    return PTB_OK;
+}
+int ptb_render_denoiser_inputs(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, float* albedoImage,
+                               float* normalImage, float* first_hit_normal, ptb_stats* stats) {
+    const size_t n = (size_t)p->W * p->H;
+    std::vector<F4> acc(n), alb(n), nrm(n);
+    memset(acc.data(), 0, n * sizeof(F4)); memset(alb.data(), 0, n * sizeof(F4)); memset(nrm.data(), 0, n * sizeof(F4));
+    Extras x; x.box = true; x.albedo = alb.data(); x.normal = nrm.data();
+    int rc = render_into(c, cam, p, acc.data(), stats, x);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++) {     // k_resolve_denoiser
+        const F4 a = acc[i], k = alb[i], m = nrm[i];
+        const float nn = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z), nm = sqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
+        if (imagedouble) { imagedouble[i * 3] = a.x / a.w; imagedouble[i * 3 + 1] = a.y / a.w; imagedouble[i * 3 + 2] = a.z / a.w; }
+        if (sample_count) sample_count[i] = a.w;
+        if (albedoImage) { albedoImage[i * 3] = k.x / a.w; albedoImage[i * 3 + 1] = k.y / a.w; albedoImage[i * 3 + 2] = k.z / a.w; }
+        if (normalImage) { normalImage[i * 3] = a.x / nn; normalImage[i * 3 + 1] = a.y / nn; normalImage[i * 3 + 2] = a.z / nn; }
+        if (first_hit_normal) { first_hit_normal[i * 3] = m.x / nm; first_hit_normal[i * 3 + 1] = m.y / nm; first_hit_normal[i * 3 + 2] = m.z / nm; }
+    }
+    return PTB_OK;
+}
+int ptb_progressive_begin(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p) {
+    if (!c->committed) return PTB_ERR_STATE;
+    c->prog = true; c->prog_cam = *cam; c->prog_p = *p; c->prog_iter = 0;
+    c->prog_accum.assign((size_t)p->W * p->H, F4{0, 0, 0, 0});
+    c->prog_lowres.assign((size_t)ceilf(p->W / 16.f) * (size_t)ceilf(p->H / 16.f) * 3, 0.f);
+    return PTB_OK;
+}
+int ptb_progressive_pass(ptb_ctx* c, int n_spp, ptb_stats* stats) {
+    if (!c->prog) return PTB_ERR_STATE;
+    const int n = std::min(n_spp, c->prog_p.nrays - c->prog_iter);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n <= 0) return PTB_OK;
+    ptb_params p = c->prog_p; p.nrays = n;
+    Extras x; x.k_first = c->prog_iter; x.lowres = c->prog_lowres.data();
+    int rc = render_into(c, &c->prog_cam, &p, c->prog_accum.data(), stats, x);
+    if (rc) return rc;
+    c->prog_iter += n;
+    return PTB_OK;
+}
+int ptb_progressive_read(ptb_ctx* c, float* imagedouble, float* sample_count, uint8_t* image, float* imagedouble_lowres, int32_t* current_nb_rays) {
+    if (!c->prog) return PTB_ERR_STATE;
+    const ptb_params& p = c->prog_p;
+    for (size_t i = 0; i < (size_t)p.W * p.H; i++) {     // k_resolve_progressive
+        const F4 a = c->prog_accum[i];
+        if (imagedouble) { imagedouble[i * 3] = a.x; imagedouble[i * 3 + 1] = a.y; imagedouble[i * 3 + 2] = a.z; }
+        if (sample_count) sample_count[i] = a.w;
+        if (image) {
+            const double ig = (double)(1 / p.gamma);
+            const float d = a.w < 1.f ? 1.f : a.w, cc[3] = {a.x, a.y, a.z};
+            for (int q = 0; q < 3; q++) { double v = 255. * pow((double)cc[q] / 196964.7 / (double)d, ig); v = v > 0. ? v : 0.; v = v < 255. ? v : 255.; image[i * 3 + q] = (uint8_t)v; }
+        }
+    }
+    if (imagedouble_lowres) memcpy(imagedouble_lowres, c->prog_lowres.data(), c->prog_lowres.size() * sizeof(float));
+    if (current_nb_rays) *current_nb_rays = c->prog_iter;
     return PTB_OK;
 }
 // in the sim the "device" buffers are plain host memory

@@ -7,6 +7,8 @@ The fixtures pin oracle/port (and through it the CUDA path) to outputs of the re
   sceneio.npz    what the reference's own FILE READERS (load_image, Texture::loadColors/loadNormals, TriMesh::readOBJ/readOFF,
                  Raytracer::load_scene) leave in memory for the fixtures under tests/golden/assets/, and the reference's render of
                  the .scn fixtures loaded by its own load_scene (ids, image, ray counters)
+  modes.npz      the reference's progressive renderer (Raytracer::render_image: sums, weights, display image, low-resolution preview,
+                 after all passes and after a stop at 2) and its has_denoiser accumulation (means, albedo, normalImage)
   scene_<n>.npz  for five miniature versions of the BASELINE.json configurations: primary-hit object /
                  triangle ids and t (the picking query), the linear image (imagedouble), sample_count,
                  the 8-bit image and the ray counters of a single-thread render
@@ -71,11 +73,34 @@ def sceneio_golden(R):
     print("sceneio.npz:", len(out), "arrays")
 
 
+def modes_golden(R):
+    """The reference's progressive renderer (render_image) and its has_denoiser accumulation on tests/parity_cases.mode_scene."""
+    from parity_cases import mode_scene
+    rt = mode_scene(R).commit()
+    rt.set_option(_abi.ORC_OPT_THREADS, 1)
+    out = {}
+    rt.render_image()
+    for k in ("imagedouble", "sample_count", "image", "imagedouble_lowres"):
+        out[f"progressive/{k}"] = getattr(rt, k).copy()
+
+    def stop_after_two(r):
+        r.stopped = r.current_nb_rays >= 2
+    rt.render_image(on_pass=stop_after_two)
+    for k in ("imagedouble", "sample_count", "image", "imagedouble_lowres"):
+        out[f"progressive2/{k}"] = getattr(rt, k).copy()
+    rt.render_denoiser_inputs()
+    for k in ("imagedouble", "sample_count", "albedoImage", "normalImage"):
+        out[f"denoiser/{k}"] = getattr(rt, k).copy()
+    np.savez_compressed(os.path.join(HERE, "modes.npz"), **out)
+    print("modes.npz:", {k: v.shape for k, v in out.items()})
+
+
 def main():
     R = ref_lib()
     assert R is not None, "oracle/_ref is not built (needs /root/reference)"
     sceneio_golden(R)
-    if "--sceneio-only" in sys.argv:
+    modes_golden(R)
+    if "--new-only" in sys.argv:
         return
     rt = scenes.config_C4(R, 32, 32, 1, nv=10).commit()   # any committed scene with a MERL table
     out = {}

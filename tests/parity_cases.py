@@ -206,3 +206,54 @@ def case_errors(test_lib):
     except _abi.PtbError:
         raised = True
     assert raised, "an empty mesh is rejected"
+
+
+# ---- the other two renderers of the reference over the same integrator -------------------------------------------------
+def mode_scene(L, W=56, H=40, spp=6):
+    """A ragged frame (not a multiple of 16 or of the tile) with every path type: mesh + textured plane + mirror sphere + dome."""
+    rt = scenes.config_C2(L, W, H, spp, nv=20, env=(64, 32))
+    # (a sphere WITHOUT any slot keeps whatever material the previous object of Scene::intersection's loop left in `localmat`,
+    #  Geometry.h:979 — its albedo AOV is undefined in the reference, so the mirror gets a slot)
+    rt.s.addObject(Sphere((-14, -20, 8), 6, mirror=True).set_material(0, Kd=Texture((.9, .9, .9))))
+    rt.s.objects[2].set_material(0, Kd=Texture((.7, .6, .5)), Ks=Texture(.1), Ne=Texture(30.0))
+    return rt
+
+
+def case_progressive(test_lib, oracle_lib, frac=FRAC_1SPP):
+    """Raytracer::render_image: un-normalised sums, weight sums, the /max(count,1) display image, the 16x16 low-resolution preview;
+    stopping after k passes; and sums == nopreviz sums (same per-(pixel,sample) streams)."""
+    a, b = mode_scene(oracle_lib).commit(), mode_scene(test_lib).commit()
+    ia, ib = a.render_image().copy(), b.render_image(passes_per_call=4).copy()      # 6 passes as 4 + 2
+    assert a.current_nb_rays == b.current_nb_rays == 6
+    check_images(ib, ia, frac)
+    assert np.allclose(a.sample_count, b.sample_count, rtol=1e-5)
+    assert np.mean(np.abs(a.image.astype(int) - b.image.astype(int)) > 1) <= 2 * frac
+    assert b.imagedouble_lowres.shape == (3, 4, 3) and np.allclose(b.imagedouble_lowres, a.imagedouble_lowres, rtol=2e-3)
+    # un-normalised: dividing by the weights gives the nopreviz image
+    nb = b.render_image_nopreviz().copy()
+    assert np.allclose(ib / b.sample_count[..., None], nb, rtol=1e-4, atol=1e-2)
+    # a stop request after 2 passes (the GUI's `stopped`, Raytracer.cpp:1452)
+    def stop_after_two(rt):
+        rt.stopped = rt.current_nb_rays >= 2
+    a.render_image(on_pass=stop_after_two); b.render_image(on_pass=stop_after_two)
+    assert a.current_nb_rays == b.current_nb_rays == 2
+    check_images(b.imagedouble, a.imagedouble, frac)
+    assert np.allclose(a.sample_count, b.sample_count, rtol=1e-5)
+    a.close(); b.close()
+
+
+def case_denoiser_inputs(test_lib, oracle_lib, frac=FRAC_1SPP):
+    """render_image_nopreviz with has_denoiser: unsplatted means, first-hit albedo, the reference's `normalImage`, and the first-hit normals."""
+    a, b = mode_scene(oracle_lib).commit(), mode_scene(test_lib).commit()
+    a.render_denoiser_inputs(); b.render_denoiser_inputs()
+    check_images(b.imagedouble, a.imagedouble, frac)
+    assert np.array_equal(a.sample_count, b.sample_count) and (b.sample_count == 6).all()
+    assert np.mean(np.abs(a.albedoImage - b.albedoImage).max(-1) > 1e-4) <= frac
+    ok = np.isfinite(a.normalImage).all(-1) & np.isfinite(b.normalImage).all(-1)
+    assert np.array_equal(np.isfinite(a.normalImage).all(-1), np.isfinite(b.normalImage).all(-1)) or ok.mean() > 0.99
+    assert np.mean(np.abs(a.normalImage - b.normalImage)[ok].reshape(-1, 3).max(-1) > 1e-3) <= 2 * frac
+    if np.isfinite(a.first_hit_normal).any():          # the compiled reference cannot produce this one (it sums colours instead)
+        fin = np.isfinite(a.first_hit_normal).all(-1) & np.isfinite(b.first_hit_normal).all(-1)
+        assert fin.mean() > 0.95 and np.mean(np.abs(a.first_hit_normal - b.first_hit_normal)[fin].reshape(-1, 3).max(-1) > 1e-3) <= 2 * frac
+        assert np.allclose(np.linalg.norm(b.first_hit_normal[fin], axis=-1), 1, atol=1e-5)
+    a.close(); b.close()

@@ -6,8 +6,8 @@ import os
 import numpy as np
 import pytest
 from golden_scenes import SCENES
-from parity_cases import (EDGE_VARIANTS, case_converged, case_edge, case_errors, case_kats, case_passes_and_shards, case_scene,
-                          check_ids)
+from parity_cases import (EDGE_VARIANTS, case_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
+                          case_progressive, case_scene, check_ids)
 
 from pathtracer_b200 import _abi, scenes
 
@@ -26,6 +26,14 @@ def test_scenes_devsim_vs_oracle(devsim, port, name):
 @pytest.mark.parametrize("variant", EDGE_VARIANTS)
 def test_edge_cases_devsim(devsim, port, variant):
     case_edge(devsim, port, variant)
+
+
+def test_progressive_devsim(devsim, port):
+    case_progressive(devsim, port)
+
+
+def test_denoiser_inputs_devsim(devsim, port):
+    case_denoiser_inputs(devsim, port)
 
 
 def test_converged_devsim(devsim, port):

@@ -79,3 +79,26 @@ def test_port_is_thread_count_invariant_up_to_summation_order(port):
     ia, ib = a.render_image_nopreviz(), b.render_image_nopreviz()
     assert np.allclose(ia, ib, rtol=1e-5)
     assert a.stats["rays_closest"] == b.stats["rays_closest"]
+
+
+def test_modes_golden_bit_exact(port):
+    """Raytracer::render_image (progressive) and the has_denoiser accumulation of render_image_nopreviz, against the reference's own outputs."""
+    from parity_cases import mode_scene
+    gold = np.load(os.path.join(GOLD, "modes.npz"))
+    rt = mode_scene(port).commit()
+    rt.set_option(_abi.ORC_OPT_THREADS, 1)
+    rt.render_image()
+    for k in ("imagedouble", "sample_count", "image", "imagedouble_lowres"):
+        assert np.array_equal(getattr(rt, k), gold[f"progressive/{k}"]), k
+
+    def stop_after_two(r):
+        r.stopped = r.current_nb_rays >= 2
+    rt.render_image(on_pass=stop_after_two)
+    for k in ("imagedouble", "sample_count", "image", "imagedouble_lowres"):
+        assert np.array_equal(getattr(rt, k), gold[f"progressive2/{k}"]), k
+    rt.render_denoiser_inputs()
+    for k in ("imagedouble", "sample_count", "albedoImage"):
+        assert np.array_equal(getattr(rt, k), gold[f"denoiser/{k}"]), k
+    assert np.array_equal(np.nan_to_num(rt.normalImage, nan=-9), np.nan_to_num(gold["denoiser/normalImage"], nan=-9))
+    fin = np.isfinite(rt.first_hit_normal).all(-1)
+    assert fin.mean() > 0.95 and np.allclose(np.linalg.norm(rt.first_hit_normal[fin], axis=-1), 1, atol=1e-5)

@@ -9,8 +9,8 @@ import os
 import numpy as np
 import pytest
 from golden_scenes import SCENES
-from parity_cases import (EDGE_VARIANTS, case_converged, case_edge, case_errors, case_kats, case_passes_and_shards, case_scene,
-                          check_ids, check_images)
+from parity_cases import (EDGE_VARIANTS, case_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
+                          case_progressive, case_scene, check_ids, check_images)
 
 from pathtracer_b200 import _abi, scenes
 
@@ -53,6 +53,14 @@ def test_scenes_gpu_vs_compiled_reference(gpu, ref):
 @pytest.mark.parametrize("variant", EDGE_VARIANTS)
 def test_edge_cases_gpu(gpu, port, variant):
     case_edge(gpu, port, variant)
+
+
+def test_progressive_gpu(gpu, port):
+    case_progressive(gpu, port)
+
+
+def test_denoiser_inputs_gpu(gpu, port):
+    case_denoiser_inputs(gpu, port)
 
 
 def test_converged_gpu(gpu, port):
