@@ -60,10 +60,12 @@ typedef struct ptb_tex {
 #define PTB_SLOT_NORMAL  (1u << 5)   /* Object::normal_map       */
 #define PTB_SLOT_ALPHA   (1u << 6)   /* Object::alphamap (hit rejected in traversal iff value < 0.5,
                                         TriangleMesh.cpp:1198-1205, 1298-1305) */
+#define PTB_SLOT_KSUB    (1u << 7)   /* Object::subsurface (subsurface albedo Ksub; a surface scatters below itself iff
+                                        |Ksub|^2 > 1e-8, Raytracer.cpp:270, 318-406) */
 
 typedef struct ptb_material {
     uint32_t present;               /* PTB_SLOT_* mask */
-    ptb_tex  Kd, Ks, Ne, transp, refr, normal, alpha;
+    ptb_tex  Kd, Ks, Ne, transp, refr, normal, alpha, Ksub;
 } ptb_material;
 
 /* Object placement == the fields Object::build_matrix reads (Geometry.h:322-360). */
@@ -77,6 +79,9 @@ typedef struct ptb_xform {
 #define PTB_OBJ_MIRROR        (1 << 0)   /* Object::miroir        */
 #define PTB_OBJ_FLIP_NORMALS  (1 << 1)   /* Object::flip_normals  */
 #define PTB_OBJ_FLAT_NORMALS  (1 << 2)   /* !TriMesh::interp_normals (default interpolates) */
+#define PTB_OBJ_GHOST         (1 << 3)   /* Object::ghost (Geometry.h:721): invisible to camera paths and shadow rays, but it
+                                            receives shadows and shows the background photo (Raytracer.cpp:522-537, 547-549,
+                                            614-621; skipped by intersection_shadow, Geometry.cpp:722) */
 
 #define PTB_BRDF_PHONG 0                 /* PhongBRDF   (BRDF.h:37-97), the Object default */
 #define PTB_BRDF_MERL  1                 /* IsoMERLBRDF (BRDF.h:192-248) */
@@ -156,6 +161,25 @@ int ptb_add_merl(ptb_ctx*, const double* table, int* out_merl_id);
 int ptb_set_envmap(ptb_ctx*, const uint8_t* rgb, int W, int H);
 /* replaces: Scene::intensite_lumiere / Scene::envmap_intensity (Raytracer.cpp:1270-1271). */
 int ptb_set_light(ptb_ctx*, float intensite_lumiere, float envmap_intensity);
+
+/* replaces: the Scene::fog_* fields the GUI sliders write (Geometry.h:1371-1377, mainApp.cpp:767-773) and
+ * Raytracer::fogContribution reads (Raytracer.cpp:40-192).  density <= 1e-8 switches the medium off (Raytracer.cpp:206).
+ * The ground level of the medium is the y translation of object 2 (Raytracer.cpp:54), so a fogged scene needs >= 3 objects. */
+typedef struct ptb_fog {
+    float   density;            /* Scene::fog_density           */
+    float   absorption;         /* Scene::fog_absorption        */
+    float   density_decay;      /* Scene::fog_density_decay     */
+    float   absorption_decay;   /* Scene::fog_absorption_decay  */
+    int32_t type;               /* Scene::fog_type        0 uniform, 1 exponential in height */
+    int32_t phase_type;         /* Scene::fog_phase_type  0 isotropic, 1 Schlick, 2 Rayleigh */
+    float   phase_aniso;        /* Scene::phase_aniso     Schlick k */
+} ptb_fog;
+int ptb_set_fog(ptb_ctx*, const ptb_fog*);
+/* replaces: Scene::load_background / clear_background (Geometry.h:1348-1366): the photo behind the scene, W*H*3 floats in
+ * Scene::background order and scale (already pow(v/255, gamma) * 196964.699).  rgb == NULL or W == 0 clears it.  Camera rays
+ * that leave the scene or reach the dome show it (Raytracer.cpp:260-268) and ghost objects tint their indirect light with
+ * it (614-621). */
+int ptb_set_background(ptb_ctx*, const float* rgb, int W, int H);
 
 /* replaces: TriMesh::build_bvh (TriangleMesh.cpp:878-885, 1029-1130) + Scene::prepare_render
  * (Geometry.cpp:280-308): builds the wide BVH over all meshes and uploads the scene to the device. */

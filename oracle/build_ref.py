@@ -20,6 +20,14 @@ Patches applied to the temp copy (each must match exactly once, else the build a
                    preceded by a reseed; see DESIGN.md "RNG"); 5c: the same reseed in front of the
                    draws of the progressive renderer render_image (Raytracer.cpp:1462)
   6. Geometry.cpp  per-thread ray counters at the top of Scene::intersection{,_shadow} (measurement)
+  7. Raytracer.h/.cpp  every `Contrib` of getColor's ring carries its own pcg32 (determinism under branching:
+                   fog and ghost objects push more than one contribution per iteration, and the ring interleaves
+                   their draws).  The continuation of a path keeps the path's stream, so non-branching renders draw
+                   exactly what patch 5 alone gives; a side branch (the in-scattering contribution of
+                   fogContribution, the straight-through ray of a ghost object) starts
+                   ptb_fork(engine, tag) = pcg32(seed = two draws of a COPY of the parent engine, stream = tag),
+                   tag 1 = fog, 2 = ghost.  `float attenuationFactor;` (read uninitialised when the first
+                   fogContribution of a sample returns early) starts at 1.
 Flags: -std=c++11 -O2 -fopenmp -fpermissive -include omp.h -D__forceinline=inline, unity TU.
 """
 import os
@@ -59,6 +67,13 @@ def patch(tmp):
     v = sub_once(v, r"long i = \*\(long \*\)&y;", "int32_t i = *(int32_t *)&y;", "4 invSqRoot pun")
     wr("Vector.h", v)
 
+    h = rd("Raytracer.h")
+    h = sub_once(h, r"(bool show_lights, has_had_subsurface_interaction, showenvmap;\s*\n)(\};)",
+                 r"\1\tpcg32 ptb_rng;\n\2\n"
+                 r"static inline pcg32 ptb_fork(const pcg32& e, uint64_t tag) { pcg32 t = e; uint64_t a = t(); uint64_t b = t(); return pcg32((a << 32) | b, tag); }\n",
+                 "7a Contrib rng")
+    wr("Raytracer.h", h)
+
     r = rd("Raytracer.cpp")
     r = sub_once(r, r"Vector& axis = -N;", "Vector axis = -N;", "2 axis ref")
     # 3: close the `else {` of the has_denoiser branch when OIDN is absent: the LAST #endif of the file
@@ -91,6 +106,26 @@ def patch(tmp):
         r"(for \(int j = j1; j < W; j \+= 8\) \{\s*)(float dx = engine\[threadid\]\(\)\*invmax - 0\.5f;)",
         r"\1engine[threadid] = pcg32((uint64_t)(i*W + j), (uint64_t)realtime_ray_iter ^ ((uint64_t)ptb_ref_global_seed << 32));\n\2",
         "5c progressive per-sample streams")
+    # 7: per-contribution engines, inside the live getColor only (a second copy sits under `#if 0`)
+    g0 = r.index("Vector Raytracer::getColor(")
+    g1 = r.index("#if 0", g0)
+    body = r[g0:g1]
+
+    def sub_n(text, pattern, repl, n_expected, what):
+        new, n = re.subn(pattern, repl, text)
+        if n != n_expected:
+            raise SystemExit(f"build_ref: patch '{what}' matched {n} times (expected {n_expected})")
+        return new
+    body = sub_n(body, r"float attenuationFactor;", "float attenuationFactor = 1.f;", 1, "7b attenuationFactor")
+    body = sub_n(body, r"(contribs\[contribIndexStart\] = Contrib\(Vector\(1\.f, 1\.f, 1\.f\), r, nb_bounces, true, false\);)",
+                 r"\1 contribs[contribIndexStart].ptb_rng = engine[threadid];", 1, "7c root engine")
+    body = sub_n(body, r"(const Contrib& curContrib = contribs\[contribIndexStart\];)", r"\1 engine[threadid] = curContrib.ptb_rng;", 1, "7d pop engine")
+    body = sub_n(body, r"(contribs\[contribIndexEnd\] = newContrib;)", r"\1 contribs[contribIndexEnd].ptb_rng = ptb_fork(engine[threadid], 1);", 6, "7e fog fork")
+    body = sub_n(body, r"(contribs\[contribIndexEnd\] = Contrib\(pathWeight, currentRay, nbrebonds, show_lights, has_had_subsurface_interaction, show_envmap\);)",
+                 r"\1 contribs[contribIndexEnd].ptb_rng = ptb_fork(engine[threadid], 2);", 1, "7f ghost fork")
+    body = sub_n(body, r"(contribs\[contribIndexEnd\] = Contrib\((?:attenuationFactor\*)?(?:pathWeight|newpathWeight), (?:rayon_miroir|new_ray|rayon_aleatoire),[^\n]*\);)",
+                 r"\1 contribs[contribIndexEnd].ptb_rng = engine[threadid];", 6, "7g continuation engine")
+    r = r[:g0] + body + r[g1:]
     wr("Raytracer.cpp", r)
 
     g = rd("Geometry.cpp")

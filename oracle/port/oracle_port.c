@@ -131,12 +131,12 @@ static vec phong_eval(const matvals* m, vec wi, vec wo, vec N) {
                  (float)(powf(d, m->Ne.z) * (m->Ne.z + 2.f) / M_TWO_PI_REF));
     return vadd(vdiv(m->Kd, (float)M_PI), vmul(lobe, m->Ks));
 }
-static vec phong_sample(const matvals* m, vec wo, vec N, float* pdf, float r1, float r2, pcg* e) {
+static vec phong_sample(const matvals* m, vec wo, vec N, float* pdf, float r1, float r2, pcg* e, int* has_sampled_diffuse) {
     float avgNe = (m->Ne.x + m->Ne.y + m->Ne.z) / 3.f;
     float p = 1 - (m->Ks.x + m->Ks.y + m->Ks.z) / 3.f;
     vec R = vreflect(vneg(wo), N), dir;
-    if (pcg_next(e) / 4294967296.f < p) dir = random_cos(N, r1, r2);
-    else dir = random_phong(R, avgNe, r1, r2);
+    if (pcg_next(e) / 4294967296.f < p) { *has_sampled_diffuse = 1; dir = random_cos(N, r1, r2); }
+    else { *has_sampled_diffuse = 0; dir = random_phong(R, avgNe, r1, r2); }
     float proba_phong = (float)((avgNe + 1) / (2.f * M_PI) * powf(vdot(R, dir), avgNe));
     *pdf = (float)(p * vdot(N, dir) / (M_PI) + (1.f - p) * proba_phong);
     return dir;
@@ -214,7 +214,7 @@ typedef struct { int vtx[3], uv[3], n[3], group; } tindex;                  /* T
 typedef struct { vec A, u, v, N; float m11, m12, m22, invdetm; float uvs[3][2]; vec normals[3]; } tsoup; /* Triangle, 67-111 */
 enum { T_MESH, T_SPHERE, T_PLANE };
 typedef struct {
-    int type, miroir, flip_normals, interp_normals, brdf;
+    int type, miroir, flip_normals, interp_normals, brdf, ghost;
     const double* merl;
     float scale, rot[9]; vec rc, tr;
     float trans[12], inv[12], rotm[9];
@@ -231,6 +231,7 @@ struct ptb_ctx {
     double** merl; int n_merl;
     uint8_t* env; int envW, envH;
     float intensite_lumiere, envmap_intensity;
+    ptb_fog fog; float* bg; int bgW, bgH;      /* Scene::fog_*, Scene::background (Geometry.h:1365-1377) */
     int committed, threads;
     char err[256];
     double ms_build; long long n_tri;
@@ -628,6 +629,7 @@ static int scene_shadow(const struct ptb_ctx* c, vec o, vec d, float dist_light,
     if (counter) counter[1]++;
     for (int i = 0; i < c->n_objs; i++) {
         const object* ob = c->objs[i];
+        if (ob->ghost) continue;                                         /* avoid_ghosts == true from getColor (Raytracer.cpp:513, Geometry.cpp:722) */
         vec dl = xf_dir(ob->inv, d), ol = xf_point(ob->inv, o);
         float t; int h, tid; vec P; matvals m;
         if (ob->type == T_MESH) h = mesh_hit(ob, ol, dl, &P, &t, &m, min_t, &tid, 1, dist_light);
@@ -652,75 +654,246 @@ static void camera_ray(const struct ptb_ctx* c, float init_t, int i, int j, floa
     *rd = nd;
 }
 
-/* Raytracer::getColor (Raytracer.cpp:196-664) without fog / subsurface / ghost / background */
-static vec get_color(const struct ptb_ctx* c, vec ro, vec rd, int sampleID, int pix, pcg* e, unsigned long long* counter, const vec* samples2d,
+/* ---- per-contribution engines (oracle/build_ref.py patch 7) ---------------------------------------- */
+typedef struct { vec w, o, d; int depth, show_lights, hadSS, showenv; pcg rng; } contrib; /* Contrib, Raytracer.h:15-23 (+ rng) */
+#define RING 200                                                                        /* sizeCircArray, Raytracer.h:114 */
+static pcg pcg_fork(const pcg* e, uint64_t tag) { pcg t = *e; uint64_t a = pcg_next(&t); uint64_t b = pcg_next(&t); return pcg_seed2((a << 32) | b, tag); }
+static contrib mk_contrib(vec w, vec o, vec d, int depth, int show_lights, int hadSS, int showenv) {
+    contrib k; k.w = w; k.o = o; k.d = d; k.depth = depth; k.show_lights = show_lights; k.hadSS = hadSS; k.showenv = showenv; k.rng.state = 0; k.rng.inc = 1; return k;
+}
+
+/* int_exponential (Raytracer.cpp:20-38) */
+static float int_exponential(float y0, float ysol, float beta, float s, float uy) {
+    float result;
+    if (fabsf(uy * beta) < 0.0001) result = expf(-beta * (y0 - ysol)) * (s);
+    else result = (expf(-beta * (y0 - ysol)) - expf(-beta * (y0 + s * uy - ysol))) / (uy * beta);
+    return result;
+}
+/* random_uniform_sphere<float> (Vector.h:604-615) */
+static vec random_uniform_sphere(pcg* e) {
+    float r1 = pcg_unif(e), r2 = pcg_unif(e);
+    float twopi = (float)(2. * M_PI);
+    return V(2.f * cosf(twopi * r1) * sqrtf(r2 * (1 - r2)), 2.f * sinf(twopi * r1) * sqrtf(r2 * (1 - r2)), 1.f - 2.f * r2);
+}
+/* Raytracer::fogContribution (Raytracer.cpp:40-192).  Returns 1 and fills *out when the in-scattered contribution exists. */
+static int fog_contribution(const struct ptb_ctx* c, vec ro, vec rd, vec sampleLightPos, float t, vec curWeight, int nbrebonds, int showLight, int hadSS,
+                            contrib* out, float* attenuationFactor, pcg* e, unsigned long long* counter) {
+    if (vnorm2(curWeight) < 1E-12) return 0;
+    const float p_uniform = 0.5f;
+    const int is_uniform_fog = (c->fog.type == 0);
+    const float alpha = c->fog.absorption, sigmaT = c->fog.absorption_decay;
+    const float groundLevel = c->objs[2]->tr.y;                            /* objects[2]->get_translation()[1], 54 */
+    float int_ext;
+    if (is_uniform_fog) int_ext = (float)(alpha * t * 0.05);
+    else int_ext = alpha * int_exponential(ro.y, groundLevel, sigmaT, t, rd.y);
+    float T = expf(-int_ext);
+    float proba_t, random_t;
+    float clamped_t = fminr(1000.f, t);
+    float a = vdot(vsub(sampleLightPos, ro), rd);
+    if (a > 0) {                                                           /* equi-angular sampling, 71-84 */
+        vec projP = vadd(ro, vscale(a, rd));
+        float D = sqrtf(vnorm2(vsub(sampleLightPos, projP)));
+        float thetaA = -atan2f(a, D);
+        float b = t - a;
+        float thetaB = atan2f(b, D);
+        float x = pcg_unif(e);
+        random_t = D * tanf((1 - x) * thetaA + x * thetaB);
+        proba_t = D / ((thetaB - thetaA) * (D * D + random_t * random_t));
+        random_t += a;
+    } else {                                                               /* truncated exponential, 90-99 */
+        float alpha2 = 5.f / clamped_t;
+        do { random_t = -logf(pcg_unif(e)) / alpha2; } while (random_t > clamped_t);
+        float normalization = 1.f / alpha2 * (1.f - expf(-alpha2 * clamped_t));
+        proba_t = expf(-alpha2 * random_t) / normalization;
+    }
+    float int_ext_partielle;
+    if (is_uniform_fog) int_ext_partielle = (float)(alpha * random_t * 0.05);
+    else int_ext_partielle = alpha * int_exponential(ro.y, groundLevel, sigmaT, random_t, rd.y);
+    vec random_P = vadd(ro, vscale(random_t, rd));
+    if (random_P.y < groundLevel) return 0;
+    vec random_dir, point_aleatoire = V(0, 0, 0);
+    vec axeOP = vnormalize(vsub(random_P, c->centerLight));
+    int is_uniform;
+    if (pcg_unif(e) < p_uniform) { random_dir = random_uniform_sphere(e); is_uniform = 1; }
+    else {
+        float r1 = pcg_unif(e), r2 = pcg_unif(e);
+        vec dir_aleatoire = random_cos(axeOP, r1, r2);
+        point_aleatoire = vadd(vscale(c->radiusLight, dir_aleatoire), c->centerLight);
+        random_dir = vnormalize(vsub(point_aleatoire, random_P));
+        is_uniform = 0;
+    }
+    float phase_func = 0, k = c->fog.phase_aniso;
+    switch (c->fog.phase_type) {                                           /* 134-144 */
+    case 0: phase_func = (float)(1. / (4. * M_PI)); break;
+    case 1: phase_func = (float)((1 - k * k) / (4. * M_PI * (1 + k * vdot(random_dir, vneg(rd))))); break;
+    case 2: { float dd = vdot(random_dir, rd); phase_func = (float)(3 / (16 * M_PI) * (1 + dd * dd)); break; }
+    }
+    vec interP = V(0, 0, 0); matvals interMat = matvals_default(); int interid = -1, intertri = -1; float intert;
+    int interinter = scene_hit(c, random_P, random_dir, &interP, &interid, &intert, &interMat, &intertri, counter);
+    vec interN = interMat.shadingN;
+    float Vis;
+    if (is_uniform) Vis = 1;
+    else {
+        float d_light2 = vnorm2(vsub(point_aleatoire, random_P));
+        if (interinter && intert * intert < d_light2 * 0.99) Vis = 0; else Vis = 1;
+    }
+    *attenuationFactor = T;
+    if (Vis == 0) return 0;
+    float pdf_uniform = (float)(1. / (4. * M_PI));
+    float J = vdot(interN, vneg(random_dir)) / vnorm2(vsub(interP, random_P));
+    float pdf_light = (interinter && interid == 0) ? (float)(vdot(vnormalize(vsub(interP, c->centerLight)), axeOP) / (M_PI * (c->radiusLight * c->radiusLight)) / J) : 0.f;
+    float proba_dir = p_uniform * pdf_uniform + (1 - p_uniform) * pdf_light;
+    float ext;
+    if (is_uniform_fog) ext = (float)(c->fog.density * 0.05);
+    else ext = c->fog.density * expf(-c->fog.density_decay * (random_P.y - groundLevel));
+    vec newweight = vscale(phase_func * ext * expf(-int_ext_partielle) / (proba_t * proba_dir), curWeight);
+    *out = mk_contrib(newweight, random_P, random_dir, nbrebonds - 1, showLight, hadSS, 1);
+    return 1;
+}
+
+/* Scene::background lookup of getColor (Raytracer.cpp:261-265, 615-619) */
+static vec background_at(const struct ptb_ctx* c, int screenI, int screenJ) {
+    int i = (int)(screenI / (float)c->H * c->bgH); if (i < 0) i = 0; if (i > c->bgH - 1) i = c->bgH - 1;
+    int j = (int)(screenJ / (float)c->W * c->bgW); if (j < 0) j = 0; if (j > c->bgW - 1) j = c->bgW - 1;
+    const float* b = c->bg + ((size_t)i * c->bgW + j) * 3;
+    return V(b[0], b[1], b[2]);
+}
+
+/* Raytracer::getColor (Raytracer.cpp:196-664): the ring of contributions with fog, ghost objects and the background photograph;
+ * the subsurface branch (318-406) is not restated (Ksub slots are refused at commit). */
+#define PUSH(k_) do { ring[end] = (k_); end++; if (end >= RING) end = 0; } while (0)
+static vec get_color(const struct ptb_ctx* c, vec ro0, vec rd0, int sampleID, int pix, pcg* e, unsigned long long* counter, const vec* samples2d,
                      vec* normalValue, vec* albedoValue) {
-    vec color = V(0, 0, 0), w = V(1.f, 1.f, 1.f);
-    int depth = c->nb_bounces, show_lights = 1;
-    for (;;) {
-        if (depth == 0) break;                                      /* 240 */
-        if (vnorm2(w) < 0.01f * 0.01f) break;                       /* 241 */
-        vec P; matvals mat = matvals_default(); int id = -1, tri = -1; float t;
+    contrib ring[RING];
+    int start = 0, end = 1;
+    const int has_fog = (c->fog.density > 1E-8);
+    const int has_bg = c->bgW > 0 && c->bg != NULL;
+    const int screenI = pix / c->W, screenJ = pix % c->W;
+    float att = 1.f;                                                     /* attenuationFactor (patch 7b) */
+    vec color = V(0, 0, 0);
+    ring[0] = mk_contrib(V(1.f, 1.f, 1.f), ro0, rd0, c->nb_bounces, 1, 0, 1);
+    ring[0].rng = *e;
+    while (start != end) {
+        const contrib cur = ring[start];
+        *e = cur.rng;
+        vec ro = cur.o, rd = cur.d, w = cur.w;
+        const int depth = cur.depth, show_lights = cur.show_lights, hadSS = cur.hadSS, show_envmap = cur.showenv;
+        start++; if (start >= RING) start = 0;
+        if (depth == 0) continue;                                       /* 240 */
+        if (vnorm2(w) < 0.01f * 0.01f) continue;                        /* 241 */
+        vec P = V(0, 0, 0); matvals mat = matvals_default(); int id = -1, tri = -1; float t = 0;
         int has = scene_hit(c, ro, rd, &P, &id, &t, &mat, &tri, counter);
         vec N = mat.shadingN;
+        if (getenv("PTB_DBG")) fprintf(stderr, "P %d %d %d %.4f\n", pix, depth, has ? id : -1, has ? t : 0.f);
         if (has && depth == c->nb_bounces && normalValue) { *normalValue = N; *albedoValue = mat.Kd; }   /* 254-257 */
-        if (!has) break;                                            /* 654-657 */
-        if (id == 1) { color = vadd(color, vmul(vscale(c->envmap_intensity, w), mat.Ke)); break; }          /* 275-301 */
-        if (id == 0) { float lp = show_lights ? c->lightPower : 0.f; color = vadd(color, vmul(w, V(lp, lp, lp))); break; } /* 303-316 */
-        const object* ob = c->objs[id];
-        color = vadd(color, vscale(c->envmap_intensity, vmul(w, mat.Ke)));                                  /* 411 */
-        if (ob->miroir) {                                            /* 413-436 */
-            vec nd = vreflect(rd, N);
-            ro = vadd(P, vscale(0.001f, N)); rd = nd; depth--; continue;
+        if (depth == c->nb_bounces && has_bg && (!has || (has && id == 1))) {                           /* 260-268 */
+            color = vadd(color, vmul(w, background_at(c, screenI, screenJ)));
+            continue;
         }
-        if (mat.transp) {                                            /* 438-489 */
-            float n1 = 1.f, n2 = mat.refr_index; vec Nt = N; int entering = 1;
-            if (vdot(rd, N) > 0) { n1 = mat.refr_index; n2 = 1; Nt = vneg(N); entering = 0; }
-            float c0 = vdot(Nt, rd);
-            float radical = 1.f - (n1 / n2) * (n1 / n2) * (1.f - c0 * c0);
-            vec no, nd;
-            if (radical > 0) {
-                vec refr = vsub(vscale(n1 / n2, vsub(rd, vscale(vdot(rd, Nt), Nt))), vscale(sqrtf(radical), Nt));
-                float r0 = (n1 - n2) / (n1 + n2), R0 = r0 * r0, R;
-                if (entering) R = R0 + (1 - R0) * powf(1.f + vdot(rd, N), 5.f);
-                else R = R0 + (1 - R0) * powf(1.f - vdot(refr, N), 5.f);
-                if (pcg_unif(e) < R) { no = vadd(P, vscale(0.001f, Nt)); nd = vreflect(rd, N); }
-                else { no = vsub(P, vscale(0.001f, Nt)); nd = refr; }
-            } else { no = vadd(P, vscale(0.001f, Nt)); nd = vreflect(rd, N); }
-            ro = no; rd = nd; depth--; continue;
+        contrib fogc;
+        if (has) {
+            if (id == 1) {                                              /* 275-301 */
+                if (!show_envmap) {
+                    if (has_fog && fog_contribution(c, ro, rd, c->centerLight, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
+                    continue;
+                }
+                if (has_fog) {
+                    if (fog_contribution(c, ro, rd, c->centerLight, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
+                    color = vadd(color, vmul(vscale(c->envmap_intensity, vscale(att, w)), mat.Ke));
+                } else color = vadd(color, vmul(vscale(c->envmap_intensity, w), mat.Ke));
+                continue;
+            }
+            if (id == 0) {                                              /* 303-316 */
+                float lp = show_lights ? c->lightPower : 0.f;
+                if (has_fog) {
+                    if (fog_contribution(c, ro, rd, c->centerLight, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
+                    color = vadd(color, vmul(vscale(att, w), V(lp, lp, lp)));
+                } else color = vadd(color, vmul(w, V(lp, lp, lp)));
+                continue;
+            }
+            const object* ob = c->objs[id];
+            color = vadd(color, vscale(c->envmap_intensity, vmul(w, mat.Ke)));                              /* 411 */
+            if (ob->miroir) {                                            /* 413-436 */
+                vec nd = vreflect(rd, N), no = vadd(P, vscale(0.001f, N));
+                contrib k;
+                if (has_fog) {
+                    if (fog_contribution(c, ro, rd, c->centerLight, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
+                    k = mk_contrib(vscale(att, w), no, nd, depth - 1, show_lights, hadSS, 1);
+                } else k = mk_contrib(w, no, nd, depth - 1, show_lights, hadSS, 1);
+                k.rng = *e; PUSH(k);
+                continue;
+            }
+            if (mat.transp) {                                            /* 438-489 */
+                float n1 = 1.f, n2 = mat.refr_index; vec Nt = N; int entering = 1;
+                if (vdot(rd, N) > 0) { n1 = mat.refr_index; n2 = 1; Nt = vneg(N); entering = 0; }
+                float c0 = vdot(Nt, rd);
+                float radical = 1.f - (n1 / n2) * (n1 / n2) * (1.f - c0 * c0);
+                vec no, nd;
+                if (radical > 0) {
+                    vec refr = vsub(vscale(n1 / n2, vsub(rd, vscale(vdot(rd, Nt), Nt))), vscale(sqrtf(radical), Nt));
+                    float r0 = (n1 - n2) / (n1 + n2), R0 = r0 * r0, R;
+                    if (entering) R = R0 + (1 - R0) * powf(1.f + vdot(rd, N), 5.f);
+                    else R = R0 + (1 - R0) * powf(1.f - vdot(refr, N), 5.f);
+                    if (pcg_unif(e) < R) { no = vadd(P, vscale(0.001f, Nt)); nd = vreflect(rd, N); }
+                    else { no = vsub(P, vscale(0.001f, Nt)); nd = refr; }
+                } else { no = vadd(P, vscale(0.001f, Nt)); nd = vreflect(rd, N); }
+                contrib k;
+                if (has_fog) {
+                    if (fog_contribution(c, ro, rd, c->centerLight, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
+                    k = mk_contrib(vscale(att, w), no, nd, depth - 1, show_lights, hadSS, 1);
+                } else k = mk_contrib(w, no, nd, depth - 1, show_lights, hadSS, 1);
+                k.rng = *e; PUSH(k);
+                continue;
+            }
+            /* opaque: next-event estimation (494-566) */
+            vec axeOP = vfast_normalize(vsub(P, c->centerLight));
+            float l1 = pcg_unif(e), l2 = pcg_unif(e);
+            vec dirl = random_cos(axeOP, l1, l2);
+            vec xl = vadd(vscale(c->radiusLight, dirl), c->centerLight);
+            vec wi = vfast_normalize(vsub(xl, P));
+            float d2 = vnorm2(vsub(xl, P));
+            int shadowed;
+            if (vdot(mat.shadingN, wi) < 0) shadowed = 1;
+            else shadowed = scene_shadow(c, vadd(P, vscale(0.01f, wi)), wi, sqrtf(d2) - 0.01f, counter);
+            vec contribution = V(0, 0, 0);
+            vec fog_o = ro;                                              /* `currentRay` as fogContribution sees it below */
+            if (!shadowed) {
+                if (ob->ghost) {                                         /* 522-537: straight through, same depth */
+                    vec offset = vdot(N, rd) > 0 ? N : vneg(N);
+                    fog_o = vadd(vadd(P, vscale(0.001f, rd)), vscale(0.001f, offset));
+                    contrib k = mk_contrib(w, fog_o, rd, depth, show_lights, hadSS, show_envmap);
+                    k.rng = pcg_fork(e, 2); PUSH(k);
+                }
+                vec fr = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, wi, vneg(rd), N) : phong_eval(&mat, wi, vneg(rd), N);
+                float J = vdot(dirl, vneg(wi)) / d2;
+                float proba = (float)(vdot(axeOP, dirl) / (M_PI * c->radiusLight * c->radiusLight));
+                if (!ob->ghost && proba > 0.f) contribution = vadd(contribution, vmul(vscale(c->lightPower * fmaxr(0.f, vdot(N, wi)) * J / proba, V(1, 1, 1)), fr));
+            }
+            if (has_fog) {                                               /* 556-566 */
+                if (fog_contribution(c, fog_o, rd, xl, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
+                color = vadd(color, vmul(vscale(att, w), contribution));
+            } else color = vadd(color, vmul(w, contribution));
+            /* continuation (570-632) */
+            float tmp;
+            float r1 = modff(c->randomPerPixel[pix].x + samples2d[sampleID].x, &tmp);
+            float r2 = modff(c->randomPerPixel[pix].y + samples2d[sampleID].y, &tmp);
+            float pdf; vec dir; int diffuse = 0;
+            if (ob->brdf == PTB_BRDF_MERL) { dir = random_cos(N, r1, r2); pdf = (float)(vdot(N, dir) / (M_PI)); }
+            else dir = phong_sample(&mat, vneg(rd), N, &pdf, r1, r2, e, &diffuse);
+            if (vdot(dir, N) < 0 || vdot(dir, vreflect(rd, N)) < 0 || pdf <= 0) continue;
+            vec fi = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, dir, vneg(rd), N) : phong_eval(&mat, dir, vneg(rd), N);
+            vec nw = vscale((vdot(N, dir) / pdf), vmul(vmul(w, V(1, 1, 1)), fi));
+            if (ob->ghost && has_bg) nw = vmul(nw, vdiv(background_at(c, screenI, screenJ), 196964.699f));  /* 614-621 */
+            contrib k = mk_contrib(has_fog ? vscale(att, nw) : nw, vadd(P, vscale(0.01f, dir)), dir, depth - 1, 0, hadSS,
+                                   (show_envmap && shadowed && diffuse) || !ob->ghost);
+            k.rng = *e; PUSH(k);
         }
-        /* opaque: next-event estimation (494-566) */
-        vec axeOP = vfast_normalize(vsub(P, c->centerLight));
-        float l1 = pcg_unif(e), l2 = pcg_unif(e);
-        vec dirl = random_cos(axeOP, l1, l2);
-        vec xl = vadd(vscale(c->radiusLight, dirl), c->centerLight);
-        vec wi = vfast_normalize(vsub(xl, P));
-        float d2 = vnorm2(vsub(xl, P));
-        int shadowed;
-        if (vdot(mat.shadingN, wi) < 0) shadowed = 1;
-        else shadowed = scene_shadow(c, vadd(P, vscale(0.01f, wi)), wi, sqrtf(d2) - 0.01f, counter);
-        vec contrib = V(0, 0, 0);
-        if (!shadowed) {
-            vec fr = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, wi, vneg(rd), N) : phong_eval(&mat, wi, vneg(rd), N);
-            float J = vdot(dirl, vneg(wi)) / d2;
-            float proba = (float)(vdot(axeOP, dirl) / (M_PI * c->radiusLight * c->radiusLight));
-            if (proba > 0.f) contrib = vadd(contrib, vmul(vscale(c->lightPower * fmaxr(0.f, vdot(N, wi)) * J / proba, V(1, 1, 1)), fr));
-        }
-        color = vadd(color, vmul(w, contrib));
-        /* continuation (570-632) */
-        float tmp;
-        float r1 = modff(c->randomPerPixel[pix].x + samples2d[sampleID].x, &tmp);
-        float r2 = modff(c->randomPerPixel[pix].y + samples2d[sampleID].y, &tmp);
-        float pdf; vec dir;
-        if (ob->brdf == PTB_BRDF_MERL) { dir = random_cos(N, r1, r2); pdf = (float)(vdot(N, dir) / (M_PI)); }
-        else dir = phong_sample(&mat, vneg(rd), N, &pdf, r1, r2, e);
-        if (vdot(dir, N) < 0 || vdot(dir, vreflect(rd, N)) < 0 || pdf <= 0) break;
-        vec fi = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, dir, vneg(rd), N) : phong_eval(&mat, dir, vneg(rd), N);
-        w = vscale((vdot(N, dir) / pdf), vmul(vmul(w, V(1, 1, 1)), fi));
-        ro = vadd(P, vscale(0.01f, dir)); rd = dir; depth--; show_lights = 0;
+        if (c->fog.density == 0) continue;                               /* 654-655 */
+        if (!has) break;                                                 /* 657 */
     }
     return color;
 }
+#undef PUSH
 
 static float sat(const float* s, int w, int i0, int i1, int j0, int j1) { /* Raytracer.cpp:1276-1291 */
     float t1 = 0, t2 = 0, t3 = 0;
@@ -780,12 +953,12 @@ void ptb_destroy(ptb_ctx* c) {
     for (int i = 0; i < c->n_objs; i++) free_object(c->objs[i]);
     free(c->objs);
     for (int i = 0; i < c->n_merl; i++) free(c->merl[i]);
-    free(c->merl); free(c->env); free(c->randomPerPixel); free(c);
+    free(c->merl); free(c->env); free(c->bg); free(c->randomPerPixel); free(c);
 }
 static object* new_object(ptb_ctx* c, int type, const ptb_xform* xf, int flags, vec default_rc) {
     object* o = (object*)calloc(1, sizeof(object));
     o->type = type; o->miroir = (flags & PTB_OBJ_MIRROR) != 0; o->flip_normals = (flags & PTB_OBJ_FLIP_NORMALS) != 0;
-    o->interp_normals = (flags & PTB_OBJ_FLAT_NORMALS) == 0;
+    o->interp_normals = (flags & PTB_OBJ_FLAT_NORMALS) == 0; o->ghost = (flags & PTB_OBJ_GHOST) != 0;
     o->scale = 1; o->rot[0] = o->rot[4] = o->rot[8] = 1; o->rc = default_rc; o->tr = V(0, 0, 0);
     if (xf) {
         o->scale = xf->scale; memcpy(o->rot, xf->rotation, sizeof(o->rot)); o->tr = V(xf->translation[0], xf->translation[1], xf->translation[2]);
@@ -891,6 +1064,9 @@ int ptb_set_group_material(ptb_ctx* c, int obj, int group, const ptb_material* m
     if (m->present & PTB_SLOT_REFR) put_slot(&o->slots[S_REFR], group, &m->refr);
     if (m->present & PTB_SLOT_NORMAL) put_slot(&o->slots[S_NORMAL], group, &m->normal);
     if (m->present & PTB_SLOT_ALPHA) put_slot(&o->slots[S_ALPHA], group, &m->alpha);
+    if ((m->present & PTB_SLOT_KSUB) && (m->Ksub.texels || m->Ksub.mult[0] * m->Ksub.mult[0] + m->Ksub.mult[1] * m->Ksub.mult[1] + m->Ksub.mult[2] * m->Ksub.mult[2] > 1E-8f)) {
+        snprintf(c->err, sizeof(c->err), "subsurface scattering is not restated by the port"); return PTB_ERR_UNSUPPORTED;
+    }
     return PTB_OK;
 }
 int ptb_add_merl(ptb_ctx* c, const double* table, int* out_id) {
@@ -921,9 +1097,20 @@ int ptb_set_envmap(ptb_ctx* c, const uint8_t* rgb, int W, int H) {
     return PTB_OK;
 }
 int ptb_set_light(ptb_ctx* c, float il, float ei) { if (!c) return PTB_ERR_INVALID; c->intensite_lumiere = il; c->envmap_intensity = ei; return PTB_OK; }
+int ptb_set_fog(ptb_ctx* c, const ptb_fog* f) { if (!c || !f) return PTB_ERR_INVALID; c->fog = *f; return PTB_OK; }
+int ptb_set_background(ptb_ctx* c, const float* rgb, int W, int H) {
+    if (!c) return PTB_ERR_INVALID;
+    free(c->bg); c->bg = NULL; c->bgW = c->bgH = 0;
+    if (!rgb || W <= 0 || H <= 0) return PTB_OK;
+    c->bg = (float*)malloc((size_t)W * H * 3 * sizeof(float));
+    memcpy(c->bg, rgb, (size_t)W * H * 3 * sizeof(float));
+    c->bgW = W; c->bgH = H;
+    return PTB_OK;
+}
 int ptb_commit(ptb_ctx* c) {
     if (!c) return PTB_ERR_INVALID;
     if (c->n_objs < 2 || c->objs[0]->type != T_SPHERE || c->objs[1]->type != T_SPHERE) { snprintf(c->err, sizeof(c->err), "need light (id 0) and dome (id 1)"); return PTB_ERR_STATE; }
+    if (c->fog.density > 1E-8 && c->n_objs < 3) { snprintf(c->err, sizeof(c->err), "fog needs object 2 (its translation is the ground level)"); return PTB_ERR_STATE; }
     c->committed = 1;
     return PTB_OK;
 }

@@ -21,6 +21,8 @@
 #define ptb_add_merl           ORC_NAME(add_merl)
 #define ptb_set_envmap         ORC_NAME(set_envmap)
 #define ptb_set_light          ORC_NAME(set_light)
+#define ptb_set_fog            ORC_NAME(set_fog)
+#define ptb_set_background     ORC_NAME(set_background)
 #define ptb_commit             ORC_NAME(commit)
 #define ptb_render             ORC_NAME(render)
 #define ptb_render_accum       ORC_NAME(render_accum)

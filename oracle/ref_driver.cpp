@@ -47,7 +47,7 @@ static void apply_xform(Object* o, const ptb_xform* xf, bool is_mesh) {
 static void apply_flags(Object* o, int flags) {
     o->miroir = (flags & PTB_OBJ_MIRROR) != 0;
     o->flip_normals = (flags & PTB_OBJ_FLIP_NORMALS) != 0;
-    o->ghost = false;
+    o->ghost = (flags & PTB_OBJ_GHOST) != 0;
 }
 
 static Texture make_tex(const ptb_tex& t, int type) {
@@ -166,6 +166,7 @@ int ptb_set_group_material(ptb_ctx* c, int obj, int group, const ptb_material* m
     if (m->present & PTB_SLOT_REFR) set_slot(o->refr_index_map, group, make_tex(m->refr, 6));
     if (m->present & PTB_SLOT_NORMAL) set_slot(o->normal_map, group, make_tex(m->normal, 2));
     if (m->present & PTB_SLOT_ALPHA) set_slot(o->alphamap, group, make_tex(m->alpha, 3));
+    if (m->present & PTB_SLOT_KSUB) set_slot(o->subsurface, group, make_tex(m->Ksub, 1));
     return PTB_OK;
 }
 
@@ -213,8 +214,27 @@ int ptb_set_light(ptb_ctx* c, float intensite_lumiere, float envmap_intensity) {
     return PTB_OK;
 }
 
+int ptb_set_fog(ptb_ctx* c, const ptb_fog* f) {
+    if (!c || !f) return PTB_ERR_INVALID;
+    Scene& s = c->rt->s;
+    s.fog_density = f->density; s.fog_absorption = f->absorption;
+    s.fog_density_decay = f->density_decay; s.fog_absorption_decay = f->absorption_decay;
+    s.fog_type = f->type; s.fog_phase_type = f->phase_type; s.phase_aniso = f->phase_aniso;
+    return PTB_OK;
+}
+
+int ptb_set_background(ptb_ctx* c, const float* rgb, int W, int H) {
+    if (!c) return PTB_ERR_INVALID;
+    Scene& s = c->rt->s;
+    if (!rgb || W <= 0 || H <= 0) { s.clear_background(); s.backgroundH = 0; return PTB_OK; }
+    s.background.assign(rgb, rgb + (size_t)W * H * 3);
+    s.backgroundW = W; s.backgroundH = H;
+    return PTB_OK;
+}
+
 int ptb_commit(ptb_ctx* c) {
     if (!c) return PTB_ERR_INVALID;
+    if (c->rt->s.fog_density > 1E-8 && c->rt->s.objects.size() < 3) { c->err = "fog needs object 2 (its translation is the ground level)"; return PTB_ERR_STATE; }
     if (c->rt->s.objects.size() < 2 || !c->rt->s.lumiere) { c->err = "need light (id 0) and dome (id 1)"; return PTB_ERR_STATE; }
     c->committed = true;
     return PTB_OK;

@@ -10,8 +10,8 @@ import ctypes as C
 import numpy as np
 
 OK = 0
-SLOT_KD, SLOT_KS, SLOT_NE, SLOT_TRANSP, SLOT_REFR, SLOT_NORMAL, SLOT_ALPHA = (1 << i for i in range(7))
-OBJ_MIRROR, OBJ_FLIP_NORMALS, OBJ_FLAT_NORMALS = 1, 2, 4
+SLOT_KD, SLOT_KS, SLOT_NE, SLOT_TRANSP, SLOT_REFR, SLOT_NORMAL, SLOT_ALPHA, SLOT_KSUB = (1 << i for i in range(8))
+OBJ_MIRROR, OBJ_FLIP_NORMALS, OBJ_FLAT_NORMALS, OBJ_GHOST = 1, 2, 4, 8
 BRDF_PHONG, BRDF_MERL = 0, 1
 OPT_COUNT_TRAVERSAL, OPT_POOL_PATHS, OPT_TIME_KERNELS, OPT_REFILL_BELOW, OPT_TRACE_BLOCKS, OPT_TRI_FRACTION, OPT_TRI_MIN_PCT = 1, 2, 3, 4, 5, 6, 7
 KERNEL_NAMES = ["raygen", "extend", "shade", "shadow", "splat"]
@@ -33,7 +33,12 @@ class Tex(C.Structure):
 
 class Material(C.Structure):
     _fields_ = [("present", C.c_uint32), ("Kd", Tex), ("Ks", Tex), ("Ne", Tex), ("transp", Tex),
-                ("refr", Tex), ("normal", Tex), ("alpha", Tex)]
+                ("refr", Tex), ("normal", Tex), ("alpha", Tex), ("Ksub", Tex)]
+
+
+class Fog(C.Structure):
+    _fields_ = [("density", C.c_float), ("absorption", C.c_float), ("density_decay", C.c_float), ("absorption_decay", C.c_float),
+                ("type", C.c_int32), ("phase_type", C.c_int32), ("phase_aniso", C.c_float)]
 
 
 class Xform(C.Structure):
@@ -87,7 +92,7 @@ class KernelTimes(C.Structure):
 
 # every symbol include/ptb200.h declares (tests check the product library exports all of them)
 SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_mesh",
-           "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "commit", "render",
+           "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "set_fog", "set_background", "commit", "render",
            "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
            "set_option", "get_scene_info", "kat", "get_kernel_times", "render_denoiser_inputs", "progressive_begin", "progressive_pass",
            "progressive_read"]
@@ -188,6 +193,8 @@ class Lib:
             "add_merl": (C.c_int, [vp, C.POINTER(C.c_double), ip]),
             "set_envmap": (C.c_int, [vp, C.POINTER(C.c_uint8), C.c_int, C.c_int]),
             "set_light": (C.c_int, [vp, C.c_float, C.c_float]),
+            "set_fog": (C.c_int, [vp, C.POINTER(Fog)]),
+            "set_background": (C.c_int, [vp, _fp, C.c_int, C.c_int]),
             "commit": (C.c_int, [vp]),
             "render": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), _fp, _fp, C.POINTER(C.c_uint8), C.POINTER(Stats)]),
             "render_accum": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), vp, C.POINTER(Stats)]),

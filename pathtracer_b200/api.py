@@ -101,7 +101,7 @@ def _texture_from_slot(slot, kind):
 
 
 _SLOTS = [("Kd", _abi.SLOT_KD), ("Ks", _abi.SLOT_KS), ("Ne", _abi.SLOT_NE), ("transp", _abi.SLOT_TRANSP),
-          ("refr", _abi.SLOT_REFR), ("normal", _abi.SLOT_NORMAL), ("alpha", _abi.SLOT_ALPHA)]
+          ("refr", _abi.SLOT_REFR), ("normal", _abi.SLOT_NORMAL), ("alpha", _abi.SLOT_ALPHA), ("Ksub", _abi.SLOT_KSUB)]
 
 
 class Object:
@@ -127,7 +127,7 @@ class Object:
 
     def _flags(self):
         return ((_abi.OBJ_MIRROR if self.miroir else 0) | (_abi.OBJ_FLIP_NORMALS if self.flip_normals else 0)
-                | (0 if self.interp_normals else _abi.OBJ_FLAT_NORMALS))
+                | (0 if self.interp_normals else _abi.OBJ_FLAT_NORMALS) | (_abi.OBJ_GHOST if self.ghost else 0))
 
     def _xform(self):
         x = _abi.Xform()
@@ -209,7 +209,18 @@ class Scene:
         self.envmap_intensity = 1.0
         self.fog_density = self.fog_absorption = self.fog_density_decay = self.fog_absorption_decay = 0.0
         self.fog_type = self.fog_phase_type = 0
+        self.phase_aniso = 0.0
         self.background = None                 # (H,W,3) uint8 as load_image returns it, or None
+        self.background_gamma = 2.2            # the `gamma` argument of Scene::load_background (Geometry.h:1355-1363)
+        self.background_values = None          # (H,W,3) float32 in Scene::background scale; overrides `background` when set
+
+    def _background_floats(self):
+        """Scene::load_background (Geometry.h:1355-1363): pow(v/255, gamma) * 196964.699, kept as float."""
+        if self.background_values is not None:
+            return np.ascontiguousarray(self.background_values, np.float32)
+        if self.background is None:
+            return None
+        return np.ascontiguousarray(np.power(np.asarray(self.background, np.float64) / 255., float(self.background_gamma)) * 196964.699, np.float32)
 
     def addObject(self, o):
         self.objects.append(o)
@@ -274,6 +285,7 @@ class Raytracer:
             s.fog_type, s.fog_phase_type = hd.fog_type, hd.fog_phase_type
             if hd.background:
                 s.background = load_image(hd.background.decode())
+                s.background_gamma = float(hd.gamma)
             for i in range(hd.n_objects):
                 o = _abi.ScnObject()
                 io.check(io.scn_get_object(h, i, C.byref(o)))
@@ -326,15 +338,9 @@ class Raytracer:
     def _unsupported(self):
         """Scene features of the reference that the CUDA path does not render: refused, never approximated."""
         s = self.s
-        if s.fog_density > 1e-8:
-            return "participating media (fog_density > 0)"
-        if s.background is not None:
-            return "background photograph"
         if getattr(self.cam, "is_lenticular", False):
             return "lenticular camera"
         for i, o in enumerate(s.objects):
-            if o.ghost:
-                return f"ghost object {i}"
             if getattr(o, "vertex_colors", None) is not None and len(o.vertex_colors):
                 return f"per-vertex colours on object {i}"
             if i != 1 and getattr(o, "envmap", None) is not None:
@@ -395,6 +401,14 @@ class Raytracer:
             env = np.ascontiguousarray(dome.envmap, np.uint8)
             L.check(L.set_envmap(ctx, env.ctypes.data_as(C.POINTER(C.c_uint8)), env.shape[1], env.shape[0]), ctx)
         L.check(L.set_light(ctx, float(self.s.intensite_lumiere), float(self.s.envmap_intensity)), ctx)
+        s = self.s
+        if s.fog_density > 0:
+            fog = _abi.Fog(float(s.fog_density), float(s.fog_absorption), float(s.fog_density_decay), float(s.fog_absorption_decay),
+                           int(s.fog_type), int(s.fog_phase_type), float(s.phase_aniso))
+            L.check(L.set_fog(ctx, C.byref(fog)), ctx)
+        bg = s._background_floats()
+        if bg is not None:
+            L.check(L.set_background(ctx, fptr(bg), bg.shape[1], bg.shape[0]), ctx)
         L.check(L.commit(ctx), ctx)
         return self
 

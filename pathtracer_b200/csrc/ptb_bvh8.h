@@ -36,6 +36,7 @@ struct alignas(16) Node8 {
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 
 #define PTB_TRI_FLAG_ALPHA 1u  /* tri.w0 bit: this triangle's group has an alpha map that can reject */
+#define PTB_TRI_FLAG_GHOST 2u  /* tri.w0 bit: the triangle belongs to a ghost object; shadow rays pass through it (Geometry.cpp:722) */
 
 struct Hit {
     float t, b1, b2;   // distance, barycentric of v1 (beta), of v2 (gamma)
@@ -281,6 +282,7 @@ PTB_HD bool traverse(const F4* __restrict__ nodes, const F4* __restrict__ tris, 
             float t, b1, b2;
             if (tri_test(a, b, c, r, tbest, t, b1, b2)) {
                 if ((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(actx, (int)prim, b1, b2)) continue;
+                if (ANY_HIT && (f2u(a.w) & PTB_TRI_FLAG_GHOST)) continue;
                 tbest = t;
                 hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = (int32_t)prim;
                 found = true;

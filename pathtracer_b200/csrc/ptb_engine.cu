@@ -35,9 +35,12 @@ using namespace ptb;
 #define PTB_MAX_BOUNCES 64
 #define PTB_CNT_CUR (2 * (PTB_MAX_BOUNCES + 1))
 #define PTB_CNT_SQ (4 * (PTB_MAX_BOUNCES + 1))
-#define PTB_N_COUNTERS (5 * (PTB_MAX_BOUNCES + 1))
+#define PTB_CNT_ALLOC (5 * (PTB_MAX_BOUNCES + 1))       // branching renders: side-branch slots handed out in this pass
+#define PTB_CNT_DROPS (5 * (PTB_MAX_BOUNCES + 1) + 1)   // side branches that found the pool full
+#define PTB_N_COUNTERS (5 * (PTB_MAX_BOUNCES + 1) + 2)
 // 64-bit totals: 0 closest rays, 1 shadow rays, 2/3 node visits / triangle tests of the closest-hit trace, 4/5 of the any-hit trace
 #define PTB_N_TOTALS 6
+#define PTB_BRANCH_MAX_LEVELS 512
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) k_rpp(float* rpp, int n) {
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev sc, FrameDev f, PoolDev
 //     the triangle group on the traversal stack (Ylitie et al. 2017, sec. 4).
 // ANY_HIT = shadow rays (queue = shadow entries, first accepted triangle ends the ray; an unoccluded ray adds its deferred
 // direct term to the path's radiance).  Closest-hit results overwrite the analytic hit record the ray's producer wrote.
-template <bool ANY_HIT, bool COUNT>
+template <bool ANY_HIT, bool COUNT, bool BRANCH = false>
 __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below, int tri_den, int tri_min_pct) {
     const uint32_t FULL = 0xffffffffu;
@@ -125,7 +128,8 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
                 const U2 e = stack[--sp];
                 if (e.y > 0x00ffffffu) ngroup = e; else tgroup = e;
             } else {
-                if (ANY_HIT) {   // unoccluded: deliver the deferred direct term (Raytracer.cpp:545-566)
+                if (ANY_HIT && BRANCH) shadow_settle_branch(p, (int)entry, item, false);
+                else if (ANY_HIT) {   // unoccluded: deliver the deferred direct term (Raytracer.cpp:545-566)
                     const F4 c = p.sh_c[entry];
                     F4 L = p.radiance[item];
                     L.x += c.x; L.y += c.y; L.z += c.z;
@@ -180,9 +184,9 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
                     if (COUNT) ct++;
                     float t, b1, b2;
                     if (tri_test(a, b, c, r, tbest, t, b1, b2)) {
-                        if (!((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(&ac, (int)prim, b1, b2))) {
+                        if (!((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(&ac, (int)prim, b1, b2)) && !(ANY_HIT && (f2u(a.w) & PTB_TRI_FLAG_GHOST))) {
                             tbest = t; hb1 = b1; hb2 = b2; hprim = (int32_t)prim;
-                            if (ANY_HIT) { live = false; tgroup.y = 0; }   // occluded: nothing to deliver
+                            if (ANY_HIT) { live = false; tgroup.y = 0; if (BRANCH) shadow_settle_branch(p, (int)entry, item, true); }   // occluded: nothing to deliver
                         }
                     }
                 }
@@ -226,6 +230,47 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, Po
     const uint32_t si = warp_push(shadow_count, out.shadow);
     if (out.shadow) { p.sh_o[si] = out.sh_o; p.sh_d[si] = out.sh_d; p.sh_c[si] = out.sh_c; }
     const uint32_t sq = __ballot_sync(0xffffffffu, out.shadow_query);
+    if ((threadIdx.x & 31) == 0 && sq) atomicAdd(shadow_queries, (uint32_t)__popc(sq));
+}
+
+// Branching renders (fog, ghost objects, background photograph): one getColor loop iteration per queue entry; side branches
+// take fresh pool slots (one atomic per warp and kind) and join the next level's queue next to the continuations.
+template <bool MERL>
+__global__ void __launch_bounds__(128) k_shade_branch(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
+                                                      int n_static, uint32_t* __restrict__ next_queue, uint32_t* next_count, uint32_t* shadow_count,
+                                                      uint32_t* shadow_queries, uint32_t* alloc, uint32_t n_roots, uint32_t cap, uint32_t* drops) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = count ? (int)*count : n_static;
+    BranchOut out;
+    out.base.cont = false; out.base.shadow = false; out.base.shadow_query = false;
+    out.fog.want = false; out.ghost.want = false; out.ghost_pending = false;
+    int path = 0;
+    uint32_t root = 0, pix = 0;
+    if (tid < n) {
+        path = queue ? (int)queue[tid] : tid;
+        root = p.root[path]; pix = p.pixel[path];
+        if (pix != 0xffffffffu) shade_branch_one<MERL>(sc, f, p, path, out);
+    }
+    uint32_t ghost_slot = 0x7fffffffu;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const ChildOut& ch = k == 0 ? out.fog : out.ghost;
+        bool want = ch.want;
+        const uint32_t slot = n_roots + warp_push(alloc, want);
+        if (want && slot >= cap) { want = false; atomicAdd(drops, 1u); }
+        if (want) { store_child(sc, p, slot, ch, root, pix); if (k == 1) ghost_slot = slot; }
+        const uint32_t ci = warp_push(next_count, want);
+        if (want) next_queue[ci] = slot;
+    }
+    const uint32_t qi = warp_push(next_count, out.base.cont);
+    if (out.base.cont) next_queue[qi] = (uint32_t)path;
+    const uint32_t si = warp_push(shadow_count, out.base.shadow);
+    if (out.base.shadow) {
+        F4 c = out.base.sh_c;
+        if (out.ghost_pending) c.w = u2f(0x80000000u | ghost_slot);
+        p.sh_o[si] = out.base.sh_o; p.sh_d[si] = out.base.sh_d; p.sh_c[si] = c;
+    }
+    const uint32_t sq = __ballot_sync(0xffffffffu, out.base.shadow_query);
     if ((threadIdx.x & 31) == 0 && sq) atomicAdd(shadow_queries, (uint32_t)__popc(sq));
 }
 
@@ -418,7 +463,7 @@ static void free_scene(ptb_ctx* c) {
 }
 static void free_pool(ptb_ctx* c) {
     void* ptrs[] = {c->pool.ray_o, c->pool.ray_d, c->pool.weight, c->pool.radiance, c->pool.hit, c->pool.rng, c->pool.pixel,
-                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1], c->pool.aov_n, c->pool.aov_kd};
+                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1], c->pool.aov_n, c->pool.aov_kd, c->pool.root};
     for (void* p : ptrs) if (p) cudaFree(p);
     memset(&c->pool, 0, sizeof(c->pool));
     c->d_queue[0] = c->d_queue[1] = nullptr;
@@ -436,9 +481,10 @@ static int upload(ptb_ctx* c, const T* host, size_t n, const T** dev) {
     return PTB_OK;
 }
 
-static int ensure_pool(ptb_ctx* c, int64_t paths, bool aov = false) {
-    if (paths <= c->pool_cap && (!aov || c->pool.aov_n)) return PTB_OK;
+static int ensure_pool(ptb_ctx* c, int64_t paths, bool aov = false, bool branch = false) {
+    if (paths <= c->pool_cap && (!aov || c->pool.aov_n) && (!branch || c->pool.root)) return PTB_OK;
     paths = std::max(paths, c->pool_cap);
+    aov = aov || c->pool.aov_n; branch = branch || c->pool.root;
     free_pool(c);
     const size_t n = (size_t)paths;
     CK(cudaMalloc((void**)&c->pool.ray_o, n * sizeof(F4)));
@@ -457,6 +503,7 @@ static int ensure_pool(ptb_ctx* c, int64_t paths, bool aov = false) {
         CK(cudaMalloc((void**)&c->pool.aov_n, n * sizeof(F4)));
         CK(cudaMalloc((void**)&c->pool.aov_kd, n * sizeof(F4)));
     }
+    if (branch) CK(cudaMalloc((void**)&c->pool.root, n * sizeof(uint32_t)));
     c->pool_cap = paths;
     return PTB_OK;
 }
@@ -590,6 +637,22 @@ int ptb_set_light(ptb_ctx* c, float intensite_lumiere, float envmap_intensity) {
     return PTB_OK;
 }
 
+int ptb_set_fog(ptb_ctx* c, const ptb_fog* fog) {
+    if (!c || !fog) return PTB_ERR_INVALID;
+    if (fog->type < 0 || fog->type > 1 || fog->phase_type < 0 || fog->phase_type > 2) { c->err = "set_fog: fog_type is 0..1, fog_phase_type 0..2"; return PTB_ERR_INVALID; }
+    c->host.fog = *fog;
+    return PTB_OK;
+}
+
+int ptb_set_background(ptb_ctx* c, const float* rgb, int W, int H) {
+    if (!c) return PTB_ERR_INVALID;
+    c->host.background.clear(); c->host.bgW = c->host.bgH = 0;
+    if (!rgb || W <= 0 || H <= 0) return PTB_OK;
+    c->host.background.assign(rgb, rgb + (size_t)W * H * 3);
+    c->host.bgW = W; c->host.bgH = H;
+    return PTB_OK;
+}
+
 int ptb_commit(ptb_ctx* c) {
     if (!c) return PTB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
@@ -601,6 +664,8 @@ int ptb_commit(ptb_ctx* c) {
     SceneDev& sc = c->sc;
     memset(&sc, 0, sizeof(sc));
     scene_header(sc, f);        // before the upload: it tags objects that do not fit the inline table
+    if ((rc = scene_modes(sc, c->host, c->err))) return rc;
+    if (sc.bgW > 0 && (rc = upload(c, c->host.background.data(), c->host.background.size(), &sc.background))) return rc;
     c->has_merl = false;
     for (const ObjectDev& o : f.objects) if (o.brdf == 1) c->has_merl = true;
     const Node8* dn; const F4* dt; const uint8_t* de;
@@ -683,6 +748,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
     auto w0 = std::chrono::steady_clock::now();
     const int64_t pixel_slots = (int64_t)f.n_my_tiles * f.tile * f.tile;
     uint64_t launches = 0;
+    unsigned long long branch_closest = 0, branch_shadow = 0;   // ray statistics of the branching level loop (counted on the host)
     LaunchTimer lt(c);
     memset(&c->ktimes, 0, sizeof(c->ktimes));
     CK(cudaMemsetAsync(c->d_totals, 0, PTB_N_TOTALS * sizeof(unsigned long long), c->stream));
@@ -698,12 +764,19 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
     if (pixel_slots > 0) {
         // samples per pixel per pass and pixel slots per pass
         int64_t pool = std::max<int64_t>(c->pool_paths, 1024);
+        // Branching renders keep every live contribution of a sample in the pool: the continuation reuses its slot, each side
+        // branch takes a new one.  A fogged path forks once per iteration (at most 2^depth - 1 forks per sample), a ghost hit once.
+        const bool branch = c->sc.has_fog || c->sc.has_ghost || c->sc.bgW > 0;
+        const int fan = !branch ? 1 : (c->sc.has_fog ? (1 << std::min(f.nb_bounces, 6)) : (c->sc.has_ghost ? 8 : 1));
+        if (branch && f.accum_albedo) { c->err = "denoiser inputs are not available with fog, ghost objects or a background photograph"; return PTB_ERR_UNSUPPORTED; }
+        const int64_t pool_cap_slots = pool;
+        pool = std::max<int64_t>(pool / fan, 1024);
         int spp_pass; int64_t slots_pass;
         if (pixel_slots * nrays <= pool) { spp_pass = nrays; slots_pass = pixel_slots; }
         else if (pixel_slots <= pool) { spp_pass = (int)std::max<int64_t>(1, pool / pixel_slots); slots_pass = pixel_slots; }
         else { spp_pass = 1; slots_pass = (pool / (f.tile * f.tile)) * (f.tile * f.tile); if (slots_pass <= 0) slots_pass = f.tile * f.tile; }
         const bool aov = f.accum_albedo != nullptr;
-        int rc = ensure_pool(c, slots_pass * spp_pass, aov);
+        int rc = ensure_pool(c, branch ? std::max<int64_t>(slots_pass * spp_pass * fan, pool_cap_slots) : slots_pass * spp_pass, aov, branch);
         if (rc) return rc;
         const int nb = f.nb_bounces;
         for (int64_t s0 = 0; s0 < pixel_slots; s0 += slots_pass) {
@@ -731,7 +804,73 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                 k_raygen<<<g256, 256, 0, c->stream>>>(c->sc, f, c->pool, n_paths);
                 lt.end();
                 launches++;
-                for (int b = 0; b < nb; b++) {
+                int levels = nb;
+                if (branch) {
+                    // Level-synchronous walk of the contribution tree; the host reads each level's queue lengths (these are the
+                    // reference's compositing / medium modes, not the benchmarked path).  Counter slots alternate with the level's
+                    // parity.  A straight-through ray keeps its depth (Raytracer.cpp:529-531), and at grazing angles the shading-normal
+                    // offset can put it back in front of the ghost triangle it just crossed: the reference then re-hits it for up to
+                    // hundreds of iterations (its ring simply keeps turning).  Here such chains end after PTB_BRANCH_MAX_LEVELS.
+                    uint32_t n_level = (uint32_t)n_paths;
+                    const bool mesh = c->sc.has_mesh != 0;
+                    int b = 0;
+                    for (; b < PTB_BRANCH_MAX_LEVELS && n_level > 0 && nb > 0; b++) {
+                        const int s = b & 1, ns = (b + 1) & 1;
+                        uint32_t* cnt_q = c->d_counters + 2 * s; uint32_t* cnt_sh = c->d_counters + 2 * s + 1; uint32_t* cnt_next = c->d_counters + 2 * ns;
+                        uint32_t* cur = c->d_counters + PTB_CNT_CUR + 2 * s; uint32_t* cnt_sq = c->d_counters + PTB_CNT_SQ + s;
+                        if (b >= 1) {
+                            CK(cudaMemsetAsync(cnt_next, 0, sizeof(uint32_t), c->stream));
+                            if (b >= 2) {
+                                CK(cudaMemsetAsync(cnt_sh, 0, sizeof(uint32_t), c->stream));
+                                CK(cudaMemsetAsync(cur, 0, 2 * sizeof(uint32_t), c->stream));
+                                CK(cudaMemsetAsync(cnt_sq, 0, sizeof(uint32_t), c->stream));
+                            }
+                        }
+                        const uint32_t* q = b == 0 ? nullptr : c->d_queue[s];
+                        const uint32_t* cnt = b == 0 ? nullptr : cnt_q;
+                        const unsigned gt = (unsigned)std::max(1, std::min<int>(c->trace_blocks, (int)((n_level + 127) / 128)));
+                        const unsigned gs = (unsigned)((n_level + 127) / 128);
+                        if (mesh) {
+                            lt.begin(1 | (std::min(b, 63) << 8));
+                            if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, cur, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                            else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, cur, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                            lt.end();
+                            launches++;
+                        }
+                        lt.begin(2 | (std::min(b, 63) << 8));
+                        if (c->has_merl) k_shade_branch<true><<<gs, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[ns], cnt_next, cnt_sh, cnt_sq, c->d_counters + PTB_CNT_ALLOC,
+                                                                                          (uint32_t)n_paths, (uint32_t)c->pool_cap, c->d_counters + PTB_CNT_DROPS);
+                        else k_shade_branch<false><<<gs, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[ns], cnt_next, cnt_sh, cnt_sq, c->d_counters + PTB_CNT_ALLOC,
+                                                                              (uint32_t)n_paths, (uint32_t)c->pool_cap, c->d_counters + PTB_CNT_DROPS);
+                        lt.end();
+                        launches++;
+                        uint32_t h_sh = 0, h_next = 0, h_sq = 0;
+                        CK(cudaMemcpyAsync(&h_sh, cnt_sh, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                        CK(cudaMemcpyAsync(&h_next, cnt_next, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                        CK(cudaMemcpyAsync(&h_sq, cnt_sq, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                        CK(cudaStreamSynchronize(c->stream));
+                        if (mesh && h_sh > 0) {
+                            const unsigned ga = (unsigned)std::max(1, std::min<int>(c->trace_blocks, (int)((h_sh + 127) / 128)));
+                            lt.begin(3 | (std::min(b, 63) << 8));
+                            if (c->count_traversal) k_trace<true, true, true><<<ga, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, cnt_sh, 0, cur + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                            else k_trace<true, false, true><<<ga, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, cnt_sh, 0, cur + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                            lt.end();
+                            launches++;
+                        }
+                        branch_closest += b == 0 ? valid_here * (unsigned long long)f.spp_pass : (unsigned long long)n_level;
+                        branch_shadow += h_sq;
+                        n_level = h_next;
+                    }
+                    levels = 0;   // k_totals adds nothing: the level loop counted on the host
+                    uint32_t drops = 0;
+                    CK(cudaMemcpyAsync(&drops, c->d_counters + PTB_CNT_DROPS, sizeof(drops), cudaMemcpyDeviceToHost, c->stream));
+                    CK(cudaStreamSynchronize(c->stream));
+                    if (drops > 0) {
+                        c->err = "branching render: contribution pool exhausted (" + std::to_string(drops) + " side branches dropped); raise PTB_OPT_POOL_PATHS";
+                        return PTB_ERR_NOMEM;
+                    }
+                }
+                for (int b = 0; b < nb && !branch; b++) {
                     const uint32_t* q = b == 0 ? nullptr : c->d_queue[b & 1];
                     const uint32_t* cnt = b == 0 ? nullptr : c->d_counters + 2 * b;
                     const bool mesh = c->sc.has_mesh != 0;
@@ -766,7 +905,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                 lt.begin(4);
                 k_splat<<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(f, c->pool, d_rgbw);
                 lt.end();
-                k_totals<<<1, 32, 0, c->stream>>>(c->d_counters, nb, nb > 0 ? valid_here * (unsigned long long)f.spp_pass : 0ull, c->d_totals);
+                k_totals<<<1, 32, 0, c->stream>>>(c->d_counters, levels, (nb > 0 && !branch) ? valid_here * (unsigned long long)f.spp_pass : 0ull, c->d_totals);
                 launches += 2;
                 CK(cudaGetLastError());
             }
@@ -776,6 +915,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
     CK(cudaStreamSynchronize(c->stream));
     unsigned long long t[PTB_N_TOTALS];
     CK(cudaMemcpy(t, c->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
+    t[0] += branch_closest; t[1] += branch_shadow;
     {
         ptb_kernel_times& kt = c->ktimes;
         for (size_t i = 0; i < c->ev_kind.size(); i++) {

@@ -60,6 +60,9 @@ struct HostScene {
     std::vector<uint8_t> envmap;
     int envW = 0, envH = 0;
     float intensite_lumiere = 0, envmap_intensity = 1;
+    ptb_fog fog = {0, 0, 0, 0, 0, 0, 0};            // Scene::fog_* (Geometry.h:1371-1377)
+    std::vector<float> background;                  // Scene::background (Geometry.h:1365), bgW*bgH*3
+    int bgW = 0, bgH = 0;
 
     int add_sphere(const float O[3], float R, const ptb_xform* xf, int flags);
     int add_plane(const float A[3], const float N[3], const ptb_xform* xf, int flags);
@@ -78,16 +81,32 @@ inline void scene_header(SceneDev& sc, FlatScene& f) {
     sc.envmap_intensity = f.envmap_intensity; sc.lightPower = f.lightPower; sc.radiusLight = f.radiusLight;
     sc.centerLight = v3(f.centerLight[0], f.centerLight[1], f.centerLight[2]);
     sc.n_inline = 0; sc.n_extra = 0;
+    sc.has_ghost = 0;
     for (size_t i = 0; i < f.objects.size(); i++) {
         ObjectDev& o = f.objects[i];
+        if (o.flags & FLAG_GHOST) sc.has_ghost = 1;
         if (o.type == OBJ_MESH) continue;
         if (sc.n_inline < PTB_INLINE_ANALYTIC) {
             AnalyticDev& a = sc.analytic[sc.n_inline++];
-            a.type = o.type; a.id = (int32_t)i; a.R2 = o.R2;
+            a.type = o.type | ((o.flags & FLAG_GHOST) ? PTB_ANALYTIC_GHOST : 0); a.id = (int32_t)i; a.R2 = o.R2;
             for (int k = 0; k < 12; k++) a.inv_trans[k] = o.inv_trans[k];
             for (int k = 0; k < 3; k++) { a.a[k] = o.a[k]; a.n[k] = o.n[k]; }
         } else { o.flags |= FLAG_NOT_INLINE; sc.n_extra++; }
     }
+}
+
+// Medium / compositing modes of the scene (by-value part; the background pointer is the caller's business).
+inline int scene_modes(SceneDev& sc, const HostScene& h, std::string& err) {
+    sc.has_fog = h.fog.density > 1E-8f ? 1 : 0;                          // Raytracer.cpp:206
+    sc.fog.density = h.fog.density; sc.fog.absorption = h.fog.absorption; sc.fog.density_decay = h.fog.density_decay;
+    sc.fog.absorption_decay = h.fog.absorption_decay; sc.fog.phase_aniso = h.fog.phase_aniso;
+    sc.fog.type = h.fog.type; sc.fog.phase_type = h.fog.phase_type; sc.fog.ground = 0;
+    if (sc.has_fog) {
+        if (h.objects.size() < 3) { err = "fog needs object 2 (its translation is the ground level, Raytracer.cpp:54)"; return PTB_ERR_STATE; }
+        sc.fog.ground = h.objects[2].xf.translation[1];
+    }
+    sc.bgW = h.bgW; sc.bgH = h.bgH; sc.background = nullptr;
+    return PTB_OK;
 }
 
 }  // namespace ptb

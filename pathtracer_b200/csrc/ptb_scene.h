@@ -14,7 +14,7 @@
 namespace ptb {
 
 enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2 };
-enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4, FLAG_NOT_INLINE = 1 << 16 };
+enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4, FLAG_GHOST = 8, FLAG_NOT_INLINE = 1 << 16 };
 enum { SLOT_KD = 1, SLOT_KS = 2, SLOT_NE = 4, SLOT_TRANSP = 8, SLOT_REFR = 16, SLOT_NORMAL = 32, SLOT_ALPHA = 64 };
 
 struct ObjectDev {          // Object / Sphere / Plane fields the path reads (Geometry.h:240-672, 849-1217)
@@ -46,9 +46,15 @@ struct alignas(16) TriShade {  // object-space vertex normals and tangents + ori
 // bank, uniform loads) instead of being gathered from global memory by every thread.
 #define PTB_INLINE_ANALYTIC 8
 struct AnalyticDev {
-    int32_t type, id;           // OBJ_SPHERE / OBJ_PLANE, scene object id
+    int32_t type, id;           // OBJ_SPHERE / OBJ_PLANE, scene object id (bit 30 of `type`: Object::ghost, skipped by shadow rays)
     float inv_trans[12];
     float a[3], n[3], R2;
+};
+
+#define PTB_ANALYTIC_GHOST (1 << 30)
+struct FogDev {                 // Scene::fog_* (Geometry.h:1371-1377) + the ground level fogContribution reads (Raytracer.cpp:54)
+    float density, absorption, density_decay, absorption_decay, phase_aniso, ground;
+    int32_t type, phase_type;
 };
 
 struct SceneDev {
@@ -65,6 +71,10 @@ struct SceneDev {
     float envmap_intensity, lightPower, radiusLight;
     V3 centerLight;
     int32_t n_inline, n_extra;  // analytic objects held inline below / left in `objects` (flag FLAG_NOT_INLINE)
+    int32_t has_fog, has_ghost; // fog_density > 1e-8 (Raytracer.cpp:206) / any Object::ghost
+    const float* background;    // Scene::background (Geometry.h:1365), bgW*bgH*3 floats, or null
+    int32_t bgW, bgH;
+    FogDev fog;
     AnalyticDev analytic[PTB_INLINE_ANALYTIC];
 };
 
@@ -153,7 +163,7 @@ PTB_HD void analytic_closest(const SceneDev& sc, V3 o, V3 d, float& tmin, int32_
     for (int i = 0; i < sc.n_inline; i++) {
         const AnalyticDev& ob = sc.analytic[i];
         float t;
-        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && t < tmin) { tmin = t; best = ob.id; }
+        if (analytic_t(ob.type & 0xff, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && t < tmin) { tmin = t; best = ob.id; }
     }
     if (sc.n_extra > 0)
         for (int i = 0; i < sc.n_objects; i++) {
@@ -169,13 +179,14 @@ PTB_HD bool analytic_occluded(const SceneDev& sc, V3 o, V3 d, float dist_light) 
     const double lim = (double)dist_light * 0.999;
     for (int i = 0; i < sc.n_inline; i++) {
         const AnalyticDev& ob = sc.analytic[i];
+        if (ob.type & PTB_ANALYTIC_GHOST) continue;   // avoid_ghosts (Geometry.cpp:722)
         float t;
-        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (double)t < lim) return true;
+        if (analytic_t(ob.type & 0xff, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (double)t < lim) return true;
     }
     if (sc.n_extra > 0)
         for (int i = 0; i < sc.n_objects; i++) {
             const ObjectDev& ob = sc.objects[i];
-            if (ob.type == OBJ_MESH || !(ob.flags & FLAG_NOT_INLINE)) continue;
+            if (ob.type == OBJ_MESH || !(ob.flags & FLAG_NOT_INLINE) || (ob.flags & FLAG_GHOST)) continue;
             float t;
             if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (double)t < lim) return true;
         }
@@ -309,6 +320,7 @@ struct PoolDev {
     F4* sh_c;         // xyz = path weight * direct contribution
     F4* aov_n;        // first-hit shading normal (normalValue, Raytracer.cpp:254-257); null unless the denoiser-input mode renders
     F4* aov_kd;       // first-hit albedo mat.Kd (albedoValue)
+    uint32_t* root;   // branching renders (fog / ghost objects): the sample slot a contribution belongs to; null otherwise
 };
 
 struct FrameDev {     // per-render constants (Raytracer fields + prepare_render results)
@@ -361,7 +373,11 @@ PTB_HD bool shard_block_sends(int tile_id, int i, int j, int W, int H, int tile,
 PTB_HD uint64_t path_inc(const FrameDev& f, int path) {  // pcg32 stream increment of the path's (pixel,sample) stream
     return (((uint64_t)(uint32_t)(f.k0 + (path % f.spp_pass)) ^ ((uint64_t)f.seed << 32)) << 1) | 1ULL;
 }
-PTB_HD uint32_t pack_state(int depth, bool show_lights) { return (uint32_t)depth | (show_lights ? 0x10000u : 0u); }
+// path state word (weight.w): depth (low 16) | show_lights | showenvmap | has_had_subsurface_interaction | pcg32 stream kind
+// (0: the sample's own stream, 1: fog fork, 2: ghost fork; oracle/build_ref.py patch 7) | fog contribution awaiting its hit
+enum { ST_SHOW_LIGHTS = 0x10000u, ST_SHOW_ENV = 0x20000u, ST_HAD_SS = 0x40000u, ST_KIND_SHIFT = 19, ST_KIND_MASK = 3u << 19,
+       ST_FOG_PENDING = 1u << 21, ST_FOG_UNIFORM = 1u << 22 };
+PTB_HD uint32_t pack_state(int depth, bool show_lights) { return (uint32_t)depth | (show_lights ? ST_SHOW_LIGHTS : 0u) | ST_SHOW_ENV; }
 
 // ---- stage 1: camera samples --------------------------------------------------------------------------
 PTB_HD void raygen_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path) {
@@ -393,6 +409,7 @@ PTB_HD void raygen_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pa
     q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
     p.rng[path] = e.state;
     p.pixel[path] = pix;
+    if (p.root) p.root[path] = (uint32_t)path;
 }
 
 // ---- stage 2: closest hit in the wide BVH (the analytic objects were tested by the ray's producer) ----------------
@@ -582,6 +599,340 @@ PTB_HD void shadow_one(const SceneDev& sc, PoolDev& p, int entry, TraverseCounte
     F4 L = p.radiance[path];
     L.x += c.x; L.y += c.y; L.z += c.z;
     p.radiance[path] = L;
+}
+
+// ---- branching contributions: participating medium, ghost objects, background photograph ----------------------------
+// getColor's ring of `Contrib` (Raytracer.cpp:213-247) becomes a level-synchronous tree walk: every contribution lives in a
+// pool slot; a slot's continuation stays in the slot, a side branch (the in-scattered contribution of fogContribution, the
+// straight-through ray of a ghost object) takes a fresh slot and its own pcg32 (oracle/build_ref.py patch 7: seed = two
+// draws of a copy of the parent engine, stream = 1 fog / 2 ghost).  Radiance of every contribution is added to the sample
+// slot `root` it descends from.
+struct ChildOut {
+    bool want;
+    F4 o, d, w;        // ray origin (.w: fog: squared distance to the sampled light point, < 0 for a uniform direction), direction
+                       // (.w: fog: weight factor still to be divided by proba_dir), weight + state word
+    uint64_t rng;
+};
+struct BranchOut {
+    ShadeOut base;
+    ChildOut fog, ghost;
+    bool ghost_pending;   // the ghost child lives only if the shadow ray in base.sh_* turns out unoccluded (Raytracer.cpp:519-537)
+};
+
+PTB_HD uint64_t stream_inc(const FrameDev& f, uint32_t root, uint32_t state) {
+    const uint32_t kind = (state & ST_KIND_MASK) >> ST_KIND_SHIFT;
+    return kind == 0 ? path_inc(f, (int)root) : (((uint64_t)kind << 1) | 1ULL);
+}
+PTB_HD uint64_t pcg32_fork(const Pcg32& e, uint64_t tag) {   // returns the STATE of pcg32(seed, stream = tag); its inc is (tag << 1) | 1
+    Pcg32 t = e;
+    const uint64_t a = pcg32_next(t), b = pcg32_next(t);
+    return pcg32_seed((a << 32) | b, tag).state;
+}
+PTB_HD void radiance_add(PoolDev& p, uint32_t root, V3 c) {
+#if defined(__CUDA_ARCH__)
+    float* q = reinterpret_cast<float*>(p.radiance + root);
+    atomicAdd(q, c.x); atomicAdd(q + 1, c.y); atomicAdd(q + 2, c.z);
+#else
+    F4& L = p.radiance[root];
+    L.x += c.x; L.y += c.y; L.z += c.z;
+#endif
+}
+PTB_HD V3 background_at(const SceneDev& sc, const FrameDev& f, uint32_t pix) {   // Raytracer.cpp:261-265, 615-619
+    const int screenI = (int)(pix / (uint32_t)f.W), screenJ = (int)(pix % (uint32_t)f.W);
+    int i = (int)((float)screenI / (float)f.H * (float)sc.bgH), j = (int)((float)screenJ / (float)f.W * (float)sc.bgW);
+    i = i < 0 ? 0 : (i > sc.bgH - 1 ? sc.bgH - 1 : i);
+    j = j < 0 ? 0 : (j > sc.bgW - 1 ? sc.bgW - 1 : j);
+    const float* b = sc.background + ((size_t)i * sc.bgW + j) * 3;
+    return v3(b[0], b[1], b[2]);
+}
+PTB_HD float int_exponential(float y0, float ysol, float beta, float s, float uy) {   // Raytracer.cpp:20-38
+    if (fabsf(uy * beta) < 0.0001f) return expf(-beta * (y0 - ysol)) * s;
+    return (expf(-beta * (y0 - ysol)) - expf(-beta * (y0 + s * uy - ysol))) / (uy * beta);
+}
+// Raytracer::fogContribution (Raytracer.cpp:40-192) up to the visibility ray: draws the scattering distance and direction from
+// `e`, describes the in-scattered contribution in `ch` (its weight is completed by shade_branch_one once the ray's hit is known,
+// lines 146-187) and returns the transmittance T (`attenuationFactor`).  When fogContribution returns before setting
+// attenuationFactor (scatter point below the ground, line 110) the reference goes on with the previous call's value; here T.
+PTB_HD float fog_sample(const SceneDev& sc, V3 ro, V3 rd, V3 lightPos, float t, V3 w, uint32_t child_state, Pcg32& e, ChildOut& ch) {
+    const FogDev& fg = sc.fog;
+    const bool uniform_fog = fg.type == 0;
+    const float alpha = fg.absorption, sigmaT = fg.absorption_decay, ground = fg.ground;
+    const float int_ext = uniform_fog ? (float)((double)(alpha * t) * 0.05) : alpha * int_exponential(ro.y, ground, sigmaT, t, rd.y);
+    const float T = expf(-int_ext);
+    float proba_t, random_t;
+    const float clamped_t = fminf(1000.f, t);
+    const float a = dot(lightPos - ro, rd);
+    if (a > 0) {                                                          // equi-angular sampling, 71-84
+        const V3 projP = ro + a * rd;
+        const float D = sqrtf(norm2(lightPos - projP));
+        const float thetaA = -atan2f(a, D);
+        const float b = t - a;
+        const float thetaB = atan2f(b, D);
+        const float x = pcg32_uniform(e);
+        random_t = D * tanf((1 - x) * thetaA + x * thetaB);
+        proba_t = D / ((thetaB - thetaA) * (D * D + random_t * random_t));
+        random_t += a;
+    } else {                                                              // truncated exponential, 90-99
+        const float alpha2 = 5.f / clamped_t;
+        int guard = 0;
+        do { random_t = -logf(pcg32_uniform(e)) / alpha2; } while (random_t > clamped_t && ++guard < 64);
+        const float normalization = 1.f / alpha2 * (1.f - expf(-alpha2 * clamped_t));
+        proba_t = expf(-alpha2 * random_t) / normalization;
+    }
+    const float int_ext_p = uniform_fog ? (float)((double)(alpha * random_t) * 0.05) : alpha * int_exponential(ro.y, ground, sigmaT, random_t, rd.y);
+    const V3 P = ro + random_t * rd;
+    if (P.y < ground) return T;
+    const V3 axeOP = normalize(P - sc.centerLight);
+    V3 dir;
+    float d_light2 = -1.f;
+    if (pcg32_uniform(e) < 0.5f) {                                        // random_uniform_sphere<float>, Vector.h:604-615
+        const float r1 = pcg32_uniform(e), r2 = pcg32_uniform(e);
+        const float twopi = 2.f * PTB_PI_F, sq = sqrtf(r2 * (1 - r2));
+        float sn, cs;
+#if defined(__CUDA_ARCH__)
+        sincosf(twopi * r1, &sn, &cs);
+#else
+        sn = sinf(twopi * r1); cs = cosf(twopi * r1);
+#endif
+        dir = v3(2.f * cs * sq, 2.f * sn * sq, 1.f - 2.f * r2);
+    } else {
+        const float r1 = pcg32_uniform(e), r2 = pcg32_uniform(e);
+        const V3 xl = random_cos(axeOP, r1, r2) * sc.radiusLight + sc.centerLight;
+        dir = normalize(xl - P);
+        d_light2 = norm2(xl - P);
+    }
+    float phase;
+    const float k = fg.phase_aniso;
+    if (fg.phase_type == 1) phase = (float)((double)(1 - k * k) / (4. * PTB_PI_D * (double)(1 + k * dot(dir, -rd))));
+    else if (fg.phase_type == 2) { const float dd = dot(dir, rd); phase = (float)(3 / (16 * PTB_PI_D) * (double)(1 + dd * dd)); }
+    else phase = (float)(1. / (4. * PTB_PI_D));
+    const float ext = uniform_fog ? (float)((double)fg.density * 0.05) : fg.density * expf(-fg.density_decay * (P.y - ground));
+    if ((child_state & 0xffffu) == 0) return T;   // a depth-0 contribution is dropped at the top of the loop (Raytracer.cpp:240)
+    ch.want = true;
+    ch.o.x = P.x; ch.o.y = P.y; ch.o.z = P.z; ch.o.w = d_light2;
+    ch.d.x = dir.x; ch.d.y = dir.y; ch.d.z = dir.z; ch.d.w = phase * ext * expf(-int_ext_p) / proba_t;
+    ch.w.x = w.x; ch.w.y = w.y; ch.w.z = w.z;
+    ch.w.w = u2f((child_state & ~(uint32_t)ST_KIND_MASK) | (1u << ST_KIND_SHIFT) | ST_FOG_PENDING | ST_SHOW_ENV | (d_light2 < 0 ? ST_FOG_UNIFORM : 0u));
+    ch.rng = pcg32_fork(e, 1);
+    return T;
+}
+
+// One iteration of getColor's loop (Raytracer.cpp:227-660) for the contribution in slot `path`, with the fog, ghost and
+// background branches; the subsurface branch (318-406) is not built.
+template <bool MERL>
+PTB_HD void shade_branch_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path, BranchOut& out) {
+    out.base.cont = false; out.base.shadow = false; out.base.shadow_query = false;
+    out.fog.want = false; out.ghost.want = false; out.ghost_pending = false;
+    const F4 wq = p.weight[path];
+    uint32_t st = f2u(wq.w);
+    const int depth = (int)(st & 0xffffu);
+    if (depth == 0) return;                                          // 240; also a ghost child whose shadow ray was blocked
+    const F4 hq = p.hit[path];
+    const int32_t id = (int32_t)f2u(hq.w);
+    const F4 oq = p.ray_o[path], dq = p.ray_d[path];
+    const V3 ro = v3(oq.x, oq.y, oq.z), rd = v3(dq.x, dq.y, dq.z);
+    V3 w = v3(wq.x, wq.y, wq.z);
+    const uint32_t root = p.root[path], pix = p.pixel[path];
+    Hit hit; hit.t = hq.x; hit.b1 = hq.y; hit.b2 = hq.z; hit.prim = id;
+    Surface s;
+    bool have_surface = false;
+    if (st & ST_FOG_PENDING) {                                       // tail of fogContribution with the hit of L_ray, 146-187
+        const bool inter = id != PTB_HIT_MISS;
+        V3 interP = v3(0, 0, 0), interN = fast_normalize(v3(0, 1, 0));
+        int interobj = -1;
+        if (inter) { surface_from_hit(sc, ro, rd, hit, id, s); have_surface = true; interP = s.P; interN = s.N; interobj = s.object; }
+        if (!(st & ST_FOG_UNIFORM) && inter && (double)(hit.t * hit.t) < (double)oq.w * 0.99) return;   // V == 0
+        const float pdf_uniform = (float)(1. / (4. * PTB_PI_D));
+        const float J = dot(interN, -rd) / norm2(interP - ro);
+        float pdf_light = 0.f;
+        if (inter && interobj == 0) {
+            const V3 axeOP = normalize(ro - sc.centerLight);
+            pdf_light = (float)((double)dot(normalize(interP - sc.centerLight), axeOP) / (PTB_PI_D * (double)(sc.radiusLight * sc.radiusLight)) / (double)J);
+        }
+        const float proba_dir = 0.5f * pdf_uniform + (1 - 0.5f) * pdf_light;
+        w = w * (dq.w / proba_dir);
+        st &= ~(uint32_t)(ST_FOG_PENDING | ST_FOG_UNIFORM);
+        if (norm2(w) < 0.01f * 0.01f) return;                        // 241
+    }
+    if (depth == f.nb_bounces && sc.bgW > 0 && (id == PTB_HIT_MISS || id == hit_id_analytic(1))) {   // 260-268
+        radiance_add(p, root, w * background_at(sc, f, pix));
+        return;
+    }
+    if (id == PTB_HIT_MISS) return;                                  // 654-657 (with fog the reference abandons the whole sample here)
+    if (!have_surface) surface_from_hit(sc, ro, rd, hit, id, s);
+    const bool show_lights = (st & ST_SHOW_LIGHTS) != 0, show_envmap = (st & ST_SHOW_ENV) != 0;
+    const uint32_t hadSS = st & ST_HAD_SS, kind_bits = st & ST_KIND_MASK;
+    const bool has_fog = sc.has_fog != 0;
+    const float t = hit.t;
+    Pcg32 e; e.state = p.rng[path]; e.inc = stream_inc(f, root, st);
+    // state of a contribution pushed from here: same stream, same subsurface flag
+    const uint32_t st_next = (uint32_t)(depth - 1) | hadSS | kind_bits;
+    const uint32_t st_fogchild = (uint32_t)(depth - 1) | hadSS | (show_lights ? ST_SHOW_LIGHTS : 0u);
+    if (s.object == 1) {                                             // 275-301
+        float att = 1.f;
+        if (has_fog) att = fog_sample(sc, ro, rd, sc.centerLight, t, w, st_fogchild, e, out.fog);
+        if (show_envmap) radiance_add(p, root, ((w * att) * sc.envmap_intensity) * s.Ke);
+        return;
+    }
+    if (s.object == 0) {                                             // 303-316
+        float att = 1.f;
+        if (has_fog) att = fog_sample(sc, ro, rd, sc.centerLight, t, w, st_fogchild, e, out.fog);
+        const float lp = show_lights ? sc.lightPower : 0.f;
+        radiance_add(p, root, (w * att) * lp);
+        return;
+    }
+    const ObjectDev& ob = sc.objects[s.object];
+    const V3 N = s.N, P = s.P;
+    V3 no, nd, nw = w;
+    uint32_t nstate;
+    if (ob.flags & FLAG_MIRROR) {                                    // 413-436
+        nd = reflect(rd, N);
+        no = P + 0.001f * N;
+        if (has_fog) nw = w * fog_sample(sc, ro, rd, sc.centerLight, t, w, st_fogchild, e, out.fog);
+        nstate = st_next | (show_lights ? ST_SHOW_LIGHTS : 0u) | ST_SHOW_ENV;
+    } else if (s.transp) {                                           // 438-489
+        float n1 = 1.f, n2 = s.refr_index;
+        V3 Nt = N;
+        bool entering = true;
+        if (dot(rd, N) > 0) { n1 = s.refr_index; n2 = 1; Nt = -N; entering = false; }
+        const float c0 = dot(Nt, rd);
+        const float radical = 1.f - (n1 / n2) * (n1 / n2) * (1.f - c0 * c0);
+        if (radical > 0) {
+            const V3 refr = (n1 / n2) * (rd - dot(rd, Nt) * Nt) - Nt * sqrtf(radical);
+            const float r0 = (n1 - n2) / (n1 + n2);
+            const float R0 = r0 * r0;
+            float R;
+            if (entering) R = R0 + (1 - R0) * powf(1.f + dot(rd, N), 5.f);
+            else R = R0 + (1 - R0) * powf(1.f - dot(refr, N), 5.f);
+            const float u = pcg32_uniform(e);
+            if (u < R) { no = P + 0.001f * Nt; nd = reflect(rd, N); }
+            else { no = P - 0.001f * Nt; nd = refr; }
+        } else {
+            no = P + 0.001f * Nt; nd = reflect(rd, N);
+        }
+        if (has_fog) nw = w * fog_sample(sc, ro, rd, sc.centerLight, t, w, st_fogchild, e, out.fog);
+        nstate = st_next | (show_lights ? ST_SHOW_LIGHTS : 0u) | ST_SHOW_ENV;
+    } else {                                                         // opaque, 490-649
+        const bool ghost = (ob.flags & FLAG_GHOST) != 0;
+        const V3 axeOP = fast_normalize(P - sc.centerLight);
+        const float l1 = pcg32_uniform(e);
+        const float l2 = pcg32_uniform(e);
+        const V3 dirl = random_cos(axeOP, l1, l2);
+        const V3 xl = dirl * sc.radiusLight + sc.centerLight;
+        const V3 toL = xl - P;
+        const V3 wi = fast_normalize(toL);
+        const float d2 = norm2(toL);
+        bool shadowed = true, pending = false;                       // pending: only the BVH can tell
+        const V3 so = P + 0.01f * wi;
+        const float dist = sqrtf(d2) - 0.01f;
+        if (!(dot(N, wi) < 0)) {
+            out.base.shadow_query = true;
+            if (!analytic_occluded(sc, so, wi, dist)) { shadowed = false; pending = sc.has_mesh != 0; }
+        }
+        V3 direct = v3(0, 0, 0);
+        if (!shadowed) {
+            if (ghost) {                                             // 522-537: straight through the ghost, same depth, same flags
+                const V3 offset = dot(N, rd) > 0 ? N : -N;
+                const V3 go = P + rd * 0.001f + offset * 0.001f;
+                out.ghost.want = true;
+                out.ghost.o.x = go.x; out.ghost.o.y = go.y; out.ghost.o.z = go.z; out.ghost.o.w = 0;
+                out.ghost.d.x = rd.x; out.ghost.d.y = rd.y; out.ghost.d.z = rd.z; out.ghost.d.w = 0;
+                out.ghost.w.x = w.x; out.ghost.w.y = w.y; out.ghost.w.z = w.z;
+                out.ghost.w.w = u2f((uint32_t)depth | hadSS | (show_lights ? ST_SHOW_LIGHTS : 0u) | (show_envmap ? ST_SHOW_ENV : 0u) | (2u << ST_KIND_SHIFT));
+                out.ghost.rng = pcg32_fork(e, 2);
+                out.ghost_pending = pending;
+            } else {
+                V3 fr;
+                if (MERL && ob.brdf == 1) fr = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, wi, -rd, N);
+                else fr = phong_eval(s.Kd, s.Ks, s.Ne, wi, -rd, N);
+                const float J = dot(dirl, -wi) / d2;
+#if defined(__CUDA_ARCH__)
+                const float proba = dot(axeOP, dirl) / (PTB_PI_F * (sc.radiusLight * sc.radiusLight));
+#else
+                const float proba = (float)((double)dot(axeOP, dirl) / (PTB_PI_D * (double)(sc.radiusLight * sc.radiusLight)));
+#endif
+                if (proba > 0.f) direct = (sc.lightPower * fmaxf(0.f, dot(N, wi)) * J / proba) * fr;
+            }
+        }
+        float att = 1.f;
+        // (with a ghost hit the reference hands fogContribution the straight-through ray, i.e. samples the medium BEHIND the
+        //  surface over the distance in front of it, Raytracer.cpp:529, 556; the incoming ray is used here)
+        if (has_fog) att = fog_sample(sc, ro, rd, xl, t, w, st_fogchild, e, out.fog);
+        const V3 c = (w * att) * direct;
+        if (!shadowed && !ghost) {
+            if (pending) {
+                out.base.shadow = true;
+                out.base.sh_o.x = so.x; out.base.sh_o.y = so.y; out.base.sh_o.z = so.z; out.base.sh_o.w = (float)((double)dist * 0.999);
+                out.base.sh_d.x = wi.x; out.base.sh_d.y = wi.y; out.base.sh_d.z = wi.z; out.base.sh_d.w = u2f(root);
+                out.base.sh_c.x = c.x; out.base.sh_c.y = c.y; out.base.sh_c.z = c.z; out.base.sh_c.w = u2f(0u);
+            } else radiance_add(p, root, c);
+        } else if (ghost && out.ghost_pending) {                     // the shadow ray decides the ghost child's fate and showenvmap below
+            out.base.shadow = true;
+            out.base.sh_o.x = so.x; out.base.sh_o.y = so.y; out.base.sh_o.z = so.z; out.base.sh_o.w = (float)((double)dist * 0.999);
+            out.base.sh_d.x = wi.x; out.base.sh_d.y = wi.y; out.base.sh_d.z = wi.z; out.base.sh_d.w = u2f((uint32_t)path);
+            out.base.sh_c.x = 0; out.base.sh_c.y = 0; out.base.sh_c.z = 0; out.base.sh_c.w = u2f(0x80000000u);   // | child slot, set by the kernel
+        }
+        // -- continuation (570-632)
+        float sx, sy;
+        extensible_lattice_2d((uint32_t)(f.k0 + ((int)root % f.spp_pass)), sx, sy);
+        const float r1 = frac_pos(f.rpp[2 * pix] + sx);
+        const float r2 = frac_pos(f.rpp[2 * pix + 1] + sy);
+        float pdf;
+        V3 dir;
+        bool diffuse = false;
+        if (MERL && ob.brdf == 1) {
+            dir = random_cos(N, r1, r2);
+            pdf = (float)((double)dot(N, dir) / PTB_PI_D);
+        } else {
+            const float u = pcg32_uniform(e);
+            dir = phong_sample(s.Ks, s.Ne, -rd, N, r1, r2, u, pdf, diffuse);
+        }
+        if (dot(dir, N) < 0 || dot(dir, reflect(rd, N)) < 0 || pdf <= 0) return;
+        V3 fi;
+        if (MERL && ob.brdf == 1) fi = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, dir, -rd, N);
+        else fi = phong_eval(s.Kd, s.Ks, s.Ne, dir, -rd, N);
+        nw = (w * fi) * (dot(N, dir) / pdf);
+        if (ghost && sc.bgW > 0) nw = nw * (background_at(sc, f, pix) / 196964.699f);   // 614-621
+        if (has_fog) nw = att * nw;
+        no = P + 0.01f * dir;
+        nd = dir;
+        // showenvmap of the continuation (626, 629): a ghost passes the dome on only below a blocked shadow ray; when the BVH
+        // still has to answer, "blocked" is assumed here and the any-hit kernel clears the bit for an unoccluded ray
+        const bool nenv = !ghost || (show_envmap && diffuse && (shadowed || pending));
+        nstate = st_next | (nenv ? ST_SHOW_ENV : 0u);
+    }
+    p.rng[path] = e.state;
+    if (depth - 1 == 0 || norm2(nw) < 0.01f * 0.01f) return;         // 240-241 of the next iteration
+    F4 q;
+    q.x = no.x; q.y = no.y; q.z = no.z; q.w = 0; p.ray_o[path] = q;
+    q.x = nd.x; q.y = nd.y; q.z = nd.z; q.w = 0; p.ray_d[path] = q;
+    q.x = nw.x; q.y = nw.y; q.z = nw.z; q.w = u2f(nstate); p.weight[path] = q;
+    float ta; int32_t ida;
+    analytic_closest(sc, no, nd, ta, ida);
+    q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
+    out.base.cont = true;
+}
+// Store a side branch in pool slot `slot` (the kernel / host loop allocated it) and give its ray the analytic hit record.
+PTB_HD void store_child(const SceneDev& sc, PoolDev& p, uint32_t slot, const ChildOut& ch, uint32_t root, uint32_t pix) {
+    p.ray_o[slot] = ch.o; p.ray_d[slot] = ch.d; p.weight[slot] = ch.w;
+    p.rng[slot] = ch.rng; p.pixel[slot] = pix; p.root[slot] = root;
+    float ta; int32_t ida;
+    analytic_closest(sc, v3(ch.o.x, ch.o.y, ch.o.z), v3(ch.d.x, ch.d.y, ch.d.z), ta, ida);
+    F4 q; q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida);
+    p.hit[slot] = q;
+}
+// What the any-hit pass does with a finished shadow ray of a branching render: deliver the deferred direct term to the sample
+// slot, or settle a ghost hit (Raytracer.cpp:519-537, 626-629): blocked -> the straight-through child dies; clear -> the
+// continuation must not show the dome.
+PTB_HD void shadow_settle_branch(PoolDev& p, int entry, uint32_t item, bool occluded) {
+    const F4 c = p.sh_c[entry];
+    const uint32_t tag = f2u(c.w);
+    if (tag & 0x80000000u) {
+        if (occluded) {
+            const uint32_t child = tag & 0x7fffffffu;
+            if (child != 0x7fffffffu) reinterpret_cast<uint32_t*>(p.weight + child)[3] &= ~0xffffu;
+        } else reinterpret_cast<uint32_t*>(p.weight + item)[3] &= ~(uint32_t)ST_SHOW_ENV;
+    } else if (!occluded) radiance_add(p, item, v3(c.x, c.y, c.z));
 }
 
 // ---- stage 5: Gaussian splat of a pixel's samples of this pass (Raytracer.cpp:1604-1659) --------------------------

@@ -143,7 +143,11 @@ int HostScene::set_group_material(int obj, int group, const ptb_material* m, std
     HostObject& o = objects[obj];
     if ((int)o.groups.size() <= group) o.groups.resize(group + 1);
     HostMaterial& g = o.groups[group];
-    g.present |= m->present;
+    if ((m->present & PTB_SLOT_KSUB) && (m->Ksub.texels || m->Ksub.mult[0] * m->Ksub.mult[0] + m->Ksub.mult[1] * m->Ksub.mult[1] + m->Ksub.mult[2] * m->Ksub.mult[2] > 1E-8f)) {
+        err = "set_group_material: subsurface scattering (Ksub != 0, Raytracer.cpp:318-406) is not built";   // a zero Ksub is the reference default
+        return PTB_ERR_UNSUPPORTED;
+    }
+    g.present |= m->present & ~(uint32_t)PTB_SLOT_KSUB;
     if (m->present & PTB_SLOT_KD) take_tex(g.Kd, m->Kd);
     if (m->present & PTB_SLOT_KS) take_tex(g.Ks, m->Ks);
     if (m->present & PTB_SLOT_NE) take_tex(g.Ne, m->Ne);
@@ -277,6 +281,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
                 const HostTex& a = o.groups[group].alpha;
                 if (a.W > 0 || a.mult[0] < 0.5f) flags |= PTB_TRI_FLAG_ALPHA;  // a constant >= 0.5 can never reject
             }
+            if (o.flags & FLAG_GHOST) flags |= PTB_TRI_FLAG_GHOST;
             F4 q;
             q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = u2f(flags); out.tris[3 * (size_t)k] = q;
             q.x = v[3] - v[0]; q.y = v[4] - v[1]; q.z = v[5] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 1] = q;

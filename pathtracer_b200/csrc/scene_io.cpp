@@ -910,17 +910,15 @@ int ptb_load_scene(ptb_ctx* ctx, const char* path, const char* replaced_names, p
     int rc = parse_scn(path, replaced_names, sc);
     if (rc) return rc;
     const ptb_scn_header& h = sc.h;
-    if (h.fog_density > 1e-8f) return fail(PTB_ERR_UNSUPPORTED, "load_scene: participating media (fog_density > 0) are not rendered");
-    if (h.background[0]) return fail(PTB_ERR_UNSUPPORTED, "load_scene: background photographs are not rendered");
     if (h.is_lenticular) return fail(PTB_ERR_UNSUPPORTED, "load_scene: lenticular cameras are not rendered");
     if (sc.objects.size() < 2 || sc.objects[0].o.type != PTB_SCN_SPHERE) return fail(PTB_ERR_INVALID, "load_scene: object 0 must be the light sphere");
     for (size_t i = 0; i < sc.objects.size(); i++) {
         const ScnObject& so = sc.objects[i];
         const ptb_scn_object& o = so.o;
-        if (o.ghost) return fail(PTB_ERR_UNSUPPORTED, "load_scene: ghost objects are not rendered");
         for (const Slot& sl : so.slots[PTB_KIND_SUBSURF])
             if (!sl.file.empty() || sl.mult[0] * sl.mult[0] + sl.mult[1] * sl.mult[1] + sl.mult[2] * sl.mult[2] > 1e-8f) return fail(PTB_ERR_UNSUPPORTED, "load_scene: subsurface scattering is not rendered");
-        int flags = (o.miroir ? PTB_OBJ_MIRROR : 0) | (o.flip_normals ? PTB_OBJ_FLIP_NORMALS : 0) | (o.interp_normals ? 0 : PTB_OBJ_FLAT_NORMALS);
+        int flags = (o.miroir ? PTB_OBJ_MIRROR : 0) | (o.flip_normals ? PTB_OBJ_FLIP_NORMALS : 0) | (o.interp_normals ? 0 : PTB_OBJ_FLAT_NORMALS) |
+                    (o.ghost ? PTB_OBJ_GHOST : 0);
         int id = -1;
         if (o.type == PTB_SCN_SPHERE) {
             rc = ptb_add_sphere(ctx, o.O, o.R, &o.xform, flags, &id);
@@ -967,6 +965,17 @@ int ptb_load_scene(ptb_ctx* ctx, const char* path, const char* replaced_names, p
         }
     }
     if ((rc = ptb_set_light(ctx, h.intensite_lumiere, h.envmap_intensity))) return rc;
+    {   // Scene::fog_* as Raytracer::load_scene reads them (Raytracer.cpp:1216-1231); phase_aniso is not stored in .scn files
+        ptb_fog fog = {h.fog_density, h.fog_absorption, h.fog_density_decay, h.fog_absorption_decay, h.fog_type, h.fog_phase_type, 0.f};
+        if ((rc = ptb_set_fog(ctx, &fog))) return fail(rc, std::string("load_scene: ") + ptb_last_error(ctx));
+    }
+    if (h.background[0]) {   // Scene::load_background(bg, gamma) (Raytracer.cpp:1208-1209, Geometry.h:1355-1363)
+        Image im;
+        if ((rc = load_image_flipped(find_file(sc, h.background).c_str(), im))) return rc;
+        std::vector<float> bg(im.rgb.size());
+        for (size_t i = 0; i < bg.size(); i++) bg[i] = (float)(std::pow(im.rgb[i] / 255., (double)h.gamma) * 196964.699);
+        if ((rc = ptb_set_background(ctx, bg.data(), im.W, im.H))) return rc;
+    } else ptb_set_background(ctx, nullptr, 0, 0);
     if (cam) *cam = h.cam;
     if (params) {
         memset(params, 0, sizeof *params);

@@ -71,7 +71,7 @@ enum ObjectType { OT_TRIMESH, OT_SPHERE, OT_PLANE };
 
 struct Object {                  // Geometry.h:240-672
     ObjectType type;
-    bool miroir = false, flip_normals = false, interp_normals = true;
+    bool miroir = false, flip_normals = false, interp_normals = true, ghost = false;
     float scale = 1.f;
     float mat_rotation[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     Vector rotation_center{NAN, NAN, NAN};   // NaN: the object's own default
@@ -103,6 +103,9 @@ struct TriMesh : Object {        // arrays as a reader fills them (TriangleMesh.
 struct Scene {                   // Geometry.h:1238-1400
     std::vector<std::shared_ptr<Object>> objects;
     float intensite_lumiere = 0.f, envmap_intensity = 1.f;
+    float fog_density = 0.f, fog_absorption = 0.f, fog_density_decay = 0.f, fog_absorption_decay = 0.f, phase_aniso = 0.f;   // Geometry.h:1371-1377
+    int fog_type = 0, fog_phase_type = 0;
+    std::vector<float> background; int backgroundW = 0, backgroundH = 0;                                                   // Geometry.h:1365-1366
     int addObject(std::shared_ptr<Object> o) { objects.push_back(std::move(o)); return (int)objects.size() - 1; }
 };
 
@@ -161,7 +164,7 @@ public:
             ptb_xform xf;
             xf.scale = o.scale; std::memcpy(xf.rotation, o.mat_rotation, sizeof(xf.rotation));
             for (int k = 0; k < 3; k++) { xf.rotation_center[k] = o.rotation_center[k]; xf.translation[k] = o.max_translation[k]; }
-            const int flags = (o.miroir ? PTB_OBJ_MIRROR : 0) | (o.flip_normals ? PTB_OBJ_FLIP_NORMALS : 0) | (o.interp_normals ? 0 : PTB_OBJ_FLAT_NORMALS);
+            const int flags = (o.miroir ? PTB_OBJ_MIRROR : 0) | (o.flip_normals ? PTB_OBJ_FLIP_NORMALS : 0) | (o.interp_normals ? 0 : PTB_OBJ_FLAT_NORMALS) | (o.ghost ? PTB_OBJ_GHOST : 0);
             int id = -1;
             if (o.type == OT_SPHERE) { auto& sp = static_cast<Sphere&>(o); ck(ptb_add_sphere(ctx_, sp.O.v, sp.R, &xf, flags, &id)); }
             else if (o.type == OT_PLANE) { auto& pl = static_cast<Plane&>(o); ck(ptb_add_plane(ctx_, pl.A.v, pl.vecN.v, &xf, flags, &id)); }
@@ -197,6 +200,9 @@ public:
             if (dome.envW > 0) ck(ptb_set_envmap(ctx_, dome.envtex.data(), dome.envW, dome.envH));
         }
         ck(ptb_set_light(ctx_, s.intensite_lumiere, s.envmap_intensity));
+        const ptb_fog fog = {s.fog_density, s.fog_absorption, s.fog_density_decay, s.fog_absorption_decay, s.fog_type, s.fog_phase_type, s.phase_aniso};
+        ck(ptb_set_fog(ctx_, &fog));
+        ck(ptb_set_background(ctx_, s.backgroundW > 0 ? s.background.data() : nullptr, s.backgroundW, s.backgroundH));
         ck(ptb_commit(ctx_));
     }
 

@@ -171,4 +171,47 @@ def config_C5(lib, W=3840, H=2160, spp=1024, nv=866, device=0):
     return rt
 
 
+def photo_background(W=96, H=64):
+    """Closed-form stand-in for a background photograph, in Scene::background scale (pow(v/255, 2.2) * 196964.699,
+    Geometry.h:1355-1363): a two-colour gradient with a bright band."""
+    y = np.arange(H, dtype=np.float64)[:, None] / (H - 1)
+    x = np.arange(W, dtype=np.float64)[None, :] / (W - 1)
+    v = np.stack([60 + 150 * x * np.ones_like(y), 90 + 100 * y * np.ones_like(x), 200 - 120 * x * y], -1)
+    v = np.where((np.abs(y - 0.5) < 0.06)[..., None], 240.0, v)
+    return (np.power(np.floor(v) / 255., 2.2) * 196964.699).astype(np.float32)
+
+
+def config_ghost(lib, W=128, H=128, spp=16, nv=24, device=0, background=True, ghost_plane=True, ghost_mesh=False):
+    """Compositing set-up of the reference (Raytracer.cpp:260-268, 522-537, 614-621): the ground plane is a ghost that only
+    receives shadows, a background photograph shows through it and behind the scene; a Phong torus and a sphere cast the shadows."""
+    rt = base(lib, W, H, spp, device=device)
+    rt.s.objects[2].ghost = ghost_plane
+    rt.s.objects[2].set_material(0, **phong((.7, .7, .7), 0.0, 1.0))
+    m = _place_like_gui(TriMesh(*displaced_torus(nv)))
+    m.set_material(0, **phong((.5, .5, .5), (.2, .2, .2), 50.0))
+    m.ghost = ghost_mesh
+    rt.s.addObject(m)
+    rt.s.addObject(Sphere((-18, -20.3, 8), 7).set_material(0, **phong((.3, .8, .3), 0.3, 50.0)))
+    if background:
+        rt.s.background_values = photo_background()
+    return rt
+
+
+def config_fog(lib, W=128, H=128, spp=16, nv=24, device=0, fog_type=0, phase=0, mesh=True):
+    """Participating medium (Raytracer::fogContribution, Raytracer.cpp:40-192) over the C1/C2 content: uniform (type 0) or
+    height-exponential (type 1) fog with an isotropic / Schlick / Rayleigh phase function."""
+    rt = base(lib, W, H, spp, device=device)
+    rt.s.addObject(Sphere((0, -17.3, 0), 10).set_material(0, **phong((.8, .3, .3), 0.0, 1.0)))
+    rt.s.addObject(Sphere((-15, -20.3, 5), 7, mirror=True))
+    if mesh:
+        m = _place_like_gui(TriMesh(*displaced_torus(nv)), scale=20.0)
+        m.max_translation = m.max_translation + np.array([16, 0, 4], np.float32)
+        m.set_material(0, **phong((.5, .5, .5), (.2, .2, .2), 50.0))
+        rt.s.addObject(m)
+    s = rt.s
+    s.fog_density, s.fog_absorption, s.fog_density_decay, s.fog_absorption_decay = 0.3, 0.3, 0.05, 0.05
+    s.fog_type, s.fog_phase_type, s.phase_aniso = fog_type, phase, 0.4
+    return rt
+
+
 CONFIGS = {"C1": config_C1, "C2": config_C2, "C3": config_C3, "C4": config_C4, "C5": config_C5}

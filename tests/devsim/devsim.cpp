@@ -47,6 +47,13 @@ int ptb_set_brdf(ptb_ctx* c, int obj, int kind, int merl) { c->host.objects[obj]
 int ptb_add_merl(ptb_ctx* c, const double* t, int* id) { c->host.merl_tables.emplace_back(t, t + 3 * (size_t)PTB_MERL_N); if (id) *id = (int)c->host.merl_tables.size() - 1; return PTB_OK; }
 int ptb_set_envmap(ptb_ctx* c, const uint8_t* rgb, int W, int H) { c->host.envmap.assign(rgb, rgb + (size_t)W * H * 3); c->host.envW = W; c->host.envH = H; return PTB_OK; }
 int ptb_set_light(ptb_ctx* c, float a, float b) { c->host.intensite_lumiere = a; c->host.envmap_intensity = b; return PTB_OK; }
+int ptb_set_fog(ptb_ctx* c, const ptb_fog* f) { c->host.fog = *f; return PTB_OK; }
+int ptb_set_background(ptb_ctx* c, const float* rgb, int W, int H) {
+    c->host.background.clear(); c->host.bgW = c->host.bgH = 0;
+    if (!rgb || W <= 0 || H <= 0) return PTB_OK;
+    c->host.background.assign(rgb, rgb + (size_t)W * H * 3); c->host.bgW = W; c->host.bgH = H;
+    return PTB_OK;
+}
 int ptb_commit(ptb_ctx* c) {
     int rc = c->host.flatten(c->flat, c->err);
     if (rc) return rc;
@@ -54,6 +61,8 @@ int ptb_commit(ptb_ctx* c) {
     sc.nodes = reinterpret_cast<const F4*>(f.nodes.data()); sc.tris = f.tris.data(); sc.tri_uv = f.tri_uv.data(); sc.tri_shade = f.tri_shade.data();
     sc.objects = f.objects.data(); sc.materials = f.materials.data(); sc.texels = f.texels.data(); sc.envmap = f.envmap.data(); sc.merl = f.merl.data();
     scene_header(sc, f);
+    if ((rc = scene_modes(sc, c->host, c->err))) return rc;
+    sc.background = c->host.background.data();
     c->committed = true;
     return PTB_OK;
 }
@@ -77,18 +86,69 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     f.spp_pass = p->nrays; f.k0 = x.k_first; f.slot0 = 0; f.n_pixel_slots = f.n_my_tiles * f.tile * f.tile;
     f.box_filter = x.box ? 1 : 0; f.accum_albedo = x.albedo; f.accum_normal = x.normal;
     f.lowres = x.lowres; f.lowresW = (int)ceilf(p->W / 16.f); f.lowresH = (int)ceilf(p->H / 16.f);
-    const size_t P = (size_t)f.n_pixel_slots * f.spp_pass;
+    const bool branch = c->sc.has_fog || c->sc.has_ghost || c->sc.bgW > 0;
+    const size_t n_roots = (size_t)f.n_pixel_slots * f.spp_pass;
+    const size_t P = n_roots * (branch ? (c->sc.has_fog ? ((size_t)1 << std::min(f.nb_bounces, 6)) : 8) : 1);
+    std::vector<uint32_t> root(branch ? P : 0);
     std::vector<F4> ray_o(P), ray_d(P), weight(P), radiance(P), hit(P), sh_o(P), sh_d(P), sh_c(P);
     std::vector<uint64_t> rng(P); std::vector<uint32_t> pixel(P), q0, q1;
     std::vector<F4> aov_n(x.albedo ? P : 0), aov_kd(x.albedo ? P : 0);
     PoolDev pool{ray_o.data(), ray_d.data(), weight.data(), radiance.data(), hit.data(), rng.data(), pixel.data(), sh_o.data(), sh_d.data(), sh_c.data(),
-                 x.albedo ? aov_n.data() : nullptr, x.albedo ? aov_kd.data() : nullptr};
+                 x.albedo ? aov_n.data() : nullptr, x.albedo ? aov_kd.data() : nullptr, branch ? root.data() : nullptr};
     unsigned long long closest = 0, shadow = 0, nodes = 0, tris = 0, samples = 0;
 #pragma omp parallel for schedule(static)
-    for (long long i = 0; i < (long long)P; i++) raygen_one(c->sc, f, pool, (int)i);
-    for (size_t i = 0; i < P; i++) if (pixel[i] != 0xffffffffu) { q0.push_back((uint32_t)i); }
+    for (long long i = 0; i < (long long)n_roots; i++) raygen_one(c->sc, f, pool, (int)i);
+    for (size_t i = 0; i < n_roots; i++) if (pixel[i] != 0xffffffffu) { q0.push_back((uint32_t)i); }
     samples = q0.size();
-    for (int b = 0; b < f.nb_bounces; b++) {
+    if (branch) {   // the level loop of render_passes' branching mode, single-threaded
+        size_t next_slot = n_roots;
+        for (int b = 0; b < 512 && !q0.empty() && f.nb_bounces > 0; b++) {   // PTB_BRANCH_MAX_LEVELS
+            closest += q0.size();
+            q1.clear();
+            size_t ns = 0;
+            for (size_t i = 0; i < q0.size(); i++) {
+                const int path = (int)q0[i];
+                TraverseCounters tc{0, 0};
+                if (c->sc.has_mesh) extend_one<true>(c->sc, pool, path, &tc);
+                nodes += tc.nodes; tris += tc.tris;
+            }
+            for (size_t i = 0; i < q0.size(); i++) {
+                const int path = (int)q0[i];
+                BranchOut out;
+                if (getenv("PTB_DBG") && (f2u(weight[path].w) & 0xffffu)) {
+                    const int32_t hid = (int32_t)f2u(hit[path].w);
+                    fprintf(stderr, "P %u %u %d %.4f\n", pixel[path], f2u(weight[path].w) & 0xffffu, hid >= 0 ? (c->sc.tri_uv[hid].object_has_uv & 0x7fffffff) : (hid == -1 ? -1 : -2 - hid), hid == -1 ? 0.f : hit[path].x);
+                }
+                shade_branch_one<true>(c->sc, f, pool, path, out);
+                uint32_t ghost_slot = 0x7fffffffu;
+                for (int k = 0; k < 2; k++) {
+                    const ChildOut& ch = k == 0 ? out.fog : out.ghost;
+                    if (!ch.want) continue;
+                    if (next_slot >= P) { c->err = "devsim: branching pool exhausted"; return PTB_ERR_NOMEM; }
+                    store_child(c->sc, pool, (uint32_t)next_slot, ch, root[path], pixel[path]);
+                    if (k == 1) ghost_slot = (uint32_t)next_slot;
+                    q1.push_back((uint32_t)next_slot++);
+                }
+                if (out.base.cont) q1.push_back((uint32_t)path);
+                if (out.base.shadow) {
+                    F4 cc = out.base.sh_c;
+                    if (out.ghost_pending) cc.w = u2f(0x80000000u | ghost_slot);
+                    sh_o[ns] = out.base.sh_o; sh_d[ns] = out.base.sh_d; sh_c[ns] = cc; ns++;
+                }
+                if (out.base.shadow_query) shadow++;
+            }
+            for (size_t i = 0; i < ns; i++) {
+                TraverseCounters tc{0, 0};
+                const AlphaCtx ac = alpha_ctx(c->sc);
+                Hit h;
+                const bool occ = traverse<true, true>(c->sc.nodes, c->sc.tris, &ac, v3(sh_o[i].x, sh_o[i].y, sh_o[i].z), v3(sh_d[i].x, sh_d[i].y, sh_d[i].z), sh_o[i].w, h, &tc);
+                shadow_settle_branch(pool, (int)i, f2u(sh_d[i].w), occ);
+                nodes += tc.nodes; tris += tc.tris;
+            }
+            q0.swap(q1);
+        }
+    }
+    for (int b = 0; b < f.nb_bounces && !branch; b++) {
         closest += q0.size();
         const long long n = (long long)q0.size();
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, tris)

@@ -9,7 +9,8 @@ The fixtures pin oracle/port (and through it the CUDA path) to outputs of the re
                  the .scn fixtures loaded by its own load_scene (ids, image, ray counters)
   modes.npz      the reference's progressive renderer (Raytracer::render_image: sums, weights, display image, low-resolution preview,
                  after all passes and after a stop at 2) and its has_denoiser accumulation (means, albedo, normalImage)
-  scene_<n>.npz  for five miniature versions of the BASELINE.json configurations: primary-hit object /
+  scene_<n>.npz  for five miniature versions of the BASELINE.json configurations and for the branching modes of getColor
+                 (background photograph, ghost objects, fog: golden_scenes.BRANCH_SCENES): primary-hit object /
                  triangle ids and t (the picking query), the linear image (imagedouble), sample_count,
                  the 8-bit image and the ray counters of a single-thread render
 Run:  python tests/golden/make_golden.py        (rewrites the .npz files; they are committed)
@@ -26,7 +27,7 @@ import ctypes as C  # noqa: E402
 import json  # noqa: E402
 
 import sceneio_cases as sio  # noqa: E402
-from golden_scenes import KAT_INPUTS, SCENES  # noqa: E402
+from golden_scenes import BRANCH_SCENES, KAT_INPUTS, SCENES  # noqa: E402
 from oracles import ref_lib  # noqa: E402
 
 from pathtracer_b200 import _abi, scenes  # noqa: E402
@@ -100,15 +101,17 @@ def main():
     assert R is not None, "oracle/_ref is not built (needs /root/reference)"
     sceneio_golden(R)
     modes_golden(R)
-    if "--new-only" in sys.argv:
-        return
-    rt = scenes.config_C4(R, 32, 32, 1, nv=10).commit()   # any committed scene with a MERL table
-    out = {}
-    for which, (inp, kw) in KAT_INPUTS().items():
-        out[f"in_{which}"] = inp
-        out[f"out_{which}"] = rt.kat(which, inp, **kw)
-    np.savez_compressed(os.path.join(HERE, "kat.npz"), **out)
-    for name, mk in SCENES.items():
+    todo = dict(BRANCH_SCENES)
+    if "--new-only" not in sys.argv:
+        todo.update(SCENES)
+    if "--new-only" not in sys.argv:
+        rt = scenes.config_C4(R, 32, 32, 1, nv=10).commit()   # any committed scene with a MERL table
+        out = {}
+        for which, (inp, kw) in KAT_INPUTS().items():
+            out[f"in_{which}"] = inp
+            out[f"out_{which}"] = rt.kat(which, inp, **kw)
+        np.savez_compressed(os.path.join(HERE, "kat.npz"), **out)
+    for name, mk in todo.items():
         rt = mk(R).commit()
         rt.set_option(_abi.ORC_OPT_THREADS, 1)
         obj, tri, t = rt.primary_ids()

@@ -11,6 +11,17 @@ SCENES = {
     "C5": lambda L, **kw: scenes.config_C5(L, 64, 40, 1, nv=12, **kw),
 }
 
+# getColor's branching modes: background photograph, ghost objects, participating medium
+BRANCH_SCENES = {
+    "BG": lambda L, **kw: scenes.config_ghost(L, 48, 48, 2, ghost_plane=False, **kw),
+    "GHOST": lambda L, **kw: scenes.config_ghost(L, 48, 48, 2, **kw),
+    "GHOSTMESH": lambda L, **kw: scenes.config_ghost(L, 48, 48, 2, ghost_mesh=True, **kw),
+    "GHOSTNOBG": lambda L, **kw: scenes.config_ghost(L, 48, 48, 2, background=False, **kw),
+    "FOG_U0": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=0, phase=0, **kw),
+    "FOG_U1": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=0, phase=1, mesh=False, **kw),
+    "FOG_E1": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=1, phase=1, **kw),
+    "FOG_E2": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=1, phase=2, **kw),
+}
 
 def _unit(rng, n):
     v = rng.normal(size=(n, 3))

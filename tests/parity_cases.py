@@ -64,6 +64,82 @@ def case_scene(test_lib, oracle_lib, mk, nrays=None, frac=FRAC_1SPP):
     a.close(); b.close()
 
 
+def case_branch_scene(test_lib, oracle_lib, mk, frac=FRAC_1SPP, gold=None):
+    """getColor's branching modes (fog, ghost objects, background photograph).  Same per-contribution pcg32 streams on both
+    sides (oracle/build_ref.py patch 7), so the images are compared at equal seed like the linear scenes.  Ray counters are
+    NOT equal by construction: the reference traces the in-scattering ray of fogContribution twice (once for its visibility,
+    once when the contribution is popped) where the wavefront traces it once, and a ghost's straight-through ray is traced
+    before its shadow ray can cancel it; they are only bracketed."""
+    a, b = mk(oracle_lib).commit(), mk(test_lib).commit()
+    check_ids(b, a, agree=0.998, need_mesh=any(hasattr(o, "tri") for o in a.s.objects))     # 2304 pixels of a coarse mesh: a few silhouette pixels may flip (99.99 % is checked at 512x512)
+    ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+    check_images(ib, ia, frac)
+    if gold is not None:
+        check_images(ib, gold["imagedouble"], max(frac, 0.01))
+    assert np.allclose(a.sample_count, b.sample_count, rtol=1e-5)
+    assert b.stats["samples"] == a.stats["samples"]
+    assert abs(a.stats["rays_shadow"] - b.stats["rays_shadow"]) <= 0.01 * a.stats["rays_shadow"] + 8
+    assert 0.5 * a.stats["rays_closest"] <= b.stats["rays_closest"] <= 1.2 * a.stats["rays_closest"]
+    assert np.mean(np.abs(a.image.astype(int) - b.image.astype(int)) > 1) <= 2 * frac
+    a.close(); b.close()
+
+
+def case_branch_converged(test_lib, oracle_lib):
+    """Fog at equal spp against a high-spp oracle image (the converged-image bound of the north star).  The medium is a
+    high-variance estimator (relRMSE of a 16-spp image is > 1), so the bound is stated at equal seed like case_converged."""
+    mk = lambda L: scenes.config_fog(L, 32, 32, 16, fog_type=1, phase=1)
+    hi = mk(oracle_lib).commit()
+    hi.nrays, hi.seed = 768, 99
+    ref_hi = hi.render_image_nopreviz().copy()
+    a, b = mk(oracle_lib).commit(), mk(test_lib).commit()
+    ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+    ea, eb = rrmse(ia, ref_hi), rrmse(ib, ref_hi)
+    assert eb <= RRMSE_FACTOR * ea + 0.005, (ea, eb)
+    assert rrmse(ib, ia) <= 0.02, "equal-seed images should be nearly the same image"
+
+
+def case_branch_passes(test_lib):
+    """Splitting a branching render into passes (small contribution pool) must not change the image; an exhausted pool is an error."""
+    mk = lambda: scenes.config_fog(test_lib, 40, 24, 3, fog_type=0, phase=2).commit()
+    whole, small = mk(), mk()
+    ref = whole.render_image_nopreviz().copy()
+    small.set_option(_abi.OPT_POOL_PATHS, 40 * 24 * 32)   # 32 slots per sample at depth 5: one sample per pass
+    img = small.render_image_nopreviz()
+    assert np.allclose(img, ref, rtol=2e-5, atol=1e-3)
+    assert small.stats["rays_closest"] == whole.stats["rays_closest"]
+    g = scenes.config_ghost(test_lib, 40, 24, 3).commit()
+    gi = g.render_image_nopreviz().copy()
+    g.set_option(_abi.OPT_POOL_PATHS, 1024)
+    assert np.allclose(g.render_image_nopreviz(), gi, rtol=2e-5, atol=1e-3)
+
+
+def case_branch_errors(test_lib):
+    rt = scenes.config_C1(test_lib, 8, 8, 1)
+    rt.s.objects[3].set_material(0, Ksub=Texture((.5, .4, .3)))
+    try:
+        rt.commit(); raised = False
+    except _abi.PtbError:
+        raised = True
+    assert raised, "subsurface scattering is refused, not approximated"
+    rt = scenes.config_C1(test_lib, 8, 8, 1)
+    rt.s.objects[3].set_material(0, Ksub=Texture((0, 0, 0)))     # the reference default: accepted
+    rt.commit(); rt.close()
+    rt = scenes.base(test_lib, 8, 8, 1)
+    rt.s.objects.pop()                                            # no object 2: the medium has no ground level
+    rt.s.fog_density = 0.2
+    try:
+        rt.commit(); raised = False
+    except _abi.PtbError:
+        raised = True
+    assert raised
+    rt = scenes.config_fog(test_lib, 16, 16, 1).commit()
+    try:
+        rt.render_denoiser_inputs(); raised = False
+    except _abi.PtbError:
+        raised = True
+    assert raised, "the denoiser-input mode is not combined with the branching modes"
+
+
 def case_converged(test_lib, oracle_lib):
     mk = lambda L: scenes.config_C2(L, 40, 40, 8, nv=24, env=(128, 64))
     hi = mk(oracle_lib).commit()

@@ -5,8 +5,8 @@ import os
 
 import numpy as np
 import pytest
-from golden_scenes import SCENES
-from parity_cases import (EDGE_VARIANTS, case_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
+from golden_scenes import BRANCH_SCENES, SCENES
+from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
                           case_progressive, case_scene, check_ids)
 
 from pathtracer_b200 import _abi, scenes
@@ -38,6 +38,15 @@ def test_denoiser_inputs_devsim(devsim, port):
 
 def test_converged_devsim(devsim, port):
     case_converged(devsim, port)
+
+
+@pytest.mark.parametrize("name", sorted(BRANCH_SCENES))
+def test_branch_scenes_devsim_vs_oracle(devsim, port, name):
+    case_branch_scene(devsim, port, BRANCH_SCENES[name])
+
+
+def test_branch_converged_devsim(devsim, port):
+    case_branch_converged(devsim, port)
 
 
 def test_bvh8_against_oracle_on_a_larger_mesh(devsim, port):

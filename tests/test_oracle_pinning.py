@@ -6,7 +6,9 @@ import os
 
 import numpy as np
 import pytest
-from golden_scenes import KAT_INPUTS, SCENES
+from golden_scenes import BRANCH_SCENES, KAT_INPUTS, SCENES
+
+ALL_SCENES = {**SCENES, **BRANCH_SCENES}
 
 from pathtracer_b200 import _abi, scenes
 
@@ -47,10 +49,10 @@ def test_kat_golden_bit_exact(port_rt):
         assert np.array_equal(got, gold[f"out_{which}"]), f"KAT {which} differs from the reference's output"
 
 
-@pytest.mark.parametrize("name", sorted(SCENES))
+@pytest.mark.parametrize("name", sorted(ALL_SCENES))
 def test_scene_golden_bit_exact(port, name):
     gold = np.load(os.path.join(GOLD, f"scene_{name}.npz"))
-    rt = SCENES[name](port).commit()
+    rt = ALL_SCENES[name](port).commit()
     rt.set_option(_abi.ORC_OPT_THREADS, 1)
     obj, tri, t = rt.primary_ids()
     assert np.array_equal(obj, gold["obj"]) and np.array_equal(tri, gold["tri"]) and np.array_equal(t, gold["t"])
@@ -60,9 +62,9 @@ def test_scene_golden_bit_exact(port, name):
     assert [rt.stats["rays_closest"], rt.stats["rays_shadow"]] == gold["rays"].tolist()
 
 
-@pytest.mark.parametrize("name", sorted(SCENES))
+@pytest.mark.parametrize("name", sorted(ALL_SCENES))
 def test_port_equals_compiled_reference(port, ref, name):
-    a, b = SCENES[name](ref).commit(), SCENES[name](port).commit()
+    a, b = ALL_SCENES[name](ref).commit(), ALL_SCENES[name](port).commit()
     for rt in (a, b):
         rt.set_option(_abi.ORC_OPT_THREADS, 1)
         rt.nrays, rt.seed = 3, 7          # a seed and spp the golden files do not cover

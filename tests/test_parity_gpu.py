@@ -8,8 +8,8 @@ import os
 
 import numpy as np
 import pytest
-from golden_scenes import SCENES
-from parity_cases import (EDGE_VARIANTS, case_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
+from golden_scenes import BRANCH_SCENES, SCENES
+from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
                           case_progressive, case_scene, check_ids, check_images)
 
 from pathtracer_b200 import _abi, scenes
@@ -48,6 +48,38 @@ def test_scenes_gpu_vs_golden_reference_images(gpu, name):
 
 def test_scenes_gpu_vs_compiled_reference(gpu, ref):
     case_scene(gpu, ref, lambda L: scenes.config_C3(L, 96, 96, 2, nv=40, tex=128))
+
+
+@pytest.mark.parametrize("name", sorted(BRANCH_SCENES))
+def test_branch_scenes_gpu_vs_oracle_and_golden(gpu, port, name):
+    """Fog, ghost objects, background photograph: the CUDA path against the oracle at equal seed and against the committed
+    output of the reference itself."""
+    case_branch_scene(gpu, port, BRANCH_SCENES[name], gold=np.load(os.path.join(GOLD, f"scene_{name}.npz")))
+
+
+def test_branch_converged_gpu(gpu, port):
+    case_branch_converged(gpu, port)
+
+
+def test_branch_passes_and_errors_gpu(gpu):
+    case_branch_passes(gpu)
+    case_branch_errors(gpu)
+
+
+def test_branch_full_size_fog_properties(gpu):
+    """C2's 1M-triangle mesh inside a medium at 512x512: energy sanity and determinism of the atomically accumulated radiance."""
+    def mk():
+        rt = scenes.config_C2(gpu, 512, 512, 4)
+        rt.s.fog_density, rt.s.fog_absorption, rt.s.fog_type = 0.2, 0.2, 0
+        return rt.commit()
+    a, b = mk(), mk()
+    ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+    assert np.isfinite(ia).all() and (ia >= 0).all() and ia.mean() > 0
+    assert np.allclose(ia, ib, rtol=1e-4, atol=1e-2 * float(ia.mean())), "same seed: same image up to the order of the float atomics"
+    assert a.stats["rays_closest"] == b.stats["rays_closest"] > a.stats["samples"]
+    clear = scenes.config_C2(gpu, 512, 512, 4).commit()
+    ic = clear.render_image_nopreviz()
+    assert not np.allclose(ia, ic, rtol=1e-2), "the medium must change the image"
 
 
 @pytest.mark.parametrize("variant", EDGE_VARIANTS)
