@@ -2,7 +2,7 @@
 # Short GPU visit: parity tests + bench lines (+ optional ncu of the trace kernel).  Every step is time-bounded.
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
+timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
 for w in ${PTB_WORKLOADS:-C2 C3}; do
   timeout 600 python bench.py --steps 2 --warmup 3 --workload $w --no-cpu-baseline 2>gpurun_out/bench_$w.err | tee gpurun_out/bench_$w.json
 done

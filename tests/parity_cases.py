@@ -95,7 +95,9 @@ def case_branch_converged(test_lib, oracle_lib):
     ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
     ea, eb = rrmse(ia, ref_hi), rrmse(ib, ref_hi)
     assert eb <= RRMSE_FACTOR * ea + 0.005, (ea, eb)
-    assert rrmse(ib, ia) <= 0.02, "equal-seed images should be nearly the same image"
+    # equal seed: nearly the same image.  A pixel sums 16 samples x up to 31 contributions, and one flipped firefly moves an
+    # RMSE a lot, so this is stated per pixel: at most 3 % of the pixels differ by more than 1e-3 relative
+    assert float(np.mean(rel_err(ia, ib) > 1e-3)) <= 0.03
 
 
 def case_branch_passes(test_lib):
