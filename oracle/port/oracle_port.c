@@ -117,9 +117,9 @@ static vec random_phong(vec R, float n, float r1, float r2) {
     vec t1 = get_tangent(R), t2 = vcross(t1, R);
     return vadd(vadd(vscale(l.z, R), vscale(l.x, t1)), vscale(l.y, t2));
 }
-typedef struct { vec shadingN, Kd, Ks, Ne, Ke; int transp; float refr_index; } matvals; /* BRDF.h:7-20 */
+typedef struct { vec shadingN, Kd, Ks, Ne, Ke, Ksub; int transp; float refr_index; } matvals; /* BRDF.h:7-20 */
 static matvals matvals_default(void) {
-    matvals m; m.shadingN = V(0, 1, 0); m.Kd = V(.5f, .5f, .5f); m.Ne = V(100, 100, 100); m.Ks = V(0, 0, 0); m.Ke = V(0, 0, 0);
+    matvals m; m.shadingN = V(0, 1, 0); m.Kd = V(.5f, .5f, .5f); m.Ne = V(100, 100, 100); m.Ks = V(0, 0, 0); m.Ke = V(0, 0, 0); m.Ksub = V(0, 0, 0);
     m.transp = 0; m.refr_index = 1.3f; /* uninitialised in the reference; only read after queryMaterial set them */
     return m;
 }
@@ -194,7 +194,7 @@ static vec merl_eval(const double* brdf, vec wi, vec wo, vec N) {
 /* ---- Texture (BRDF.h:252-426) --------------------------------------------------------------------- */
 typedef struct { float mult[3]; size_t W, H; float* values; } tex;
 typedef struct { tex* t; int n; } slotv; /* std::vector<Texture> */
-enum { S_KD, S_KS, S_NE, S_TRANSP, S_REFR, S_NORMAL, S_ALPHA, S_COUNT };
+enum { S_KD, S_KS, S_NE, S_TRANSP, S_REFR, S_NORMAL, S_ALPHA, S_KSUB, S_COUNT };
 static float tex_wrap(float u) { u -= (int)u; if (u < 0) u += 1; return u; }
 static size_t tex_idx(const tex* t, float u, float v) { int x = (int)(u * (t->W - 1)); int y = (int)(v * (t->H - 1)); return (y * t->W + x) * 3; }
 static vec tex_vec(const tex* t, float u, float v) {
@@ -277,6 +277,7 @@ static void query_material(const object* o, int idx, float u, float v, matvals* 
     size_t i = (size_t)idx;
     if (i >= (size_t)o->slots[S_KD].n) m->Kd = V(1, 1, 1); else m->Kd = tex_vec(&o->slots[S_KD].t[i], u, v);
     if (i >= (size_t)o->slots[S_KS].n) m->Ks = V(0, 0, 0); else m->Ks = tex_vec(&o->slots[S_KS].t[i], u, v);
+    if (i >= (size_t)o->slots[S_KSUB].n) m->Ksub = V(0, 0, 0); else m->Ksub = tex_vec(&o->slots[S_KSUB].t[i], u, v);
     if (i >= (size_t)o->slots[S_NE].n) m->Ne = V(1, 1, 1); else m->Ne = tex_vec(&o->slots[S_NE].t[i], u, v);
     if (i >= (size_t)o->slots[S_TRANSP].n) m->transp = 0; else m->transp = tex_red(&o->slots[S_TRANSP].t[i], u, v) < 0.5f;
     if (i >= (size_t)o->slots[S_REFR].n) m->refr_index = 1.3f; else m->refr_index = tex_red(&o->slots[S_REFR].t[i], u, v);
@@ -553,6 +554,61 @@ static int mesh_hit(const object* g, vec o, vec d, vec* P, float* t, matvals* ma
     return has;
 }
 
+/* TriMesh::reservoir_sampling_intersection (TriangleMesh.cpp:1321-1424): a uniformly random one of the mesh's intersections with
+ * min_t <= t < max_t, by reservoir sampling in BVH traversal order (one draw per accepted hit) */
+static int mesh_reservoir(const object* g, vec o, vec d, vec* P, float* t, matvals* mat, int* tri_id, int* nb_intersections, float min_t, float max_t, pcg* e) {
+    int has = 0, best = -1;
+    float tl, tr_, lt, alpha, beta, gamma;
+    vec lp;
+    invray r; r.o = o; r.id = V((float)(1. / d.x), (float)(1. / d.y), (float)(1. / d.z));
+    char s[3] = {(char)(r.id.x >= 0 ? 1 : 0), (char)(r.id.y >= 0 ? 1 : 0), (char)(r.id.z >= 0 ? 1 : 0)};
+    if (!box_invd(&g->bvh_bbox, &r, s, &tl)) return 0;
+    if (tl > max_t) return 0;
+    int l[50]; float tn[50]; int top = -1;
+    l[++top] = 0; tn[top] = tl;
+    while (top >= 0) {
+        if (tn[top] > max_t) { top--; continue; }
+        int cur = l[top--];
+        int fg = g->nodes[cur].fg, fd = g->nodes[cur].fd;
+        if (!g->nodes[cur].isleaf) {
+            int gl = box_invd_x(&g->nodes[fg].bb, &r, s, &tl, s[0] == 1) && tl < max_t;
+            int gr = box_invd_x(&g->nodes[fd].bb, &r, s, &tr_, s[0] == 1) && tr_ < max_t;
+            if (gl && gr) {
+                if (tl < tr_) { l[++top] = fd; tn[top] = tr_; l[++top] = fg; tn[top] = tl; }
+                else { l[++top] = fg; tn[top] = tl; l[++top] = fd; tn[top] = tr_; }
+            } else {
+                if (gl) { l[++top] = fg; tn[top] = tl; }
+                if (gr) { l[++top] = fd; tn[top] = tr_; }
+            }
+        } else {
+            for (int i = fg; i < fd; i++) {
+                if (soup_hit(&g->soup[i], o, d, &lp, &lt, &alpha, &beta, &gamma)) {
+                    if (lt < max_t && lt >= min_t) {
+                        if (alpha_skip(g, i, alpha, beta, gamma)) continue;
+                        (*nb_intersections)++;
+                        float r1 = pcg_unif(e);
+                        if (r1 < 1. / *nb_intersections) { has = 1; best = i; *t = lt; }
+                    }
+                }
+            }
+        }
+    }
+    if (has) {
+        *tri_id = best;
+        soup_hit(&g->soup[best], o, d, &lp, &lt, &alpha, &beta, &gamma);
+        if (isnan(alpha) && isnan(beta) && isnan(gamma)) { alpha = 1; beta = 0; gamma = 0; }
+        if (isnan(alpha)) alpha = 0;
+        if (isnan(beta)) beta = 0;
+        if (isnan(gamma)) gamma = 0;
+        if (isinf(alpha)) alpha = 1;
+        if (isinf(beta)) beta = 1;
+        if (isinf(gamma)) gamma = 1;
+        *P = lp;
+        mesh_material(g, best, alpha, beta, gamma, mat);
+    }
+    return has;
+}
+
 /* Sphere::intersection (Geometry.h:918-992) / intersection_shadow (1071-1094) */
 static int sphere_hit(const object* sp, vec o, vec d, vec* P, float* t, matvals* mat, int shadow) {
     float b = vdot(d, vsub(o, sp->O));
@@ -638,6 +694,19 @@ static int scene_shadow(const struct ptb_ctx* c, vec o, vec d, float dist_light,
         if (h && t < dist_light * 0.999) return 1;
     }
     return 0;
+}
+
+/* Scene::get_random_intersection (Geometry.cpp:339-472) restricted to object `id`, a TriMesh (the only kind whose
+ * reservoir_sampling_intersection the subsurface branch can use: Sphere's returns true without a point, Geometry.h:994-1012) */
+static int scene_random_hit(const struct ptb_ctx* c, vec o, vec d, vec* P, int id, float* min_t, matvals* mat, int* tri_id, float tmin, float tmax, pcg* e) {
+    const object* ob = c->objs[id];
+    *min_t = INFINITY;
+    int nb = 0;
+    vec dl = xf_dir(ob->inv, d), ol = xf_point(ob->inv, o);
+    int has = mesh_reservoir(ob, ol, dl, P, min_t, mat, tri_id, &nb, tmin, tmax, e);
+    if (has) { *P = xf_point(ob->trans, *P); mat->shadingN = xf_rot(ob->rotm, mat->shadingN); }
+    mat->shadingN = vfast_normalize(mat->shadingN);
+    return has;
 }
 
 /* Camera::generateDirection (Vector.h:792-825), non-lenticular */
@@ -760,7 +829,7 @@ static vec background_at(const struct ptb_ctx* c, int screenI, int screenJ) {
 }
 
 /* Raytracer::getColor (Raytracer.cpp:196-664): the ring of contributions with fog, ghost objects and the background photograph;
- * the subsurface branch (318-406) is not restated (Ksub slots are refused at commit). */
+ * the subsurface branch (318-406) is restated for TriMesh objects (the only kind it is defined for). */
 #define PUSH(k_) do { ring[end] = (k_); end++; if (end >= RING) end = 0; } while (0)
 static vec get_color(const struct ptb_ctx* c, vec ro0, vec rd0, int sampleID, int pix, pcg* e, unsigned long long* counter, const vec* samples2d,
                      vec* normalValue, vec* albedoValue) {
@@ -812,12 +881,60 @@ static vec get_color(const struct ptb_ctx* c, vec ro0, vec rd0, int sampleID, in
                 continue;
             }
             const object* ob = c->objs[id];
+            /* subsurface scattering (318-406): with probability 0.6 the path leaves the surface at a random nearby point of the same object */
+            const int is_subsurface = vnorm2(mat.Ksub) > 1E-8;                                              /* 270 */
+            const float subsProba = (hadSS || !is_subsurface) ? 0.f : 0.6f;
+            const float inv1MSubsProba = 1.f / (1.f - subsProba);
+            vec subsW = V(inv1MSubsProba, inv1MSubsProba, inv1MSubsProba);
+            int sub_interaction = 0;
+            const vec cur_d = rd;                                        /* currentRay.direction: what fogContribution keeps seeing */
+            if (is_subsurface && pcg_unif(e) < subsProba) {
+                sub_interaction = 1;
+                const float invSubsProba = 1.f / subsProba;
+                subsW = V(invSubsProba, invSubsProba, invSubsProba);
+                const float sigmasub = 1.5f;
+                const float diskR = sqrtf(12.46f) * sigmasub;
+                float integ = 1.f - expf(-diskR * diskR / (2.f * sigmasub * sigmasub));
+                float randR = sigmasub * sqrtf(-2.f * logf(1.f - pcg_unif(e) * integ));
+                float randangle = pcg_unif(e) * 2.f * (float)M_PI;
+                float g0 = randR * sinf(randangle), g1 = randR * cosf(randangle), g2 = randR;
+                float gaussval = (float)((1. / (sigmasub * sigmasub * 2.f * (float)M_PI)) * expf(-(g2 * g2) / (2.f * sigmasub * sigmasub)));
+                float pdfgauss = gaussval / integ;
+                vec Tg = get_tangent(N), Tg2 = vcross(N, Tg);
+                vec PtaboveP = vadd(vadd(vadd(P, vscale(g0, Tg)), vscale(g1, Tg2)), vscale(diskR, N));
+                float r1 = pcg_unif(e);
+                vec axis = vneg(N);
+                float tmax, wAxis;
+                float h = sqrtf(diskR * diskR - g2 * g2);
+                vec subsOrigin = vadd(PtaboveP, vscale(diskR - h, vneg(N)));
+                if (r1 < 0.5f) { wAxis = 0.5f; tmax = 2.f * h; }
+                else {
+                    wAxis = 0.25f; tmax = 2.f * g2;
+                    axis = r1 < 0.75f ? Tg : Tg2;
+                    float r2 = pcg_unif(e);
+                    if (r2 < 0.5f) subsOrigin = vsub(subsOrigin, vscale(h, N));
+                }
+                matvals subsmat = matvals_default(); int substri = -1; float subst; vec localP2 = V(0, 0, 0);
+                if (ob->type == T_MESH && scene_random_hit(c, subsOrigin, axis, &localP2, id, &subst, &subsmat, &substri, 0, tmax, e)) {
+                    float chris = (float)exp(-vnorm2(vsub(P, localP2)) / (2. * sigmasub * sigmasub));
+                    float a0 = vdot(subsmat.shadingN, N), a1 = vdot(subsmat.shadingN, Tg), a2 = vdot(subsmat.shadingN, Tg2);
+                    float sumpdfs = (float)((0.5 * a0) * (0.5 * a0) + (0.25 * a1) * (0.25 * a1) + (0.25 * a2) * (0.25 * a2));
+                    float pdfdisk = wAxis * fabsf(vdot(axis, subsmat.shadingN)) / sumpdfs;
+                    subsW = vscale(pdfdisk / fmaxr(pdfgauss, 0.05f) * chris, subsW);
+                    rd = vnormalize(vsub(localP2, P));                   /* rayDirection */
+                    P = vadd(localP2, vscale(0.005f, subsmat.shadingN));
+                    subsW = vscale(r1 < 0.5f ? 2.f : 4.f, subsW);
+                    subsW = vmul(subsW, vdiv(mat.Ksub, (float)M_PI));
+                    mat = subsmat;
+                    N = mat.shadingN;
+                }
+            }
             color = vadd(color, vscale(c->envmap_intensity, vmul(w, mat.Ke)));                              /* 411 */
             if (ob->miroir) {                                            /* 413-436 */
                 vec nd = vreflect(rd, N), no = vadd(P, vscale(0.001f, N));
                 contrib k;
                 if (has_fog) {
-                    if (fog_contribution(c, ro, rd, c->centerLight, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
+                    if (fog_contribution(c, ro, cur_d, c->centerLight, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
                     k = mk_contrib(vscale(att, w), no, nd, depth - 1, show_lights, hadSS, 1);
                 } else k = mk_contrib(w, no, nd, depth - 1, show_lights, hadSS, 1);
                 k.rng = *e; PUSH(k);
@@ -839,7 +956,7 @@ static vec get_color(const struct ptb_ctx* c, vec ro0, vec rd0, int sampleID, in
                 } else { no = vadd(P, vscale(0.001f, Nt)); nd = vreflect(rd, N); }
                 contrib k;
                 if (has_fog) {
-                    if (fog_contribution(c, ro, rd, c->centerLight, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
+                    if (fog_contribution(c, ro, cur_d, c->centerLight, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
                     k = mk_contrib(vscale(att, w), no, nd, depth - 1, show_lights, hadSS, 1);
                 } else k = mk_contrib(w, no, nd, depth - 1, show_lights, hadSS, 1);
                 k.rng = *e; PUSH(k);
@@ -856,21 +973,23 @@ static vec get_color(const struct ptb_ctx* c, vec ro0, vec rd0, int sampleID, in
             if (vdot(mat.shadingN, wi) < 0) shadowed = 1;
             else shadowed = scene_shadow(c, vadd(P, vscale(0.01f, wi)), wi, sqrtf(d2) - 0.01f, counter);
             vec contribution = V(0, 0, 0);
-            vec fog_o = ro;                                              /* `currentRay` as fogContribution sees it below */
+            vec fog_o = ro, fog_d = cur_d;                               /* `currentRay` as fogContribution sees it below */
             if (!shadowed) {
                 if (ob->ghost) {                                         /* 522-537: straight through, same depth */
                     vec offset = vdot(N, rd) > 0 ? N : vneg(N);
-                    fog_o = vadd(vadd(P, vscale(0.001f, rd)), vscale(0.001f, offset));
+                    fog_o = vadd(vadd(P, vscale(0.001f, rd)), vscale(0.001f, offset)); fog_d = rd;
                     contrib k = mk_contrib(w, fog_o, rd, depth, show_lights, hadSS, show_envmap);
                     k.rng = pcg_fork(e, 2); PUSH(k);
                 }
-                vec fr = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, wi, vneg(rd), N) : phong_eval(&mat, wi, vneg(rd), N);
+                vec fr;
+                if (sub_interaction) fr = vdiv(mat.Ksub, (float)M_PI);
+                else fr = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, wi, vneg(rd), N) : phong_eval(&mat, wi, vneg(rd), N);
                 float J = vdot(dirl, vneg(wi)) / d2;
                 float proba = (float)(vdot(axeOP, dirl) / (M_PI * c->radiusLight * c->radiusLight));
-                if (!ob->ghost && proba > 0.f) contribution = vadd(contribution, vmul(vscale(c->lightPower * fmaxr(0.f, vdot(N, wi)) * J / proba, V(1, 1, 1)), fr));
+                if (!ob->ghost && proba > 0.f) contribution = vadd(contribution, vmul(vscale(c->lightPower * fmaxr(0.f, vdot(N, wi)) * J / proba, subsW), fr));
             }
             if (has_fog) {                                               /* 556-566 */
-                if (fog_contribution(c, fog_o, rd, xl, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
+                if (fog_contribution(c, fog_o, fog_d, xl, t, w, depth, show_lights, hadSS, &fogc, &att, e, counter)) { fogc.rng = pcg_fork(e, 1); PUSH(fogc); }
                 color = vadd(color, vmul(vscale(att, w), contribution));
             } else color = vadd(color, vmul(w, contribution));
             /* continuation (570-632) */
@@ -878,13 +997,16 @@ static vec get_color(const struct ptb_ctx* c, vec ro0, vec rd0, int sampleID, in
             float r1 = modff(c->randomPerPixel[pix].x + samples2d[sampleID].x, &tmp);
             float r2 = modff(c->randomPerPixel[pix].y + samples2d[sampleID].y, &tmp);
             float pdf; vec dir; int diffuse = 0;
-            if (ob->brdf == PTB_BRDF_MERL) { dir = random_cos(N, r1, r2); pdf = (float)(vdot(N, dir) / (M_PI)); }
+            if (sub_interaction) { dir = random_cos(mat.shadingN, r1, r2); pdf = vdot(N, dir) / (float)M_PI; diffuse = 1; }   /* 598-601 */
+            else if (ob->brdf == PTB_BRDF_MERL) { dir = random_cos(N, r1, r2); pdf = (float)(vdot(N, dir) / (M_PI)); }
             else dir = phong_sample(&mat, vneg(rd), N, &pdf, r1, r2, e, &diffuse);
             if (vdot(dir, N) < 0 || vdot(dir, vreflect(rd, N)) < 0 || pdf <= 0) continue;
-            vec fi = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, dir, vneg(rd), N) : phong_eval(&mat, dir, vneg(rd), N);
-            vec nw = vscale((vdot(N, dir) / pdf), vmul(vmul(w, V(1, 1, 1)), fi));
+            vec fi;
+            if (sub_interaction) fi = vdiv(mat.Ksub, (float)M_PI);
+            else fi = ob->brdf == PTB_BRDF_MERL ? merl_eval(ob->merl, dir, vneg(rd), N) : phong_eval(&mat, dir, vneg(rd), N);
+            vec nw = vscale((vdot(N, dir) / pdf), vmul(vmul(w, subsW), fi));
             if (ob->ghost && has_bg) nw = vmul(nw, vdiv(background_at(c, screenI, screenJ), 196964.699f));  /* 614-621 */
-            contrib k = mk_contrib(has_fog ? vscale(att, nw) : nw, vadd(P, vscale(0.01f, dir)), dir, depth - 1, 0, hadSS,
+            contrib k = mk_contrib(has_fog ? vscale(att, nw) : nw, vadd(P, vscale(0.01f, dir)), dir, depth - 1, 0, sub_interaction ? 1 : hadSS,
                                    (show_envmap && shadowed && diffuse) || !ob->ghost);
             k.rng = *e; PUSH(k);
         }
@@ -1064,8 +1186,11 @@ int ptb_set_group_material(ptb_ctx* c, int obj, int group, const ptb_material* m
     if (m->present & PTB_SLOT_REFR) put_slot(&o->slots[S_REFR], group, &m->refr);
     if (m->present & PTB_SLOT_NORMAL) put_slot(&o->slots[S_NORMAL], group, &m->normal);
     if (m->present & PTB_SLOT_ALPHA) put_slot(&o->slots[S_ALPHA], group, &m->alpha);
-    if ((m->present & PTB_SLOT_KSUB) && (m->Ksub.texels || m->Ksub.mult[0] * m->Ksub.mult[0] + m->Ksub.mult[1] * m->Ksub.mult[1] + m->Ksub.mult[2] * m->Ksub.mult[2] > 1E-8f)) {
-        snprintf(c->err, sizeof(c->err), "subsurface scattering is not restated by the port"); return PTB_ERR_UNSUPPORTED;
+    if (m->present & PTB_SLOT_KSUB) {
+        if (o->type != T_MESH && (m->Ksub.texels || m->Ksub.mult[0] * m->Ksub.mult[0] + m->Ksub.mult[1] * m->Ksub.mult[1] + m->Ksub.mult[2] * m->Ksub.mult[2] > 1E-8f)) {
+            snprintf(c->err, sizeof(c->err), "subsurface scattering on a sphere / plane is undefined in the reference (Geometry.h:994-1012)"); return PTB_ERR_UNSUPPORTED;
+        }
+        put_slot(&o->slots[S_KSUB], group, &m->Ksub);
     }
     return PTB_OK;
 }

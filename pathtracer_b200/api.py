@@ -345,10 +345,11 @@ class Raytracer:
                 return f"per-vertex colours on object {i}"
             if i != 1 and getattr(o, "envmap", None) is not None:
                 return f"environment map on object {i} (only the dome, object 1)"
-            for slots in o.materials.values():
-                t = slots.get("Ksub")
-                if t is not None and (t.values is not None or sum(x * x for x in t.multiplier) > 1e-8):
-                    return f"subsurface scattering on object {i}"
+            if not isinstance(o, TriMesh):
+                for slots in o.materials.values():
+                    t = slots.get("Ksub")
+                    if t is not None and (t.values is not None or sum(x * x for x in t.multiplier) > 1e-8):
+                        return f"subsurface scattering on object {i}: the reference defines it for triangle meshes only"
         return None
 
     # ---- scene hand-over -------------------------------------------------------------------------

@@ -297,4 +297,64 @@ PTB_HD bool traverse(const F4* __restrict__ nodes, const F4* __restrict__ tris, 
     return found;
 }
 
+// Every accepted triangle with 0 <= t < tmax, in traversal order: `on_hit(prim, t, b1, b2, flags)`.  Used by the subsurface probe
+// (TriMesh::reservoir_sampling_intersection, TriangleMesh.cpp:1321-1424), which is not a hot path.
+template <class F>
+PTB_HD void traverse_all(const F4* __restrict__ nodes, const F4* __restrict__ tris, const AlphaCtx* actx, V3 o, V3 d, float tmax, F& on_hit) {
+    const RayPrep r = ray_prep(o, d);
+    U2 stack[PTB_STACK];
+    int sp = 0;
+    U2 ngroup, tgroup;
+    ngroup.x = 0; ngroup.y = 0x80000000u;
+    for (;;) {
+        {
+            const uint32_t hits_imask = ngroup.y;
+            const uint32_t child_bit = highest_bit(hits_imask);
+            const uint32_t child_base = ngroup.x;
+            ngroup.y &= ~(1u << child_bit);
+            if (ngroup.y > 0x00ffffffu) { if (sp < PTB_STACK) stack[sp++] = ngroup; }
+            const uint32_t slot = (child_bit - 24u) ^ (r.oct_inv4 & 0xffu);
+            const uint32_t rel = popcount32(hits_imask & ~(0xffffffffu << slot));
+            const F4* np = nodes + (size_t)(child_base + rel) * 5;
+            F4 n0, n1, n2, n3, n4;
+            {
+                auto l0 = PTB_LDG_F4(np + 0); auto l1 = PTB_LDG_F4(np + 1); auto l2 = PTB_LDG_F4(np + 2);
+                auto l3 = PTB_LDG_F4(np + 3); auto l4 = PTB_LDG_F4(np + 4);
+                n0.x = l0.x; n0.y = l0.y; n0.z = l0.z; n0.w = l0.w;
+                n1.x = l1.x; n1.y = l1.y; n1.z = l1.z; n1.w = l1.w;
+                n2.x = l2.x; n2.y = l2.y; n2.z = l2.z; n2.w = l2.w;
+                n3.x = l3.x; n3.y = l3.y; n3.z = l3.z; n3.w = l3.w;
+                n4.x = l4.x; n4.y = l4.y; n4.z = l4.z; n4.w = l4.w;
+            }
+            const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, tmax);
+            ngroup.x = f2u(n1.x);
+            tgroup.x = f2u(n1.y);
+            ngroup.y = (hm & 0xff000000u) | (f2u(n0.w) >> 24);
+            tgroup.y = hm & 0x00ffffffu;
+        }
+        while (tgroup.y != 0) {
+            const uint32_t ti = highest_bit(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            const uint32_t prim = tgroup.x + ti;
+            const F4* tp = tris + (size_t)prim * 3;
+            F4 a, b, c;
+            {
+                auto l0 = PTB_LDG_F4(tp + 0); auto l1 = PTB_LDG_F4(tp + 1); auto l2 = PTB_LDG_F4(tp + 2);
+                a.x = l0.x; a.y = l0.y; a.z = l0.z; a.w = l0.w;
+                b.x = l1.x; b.y = l1.y; b.z = l1.z; b.w = l1.w;
+                c.x = l2.x; c.y = l2.y; c.z = l2.z; c.w = l2.w;
+            }
+            float t, b1, b2;
+            if (tri_test(a, b, c, r, tmax, t, b1, b2)) {
+                if ((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(actx, (int)prim, b1, b2)) continue;
+                on_hit((int32_t)prim, t, b1, b2);
+            }
+        }
+        if (ngroup.y <= 0x00ffffffu) {
+            if (sp > 0) ngroup = stack[--sp];
+            else break;
+        }
+    }
+}
+
 }  // namespace ptb

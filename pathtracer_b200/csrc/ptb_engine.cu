@@ -37,7 +37,8 @@ using namespace ptb;
 #define PTB_CNT_SQ (4 * (PTB_MAX_BOUNCES + 1))
 #define PTB_CNT_ALLOC (5 * (PTB_MAX_BOUNCES + 1))       // branching renders: side-branch slots handed out in this pass
 #define PTB_CNT_DROPS (5 * (PTB_MAX_BOUNCES + 1) + 1)   // side branches that found the pool full
-#define PTB_N_COUNTERS (5 * (PTB_MAX_BOUNCES + 1) + 2)
+#define PTB_CNT_PROBE (5 * (PTB_MAX_BOUNCES + 1) + 2)   // subsurface probes emitted at the current level
+#define PTB_N_COUNTERS (5 * (PTB_MAX_BOUNCES + 1) + 3)
 // 64-bit totals: 0 closest rays, 1 shadow rays, 2/3 node visits / triangle tests of the closest-hit trace, 4/5 of the any-hit trace
 #define PTB_N_TOTALS 6
 #define PTB_BRANCH_MAX_LEVELS 512
@@ -238,16 +239,18 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, Po
 template <bool MERL>
 __global__ void __launch_bounds__(128) k_shade_branch(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                       int n_static, uint32_t* __restrict__ next_queue, uint32_t* next_count, uint32_t* shadow_count,
-                                                      uint32_t* shadow_queries, uint32_t* alloc, uint32_t n_roots, uint32_t cap, uint32_t* drops) {
+                                                      uint32_t* shadow_queries, uint32_t* alloc, uint32_t n_roots, uint32_t cap, uint32_t* drops,
+                                                      uint32_t* probe_count, const F4* __restrict__ resume) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = count ? (int)*count : n_static;
     BranchOut out;
     out.base.cont = false; out.base.shadow = false; out.base.shadow_query = false;
-    out.fog.want = false; out.ghost.want = false; out.ghost_pending = false;
+    out.fog.want = false; out.ghost.want = false; out.ghost_pending = false; out.probe = false;
     int path = 0;
     uint32_t root = 0, pix = 0;
     if (tid < n) {
-        path = queue ? (int)queue[tid] : tid;
+        // `resume`: second visit of the hits whose subsurface probe has been answered (the probe entries name the paths)
+        path = resume ? (int)f2u(resume[tid].w) : (queue ? (int)queue[tid] : tid);
         root = p.root[path]; pix = p.pixel[path];
         if (pix != 0xffffffffu) shade_branch_one<MERL>(sc, f, p, path, out);
     }
@@ -272,6 +275,14 @@ __global__ void __launch_bounds__(128) k_shade_branch(SceneDev sc, FrameDev f, P
     }
     const uint32_t sq = __ballot_sync(0xffffffffu, out.base.shadow_query);
     if ((threadIdx.x & 31) == 0 && sq) atomicAdd(shadow_queries, (uint32_t)__popc(sq));
+    const uint32_t pi = warp_push(probe_count, out.probe);
+    if (out.probe) { p.probe_o[pi] = out.probe_o; p.probe_d[pi] = out.probe_d; p.probe_x[pi] = out.probe_x; }
+}
+
+// Subsurface probes: one thread per probe, plain stack traversal collecting every hit of a short ray (not a hot path).
+__global__ void __launch_bounds__(128) k_probe(SceneDev sc, PoolDev p, int n) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < n) probe_one(sc, p, tid);
 }
 
 struct RedAddV4 {
@@ -463,7 +474,7 @@ static void free_scene(ptb_ctx* c) {
 }
 static void free_pool(ptb_ctx* c) {
     void* ptrs[] = {c->pool.ray_o, c->pool.ray_d, c->pool.weight, c->pool.radiance, c->pool.hit, c->pool.rng, c->pool.pixel,
-                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1], c->pool.aov_n, c->pool.aov_kd, c->pool.root};
+                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1], c->pool.aov_n, c->pool.aov_kd, c->pool.root, c->pool.probe_o, c->pool.probe_d, c->pool.probe_x, c->pool.hit2};
     for (void* p : ptrs) if (p) cudaFree(p);
     memset(&c->pool, 0, sizeof(c->pool));
     c->d_queue[0] = c->d_queue[1] = nullptr;
@@ -481,10 +492,10 @@ static int upload(ptb_ctx* c, const T* host, size_t n, const T** dev) {
     return PTB_OK;
 }
 
-static int ensure_pool(ptb_ctx* c, int64_t paths, bool aov = false, bool branch = false) {
-    if (paths <= c->pool_cap && (!aov || c->pool.aov_n) && (!branch || c->pool.root)) return PTB_OK;
+static int ensure_pool(ptb_ctx* c, int64_t paths, bool aov = false, bool branch = false, bool sss = false) {
+    if (paths <= c->pool_cap && (!aov || c->pool.aov_n) && (!branch || c->pool.root) && (!sss || c->pool.hit2)) return PTB_OK;
     paths = std::max(paths, c->pool_cap);
-    aov = aov || c->pool.aov_n; branch = branch || c->pool.root;
+    aov = aov || c->pool.aov_n; branch = branch || c->pool.root; sss = sss || c->pool.hit2;
     free_pool(c);
     const size_t n = (size_t)paths;
     CK(cudaMalloc((void**)&c->pool.ray_o, n * sizeof(F4)));
@@ -504,6 +515,12 @@ static int ensure_pool(ptb_ctx* c, int64_t paths, bool aov = false, bool branch 
         CK(cudaMalloc((void**)&c->pool.aov_kd, n * sizeof(F4)));
     }
     if (branch) CK(cudaMalloc((void**)&c->pool.root, n * sizeof(uint32_t)));
+    if (sss) {
+        CK(cudaMalloc((void**)&c->pool.probe_o, n * sizeof(F4)));
+        CK(cudaMalloc((void**)&c->pool.probe_d, n * sizeof(F4)));
+        CK(cudaMalloc((void**)&c->pool.probe_x, n * sizeof(F4)));
+        CK(cudaMalloc((void**)&c->pool.hit2, n * sizeof(F4)));
+    }
     c->pool_cap = paths;
     return PTB_OK;
 }
@@ -766,9 +783,9 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
         int64_t pool = std::max<int64_t>(c->pool_paths, 1024);
         // Branching renders keep every live contribution of a sample in the pool: the continuation reuses its slot, each side
         // branch takes a new one.  A fogged path forks once per iteration (at most 2^depth - 1 forks per sample), a ghost hit once.
-        const bool branch = c->sc.has_fog || c->sc.has_ghost || c->sc.bgW > 0;
+        const bool branch = c->sc.has_fog || c->sc.has_ghost || c->sc.bgW > 0 || c->sc.has_sss;
         const int fan = !branch ? 1 : (c->sc.has_fog ? (1 << std::min(f.nb_bounces, 6)) : (c->sc.has_ghost ? 8 : 1));
-        if (branch && f.accum_albedo) { c->err = "denoiser inputs are not available with fog, ghost objects or a background photograph"; return PTB_ERR_UNSUPPORTED; }
+        if (branch && f.accum_albedo) { c->err = "denoiser inputs are not available with fog, ghost objects, subsurface scattering or a background photograph"; return PTB_ERR_UNSUPPORTED; }
         const int64_t pool_cap_slots = pool;
         pool = std::max<int64_t>(pool / fan, 1024);
         int spp_pass; int64_t slots_pass;
@@ -776,7 +793,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
         else if (pixel_slots <= pool) { spp_pass = (int)std::max<int64_t>(1, pool / pixel_slots); slots_pass = pixel_slots; }
         else { spp_pass = 1; slots_pass = (pool / (f.tile * f.tile)) * (f.tile * f.tile); if (slots_pass <= 0) slots_pass = f.tile * f.tile; }
         const bool aov = f.accum_albedo != nullptr;
-        int rc = ensure_pool(c, branch ? std::max<int64_t>(slots_pass * spp_pass * fan, pool_cap_slots) : slots_pass * spp_pass, aov, branch);
+        int rc = ensure_pool(c, branch ? std::max<int64_t>(slots_pass * spp_pass * fan, pool_cap_slots) : slots_pass * spp_pass, aov, branch, c->sc.has_sss != 0);
         if (rc) return rc;
         const int nb = f.nb_bounces;
         for (int64_t s0 = 0; s0 < pixel_slots; s0 += slots_pass) {
@@ -825,6 +842,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                                 CK(cudaMemsetAsync(cur, 0, 2 * sizeof(uint32_t), c->stream));
                                 CK(cudaMemsetAsync(cnt_sq, 0, sizeof(uint32_t), c->stream));
                             }
+                            CK(cudaMemsetAsync(c->d_counters + PTB_CNT_PROBE, 0, sizeof(uint32_t), c->stream));
                         }
                         const uint32_t* q = b == 0 ? nullptr : c->d_queue[s];
                         const uint32_t* cnt = b == 0 ? nullptr : cnt_q;
@@ -838,12 +856,25 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                             launches++;
                         }
                         lt.begin(2 | (std::min(b, 63) << 8));
-                        if (c->has_merl) k_shade_branch<true><<<gs, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[ns], cnt_next, cnt_sh, cnt_sq, c->d_counters + PTB_CNT_ALLOC,
-                                                                                          (uint32_t)n_paths, (uint32_t)c->pool_cap, c->d_counters + PTB_CNT_DROPS);
-                        else k_shade_branch<false><<<gs, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[ns], cnt_next, cnt_sh, cnt_sq, c->d_counters + PTB_CNT_ALLOC,
-                                                                              (uint32_t)n_paths, (uint32_t)c->pool_cap, c->d_counters + PTB_CNT_DROPS);
+#define PTB_SHADE_BRANCH(M, GRID, Q, CNT, NSTATIC, RESUME) k_shade_branch<M><<<GRID, 128, 0, c->stream>>>(c->sc, f, c->pool, Q, CNT, NSTATIC, c->d_queue[ns], cnt_next, cnt_sh, cnt_sq, \
+                            c->d_counters + PTB_CNT_ALLOC, (uint32_t)n_paths, (uint32_t)c->pool_cap, c->d_counters + PTB_CNT_DROPS, c->d_counters + PTB_CNT_PROBE, RESUME)
+                        if (c->has_merl) PTB_SHADE_BRANCH(true, gs, q, cnt, n_paths, nullptr); else PTB_SHADE_BRANCH(false, gs, q, cnt, n_paths, nullptr);
                         lt.end();
                         launches++;
+                        if (c->sc.has_sss) {   // answer this level's subsurface probes, then shade those hits for good
+                            uint32_t h_probe = 0;
+                            CK(cudaMemcpyAsync(&h_probe, c->d_counters + PTB_CNT_PROBE, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                            CK(cudaStreamSynchronize(c->stream));
+                            if (h_probe > 0) {
+                                const unsigned gp = (unsigned)((h_probe + 127) / 128);
+                                k_probe<<<gp, 128, 0, c->stream>>>(c->sc, c->pool, (int)h_probe);
+                                lt.begin(2 | (std::min(b, 63) << 8));
+                                if (c->has_merl) PTB_SHADE_BRANCH(true, gp, nullptr, nullptr, (int)h_probe, c->pool.probe_d); else PTB_SHADE_BRANCH(false, gp, nullptr, nullptr, (int)h_probe, c->pool.probe_d);
+                                lt.end();
+                                launches += 2;
+                            }
+                        }
+#undef PTB_SHADE_BRANCH
                         uint32_t h_sh = 0, h_next = 0, h_sq = 0;
                         CK(cudaMemcpyAsync(&h_sh, cnt_sh, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
                         CK(cudaMemcpyAsync(&h_next, cnt_next, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -24,7 +24,7 @@ struct HostTex {
 };
 struct HostMaterial {
     uint32_t present = 0;
-    HostTex Kd, Ks, Ne, transp, refr, normal, alpha;
+    HostTex Kd, Ks, Ne, transp, refr, normal, alpha, Ksub;
 };
 struct HostObject {
     int type = OBJ_SPHERE, flags = 0, brdf = 0, merl = 0;
@@ -52,6 +52,7 @@ struct FlatScene {
     float envmap_intensity = 1, lightPower = 0, radiusLight = 0, centerLight[3] = {0, 0, 0};
     Bvh8Stats bvh;
     double ms_bvh = 0;
+    bool has_sss = false;                  // some mesh group carries a subsurface albedo
 };
 
 struct HostScene {
@@ -82,6 +83,7 @@ inline void scene_header(SceneDev& sc, FlatScene& f) {
     sc.centerLight = v3(f.centerLight[0], f.centerLight[1], f.centerLight[2]);
     sc.n_inline = 0; sc.n_extra = 0;
     sc.has_ghost = 0;
+    sc.has_sss = f.has_sss ? 1 : 0;
     for (size_t i = 0; i < f.objects.size(); i++) {
         ObjectDev& o = f.objects[i];
         if (o.flags & FLAG_GHOST) sc.has_ghost = 1;

@@ -15,7 +15,7 @@ namespace ptb {
 
 enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2 };
 enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4, FLAG_GHOST = 8, FLAG_NOT_INLINE = 1 << 16 };
-enum { SLOT_KD = 1, SLOT_KS = 2, SLOT_NE = 4, SLOT_TRANSP = 8, SLOT_REFR = 16, SLOT_NORMAL = 32, SLOT_ALPHA = 64 };
+enum { SLOT_KD = 1, SLOT_KS = 2, SLOT_NE = 4, SLOT_TRANSP = 8, SLOT_REFR = 16, SLOT_NORMAL = 32, SLOT_ALPHA = 64, SLOT_KSUB = 128 };
 
 struct ObjectDev {          // Object / Sphere / Plane fields the path reads (Geometry.h:240-672, 849-1217)
     int32_t type, flags, brdf, merl;
@@ -29,7 +29,7 @@ struct ObjectDev {          // Object / Sphere / Plane fields the path reads (Ge
 };
 struct MaterialDev {
     uint32_t present;
-    TexDev Kd, Ks, Ne, transp, refr, normal, alpha;
+    TexDev Kd, Ks, Ne, transp, refr, normal, alpha, Ksub;
 };
 struct alignas(16) TriUV {     // what the in-traversal alpha test and the uv interpolation need (32 B)
     float u0, v0, u1, v1, u2, v2;
@@ -72,6 +72,7 @@ struct SceneDev {
     V3 centerLight;
     int32_t n_inline, n_extra;  // analytic objects held inline below / left in `objects` (flag FLAG_NOT_INLINE)
     int32_t has_fog, has_ghost; // fog_density > 1e-8 (Raytracer.cpp:206) / any Object::ghost
+    int32_t has_sss, pad1;      // some mesh group carries a non-zero subsurface albedo Ksub (Raytracer.cpp:270)
     const float* background;    // Scene::background (Geometry.h:1365), bgW*bgH*3 floats, or null
     int32_t bgW, bgH;
     FogDev fog;
@@ -212,7 +213,7 @@ PTB_HD void extend_ray(const SceneDev& sc, V3 o, V3 d, Hit& hit, int32_t& id, Tr
 }
 
 struct Surface {   // MaterialValues (BRDF.h:7-20) + what getColor needs about the object
-    V3 P, N, Kd, Ks, Ne, Ke;
+    V3 P, N, Kd, Ks, Ne, Ke, Ksub;
     float refr_index;
     bool transp;
     int32_t object;
@@ -230,6 +231,7 @@ PTB_HD void query_material(const SceneDev& sc, const ObjectDev& ob, int group, f
     s.transp = (present & SLOT_TRANSP) ? (tex_red(m->transp, sc.texels, u, v) < 0.5f) : false;
     s.refr_index = (present & SLOT_REFR) ? tex_red(m->refr, sc.texels, u, v) : 1.3f;
     s.Ke = v3(0, 0, 0);
+    s.Ksub = (present & SLOT_KSUB) ? tex_vec(m->Ksub, sc.texels, u, v) : v3(0, 0, 0);   // read by the branching shader only
 }
 
 // Rebuild the shading point of a hit: Object::intersection's material part + the tail of Scene::intersection.
@@ -287,7 +289,7 @@ PTB_HD void surface_from_hit(const SceneDev& sc, V3 o, V3 d, const Hit& hit, int
                 else s.Ke = v3((float)sc.envmap[idx], (float)sc.envmap[idx + 1], (float)sc.envmap[idx + 2]) * (100000.f / 255.f);
             } else {
                 // MaterialValues() defaults when the sphere has no slot at all (BRDF.h:9-16)
-                s.Kd = v3(.5f, .5f, .5f); s.Ks = v3(0, 0, 0); s.Ne = v3(100, 100, 100); s.transp = false; s.refr_index = 1.3f;
+                s.Kd = v3(.5f, .5f, .5f); s.Ks = v3(0, 0, 0); s.Ne = v3(100, 100, 100); s.transp = false; s.refr_index = 1.3f; s.Ksub = v3(0, 0, 0);
                 if (ob.slot_mask & (SLOT_KD | SLOT_KS | SLOT_NE | SLOT_TRANSP | SLOT_REFR)) {
                     N = fast_normalize(N);
                     const float theta = 1.f - acosf(N.y) / PTB_PI_F;
@@ -321,6 +323,10 @@ struct PoolDev {
     F4* aov_n;        // first-hit shading normal (normalValue, Raytracer.cpp:254-257); null unless the denoiser-input mode renders
     F4* aov_kd;       // first-hit albedo mat.Kd (albedoValue)
     uint32_t* root;   // branching renders (fog / ghost objects): the sample slot a contribution belongs to; null otherwise
+    F4* probe_o;      // subsurface probes (entry-indexed): xyz origin, w = tmax
+    F4* probe_d;      // xyz axis, w = path slot bits
+    F4* probe_x;      // x,y = pcg32 state of the probe's own stream (lo, hi), z = object id bits
+    F4* hit2;         // slot-indexed: the probe's answer t, b1, b2, prim bits (prim -1: nothing found)
 };
 
 struct FrameDev {     // per-render constants (Raytracer fields + prepare_render results)
@@ -376,7 +382,7 @@ PTB_HD uint64_t path_inc(const FrameDev& f, int path) {  // pcg32 stream increme
 // path state word (weight.w): depth (low 16) | show_lights | showenvmap | has_had_subsurface_interaction | pcg32 stream kind
 // (0: the sample's own stream, 1: fog fork, 2: ghost fork; oracle/build_ref.py patch 7) | fog contribution awaiting its hit
 enum { ST_SHOW_LIGHTS = 0x10000u, ST_SHOW_ENV = 0x20000u, ST_HAD_SS = 0x40000u, ST_KIND_SHIFT = 19, ST_KIND_MASK = 3u << 19,
-       ST_FOG_PENDING = 1u << 21, ST_FOG_UNIFORM = 1u << 22 };
+       ST_FOG_PENDING = 1u << 21, ST_FOG_UNIFORM = 1u << 22, ST_SSS_WAIT = 1u << 23 /* the subsurface probe of this hit is in flight / answered */ };
 PTB_HD uint32_t pack_state(int depth, bool show_lights) { return (uint32_t)depth | (show_lights ? ST_SHOW_LIGHTS : 0u) | ST_SHOW_ENV; }
 
 // ---- stage 1: camera samples --------------------------------------------------------------------------
@@ -617,6 +623,8 @@ struct BranchOut {
     ShadeOut base;
     ChildOut fog, ghost;
     bool ghost_pending;   // the ghost child lives only if the shadow ray in base.sh_* turns out unoccluded (Raytracer.cpp:519-537)
+    bool probe;           // a subsurface probe must be answered before this hit can be shaded (get_random_intersection, Raytracer.cpp:377)
+    F4 probe_o, probe_d, probe_x;
 };
 
 PTB_HD uint64_t stream_inc(const FrameDev& f, uint32_t root, uint32_t state) {
@@ -722,7 +730,7 @@ PTB_HD float fog_sample(const SceneDev& sc, V3 ro, V3 rd, V3 lightPos, float t, 
 template <bool MERL>
 PTB_HD void shade_branch_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path, BranchOut& out) {
     out.base.cont = false; out.base.shadow = false; out.base.shadow_query = false;
-    out.fog.want = false; out.ghost.want = false; out.ghost_pending = false;
+    out.fog.want = false; out.ghost.want = false; out.ghost_pending = false; out.probe = false;
     const F4 wq = p.weight[path];
     uint32_t st = f2u(wq.w);
     const int depth = (int)(st & 0xffffu);
@@ -782,35 +790,105 @@ PTB_HD void shade_branch_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, 
         return;
     }
     const ObjectDev& ob = sc.objects[s.object];
+    // -- subsurface scattering (318-406): with probability 0.6 the path re-emerges at a random nearby point of the same mesh.
+    //    The probe (Scene::get_random_intersection, reservoir sampling over all hits of a short ray) needs a traversal of its
+    //    own: the first visit of the hit only emits the probe (ST_SSS_WAIT), the second one redraws the same numbers and goes on.
+    //    The reservoir draws come from a fork of the engine (tag 3): their number depends on the traversal order of the
+    //    reference's binary BVH, so no stream alignment with the reference survives this branch anyway.
+    const V3 cur_d = rd;                                             // currentRay.direction: what fogContribution keeps seeing
+    V3 sd = rd;                                                      // rayDirection
+    V3 subsW = v3(1, 1, 1);
+    bool sub_interaction = false;
+    if (sc.has_sss) {
+        const bool is_subsurface = (double)norm2(s.Ksub) > 1E-8;
+        const float subsProba = (hadSS || !is_subsurface) ? 0.f : 0.6f;
+        const float inv1M = 1.f / (1.f - subsProba);
+        subsW = v3(inv1M, inv1M, inv1M);
+        if (is_subsurface && pcg32_uniform(e) < subsProba) {
+            sub_interaction = true;
+            const float invp = 1.f / subsProba;
+            subsW = v3(invp, invp, invp);
+            const float sigmasub = 1.5f;
+            const float diskR = sqrtf(12.46f) * sigmasub;
+            const float integ = 1.f - expf(-diskR * diskR / (2.f * sigmasub * sigmasub));
+            const float randR = sigmasub * sqrtf(-2.f * logf(1.f - pcg32_uniform(e) * integ));
+            const float randangle = pcg32_uniform(e) * 2.f * PTB_PI_F;
+            const float g0 = randR * sinf(randangle), g1 = randR * cosf(randangle), g2 = randR;
+            const float gaussval = (float)((1. / (double)(sigmasub * sigmasub * 2.f * PTB_PI_F)) * (double)expf(-(g2 * g2) / (2.f * sigmasub * sigmasub)));
+            const float pdfgauss = gaussval / integ;
+            const V3 N0 = s.N, P0 = s.P;
+            const V3 Tg = get_tangent(N0), Tg2 = cross(N0, Tg);
+            const V3 above = P0 + g0 * Tg + g1 * Tg2 + N0 * diskR;
+            const float r1 = pcg32_uniform(e);
+            V3 axis = -N0;
+            float tmax, wAxis;
+            const float h = sqrtf(diskR * diskR - g2 * g2);
+            V3 so = above + (diskR - h) * (-N0);
+            if (r1 < 0.5f) { wAxis = 0.5f; tmax = 2.f * h; }
+            else {
+                wAxis = 0.25f; tmax = 2.f * g2;
+                axis = r1 < 0.75f ? Tg : Tg2;
+                const float r2 = pcg32_uniform(e);
+                if (r2 < 0.5f) so = so - h * N0;
+            }
+            if (!(st & ST_SSS_WAIT)) {
+                out.probe = true;
+                out.probe_o.x = so.x; out.probe_o.y = so.y; out.probe_o.z = so.z; out.probe_o.w = tmax;
+                out.probe_d.x = axis.x; out.probe_d.y = axis.y; out.probe_d.z = axis.z; out.probe_d.w = u2f((uint32_t)path);
+                const uint64_t fs = pcg32_fork(e, 3);
+                out.probe_x.x = u2f((uint32_t)fs); out.probe_x.y = u2f((uint32_t)(fs >> 32)); out.probe_x.z = u2f((uint32_t)s.object); out.probe_x.w = 0;
+                reinterpret_cast<uint32_t*>(p.weight + path)[3] |= ST_SSS_WAIT;
+                return;                                              // nothing of this visit is kept: the second visit redraws from p.rng
+            }
+            const F4 h2 = p.hit2[path];
+            const int32_t prim2 = (int32_t)f2u(h2.w);
+            if (prim2 >= 0) {
+                Hit hh; hh.t = h2.x; hh.b1 = h2.y; hh.b2 = h2.z; hh.prim = prim2;
+                Surface s2;
+                surface_from_hit(sc, so, axis, hh, prim2, s2);
+                const float chris = (float)exp(-(double)norm2(P0 - s2.P) / (2. * (double)sigmasub * (double)sigmasub));
+                const float a0 = dot(s2.N, N0), a1 = dot(s2.N, Tg), a2 = dot(s2.N, Tg2);
+                const float sumpdfs = (float)((0.5 * a0) * (0.5 * a0) + (0.25 * a1) * (0.25 * a1) + (0.25 * a2) * (0.25 * a2));
+                const float pdfdisk = wAxis * fabsf(dot(axis, s2.N)) / sumpdfs;
+                subsW = subsW * (pdfdisk / fmaxf(pdfgauss, 0.05f) * chris);
+                sd = normalize(s2.P - P0);
+                subsW = subsW * (r1 < 0.5f ? 2.f : 4.f);
+                subsW = subsW * (s.Ksub / PTB_PI_F);
+                const V3 newP = s2.P + 0.005f * s2.N;
+                s = s2;
+                s.P = newP;
+            }
+        }
+    }
     const V3 N = s.N, P = s.P;
     V3 no, nd, nw = w;
     uint32_t nstate;
     if (ob.flags & FLAG_MIRROR) {                                    // 413-436
-        nd = reflect(rd, N);
+        nd = reflect(sd, N);
         no = P + 0.001f * N;
-        if (has_fog) nw = w * fog_sample(sc, ro, rd, sc.centerLight, t, w, st_fogchild, e, out.fog);
+        if (has_fog) nw = w * fog_sample(sc, ro, cur_d, sc.centerLight, t, w, st_fogchild, e, out.fog);
         nstate = st_next | (show_lights ? ST_SHOW_LIGHTS : 0u) | ST_SHOW_ENV;
     } else if (s.transp) {                                           // 438-489
         float n1 = 1.f, n2 = s.refr_index;
         V3 Nt = N;
         bool entering = true;
-        if (dot(rd, N) > 0) { n1 = s.refr_index; n2 = 1; Nt = -N; entering = false; }
-        const float c0 = dot(Nt, rd);
+        if (dot(sd, N) > 0) { n1 = s.refr_index; n2 = 1; Nt = -N; entering = false; }
+        const float c0 = dot(Nt, sd);
         const float radical = 1.f - (n1 / n2) * (n1 / n2) * (1.f - c0 * c0);
         if (radical > 0) {
-            const V3 refr = (n1 / n2) * (rd - dot(rd, Nt) * Nt) - Nt * sqrtf(radical);
+            const V3 refr = (n1 / n2) * (sd - dot(sd, Nt) * Nt) - Nt * sqrtf(radical);
             const float r0 = (n1 - n2) / (n1 + n2);
             const float R0 = r0 * r0;
             float R;
-            if (entering) R = R0 + (1 - R0) * powf(1.f + dot(rd, N), 5.f);
+            if (entering) R = R0 + (1 - R0) * powf(1.f + dot(sd, N), 5.f);
             else R = R0 + (1 - R0) * powf(1.f - dot(refr, N), 5.f);
             const float u = pcg32_uniform(e);
-            if (u < R) { no = P + 0.001f * Nt; nd = reflect(rd, N); }
+            if (u < R) { no = P + 0.001f * Nt; nd = reflect(sd, N); }
             else { no = P - 0.001f * Nt; nd = refr; }
         } else {
-            no = P + 0.001f * Nt; nd = reflect(rd, N);
+            no = P + 0.001f * Nt; nd = reflect(sd, N);
         }
-        if (has_fog) nw = w * fog_sample(sc, ro, rd, sc.centerLight, t, w, st_fogchild, e, out.fog);
+        if (has_fog) nw = w * fog_sample(sc, ro, cur_d, sc.centerLight, t, w, st_fogchild, e, out.fog);
         nstate = st_next | (show_lights ? ST_SHOW_LIGHTS : 0u) | ST_SHOW_ENV;
     } else {                                                         // opaque, 490-649
         const bool ghost = (ob.flags & FLAG_GHOST) != 0;
@@ -832,32 +910,33 @@ PTB_HD void shade_branch_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, 
         V3 direct = v3(0, 0, 0);
         if (!shadowed) {
             if (ghost) {                                             // 522-537: straight through the ghost, same depth, same flags
-                const V3 offset = dot(N, rd) > 0 ? N : -N;
-                const V3 go = P + rd * 0.001f + offset * 0.001f;
+                const V3 offset = dot(N, sd) > 0 ? N : -N;
+                const V3 go = P + sd * 0.001f + offset * 0.001f;
                 out.ghost.want = true;
                 out.ghost.o.x = go.x; out.ghost.o.y = go.y; out.ghost.o.z = go.z; out.ghost.o.w = 0;
-                out.ghost.d.x = rd.x; out.ghost.d.y = rd.y; out.ghost.d.z = rd.z; out.ghost.d.w = 0;
+                out.ghost.d.x = sd.x; out.ghost.d.y = sd.y; out.ghost.d.z = sd.z; out.ghost.d.w = 0;
                 out.ghost.w.x = w.x; out.ghost.w.y = w.y; out.ghost.w.z = w.z;
                 out.ghost.w.w = u2f((uint32_t)depth | hadSS | (show_lights ? ST_SHOW_LIGHTS : 0u) | (show_envmap ? ST_SHOW_ENV : 0u) | (2u << ST_KIND_SHIFT));
                 out.ghost.rng = pcg32_fork(e, 2);
                 out.ghost_pending = pending;
             } else {
                 V3 fr;
-                if (MERL && ob.brdf == 1) fr = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, wi, -rd, N);
-                else fr = phong_eval(s.Kd, s.Ks, s.Ne, wi, -rd, N);
+                if (sub_interaction) fr = s.Ksub / PTB_PI_F;
+                else if (MERL && ob.brdf == 1) fr = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, wi, -sd, N);
+                else fr = phong_eval(s.Kd, s.Ks, s.Ne, wi, -sd, N);
                 const float J = dot(dirl, -wi) / d2;
 #if defined(__CUDA_ARCH__)
                 const float proba = dot(axeOP, dirl) / (PTB_PI_F * (sc.radiusLight * sc.radiusLight));
 #else
                 const float proba = (float)((double)dot(axeOP, dirl) / (PTB_PI_D * (double)(sc.radiusLight * sc.radiusLight)));
 #endif
-                if (proba > 0.f) direct = (sc.lightPower * fmaxf(0.f, dot(N, wi)) * J / proba) * fr;
+                if (proba > 0.f) direct = (subsW * (sc.lightPower * fmaxf(0.f, dot(N, wi)) * J / proba)) * fr;
             }
         }
         float att = 1.f;
         // (with a ghost hit the reference hands fogContribution the straight-through ray, i.e. samples the medium BEHIND the
         //  surface over the distance in front of it, Raytracer.cpp:529, 556; the incoming ray is used here)
-        if (has_fog) att = fog_sample(sc, ro, rd, xl, t, w, st_fogchild, e, out.fog);
+        if (has_fog) att = fog_sample(sc, ro, cur_d, xl, t, w, st_fogchild, e, out.fog);
         const V3 c = (w * att) * direct;
         if (!shadowed && !ghost) {
             if (pending) {
@@ -880,18 +959,23 @@ PTB_HD void shade_branch_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, 
         float pdf;
         V3 dir;
         bool diffuse = false;
-        if (MERL && ob.brdf == 1) {
+        if (sub_interaction) {                                       // 598-601
+            dir = random_cos(N, r1, r2);
+            pdf = dot(N, dir) / PTB_PI_F;
+            diffuse = true;
+        } else if (MERL && ob.brdf == 1) {
             dir = random_cos(N, r1, r2);
             pdf = (float)((double)dot(N, dir) / PTB_PI_D);
         } else {
             const float u = pcg32_uniform(e);
-            dir = phong_sample(s.Ks, s.Ne, -rd, N, r1, r2, u, pdf, diffuse);
+            dir = phong_sample(s.Ks, s.Ne, -sd, N, r1, r2, u, pdf, diffuse);
         }
-        if (dot(dir, N) < 0 || dot(dir, reflect(rd, N)) < 0 || pdf <= 0) return;
+        if (dot(dir, N) < 0 || dot(dir, reflect(sd, N)) < 0 || pdf <= 0) return;
         V3 fi;
-        if (MERL && ob.brdf == 1) fi = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, dir, -rd, N);
-        else fi = phong_eval(s.Kd, s.Ks, s.Ne, dir, -rd, N);
-        nw = (w * fi) * (dot(N, dir) / pdf);
+        if (sub_interaction) fi = s.Ksub / PTB_PI_F;
+        else if (MERL && ob.brdf == 1) fi = merl_eval(sc.merl + (size_t)ob.merl * 3 * PTB_MERL_N, dir, -sd, N);
+        else fi = phong_eval(s.Kd, s.Ks, s.Ne, dir, -sd, N);
+        nw = ((w * subsW) * fi) * (dot(N, dir) / pdf);
         if (ghost && sc.bgW > 0) nw = nw * (background_at(sc, f, pix) / 196964.699f);   // 614-621
         if (has_fog) nw = att * nw;
         no = P + 0.01f * dir;
@@ -899,7 +983,7 @@ PTB_HD void shade_branch_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, 
         // showenvmap of the continuation (626, 629): a ghost passes the dome on only below a blocked shadow ray; when the BVH
         // still has to answer, "blocked" is assumed here and the any-hit kernel clears the bit for an unoccluded ray
         const bool nenv = !ghost || (show_envmap && diffuse && (shadowed || pending));
-        nstate = st_next | (nenv ? ST_SHOW_ENV : 0u);
+        nstate = st_next | (nenv ? ST_SHOW_ENV : 0u) | (sub_interaction ? (uint32_t)ST_HAD_SS : 0u);
     }
     p.rng[path] = e.state;
     if (depth - 1 == 0 || norm2(nw) < 0.01f * 0.01f) return;         // 240-241 of the next iteration
@@ -912,6 +996,35 @@ PTB_HD void shade_branch_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, 
     q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
     out.base.cont = true;
 }
+// Scene::get_random_intersection restricted to one TriMesh (Geometry.cpp:339-472, TriangleMesh.cpp:1321-1424): a uniformly random
+// one of the object's intersections with 0 <= t < tmax, by reservoir sampling in (this BVH's) traversal order.
+struct ReservoirPick {
+    const SceneDev* sc;
+    int32_t obj;
+    Pcg32 e;
+    int count;
+    Hit best;
+    PTB_HD void operator()(int32_t prim, float t, float b1, float b2) {
+        if ((sc->tri_uv[prim].object_has_uv & 0x7fffffff) != obj) return;
+        count++;
+        const float r1 = pcg32_uniform(e);
+        if ((double)r1 < 1. / (double)count) { best.t = t; best.b1 = b1; best.b2 = b2; best.prim = prim; }
+    }
+};
+PTB_HD void probe_one(const SceneDev& sc, PoolDev& p, int entry) {
+    const F4 o = p.probe_o[entry], d = p.probe_d[entry], x = p.probe_x[entry];
+    ReservoirPick pick;
+    pick.sc = &sc; pick.obj = (int32_t)f2u(x.z); pick.count = 0;
+    pick.e.state = (uint64_t)f2u(x.x) | ((uint64_t)f2u(x.y) << 32); pick.e.inc = (3ULL << 1) | 1ULL;
+    pick.best.t = 0; pick.best.b1 = 0; pick.best.b2 = 0; pick.best.prim = -1;
+    if (sc.has_mesh && o.w > 0.f) {
+        const AlphaCtx ac = alpha_ctx(sc);
+        traverse_all(sc.nodes, sc.tris, &ac, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, pick);
+    }
+    F4 q; q.x = pick.best.t; q.y = pick.best.b1; q.z = pick.best.b2; q.w = u2f((uint32_t)pick.best.prim);
+    p.hit2[f2u(d.w)] = q;
+}
+
 // Store a side branch in pool slot `slot` (the kernel / host loop allocated it) and give its ray the analytic hit record.
 PTB_HD void store_child(const SceneDev& sc, PoolDev& p, uint32_t slot, const ChildOut& ch, uint32_t root, uint32_t pix) {
     p.ray_o[slot] = ch.o; p.ray_d[slot] = ch.d; p.weight[slot] = ch.w;

@@ -143,11 +143,15 @@ int HostScene::set_group_material(int obj, int group, const ptb_material* m, std
     HostObject& o = objects[obj];
     if ((int)o.groups.size() <= group) o.groups.resize(group + 1);
     HostMaterial& g = o.groups[group];
-    if ((m->present & PTB_SLOT_KSUB) && (m->Ksub.texels || m->Ksub.mult[0] * m->Ksub.mult[0] + m->Ksub.mult[1] * m->Ksub.mult[1] + m->Ksub.mult[2] * m->Ksub.mult[2] > 1E-8f)) {
-        err = "set_group_material: subsurface scattering (Ksub != 0, Raytracer.cpp:318-406) is not built";   // a zero Ksub is the reference default
+    const bool ksub = (m->present & PTB_SLOT_KSUB) && ((m->Ksub.texels && m->Ksub.W > 0) || m->Ksub.mult[0] * m->Ksub.mult[0] + m->Ksub.mult[1] * m->Ksub.mult[1] + m->Ksub.mult[2] * m->Ksub.mult[2] > 1E-8f);
+    if (ksub && o.type != OBJ_MESH) {
+        // Sphere::reservoir_sampling_intersection returns true without a point or a material (Geometry.h:994-1012): the subsurface
+        // branch is only defined on triangle meshes
+        err = "set_group_material: subsurface scattering (Ksub != 0) is only defined for triangle meshes";
         return PTB_ERR_UNSUPPORTED;
     }
     g.present |= m->present & ~(uint32_t)PTB_SLOT_KSUB;
+    if (ksub) { g.present |= PTB_SLOT_KSUB; take_tex(g.Ksub, m->Ksub); }   // a zero Ksub is the reference default: slot left absent
     if (m->present & PTB_SLOT_KD) take_tex(g.Kd, m->Kd);
     if (m->present & PTB_SLOT_KS) take_tex(g.Ks, m->Ks);
     if (m->present & PTB_SLOT_NE) take_tex(g.Ne, m->Ne);
@@ -211,6 +215,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
             m.Kd = put_tex(g.Kd, out.texels); m.Ks = put_tex(g.Ks, out.texels); m.Ne = put_tex(g.Ne, out.texels);
             m.transp = put_tex(g.transp, out.texels); m.refr = put_tex(g.refr, out.texels);
             m.normal = put_tex(g.normal, out.texels); m.alpha = put_tex(g.alpha, out.texels);
+            if (g.present & SLOT_KSUB) { m.Ksub = put_tex(g.Ksub, out.texels); out.has_sss = true; }
             out.materials.push_back(m);
             d.slot_mask |= (int32_t)g.present;
         }

@@ -214,4 +214,20 @@ def config_fog(lib, W=128, H=128, spp=16, nv=24, device=0, fog_type=0, phase=0, 
     return rt
 
 
+def config_sss(lib, W=128, H=128, spp=16, nv=24, device=0, mixed=True):
+    """Subsurface scattering (Raytracer.cpp:318-406) on a torus: Ksub drives the below-surface random walk step; a second,
+    ordinary Phong torus and a mirror sphere share the scene when `mixed`."""
+    rt = base(lib, W, H, spp, device=device)
+    m = _place_like_gui(TriMesh(*displaced_torus(nv)))
+    m.set_material(0, **phong((.5, .45, .4), (.1, .1, .1), 30.0, Ksub=Texture((.8, .5, .4))))
+    rt.s.addObject(m)
+    if mixed:
+        m2 = _place_like_gui(TriMesh(*displaced_torus(max(8, nv // 2))), scale=12.0)
+        m2.max_translation = m2.max_translation + np.array([-20, 0, 10], np.float32)
+        m2.set_material(0, **phong((.3, .6, .8), (.2, .2, .2), 50.0))
+        rt.s.addObject(m2)
+        rt.s.addObject(Sphere((18, -21.3, 12), 6, mirror=True))
+    return rt
+
+
 CONFIGS = {"C1": config_C1, "C2": config_C2, "C3": config_C3, "C4": config_C4, "C5": config_C5}

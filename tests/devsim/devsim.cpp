@@ -86,15 +86,17 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     f.spp_pass = p->nrays; f.k0 = x.k_first; f.slot0 = 0; f.n_pixel_slots = f.n_my_tiles * f.tile * f.tile;
     f.box_filter = x.box ? 1 : 0; f.accum_albedo = x.albedo; f.accum_normal = x.normal;
     f.lowres = x.lowres; f.lowresW = (int)ceilf(p->W / 16.f); f.lowresH = (int)ceilf(p->H / 16.f);
-    const bool branch = c->sc.has_fog || c->sc.has_ghost || c->sc.bgW > 0;
+    const bool branch = c->sc.has_fog || c->sc.has_ghost || c->sc.bgW > 0 || c->sc.has_sss;
     const size_t n_roots = (size_t)f.n_pixel_slots * f.spp_pass;
     const size_t P = n_roots * (branch ? (c->sc.has_fog ? ((size_t)1 << std::min(f.nb_bounces, 6)) : 8) : 1);
     std::vector<uint32_t> root(branch ? P : 0);
+    std::vector<F4> probe_o(c->sc.has_sss ? P : 0), probe_d(probe_o.size()), probe_x(probe_o.size()), hit2(probe_o.size());
     std::vector<F4> ray_o(P), ray_d(P), weight(P), radiance(P), hit(P), sh_o(P), sh_d(P), sh_c(P);
     std::vector<uint64_t> rng(P); std::vector<uint32_t> pixel(P), q0, q1;
     std::vector<F4> aov_n(x.albedo ? P : 0), aov_kd(x.albedo ? P : 0);
     PoolDev pool{ray_o.data(), ray_d.data(), weight.data(), radiance.data(), hit.data(), rng.data(), pixel.data(), sh_o.data(), sh_d.data(), sh_c.data(),
-                 x.albedo ? aov_n.data() : nullptr, x.albedo ? aov_kd.data() : nullptr, branch ? root.data() : nullptr};
+                 x.albedo ? aov_n.data() : nullptr, x.albedo ? aov_kd.data() : nullptr, branch ? root.data() : nullptr,
+                 probe_o.data(), probe_d.data(), probe_x.data(), hit2.data()};
     unsigned long long closest = 0, shadow = 0, nodes = 0, tris = 0, samples = 0;
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)n_roots; i++) raygen_one(c->sc, f, pool, (int)i);
@@ -112,8 +114,9 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
                 if (c->sc.has_mesh) extend_one<true>(c->sc, pool, path, &tc);
                 nodes += tc.nodes; tris += tc.tris;
             }
-            for (size_t i = 0; i < q0.size(); i++) {
-                const int path = (int)q0[i];
+            std::vector<uint32_t> visit(q0.begin(), q0.end());
+            for (size_t i = 0; i < visit.size(); i++) {     // hits that emit a subsurface probe are answered and revisited at the end of the list
+                const int path = (int)visit[i];
                 BranchOut out;
                 if (getenv("PTB_DBG") && (f2u(weight[path].w) & 0xffffu)) {
                     const int32_t hid = (int32_t)f2u(hit[path].w);
@@ -136,6 +139,7 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
                     sh_o[ns] = out.base.sh_o; sh_d[ns] = out.base.sh_d; sh_c[ns] = cc; ns++;
                 }
                 if (out.base.shadow_query) shadow++;
+                if (out.probe) { probe_o[0] = out.probe_o; probe_d[0] = out.probe_d; probe_x[0] = out.probe_x; probe_one(c->sc, pool, 0); visit.push_back((uint32_t)path); }
             }
             for (size_t i = 0; i < ns; i++) {
                 TraverseCounters tc{0, 0};

@@ -22,6 +22,12 @@ BRANCH_SCENES = {
     "FOG_E1": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=1, phase=1, **kw),
     "FOG_E2": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=1, phase=2, **kw),
 }
+# the subsurface branch (Raytracer.cpp:318-406): pinned port == reference bit for bit; the CUDA path can only be compared
+# statistically (the reservoir over a probe ray's hits draws in BVH traversal order, parity_cases.case_sss_converged)
+STAT_SCENES = {
+    "SSS": lambda L, **kw: scenes.config_sss(L, 48, 48, 2, **kw),
+    "SSS_ALONE": lambda L, **kw: scenes.config_sss(L, 48, 48, 2, mixed=False, **kw),
+}
 
 def _unit(rng, n):
     v = rng.normal(size=(n, 3))

@@ -100,6 +100,32 @@ def case_branch_converged(test_lib, oracle_lib):
     assert float(np.mean(rel_err(ia, ib) > 1e-3)) <= 0.03
 
 
+def case_sss_converged(test_lib, oracle_lib, spp=64):
+    """Subsurface scattering.  The reference picks the re-emergence point by reservoir sampling over the hits of a probe ray,
+    one draw per hit in the traversal order of ITS binary BVH; a different BVH meets the hits in another order, so the two
+    sides cannot draw the same numbers and the comparison is the north star's converged-image bound: at equal spp the test
+    image is as close to a high-spp oracle image as the oracle's own image of that spp, and the means agree within 2 %."""
+    mk = lambda L: scenes.config_sss(L, 40, 40, spp)
+    hi = mk(oracle_lib).commit()
+    hi.nrays, hi.seed = 1024, 99
+    ref_hi = hi.render_image_nopreviz().copy()
+    a, b = mk(oracle_lib).commit(), mk(test_lib).commit()
+    check_ids(b, a, agree=0.998)
+    ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+    assert np.isfinite(ib).all() and (ib >= 0).all()
+    ea, eb = rrmse(ia, ref_hi), rrmse(ib, ref_hi)
+    assert eb <= 1.15 * ea + 0.01, (ea, eb)
+    assert abs(float(ib.mean()) / float(ref_hi.mean()) - 1) < 0.02
+    # the branch must actually be exercised: without Ksub the image is a different one
+    plain = mk(test_lib)
+    for o in plain.s.objects:
+        for slots in o.materials.values():
+            slots.pop("Ksub", None)
+    ip = plain.commit().render_image_nopreviz()
+    assert rrmse(ip, ref_hi) > 2 * eb
+    assert abs(b.stats["rays_closest"] / a.stats["rays_closest"] - 1) < 0.02
+
+
 def case_branch_passes(test_lib):
     """Splitting a branching render into passes (small contribution pool) must not change the image; an exhausted pool is an error."""
     mk = lambda: scenes.config_fog(test_lib, 40, 24, 3, fog_type=0, phase=2).commit()
@@ -113,6 +139,10 @@ def case_branch_passes(test_lib):
     gi = g.render_image_nopreviz().copy()
     g.set_option(_abi.OPT_POOL_PATHS, 1024)
     assert np.allclose(g.render_image_nopreviz(), gi, rtol=2e-5, atol=1e-3)
+    s1, s2 = scenes.config_sss(test_lib, 40, 24, 3).commit(), scenes.config_sss(test_lib, 40, 24, 3).commit()
+    si = s1.render_image_nopreviz().copy()
+    s2.set_option(_abi.OPT_POOL_PATHS, 1024)
+    assert np.allclose(s2.render_image_nopreviz(), si, rtol=2e-5, atol=1e-3), "subsurface probes draw from per-contribution streams: pass splitting cannot matter"
 
 
 def case_branch_errors(test_lib):

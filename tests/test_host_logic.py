@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 from golden_scenes import BRANCH_SCENES, SCENES
-from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
+from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
                           case_progressive, case_scene, check_ids)
 
 from pathtracer_b200 import _abi, scenes
@@ -47,6 +47,10 @@ def test_branch_scenes_devsim_vs_oracle(devsim, port, name):
 
 def test_branch_converged_devsim(devsim, port):
     case_branch_converged(devsim, port)
+
+
+def test_sss_converged_devsim(devsim, port):
+    case_sss_converged(devsim, port, spp=48)
 
 
 def test_bvh8_against_oracle_on_a_larger_mesh(devsim, port):

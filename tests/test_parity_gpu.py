@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 from golden_scenes import BRANCH_SCENES, SCENES
-from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
+from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
                           case_progressive, case_scene, check_ids, check_images)
 
 from pathtracer_b200 import _abi, scenes
@@ -59,6 +59,10 @@ def test_branch_scenes_gpu_vs_oracle_and_golden(gpu, port, name):
 
 def test_branch_converged_gpu(gpu, port):
     case_branch_converged(gpu, port)
+
+
+def test_sss_converged_gpu(gpu, port):
+    case_sss_converged(gpu, port, spp=96)
 
 
 def test_branch_passes_and_errors_gpu(gpu):
