@@ -181,6 +181,18 @@ int ptb_set_fog(ptb_ctx*, const ptb_fog*);
  * it (614-621). */
 int ptb_set_background(ptb_ctx*, const float* rgb, int W, int H);
 
+/* replaces: Object::{scale,translation,rotation}_keyframes (Geometry.h:313-320; one key of each kind per Object::add_keyframe,
+ * nb_transforms rows each in a .scn) and Scene::current_frame (mainApp.cpp:790).  At ptb_commit every object with keys is placed
+ * by Object::get_scale / get_translation / get_rotation at the current frame (Geometry.h:258-312: clamped outside the keyed
+ * range, linear inside, quaternion Slerp between rotation keys, Vector.h:222-269) exactly like Scene::prepare_render ->
+ * Object::build_matrix(current_frame) (Geometry.cpp:283).  An animation is: set_frame, commit, render, per frame.
+ * values: n x 1 (scale), n x 3 (translation), n x 9 (rotation, row-major Matrix33); n == 0 clears the track. */
+#define PTB_KEY_SCALE        0
+#define PTB_KEY_TRANSLATION  1
+#define PTB_KEY_ROTATION     2
+int ptb_set_keyframes(ptb_ctx*, int obj, int kind, const float* frames, const float* values, int n);
+int ptb_set_frame(ptb_ctx*, float frame);
+
 /* replaces: TriMesh::build_bvh (TriangleMesh.cpp:878-885, 1029-1130) + Scene::prepare_render
  * (Geometry.cpp:280-308): builds the wide BVH over all meshes and uploads the scene to the device. */
 int ptb_commit(ptb_ctx*);

@@ -23,6 +23,8 @@
 #define ptb_set_light          ORC_NAME(set_light)
 #define ptb_set_fog            ORC_NAME(set_fog)
 #define ptb_set_background     ORC_NAME(set_background)
+#define ptb_set_keyframes      ORC_NAME(set_keyframes)
+#define ptb_set_frame          ORC_NAME(set_frame)
 #define ptb_commit             ORC_NAME(commit)
 #define ptb_render             ORC_NAME(render)
 #define ptb_render_accum       ORC_NAME(render_accum)

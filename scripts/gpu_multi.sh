@@ -11,4 +11,4 @@ done
 if [ "${PTB_SINGLE:-1}" = "1" ]; then
   timeout 1200 python bench.py --gpus 1 --steps 2 --warmup 3 --workload C5 --no-cpu-baseline 2>gpurun_out/bench_C5_N1.err | tee gpurun_out/bench_C5_N1.json
 fi
-tail -3 gpurun_out/*.err
+for f in gpurun_out/*.err; do tail -n 3 "$f"; done
