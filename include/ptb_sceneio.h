@@ -93,7 +93,7 @@ typedef struct ptb_scn_object {
     int32_t   type;                   /* PTB_SCN_* */
     char      name[PTB_PATH_MAX];     /* Object::name: the mesh file for meshes */
     int32_t   miroir, ghost, display_edges, interp_normals, flip_normals;
-    int32_t   n_keyframes;            /* nb_transforms; the placement below is evaluated at frame 0 */
+    int32_t   n_keyframes;            /* nb_transforms; the placement below is evaluated at frame 0 (Slerp between rotation keys) */
     ptb_xform xform;                  /* scale, mat_rotation, rotation_center, max_translation */
     int32_t   n_slots[PTB_N_KINDS];   /* length of each slot vector */
     int32_t   is_envmap;  char envmap[PTB_PATH_MAX];  float O[3], R;   /* sphere */
@@ -109,6 +109,10 @@ void ptb_scn_free(ptb_scn*);
 int  ptb_scn_get_header(const ptb_scn*, ptb_scn_header* out);
 int  ptb_scn_get_object(const ptb_scn*, int obj, ptb_scn_object* out);
 int  ptb_scn_get_slot(const ptb_scn*, int obj, int kind, int idx, ptb_slot* out);
+/* The object's keyframe maps (Object::{scale,translation,rotation}_keyframes, Geometry.h:318-320, nb_transforms rows each):
+ * kind = PTB_KEY_SCALE / _TRANSLATION / _ROTATION of ptb200.h, values n x 1 / 3 / 9, frames ascending.  Returns the number of keys
+ * (writes at most `cap`); frames / values may be NULL to query the count. */
+int  ptb_scn_get_keyframes(const ptb_scn*, int obj, int kind, float* frames, float* values, int cap);
 /* replaces: Raytracer::save_scene (Raytracer.cpp:1096-1146) for a parsed scene (round-trip tests, tools). */
 int  ptb_scn_save(const ptb_scn*, const char* path);
 

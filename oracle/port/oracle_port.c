@@ -217,6 +217,8 @@ typedef struct {
     int type, miroir, flip_normals, interp_normals, brdf, ghost;
     const double* merl;
     float scale, rot[9]; vec rc, tr;
+    int nkey[3]; float* kframe[3]; float* kval[3];      /* scale / translation / rotation keyframes (Geometry.h:318-320), frames ascending */
+    float scale_at, rot_at[9]; vec tr_at;               /* the placement at Scene::current_frame (get_scale / get_rotation / get_translation) */
     float trans[12], inv[12], rotm[9];
     slotv slots[S_COUNT];
     vec O; float R, R2; int has_envmap; const uint8_t* envtex; int envW, envH;   /* Sphere */
@@ -232,6 +234,7 @@ struct ptb_ctx {
     uint8_t* env; int envW, envH;
     float intensite_lumiere, envmap_intensity;
     ptb_fog fog; float* bg; int bgW, bgH;      /* Scene::fog_*, Scene::background (Geometry.h:1365-1377) */
+    int current_frame;                          /* Scene::current_frame (an int, Geometry.h:1372) */
     int committed, threads;
     char err[256];
     double ms_build; long long n_tri;
@@ -247,11 +250,56 @@ struct ptb_ctx {
 };
 static char g_err[256];
 
-/* Object::build_matrix (Geometry.h:322-360) */
-static void build_matrix(object* o) {
-    const float* m = o->rot; float mt[9];
+/* Matrix<3,3,float>::toQuaternion / fromQuaternion (Vector.h:104-160), Slerp (Vector.h:222-269) */
+static void mat_to_quat(const float* v, float q[4]) {
+    float m00 = v[0], m01 = v[3], m02 = v[6], m10 = v[1], m11 = v[4], m12 = v[7], m20 = v[2], m21 = v[5], m22 = v[8];
+    float tr = m00 + m11 + m22, qw, qx, qy, qz;
+    if (tr > 0) { float S = (float)(sqrt(tr + 1.0) * 2); qw = (float)(0.25 * S); qx = (m21 - m12) / S; qy = (m02 - m20) / S; qz = (m10 - m01) / S; }
+    else if ((m00 > m11) & (m00 > m22)) { float S = (float)(sqrt(1.0 + m00 - m11 - m22) * 2); qw = (m21 - m12) / S; qx = (float)(0.25 * S); qy = (m01 + m10) / S; qz = (m02 + m20) / S; }
+    else if (m11 > m22) { float S = (float)(sqrt(1.0 + m11 - m00 - m22) * 2); qw = (m02 - m20) / S; qx = (m01 + m10) / S; qy = (float)(0.25 * S); qz = (m12 + m21) / S; }
+    else { float S = (float)(sqrt(1.0 + m22 - m00 - m11) * 2); qw = (m10 - m01) / S; qx = (m02 + m20) / S; qy = (m12 + m21) / S; qz = (float)(0.25 * S); }
+    q[0] = qw; q[1] = qx; q[2] = qy; q[3] = qz;
+}
+static void slerp33(const float* a, const float* b, float t, float* v) {
+    float q1[4], q2[4];
+    mat_to_quat(a, q1); mat_to_quat(b, q2);
+    float w1 = q1[0], x1 = q1[1], y1 = q1[2], z1 = q1[3], w2 = q2[0], x2 = q2[1], y2 = q2[2], z2 = q2[3];
+    if (w1 * w2 + x1 * x2 + y1 * y2 + z1 * z2 < 0) { w2 = -w2; x2 = -x2; y2 = -y2; z2 = -z2; }
+    float theta = acosf(w1 * w2 + x1 * x2 + y1 * y2 + z1 * z2), mult1, mult2;
+    if (theta > 0.000001) { mult1 = sinf((1 - t) * theta) / sinf(theta); mult2 = sinf(t * theta) / sinf(theta); }
+    else { mult1 = 1 - t; mult2 = t; }
+    float w = mult1 * w1 + mult2 * w2, x = mult1 * x1 + mult2 * x2, y = mult1 * y1 + mult2 * y2, z = mult1 * z1 + mult2 * z2;
+    v[0] = w * w + x * x - y * y - z * z; v[1] = (float)(2.0 * x * y + 2.0 * w * z); v[2] = (float)(2.0 * x * z - 2.0 * y * w);
+    v[3] = (float)(2.0 * x * y - 2.0 * w * z); v[4] = w * w - x * x + y * y - z * z; v[5] = (float)(2.0 * y * z + 2.0 * w * x);
+    v[6] = (float)(2.0 * x * z + 2.0 * w * y); v[7] = (float)(2.0 * y * z - 2.0 * w * x); v[8] = w * w - x * x - y * y + z * z;
+}
+/* Object::get_scale / get_translation / get_rotation (Geometry.h:258-312) for track `kind` (width 1 / 3 / 9) */
+static int key_eval(const object* o, int kind, float frame, float* out) {
+    static const int width[3] = {1, 3, 9};
+    int n = o->nkey[kind], w = width[kind];
+    if (n == 0) return 0;
+    const float* fr = o->kframe[kind]; const float* val = o->kval[kind];
+    int up = 0;
+    while (up < n && !(fr[up] > frame)) up++;                          /* upper_bound */
+    if (up == n) { memcpy(out, val + (size_t)(n - 1) * w, w * sizeof(float)); return 1; }
+    if (up == 0) { memcpy(out, val, w * sizeof(float)); return 1; }
+    float t = (frame - fr[up - 1]) / (fr[up] - fr[up - 1]);
+    const float* a = val + (size_t)(up - 1) * w; const float* b = val + (size_t)up * w;
+    if (w == 9) slerp33(a, b, t, out);
+    else if (w == 3) for (int i = 0; i < 3; i++) out[i] = (1 - t) * a[i] + t * b[i];
+    else out[0] = (1.f - t) * a[0] + t * b[0];
+    return 1;
+}
+/* Object::build_matrix(frame) (Geometry.h:322-360) */
+static void build_matrix(object* o, float frame) {
+    o->scale_at = o->scale; memcpy(o->rot_at, o->rot, sizeof(o->rot)); o->tr_at = o->tr;
+    float tv[3];
+    key_eval(o, PTB_KEY_SCALE, frame, &o->scale_at);
+    if (key_eval(o, PTB_KEY_TRANSLATION, frame, tv)) o->tr_at = V(tv[0], tv[1], tv[2]);
+    key_eval(o, PTB_KEY_ROTATION, frame, o->rot_at);
+    const float* m = o->rot_at; float mt[9];
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) mt[j * 3 + i] = m[i * 3 + j];
-    float s = o->scale;
+    float s = o->scale_at;
     for (int i = 0; i < 3; i++) {
         vec v2 = V(m[0 * 3 + i], m[1 * 3 + i], m[2 * 3 + i]);
         o->trans[0 * 4 + i] = v2.x * s; o->trans[1 * 4 + i] = v2.y * s; o->trans[2 * 4 + i] = v2.z * s;
@@ -261,8 +309,8 @@ static void build_matrix(object* o) {
     }
     float b[3] = {-o->rc.x, -o->rc.y, -o->rc.z}, r[3];
     for (int i = 0; i < 3; i++) { float v = 0; for (int j = 0; j < 3; j++) v += m[i * 3 + j] * b[j]; r[i] = v; }
-    o->trans[3] = r[0] * s + o->rc.x + o->tr.x; o->trans[7] = r[1] * s + o->rc.y + o->tr.y; o->trans[11] = r[2] * s + o->rc.z + o->tr.z;
-    vec q = vsub(vneg(o->rc), o->tr);
+    o->trans[3] = r[0] * s + o->rc.x + o->tr_at.x; o->trans[7] = r[1] * s + o->rc.y + o->tr_at.y; o->trans[11] = r[2] * s + o->rc.z + o->tr_at.z;
+    vec q = vsub(vneg(o->rc), o->tr_at);
     float b2[3] = {q.x, q.y, q.z};
     for (int i = 0; i < 3; i++) { float v = 0; for (int j = 0; j < 3; j++) v += mt[i * 3 + j] * b2[j]; r[i] = v; }
     o->inv[3] = r[0] / s + o->rc.x; o->inv[7] = r[1] / s + o->rc.y; o->inv[11] = r[2] / s + o->rc.z;
@@ -751,7 +799,7 @@ static int fog_contribution(const struct ptb_ctx* c, vec ro, vec rd, vec sampleL
     const float p_uniform = 0.5f;
     const int is_uniform_fog = (c->fog.type == 0);
     const float alpha = c->fog.absorption, sigmaT = c->fog.absorption_decay;
-    const float groundLevel = c->objs[2]->tr.y;                            /* objects[2]->get_translation()[1], 54 */
+    const float groundLevel = c->objs[2]->tr_at.y;                         /* objects[2]->get_translation(r.time)[1], 54 */
     float int_ext;
     if (is_uniform_fog) int_ext = (float)(alpha * t * 0.05);
     else int_ext = alpha * int_exponential(ro.y, groundLevel, sigmaT, t, rd.y);
@@ -1045,11 +1093,11 @@ static void prepare_render(struct ptb_ctx* c) {
                 for (int j2 = -fs; j2 <= j; j2++) { float w = (float)(fast_exp(-(i2 * i2 + j2 * j2) / (2. * sg * sg)) / (sg * sg * 2. * M_PI)); integ += w; }
             c->filter_integral[(i + fs) * ftw + (j + fs)] = integ;
         }
-    for (int i = 0; i < c->n_objs; i++) build_matrix(c->objs[i]);
+    for (int i = 0; i < c->n_objs; i++) build_matrix(c->objs[i], (float)c->current_frame);
     const object* L = c->objs[0];
     c->centerLight = xf_point(L->trans, L->O);
-    c->radiusLight = L->scale * L->R;
-    c->lightPower = c->intensite_lumiere / (L->scale * L->scale);
+    c->radiusLight = L->scale_at * L->R;
+    c->lightPower = c->intensite_lumiere / (L->scale_at * L->scale_at);
 }
 
 /* ---- ABI -------------------------------------------------------------------------------------------- */
@@ -1065,6 +1113,7 @@ int ptb_create(int device_id, ptb_ctx** out) {
 }
 static void free_object(object* o) {
     for (int s = 0; s < S_COUNT; s++) { for (int i = 0; i < o->slots[s].n; i++) free(o->slots[s].t[i].values); free(o->slots[s].t); }
+    for (int k = 0; k < 3; k++) { free(o->kframe[k]); free(o->kval[k]); }
     free(o->vertices); free(o->normals); free(o->uvs); free(o->indices); free(o->soup); free(o->tangent_soup); free(o->permuted); free(o->nodes);
     free(o);
 }
@@ -1223,6 +1272,28 @@ int ptb_set_envmap(ptb_ctx* c, const uint8_t* rgb, int W, int H) {
 }
 int ptb_set_light(ptb_ctx* c, float il, float ei) { if (!c) return PTB_ERR_INVALID; c->intensite_lumiere = il; c->envmap_intensity = ei; return PTB_OK; }
 int ptb_set_fog(ptb_ctx* c, const ptb_fog* f) { if (!c || !f) return PTB_ERR_INVALID; c->fog = *f; return PTB_OK; }
+/* the std::map<float, ...> keyframe tracks: ascending frames, a later assignment to the same frame wins */
+int ptb_set_keyframes(ptb_ctx* c, int obj, int kind, const float* frames, const float* values, int n) {
+    static const int width[3] = {1, 3, 9};
+    if (!c || obj < 0 || obj >= c->n_objs || kind < 0 || kind > 2 || n < 0) return PTB_ERR_INVALID;
+    object* o = c->objs[obj]; int w = width[kind];
+    free(o->kframe[kind]); free(o->kval[kind]); o->kframe[kind] = o->kval[kind] = NULL; o->nkey[kind] = 0;
+    if (n == 0) return PTB_OK;
+    o->kframe[kind] = (float*)malloc(n * sizeof(float)); o->kval[kind] = (float*)malloc((size_t)n * w * sizeof(float));
+    int m = 0;
+    for (int i = 0; i < n; i++) {                                       /* insertion into the sorted track */
+        int pos = 0;
+        while (pos < m && o->kframe[kind][pos] < frames[i]) pos++;
+        if (pos < m && o->kframe[kind][pos] == frames[i]) { memcpy(o->kval[kind] + (size_t)pos * w, values + (size_t)i * w, w * sizeof(float)); continue; }
+        memmove(o->kframe[kind] + pos + 1, o->kframe[kind] + pos, (m - pos) * sizeof(float));
+        memmove(o->kval[kind] + (size_t)(pos + 1) * w, o->kval[kind] + (size_t)pos * w, (size_t)(m - pos) * w * sizeof(float));
+        o->kframe[kind][pos] = frames[i]; memcpy(o->kval[kind] + (size_t)pos * w, values + (size_t)i * w, w * sizeof(float));
+        m++;
+    }
+    o->nkey[kind] = m;
+    return PTB_OK;
+}
+int ptb_set_frame(ptb_ctx* c, float frame) { if (!c) return PTB_ERR_INVALID; c->current_frame = (int)frame; return PTB_OK; }
 int ptb_set_background(ptb_ctx* c, const float* rgb, int W, int H) {
     if (!c) return PTB_ERR_INVALID;
     free(c->bg); c->bg = NULL; c->bgW = c->bgH = 0;
@@ -1516,7 +1587,7 @@ int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* ob
     if (!c || !cam || W <= 0 || H <= 0) return PTB_ERR_INVALID;
     if (!c->committed) return PTB_ERR_STATE;
     set_frame(c, cam, W, H);
-    for (int i = 0; i < c->n_objs; i++) build_matrix(c->objs[i]);
+    for (int i = 0; i < c->n_objs; i++) build_matrix(c->objs[i], (float)c->current_frame);
 #pragma omp parallel for schedule(dynamic, 4)
     for (int i = 0; i < H; i++)
         for (int j = 0; j < W; j++) {

@@ -31,6 +31,7 @@ struct ptb_ctx {
     int threads;
     double ms_build;
     long long n_tri;
+    int frame = 0;
 };
 
 static std::string g_create_err;
@@ -214,6 +215,25 @@ int ptb_set_light(ptb_ctx* c, float intensite_lumiere, float envmap_intensity) {
     return PTB_OK;
 }
 
+int ptb_set_keyframes(ptb_ctx* c, int obj, int kind, const float* frames, const float* values, int n) {
+    if (!c || obj < 0 || obj >= (int)c->rt->s.objects.size() || n < 0) return PTB_ERR_INVALID;
+    Object* o = c->rt->s.objects[obj];
+    if (kind == PTB_KEY_SCALE) { o->scale_keyframes.clear(); for (int i = 0; i < n; i++) o->scale_keyframes[frames[i]] = values[i]; }
+    else if (kind == PTB_KEY_TRANSLATION) { o->translation_keyframes.clear(); for (int i = 0; i < n; i++) o->translation_keyframes[frames[i]] = Vector(values[3 * i], values[3 * i + 1], values[3 * i + 2]); }
+    else if (kind == PTB_KEY_ROTATION) {
+        o->rotation_keyframes.clear();
+        for (int i = 0; i < n; i++) { Matrix33 m; for (int k = 0; k < 9; k++) m[k] = values[9 * i + k]; o->rotation_keyframes[frames[i]] = m; }
+    } else return PTB_ERR_INVALID;
+    return PTB_OK;
+}
+
+int ptb_set_frame(ptb_ctx* c, float frame) {
+    if (!c) return PTB_ERR_INVALID;
+    c->frame = (int)frame;            // Scene::current_frame is an int (Geometry.h:1372)
+    c->rt->s.current_frame = c->frame;
+    return PTB_OK;
+}
+
 int ptb_set_fog(ptb_ctx* c, const ptb_fog* f) {
     if (!c || !f) return PTB_ERR_INVALID;
     Scene& s = c->rt->s;
@@ -256,7 +276,7 @@ static int setup_frame(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p) {
     set_camera(rt, cam);
     rt->W = p->W; rt->H = p->H; rt->nrays = p->nrays; rt->nb_bounces = p->nb_bounces;
     rt->sigma_filter = p->sigma_filter; rt->gamma = p->gamma;
-    rt->s.double_frustum_start_t = 0; rt->s.current_frame = 0;
+    rt->s.double_frustum_start_t = 0; rt->s.current_frame = c->frame;
     ptb_ref_global_seed = p->seed;
     int nt = c->threads > 0 ? c->threads : omp_get_num_procs();
     if (nt > 64) nt = 64;  // engine[64], contribsArray[64] (Vector.h:29, Raytracer.h:114-115)
@@ -359,7 +379,7 @@ int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* ob
     if (!c->committed) return PTB_ERR_STATE;
     Raytracer* rt = c->rt;
     set_camera(rt, cam);
-    rt->s.current_frame = 0;
+    rt->s.current_frame = c->frame;
     rt->s.prepare_render(false);
     // the picking query, mainApp.h:686-692
 #pragma omp parallel for schedule(dynamic, 4)
@@ -630,6 +650,17 @@ int ref_scn_get_object(const void* hh, int i, ptb_scn_object* o) {
         o->is_centered = g->is_centered; o->has_csv = g->csv_file.size() != 0; ref_copy_str(o->csv_file, g->csv_file);
     }
     return PTB_OK;
+}
+int ref_scn_get_keyframes(const void* hh, int i, int kind, float* frames, float* values, int cap) {
+    const Raytracer* rt = ((const ptb_ctx*)hh)->rt;
+    if (i < 0 || i >= (int)rt->s.objects.size()) return PTB_ERR_INVALID;
+    const Object* b = rt->s.objects[i];
+    int n = 0;
+    if (kind == PTB_KEY_SCALE) for (std::map<float, float>::const_iterator it = b->scale_keyframes.begin(); it != b->scale_keyframes.end(); ++it, ++n) { if (n < cap) { if (frames) frames[n] = it->first; if (values) values[n] = it->second; } }
+    else if (kind == PTB_KEY_TRANSLATION) for (std::map<float, Vector>::const_iterator it = b->translation_keyframes.begin(); it != b->translation_keyframes.end(); ++it, ++n) { if (n < cap) { if (frames) frames[n] = it->first; if (values) for (int k = 0; k < 3; k++) values[3 * n + k] = it->second[k]; } }
+    else if (kind == PTB_KEY_ROTATION) for (std::map<float, Matrix33>::const_iterator it = b->rotation_keyframes.begin(); it != b->rotation_keyframes.end(); ++it, ++n) { if (n < cap) { if (frames) frames[n] = it->first; if (values) for (int k = 0; k < 9; k++) values[9 * n + k] = it->second[k]; } }
+    else return PTB_ERR_INVALID;
+    return n;
 }
 int ref_scn_get_slot(const void* hh, int i, int kind, int idx, ptb_slot* out) {
     const Raytracer* rt = ((const ptb_ctx*)hh)->rt;

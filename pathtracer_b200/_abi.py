@@ -13,6 +13,7 @@ OK = 0
 SLOT_KD, SLOT_KS, SLOT_NE, SLOT_TRANSP, SLOT_REFR, SLOT_NORMAL, SLOT_ALPHA, SLOT_KSUB = (1 << i for i in range(8))
 OBJ_MIRROR, OBJ_FLIP_NORMALS, OBJ_FLAT_NORMALS, OBJ_GHOST = 1, 2, 4, 8
 BRDF_PHONG, BRDF_MERL = 0, 1
+KEY_SCALE, KEY_TRANSLATION, KEY_ROTATION = 0, 1, 2
 OPT_COUNT_TRAVERSAL, OPT_POOL_PATHS, OPT_TIME_KERNELS, OPT_REFILL_BELOW, OPT_TRACE_BLOCKS, OPT_TRI_FRACTION, OPT_TRI_MIN_PCT = 1, 2, 3, 4, 5, 6, 7
 KERNEL_NAMES = ["raygen", "extend", "shade", "shadow", "splat"]
 ORC_OPT_THREADS = 100
@@ -92,7 +93,7 @@ class KernelTimes(C.Structure):
 
 # every symbol include/ptb200.h declares (tests check the product library exports all of them)
 SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_mesh",
-           "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "set_fog", "set_background", "commit", "render",
+           "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "set_fog", "set_background", "set_keyframes", "set_frame", "commit", "render",
            "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
            "set_option", "get_scene_info", "kat", "get_kernel_times", "render_denoiser_inputs", "progressive_begin", "progressive_pass",
            "progressive_read"]
@@ -132,7 +133,7 @@ class ScnObject(C.Structure):
 
 # every symbol include/ptb_sceneio.h declares
 SCENEIO_SYMBOLS = ["sceneio_last_error", "image_load", "image_free", "texture_load", "meshfile_read", "meshfile_free", "meshfile_get",
-                   "meshfile_group_name", "meshfile_group_slot", "scn_load", "scn_free", "scn_get_header", "scn_get_object", "scn_get_slot",
+                   "meshfile_group_name", "meshfile_group_slot", "scn_load", "scn_free", "scn_get_header", "scn_get_object", "scn_get_slot", "scn_get_keyframes",
                    "scn_save", "load_scene"]
 
 
@@ -160,6 +161,7 @@ class SceneIO:
             "scn_get_header": (C.c_int, [vp, C.POINTER(ScnHeader)]),
             "scn_get_object": (C.c_int, [vp, C.c_int, C.POINTER(ScnObject)]),
             "scn_get_slot": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(Slot)]),
+            "scn_get_keyframes": (C.c_int, [vp, C.c_int, C.c_int, _fp, _fp, C.c_int]),
             "scn_save": (C.c_int, [vp, C.c_char_p]),
             "load_scene": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.POINTER(Camera), C.POINTER(Params)]),
         }
@@ -195,6 +197,8 @@ class Lib:
             "set_light": (C.c_int, [vp, C.c_float, C.c_float]),
             "set_fog": (C.c_int, [vp, C.POINTER(Fog)]),
             "set_background": (C.c_int, [vp, _fp, C.c_int, C.c_int]),
+            "set_keyframes": (C.c_int, [vp, C.c_int, C.c_int, _fp, _fp, C.c_int]),
+            "set_frame": (C.c_int, [vp, C.c_float]),
             "commit": (C.c_int, [vp]),
             "render": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), _fp, _fp, C.POINTER(C.c_uint8), C.POINTER(Stats)]),
             "render_accum": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), vp, C.POINTER(Stats)]),

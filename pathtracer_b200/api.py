@@ -119,6 +119,15 @@ class Object:
         self.materials = {}                    # group -> {slot name: Texture}
         self.ghost = False
         self.name = ""
+        # Object::{scale,translation,rotation}_keyframes (Geometry.h:318-320): frame -> value, like the reference's std::maps
+        self.scale_keyframes, self.translation_keyframes, self.rotation_keyframes = {}, {}, {}
+
+    def add_keyframe(self, frame):
+        """Object::add_keyframe (Geometry.h:313-317): the current placement becomes the key of `frame`."""
+        self.rotation_keyframes[float(frame)] = np.array(self.mat_rotation, np.float32).reshape(3, 3).copy()
+        self.translation_keyframes[float(frame)] = np.array(self.max_translation, np.float32).copy()
+        self.scale_keyframes[float(frame)] = float(self.scale)
+        return self
 
     def set_material(self, group=0, **slots):
         """e.g. set_material(0, Kd=Texture((.5,.5,.5)), Ks=Texture(.2), Ne=Texture(50))"""
@@ -210,6 +219,7 @@ class Scene:
         self.fog_density = self.fog_absorption = self.fog_density_decay = self.fog_absorption_decay = 0.0
         self.fog_type = self.fog_phase_type = 0
         self.phase_aniso = 0.0
+        self.current_frame = 0                 # Scene::current_frame (an int, Geometry.h:1372)
         self.background = None                 # (H,W,3) uint8 as load_image returns it, or None
         self.background_gamma = 2.2            # the `gamma` argument of Scene::load_background (Geometry.h:1355-1363)
         self.background_values = None          # (H,W,3) float32 in Scene::background scale; overrides `background` when set
@@ -307,6 +317,15 @@ class Raytracer:
                 obj.mat_rotation = np.array(o.xform.rotation, np.float32).reshape(3, 3)
                 obj.rotation_center = tuple(o.xform.rotation_center)
                 obj.max_translation = np.array(o.xform.translation, np.float32)
+                if o.n_keyframes > 0:      # the three keyframe maps (Geometry.h:544-567)
+                    for kind, width, store in ((_abi.KEY_SCALE, 1, obj.scale_keyframes), (_abi.KEY_TRANSLATION, 3, obj.translation_keyframes),
+                                               (_abi.KEY_ROTATION, 9, obj.rotation_keyframes)):
+                        n = io.scn_get_keyframes(h, i, kind, None, None, 0)
+                        fr, val = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1) * width, np.float32)
+                        io.scn_get_keyframes(h, i, kind, fptr(fr), fptr(val), n)
+                        for k in range(n):
+                            v = val[k * width:(k + 1) * width]
+                            store[float(fr[k])] = float(v[0]) if width == 1 else (v.copy() if width == 3 else v.reshape(3, 3).copy())
                 for kind, slot_name in _KIND_NAMES.items():
                     for g in range(o.n_slots[kind]):
                         sl = _abi.Slot()
@@ -328,6 +347,7 @@ class Raytracer:
         self._ctx = ctx
         cam, p = _abi.Camera(), _abi.Params()
         io.check(io.load_scene(ctx, str(filename).encode(), replacedNames.encode() if replacedNames else None, C.byref(cam), C.byref(p)))
+        L.check(L.set_frame(ctx, float(int(self.s.current_frame))), ctx)
         self.W, self.H, self.nrays, self.nb_bounces = p.W, p.H, p.nrays, p.nb_bounces
         self.sigma_filter, self.gamma = float(p.sigma_filter), float(p.gamma)
         self.cam = Camera(tuple(cam.position), tuple(cam.direction), tuple(cam.up))
@@ -381,6 +401,12 @@ class Raytracer:
                 L.check(L.add_mesh(ctx, C.byref(m), C.byref(xf), o._flags(), C.byref(oid)), ctx)
             else:
                 raise TypeError(type(o))
+            for kind, keys, width in ((_abi.KEY_SCALE, o.scale_keyframes, 1), (_abi.KEY_TRANSLATION, o.translation_keyframes, 3),
+                                      (_abi.KEY_ROTATION, o.rotation_keyframes, 9)):
+                if keys:
+                    fr = f32(sorted(keys))
+                    val = f32(np.stack([np.asarray(keys[k], np.float32).reshape(width) for k in sorted(keys)]))
+                    L.check(L.set_keyframes(ctx, oid.value, kind, fptr(fr), fptr(val), len(fr)), ctx)
             for group, slots in sorted(o.materials.items()):
                 mat = _abi.Material()
                 for name, bit in _SLOTS:
@@ -403,6 +429,7 @@ class Raytracer:
             L.check(L.set_envmap(ctx, env.ctypes.data_as(C.POINTER(C.c_uint8)), env.shape[1], env.shape[0]), ctx)
         L.check(L.set_light(ctx, float(self.s.intensite_lumiere), float(self.s.envmap_intensity)), ctx)
         s = self.s
+        L.check(L.set_frame(ctx, float(int(s.current_frame))), ctx)
         if s.fog_density > 0:
             fog = _abi.Fog(float(s.fog_density), float(s.fog_absorption), float(s.fog_density_decay), float(s.fog_absorption_decay),
                            int(s.fog_type), int(s.fog_phase_type), float(s.phase_aniso))

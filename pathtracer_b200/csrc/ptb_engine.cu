@@ -654,6 +654,22 @@ int ptb_set_light(ptb_ctx* c, float intensite_lumiere, float envmap_intensity) {
     return PTB_OK;
 }
 
+int ptb_set_keyframes(ptb_ctx* c, int obj, int kind, const float* frames, const float* values, int n) {
+    if (!c || obj < 0 || obj >= (int)c->host.objects.size() || kind < PTB_KEY_SCALE || kind > PTB_KEY_ROTATION || n < 0 || (n > 0 && (!frames || !values))) {
+        if (c) c->err = "set_keyframes: bad object, kind or arrays";
+        return PTB_ERR_INVALID;
+    }
+    static const int width[3] = {1, 3, 9};
+    key_track_set(c->host.objects[obj].keys[kind], frames, values, n, width[kind]);
+    return PTB_OK;
+}
+
+int ptb_set_frame(ptb_ctx* c, float frame) {
+    if (!c) return PTB_ERR_INVALID;
+    c->host.current_frame = frame;
+    return PTB_OK;
+}
+
 int ptb_set_fog(ptb_ctx* c, const ptb_fog* fog) {
     if (!c || !fog) return PTB_ERR_INVALID;
     if (fog->type < 0 || fog->type > 1 || fog->phase_type < 0 || fog->phase_type > 2) { c->err = "set_fog: fog_type is 0..1, fog_phase_type 0..2"; return PTB_ERR_INVALID; }

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/ptb200.h"
+#include "ptb_keyframes.h"
 #include "ptb_scene.h"
 
 namespace ptb {
@@ -35,7 +36,17 @@ struct HostObject {
     std::vector<float> vertices, normals, uvs, tangents;   // tangents: per vertex
     std::vector<int32_t> tri;              // n x 10
     float trans[12], inv_trans[12], rot[9];
+    KeyTrack keys[3];                      // PTB_KEY_SCALE / _TRANSLATION / _ROTATION (Geometry.h:318-320)
 };
+
+// The object's placement at `frame`: keyed tracks replace the static fields (Object::build_matrix(frame), Geometry.h:322-328)
+inline ptb_xform placement_at(const HostObject& o, float frame) {
+    ptb_xform x = o.xf;
+    key_eval(o.keys[PTB_KEY_SCALE], frame, &x.scale);
+    key_eval(o.keys[PTB_KEY_TRANSLATION], frame, x.translation);
+    key_eval(o.keys[PTB_KEY_ROTATION], frame, x.rotation);
+    return x;
+}
 
 // Everything ptb_commit produces, ready to upload.
 struct FlatScene {
@@ -64,6 +75,7 @@ struct HostScene {
     ptb_fog fog = {0, 0, 0, 0, 0, 0, 0};            // Scene::fog_* (Geometry.h:1371-1377)
     std::vector<float> background;                  // Scene::background (Geometry.h:1365), bgW*bgH*3
     int bgW = 0, bgH = 0;
+    float current_frame = 0;                        // Scene::current_frame
 
     int add_sphere(const float O[3], float R, const ptb_xform* xf, int flags);
     int add_plane(const float A[3], const float N[3], const ptb_xform* xf, int flags);
@@ -105,7 +117,7 @@ inline int scene_modes(SceneDev& sc, const HostScene& h, std::string& err) {
     sc.fog.type = h.fog.type; sc.fog.phase_type = h.fog.phase_type; sc.fog.ground = 0;
     if (sc.has_fog) {
         if (h.objects.size() < 3) { err = "fog needs object 2 (its translation is the ground level, Raytracer.cpp:54)"; return PTB_ERR_STATE; }
-        sc.fog.ground = h.objects[2].xf.translation[1];
+        sc.fog.ground = placement_at(h.objects[2], h.current_frame).translation[1];   // get_translation(r.time)[1], r.time = current_frame
     }
     sc.bgW = h.bgW; sc.bgH = h.bgH; sc.background = nullptr;
     return PTB_OK;

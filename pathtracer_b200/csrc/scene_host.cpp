@@ -203,7 +203,10 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
     out = FlatScene();
     int64_t n_tri = 0;
     for (auto& o : objects) {
+        const ptb_xform static_xf = o.xf;
+        o.xf = placement_at(o, current_frame);          // Scene::prepare_render -> build_matrix(current_frame) (Geometry.cpp:283)
         build_matrix(o);
+        o.xf = static_xf;
         ObjectDev d;
         memset(&d, 0, sizeof(d));
         d.type = o.type; d.flags = o.flags; d.brdf = o.brdf; d.merl = o.merl;
@@ -233,8 +236,9 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
         const HostObject& L = objects[0];
         const V3 c = xf_point(L.trans, v3(L.a[0], L.a[1], L.a[2]));
         out.centerLight[0] = c.x; out.centerLight[1] = c.y; out.centerLight[2] = c.z;
-        out.radiusLight = L.xf.scale * L.R;
-        out.lightPower = intensite_lumiere / (L.xf.scale * L.xf.scale);
+        const float lum_scale = placement_at(L, current_frame).scale;     // s.lumiere->get_scale(time) (Raytracer.cpp:1378)
+        out.radiusLight = lum_scale * L.R;
+        out.lightPower = intensite_lumiere / (lum_scale * lum_scale);
         out.envmap_intensity = envmap_intensity;
     }
     out.envmap = envmap; out.envW = envW; out.envH = envH;

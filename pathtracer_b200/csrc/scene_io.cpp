@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/ptb_sceneio.h"
+#include "ptb_keyframes.h"
 
 namespace {
 
@@ -546,21 +547,17 @@ namespace {
 
 #define NEED(cond, what) do { if (!(cond)) return fail(PTB_ERR_INVALID, std::string("scn: expected ") + what + " near line " + std::to_string(L.pos)); } while (0)
 
-// key-framed placement evaluated at frame 0 (Object::get_translation / get_scale / get_rotation, Geometry.h:258-312)
-template <class V>
-int key_at0(const std::vector<std::pair<float, V>>& keys, V& out, bool& interp, float& t, V& a, V& b) {
-    interp = false;
-    if (keys.empty()) return 0;
-    std::vector<std::pair<float, V>> k = keys;
-    std::stable_sort(k.begin(), k.end(), [](const std::pair<float, V>& x, const std::pair<float, V>& y) { return x.first < y.first; });
-    size_t up = 0;
-    while (up < k.size() && !(k[up].first > 0.f)) up++;          // upper_bound(0)
-    if (up == k.size()) { out = k.back().second; return 1; }
-    if (up == 0) { out = k[0].second; return 1; }
-    interp = true;
-    t = (0.f - k[up - 1].first) / (k[up].first - k[up - 1].first);
-    a = k[up - 1].second; b = k[up].second;
-    return 1;
+// the three keyframe maps of an object as tracks (ptb_keyframes.h): 0 scale, 1 translation, 2 rotation
+static void keys_to_tracks(const Keyframes& k, ptb::KeyTrack tr[3]) {
+    std::vector<float> fr, val;
+    for (auto& e : k.scale) { fr.push_back(e.first); val.push_back(e.second); }
+    ptb::key_track_set(tr[0], fr.data(), val.data(), (int)fr.size(), 1);
+    fr.clear(); val.clear();
+    for (auto& e : k.translation) { fr.push_back(e.first); val.insert(val.end(), e.second.begin(), e.second.end()); }
+    ptb::key_track_set(tr[1], fr.data(), val.data(), (int)fr.size(), 3);
+    fr.clear(); val.clear();
+    for (auto& e : k.rotation) { fr.push_back(e.first); val.insert(val.end(), e.second.begin(), e.second.end()); }
+    ptb::key_track_set(tr[2], fr.data(), val.data(), (int)fr.size(), 9);
 }
 
 int parse_slots(Lines& L, std::string& s, ScnObject& so, int kind, const char* count_key, bool line_in_s) {
@@ -647,15 +644,12 @@ int parse_object_common(Lines& L, ScnObject& so, const char* replaced) {
     if ((rc = parse_slots(L, s, so, PTB_KIND_TRANSP, "nb_transpmaps:", false))) return rc;
     if ((rc = parse_slots(L, s, so, PTB_KIND_REFR, "nb_refrindexmaps:", false))) return rc;
     for (int k = 0; k < PTB_N_KINDS; k++) o.n_slots[k] = (int32_t)so.slots[k].size();
-    // key-framed placement replaces the static one when keys exist (Geometry.h:258-312), evaluated at frame 0
-    bool interp; float t = 0, sa = 0, sb = 0, sv = 0;
-    if (key_at0(so.keys.scale, sv, interp, t, sa, sb)) o.xform.scale = interp ? (1.f - t) * sa + t * sb : sv;
-    std::vector<float> va, vb, vv;
-    if (key_at0(so.keys.translation, vv, interp, t, va, vb)) for (int k = 0; k < 3; k++) tr[k] = interp ? (1 - t) * va[k] + t * vb[k] : vv[k];
-    if (key_at0(so.keys.rotation, vv, interp, t, va, vb)) {
-        if (interp) return fail(PTB_ERR_UNSUPPORTED, "scn: rotation keyframes straddling frame 0 (needs Slerp) are not evaluated");
-        for (int k = 0; k < 9; k++) r[k] = vv[k];
-    }
+    // key-framed placement replaces the static one when keys exist (Geometry.h:258-312); ptb_scn_object reports it at frame 0
+    ptb::KeyTrack tracks[3];
+    keys_to_tracks(so.keys, tracks);
+    ptb::key_eval(tracks[0], 0.f, &o.xform.scale);
+    ptb::key_eval(tracks[1], 0.f, tr);
+    ptb::key_eval(tracks[2], 0.f, r);
     return PTB_OK;
 }
 
@@ -864,6 +858,19 @@ int ptb_scn_get_slot(const ptb_scn* s, int obj, int kind, int idx, ptb_slot* out
     return PTB_OK;
 }
 
+int ptb_scn_get_keyframes(const ptb_scn* s, int obj, int kind, float* frames, float* values, int cap) {
+    if (!s || obj < 0 || obj >= (int)s->objects.size() || kind < 0 || kind > 2) return fail(PTB_ERR_INVALID, "scn_get_keyframes: bad argument");
+    ptb::KeyTrack tracks[3];
+    keys_to_tracks(s->objects[obj].keys, tracks);
+    const ptb::KeyTrack& t = tracks[kind];
+    const int n = (int)t.frames.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        if (frames) frames[i] = t.frames[i];
+        if (values) std::copy(t.values.begin() + (size_t)i * t.width, t.values.begin() + (size_t)(i + 1) * t.width, values + (size_t)i * t.width);
+    }
+    return n;
+}
+
 int ptb_scn_save(const ptb_scn* s, const char* path) {
     if (!s || !path) return fail(PTB_ERR_INVALID, "scn_save: null argument");
     FILE* f = fopen(path, "w");
@@ -884,8 +891,19 @@ int ptb_scn_save(const ptb_scn* s, const char* path) {
         const float* t = o.xform.translation; const float* r = o.xform.rotation; const float* c = o.xform.rotation_center;
         fprintf(f, "translation: (%f, %f, %f)\n", t[0], t[1], t[2]);
         fprintf(f, "rotation: (%f, %f, %f, %f, %f, %f, %f, %f, %f)\n", r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8]);
-        fprintf(f, "center: (%f, %f, %f)\nscale: %f\ndisplay_edges: %u\ninterp_normals: %u\nflip_normals: %u\nnb_transforms: 0\n", c[0], c[1], c[2], o.xform.scale,
+        fprintf(f, "center: (%f, %f, %f)\nscale: %f\ndisplay_edges: %u\ninterp_normals: %u\nflip_normals: %u\n", c[0], c[1], c[2], o.xform.scale,
                 o.display_edges, o.interp_normals, o.flip_normals);
+        {   // Geometry.h:466-476: nb_transforms = translation_keyframes.size(), then the scale, translation and rotation rows
+            ptb::KeyTrack tk[3];
+            keys_to_tracks(so.keys, tk);
+            fprintf(f, "nb_transforms: %u\n", (unsigned)tk[1].frames.size());
+            for (size_t i = 0; i < tk[0].frames.size(); i++) fprintf(f, "%f %f\n", tk[0].frames[i], tk[0].values[i]);
+            for (size_t i = 0; i < tk[1].frames.size(); i++) fprintf(f, "%f %f, %f, %f\n", tk[1].frames[i], tk[1].values[3 * i], tk[1].values[3 * i + 1], tk[1].values[3 * i + 2]);
+            for (size_t i = 0; i < tk[2].frames.size(); i++) {
+                const float* m = &tk[2].values[9 * i];
+                fprintf(f, "%f %f, %f, %f, %f, %f, %f, %f, %f, %f\n", tk[2].frames[i], m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]);
+            }
+        }
         for (int k = 0; k < PTB_N_KINDS; k++) {
             fprintf(f, "%s: %u\n", kind_key[k], (unsigned)so.slots[k].size());
             for (const Slot& sl : so.slots[k]) {
@@ -944,6 +962,12 @@ int ptb_load_scene(ptb_ctx* ctx, const char* path, const char* replaced_names, p
             rc = ptb_add_mesh(ctx, &m, &o.xform, flags, &id);
         } else return fail(PTB_ERR_UNSUPPORTED, "load_scene: PointSet objects are not rendered");
         if (rc) return fail(rc, std::string("load_scene: object ") + std::to_string(i) + ": " + ptb_last_error(ctx));
+        {   // the keyframe maps travel with the object; ptb_set_frame + ptb_commit place it (Scene::prepare_render -> build_matrix(frame))
+            ptb::KeyTrack tk[3];
+            keys_to_tracks(so.keys, tk);
+            for (int k = 0; k < 3; k++)
+                if (!tk[k].empty() && (rc = ptb_set_keyframes(ctx, id, k, tk[k].frames.data(), tk[k].values.data(), (int)tk[k].frames.size()))) return fail(rc, "load_scene: keyframes");
+        }
         // per-group slots: a kind is present for group g iff g < its vector's length (Object::queryMaterial, Geometry.h:399-445)
         size_t ng = 0;
         for (int k = 0; k < PTB_N_KINDS; k++) if (k != PTB_KIND_SUBSURF) ng = std::max(ng, so.slots[k].size());

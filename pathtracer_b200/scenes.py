@@ -230,4 +230,39 @@ def config_sss(lib, W=128, H=128, spp=16, nv=24, device=0, mixed=True):
     return rt
 
 
+def _rot(ax, ay):
+    cx, sx, cy, sy = math.cos(ax), math.sin(ax), math.cos(ay), math.sin(ay)
+    rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    return (ry @ rx).astype(np.float32)
+
+
+def config_anim(lib, W=128, H=128, spp=8, nv=20, frame=0, device=0):
+    """Key-framed placement (Object::get_translation / get_rotation / get_scale + Slerp, Geometry.h:258-312): a torus that moves,
+    turns and shrinks between frames 2 and 8, a sphere on a three-key translation track, and a light whose radius is keyed."""
+    rt = base(lib, W, H, spp, device=device)
+    m = _place_like_gui(TriMesh(*displaced_torus(nv)))
+    m.set_material(0, **phong((.5, .5, .5), (.2, .2, .2), 50.0))
+    m.add_keyframe(2)
+    m.scale, m.mat_rotation = 20.0, _rot(0.7, 0.9)
+    m.max_translation = m.max_translation + np.array([8, 4, -6], np.float32)
+    m.add_keyframe(8)
+    # (the sphere goes in before the mesh: Sphere::intersection resets `triangle_id` to -1 whenever it is hit, even behind a closer
+    #  mesh, so the reference's picking query loses the triangle id of mesh pixels in front of a LATER sphere, Geometry.h:990)
+    sp = Sphere((-15, -20.3, 5), 7).set_material(0, **phong((.3, .8, .3), 0.3, 50.0))
+    for fr, t in ((0, (0, 0, 0)), (4, (6, 3, 0)), (9, (6, 12, -8))):
+        sp.translation_keyframes[float(fr)] = np.array(t, np.float32)
+        sp.scale_keyframes[float(fr)] = 1.0
+        sp.rotation_keyframes[float(fr)] = np.eye(3, dtype=np.float32)
+    rt.s.addObject(sp)
+    rt.s.addObject(m)
+    light = rt.s.objects[0]
+    for fr, sc in ((1, 1.0), (7, 0.5)):
+        light.scale_keyframes[float(fr)] = sc
+        light.translation_keyframes[float(fr)] = np.array((0, 0, -2.0 * fr), np.float32)
+        light.rotation_keyframes[float(fr)] = np.eye(3, dtype=np.float32)
+    rt.s.current_frame = frame
+    return rt
+
+
 CONFIGS = {"C1": config_C1, "C2": config_C2, "C3": config_C3, "C4": config_C4, "C5": config_C5}

@@ -48,6 +48,12 @@ int ptb_add_merl(ptb_ctx* c, const double* t, int* id) { c->host.merl_tables.emp
 int ptb_set_envmap(ptb_ctx* c, const uint8_t* rgb, int W, int H) { c->host.envmap.assign(rgb, rgb + (size_t)W * H * 3); c->host.envW = W; c->host.envH = H; return PTB_OK; }
 int ptb_set_light(ptb_ctx* c, float a, float b) { c->host.intensite_lumiere = a; c->host.envmap_intensity = b; return PTB_OK; }
 int ptb_set_fog(ptb_ctx* c, const ptb_fog* f) { c->host.fog = *f; return PTB_OK; }
+int ptb_set_keyframes(ptb_ctx* c, int obj, int kind, const float* frames, const float* values, int n) {
+    static const int width[3] = {1, 3, 9};
+    key_track_set(c->host.objects[obj].keys[kind], frames, values, n, width[kind]);
+    return PTB_OK;
+}
+int ptb_set_frame(ptb_ctx* c, float frame) { c->host.current_frame = frame; return PTB_OK; }
 int ptb_set_background(ptb_ctx* c, const float* rgb, int W, int H) {
     c->host.background.clear(); c->host.bgW = c->host.bgH = 0;
     if (!rgb || W <= 0 || H <= 0) return PTB_OK;

@@ -27,7 +27,7 @@ import ctypes as C  # noqa: E402
 import json  # noqa: E402
 
 import sceneio_cases as sio  # noqa: E402
-from golden_scenes import BRANCH_SCENES, KAT_INPUTS, SCENES, STAT_SCENES  # noqa: E402
+from golden_scenes import ANIM_SCENES, BRANCH_SCENES, KAT_INPUTS, SCENES, STAT_SCENES  # noqa: E402
 from oracles import ref_lib  # noqa: E402
 
 from pathtracer_b200 import _abi, scenes  # noqa: E402
@@ -101,7 +101,7 @@ def main():
     assert R is not None, "oracle/_ref is not built (needs /root/reference)"
     sceneio_golden(R)
     modes_golden(R)
-    todo = {**BRANCH_SCENES, **STAT_SCENES}
+    todo = {**BRANCH_SCENES, **STAT_SCENES, **ANIM_SCENES}
     if "--new-only" not in sys.argv:
         todo.update(SCENES)
     if "--new-only" not in sys.argv:

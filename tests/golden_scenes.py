@@ -22,6 +22,9 @@ BRANCH_SCENES = {
     "FOG_E1": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=1, phase=1, **kw),
     "FOG_E2": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=1, phase=2, **kw),
 }
+# key-framed placement at several frames: before the first key, between keys (Slerp), on a key, after the last
+ANIM_SCENES = {f"ANIM_F{fr}": (lambda L, fr=fr, **kw: scenes.config_anim(L, 48, 48, 2, frame=fr, **kw)) for fr in (0, 3, 5, 8, 12)}
+
 # the subsurface branch (Raytracer.cpp:318-406): pinned port == reference bit for bit; the CUDA path can only be compared
 # statistically (the reservoir over a probe ray's hits draws in BVH traversal order, parity_cases.case_sss_converged)
 STAT_SCENES = {

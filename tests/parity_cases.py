@@ -47,11 +47,11 @@ def check_ids(rt_test, rt_oracle, W=None, H=None, agree=ID_AGREE, need_mesh=True
     assert np.allclose(da[hit], db[hit], rtol=2e-4), "hit distances"
 
 
-def case_scene(test_lib, oracle_lib, mk, nrays=None, frac=FRAC_1SPP):
+def case_scene(test_lib, oracle_lib, mk, nrays=None, frac=FRAC_1SPP, agree=ID_AGREE):
     a, b = mk(oracle_lib).commit(), mk(test_lib).commit()
     if nrays:
         a.nrays = b.nrays = nrays
-    check_ids(b, a, need_mesh=len(a.s.objects) > 5 or any(hasattr(o, "tri") for o in a.s.objects))
+    check_ids(b, a, agree=agree, need_mesh=len(a.s.objects) > 5 or any(hasattr(o, "tri") for o in a.s.objects))
     ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
     check_images(ib, ia, frac)
     assert np.allclose(a.sample_count, b.sample_count, rtol=1e-5)

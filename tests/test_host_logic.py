@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 import pytest
-from golden_scenes import BRANCH_SCENES, SCENES
+from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
 from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
                           case_progressive, case_scene, check_ids)
 
@@ -38,6 +38,11 @@ def test_denoiser_inputs_devsim(devsim, port):
 
 def test_converged_devsim(devsim, port):
     case_converged(devsim, port)
+
+
+@pytest.mark.parametrize("name", sorted(ANIM_SCENES))
+def test_keyframed_scenes_devsim_vs_oracle(devsim, port, name):
+    case_scene(devsim, port, ANIM_SCENES[name], agree=0.998)   # 2304 pixels of a coarse, rotated mesh: a silhouette pixel may flip
 
 
 @pytest.mark.parametrize("name", sorted(BRANCH_SCENES))

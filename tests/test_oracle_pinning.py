@@ -6,9 +6,9 @@ import os
 
 import numpy as np
 import pytest
-from golden_scenes import BRANCH_SCENES, KAT_INPUTS, SCENES, STAT_SCENES
+from golden_scenes import ANIM_SCENES, BRANCH_SCENES, KAT_INPUTS, SCENES, STAT_SCENES
 
-ALL_SCENES = {**SCENES, **BRANCH_SCENES, **STAT_SCENES}
+ALL_SCENES = {**SCENES, **BRANCH_SCENES, **STAT_SCENES, **ANIM_SCENES}
 
 from pathtracer_b200 import _abi, scenes
 

@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 import pytest
-from golden_scenes import BRANCH_SCENES, SCENES
+from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
 from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
                           case_progressive, case_scene, check_ids, check_images)
 
@@ -48,6 +48,24 @@ def test_scenes_gpu_vs_golden_reference_images(gpu, name):
 
 def test_scenes_gpu_vs_compiled_reference(gpu, ref):
     case_scene(gpu, ref, lambda L: scenes.config_C3(L, 96, 96, 2, nv=40, tex=128))
+
+
+@pytest.mark.parametrize("name", sorted(ANIM_SCENES))
+def test_keyframed_scenes_gpu_vs_oracle(gpu, port, name):
+    """Key-framed transforms: the placement at Scene::current_frame (linear / Slerp between keys) reaches the BVH and the light."""
+    case_scene(gpu, port, ANIM_SCENES[name], agree=0.998)   # 2304 pixels of a coarse, rotated mesh: a silhouette pixel may flip
+
+
+def test_animation_recommit_gpu(gpu, port):
+    """An animation on ONE context: set_frame + commit + render per frame equals a fresh context per frame."""
+    rt = scenes.config_anim(gpu, 40, 40, 2, frame=0).commit()
+    for fr in (0, 5, 12):
+        rt.s.current_frame = fr
+        img = rt.commit().render_image_nopreviz().copy()
+        fresh = scenes.config_anim(gpu, 40, 40, 2, frame=fr).commit().render_image_nopreviz()
+        assert np.allclose(img, fresh, rtol=1e-5, atol=1e-3), fr
+    a, b = scenes.config_anim(gpu, 40, 40, 2, frame=0).commit().render_image_nopreviz().copy(), scenes.config_anim(gpu, 40, 40, 2, frame=5).commit().render_image_nopreviz()
+    assert not np.allclose(a, b, rtol=1e-2), "the frames must differ"
 
 
 @pytest.mark.parametrize("name", sorted(BRANCH_SCENES))

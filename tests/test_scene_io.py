@@ -174,6 +174,49 @@ def test_scn_fog_ghost_background_reach_the_renderer(port, ref, tmp_path):
     assert [rt.stats["rays_closest"], rt.stats["rays_shadow"]] == [st.rays_closest, st.rays_shadow]
 
 
+@pytest.mark.parametrize("frame", [0, 3])
+def test_scn_keyframes_straddling_the_frame_are_slerped(port, ref, io, tmp_path, frame):
+    """full.scn with its keys moved to frames -5 / 4 and -1 / 7: at frames 0 and 3 the placement is an interpolation (Slerp for the
+    rotation).  Reference load_scene + render at Scene::current_frame == oracle fed by the product reader, bit for bit; and the
+    parsed keys themselves equal the reference's maps."""
+    txt = open(os.path.join(sio.ASSETS, "full.scn")).read()
+    for old, new in (("\n-1.000000 ", "\n4.000000 "), ("\n3.000000 ", "\n-1.000000 ")):
+        assert old in txt
+        txt = txt.replace(old, new)
+    f = tmp_path / "keys.scn"
+    f.write_text(txt)
+    with sio.in_assets():
+        RIO = sio.sceneio_of(ref.cdll, "ref_")
+        ctx = C.c_void_p()
+        ref.check(ref.create(0, C.byref(ctx)))
+        cam, p = _abi.Camera(), _abi.Params()
+        RIO.check(RIO.load_scene(ctx, str(f).encode(), None, C.byref(cam), C.byref(p)))
+        ref.check(ref.set_frame(ctx, float(frame)), ctx)
+        ref.check(ref.commit(ctx), ctx)
+        ref.check(ref.set_option(ctx, _abi.ORC_OPT_THREADS, 1), ctx)
+        want = np.empty((p.H, p.W, 3), np.float32)
+        ref.check(ref.render(ctx, C.byref(cam), C.byref(p), _abi.fptr(want), None, None, None), ctx)
+        h = C.c_void_p()
+        io.check(io.scn_load(str(f).encode(), None, C.byref(h)))
+        for obj in range(6):
+            for kind, width in ((_abi.KEY_SCALE, 1), (_abi.KEY_TRANSLATION, 3), (_abi.KEY_ROTATION, 9)):
+                n = io.scn_get_keyframes(h, obj, kind, None, None, 0)
+                assert n == RIO.scn_get_keyframes(ctx, obj, kind, None, None, 0)
+                a, b = np.zeros((2, max(n, 1)), np.float32), np.zeros((2, max(n, 1) * width), np.float32)
+                io.scn_get_keyframes(h, obj, kind, _abi.fptr(a[0]), _abi.fptr(b[0]), n)
+                RIO.scn_get_keyframes(ctx, obj, kind, _abi.fptr(a[1]), _abi.fptr(b[1]), n)
+                assert np.array_equal(a[0], a[1]) and np.array_equal(b[0], b[1]), (obj, kind)
+        io.scn_free(h)
+        ref.destroy(ctx)
+        rt = api.Raytracer(port).load_scene(str(f))
+        assert sum(len(o.rotation_keyframes) for o in rt.s.objects) == 4
+        rt.s.current_frame = frame
+        rt.commit()
+        rt.set_option(_abi.ORC_OPT_THREADS, 1)
+        got = rt.render_image_nopreviz().copy()
+    assert np.array_equal(got, want)
+
+
 def test_unsupported_scene_features_are_refused(port, tmp_path):
     txt = open(os.path.join(sio.ASSETS, "old.scn")).read()
     with sio.in_assets():
