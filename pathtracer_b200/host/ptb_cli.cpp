@@ -32,12 +32,13 @@ static std::shared_ptr<TriMesh> displaced_torus(int nv) {   // SURVEY.md §8d ge
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { std::fprintf(stderr, "usage: %s <scene.scn|C1|torus> <out.ppm> [W H spp nv]\n", argv[0]); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: %s <scene.scn|C1|torus> <out.ppm> [W H spp nv]   (PTB_FRAME=<n> renders frame n of a key-framed .scn)\n", argv[0]); return 2; }
     try {
         Raytracer rt;
         const size_t len = std::strlen(argv[1]);
         const bool scn = len > 4 && !std::strcmp(argv[1] + len - 4, ".scn");
         if (scn) {
+            if (const char* fr = std::getenv("PTB_FRAME")) rt.s.current_frame = std::atoi(fr);
             rt.load_scene(argv[1]);
             if (argc > 3 && std::atoi(argv[3]) > 0) rt.W = std::atoi(argv[3]);
             if (argc > 4 && std::atoi(argv[4]) > 0) rt.H = std::atoi(argv[4]);

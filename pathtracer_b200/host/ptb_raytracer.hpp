@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <array>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -79,6 +81,13 @@ struct Object {                  // Geometry.h:240-672
     int brdf_kind = PTB_BRDF_PHONG;
     std::shared_ptr<std::vector<double>> merl;   // IsoMERLBRDF::data
     std::vector<Material> materials;             // index = group
+    std::map<float, float> scale_keyframes;                  // Geometry.h:318-320
+    std::map<float, Vector> translation_keyframes;
+    std::map<float, std::array<float, 9>> rotation_keyframes;
+    void add_keyframe(int frame) {                           // Geometry.h:313-317
+        std::array<float, 9> m; std::memcpy(m.data(), mat_rotation, sizeof(mat_rotation));
+        rotation_keyframes[(float)frame] = m; translation_keyframes[(float)frame] = max_translation; scale_keyframes[(float)frame] = scale;
+    }
     explicit Object(ObjectType t) : type(t) {}
     virtual ~Object() = default;
 };
@@ -105,6 +114,7 @@ struct Scene {                   // Geometry.h:1238-1400
     float intensite_lumiere = 0.f, envmap_intensity = 1.f;
     float fog_density = 0.f, fog_absorption = 0.f, fog_density_decay = 0.f, fog_absorption_decay = 0.f, phase_aniso = 0.f;   // Geometry.h:1371-1377
     int fog_type = 0, fog_phase_type = 0;
+    int current_frame = 0;                                                                                                 // Geometry.h:1372
     std::vector<float> background; int backgroundW = 0, backgroundH = 0;                                                   // Geometry.h:1365-1366
     int addObject(std::shared_ptr<Object> o) { objects.push_back(std::move(o)); return (int)objects.size() - 1; }
 };
@@ -151,6 +161,14 @@ public:
         W = p.W; H = p.H; nrays = p.nrays; nb_bounces = p.nb_bounces; sigma_filter = p.sigma_filter; gamma = p.gamma;
         cam = Camera(Vector(c.position[0], c.position[1], c.position[2]), Vector(c.direction[0], c.direction[1], c.direction[2]), Vector(c.up[0], c.up[1], c.up[2]));
         cam.fov = c.fov; cam.focus_distance = c.focus_distance; cam.aperture = c.aperture;
+        ck(ptb_set_frame(ctx_, (float)s.current_frame));
+        ck(ptb_commit(ctx_));
+    }
+    // One frame of an animation (mainApp.cpp:874-877): key-framed objects are placed at `frame` and the scene is committed again.
+    void set_frame(int frame) {
+        s.current_frame = frame;
+        if (!ctx_) { commit(); return; }
+        ck(ptb_set_frame(ctx_, (float)frame));
         ck(ptb_commit(ctx_));
     }
 
@@ -179,6 +197,17 @@ public:
                 for (int k = 0; k < 3; k++) m.offset[k] = g.offset[k];
                 ck(ptb_add_mesh(ctx_, &m, &xf, flags, &id));
             }
+            {
+                std::vector<float> fr, val;
+                for (auto& k : o.scale_keyframes) { fr.push_back(k.first); val.push_back(k.second); }
+                if (!fr.empty()) ck(ptb_set_keyframes(ctx_, id, PTB_KEY_SCALE, fr.data(), val.data(), (int)fr.size()));
+                fr.clear(); val.clear();
+                for (auto& k : o.translation_keyframes) { fr.push_back(k.first); for (int q = 0; q < 3; q++) val.push_back(k.second[q]); }
+                if (!fr.empty()) ck(ptb_set_keyframes(ctx_, id, PTB_KEY_TRANSLATION, fr.data(), val.data(), (int)fr.size()));
+                fr.clear(); val.clear();
+                for (auto& k : o.rotation_keyframes) { fr.push_back(k.first); for (int q = 0; q < 9; q++) val.push_back(k.second[q]); }
+                if (!fr.empty()) ck(ptb_set_keyframes(ctx_, id, PTB_KEY_ROTATION, fr.data(), val.data(), (int)fr.size()));
+            }
             for (size_t gi = 0; gi < o.materials.size(); gi++) {
                 const Material& mm = o.materials[gi];
                 ptb_material pm;
@@ -203,6 +232,7 @@ public:
         const ptb_fog fog = {s.fog_density, s.fog_absorption, s.fog_density_decay, s.fog_absorption_decay, s.fog_type, s.fog_phase_type, s.phase_aniso};
         ck(ptb_set_fog(ctx_, &fog));
         ck(ptb_set_background(ctx_, s.backgroundW > 0 ? s.background.data() : nullptr, s.backgroundW, s.backgroundH));
+        ck(ptb_set_frame(ctx_, (float)s.current_frame));
         ck(ptb_commit(ctx_));
     }
 
