@@ -1,13 +1,16 @@
 // ptb_scene.h — device-side scene description and the per-path stages of the wavefront integrator.
 //
-// The stages restate Raytracer::getColor (Raytracer.cpp:196-664, fog / subsurface / ghost / background
-// branches excluded, see DESIGN.md "scope") as four per-path functions that the kernels in kernels.cu
-// call once per queue entry:
+// The stages restate Raytracer::getColor (Raytracer.cpp:196-664) as per-path functions that the kernels in
+// ptb_engine.cu call once per queue entry.  The linear path (no fog, ghost object, background photograph or
+// subsurface material in the scene: every loop iteration pushes at most one contribution) is:
 //     raygen_one  — precomputeRayBatch + Camera::generateDirection (Raytracer.cpp:1404-1420)
 //     extend_one  — Scene::intersection (Geometry.cpp:589-688)
 //     shade_one   — getColor's per-bounce body: emission, mirror, dielectric, NEE sample, BSDF sample
 //     shadow_one  — Scene::intersection_shadow (Geometry.cpp:691-744) + the deferred direct term
 //     splat_pixel — the Gaussian splat (Raytracer.cpp:1604-1659)
+// Scenes with a medium, ghosts, a background photograph or subsurface scattering take shade_branch_one instead
+// of shade_one: the same loop body with those branches, walking the contribution tree level by level
+// (DESIGN.md section 10).
 #pragma once
 #include "ptb_bvh8.h"
 
