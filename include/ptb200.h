@@ -261,6 +261,8 @@ int ptb_primary_ids(ptb_ctx*, const ptb_camera*, int W, int H,
 #define PTB_OPT_REFILL_BELOW     4   /* tuning: a traversal warp refills idle lanes when fewer than this many are live (1..33) */
 #define PTB_OPT_TRI_FRACTION     6   /* tuning: triangle steps repeat while >= 1/value of a warp's live lanes have triangle work */
 #define PTB_OPT_TRI_MIN_PCT      7   /* tuning: the triangle phase of a warp starts once this % of its live lanes hold triangle work */
+#define PTB_OPT_SORT_HITS        8   /* tuning, default 0: 1 = a compaction pass shades the terminal hits (miss / light / dome) and hands k_shade
+                                        surface hits only (measured slower: k_shade is not bound by lane divergence) */
 #define PTB_OPT_TRACE_BLOCKS     5   /* tuning: persistent grid size of the traversal kernels (default: SMs x resident blocks) */
 int ptb_set_option(ptb_ctx*, int option, int64_t value);
 

@@ -38,7 +38,8 @@ using namespace ptb;
 #define PTB_CNT_ALLOC (5 * (PTB_MAX_BOUNCES + 1))       // branching renders: side-branch slots handed out in this pass
 #define PTB_CNT_DROPS (5 * (PTB_MAX_BOUNCES + 1) + 1)   // side branches that found the pool full
 #define PTB_CNT_PROBE (5 * (PTB_MAX_BOUNCES + 1) + 2)   // subsurface probes emitted at the current level
-#define PTB_N_COUNTERS (5 * (PTB_MAX_BOUNCES + 1) + 3)
+#define PTB_CNT_SURF (5 * (PTB_MAX_BOUNCES + 1) + 3)    // [+ b] surface hits of bounce b (the queue k_sort_hits leaves for k_shade)
+#define PTB_N_COUNTERS (6 * (PTB_MAX_BOUNCES + 1) + 3)
 // 64-bit totals: 0 closest rays, 1 shadow rays, 2/3 node visits / triangle tests of the closest-hit trace, 4/5 of the any-hit trace
 #define PTB_N_TOTALS 6
 #define PTB_BRANCH_MAX_LEVELS 512
@@ -211,6 +212,21 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool want) {
     if ((int)lane == leader) base = atomicAdd(counter, __popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// Shades the terminal hits of a bounce (miss / light / dome) and compacts the surface hits into `out_queue` for k_shade.
+__global__ void __launch_bounds__(256) k_sort_hits(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count, int n_static,
+                                                   uint32_t* __restrict__ out_queue, uint32_t* out_count) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = count ? (int)*count : n_static;
+    bool surface = false;
+    int path = 0;
+    if (tid < n) {
+        path = queue ? (int)queue[tid] : tid;
+        surface = !shade_terminal_one(sc, p, path);
+    }
+    const uint32_t qi = warp_push(out_count, surface);
+    if (surface) out_queue[qi] = (uint32_t)path;
 }
 
 template <bool MERL, int MINB, bool AOV>
@@ -430,6 +446,8 @@ struct ptb_ctx {
     int64_t pool_paths = (int64_t)1 << 25, pool_cap = 0;   // measured: larger pools amortise the tails of the persistent kernels (tune4.log)
     PoolDev pool;
     uint32_t* d_queue[2] = {nullptr, nullptr};
+    uint32_t* d_queue_surf = nullptr;          // the surface hits of the current bounce (k_sort_hits -> k_shade)
+    bool sort_hits = false;                    // PTB_OPT_SORT_HITS (measured r01k: slower)
     uint32_t* d_counters = nullptr;
     unsigned long long* d_totals = nullptr;
     float* d_rpp = nullptr;
@@ -474,10 +492,10 @@ static void free_scene(ptb_ctx* c) {
 }
 static void free_pool(ptb_ctx* c) {
     void* ptrs[] = {c->pool.ray_o, c->pool.ray_d, c->pool.weight, c->pool.radiance, c->pool.hit, c->pool.rng, c->pool.pixel,
-                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1], c->pool.aov_n, c->pool.aov_kd, c->pool.root, c->pool.probe_o, c->pool.probe_d, c->pool.probe_x, c->pool.hit2};
+                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1], c->d_queue_surf, c->pool.aov_n, c->pool.aov_kd, c->pool.root, c->pool.probe_o, c->pool.probe_d, c->pool.probe_x, c->pool.hit2};
     for (void* p : ptrs) if (p) cudaFree(p);
     memset(&c->pool, 0, sizeof(c->pool));
-    c->d_queue[0] = c->d_queue[1] = nullptr;
+    c->d_queue[0] = c->d_queue[1] = nullptr; c->d_queue_surf = nullptr;
     c->pool_cap = 0;
 }
 
@@ -510,6 +528,7 @@ static int ensure_pool(ptb_ctx* c, int64_t paths, bool aov = false, bool branch 
     CK(cudaMalloc((void**)&c->pool.sh_c, n * sizeof(F4)));
     CK(cudaMalloc((void**)&c->d_queue[0], n * sizeof(uint32_t)));
     CK(cudaMalloc((void**)&c->d_queue[1], n * sizeof(uint32_t)));
+    CK(cudaMalloc((void**)&c->d_queue_surf, n * sizeof(uint32_t)));
     if (aov) {
         CK(cudaMalloc((void**)&c->pool.aov_n, n * sizeof(F4)));
         CK(cudaMalloc((void**)&c->pool.aov_kd, n * sizeof(F4)));
@@ -559,6 +578,7 @@ int ptb_create(int device_id, ptb_ctx** out) {
     ptb_ctx* c = new ptb_ctx();
     c->device = device_id;
     if (const char* e = getenv("PTB_SHADE_MINB")) c->shade_minb = atoi(e);
+    if (const char* e = getenv("PTB_SORT_HITS")) c->sort_hits = atoi(e) != 0;   // experiments: 0 = k_shade sees every hit
     memset(&c->pool, 0, sizeof(c->pool));
     memset(&c->sc, 0, sizeof(c->sc));
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -931,7 +951,15 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         launches++;
                     }
                     lt.begin(2 | (b << 8));
-#define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, q, cnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1), \
+                    // optional: terminal hits (miss / light / dome) shaded by a compaction pass, k_shade sees surface hits only (off: measured slower)
+                    const bool sorted = c->sort_hits && !(aov && b == 0);
+                    const uint32_t* sq = q; const uint32_t* scnt = cnt;
+                    if (sorted) {
+                        k_sort_hits<<<g256, 256, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_queue_surf, c->d_counters + PTB_CNT_SURF + b);
+                        sq = c->d_queue_surf; scnt = c->d_counters + PTB_CNT_SURF + b;
+                        launches++;
+                    }
+#define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, sq, scnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1), \
                                                                           c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b)
                     if (aov && b == 0) { if (c->has_merl) PTB_SHADE(true, 5, true); else PTB_SHADE(false, 6, true); }   // camera rays of a denoiser-input render
                     else if (c->has_merl) PTB_SHADE(true, 5, false);
@@ -1222,6 +1250,7 @@ int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
     case PTB_OPT_TRI_FRACTION: if (value < 1 || value > 64) return PTB_ERR_INVALID; c->tri_den = (int)value; return PTB_OK;
     case PTB_OPT_TRI_MIN_PCT: if (value < 0 || value > 100) return PTB_ERR_INVALID; c->tri_min_pct = (int)value; return PTB_OK;
     case PTB_OPT_TRACE_BLOCKS: if (value < 1) return PTB_ERR_INVALID; c->trace_blocks = (int)value; return PTB_OK;
+    case PTB_OPT_SORT_HITS: c->sort_hits = value != 0; return PTB_OK;
     default: return PTB_OK;  // unknown options (e.g. the CPU checkers' thread count) are ignored
     }
 }

@@ -447,6 +447,36 @@ struct ShadeOut {
 // lookup code (fewer registers, higher occupancy).
 // AOV = this launch shades the camera rays of a denoiser-input render: the first hit's shading normal and albedo are recorded
 // (`if (has_inter && nbrebonds == nb_bounces) { normalValue = N; albedoValue = mat.Kd; }`, Raytracer.cpp:254-257).
+// The terminal hits of getColor's loop: a miss (654-657), the light (303-316) and the dome (275-301).  They need no BRDF, no RNG
+// and no new ray, and they are roughly every second queue entry of an environment-lit scene; k_sort_hits shades them where it
+// compacts the queue so that k_shade's warps hold surface hits only (ncu r01j: 13 of 32 lanes active in k_shade before).
+// Returns false for a surface hit (nothing is touched).
+PTB_HD bool shade_terminal_one(const SceneDev& sc, PoolDev& p, int path) {
+    const F4 hq = p.hit[path];
+    const int32_t id = (int32_t)f2u(hq.w);
+    if (id == PTB_HIT_MISS) return true;
+    if (id >= 0 || (id != hit_id_analytic(0) && id != hit_id_analytic(1))) return false;
+    const F4 wq = p.weight[path];
+    const V3 w = v3(wq.x, wq.y, wq.z);
+    if (id == hit_id_analytic(0)) {
+        const float lp = (f2u(wq.w) & ST_SHOW_LIGHTS) ? sc.lightPower : 0.f;
+        F4 Lq = p.radiance[path];
+        Lq.x += w.x * lp; Lq.y += w.y * lp; Lq.z += w.z * lp;
+        p.radiance[path] = Lq;
+        return true;
+    }
+    if (!sc.has_envmap) return true;                                 // dome without a map: Ke = 0
+    const F4 oq = p.ray_o[path], dq = p.ray_d[path];
+    Hit hit; hit.t = hq.x; hit.b1 = hq.y; hit.b2 = hq.z; hit.prim = id;
+    Surface s;
+    surface_from_hit(sc, v3(oq.x, oq.y, oq.z), v3(dq.x, dq.y, dq.z), hit, id, s);
+    const V3 c = (w * sc.envmap_intensity) * s.Ke;
+    F4 Lq = p.radiance[path];
+    Lq.x += c.x; Lq.y += c.y; Lq.z += c.z;
+    p.radiance[path] = Lq;
+    return true;
+}
+
 template <bool MERL, bool AOV = false>
 PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path, ShadeOut& out) {
     out.cont = false; out.shadow = false; out.shadow_query = false;
