@@ -140,6 +140,7 @@ def main():
     base_line = {"metric": "Msamples/s", "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                  "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                  "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "spp_sharding": "image tiles 64x64, tile_id % n_gpus",
+                            "pass_pipelines": int(os.environ.get("PTB_PIPES", "2")),
                             "l2": "working set per step (BVH + triangles + path pool, >2 GB) exceeds the 126 MB L2; no flush needed"}}
 
     if args.impl == "reference":
@@ -163,6 +164,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = pathtracer_b200.load()
+    N_PIPES = int(os.environ.get("PTB_PIPES", "2"))
     t0 = time.time(); rt = make_rt(lib, args.workload, device=local); gen_s = time.time() - t0
     t0 = time.time(); rt.commit(); commit_s = time.time() - t0
     info = rt.scene_info()
@@ -244,14 +246,20 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # per-kernel CUDA-event timing rides along in the timed region (two event records per launch on the launching stream)
-    rt.set_option(_abi.OPT_TIME_KERNELS, 1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     wall_ms, dev_ms, launches, rays = timed(step_resident, args.steps)
-    kt = rt.kernel_times()        # of the last step
+    # per-kernel CUDA-event timing (two event records per launch on the launching stream).  The timed region above runs the passes
+    # on two pipelines (streams) whose kernels overlap, so a kernel's own duration is taken from one more step of the same
+    # workload, right here, with the pipelines serialised: `roofline.launch_ms` is the kernel running alone on the GPU.
+    rt.set_option(_abi.OPT_PIPES, 1)
+    rt.set_option(_abi.OPT_TIME_KERNELS, 1)
+    step_resident()
+    kt = rt.kernel_times()
+    serial_ms = rt.stats["ms_device"] if world == 1 else None
     rt.set_option(_abi.OPT_TIME_KERNELS, 0)
+    rt.set_option(_abi.OPT_PIPES, N_PIPES)
     for _ in range(1):
         step_e2e()
     e2e_ms, _, _, _ = timed(step_e2e, args.steps)
@@ -288,6 +296,8 @@ def main():
                         "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "n_node": n_node, "n_tri": n_tri,
                         "rays_per_launch": rays_per_launch, "launch_ms": ext_launch_ms, "launches_per_step": ext["launches"],
                         "share_of_step": ext["ms"] / step_kernel_ms if step_kernel_ms else None,
+                        "timing": "CUDA events around every launch of one extra step with the pass pipelines serialised (PTB_OPT_PIPES=1), taken between the timed region and the e2e region",
+                        "serialised_step_ms": serial_ms,
                         "kernel_ms_per_step": {k: v["ms"] for k, v in kt.items()}}
     if world > 1:
         dist.barrier()

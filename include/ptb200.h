@@ -264,6 +264,8 @@ int ptb_primary_ids(ptb_ctx*, const ptb_camera*, int W, int H,
 #define PTB_OPT_SORT_HITS        8   /* tuning, default 0: 1 = a compaction pass shades the terminal hits (miss / light / dome) and hands k_shade
                                         surface hits only (measured slower: k_shade is not bound by lane divergence) */
 #define PTB_OPT_TRACE_BLOCKS     5   /* tuning: persistent grid size of the traversal kernels (default: SMs x resident blocks) */
+#define PTB_OPT_PIPES            9   /* pass pipelines (1..4): consecutive passes of a render run on this many streams, each with its own slice of
+                                        the path pool, so that the shade kernels of one pass overlap the traversal kernels of another */
 int ptb_set_option(ptb_ctx*, int option, int64_t value);
 
 /* Per-kernel device time of the LAST render, measured with CUDA events on the launching stream
@@ -300,6 +302,8 @@ int ptb_get_scene_info(const ptb_ctx*, ptb_scene_info*);
 #define PTB_KAT_FAST_NORMALIZE 9   /* in: v[3]                 -> out: v[3]                  (Vector.h:294-309, 376-382) */
 #define PTB_KAT_RANDOM_PER_PIXEL 10 /* in: pixel index p       -> out: randomPerPixel[p].x,.y (Raytracer.cpp:1341-1344) */
 #define PTB_KAT_FILTER_RATIO   11  /* in: i,j,W,H,sigma        -> out: ratio                 (Raytracer.cpp:1604-1608) */
+#define PTB_KAT_MERL_INDEX     12  /* in: wi3,wo3 (local frame, z = normal) -> out: bin index of the float path (-1: it declined), bin index of
+                                      the double path (MERLBRDFRead.cpp:76-207); the two must agree wherever the first is >= 0 */
 int ptb_kat(ptb_ctx*, int which, const ptb_camera* cam, int W, int H,
             const double* in, int n, int in_stride, double* out, int out_stride);
 

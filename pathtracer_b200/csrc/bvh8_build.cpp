@@ -35,6 +35,20 @@ struct BNode {   // binary node: leaf iff count > 0
     Box box;
     int32_t left, right;   // children (internal)
     int32_t first, count;  // range in the index array (leaf)
+    int32_t sfirst, scount;  // range of the whole subtree in the index array (the in-place partition keeps it contiguous)
+};
+
+// Cost-optimal collapse (Ylitie, Karras, Laine 2017, sec. 3.1): for every binary node n and i = 1..7,
+//   C(n,1) = min( leaf: A(n) * P(n) * c_prim  [P(n) <= 3],  wide node: A(n) * c_node + D(n,8) )
+//   C(n,i) = min( D(n,i), C(n,i-1) )                      the subtree of n as a forest of at most i children of a wide node
+//   D(n,j) = min over 0 < k < j of C(left,k) + C(right,j-k)
+// The greedy collapse (open the child of largest area until 8) leaves the lowest wide nodes with 2-3 small leaves: 275k nodes of
+// 2.8 children on average for the 1M-triangle mesh, hence one node visit per level of a deep tree; the optimal collapse decides
+// leaf sizes and node shapes together.
+struct Collapse {
+    float c[7];            // C(n,1..7)
+    uint8_t d[7];          // d[0]: 0 leaf / 1 wide node; d[i-1], i >= 2: 0 = "as C(n,i-1)", else k = children handed to the left subtree
+    uint8_t k8;            // split of D(n,8), the children of the wide node rooted at n
 };
 
 struct Builder {
@@ -44,7 +58,10 @@ struct Builder {
     std::vector<float> pcen;       // 3 per prim
     std::vector<uint32_t> idx;
     std::vector<BNode> nodes;
+    std::vector<Collapse> dp;      // empty: greedy collapse
+    int max_leaf = 3;
     std::atomic<int64_t> n_nodes{0};
+    void solve(int64_t node);
 
     int64_t alloc2() { return n_nodes.fetch_add(2); }
 
@@ -56,6 +73,38 @@ constexpr int NBINS = 16;
 static float env_f(const char* n, float d) { const char* v = getenv(n); return v ? (float)atof(v) : d; }
 static const float C_TRAV = env_f("PTB_BVH_CTRAV", 0.25f);   // binary nodes mostly vanish in the collapse
 static const int MAX_LEAF = (int)env_f("PTB_BVH_MAXLEAF", 3.f);
+static const int COLLAPSE_DP = (int)env_f("PTB_BVH_COLLAPSE_DP", 1.f);   // 0: greedy surface-area collapse of a binary tree with <= 3-triangle leaves
+static const float C_NODE = env_f("PTB_BVH_CNODE", 1.f), C_PRIM = env_f("PTB_BVH_CPRIM", 0.5f);   // measured (profiles/r01m): 0.5 beats 0.3 and 0.15 on C2 and C3
+
+void Builder::solve(int64_t node) {
+    const BNode& nd = nodes[node];
+    Collapse& q = dp[node];
+    const float A = nd.box.area();
+    if (nd.count > 0) {   // binary leaf (one triangle, or an unsplittable group)
+        for (int i = 0; i < 7; i++) { q.c[i] = A * (float)nd.count * C_PRIM; q.d[i] = 0; }
+        q.k8 = 0;
+        return;
+    }
+    const Collapse& L = dp[nd.left];
+    const Collapse& R = dp[nd.right];
+    auto distribute = [&](int j, uint8_t& kbest) {
+        float best = INFINITY; kbest = 1;
+        for (int k = 1; k < j; k++) {
+            if (k > 7 || j - k > 7) continue;
+            const float v = L.c[k - 1] + R.c[j - k - 1];
+            if (v < best) { best = v; kbest = (uint8_t)k; }
+        }
+        return best;
+    };
+    const float wide = A * C_NODE + distribute(8, q.k8);
+    const float leaf = nd.scount <= 3 ? A * (float)nd.scount * C_PRIM : INFINITY;
+    if (leaf <= wide) { q.c[0] = leaf; q.d[0] = 0; } else { q.c[0] = wide; q.d[0] = 1; }
+    for (int i = 2; i <= 7; i++) {
+        uint8_t k;
+        const float dcost = distribute(i, k);
+        if (dcost < q.c[i - 2]) { q.c[i - 1] = dcost; q.d[i - 1] = k; } else { q.c[i - 1] = q.c[i - 2]; q.d[i - 1] = 0; }
+    }
+}
 
 void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
     BNode& nd = nodes[node];
@@ -64,7 +113,9 @@ void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
     for (int64_t i = b; i < e; i++) { box.grow(pbox[idx[i]]); cb.grow(&pcen[3 * (size_t)idx[i]]); }
     nd.box = box;
     const int64_t cnt = e - b;
-    auto make_leaf = [&]() { nd.left = nd.right = -1; nd.first = (int32_t)b; nd.count = (int32_t)cnt; };
+    nd.sfirst = (int32_t)b; nd.scount = (int32_t)cnt;
+    const int MAX_LEAF = max_leaf;
+    auto make_leaf = [&]() { nd.left = nd.right = -1; nd.first = (int32_t)b; nd.count = (int32_t)cnt; if (!dp.empty()) solve(node); };
     if (cnt == 1) { make_leaf(); return; }
 
     // binned SAH over the three axes
@@ -123,6 +174,7 @@ void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
         build(c0, b, mid, depth + 1);
         build(c0 + 1, mid, e, depth + 1);
     }
+    if (!dp.empty()) solve(node);
 }
 
 inline uint8_t exponent_byte(float extent) {
@@ -156,6 +208,8 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
         B.idx[i] = (uint32_t)i;
     }
     B.nodes.resize(2 * (size_t)n_tri + 2);
+    B.max_leaf = COLLAPSE_DP ? 1 : MAX_LEAF;          // the optimal collapse forms the leaves itself, from single triangles
+    if (COLLAPSE_DP) B.dp.resize(B.nodes.size());
     B.n_nodes = 1;
 #pragma omp parallel
     {
@@ -174,8 +228,27 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
     while (head < queue.size()) {
         const Work w = queue[head++];
         stats.depth = std::max(stats.depth, w.depth);
-        int32_t ch[8]; int nc = 0;
+        int32_t ch[8]; bool ch_leaf[8]; int nc = 0;
         const BNode& root = B.nodes[w.bnode];
+        if (!B.dp.empty()) {
+            // children of the wide node rooted at w.bnode: follow the recorded decisions
+            struct Item { int32_t n; int i; };
+            Item st[16]; int sp = 0;
+            if (root.count > 0 || root.scount <= 3) { ch[nc] = w.bnode; ch_leaf[nc++] = true; }   // a tiny mesh: the root holds one leaf
+            else {
+                const int k = B.dp[w.bnode].k8;
+                st[sp++] = {root.right, 8 - k}; st[sp++] = {root.left, k};
+            }
+            while (sp > 0) {
+                const Item it = st[--sp];
+                const BNode& m = B.nodes[it.n];
+                if (m.count > 0) { ch[nc] = it.n; ch_leaf[nc++] = true; continue; }
+                if (it.i == 1) { ch[nc] = it.n; ch_leaf[nc++] = B.dp[it.n].d[0] == 0; continue; }
+                const int k = B.dp[it.n].d[it.i - 1];
+                if (k == 0) st[sp++] = {it.n, it.i - 1};
+                else { st[sp++] = {m.right, it.i - k}; st[sp++] = {m.left, k}; }
+            }
+        } else {
         if (root.count > 0) ch[nc++] = w.bnode;           // a leaf root: one leaf child
         else { ch[nc++] = root.left; ch[nc++] = root.right; }
         while (nc < 8) {
@@ -189,6 +262,8 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
             if (best < 0) break;
             const BNode& c = B.nodes[ch[best]];
             ch[best] = c.left; ch[nc++] = c.right;
+        }
+        for (int i = 0; i < nc; i++) ch_leaf[i] = B.nodes[ch[i]].count > 0;
         }
         // node box
         Box nb; nb.reset();
@@ -246,11 +321,11 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
                 hi = std::min(std::max(hi, 0.f), 255.f);
                 ql[k][s] = (uint8_t)lo; qh[k][s] = (uint8_t)hi;
             }
-            if (c.count > 0) {
-                const uint32_t unary = (c.count == 1) ? 1u : (c.count == 2 ? 3u : 7u);
+            if (ch_leaf[i]) {
+                const uint32_t unary = (c.scount == 1) ? 1u : (c.scount == 2 ? 3u : 7u);
                 nd.meta[s] = (uint8_t)((unary << 5) | tri_off);
-                for (int t = 0; t < c.count; t++) leaf_order.push_back(B.idx[c.first + t]);
-                tri_off += (uint32_t)c.count;
+                for (int t = 0; t < c.scount; t++) leaf_order.push_back(B.idx[c.sfirst + t]);
+                tri_off += (uint32_t)c.scount;
                 stats.leaves++;
             } else {
                 nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
@@ -261,7 +336,7 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
         // allocate the internal children contiguously, in slot order
         for (int s = 0; s < 8; s++) {
             const int i = slot_child[s];
-            if (i < 0 || B.nodes[ch[i]].count > 0) continue;
+            if (i < 0 || ch_leaf[i]) continue;
             queue.push_back({ch[i], (uint32_t)out_nodes.size(), w.depth + 1});
             out_nodes.emplace_back();
         }

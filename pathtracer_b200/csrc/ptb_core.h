@@ -297,6 +297,60 @@ PTB_HD int merl_index(double theta_in, double fi_in, double theta_out, double fi
     return ip + id * 180 + ih * 180 * 90;
 }
 #define PTB_MERL_N (90 * 90 * 180)
+// Float evaluation of the same three bin positions with a guard band.  The double path above costs about a third of k_shade's
+// instructions on the MERL configuration (12 double sin/cos, 2 acos, 2 atan2, 3 sqrt, 6 divisions per lookup), but its result is
+// three small integers: the float path computes the CONTINUOUS bin positions from the local unit vectors (no angles: the Rodrigues
+// rotations by -phi_h and -theta_h are written with cos/sin taken from the half vector), and answers only when every position is
+// farther from a bin edge than a bound on everything that separates the two evaluations (the reference's float acosf/atan2f of
+// the inputs, 1-3 ulp; float rounding here): 1.5e-6 on the unit vectors, propagated to each position.  Otherwise it returns false
+// and the caller runs the double path, so the bin index is the reference's in both cases (checked against the double path on 1e8
+// random direction pairs by tests/test_host_logic.py::test_merl_index_fast, and on the device by the MERL KAT).
+#if !defined(PTB_MERL_EPS0)
+#define PTB_MERL_EPS0 1.5e-6f
+#endif
+PTB_HD bool merl_index_fast(V3 wil, V3 wol, int& ind) {
+    const float HALF_PI = 1.57079632679489662f, INV_PI_180 = 57.2957795130823209f;   // 180/pi = 90/(pi/2)
+    const float li = 1.f / sqrtf(dot(wil, wil)), lo = 1.f / sqrtf(dot(wol, wol));
+    const V3 in = wil * li, out = wol * lo;
+    V3 h = in + out;
+    const float hl2 = dot(h, h);
+    if (!(hl2 > 1e-4f)) return false;
+    const float rhl = 1.f / sqrtf(hl2);
+    h = h * rhl;
+    const float sh2 = h.x * h.x + h.y * h.y;
+    if (!(sh2 > 1e-6f)) return false;               // theta_half < 1e-3: phi_half (and with it phi_diff) is ill-conditioned
+    const float sh = sqrtf(sh2), ch = h.z, rsh = 1.f / sh;
+    const float cp = h.x * rsh, sp = h.y * rsh;
+    const float tx = cp * in.x + sp * in.y, ty = cp * in.y - sp * in.x, tz = in.z;     // rotation by -phi_half about the normal
+    const float dx = ch * tx - sh * tz, dy = ty, dz = sh * tx + ch * tz;               // rotation by -theta_half about the bi-normal
+    const float sd2 = dx * dx + dy * dy;
+    if (!(sd2 > 1e-6f)) return false;               // theta_diff < 1e-3: phi_diff is ill-conditioned
+    const float sd = sqrtf(sd2);
+    const float theta_half = atan2f(sh, ch), theta_diff = atan2f(sd, dz);
+    float fi_diff = atan2f(dy, dx);
+    if (fi_diff < 0.f) fi_diff += 3.14159265358979323846f;
+    const float ph = sqrtf(theta_half * (8100.f / HALF_PI));   // sqrt(theta_half / (pi/2) * 90 * 90)
+    const float pd = theta_diff * INV_PI_180;
+    const float pp = fi_diff * INV_PI_180;
+    // error propagation: each unit vector is uncertain by EPS0 plus what the reference loses by going through theta = acosf(z)
+    // (z is quantised to 6e-8 next to 1: 1.2e-7 / sin theta) -> the half vector (cancellation in in + out: / |in + out|) ->
+    // theta_half, and phi_half (/ sin theta_half) -> the rotated vector -> theta_diff, and phi_diff (/ sin theta_diff); then
+    // d(position)/d(angle)
+    const float si2 = in.x * in.x + in.y * in.y, so2 = out.x * out.x + out.y * out.y;
+    if (!(si2 > 1e-8f && so2 > 1e-8f)) return false;
+    const float ei = PTB_MERL_EPS0 + 1.2e-7f / sqrtf(si2), eo = PTB_MERL_EPS0 + 1.2e-7f / sqrtf(so2);
+    const float eh = (ei + eo) * rhl;
+    const float ed = ei + eh * (1.f + rsh);
+    const float gh = 35.9f * eh / sqrtf(theta_half) + 3e-5f, gd = INV_PI_180 * ed + 3e-5f, gp = INV_PI_180 * ed / sd + 3e-5f;
+    const float fh = ph - floorf(ph), fd = pd - floorf(pd), fp = pp - floorf(pp);
+    if (!(fh > gh && fh < 1.f - gh && fd > gd && fd < 1.f - gd && fp > gp && fp < 1.f - gp)) return false;
+    int ih = (int)ph, id = (int)pd, ip = (int)pp;
+    if (ih >= 90) ih = 89;
+    if (id >= 89) id = 89;
+    if (ip >= 179) ip = 179;
+    ind = ip + id * 180 + ih * 180 * 90;
+    return true;
+}
 PTB_HD V3 merl_eval(const float* table, V3 wi, V3 wo, V3 N) {
     V3 t1 = get_tangent(N);
     V3 t2 = cross(t1, N);
@@ -306,12 +360,31 @@ PTB_HD V3 merl_eval(const float* table, V3 wi, V3 wo, V3 N) {
     if ((double)thetai >= PTB_PI_D / 2) return v3(0, 0, 0);
     float thetao = acosf(wol.z);
     if ((double)thetao >= PTB_PI_D / 2) return v3(0, 0, 0);
+    int ind;
+#if !defined(PTB_MERL_DOUBLE_ONLY)
+    if (!merl_index_fast(wil, wol, ind))
+#endif
+    {
+        float phio = atan2f(wol.y, wol.x);
+        if (phio < 0) phio = (float)((double)phio + 2 * PTB_PI_D);
+        float phii = atan2f(wil.y, wil.x);
+        if (phii < 0) phii = (float)((double)phii + 2 * PTB_PI_D);
+        ind = merl_index((double)thetai, (double)phii, (double)thetao, (double)phio);
+    }
+    return v3(table[ind], table[ind + PTB_MERL_N], table[ind + 2 * PTB_MERL_N]);
+}
+
+// test hook (PTB_KAT_MERL_INDEX): both evaluations of the bin index for one pair of local directions
+PTB_HD void merl_index_both(V3 wil, V3 wol, int& fast, int& exact) {
+    fast = -1;
+    int ind;
+    if (merl_index_fast(wil, wol, ind)) fast = ind;
+    float thetai = acosf(wil.z), thetao = acosf(wol.z);
     float phio = atan2f(wol.y, wol.x);
     if (phio < 0) phio = (float)((double)phio + 2 * PTB_PI_D);
     float phii = atan2f(wil.y, wil.x);
     if (phii < 0) phii = (float)((double)phii + 2 * PTB_PI_D);
-    int ind = merl_index((double)thetai, (double)phii, (double)thetao, (double)phio);
-    return v3(table[ind], table[ind + PTB_MERL_N], table[ind + 2 * PTB_MERL_N]);
+    exact = merl_index((double)thetai, (double)phii, (double)thetao, (double)phio);
 }
 
 // ---- Texture lookups (BRDF.h:270-392): nearest texel, wrap -----------------------------------------

@@ -43,6 +43,7 @@ using namespace ptb;
 // 64-bit totals: 0 closest rays, 1 shadow rays, 2/3 node visits / triangle tests of the closest-hit trace, 4/5 of the any-hit trace
 #define PTB_N_TOTALS 6
 #define PTB_BRANCH_MAX_LEVELS 512
+#define PTB_MAX_PIPES 4
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) k_rpp(float* rpp, int n) {
@@ -317,8 +318,8 @@ __global__ void k_totals(const uint32_t* counters, int nb, unsigned long long va
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned long long closest = valid_paths, shadow = 0;
     for (int b = 0; b < nb; b++) { if (b > 0) closest += counters[2 * b]; shadow += counters[PTB_CNT_SQ + b]; }
-    totals[0] += closest;
-    totals[1] += shadow;
+    atomicAdd(&totals[0], closest);   // passes of different pipelines finish concurrently
+    atomicAdd(&totals[1], shadow);
 }
 
 __global__ void __launch_bounds__(256) k_resolve(const F4* accum, size_t n, float gamma, float* imagedouble, float* sample_count, uint8_t* image) {
@@ -427,6 +428,7 @@ __global__ void k_kat(int which, SceneDev sc, CameraDev cam, FilterDev filt, int
     case PTB_KAT_FAST_NORMALIZE: { V3 v = fast_normalize(v3((float)a[0], (float)a[1], (float)a[2])); o[0] = v.x; o[1] = v.y; o[2] = v.z; } break;
     case PTB_KAT_RANDOM_PER_PIXEL: { float x, y; random_per_pixel((uint32_t)a[0], x, y); o[0] = x; o[1] = y; } break;
     case PTB_KAT_FILTER_RATIO: { int b0, b1, b2, b3; o[0] = filter_ratio(filt, (int)a[0], (int)a[1], W, H, b0, b1, b2, b3); } break;
+    case PTB_KAT_MERL_INDEX: { int f, e; merl_index_both(v3((float)a[0], (float)a[1], (float)a[2]), v3((float)a[3], (float)a[4], (float)a[5]), f, e); o[0] = f; o[1] = e; } break;
     default: break;
     }
 }
@@ -471,6 +473,13 @@ struct ptb_ctx {
     int64_t lowres_n = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // pass pipelines (PTB_OPT_PIPES): consecutive passes of a linear render go round-robin to `n_pipes` streams, each with its own
+    // slice of the path pool, queues and counters, so that the latency-bound k_shade of one pass shares the SMs with the issue-bound
+    // k_trace of another and the tails of the persistent kernels are filled.  Pipe 0 is `stream`.
+    int n_pipes = 2;                           // measured (profiles/r01m): 2 pipelines with 6 resident k_trace blocks per SM each: +3 % on C2 / C4, +1 % on C3
+    int trace_blocks_piped = 148 * 6;          // persistent grid of k_trace per pipeline when more than one runs
+    cudaStream_t pipe_stream[PTB_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done[PTB_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};
     bool count_traversal = false;
     bool time_kernels = false;
     bool has_merl = false;
@@ -578,12 +587,13 @@ int ptb_create(int device_id, ptb_ctx** out) {
     ptb_ctx* c = new ptb_ctx();
     c->device = device_id;
     if (const char* e = getenv("PTB_SHADE_MINB")) c->shade_minb = atoi(e);
+    if (const char* e = getenv("PTB_PIPES")) c->n_pipes = std::max(1, std::min(atoi(e), PTB_MAX_PIPES));
     if (const char* e = getenv("PTB_SORT_HITS")) c->sort_hits = atoi(e) != 0;   // experiments: 0 = k_shade sees every hit
     memset(&c->pool, 0, sizeof(c->pool));
     memset(&c->sc, 0, sizeof(c->sc));
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaMalloc((void**)&c->d_counters, PTB_N_COUNTERS * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_counters, PTB_MAX_PIPES * PTB_N_COUNTERS * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc((void**)&c->d_totals, PTB_N_TOTALS * sizeof(unsigned long long)) != cudaSuccess) {
         g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
         delete c;
@@ -594,6 +604,7 @@ int ptb_create(int device_id, ptb_ctx** out) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, false>, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 8;
         c->trace_blocks = sms * per_sm;
+        c->trace_blocks_piped = sms * std::max(1, (per_sm * 2 + 2) / 3);   // 6 of 9: two pipelines in their trace phase still fill the SM
     }
     *out = c;
     return PTB_OK;
@@ -609,6 +620,7 @@ void ptb_destroy(ptb_ctx* c) {
     for (void* p : ptrs) if (p) cudaFree(p);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (int i = 1; i < PTB_MAX_PIPES; i++) { if (c->pipe_stream[i]) cudaStreamDestroy(c->pipe_stream[i]); if (c->pipe_done[i]) cudaEventDestroy(c->pipe_done[i]); }
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -780,20 +792,33 @@ static int frame_setup(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
 
 // PTB_OPT_TIME_KERNELS: a start/stop event pair around one launch, on the launching stream
 struct LaunchTimer {
-    ptb_ctx* c; size_t used = 0;
+    ptb_ctx* c; size_t used = 0; cudaStream_t cur = nullptr;
     explicit LaunchTimer(ptb_ctx* ctx) : c(ctx) { c->ev_kind.clear(); }
-    void begin(int kind) {
+    void begin(int kind, cudaStream_t st = nullptr) {
         if (!c->time_kernels) return;
+        cur = st ? st : c->stream;
         if (used + 2 > c->ev_pool.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); c->ev_pool.push_back(a); c->ev_pool.push_back(b); }
         c->ev_kind.push_back(kind);
-        cudaEventRecord(c->ev_pool[used], c->stream);
+        cudaEventRecord(c->ev_pool[used], cur);
     }
     void end() {
         if (!c->time_kernels) return;
-        cudaEventRecord(c->ev_pool[used + 1], c->stream);
+        cudaEventRecord(c->ev_pool[used + 1], cur);
         used += 2;
     }
 };
+
+// the slice of the path pool that starts at path `off` (one pipeline's share; queue entries are indices relative to it)
+static PoolDev pool_slice(const PoolDev& p, size_t off) {
+    if (off == 0) return p;
+    PoolDev s = p;
+    F4** f4s[] = {&s.ray_o, &s.ray_d, &s.weight, &s.radiance, &s.hit, &s.sh_o, &s.sh_d, &s.sh_c, &s.aov_n, &s.aov_kd, &s.probe_o, &s.probe_d, &s.probe_x, &s.hit2};
+    for (F4** q : f4s) if (*q) *q += off;
+    if (s.rng) s.rng += off;
+    if (s.pixel) s.pixel += off;
+    if (s.root) s.root += off;
+    return s;
+}
 
 // the pass loop; accumulates into d_rgbw (device, W*H float4)
 // samples k_first .. k_first + nrays - 1 of every pixel of the shard
@@ -824,14 +849,23 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
         if (branch && f.accum_albedo) { c->err = "denoiser inputs are not available with fog, ghost objects, subsurface scattering or a background photograph"; return PTB_ERR_UNSUPPORTED; }
         const int64_t pool_cap_slots = pool;
         pool = std::max<int64_t>(pool / fan, 1024);
+        const int n_pipes = branch ? 1 : std::max(1, std::min(c->n_pipes, PTB_MAX_PIPES));
+        if (n_pipes > 1 && pixel_slots * nrays < pool * n_pipes)   // a frame smaller than the pools is still split so that every pipeline gets a pass
+            pool = std::max<int64_t>((pixel_slots * nrays + n_pipes - 1) / n_pipes, (int64_t)1 << 18);
         int spp_pass; int64_t slots_pass;
         if (pixel_slots * nrays <= pool) { spp_pass = nrays; slots_pass = pixel_slots; }
         else if (pixel_slots <= pool) { spp_pass = (int)std::max<int64_t>(1, pool / pixel_slots); slots_pass = pixel_slots; }
         else { spp_pass = 1; slots_pass = (pool / (f.tile * f.tile)) * (f.tile * f.tile); if (slots_pass <= 0) slots_pass = f.tile * f.tile; }
         const bool aov = f.accum_albedo != nullptr;
-        int rc = ensure_pool(c, branch ? std::max<int64_t>(slots_pass * spp_pass * fan, pool_cap_slots) : slots_pass * spp_pass, aov, branch, c->sc.has_sss != 0);
+        const int64_t stride = slots_pass * spp_pass;   // paths per pass = pool slice of one pipeline
+        int rc = ensure_pool(c, branch ? std::max<int64_t>(stride * fan, pool_cap_slots) : stride * n_pipes, aov, branch, c->sc.has_sss != 0);
         if (rc) return rc;
+        for (int i = 1; i < n_pipes; i++) {
+            if (!c->pipe_stream[i]) { CK(cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->pipe_done[i], cudaEventDisableTiming)); }
+            CK(cudaStreamWaitEvent(c->pipe_stream[i], c->ev0, 0));
+        }
         const int nb = f.nb_bounces;
+        int64_t pass_index = 0;
         for (int64_t s0 = 0; s0 < pixel_slots; s0 += slots_pass) {
             const int64_t ns = std::min(slots_pass, pixel_slots - s0);
             // valid pixels in this slot range (for the ray statistics)
@@ -852,9 +886,16 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                 f.n_pixel_slots = (int)ns;
                 const int n_paths = (int)(ns * f.spp_pass);
                 const unsigned g256 = (unsigned)((n_paths + 255) / 256), g128 = (unsigned)((n_paths + 127) / 128);
-                CK(cudaMemsetAsync(c->d_counters, 0, PTB_N_COUNTERS * sizeof(uint32_t), c->stream));
-                lt.begin(0);
-                k_raygen<<<g256, 256, 0, c->stream>>>(c->sc, f, c->pool, n_paths);
+                // this pass's pipeline: stream, pool slice, queues, counters (pipe 0 = the context's own; branching renders only use pipe 0)
+                const int pi = (int)(pass_index++ % n_pipes);
+                cudaStream_t ps = pi ? c->pipe_stream[pi] : c->stream;
+                const PoolDev pp = pool_slice(c->pool, (size_t)pi * (size_t)stride);
+                uint32_t* const pq[2] = {c->d_queue[0] + (size_t)pi * stride, c->d_queue[1] + (size_t)pi * stride};
+                uint32_t* const pqs = c->d_queue_surf + (size_t)pi * stride;
+                uint32_t* const pc = c->d_counters + (size_t)pi * PTB_N_COUNTERS;
+                CK(cudaMemsetAsync(pc, 0, PTB_N_COUNTERS * sizeof(uint32_t), ps));
+                lt.begin(0, ps);
+                k_raygen<<<g256, 256, 0, ps>>>(c->sc, f, pp, n_paths);
                 lt.end();
                 launches++;
                 int levels = nb;
@@ -938,29 +979,28 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     }
                 }
                 for (int b = 0; b < nb && !branch; b++) {
-                    const uint32_t* q = b == 0 ? nullptr : c->d_queue[b & 1];
-                    const uint32_t* cnt = b == 0 ? nullptr : c->d_counters + 2 * b;
+                    const uint32_t* q = b == 0 ? nullptr : pq[b & 1];
+                    const uint32_t* cnt = b == 0 ? nullptr : pc + 2 * b;
                     const bool mesh = c->sc.has_mesh != 0;
                     // persistent grid: as many blocks as are resident at once, but no more than the queue can feed
-                    const unsigned gt = (unsigned)std::max(1, std::min<int>(c->trace_blocks, (n_paths + 127) / 128));
+                    const unsigned gt = (unsigned)std::max(1, std::min<int>(n_pipes > 1 ? c->trace_blocks_piped : c->trace_blocks, (n_paths + 127) / 128));
                     if (mesh) {
-                        lt.begin(1 | (b << 8));
-                        if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
-                        else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_counters + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                        lt.begin(1 | (b << 8), ps);
+                        if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, ps>>>(c->sc, pp, q, cnt, n_paths, pc + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                        else k_trace<false, false><<<gt, 128, 0, ps>>>(c->sc, pp, q, cnt, n_paths, pc + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
                         lt.end();
                         launches++;
                     }
-                    lt.begin(2 | (b << 8));
+                    lt.begin(2 | (b << 8), ps);
                     // optional: terminal hits (miss / light / dome) shaded by a compaction pass, k_shade sees surface hits only (off: measured slower)
                     const bool sorted = c->sort_hits && !(aov && b == 0);
                     const uint32_t* sq = q; const uint32_t* scnt = cnt;
                     if (sorted) {
-                        k_sort_hits<<<g256, 256, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, c->d_queue_surf, c->d_counters + PTB_CNT_SURF + b);
-                        sq = c->d_queue_surf; scnt = c->d_counters + PTB_CNT_SURF + b;
+                        k_sort_hits<<<g256, 256, 0, ps>>>(c->sc, pp, q, cnt, n_paths, pqs, pc + PTB_CNT_SURF + b);
+                        sq = pqs; scnt = pc + PTB_CNT_SURF + b;
                         launches++;
                     }
-#define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<g128, 128, 0, c->stream>>>(c->sc, f, c->pool, sq, scnt, n_paths, c->d_queue[(b + 1) & 1], c->d_counters + 2 * (b + 1), \
-                                                                          c->d_counters + 2 * b + 1, c->d_counters + PTB_CNT_SQ + b)
+#define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<g128, 128, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
                     if (aov && b == 0) { if (c->has_merl) PTB_SHADE(true, 5, true); else PTB_SHADE(false, 6, true); }   // camera rays of a denoiser-input render
                     else if (c->has_merl) PTB_SHADE(true, 5, false);
                     else if (c->shade_minb == 8) PTB_SHADE(false, 8, false);
@@ -970,20 +1010,24 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     lt.end();
                     launches++;
                     if (mesh) {
-                        lt.begin(3 | (b << 8));
-                        if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
-                        else k_trace<true, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, c->d_counters + 2 * b + 1, 0, c->d_counters + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                        lt.begin(3 | (b << 8), ps);
+                        if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, ps>>>(c->sc, pp, nullptr, pc + 2 * b + 1, 0, pc + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                        else k_trace<true, false><<<gt, 128, 0, ps>>>(c->sc, pp, nullptr, pc + 2 * b + 1, 0, pc + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
                         lt.end();
                         launches++;
                     }
                 }
-                lt.begin(4);
-                k_splat<<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(f, c->pool, d_rgbw);
+                lt.begin(4, ps);
+                k_splat<<<(unsigned)((ns + 127) / 128), 128, 0, ps>>>(f, pp, d_rgbw);
                 lt.end();
-                k_totals<<<1, 32, 0, c->stream>>>(c->d_counters, levels, (nb > 0 && !branch) ? valid_here * (unsigned long long)f.spp_pass : 0ull, c->d_totals);
+                k_totals<<<1, 32, 0, ps>>>(pc, levels, (nb > 0 && !branch) ? valid_here * (unsigned long long)f.spp_pass : 0ull, c->d_totals);
                 launches += 2;
                 CK(cudaGetLastError());
             }
+        }
+        for (int i = 1; i < n_pipes; i++) {   // join the pipelines on the context's stream
+            CK(cudaEventRecord(c->pipe_done[i], c->pipe_stream[i]));
+            CK(cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
         }
     }
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -1249,8 +1293,9 @@ int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
     case PTB_OPT_REFILL_BELOW: if (value < 1 || value > 33) return PTB_ERR_INVALID; c->refill_below = (int)value; return PTB_OK;
     case PTB_OPT_TRI_FRACTION: if (value < 1 || value > 64) return PTB_ERR_INVALID; c->tri_den = (int)value; return PTB_OK;
     case PTB_OPT_TRI_MIN_PCT: if (value < 0 || value > 100) return PTB_ERR_INVALID; c->tri_min_pct = (int)value; return PTB_OK;
-    case PTB_OPT_TRACE_BLOCKS: if (value < 1) return PTB_ERR_INVALID; c->trace_blocks = (int)value; return PTB_OK;
+    case PTB_OPT_TRACE_BLOCKS: if (value < 1) return PTB_ERR_INVALID; c->trace_blocks = c->trace_blocks_piped = (int)value; return PTB_OK;
     case PTB_OPT_SORT_HITS: c->sort_hits = value != 0; return PTB_OK;
+    case PTB_OPT_PIPES: if (value < 1 || value > PTB_MAX_PIPES) return PTB_ERR_INVALID; c->n_pipes = (int)value; return PTB_OK;
     default: return PTB_OK;  // unknown options (e.g. the CPU checkers' thread count) are ignored
     }
 }

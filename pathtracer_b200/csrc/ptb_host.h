@@ -104,6 +104,11 @@ inline void scene_header(SceneDev& sc, FlatScene& f) {
             AnalyticDev& a = sc.analytic[sc.n_inline++];
             a.type = o.type | ((o.flags & FLAG_GHOST) ? PTB_ANALYTIC_GHOST : 0); a.id = (int32_t)i; a.R2 = o.R2;
             for (int k = 0; k < 12; k++) a.inv_trans[k] = o.inv_trans[k];
+            // the light, the dome and the ground plane are normally placed without rotation or scaling: mark an exact identity linear
+            // part so that the ray producers skip the 3x3 products (m = I gives bit-identical results: 1*x + 0*y + 0*z == x)
+            const float* m = a.inv_trans;
+            if (m[0] == 1.f && m[1] == 0.f && m[2] == 0.f && m[4] == 0.f && m[5] == 1.f && m[6] == 0.f && m[8] == 0.f && m[9] == 0.f && m[10] == 1.f)
+                a.type |= PTB_ANALYTIC_LINEAR_ID;
             for (int k = 0; k < 3; k++) { a.a[k] = o.a[k]; a.n[k] = o.n[k]; }
         } else { o.flags |= FLAG_NOT_INLINE; sc.n_extra++; }
     }

@@ -55,6 +55,7 @@ struct AnalyticDev {
 };
 
 #define PTB_ANALYTIC_GHOST (1 << 30)
+#define PTB_ANALYTIC_LINEAR_ID (1 << 29)   /* inv_trans = [I | t] exactly */
 struct FogDev {                 // Scene::fog_* (Geometry.h:1371-1377) + the ground level fogContribution reads (Raytracer.cpp:54)
     float density, absorption, density_decay, absorption_decay, phase_aniso, ground;
     int32_t type, phase_type;
@@ -155,9 +156,15 @@ PTB_HD int32_t hit_id_analytic(int obj) { return -2 - obj; }
 // Nearest hit over the analytic objects (Sphere / Plane) of Scene::intersection's loop (Geometry.cpp:601-626):
 // object-space rays, world t.  Meshes are handled by the wide BVH afterwards.
 PTB_HD bool analytic_t(int type, const float* inv_trans, const float* A, const float* N, float R2, V3 o, V3 d, float& t) {
-    const V3 dl = xf_dir(inv_trans, d);
-    const V3 ol = xf_point(inv_trans, o);
-    return (type == OBJ_SPHERE) ? sphere_t(A, R2, ol, dl, t) : plane_t(A, N, ol, dl, t);
+    V3 dl, ol;
+    if (type & PTB_ANALYTIC_LINEAR_ID) {   // uniform per object; same bits as the general form for m = [I | t]
+        dl = d;
+        ol = v3(o.x + inv_trans[3], o.y + inv_trans[7], o.z + inv_trans[11]);
+    } else {
+        dl = xf_dir(inv_trans, d);
+        ol = xf_point(inv_trans, o);
+    }
+    return ((type & 0xff) == OBJ_SPHERE) ? sphere_t(A, R2, ol, dl, t) : plane_t(A, N, ol, dl, t);
 }
 PTB_HD void analytic_closest(const SceneDev& sc, V3 o, V3 d, float& tmin, int32_t& id) {
     tmin = INFINITY;
@@ -167,7 +174,7 @@ PTB_HD void analytic_closest(const SceneDev& sc, V3 o, V3 d, float& tmin, int32_
     for (int i = 0; i < sc.n_inline; i++) {
         const AnalyticDev& ob = sc.analytic[i];
         float t;
-        if (analytic_t(ob.type & 0xff, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && t < tmin) { tmin = t; best = ob.id; }
+        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && t < tmin) { tmin = t; best = ob.id; }
     }
     if (sc.n_extra > 0)
         for (int i = 0; i < sc.n_objects; i++) {
@@ -185,7 +192,7 @@ PTB_HD bool analytic_occluded(const SceneDev& sc, V3 o, V3 d, float dist_light) 
         const AnalyticDev& ob = sc.analytic[i];
         if (ob.type & PTB_ANALYTIC_GHOST) continue;   // avoid_ghosts (Geometry.cpp:722)
         float t;
-        if (analytic_t(ob.type & 0xff, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (double)t < lim) return true;
+        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (double)t < lim) return true;
     }
     if (sc.n_extra > 0)
         for (int i = 0; i < sc.n_objects; i++) {

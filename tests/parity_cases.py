@@ -205,6 +205,33 @@ def case_kats(test_lib, gold):
     rt.close()
 
 
+def case_merl_index_fast(test_lib, n=400000):
+    """The float evaluation of the MERL bin index (merl_index_fast) either declines or returns the bin of the double path
+    (MERLBRDFRead.cpp:76-207): random pairs as the integrator makes them, plus the ill-conditioned corners (direction next to the
+    normal, half vector next to the normal, coincident directions, grazing directions)."""
+    rng = np.random.default_rng(20261017)
+    def hemi(m):
+        r2, ph = rng.random(m), 2 * np.pi * rng.random(m)
+        s = np.sqrt(1 - r2)
+        return np.stack([np.cos(ph) * s, np.sin(ph) * s, np.sqrt(r2)], -1)
+    a, b = hemi(n), hemi(n)
+    k = n // 8
+    b[:k] = a[:k] + 1e-3 * (rng.random((k, 3)) - .5)                                       # theta_diff -> 0
+    b[k:2 * k] = a[k:2 * k] * np.array([-1, -1, 1]) + 1e-3 * (rng.random((k, 3)) - .5)        # half vector -> normal
+    b[2 * k:3 * k] = np.array([0, 0, 1]) + 3e-3 * (rng.random((k, 3)) - .5)                  # wo -> normal
+    a[3 * k:4 * k, 2] = 1e-3 * rng.random(k)                                                 # grazing wi
+    a /= np.linalg.norm(a, axis=1, keepdims=True); b /= np.linalg.norm(b, axis=1, keepdims=True)
+    inp = np.concatenate([a, b], -1).astype(np.float32).astype(np.float64)
+    rt = scenes.config_C4(test_lib, 16, 16, 1, nv=8).commit()
+    out = rt.kat(_abi.KAT_MERL_INDEX, inp)
+    rt.close()
+    fast, exact = out[:, 0].astype(np.int64), out[:, 1].astype(np.int64)
+    took = fast >= 0
+    assert (fast[took] == exact[took]).all(), f"{(fast[took] != exact[took]).sum()} bins differ"
+    assert took[4 * k:].mean() > 0.97, "the float path should answer almost every ordinary pair"
+    assert (exact >= 0).all() and (exact < 90 * 90 * 180).all()
+
+
 # ---- edge cases -------------------------------------------------------------------------------------------------
 def quad_mesh(n=6, with_uv=True, with_normals=True, groups=False):
     """A wavy (n x n)-quad sheet in file axes."""

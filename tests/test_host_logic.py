@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
-from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
+from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_passes_and_shards,
                           case_progressive, case_scene, check_ids)
 
 from pathtracer_b200 import _abi, scenes
@@ -16,6 +16,10 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def test_kats_devsim(devsim):
     case_kats(devsim, np.load(os.path.join(GOLD, "kat.npz")))
+
+
+def test_merl_index_fast_devsim(devsim):
+    case_merl_index_fast(devsim)
 
 
 @pytest.mark.parametrize("name", sorted(SCENES))

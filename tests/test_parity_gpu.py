@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
-from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_passes_and_shards,
+from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_passes_and_shards,
                           case_progressive, case_scene, check_ids, check_images)
 
 from pathtracer_b200 import _abi, scenes
@@ -28,6 +28,11 @@ def test_native_library_is_what_runs(gpu):
 
 def test_kats_gpu(gpu):
     case_kats(gpu, np.load(os.path.join(GOLD, "kat.npz")))
+
+
+def test_merl_index_fast_gpu(gpu):
+    """the device's float path (its own atan2f / sqrtf / division) against the device's double path"""
+    case_merl_index_fast(gpu, n=2000000)
 
 
 @pytest.mark.parametrize("name", sorted(SCENES))
@@ -182,6 +187,25 @@ def test_determinism_and_seed(gpu):
 
 
 # ---- full-size properties (BASELINE.json sizes; the oracle cannot run these in seconds) -----------------------------
+def test_pass_pipelines_same_frame(gpu):
+    """PTB_OPT_PIPES: the passes of a render spread over 1..4 streams with their own pool slices give the same frame (up to the
+    order of the float adds into the accumulator) and exactly the same ray counters."""
+    rt = scenes.config_C2(gpu, 256, 192, 24, nv=40, env=(64, 32)).commit()
+    rt.set_option(_abi.OPT_POOL_PATHS, 1 << 18)          # 256*192*24 = 1.18M paths -> 5 passes or more
+    rt.set_option(_abi.OPT_PIPES, 1)
+    ref = rt.render_image_nopreviz().copy()
+    st = dict(rt.stats)
+    cnt = rt.sample_count.copy()
+    for pipes in (2, 3, 4):
+        rt.set_option(_abi.OPT_PIPES, pipes)
+        img = rt.render_image_nopreviz()
+        assert np.allclose(img, ref, rtol=5e-5, atol=1e-2 * float(ref.mean()) * 1e-3), pipes
+        assert np.allclose(rt.sample_count, cnt, rtol=1e-5)
+        for k in ("samples", "rays_closest", "rays_shadow"):
+            assert rt.stats[k] == st[k], (pipes, k)
+    assert gpu.set_option(rt._ctx, _abi.OPT_PIPES, 5) != 0 and gpu.set_option(rt._ctx, _abi.OPT_PIPES, 0) != 0
+
+
 def test_full_size_C2_properties(gpu):
     """1,000,000 triangles, 1024x1024: traversal counters, pass splitting and weight normalisation at full size."""
     rt = scenes.config_C2(gpu, spp=4).commit()
@@ -202,7 +226,7 @@ def test_full_size_C2_properties(gpu):
     rt2.set_option(_abi.OPT_POOL_PATHS, 1 << 19)
     img2 = rt2.render_image_nopreviz()
     assert np.allclose(img2, img, rtol=5e-5, atol=1e-2)
-    assert rt2.stats["rays_closest"] == st["rays_closest"] and rt2.stats["kernel_launches"] > 4 * st["kernel_launches"]
+    assert rt2.stats["rays_closest"] == st["rays_closest"] and rt2.stats["kernel_launches"] > 2 * st["kernel_launches"]
     # primary ids: every mesh pixel reports a valid original triangle id
     obj, tri, t = rt.primary_ids()
     assert ((obj == 3) == (tri >= 0)).all() and tri.max() < 1000000 and (t[obj >= 0] > 0).all()
