@@ -20,6 +20,13 @@
 #define PTB_HD inline
 #define PTB_D inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define PTB_HD_NOINLINE __host__ __device__ __noinline__
+#elif defined(__CUDACC__)
+#define PTB_HD_NOINLINE __host__ __device__
+#else
+#define PTB_HD_NOINLINE inline
+#endif
 
 #define PTB_PI_F 3.14159274101257324f            /* float(M_PI) */
 #define PTB_PI_D 3.1415926535897932              /* M_PI as the reference defines it, Vector.h:8-10 */
@@ -256,7 +263,9 @@ PTB_HD void merl_rotate(const double* v, const double* axis, double angle, doubl
     double cr[3] = {axis[1] * v[2] - axis[2] * v[1], axis[2] * v[0] - axis[0] * v[2], axis[0] * v[1] - axis[1] * v[0]};
     out[0] += cr[0] * s; out[1] += cr[1] * s; out[2] += cr[2] * s;
 }
-PTB_HD int merl_index(double theta_in, double fi_in, double theta_out, double fi_out) {
+// Out of line on the device: it is the rare fallback of merl_index_fast, and inlined it dictates the register allocation of the
+// whole shade kernel (102 registers, 5 blocks/SM).
+PTB_HD_NOINLINE int merl_index(double theta_in, double fi_in, double theta_out, double fi_out) {
     const double MPI = 3.1415926535897932384626433832795;
     double in_z = cos(theta_in), pin = sin(theta_in);
     double in_x = pin * cos(fi_in), in_y = pin * sin(fi_in);
@@ -306,12 +315,17 @@ PTB_HD int merl_index(double theta_in, double fi_in, double theta_out, double fi
 // and the caller runs the double path, so the bin index is the reference's in both cases (checked against the double path on 1e8
 // random direction pairs by tests/test_host_logic.py::test_merl_index_fast, and on the device by the MERL KAT).
 #if !defined(PTB_MERL_EPS0)
-#define PTB_MERL_EPS0 1.5e-6f
+#define PTB_MERL_EPS0 2.5e-6f   /* device atan2f: 2 ulp of an azimuth up to 2 pi = 1e-6; acosf; the float arithmetic here */
 #endif
 PTB_HD bool merl_index_fast(V3 wil, V3 wol, int& ind) {
     const float HALF_PI = 1.57079632679489662f, INV_PI_180 = 57.2957795130823209f;   // 180/pi = 90/(pi/2)
-    const float li = 1.f / sqrtf(dot(wil, wil)), lo = 1.f / sqrtf(dot(wol, wol));
-    const V3 in = wil * li, out = wol * lo;
+    // the reference goes through theta = acosf(z), phi = atan2f(y, x) and rebuilds (sin theta cos phi, sin theta sin phi, cos theta):
+    // z is kept AS IS (the local vectors are only approximately unit: the shading normal comes from fast_normalize) and (x, y) only
+    // give the azimuth
+    const float ri2 = wil.x * wil.x + wil.y * wil.y, ro2 = wol.x * wol.x + wol.y * wol.y;
+    if (!(ri2 > 1e-12f && ro2 > 1e-12f)) return false;
+    const float si = sqrtf((1.f - wil.z) * (1.f + wil.z)) / sqrtf(ri2), so = sqrtf((1.f - wol.z) * (1.f + wol.z)) / sqrtf(ro2);
+    const V3 in = v3(wil.x * si, wil.y * si, wil.z), out = v3(wol.x * so, wol.y * so, wol.z);
     V3 h = in + out;
     const float hl2 = dot(h, h);
     if (!(hl2 > 1e-4f)) return false;

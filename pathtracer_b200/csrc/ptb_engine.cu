@@ -483,10 +483,11 @@ struct ptb_ctx {
     bool count_traversal = false;
     bool time_kernels = false;
     bool has_merl = false;
+    int shade_minb_merl = 8;                   // the same for scenes with a MERL object (PTB_SHADE_MINB_MERL: 5, 6 or 8; measured r01m: 89.0 / 81.2 / 76.8 ms on C4)
     int shade_minb = 8;                        // k_shade variant (resident blocks/SM the compiler must allow); PTB_SHADE_MINB overrides for experiments
     int trace_blocks = 148 * 8;                // persistent grid of k_trace, set from the occupancy query in ptb_create
     int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
-    int tri_min_pct = 0;                       // the triangle phase starts once this share of a warp's live lanes hold triangles
+    int tri_min_pct = 25;                      // the triangle phase starts once this share of a warp's live lanes hold triangles
     int tri_den = 4;                           // triangle steps repeat while >= 1/tri_den of the live lanes take part
     std::vector<cudaEvent_t> ev_pool;          // PTB_OPT_TIME_KERNELS: start/stop pairs, one per launch
     std::vector<int> ev_kind;
@@ -587,6 +588,7 @@ int ptb_create(int device_id, ptb_ctx** out) {
     ptb_ctx* c = new ptb_ctx();
     c->device = device_id;
     if (const char* e = getenv("PTB_SHADE_MINB")) c->shade_minb = atoi(e);
+    if (const char* e = getenv("PTB_SHADE_MINB_MERL")) c->shade_minb_merl = atoi(e);
     if (const char* e = getenv("PTB_PIPES")) c->n_pipes = std::max(1, std::min(atoi(e), PTB_MAX_PIPES));
     if (const char* e = getenv("PTB_SORT_HITS")) c->sort_hits = atoi(e) != 0;   // experiments: 0 = k_shade sees every hit
     memset(&c->pool, 0, sizeof(c->pool));
@@ -1002,7 +1004,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     }
 #define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<g128, 128, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
                     if (aov && b == 0) { if (c->has_merl) PTB_SHADE(true, 5, true); else PTB_SHADE(false, 6, true); }   // camera rays of a denoiser-input render
-                    else if (c->has_merl) PTB_SHADE(true, 5, false);
+                    else if (c->has_merl) { if (c->shade_minb_merl == 8) PTB_SHADE(true, 8, false); else if (c->shade_minb_merl == 6) PTB_SHADE(true, 6, false); else PTB_SHADE(true, 5, false); }
                     else if (c->shade_minb == 8) PTB_SHADE(false, 8, false);
                     else if (c->shade_minb == 10) PTB_SHADE(false, 10, false);
                     else PTB_SHADE(false, 6, false);
