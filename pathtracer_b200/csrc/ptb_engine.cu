@@ -234,24 +234,24 @@ template <bool MERL, int MINB, bool AOV>
 __global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
                                                const uint32_t* __restrict__ count, int n_static, uint32_t* __restrict__ next_queue,
                                                uint32_t* next_count, uint32_t* shadow_count, uint32_t* shadow_queries) {
+    // one thread per pool slot; the queue length lives in device memory, so after the first bounce most blocks return at once.
+    // A bounded grid striding over the live part of the queue was measured (profiles/r01m_ab_prefetch_shadegrid.txt): the loop
+    // costs registers the 64-register kernel does not have (spills: +3 % on C2, +25 % with the MERL lookup) and saves nothing.
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = count ? (int)*count : n_static;
-    // grid-stride over the queue: the launch is sized for the pool (the queue length lives in device memory), so after the first
-    // bounce most blocks of a one-thread-per-slot launch would find nothing to do; a bounded grid walks the live part instead
-    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid - (int)(threadIdx.x & 31) < n; tid += gridDim.x * blockDim.x) {
-        ShadeOut out;
-        out.cont = false; out.shadow = false; out.shadow_query = false;
-        int path = 0;
-        if (tid < n) {
-            path = queue ? (int)queue[tid] : tid;
-            shade_one<MERL, AOV>(sc, f, p, path, out);
-        }
-        const uint32_t qi = warp_push(next_count, out.cont);
-        if (out.cont) next_queue[qi] = (uint32_t)path;
-        const uint32_t si = warp_push(shadow_count, out.shadow);
-        if (out.shadow) { p.sh_o[si] = out.sh_o; p.sh_d[si] = out.sh_d; p.sh_c[si] = out.sh_c; }
-        const uint32_t sq = __ballot_sync(0xffffffffu, out.shadow_query);
-        if ((threadIdx.x & 31) == 0 && sq) atomicAdd(shadow_queries, (uint32_t)__popc(sq));
+    ShadeOut out;
+    out.cont = false; out.shadow = false; out.shadow_query = false;
+    int path = 0;
+    if (tid < n) {
+        path = queue ? (int)queue[tid] : tid;
+        shade_one<MERL, AOV>(sc, f, p, path, out);
     }
+    const uint32_t qi = warp_push(next_count, out.cont);
+    if (out.cont) next_queue[qi] = (uint32_t)path;
+    const uint32_t si = warp_push(shadow_count, out.shadow);
+    if (out.shadow) { p.sh_o[si] = out.sh_o; p.sh_d[si] = out.sh_d; p.sh_c[si] = out.sh_c; }
+    const uint32_t sq = __ballot_sync(0xffffffffu, out.shadow_query);
+    if ((threadIdx.x & 31) == 0 && sq) atomicAdd(shadow_queries, (uint32_t)__popc(sq));
 }
 
 // Branching renders (fog, ghost objects, background photograph): one getColor loop iteration per queue entry; side branches
@@ -487,7 +487,6 @@ struct ptb_ctx {
     bool time_kernels = false;
     bool has_merl = false;
     int shade_minb_merl = 8;                   // the same for scenes with a MERL object (PTB_SHADE_MINB_MERL: 5, 6 or 8; measured r01m: 89.0 / 81.2 / 76.8 ms on C4)
-    int shade_grid = 0;                        // blocks of k_shade after the first bounce (0: one thread per pool slot); PTB_SHADE_GRID
     int shade_minb = 8;                        // k_shade variant (resident blocks/SM the compiler must allow); PTB_SHADE_MINB overrides for experiments
     int trace_blocks = 148 * 8;                // persistent grid of k_trace, set from the occupancy query in ptb_create
     int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
@@ -593,7 +592,6 @@ int ptb_create(int device_id, ptb_ctx** out) {
     c->device = device_id;
     if (const char* e = getenv("PTB_SHADE_MINB")) c->shade_minb = atoi(e);
     if (const char* e = getenv("PTB_SHADE_MINB_MERL")) c->shade_minb_merl = atoi(e);
-    if (const char* e = getenv("PTB_SHADE_GRID")) c->shade_grid = atoi(e);
     if (const char* e = getenv("PTB_PIPES")) c->n_pipes = std::max(1, std::min(atoi(e), PTB_MAX_PIPES));
     if (const char* e = getenv("PTB_SORT_HITS")) c->sort_hits = atoi(e) != 0;   // experiments: 0 = k_shade sees every hit
     memset(&c->pool, 0, sizeof(c->pool));
@@ -998,7 +996,6 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         lt.end();
                         launches++;
                     }
-                    const unsigned gsh = (c->shade_grid > 0 && b > 0) ? std::min<unsigned>(g128, (unsigned)c->shade_grid) : g128;
                     lt.begin(2 | (b << 8), ps);
                     // optional: terminal hits (miss / light / dome) shaded by a compaction pass, k_shade sees surface hits only (off: measured slower)
                     const bool sorted = c->sort_hits && !(aov && b == 0);
@@ -1008,7 +1005,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         sq = pqs; scnt = pc + PTB_CNT_SURF + b;
                         launches++;
                     }
-#define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<gsh, 128, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
+#define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<g128, 128, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
                     if (aov && b == 0) { if (c->has_merl) PTB_SHADE(true, 5, true); else PTB_SHADE(false, 6, true); }   // camera rays of a denoiser-input render
                     else if (c->has_merl) { if (c->shade_minb_merl == 8) PTB_SHADE(true, 8, false); else if (c->shade_minb_merl == 6) PTB_SHADE(true, 6, false); else PTB_SHADE(true, 5, false); }
                     else if (c->shade_minb == 8) PTB_SHADE(false, 8, false);
@@ -1311,7 +1308,7 @@ int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
 int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
     if (!c || !info) return PTB_ERR_INVALID;
     memset(info, 0, sizeof(*info));
-    info->n_triangles = c->bytes_tris / 48;
+    info->n_triangles = c->flat.n_tri_scene;   // as handed over; bytes_triangles counts those resident (alpha maps can rule triangles out, scene_host.cpp)
     info->n_bvh_nodes = c->flat.bvh.n_nodes;
     info->bytes_nodes = c->bytes_nodes; info->bytes_triangles = c->bytes_tris; info->bytes_attributes = c->bytes_attr; info->bytes_textures = c->bytes_tex;
     info->n_objects = (int32_t)c->host.objects.size();

@@ -64,6 +64,8 @@ struct FlatScene {
     Bvh8Stats bvh;
     double ms_bvh = 0;
     bool has_sss = false;                  // some mesh group carries a subsurface albedo
+    int64_t n_tri_scene = 0;               // triangles handed over (tris holds those that can ever be hit, see alpha classification)
+    int64_t n_tri_alpha_opaque = 0, n_tri_alpha_invisible = 0, n_tri_alpha_tested = 0;
 };
 
 struct HostScene {

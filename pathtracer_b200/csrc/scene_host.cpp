@@ -195,6 +195,54 @@ static TexDev put_tex(const HostTex& t, std::vector<float>& pool) {
     return d;
 }
 
+// ---- alpha-map pre-classification ------------------------------------------------------------------------------
+// The reference rejects a hit whose alpha texel reads < 0.5 inside the traversal (TriangleMesh.cpp:1198-1205).  Which texels a
+// triangle can ever read is known at commit time: the uv of a hit is a convex combination of the corner uvs, the lookup is
+// nearest-texel after wrapping (BRDF.h:270-300).  With a summed-area table of "this texel rejects" per alpha map, a triangle whose
+// (conservatively padded) texel rectangle holds no rejecting texel needs no test in the traversal, and one whose rectangle holds
+// only rejecting texels can never be hit by anything (closest hit, shadow ray, subsurface probe all apply the same rejection) and
+// is left out of the BVH.  Hits and images are exactly those of testing every triangle; only triangles that straddle a border of
+// the map's opaque / transparent regions keep PTB_TRI_FLAG_ALPHA.
+struct AlphaSat {
+    int W = 0, H = 0;
+    std::vector<uint32_t> sat;   // (W+1) x (H+1) inclusive prefix counts of rejecting texels
+    void build(const HostTex& a) {
+        W = a.W; H = a.H;
+        sat.assign((size_t)(W + 1) * (H + 1), 0u);
+        for (int y = 0; y < H; y++) {
+            uint32_t row = 0;
+            for (int x = 0; x < W; x++) {
+                row += (a.texels[((size_t)y * W + x) * 3] * a.mult[0] < 0.5f) ? 1u : 0u;   // tex_red(...) < 0.5f
+                sat[(size_t)(y + 1) * (W + 1) + (x + 1)] = sat[(size_t)y * (W + 1) + (x + 1)] + row;
+            }
+        }
+    }
+    uint32_t count(int x0, int y0, int x1, int y1) const {   // inclusive rectangle
+        return sat[(size_t)(y1 + 1) * (W + 1) + (x1 + 1)] - sat[(size_t)y0 * (W + 1) + (x1 + 1)] - sat[(size_t)(y1 + 1) * (W + 1) + x0] + sat[(size_t)y0 * (W + 1) + x0];
+    }
+};
+enum { ALPHA_TEST = 0, ALPHA_OPAQUE = 1, ALPHA_INVISIBLE = 2 };
+// texel range [lo, hi] that tex_wrap + tex_index can produce for coordinates in [cmin, cmax]; false when the range crosses an
+// integer (the wrap is not monotonic there) or is not finite
+static bool texel_range(float cmin, float cmax, int n, int& lo, int& hi) {
+    if (!(cmin <= cmax) || !std::isfinite(cmin) || !std::isfinite(cmax) || std::fabs(cmin) > 1e6f || std::fabs(cmax) > 1e6f) return false;
+    const float pad = 1e-5f * std::max(1.f, std::max(std::fabs(cmin), std::fabs(cmax)));   // barycentric rounding of the interpolated uv
+    const float a = cmin - pad, b = cmax + pad;
+    if (std::floor(a) != std::floor(b)) return false;
+    const float wa = tex_wrap(a), wb = tex_wrap(b);
+    if (!(wa <= wb)) return false;
+    lo = (int)(wa * (float)(n - 1)) - 1; hi = (int)(wb * (float)(n - 1)) + 1;
+    lo = std::max(lo, 0); hi = std::min(hi, n - 1);
+    return lo <= hi;
+}
+static int alpha_class(const AlphaSat& s, const float* uv0, const float* uv1, const float* uv2) {
+    int x0, x1, y0, y1;
+    if (!texel_range(std::min(uv0[0], std::min(uv1[0], uv2[0])), std::max(uv0[0], std::max(uv1[0], uv2[0])), s.W, x0, x1)) return ALPHA_TEST;
+    if (!texel_range(std::min(uv0[1], std::min(uv1[1], uv2[1])), std::max(uv0[1], std::max(uv1[1], uv2[1])), s.H, y0, y1)) return ALPHA_TEST;
+    const uint32_t n = s.count(x0, y0, x1, y1), area = (uint32_t)(x1 - x0 + 1) * (uint32_t)(y1 - y0 + 1);
+    return n == 0 ? ALPHA_OPAQUE : (n == area ? ALPHA_INVISIBLE : ALPHA_TEST);
+}
+
 int HostScene::flatten(FlatScene& out, std::string& err) {
     if (objects.size() < 2 || objects[0].type != OBJ_SPHERE || objects[1].type != OBJ_SPHERE) {
         err = "commit: object 0 must be the spherical light and object 1 the environment dome (Raytracer.cpp:1257-1266)";
@@ -253,24 +301,49 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
     if (out.merl.empty()) out.merl.push_back(0.f);
 
     // ---- world-space triangle soup over all meshes ----
+    out.n_tri_scene = n_tri;
+    struct Src { int obj; int tri; uint8_t alpha; };
+    std::vector<float> verts9(9 * (size_t)n_tri);
+    std::vector<Src> src(n_tri);
     if (n_tri > 0) {
-        struct Src { int obj; int tri; };
-        std::vector<float> verts9(9 * (size_t)n_tri);
-        std::vector<Src> src(n_tri);
+        static const bool classify = !(getenv("PTB_ALPHA_CLASSIFY") && atoi(getenv("PTB_ALPHA_CLASSIFY")) == 0);   // experiments: 0 = test every alpha-mapped triangle
         int64_t w = 0;
         for (int oi = 0; oi < (int)objects.size(); oi++) {
             const HostObject& o = objects[oi];
             if (o.type != OBJ_MESH) continue;
             const int nt = (int)(o.tri.size() / 10);
-            for (int i = 0; i < nt; i++, w++) {
+            std::vector<AlphaSat> sats(o.groups.size());
+            for (int i = 0; i < nt; i++) {
                 const int32_t* t = &o.tri[10 * (size_t)i];
+                // same condition as the PTB_TRI_FLAG_ALPHA decision below
+                uint8_t cls = ALPHA_OPAQUE;
+                const int group = t[9];
+                const bool uv_all = !o.uvs.empty() && t[3] >= 0 && t[4] >= 0 && t[5] >= 0;
+                if (uv_all && group >= 0 && group < (int)o.groups.size() && (o.groups[group].present & SLOT_ALPHA)) {
+                    const HostTex& a = o.groups[group].alpha;
+                    if (a.W > 0 && a.H > 0) {
+                        cls = ALPHA_TEST;
+                        if (classify) {
+                            if (sats[group].W == 0) sats[group].build(a);
+                            cls = (uint8_t)alpha_class(sats[group], &o.uvs[2 * (size_t)t[3]], &o.uvs[2 * (size_t)t[4]], &o.uvs[2 * (size_t)t[5]]);
+                        }
+                    } else if (a.mult[0] < 0.5f) cls = classify ? ALPHA_INVISIBLE : ALPHA_TEST;   // a constant below 0.5 rejects every hit
+                    if (cls == ALPHA_OPAQUE && a.W > 0) out.n_tri_alpha_opaque++;
+                    else if (cls == ALPHA_INVISIBLE) out.n_tri_alpha_invisible++;
+                    else if (cls == ALPHA_TEST) out.n_tri_alpha_tested++;
+                }
+                if (cls == ALPHA_INVISIBLE) continue;
                 for (int c = 0; c < 3; c++) {
                     const V3 p = xf_point(o.trans, V(o.vertices, t[c]));
                     verts9[9 * (size_t)w + 3 * c] = p.x; verts9[9 * (size_t)w + 3 * c + 1] = p.y; verts9[9 * (size_t)w + 3 * c + 2] = p.z;
                 }
-                src[w].obj = oi; src[w].tri = i;
+                src[w].obj = oi; src[w].tri = i; src[w].alpha = cls;
+                w++;
             }
         }
+        n_tri = w;
+    }
+    if (n_tri > 0) {
         auto t0 = std::chrono::steady_clock::now();
         std::vector<uint32_t> order;
         build_bvh8(verts9.data(), n_tri, out.nodes, order, out.bvh);
@@ -286,10 +359,8 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
             const bool uv_all = !o.uvs.empty() && t[3] >= 0 && t[4] >= 0 && t[5] >= 0;
             const bool has_uv = !o.uvs.empty() && group >= 0 && t[3] >= 0;      // TriangleMesh.cpp:928
             uint32_t flags = 0;
-            if (uv_all && group >= 0 && group < (int)o.groups.size() && (o.groups[group].present & SLOT_ALPHA)) {
-                const HostTex& a = o.groups[group].alpha;
-                if (a.W > 0 || a.mult[0] < 0.5f) flags |= PTB_TRI_FLAG_ALPHA;  // a constant >= 0.5 can never reject
-            }
+            if (src[in].alpha == ALPHA_TEST) flags |= PTB_TRI_FLAG_ALPHA;   // a constant >= 0.5 or an all-opaque footprint can never reject
+            (void)uv_all;
             if (o.flags & FLAG_GHOST) flags |= PTB_TRI_FLAG_GHOST;
             F4 q;
             q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = u2f(flags); out.tris[3 * (size_t)k] = q;

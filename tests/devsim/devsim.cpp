@@ -312,8 +312,8 @@ int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* ob
 int ptb_set_option(ptb_ctx*, int, int64_t) { return PTB_OK; }
 int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
     memset(info, 0, sizeof(*info));
-    info->n_triangles = (int64_t)c->flat.tris.size() / 3; info->n_bvh_nodes = c->flat.bvh.n_nodes; info->bvh_depth = c->flat.bvh.depth;
-    info->bytes_nodes = info->n_bvh_nodes * 80; info->bytes_triangles = info->n_triangles * 48; info->ms_bvh_build = c->flat.ms_bvh;
+    info->n_triangles = c->flat.n_tri_scene; info->n_bvh_nodes = c->flat.bvh.n_nodes; info->bvh_depth = c->flat.bvh.depth;
+    info->bytes_nodes = info->n_bvh_nodes * 80; info->bytes_triangles = (int64_t)c->flat.tris.size() / 3 * 48; info->ms_bvh_build = c->flat.ms_bvh;
     info->n_objects = (int)c->host.objects.size();
     return PTB_OK;
 }

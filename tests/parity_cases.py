@@ -281,6 +281,21 @@ def edge_scene(L, variant, W=37, H=23, spp=3):
         rt.s.addObject(m)
         pl = rt.s.objects[2]
         pl.set_material(0, Kd=Texture((1, 1, 1), kd))
+    elif variant == "alpha_classes":
+        # the commit-time alpha classification (scene_host.cpp): a fine mesh under a coarse alpha map has triangles that are
+        # entirely opaque, entirely transparent (left out of the BVH) and straddling (still tested); uvs run over [-1.5, 2.5]
+        # so that the wrap is exercised; a second group has a constant alpha below 0.5 (never hit)
+        v, n, uv, tri = quad_mesh(n=24, groups=True)
+        uv = (uv * 4.0 - 1.5).astype(np.float32)
+        m = scenes._place_like_gui(TriMesh(v, n, uv, tri))
+        a = np.ones((8, 8, 3), np.float32); a[::2, 1::3] = 0.0; a[5, :] = 0.0
+        m.set_material(0, **scenes.phong((.7, .7, .3), 0.1, 25.0, alpha=Texture(1.0, a)))
+        m.set_material(1, **scenes.phong((.2, .3, .8), 0.1, 25.0, alpha=Texture(0.25)))
+        rt.s.addObject(m)
+        m2 = scenes._place_like_gui(TriMesh(*quad_mesh(n=8)), scale=14.0)
+        m2.max_translation = m2.max_translation + np.array([0, 6, -4], np.float32)
+        m2.set_material(0, **scenes.phong((.8, .3, .3), 0.0, 1.0, alpha=Texture(1.0, scenes.checker_alpha_map(64))))
+        rt.s.addObject(m2)
     elif variant == "many_spheres":      # more analytic objects than the kernel-parameter table holds (8)
         for k in range(9):
             c = (-16 + 4 * k, -22.3 + (k % 3), -6 + 3 * (k % 4))
@@ -296,7 +311,7 @@ def edge_scene(L, variant, W=37, H=23, spp=3):
     return rt
 
 
-EDGE_VARIANTS = ["many_spheres", "mirror_and_flip", "mesh_no_uv_groups", "mesh_flat", "textured_rotated", "wide_filter", "depth_one"]
+EDGE_VARIANTS = ["many_spheres", "mirror_and_flip", "mesh_no_uv_groups", "mesh_flat", "textured_rotated", "alpha_classes", "wide_filter", "depth_one"]
 
 
 def case_edge(test_lib, oracle_lib, variant):
@@ -306,6 +321,11 @@ def case_edge(test_lib, oracle_lib, variant):
     assert np.allclose(a.sample_count, b.sample_count, rtol=1e-5)
     oa, ta, _ = a.primary_ids(); ob, tb, _ = b.primary_ids()
     assert ((oa == ob) & (ta == tb)).mean() >= 0.998   # 851 pixels: at most one edge pixel may flip
+    if variant == "alpha_classes":
+        info = b.scene_info()
+        assert info["n_triangles"] == 2 * 24 * 24 + 2 * 8 * 8
+        if "bytes_triangles" in info and info["bytes_triangles"]:
+            assert info["bytes_triangles"] < 48 * info["n_triangles"] * 0.8, "the constant-transparent group and the all-transparent footprints are not resident"
 
 
 def case_passes_and_shards(test_lib):
