@@ -119,7 +119,9 @@ typedef struct ptb_params {
     float    sigma_filter;   /* Gaussian splat sigma         */
     float    gamma;          /* display gamma                */
     uint32_t seed;           /* global seed of the per-(pixel,sample) pcg32 streams (DESIGN.md "RNG") */
-    int32_t  shard_rank;     /* image tiles with (tile_id % shard_count) == shard_rank are rendered */
+    int32_t  shard_rank;     /* image tiles with (tile_id % shard_count) == shard_rank are rendered; tile ids count row by row with
+                                every row rotated against the previous one (ptb_scene.h shard_tile_shift), so that shards are
+                                spread over the frame instead of forming vertical stripes */
     int32_t  shard_count;    /* 1 = whole frame */
     int32_t  tile_size;      /* tile edge in pixels for sharding; 0 = default 64 */
 } ptb_params;

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(128) k_primary(SceneDev sc, CameraDev cam, int
 }
 
 // tile pack / unpack-add with apron (multi-GPU gather).  One thread per packed texel.
-__global__ void __launch_bounds__(256) k_shard_pack(const F4* rgbw, F4* packed, int W, int H, int tile, int apron, int tiles_x, int n_tiles_total,
+__global__ void __launch_bounds__(256) k_shard_pack(const F4* rgbw, F4* packed, int W, int H, int tile, int apron, int tiles_x, int n_tiles_total, int shift,
                                                     int rank, int count, long long n_packed, int unpack) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_packed) return;
@@ -396,12 +396,13 @@ __global__ void __launch_bounds__(256) k_shard_pack(const F4* rgbw, F4* packed, 
     const int r = (int)(idx - (long long)lt * per);
     const int tile_id = rank + lt * count;
     if (tile_id >= n_tiles_total) return;
-    const int ty = tile_id / tiles_x, tx = tile_id - ty * tiles_x;
+    int ty, tx;
+    tile_physical(tile_id, tiles_x, shift, ty, tx);
     const int i = ty * tile - apron + r / side, j = tx * tile - apron + r % side;
     const bool inside = i >= 0 && i < H && j >= 0 && j < W;
     if (!unpack) {
         const int tiles_y = (H + tile - 1) / tile;
-        const bool send = shard_block_sends(tile_id, i, j, W, H, tile, apron, tiles_x, tiles_y, rank, count);
+        const bool send = shard_block_sends(tile_id, i, j, W, H, tile, apron, tiles_x, tiles_y, rank, count, shift);
         F4 z; z.x = z.y = z.z = z.w = 0;
         packed[idx] = send ? rgbw[(size_t)(H - 1 - i) * W + j] : z;
     } else if (inside) {
@@ -779,6 +780,7 @@ static int frame_setup(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     f.shard_count = p->shard_count > 0 ? p->shard_count : 1;
     f.shard_rank = p->shard_rank;
     if (f.shard_rank < 0 || f.shard_rank >= f.shard_count) { c->err = "render: shard_rank out of range"; return PTB_ERR_INVALID; }
+    f.tile_shift = shard_tile_shift(f.tiles_x, f.shard_count);
     const int total_tiles = f.tiles_x * f.tiles_y;
     f.n_my_tiles = total_tiles > f.shard_rank ? (total_tiles - f.shard_rank + f.shard_count - 1) / f.shard_count : 0;
     // randomPerPixel (prepare_render): regenerated when the frame size changes
@@ -840,7 +842,8 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
     unsigned long long valid_pixels = 0;
     for (int lt = 0; lt < f.n_my_tiles; lt++) {
         const int tile_id = f.shard_rank + lt * f.shard_count;
-        const int ty = tile_id / f.tiles_x, tx = tile_id % f.tiles_x;
+        int ty, tx;
+        tile_physical(tile_id, f.tiles_x, f.tile_shift, ty, tx);
         const int h = std::min(f.tile, f.H - ty * f.tile), w = std::min(f.tile, f.W - tx * f.tile);
         valid_pixels += (unsigned long long)h * w;
     }
@@ -879,7 +882,8 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                 const int tp = f.tile * f.tile;
                 for (int64_t lt = s0 / tp; lt * tp < s0 + ns; lt++) {
                     const int tile_id = f.shard_rank + (int)lt * f.shard_count;
-                    const int ty = tile_id / f.tiles_x, tx = tile_id % f.tiles_x;
+                    int ty, tx;
+                    tile_physical(tile_id, f.tiles_x, f.tile_shift, ty, tx);
                     const int h = std::min(f.tile, f.H - ty * f.tile), w = std::min(f.tile, f.W - tx * f.tile);
                     valid_here += (unsigned long long)h * w;
                 }
@@ -1261,7 +1265,7 @@ static int shard_move(ptb_ctx* c, const ptb_params* p, int shard_rank, const flo
     const long long side = tile + 2 * apron, n = (long long)mine * side * side;
     if (n == 0) return PTB_OK;
     k_shard_pack<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const F4*>(d_rgbw), reinterpret_cast<F4*>(d_packed), p->W, p->H, tile, apron,
-                                                                    tiles_x, total, shard_rank, p->shard_count > 0 ? p->shard_count : 1, n, unpack);
+                                                                    tiles_x, total, shard_tile_shift(tiles_x, p->shard_count > 0 ? p->shard_count : 1), shard_rank, p->shard_count > 0 ? p->shard_count : 1, n, unpack);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     return PTB_OK;

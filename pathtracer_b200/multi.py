@@ -1,6 +1,7 @@
 """Tile-sharded render over the GPUs of one box: one process per GPU, one NCCL gather at the end.
 
-The frame is cut into tiles; rank r renders the tiles with `tile_id % world == r` into its own
+The frame is cut into tiles; rank r renders the tiles with `tile_id % world == r` (tile ids count row by row, each row rotated
+against the one above so that no rank gets a vertical stripe, ptb_scene.h `shard_tile_shift`) into its own
 full-frame float4 accumulator (only its tiles plus a ceil(2*sigma) apron are non-zero), packs those
 tiles+aprons densely, and rank 0 gathers the packs over NCCL/NVLink, adds them into its accumulator
 and resolves.  There is no other exchange: scene and BVH are replicated.

@@ -83,6 +83,7 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     f.tile = p->tile_size > 0 ? p->tile_size : 64;
     f.tiles_x = (p->W + f.tile - 1) / f.tile; f.tiles_y = (p->H + f.tile - 1) / f.tile;
     f.shard_count = p->shard_count > 0 ? p->shard_count : 1; f.shard_rank = p->shard_rank;
+    f.tile_shift = shard_tile_shift(f.tiles_x, f.shard_count);
     const int total = f.tiles_x * f.tiles_y;
     f.n_my_tiles = total > f.shard_rank ? (total - f.shard_rank + f.shard_count - 1) / f.shard_count : 0;
     const size_t npix = (size_t)p->W * p->H;
@@ -275,13 +276,15 @@ static int shard_move(const ptb_params* p, int rank, F4* rgbw, F4* packed, int u
     shard_geometry(p, rank, tile, apron, tiles_x, total, mine);
     const int side = tile + 2 * apron, count = p->shard_count > 0 ? p->shard_count : 1;
     for (int lt = 0; lt < mine; lt++) {
-        const int tile_id = rank + lt * count, ty = tile_id / tiles_x, tx = tile_id % tiles_x;
+        const int tile_id = rank + lt * count, shift = shard_tile_shift(tiles_x, count);
+        int ty, tx;
+        tile_physical(tile_id, tiles_x, shift, ty, tx);
         for (int r = 0; r < side * side; r++) {
             const int i = ty * tile - apron + r / side, j = tx * tile - apron + r % side;
             const bool inside = i >= 0 && i < p->H && j >= 0 && j < p->W;
             F4& q = packed[(size_t)lt * side * side + r];
             const int tiles_y = (p->H + tile - 1) / tile;
-            const bool send = shard_block_sends(tile_id, i, j, p->W, p->H, tile, apron, tiles_x, tiles_y, rank, count);
+            const bool send = shard_block_sends(tile_id, i, j, p->W, p->H, tile, apron, tiles_x, tiles_y, rank, count, shift);
             if (!unpack) { F4 z; z.x = z.y = z.z = z.w = 0; q = send ? rgbw[(size_t)(p->H - 1 - i) * p->W + j] : z; }
             else if (inside) { F4& d = rgbw[(size_t)(p->H - 1 - i) * p->W + j]; d.x += q.x; d.y += q.y; d.z += q.z; d.w += q.w; }
         }
