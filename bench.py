@@ -139,7 +139,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     base_line = {"metric": "Msamples/s", "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                  "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                 "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "spp_sharding": "image tiles 64x64, tile_id % n_gpus",
+                 "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "spp_sharding": "image tiles (32x32 when shared, rows rotated), tile_id % n_gpus",
                             "pass_pipelines": int(os.environ.get("PTB_PIPES", "2")),
                             "l2": "working set per step (BVH + triangles + path pool, >2 GB) exceeds the 126 MB L2; no flush needed"}}
 

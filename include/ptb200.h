@@ -123,7 +123,7 @@ typedef struct ptb_params {
                                 every row rotated against the previous one (ptb_scene.h shard_tile_shift), so that shards are
                                 spread over the frame instead of forming vertical stripes */
     int32_t  shard_count;    /* 1 = whole frame */
-    int32_t  tile_size;      /* tile edge in pixels for sharding; 0 = default 64 */
+    int32_t  tile_size;      /* tile edge in pixels for sharding; 0 = default (64 for a whole frame, 32 for a shared one) */
 } ptb_params;
 
 typedef struct ptb_stats {

@@ -775,7 +775,7 @@ static int frame_setup(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     camera_from_abi(f.cam, cam, p->W, p->H);
     filter_setup(f.filter, p->sigma_filter);
     f.W = p->W; f.H = p->H; f.nb_bounces = p->nb_bounces; f.seed = p->seed;
-    f.tile = p->tile_size > 0 ? p->tile_size : 64;
+    f.tile = p->tile_size > 0 ? p->tile_size : ptb_default_tile(p->shard_count);
     f.tiles_x = (p->W + f.tile - 1) / f.tile; f.tiles_y = (p->H + f.tile - 1) / f.tile;
     f.shard_count = p->shard_count > 0 ? p->shard_count : 1;
     f.shard_rank = p->shard_rank;
@@ -1240,7 +1240,7 @@ int ptb_progressive_read(ptb_ctx* c, float* imagedouble, float* sample_count, ui
 }
 
 static void shard_geometry(const ptb_params* p, int rank, int& tile, int& apron, int& tiles_x, int& total, int& mine) {
-    tile = p->tile_size > 0 ? p->tile_size : 64;
+    tile = p->tile_size > 0 ? p->tile_size : ptb_default_tile(p->shard_count);
     apron = (int)ceilf(p->sigma_filter * 2);
     tiles_x = (p->W + tile - 1) / tile;
     total = tiles_x * ((p->H + tile - 1) / tile);

@@ -80,7 +80,7 @@ static int render_into(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     camera_setup(f.cam, cam->position, cam->direction, cam->up, cam->fov, cam->focus_distance, cam->aperture, p->W, p->H);
     filter_setup(f.filter, p->sigma_filter);
     f.W = p->W; f.H = p->H; f.nb_bounces = p->nb_bounces; f.seed = p->seed;
-    f.tile = p->tile_size > 0 ? p->tile_size : 64;
+    f.tile = p->tile_size > 0 ? p->tile_size : ptb_default_tile(p->shard_count);
     f.tiles_x = (p->W + f.tile - 1) / f.tile; f.tiles_y = (p->H + f.tile - 1) / f.tile;
     f.shard_count = p->shard_count > 0 ? p->shard_count : 1; f.shard_rank = p->shard_rank;
     f.tile_shift = shard_tile_shift(f.tiles_x, f.shard_count);
@@ -257,7 +257,7 @@ int ptb_resolve(ptb_ctx*, const float* d_rgbw, int W, int H, float gamma, float*
     return PTB_OK;
 }
 static void shard_geometry(const ptb_params* p, int rank, int& tile, int& apron, int& tiles_x, int& total, int& mine) {
-    tile = p->tile_size > 0 ? p->tile_size : 64;
+    tile = p->tile_size > 0 ? p->tile_size : ptb_default_tile(p->shard_count);
     apron = (int)ceilf(p->sigma_filter * 2);
     tiles_x = (p->W + tile - 1) / tile;
     total = tiles_x * ((p->H + tile - 1) / tile);
