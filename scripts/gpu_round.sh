@@ -18,5 +18,6 @@ if [ "${PTB_NCU:-1}" = "1" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 40 -c 4 -o gpurun_out/prof_trace_C2 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_C2.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 40 -c 4 -o gpurun_out/prof_trace_C3 python bench.py --steps 1 --warmup 3 --workload C3 --no-cpu-baseline > gpurun_out/ncu_full_C3.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 20 -c 2 -o gpurun_out/prof_shade_C2 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_shade.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 20 -c 2 -o gpurun_out/prof_shade_C4 python bench.py --steps 1 --warmup 3 --workload C4 --no-cpu-baseline > gpurun_out/ncu_full_shade_C4.log 2>&1
 fi
 ls -la gpurun_out
