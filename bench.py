@@ -287,13 +287,19 @@ def main():
     ext_launch_ms = ext["ms"] / max(1, ext["launches"])
     rays_per_launch = ext["items"] / max(1, ext["launches"])
     achieved = rays_per_launch * bytes_per_ray / (ext_launch_ms * 1e-3) / 1e9 if ext_launch_ms > 0 else 0.0
-    traffic = None
+    traffic, ncu = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get("k_trace_closest_dram_bytes_per_launch")
+        rec = json.load(open(tpath)).get(args.workload, {})
+        traffic = rec.get("k_trace_closest_dram_bytes_per_launch")
+        ncu = {k: rec[k] for k in ("issue_active_pct", "active_lanes_per_instruction", "fma_pipe_active_pct", "dram_throughput_pct", "l2_throughput_pct",
+                                   "l1_hit_pct", "l2_hit_pct", "source") if k in rec} or None
     step_kernel_ms = sum(v["ms"] for v in kt.values())
     line["roofline"] = {"bound": "hbm", "kernel": "k_trace<closest-hit> (BVH8 traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                        "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "n_node": n_node, "n_tri": n_tri,
+                        "peak_source": peak_src,
+                        # counters of the same kernel from the committed ncu capture (profiles/): the traversal is bound by instruction issue
+                        # under divergence (ALU / FMA pipes), its DRAM traffic is a few percent of the algorithmic bytes (L1 / L2 hits)
+                        "ncu": ncu, "bytes_per_ray": bytes_per_ray, "n_node": n_node, "n_tri": n_tri,
                         "rays_per_launch": rays_per_launch, "launch_ms": ext_launch_ms, "launches_per_step": ext["launches"],
                         "share_of_step": ext["ms"] / step_kernel_ms if step_kernel_ms else None,
                         "timing": "CUDA events around every launch of one extra step with the pass pipelines serialised (PTB_OPT_PIPES=1), taken between the timed region and the e2e region",

@@ -64,7 +64,18 @@ def traffic(tag, rep):
     ms = [float(rows["gpu__time_duration.sum"][2 + i]) for i, n in enumerate(names) if "k_trace<0" in n]
     tpath = os.path.join(PROF, "roofline_traffic.json")
     d = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    def mean_of(metric):
+        r = rows.get(metric)
+        xs = [float(r[2 + i]) for i, n in enumerate(names) if "k_trace<0" in n] if r else []
+        return sum(xs) / len(xs) if xs else None
     d[w] = {"k_trace_closest_dram_bytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals), "ncu_ms_per_launch": sum(ms) / len(ms),
+            # what bounds the kernel (the algorithmic-byte figure of bench.py is a model; these are the counters)
+            "issue_active_pct": mean_of("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "active_lanes_per_instruction": mean_of("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "fma_pipe_active_pct": mean_of("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+            "dram_throughput_pct": mean_of("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "l2_throughput_pct": mean_of("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+            "l1_hit_pct": mean_of("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": mean_of("lts__t_sector_hit_rate.pct"),
             "source": f"profiles/{tag}_k_trace_{w}.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, closest-hit launches of bounces 0 and 1 of one pass)"}
     json.dump(d, open(tpath, "w"), indent=1)
     print(w, d[w])
