@@ -167,6 +167,7 @@ def main():
     N_PIPES = int(os.environ.get("PTB_PIPES", "2"))
     t0 = time.time(); rt = make_rt(lib, args.workload, device=local); gen_s = time.time() - t0
     t0 = time.time(); rt.commit(); commit_s = time.time() - t0
+    rt.reuse_buffers = True     # like the reference, whose Raytracer owns its output vectors (Raytracer.h:90-105)
     info = rt.scene_info()
     samples_frame = rt.W * rt.H * rt.nrays
 

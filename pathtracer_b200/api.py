@@ -250,6 +250,10 @@ class Raytracer:
         self.cam = Camera()
         self.s = Scene()
         self.imagedouble = self.sample_count = self.image = None
+        # the reference's Raytracer OWNS imagedouble / sample_count / image (std::vector members resized when the frame size
+        # changes, Raytracer.h:90-105).  True: the output arrays are kept across renders like that (no fresh, untouched pages for
+        # the device-to-host copies of every call); False (default): every render returns new arrays.
+        self.reuse_buffers = False
         self.stats = None
         self._ctx = None
         self._keep = []
@@ -448,15 +452,25 @@ class Raytracer:
         return p
 
     # ---- Raytracer::render_image_nopreviz (Raytracer.cpp:1565-1798) ----
+    def _out(self, name, shape, dtype):
+        a = getattr(self, name, None)
+        if not (self.reuse_buffers and a is not None and a.shape == shape and a.dtype == dtype):
+            a = np.empty(shape, dtype)
+            setattr(self, name, a)
+        return a
+
     def render_image_nopreviz(self, want_image=True):
         L, ctx = self.lib, self._ctx
         if ctx is None:
             self.commit()
             ctx = self._ctx
         n = self.W * self.H
-        self.imagedouble = np.empty((self.H, self.W, 3), np.float32)
-        self.sample_count = np.empty((self.H, self.W), np.float32)
-        self.image = np.empty((self.H, self.W, 3), np.uint8) if want_image else None
+        self._out("imagedouble", (self.H, self.W, 3), np.float32)
+        self._out("sample_count", (self.H, self.W), np.float32)
+        if want_image:
+            self._out("image", (self.H, self.W, 3), np.uint8)
+        else:
+            self.image = None
         st, cam, p = _abi.Stats(), self.cam.c_struct(), self.params()
         L.check(L.render(ctx, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count),
                          self.image.ctypes.data_as(C.POINTER(C.c_uint8)) if want_image else None, C.byref(st)), ctx)
@@ -529,9 +543,12 @@ class Raytracer:
 
     def resolve(self, d_rgbw_ptr, want_image=True):
         L, ctx = self.lib, self._ctx
-        self.imagedouble = np.empty((self.H, self.W, 3), np.float32)
-        self.sample_count = np.empty((self.H, self.W), np.float32)
-        self.image = np.empty((self.H, self.W, 3), np.uint8) if want_image else None
+        self._out("imagedouble", (self.H, self.W, 3), np.float32)
+        self._out("sample_count", (self.H, self.W), np.float32)
+        if want_image:
+            self._out("image", (self.H, self.W, 3), np.uint8)
+        else:
+            self.image = None
         L.check(L.resolve(ctx, C.c_void_p(d_rgbw_ptr), self.W, self.H, self.gamma, fptr(self.imagedouble), fptr(self.sample_count),
                           self.image.ctypes.data_as(C.POINTER(C.c_uint8)) if want_image else None), ctx)
         return self.imagedouble
