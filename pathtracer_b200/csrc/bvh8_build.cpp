@@ -307,7 +307,7 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
         nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
         nd.child_base = (uint32_t)out_nodes.size();
         nd.tri_base = (uint32_t)leaf_order.size();
-        uint32_t n_internal = 0, tri_off = 0;
+        uint32_t n_internal = 0, tri_off = 0, valid24 = 0;
         for (int s = 0; s < 8; s++) {
             const int i = slot_child[s];
             if (i < 0) continue;
@@ -323,16 +323,16 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
             }
             if (ch_leaf[i]) {
                 const uint32_t unary = (c.scount == 1) ? 1u : (c.scount == 2 ? 3u : 7u);
-                nd.meta[s] = (uint8_t)((unary << 5) | tri_off);
+                valid24 |= unary << (3 * s);
                 for (int t = 0; t < c.scount; t++) leaf_order.push_back(B.idx[c.sfirst + t]);
                 tri_off += (uint32_t)c.scount;
                 stats.leaves++;
             } else {
-                nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
                 nd.imask |= (uint8_t)(1u << s);
                 n_internal++;
             }
         }
+        nd.valid24[0] = (uint8_t)(valid24 & 0xffu); nd.valid24[1] = (uint8_t)((valid24 >> 8) & 0xffu); nd.valid24[2] = (uint8_t)((valid24 >> 16) & 0xffu);
         // allocate the internal children contiguously, in slot order
         for (int s = 0; s < 8; s++) {
             const int i = slot_child[s];

@@ -11,7 +11,9 @@
 //            15  imask    bit s set <=> slot s holds an internal node
 //         16-19  child_base   index of the first internal child (children are contiguous, slot order)
 //         20-23  tri_base     index of the node's first triangle (leaf children contiguous)
-//         24-31  meta[8]  empty: 0; internal: (1<<5) | (24+slot); leaf: (unary count in top 3 bits) | first-triangle offset
+//         24-26  valid24  bit 3*s + k set <=> slot s is a leaf with more than k triangles (at most 3 per leaf); the node's
+//                         triangles are stored compactly in this bit order: index = tri_base + popcount(valid24 below the bit)
+//         27-31  reserved (0)
 //         32-79  qlo_x[8] qlo_y[8] qlo_z[8] qhi_x[8] qhi_y[8] qhi_z[8]
 //
 // Triangles are stored in leaf order as 3 x float4 = 48 bytes {v0, e1 = v1-v0, e2 = v2-v0}; the .w
@@ -30,7 +32,8 @@ struct alignas(16) Node8 {
     float px, py, pz;
     uint8_t ex, ey, ez, imask;
     uint32_t child_base, tri_base;
-    uint8_t meta[8];
+    uint8_t valid24[3];   // see the layout above
+    uint8_t reserved[5];
     uint8_t qlox[8], qloy[8], qloz[8], qhix[8], qhiy[8], qhiz[8];
 };
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
@@ -68,7 +71,8 @@ struct float4_host { float x, y, z, w; };
 // Per-ray constants of the slab test in quantised space.
 struct RayPrep {
     V3 o, d, idir;
-    uint32_t oct_inv4;  // (7 - octant) replicated in 4 bytes; octant bit set <=> direction component negative
+    uint32_t oct_inv4;  // byte 0: 7 - octant (octant bit set <=> direction component negative); bytes 1..3: the slot masks of
+                        // pick_slot for that octant (the half, the pairs, the single slots visited first)
 };
 PTB_HD RayPrep ray_prep(V3 o, V3 d) {
     RayPrep r;
@@ -77,7 +81,9 @@ PTB_HD RayPrep ray_prep(V3 o, V3 d) {
     r.idir.x = 1.f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
     r.idir.y = 1.f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
     r.idir.z = 1.f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
-    r.oct_inv4 = ((d.x < 0 ? 0u : 0x04040404u) | (d.y < 0 ? 0u : 0x02020202u) | (d.z < 0 ? 0u : 0x01010101u));
+    const uint32_t oinv = (d.x < 0 ? 0u : 4u) | (d.y < 0 ? 0u : 2u) | (d.z < 0 ? 0u : 1u);
+    // children are visited in descending (slot ^ oinv): first the half of the slots whose bit 2 differs from oinv's, ...
+    r.oct_inv4 = oinv | ((oinv & 4u) ? 0x0f00u : 0xf000u) | ((oinv & 2u) ? 0x330000u : 0xcc0000u) | ((oinv & 1u) ? 0x55000000u : 0xaa000000u);
     return r;
 }
 
@@ -85,12 +91,12 @@ PTB_HD RayPrep ray_prep(V3 o, V3 d) {
 struct AlphaCtx;
 PTB_HD bool alpha_rejects(const AlphaCtx* ctx, int prim, float b1, float b2);
 
-// Tests the 8 children of `n` against the ray; returns the hit mask in traversal-priority order:
-// bits 31..24 internal children (bit 24 + (slot ^ (7-oct))), bits 23..0 triangles of hit leaves.
+// Tests the 8 children of `n` against the ray; returns the hit mask in SLOT order: bit 24 + s = the internal child in slot s,
+// bits 3s..3s+2 = the triangles of the leaf in slot s (only bits that exist: valid24 / imask).
 #if defined(__CUDA_ARCH__)
 // Device form.  ncu on the straightforward form showed the XU pipe (48 I2F.U8 per node) as the busiest pipe, so the
 // quantised planes are turned into floats without any conversion instruction (see planes4 below) and the bias is folded
-// into the FFMA constant.  The meta bytes are decoded four at a time (Ylitie et al. 2017).
+// into the FFMA constant.
 // Both the fma pipe (FFMA, HADD2, IMAD) and the alu pipe (PRMT, FMNMX, LOP3, SHF, SEL, ISETP) issue one warp instruction
 // every 2 cycles per SM sub-partition; the node test is bound by the alu pipe (about 116 alu vs 96 fma instructions per node).
 #if !defined(PTB_PLANES_PRMT32)
@@ -122,10 +128,12 @@ __device__ __forceinline__ uint32_t node_hitmask(const F4& n0, const F4& n1, con
     const float box = fmaf(-PTB_PLANE_BIAS, adx, (n0.x - r.o.x) * r.idir.x), boy = fmaf(-PTB_PLANE_BIAS, ady, (n0.y - r.o.y) * r.idir.y),
                 boz = fmaf(-PTB_PLANE_BIAS, adz, (n0.z - r.o.z) * r.idir.z);
     const bool negx = r.d.x < 0, negy = r.d.y < 0, negz = r.d.z < 0;
+    // The mask is built in SLOT order with immediates (slot s: its three triangle bits and its internal-child bit) and cut down to
+    // what exists with one AND; the octant order is applied when a child is picked (pick_slot).  The per-child byte extracts and
+    // variable shifts of a traversal-ordered mask were a quarter of the node step's instructions.
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const uint32_t meta4 = f2u(half ? n1.w : n1.z);
         const uint32_t lox = f2u(half ? n2.y : n2.x), loy = f2u(half ? n2.w : n2.z), loz = f2u(half ? n3.y : n3.x);
         const uint32_t hix = f2u(half ? n3.w : n3.z), hiy = f2u(half ? n4.y : n4.x), hiz = f2u(half ? n4.w : n4.z);
         float tnx[4], tny[4], tnz[4], tfx[4], tfy[4], tfz[4];
@@ -135,18 +143,15 @@ __device__ __forceinline__ uint32_t node_hitmask(const F4& n0, const F4& n1, con
         planes4(negy ? loy : hiy, ady, boy, tfy[0], tfy[1], tfy[2], tfy[3]);
         planes4(negz ? hiz : loz, adz, boz, tnz[0], tnz[1], tnz[2], tnz[3]);
         planes4(negz ? loz : hiz, adz, boz, tfz[0], tfz[1], tfz[2], tfz[3]);
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;                          // per byte: 0xff iff internal child
-        const uint32_t bit_index4 = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float tn = fmaxf(fmaxf(tnx[j], tny[j]), fmaxf(tnz[j], 0.f));
             const float tf = fminf(fminf(tfx[j], tfy[j]), fminf(tfz[j], tmax));
-            if (tn <= tf) hitmask |= ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
+            const int s = 4 * half + j;
+            if (tn <= tf) hitmask |= (7u << (3 * s)) | (1u << (24 + s));
         }
     }
-    return hitmask;
+    return hitmask & ((e_imask & 0xff000000u) | (f2u(n1.z) & 0x00ffffffu));
 }
 #else
 inline uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4& n3, const F4& n4, const RayPrep& r, float tmax) {
@@ -154,14 +159,12 @@ inline uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4&
     const float sx = u2f(((e_imask >> 0) & 0xffu) << 23), sy = u2f(((e_imask >> 8) & 0xffu) << 23), sz = u2f(((e_imask >> 16) & 0xffu) << 23);
     const float adx = sx * r.idir.x, ady = sy * r.idir.y, adz = sz * r.idir.z;
     const float box = (n0.x - r.o.x) * r.idir.x, boy = (n0.y - r.o.y) * r.idir.y, boz = (n0.z - r.o.z) * r.idir.z;
-    const uint32_t meta_lo = f2u(n1.z), meta_hi = f2u(n1.w);
     const uint32_t qlox_lo = f2u(n2.x), qlox_hi = f2u(n2.y), qloy_lo = f2u(n2.z), qloy_hi = f2u(n2.w);
     const uint32_t qloz_lo = f2u(n3.x), qloz_hi = f2u(n3.y), qhix_lo = f2u(n3.z), qhix_hi = f2u(n3.w);
     const uint32_t qhiy_lo = f2u(n4.x), qhiy_hi = f2u(n4.y), qhiz_lo = f2u(n4.z), qhiz_hi = f2u(n4.w);
     const bool negx = r.d.x < 0, negy = r.d.y < 0, negz = r.d.z < 0;
     uint32_t hitmask = 0;
     for (int half = 0; half < 2; half++) {
-        const uint32_t meta4 = half ? meta_hi : meta_lo;
         const uint32_t lox = half ? qlox_hi : qlox_lo, loy = half ? qloy_hi : qloy_lo, loz = half ? qloz_hi : qloz_lo;
         const uint32_t hix = half ? qhix_hi : qhix_lo, hiy = half ? qhiy_hi : qhiy_lo, hiz = half ? qhiz_hi : qhiz_lo;
         // entry plane is lo for positive direction, hi for negative
@@ -178,16 +181,11 @@ inline uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4&
             const float tfz = (float)((fz >> sh) & 0xffu) * adz + boz;
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (tn <= tf) {
-                const uint32_t meta = (meta4 >> sh) & 0xffu;
-                // internal children carry 0b001 in the top bits and 24+slot below: reorder them by octant
-                const uint32_t is_inner = ((meta & 0x18u) == 0x18u) ? 0xffu : 0u;
-                const uint32_t bit_index = (meta ^ (r.oct_inv4 & is_inner)) & 0x1fu;
-                hitmask |= (meta >> 5) << bit_index;
-            }
+            const int s = 4 * half + j;
+            if (tn <= tf) hitmask |= (7u << (3 * s)) | (1u << (24 + s));   // slot s: its triangle bits and its internal-child bit
         }
     }
-    return hitmask;
+    return hitmask & ((e_imask & 0xff000000u) | (f2u(n1.z) & 0x00ffffffu));   // what exists: imask, valid24
 }
 #endif
 
@@ -215,6 +213,16 @@ PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, fl
     return true;
 }
 
+// The hit internal child (bits 24..31 of a node group, slot order) that the ray meets first: the slot s with the largest s ^ oinv.
+// Three narrowing steps: keep the preferred half / pairs / slots whenever one of them is hit.
+PTB_HD uint32_t pick_slot(uint32_t hits8, uint32_t oct_inv4) {
+    uint32_t x = hits8, t;
+    t = x & (oct_inv4 >> 8) & 0xffu;  x = t ? t : x;
+    t = x & (oct_inv4 >> 16) & 0xffu; x = t ? t : x;
+    t = x & (oct_inv4 >> 24);         x = t ? t : x;
+    return highest_bit(x);            // one bit is left
+}
+
 #define PTB_STACK 32
 
 struct TraverseCounters {
@@ -230,6 +238,7 @@ PTB_HD bool traverse(const F4* __restrict__ nodes, const F4* __restrict__ tris, 
     U2 stack[PTB_STACK];
     int sp = 0;
     U2 ngroup, tgroup;
+    uint32_t tvalid = 0;
     // the root enters as a one-child group: bit 31 set, no imask bits -> relative index 0
     ngroup.x = 0; ngroup.y = 0x80000000u;
     bool found = false;
@@ -238,13 +247,12 @@ PTB_HD bool traverse(const F4* __restrict__ nodes, const F4* __restrict__ tris, 
         // invariant: ngroup has at least one pending internal child (a bit in 31..24)
         {
             const uint32_t hits_imask = ngroup.y;
-            const uint32_t child_bit = highest_bit(hits_imask);
+            const uint32_t slot = pick_slot(hits_imask >> 24, r.oct_inv4);
             const uint32_t child_base = ngroup.x;
-            ngroup.y &= ~(1u << child_bit);
+            ngroup.y &= ~(1u << (24u + slot));
             if (ngroup.y > 0x00ffffffu) {
                 if (sp < PTB_STACK) stack[sp++] = ngroup;
             }
-            const uint32_t slot = (child_bit - 24u) ^ (r.oct_inv4 & 0xffu);
             const uint32_t rel = popcount32(hits_imask & ~(0xffffffffu << slot));
             const uint32_t child_index = child_base + rel;
             const F4* np = nodes + (size_t)child_index * 5;
@@ -265,11 +273,12 @@ PTB_HD bool traverse(const F4* __restrict__ nodes, const F4* __restrict__ tris, 
             tgroup.x = f2u(n1.y);
             ngroup.y = (hm & 0xff000000u) | imask;
             tgroup.y = hm & 0x00ffffffu;
+            tvalid = f2u(n1.z) & 0x00ffffffu;
         }
         while (tgroup.y != 0) {
             const uint32_t ti = highest_bit(tgroup.y);
             tgroup.y &= ~(1u << ti);
-            const uint32_t prim = tgroup.x + ti;
+            const uint32_t prim = tgroup.x + popcount32(tvalid & ~(0xffffffffu << ti));
             const F4* tp = tris + (size_t)prim * 3;
             F4 a, b, c;
             {
@@ -305,15 +314,15 @@ PTB_HD void traverse_all(const F4* __restrict__ nodes, const F4* __restrict__ tr
     U2 stack[PTB_STACK];
     int sp = 0;
     U2 ngroup, tgroup;
+    uint32_t tvalid = 0;
     ngroup.x = 0; ngroup.y = 0x80000000u;
     for (;;) {
         {
             const uint32_t hits_imask = ngroup.y;
-            const uint32_t child_bit = highest_bit(hits_imask);
+            const uint32_t slot = pick_slot(hits_imask >> 24, r.oct_inv4);
             const uint32_t child_base = ngroup.x;
-            ngroup.y &= ~(1u << child_bit);
+            ngroup.y &= ~(1u << (24u + slot));
             if (ngroup.y > 0x00ffffffu) { if (sp < PTB_STACK) stack[sp++] = ngroup; }
-            const uint32_t slot = (child_bit - 24u) ^ (r.oct_inv4 & 0xffu);
             const uint32_t rel = popcount32(hits_imask & ~(0xffffffffu << slot));
             const F4* np = nodes + (size_t)(child_base + rel) * 5;
             F4 n0, n1, n2, n3, n4;
@@ -331,11 +340,12 @@ PTB_HD void traverse_all(const F4* __restrict__ nodes, const F4* __restrict__ tr
             tgroup.x = f2u(n1.y);
             ngroup.y = (hm & 0xff000000u) | (f2u(n0.w) >> 24);
             tgroup.y = hm & 0x00ffffffu;
+            tvalid = f2u(n1.z) & 0x00ffffffu;
         }
         while (tgroup.y != 0) {
             const uint32_t ti = highest_bit(tgroup.y);
             tgroup.y &= ~(1u << ti);
-            const uint32_t prim = tgroup.x + ti;
+            const uint32_t prim = tgroup.x + popcount32(tvalid & ~(0xffffffffu << ti));
             const F4* tp = tris + (size_t)prim * 3;
             F4 a, b, c;
             {

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
     float tbest = 0.f, hb1 = 0.f, hb2 = 0.f;
     int32_t hprim = -1;
     U2 ngroup, tgroup, stack[PTB_STACK];
+    uint32_t tvalid = 0;   // valid24 of the node the live triangle group came from (all ones for a group popped from the stack: compact bits)
     int sp = 0;
     ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
     uint32_t cn = 0, ct = 0;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
         if (live && ngroup.y <= 0x00ffffffu && tgroup.y == 0) {
             if (sp > 0) {
                 const U2 e = stack[--sp];
-                if (e.y > 0x00ffffffu) ngroup = e; else tgroup = e;
+                if (e.y > 0x00ffffffu) ngroup = e; else { tgroup = e; tvalid = 0x00ffffffu; }
             } else {
                 if (ANY_HIT && BRANCH) shadow_settle_branch(p, (int)entry, item, false);
                 else if (ANY_HIT) {   // unoccluded: deliver the deferred direct term (Raytracer.cpp:545-566)
@@ -146,13 +147,22 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
         }
         // ---- node phase: ONE node step
         if (live && ngroup.y > 0x00ffffffu) {
-            if (tgroup.y != 0) { if (sp < PTB_STACK) stack[sp++] = tgroup; tgroup.y = 0; }   // postpone leftover triangles
+            if (tgroup.y != 0) {   // postpone leftover triangles: stacked in compact form (bit = index relative to tri_base)
+                uint32_t m = tgroup.y, cm = 0;
+                do {
+                    const uint32_t b = highest_bit(m);
+                    m &= ~(1u << b);
+                    cm |= 1u << popcount32(tvalid & ~(0xffffffffu << b));
+                } while (m);
+                tgroup.y = cm;
+                if (sp < PTB_STACK) stack[sp++] = tgroup;
+                tgroup.y = 0;
+            }
             const uint32_t hits_imask = ngroup.y;
-            const uint32_t child_bit = highest_bit(hits_imask);
+            const uint32_t slot = pick_slot(hits_imask >> 24, r.oct_inv4);
             const uint32_t child_base = ngroup.x;
-            ngroup.y &= ~(1u << child_bit);
+            ngroup.y &= ~(1u << (24u + slot));
             if (ngroup.y > 0x00ffffffu) { if (sp < PTB_STACK) stack[sp++] = ngroup; }
-            const uint32_t slot = (child_bit - 24u) ^ (r.oct_inv4 & 0xffu);
             const uint32_t rel = popcount32(hits_imask & ~(0xffffffffu << slot));
             const float4* np = reinterpret_cast<const float4*>(nodes) + (size_t)(child_base + rel) * 5;
             const float4 l0 = __ldg(np), l1 = __ldg(np + 1), l2 = __ldg(np + 2), l3 = __ldg(np + 3), l4 = __ldg(np + 4);
@@ -166,6 +176,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
             tgroup.x = f2u(n1.y);
             ngroup.y = (hm & 0xff000000u) | (f2u(n0.w) >> 24);
             tgroup.y = hm & 0x00ffffffu;
+            tvalid = f2u(n1.z) & 0x00ffffffu;
         }
         // ---- triangle phase: entered when tri_min_pct % of the live lanes hold triangle work (default 0: always; postponing
         //      further was measured to cost more node visits than it saves issue slots) or when nobody can do anything else;
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
                 if (live && tgroup.y != 0) {
                     const uint32_t ti = highest_bit(tgroup.y);
                     tgroup.y &= ~(1u << ti);
-                    const uint32_t prim = tgroup.x + ti;
+                    const uint32_t prim = tgroup.x + popcount32(tvalid & ~(0xffffffffu << ti));
                     const float4* tp = reinterpret_cast<const float4*>(tris) + (size_t)prim * 3;
                     const float4 l0 = __ldg(tp), l1 = __ldg(tp + 1), l2 = __ldg(tp + 2);
                     F4 a, b, c;
