@@ -76,6 +76,17 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
                                                int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below, int tri_den, int tri_min_pct) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
+#if !defined(PTB_NO_PICK_LUT)
+    // pick_slot as a table: slot = lut[7 - octant][hit internal children] (2 KB of shared memory, filled once per persistent block):
+    // one LDS instead of thirteen ALU instructions per node visit (+1.2 % on C2 / C3, profiles/r01p_ab_pick_lut.txt)
+    __shared__ uint8_t pick_lut[8 * 256];
+    for (uint32_t i = threadIdx.x; i < 8u * 256u; i += blockDim.x) {
+        const uint32_t oinv = i >> 8;
+        const uint32_t packed = oinv | ((oinv & 4u) ? 0x0f00u : 0xf000u) | ((oinv & 2u) ? 0x330000u : 0xcc0000u) | ((oinv & 1u) ? 0x55000000u : 0xaa000000u);
+        pick_lut[i] = (i & 0xffu) ? (uint8_t)pick_slot(i & 0xffu, packed) : (uint8_t)0;
+    }
+    __syncthreads();
+#endif
     const uint32_t n = count ? *count : (uint32_t)n_static;
     const AlphaCtx ac = alpha_ctx(sc);
     const F4* __restrict__ nodes = sc.nodes;
@@ -159,7 +170,11 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
                 tgroup.y = 0;
             }
             const uint32_t hits_imask = ngroup.y;
+#if !defined(PTB_NO_PICK_LUT)
+            const uint32_t slot = pick_lut[((r.oct_inv4 & 7u) << 8) | (hits_imask >> 24)];
+#else
             const uint32_t slot = pick_slot(hits_imask >> 24, r.oct_inv4);
+#endif
             const uint32_t child_base = ngroup.x;
             ngroup.y &= ~(1u << (24u + slot));
             if (ngroup.y > 0x00ffffffu) { if (sp < PTB_STACK) stack[sp++] = ngroup; }
