@@ -8,7 +8,7 @@ G = ptb.load()
 for spec in (sys.argv[1:] or ["C2:128", "C3:64"]):
     wl, spp = spec.split(":")
     rt = scenes.CONFIGS[wl](G); rt.nrays = int(spp); rt.commit()
-    for refill, den, pct in ((24, 4, 0), (24, 4, 0), (20, 4, 0), (28, 4, 0), (32, 4, 0), (24, 3, 0), (24, 6, 0), (24, 8, 0), (24, 2, 0), (24, 4, 10), (24, 4, 25), (28, 6, 0)):
+    for refill, den, pct in [tuple(int(x) for x in a.split(',')) for a in os.environ.get('PTB_SWEEP', '24,4,25 24,4,25 24,4,0 24,4,15 24,4,35 22,4,25 26,4,25 24,3,25 24,6,25').split()]:
         rt.set_option(_abi.OPT_REFILL_BELOW, refill); rt.set_option(_abi.OPT_TRI_FRACTION, den); rt.set_option(_abi.OPT_TRI_MIN_PCT, pct)
         best = 1e30
         for rep in range(3):
