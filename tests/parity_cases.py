@@ -296,6 +296,16 @@ def edge_scene(L, variant, W=37, H=23, spp=3):
         m2.max_translation = m2.max_translation + np.array([0, 6, -4], np.float32)
         m2.set_material(0, **scenes.phong((.8, .3, .3), 0.0, 1.0, alpha=Texture(1.0, scenes.checker_alpha_map(64))))
         rt.s.addObject(m2)
+    elif variant in ("mesh_one_triangle", "mesh_four_triangles"):
+        # the smallest trees: a root that holds a single leaf, and a root with four one-triangle leaves (valid24 / compact indices)
+        v = np.array([[-1, 0, -1], [1, 0, -1], [1, 0.3, 1], [-1, 0.2, 1], [0, 1, 0]], np.float32)
+        n = np.tile(np.array([[0, 1, 0]], np.float32), (5, 1))
+        uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1], [.5, .5]], np.float32)
+        faces = [(0, 2, 1), (0, 3, 2), (0, 1, 4), (1, 2, 4)][:1 if variant == "mesh_one_triangle" else 4]
+        tri = np.array([[*f, *f, *f, 0] for f in faces], np.int32)
+        m = scenes._place_like_gui(TriMesh(v, n, uv, tri))
+        m.set_material(0, **scenes.phong((.7, .4, .3), 0.1, 20.0))
+        rt.s.addObject(m)
     elif variant == "many_spheres":      # more analytic objects than the kernel-parameter table holds (8)
         for k in range(9):
             c = (-16 + 4 * k, -22.3 + (k % 3), -6 + 3 * (k % 4))
@@ -311,7 +321,7 @@ def edge_scene(L, variant, W=37, H=23, spp=3):
     return rt
 
 
-EDGE_VARIANTS = ["many_spheres", "mirror_and_flip", "mesh_no_uv_groups", "mesh_flat", "textured_rotated", "alpha_classes", "wide_filter", "depth_one"]
+EDGE_VARIANTS = ["many_spheres", "mirror_and_flip", "mesh_no_uv_groups", "mesh_flat", "textured_rotated", "alpha_classes", "mesh_one_triangle", "mesh_four_triangles", "wide_filter", "depth_one"]
 
 
 def case_edge(test_lib, oracle_lib, variant):
