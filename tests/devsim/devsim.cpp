@@ -346,4 +346,21 @@ int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H, const do
     }
     return PTB_OK;
 }
+
+// test hook: the tile ownership arithmetic of ptb_scene.h (shard_tile_shift, tile_physical, tile_logical) for one frame layout:
+// owner[ty * tiles_x + tx] = shard that renders the tile, order[...] = its position in that shard's render order
+int devsim_tile_owners(int tiles_x, int tiles_y, int count, int32_t* owner, int32_t* order) {
+    const int shift = shard_tile_shift(tiles_x, count), total = tiles_x * tiles_y;
+    for (int i = 0; i < total; i++) owner[i] = order[i] = -1;
+    for (int r = 0; r < count; r++)
+        for (int lt = 0, l = r; l < total; lt++, l += count) {
+            int ty, tx;
+            tile_physical(l, tiles_x, shift, ty, tx);
+            if (ty < 0 || ty >= tiles_y || tx < 0 || tx >= tiles_x) return -1;
+            if (owner[ty * tiles_x + tx] != -1) return -2;                       // a tile handed out twice
+            if (tile_logical(ty, tx, tiles_x, shift) != l) return -3;            // the two directions disagree
+            owner[ty * tiles_x + tx] = r; order[ty * tiles_x + tx] = lt;
+        }
+    return shift;
+}
 }

@@ -109,6 +109,30 @@ def test_shard_pack_roundtrip_devsim(devsim):
         assert np.allclose(merged, full, rtol=2e-5, atol=1e-2), world
 
 
+def test_tile_ownership_is_a_spread_bijection(devsim):
+    """ptb_scene.h shard_tile_shift / tile_physical / tile_logical: every tile belongs to exactly one shard, shard sizes differ by at
+    most one tile, and when the tile columns are a multiple of the shard count (the case that used to give vertical stripes) every row
+    AND every column of tiles holds every shard equally often."""
+    import ctypes
+    raw = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "devsim", "libptb_devsim.so"))
+    for tiles_x, tiles_y, count in [(16, 16, 8), (16, 16, 4), (16, 16, 2), (60, 34, 8), (30, 17, 8), (5, 3, 3), (13, 7, 8), (1, 9, 4), (7, 1, 3), (32, 32, 8), (3, 3, 1)]:
+        owner = np.full(tiles_x * tiles_y, -7, np.int32); order = owner.copy()
+        ip = ctypes.POINTER(ctypes.c_int32)
+        shift = raw.devsim_tile_owners(tiles_x, tiles_y, count, owner.ctypes.data_as(ip), order.ctypes.data_as(ip))
+        assert shift >= 0, (tiles_x, tiles_y, count, shift)
+        assert (owner >= 0).all() and (owner < count).all()
+        sizes = np.bincount(owner, minlength=count)
+        assert sizes.max() - sizes.min() <= 1
+        for r in range(count):                                   # a shard's render order enumerates its tiles 0..n-1
+            assert sorted(order[owner == r]) == list(range(sizes[r]))
+        if count == 1:
+            assert shift == 0 and (order == np.arange(tiles_x * tiles_y)).all()     # one GPU keeps the plain row-major order
+        if count > 1 and tiles_x % count == 0 and tiles_y % count == 0:
+            grid = owner.reshape(tiles_y, tiles_x)
+            for r in range(count):
+                assert ((grid == r).sum(0) == tiles_y // count).all() and ((grid == r).sum(1) == tiles_x // count).all()
+
+
 def test_errors_devsim(devsim):
     case_errors(devsim)
 
