@@ -232,6 +232,40 @@ def case_merl_index_fast(test_lib, n=400000):
     assert (exact >= 0).all() and (exact < 90 * 90 * 180).all()
 
 
+def triangle_soup(n, seed=7):
+    """n unconnected random triangles of very different sizes in a unit cube (file axes): irregular trees, leaves of 1-3 triangles in
+    arbitrary slots, overlapping boxes - what a displaced torus never produces."""
+    rng = np.random.default_rng(seed)
+    c = rng.random((n, 1, 3)) * 2 - 1
+    size = (0.02 + 0.5 * rng.random((n, 1, 1)) ** 4)
+    v = (c + size * (rng.random((n, 3, 3)) - 0.5)).reshape(-1, 3).astype(np.float32)
+    nrm = np.cross(v[1::3] - v[0::3], v[2::3] - v[0::3])
+    nrm = np.repeat(nrm / np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20), 3, 0).astype(np.float32)
+    idx = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+    tri = np.concatenate([idx, np.full((n, 3), -1, np.int32), idx, np.zeros((n, 1), np.int32)], 1)
+    return v, nrm, np.zeros((0, 2), np.float32), tri
+
+
+def case_triangle_soup(test_lib, oracle_lib, n=3000, agree=ID_AGREE):
+    """closest hits (primary ids from two view points) and a path-traced image (closest + shadow rays) over a random soup"""
+    def mk(L):
+        rt = scenes.base(L, 96, 72, 2)
+        m = scenes._place_like_gui(TriMesh(*triangle_soup(n)), scale=22.0)
+        m.set_material(0, **scenes.phong((.6, .5, .4), 0.1, 20.0))
+        rt.s.addObject(m)
+        return rt.commit()
+    a, b = mk(oracle_lib), mk(test_lib)
+    check_ids(b, a, agree=agree)
+    ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+    check_images(ib, ia, frac=0.01)
+    for rt in (a, b):
+        rt.cam.position = np.array([25, 10, -30], np.float32)
+        d = np.array([-0.55, -0.45, 0.7], np.float32)
+        rt.cam.direction = d / np.float32(np.linalg.norm(d))
+        rt.cam.up = np.array([0, 1, 0], np.float32)
+    check_ids(b, a, agree=agree)
+
+
 # ---- edge cases -------------------------------------------------------------------------------------------------
 def quad_mesh(n=6, with_uv=True, with_normals=True, groups=False):
     """A wavy (n x n)-quad sheet in file axes."""

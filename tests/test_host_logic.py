@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
-from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_passes_and_shards,
+from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_triangle_soup, case_passes_and_shards,
                           case_progressive, case_scene, check_ids)
 
 from pathtracer_b200 import _abi, scenes
@@ -74,6 +74,10 @@ def test_bvh8_against_oracle_on_a_larger_mesh(devsim, port):
         rt.cam.direction = np.array([-0.6, -0.35, -0.72], np.float32) / np.float32(np.linalg.norm([-0.6, -0.35, -0.72]))
         rt.cam.up = np.array([0, 1, 0], np.float32)
     check_ids(b, a)
+
+
+def test_triangle_soup_devsim(devsim, port):
+    case_triangle_soup(devsim, port)
 
 
 def test_passes_and_shards_devsim(devsim):

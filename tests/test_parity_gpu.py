@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
-from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_passes_and_shards,
+from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_triangle_soup, case_passes_and_shards,
                           case_progressive, case_scene, check_ids, check_images)
 
 from pathtracer_b200 import _abi, scenes
@@ -28,6 +28,11 @@ def test_native_library_is_what_runs(gpu):
 
 def test_kats_gpu(gpu):
     case_kats(gpu, np.load(os.path.join(GOLD, "kat.npz")))
+
+
+def test_triangle_soup_gpu(gpu, port):
+    """irregular trees (random unconnected triangles): persistent-warp traversal, valid24 / compact indices, postponed triangle groups"""
+    case_triangle_soup(gpu, port, n=20000, agree=0.998)   # 6912 pixels full of silhouette edges: a handful may flip under FMA contraction
 
 
 def test_merl_index_fast_gpu(gpu):
