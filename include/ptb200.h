@@ -11,6 +11,9 @@
  *     (the reference reports nothing: failures there are crashes or silent garbage.)
  *   - the caller owns all input arrays; the library copies what it needs before returning.
  *   - one ptb_ctx is bound to one CUDA device and is used from one host thread at a time.
+ *   - streams: every context works on its own non-blocking CUDA stream and each call returns only after its device work has
+ *     finished.  DEVICE buffers handed in by the caller (ptb_render_accum, ptb_resolve, ptb_shard_*) must therefore be ready
+ *     before the call (synchronise the stream that produced them), and what the call wrote is complete when it returns.
  *   - object ids are assigned in call order exactly like Scene::addObject (Geometry.cpp:249-252):
  *     id 0 is the spherical light, id 1 the environment dome (Raytracer.cpp:1257-1266, hard-wired
  *     in getColor at Raytracer.cpp:275, 303).
@@ -250,6 +253,47 @@ int ptb_shard_pack_size(const ptb_params*, int shard_rank, int64_t* out_floats);
 int ptb_shard_pack(ptb_ctx*, const ptb_params*, int shard_rank, const float* d_rgbw, float* d_packed);
 int ptb_shard_unpack_add(ptb_ctx*, const ptb_params*, int shard_rank, const float* d_packed, float* d_rgbw);
 
+/* ---- multi-GPU: the tile-sharded render under ONE call ---------------------------------------------- */
+/* The reference's callers make one call per frame, Raytracer::render_image_nopreviz() (mainApp.cpp:38-49).  With several GPUs the
+ * frame is sharded by image tiles (owner = tile id % n_ranks, rows rotated), every GPU holds the whole scene, and the only exchange
+ * is the gather of the owned tiles (+ a ceil(2 sigma) splat apron) on rank 0: pack -> ncclSend/ncclRecv over NVLink -> unpack-add
+ * -> resolve, all inside the call and all on the context's own stream.  NCCL is bound at run time (dlopen of libnccl.so.2: the
+ * copy already in the process if there is one; PTB_NCCL_PATH overrides).
+ *
+ * (1) One process per GPU (e.g. torchrun).  Rank 0 calls ptb_comm_unique_id and hands the 128 bytes to every rank by any means
+ * (torch.distributed broadcast, MPI, a file); every rank calls ptb_comm_init on its context (collective), commits the same scene,
+ * and then calls ptb_render_sharded with the same camera and parameters (p->shard_rank / shard_count are taken from the
+ * communicator).  Rank 0 receives the outputs of ptb_render; on the other ranks the output pointers are ignored.  With all
+ * three outputs NULL on rank 0 the gathered sums stay on its device (ptb_resolve_last reads them later).  stats are per rank. */
+#define PTB_COMM_ID_BYTES 128
+int ptb_comm_unique_id(void* out_id128);
+int ptb_comm_init(ptb_ctx*, int n_ranks, int rank, const void* id128);
+int ptb_comm_destroy(ptb_ctx*);
+int ptb_render_sharded(ptb_ctx*, const ptb_camera*, const ptb_params*,
+                       float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats);
+int ptb_resolve_last(ptb_ctx*, int W, int H, float gamma, float* imagedouble, float* sample_count, uint8_t* image);
+
+/* (2) One process, several GPUs: a group owns one context (and, during a render, one host thread) per device.  The scene is handed
+ * to the LEADER context, ptb_group_ctx(g, 0), with the ptb_add_* / ptb_set_* calls above; ptb_group_commit flattens it and builds
+ * the BVH ONCE and uploads it to every device; ptb_group_render is render_image_nopreviz() on all of them (stats: sums over the
+ * devices, ms_device of the slowest).  Do not call ptb_commit / ptb_render on the member contexts directly. */
+typedef struct ptb_group ptb_group;
+int  ptb_group_create(const int* device_ids, int n_devices, ptb_group** out);
+void ptb_group_destroy(ptb_group*);
+const char* ptb_group_last_error(const ptb_group*);      /* group may be NULL: last error of a failed create */
+int  ptb_group_size(const ptb_group*);
+ptb_ctx* ptb_group_ctx(ptb_group*, int i);
+int  ptb_group_commit(ptb_group*);
+int  ptb_group_set_option(ptb_group*, int option, int64_t value);
+int  ptb_group_render(ptb_group*, const ptb_camera*, const ptb_params*,
+                      float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats);
+
+/* Host output buffers that live across frames (Raytracer::imagedouble / sample_count / image are members, Raytracer.h:90-105) can
+ * be page-locked once, so that the device->host copies that end a render run at PCIe speed without a staging copy.  The buffer
+ * must stay allocated until ptb_unpin_host_buffer or ptb_destroy. */
+int ptb_pin_host_buffer(ptb_ctx*, void* ptr, int64_t bytes);
+int ptb_unpin_host_buffer(ptb_ctx*, void* ptr);
+
 /* replaces: the picking query (mainApp.h:686-692): pixel-centre rays
  * cam.generateDirection(0,i,j,0,0,0,0,0,W,H) + Scene::intersection.  HOST outputs W*H each, row i,
  * column j at [i*W+j] (camera order, not flipped); obj_id -1 = miss; tri_id -1 = not a mesh. */
@@ -268,6 +312,11 @@ int ptb_primary_ids(ptb_ctx*, const ptb_camera*, int W, int H,
 #define PTB_OPT_TRACE_BLOCKS     5   /* tuning: persistent grid size of the traversal kernels (default: SMs x resident blocks) */
 #define PTB_OPT_PIPES            9   /* pass pipelines (1..4): consecutive passes of a render run on this many streams, each with its own slice of
                                         the path pool, so that the shade kernels of one pass overlap the traversal kernels of another */
+#define PTB_OPT_BUILD_THREADS    10   /* OpenMP threads of the host BVH build at ptb_commit (0 = the OpenMP runtime's default; launchers such as
+                                        torchrun export OMP_NUM_THREADS=1, which would serialise the build) */
+#define PTB_OPT_STACK_LIMIT      11   /* ptb_commit fails with PTB_ERR_UNSUPPORTED when the BVH8 needs more traversal-stack entries (two per level)
+                                        than this; default and maximum: the kernels' 64 entries (32 levels).  The reference's own 50-entry stack
+                                        overflows silently (TriangleMesh.cpp:1158). */
 int ptb_set_option(ptb_ctx*, int option, int64_t value);
 
 /* Per-kernel device time of the LAST render, measured with CUDA events on the launching stream

@@ -15,6 +15,8 @@ OBJ_MIRROR, OBJ_FLIP_NORMALS, OBJ_FLAT_NORMALS, OBJ_GHOST = 1, 2, 4, 8
 BRDF_PHONG, BRDF_MERL = 0, 1
 KEY_SCALE, KEY_TRANSLATION, KEY_ROTATION = 0, 1, 2
 OPT_COUNT_TRAVERSAL, OPT_POOL_PATHS, OPT_TIME_KERNELS, OPT_REFILL_BELOW, OPT_TRACE_BLOCKS, OPT_TRI_FRACTION, OPT_TRI_MIN_PCT, OPT_SORT_HITS, OPT_PIPES = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OPT_BUILD_THREADS, OPT_STACK_LIMIT = 10, 11
+COMM_ID_BYTES = 128
 KERNEL_NAMES = ["raygen", "extend", "shade", "shadow", "splat"]
 ORC_OPT_THREADS = 100
 (KAT_PCG32, KAT_LATTICE, KAT_CAMERA, KAT_RANDOM_COS, KAT_RANDOM_PHONG, KAT_PHONG_EVAL, KAT_MERL_EVAL,
@@ -97,6 +99,9 @@ SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plan
            "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
            "set_option", "get_scene_info", "kat", "get_kernel_times", "render_denoiser_inputs", "progressive_begin", "progressive_pass",
            "progressive_read"]
+# multi-GPU and host-buffer entry points: the CUDA library only (the CPU checkers under oracle/ and tests/devsim do not have them)
+MULTI_SYMBOLS = ["comm_unique_id", "comm_init", "comm_destroy", "render_sharded", "resolve_last", "group_create", "group_destroy", "group_last_error",
+                 "group_size", "group_ctx", "group_commit", "group_set_option", "group_render", "pin_host_buffer", "unpin_host_buffer"]
 
 
 # ---- include/ptb_sceneio.h -------------------------------------------------------------------------
@@ -221,6 +226,37 @@ class Lib:
             fn = getattr(cdll, prefix + name)  # AttributeError if the symbol is missing: loud by design
             fn.restype, fn.argtypes = res, args
             setattr(self, name, fn)
+        u8p = C.POINTER(C.c_uint8)
+        multi = {
+            "comm_unique_id": (C.c_int, [vp]),
+            "comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+            "comm_destroy": (C.c_int, [vp]),
+            "render_sharded": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), _fp, _fp, u8p, C.POINTER(Stats)]),
+            "resolve_last": (C.c_int, [vp, C.c_int, C.c_int, C.c_float, _fp, _fp, u8p]),
+            "group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+            "group_destroy": (None, [vp]),
+            "group_last_error": (C.c_char_p, [vp]),
+            "group_size": (C.c_int, [vp]),
+            "group_ctx": (vp, [vp, C.c_int]),
+            "group_commit": (C.c_int, [vp]),
+            "group_set_option": (C.c_int, [vp, C.c_int, C.c_int64]),
+            "group_render": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), _fp, _fp, u8p, C.POINTER(Stats)]),
+            "pin_host_buffer": (C.c_int, [vp, vp, C.c_int64]),
+            "unpin_host_buffer": (C.c_int, [vp, vp]),
+        }
+        assert sorted(multi) == sorted(MULTI_SYMBOLS)
+        self.has_multi = hasattr(cdll, prefix + "render_sharded")
+        if self.has_multi or prefix == "ptb_":       # the product must export all of them (AttributeError otherwise)
+            for name, (res, args) in multi.items():
+                fn = getattr(cdll, prefix + name)
+                fn.restype, fn.argtypes = res, args
+                setattr(self, name, fn)
+            self.has_multi = True
+
+    def check_group(self, rc, group=None):
+        if rc != OK:
+            msg = self.group_last_error(group)
+            raise PtbError(f"{self.prefix}group call failed rc={rc}: {msg.decode() if msg else ''}")
 
     def check(self, rc, ctx=None):
         if rc != OK:

@@ -241,9 +241,14 @@ class Raytracer:
     """Raytracer.h:25-121.  Fill the public fields, then `render_image_nopreviz()`; outputs land in
     `imagedouble`, `sample_count`, `image` like the reference's public buffers."""
 
-    def __init__(self, lib, device=0):
+    def __init__(self, lib, device=0, devices=None):
+        """`devices=[0, 1, ...]`: render every frame on several GPUs of this process (tile-sharded, gathered over NCCL inside the
+        library: ptb_group_*, include/ptb200.h); the interface stays the reference's single render_image_nopreviz() call."""
         self.lib = lib
-        self.device = device
+        self.devices = list(devices) if devices is not None else None
+        self.device = self.devices[0] if self.devices else device
+        self._group = None
+        self._comm = (1, 0)          # (ranks, rank) of the one-process-per-GPU communicator, see comm_init
         self.W, self.H, self.nrays, self.nb_bounces = 1000, 800, 100, 3
         self.sigma_filter, self.gamma = 0.5, 2.2
         self.seed = 0
@@ -257,6 +262,7 @@ class Raytracer:
         self.stats = None
         self._ctx = None
         self._keep = []
+        self._pinned = {}
 
     # ---- Raytracer::loadScene (Raytracer.cpp:1238-1274) ----
     def loadScene(self):
@@ -382,10 +388,23 @@ class Raytracer:
         if bad:
             raise _abi.PtbError(f"unsupported by this renderer: {bad}")
         L = self.lib
+        comm = getattr(self, "_comm_args", None)
         self.close()
         ctx = C.c_void_p()
-        L.check(L.create(self.device, C.byref(ctx)))
+        if self.devices and len(self.devices) > 1:
+            g = C.c_void_p()
+            L.check_group(L.group_create((C.c_int * len(self.devices))(*self.devices), len(self.devices), C.byref(g)))
+            self._group = g
+            ctx = C.c_void_p(L.group_ctx(g, 0))
+            for opt, val in getattr(self, "_group_options", {}).items():
+                L.check_group(L.group_set_option(g, opt, val), g)
+        else:
+            L.check(L.create(self.device, C.byref(ctx)))
         self._ctx = ctx
+        if comm is not None:
+            self.comm_init(*comm)
+        if getattr(self, "build_threads", 0):
+            L.check(L.set_option(ctx, _abi.OPT_BUILD_THREADS, int(self.build_threads)), ctx)
         merl_ids = {}
         for o in self.s.objects:
             oid = C.c_int(-1)
@@ -441,8 +460,28 @@ class Raytracer:
         bg = s._background_floats()
         if bg is not None:
             L.check(L.set_background(ctx, fptr(bg), bg.shape[1], bg.shape[0]), ctx)
-        L.check(L.commit(ctx), ctx)
+        if self._group is not None:
+            L.check_group(L.group_commit(self._group), self._group)
+        else:
+            L.check(L.commit(ctx), ctx)
         return self
+
+    # ---- multi-GPU, one process per GPU: every rank builds the same scene, then calls render_image_nopreviz() ----
+    def comm_init(self, n_ranks, rank, id_bytes):
+        """Join the NCCL communicator of a tile-sharded render (ptb_comm_init).  `id_bytes`: the 128 bytes rank 0 got from
+        `comm_unique_id()` and distributed (e.g. torch.distributed.broadcast_object_list).  Survives commit()."""
+        self._comm_args = (int(n_ranks), int(rank), bytes(id_bytes) if id_bytes is not None else None)
+        if self._ctx is not None:
+            buf = C.create_string_buffer(self._comm_args[2], _abi.COMM_ID_BYTES) if self._comm_args[2] is not None else None
+            if int(n_ranks) > 1 or self.lib.has_multi:
+                self.lib.check(self.lib.comm_init(self._ctx, int(n_ranks), int(rank), buf), self._ctx)
+        self._comm = (int(n_ranks), int(rank))
+        return self
+
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(_abi.COMM_ID_BYTES)
+        self.lib.check(self.lib.comm_unique_id(buf), None)
+        return buf.raw
 
     def params(self, shard_rank=0, shard_count=1, tile_size=0):
         p = _abi.Params()
@@ -455,8 +494,14 @@ class Raytracer:
     def _out(self, name, shape, dtype):
         a = getattr(self, name, None)
         if not (self.reuse_buffers and a is not None and a.shape == shape and a.dtype == dtype):
+            if a is not None and id(a) in self._pinned and self._ctx is not None:
+                self.lib.unpin_host_buffer(self._ctx, C.c_void_p(a.ctypes.data)); self._pinned.pop(id(a))
             a = np.empty(shape, dtype)
             setattr(self, name, a)
+        if self.reuse_buffers and self.lib.has_multi and id(a) not in self._pinned and self._ctx is not None:
+            # the Raytracer owns these arrays across frames (Raytracer.h:90-105): page-lock them once
+            if self.lib.pin_host_buffer(self._ctx, C.c_void_p(a.ctypes.data), a.nbytes) == 0:
+                self._pinned[id(a)] = a
         return a
 
     def render_image_nopreviz(self, want_image=True):
@@ -472,9 +517,39 @@ class Raytracer:
         else:
             self.image = None
         st, cam, p = _abi.Stats(), self.cam.c_struct(), self.params()
-        L.check(L.render(ctx, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count),
-                         self.image.ctypes.data_as(C.POINTER(C.c_uint8)) if want_image else None, C.byref(st)), ctx)
+        u8 = self.image.ctypes.data_as(C.POINTER(C.c_uint8)) if want_image else None
+        if self._group is not None:        # several GPUs of this process under the one call
+            L.check_group(L.group_render(self._group, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count), u8, C.byref(st)), self._group)
+        elif self._comm[0] > 1:            # one process per GPU: this rank's share; rank 0 receives the frame
+            L.check(L.render_sharded(ctx, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count), u8, C.byref(st)), ctx)
+            if self._comm[1] != 0:
+                self.imagedouble = self.sample_count = self.image = None
+        else:
+            L.check(L.render(ctx, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count), u8, C.byref(st)), ctx)
         self.stats = st.as_dict()
+        return self.imagedouble
+
+    def render_resident(self):
+        """The same render with the frame left on the device (rank 0 / device 0 holds the gathered sums; `resolve_last()` reads them)."""
+        L, ctx = self.lib, self._ctx
+        st, cam, p = _abi.Stats(), self.cam.c_struct(), self.params()
+        if self._group is not None:
+            L.check_group(L.group_render(self._group, C.byref(cam), C.byref(p), None, None, None, C.byref(st)), self._group)
+        else:
+            L.check(L.render_sharded(ctx, C.byref(cam), C.byref(p), None, None, None, C.byref(st)), ctx)
+        self.stats = st.as_dict()
+        return self.stats
+
+    def resolve_last(self, want_image=True):
+        L, ctx = self.lib, self._ctx
+        self._out("imagedouble", (self.H, self.W, 3), np.float32)
+        self._out("sample_count", (self.H, self.W), np.float32)
+        if want_image:
+            self._out("image", (self.H, self.W, 3), np.uint8)
+        else:
+            self.image = None
+        L.check(L.resolve_last(ctx, self.W, self.H, self.gamma, fptr(self.imagedouble), fptr(self.sample_count),
+                               self.image.ctypes.data_as(C.POINTER(C.c_uint8)) if want_image else None), ctx)
         return self.imagedouble
 
     # ---- Raytracer::render_image (Raytracer.cpp:1424-1563): the progressive renderer ----
@@ -577,7 +652,10 @@ class Raytracer:
         return out
 
     def set_option(self, option, value):
-        self.lib.check(self.lib.set_option(self._ctx, option, int(value)), self._ctx)
+        if self._group is not None:
+            self.lib.check_group(self.lib.group_set_option(self._group, option, int(value)), self._group)
+        else:
+            self.lib.check(self.lib.set_option(self._ctx, option, int(value)), self._ctx)
 
     def kernel_times(self):
         kt = _abi.KernelTimes()
@@ -590,6 +668,11 @@ class Raytracer:
         return info.as_dict()
 
     def close(self):
+        self._pinned = {}                      # ptb_destroy unregisters what was page-locked
+        if self._group is not None:
+            self.lib.group_destroy(self._group)
+            self._group = None
+            self._ctx = None
         if self._ctx is not None:
             self.lib.destroy(self._ctx)
             self._ctx = None

@@ -223,7 +223,10 @@ PTB_HD uint32_t pick_slot(uint32_t hits8, uint32_t oct_inv4) {
     return highest_bit(x);            // one bit is left
 }
 
-#define PTB_STACK 32
+// Traversal stack entries per ray.  A node step pushes at most two entries (the node's other hit children and the triangle group it
+// postpones), so a BVH8 of `depth` wide levels needs at most 2 * depth; ptb_commit refuses deeper trees (PTB_ERR_UNSUPPORTED) instead
+// of dropping subtrees the way a full stack would (the reference's own 50-entry stack overflows silently, TriangleMesh.cpp:1158).
+#define PTB_STACK 64
 
 struct TraverseCounters {
     uint32_t nodes, tris;

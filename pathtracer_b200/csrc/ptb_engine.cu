@@ -8,11 +8,17 @@
 // its element count from device memory, so the host never waits for a count.
 // There is no CPU implementation behind this ABI: a missing device or a failed launch is an error code.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <omp.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ptb_host.h"
@@ -44,6 +50,9 @@ using namespace ptb;
 #define PTB_N_TOTALS 6
 #define PTB_BRANCH_MAX_LEVELS 512
 #define PTB_MAX_PIPES 4
+#ifndef PTB_SMEM_STACK
+#define PTB_SMEM_STACK 0   /* entries of k_trace's traversal stack held in shared memory (A/B: profiles/r02a_ab_smem_stack.txt) */
+#endif
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) k_rpp(float* rpp, int n) {
@@ -96,7 +105,23 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
     RayPrep r;
     float tbest = 0.f, hb1 = 0.f, hb2 = 0.f;
     int32_t hprim = -1;
-    U2 ngroup, tgroup, stack[PTB_STACK];
+    // Traversal stack: the first PTB_SMEM_STACK entries of every lane live in shared memory ([entry][thread]: a warp's 8-byte accesses
+    // are conflict-free whatever the lanes' depths), deeper entries in local memory.
+    U2 ngroup, tgroup;
+#if PTB_SMEM_STACK > 0 && defined(PTB_SMEM_STACK_ONLY)   // A/B only: no local-memory part at all (entries beyond PTB_SMEM_STACK would be lost)
+    __shared__ uint2 sstack[PTB_SMEM_STACK * 128];
+#define PTB_STK_PUSH(e) do { sstack[(sp < PTB_SMEM_STACK ? sp : PTB_SMEM_STACK - 1) * 128 + threadIdx.x] = make_uint2((e).x, (e).y); sp++; } while (0)
+#define PTB_STK_POP(e) do { --sp; const uint2 q_ = sstack[sp * 128 + threadIdx.x]; (e).x = q_.x; (e).y = q_.y; } while (0)
+#elif PTB_SMEM_STACK > 0
+    __shared__ uint2 sstack[PTB_SMEM_STACK * 128];
+    U2 lstack[PTB_STACK - PTB_SMEM_STACK];
+#define PTB_STK_PUSH(e) do { if (sp < PTB_SMEM_STACK) sstack[sp * 128 + threadIdx.x] = make_uint2((e).x, (e).y); else lstack[sp - PTB_SMEM_STACK] = (e); sp++; } while (0)
+#define PTB_STK_POP(e) do { --sp; if (sp < PTB_SMEM_STACK) { const uint2 q_ = sstack[sp * 128 + threadIdx.x]; (e).x = q_.x; (e).y = q_.y; } else (e) = lstack[sp - PTB_SMEM_STACK]; } while (0)
+#else
+    U2 lstack[PTB_STACK];
+#define PTB_STK_PUSH(e) do { lstack[sp++] = (e); } while (0)
+#define PTB_STK_POP(e) do { (e) = lstack[--sp]; } while (0)
+#endif
     uint32_t tvalid = 0;   // valid24 of the node the live triangle group came from (all ones for a group popped from the stack: compact bits)
     int sp = 0;
     ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
@@ -140,7 +165,8 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
         // ---- pop / finish: lanes with neither node nor triangle work
         if (live && ngroup.y <= 0x00ffffffu && tgroup.y == 0) {
             if (sp > 0) {
-                const U2 e = stack[--sp];
+                U2 e;
+                PTB_STK_POP(e);
                 if (e.y > 0x00ffffffu) ngroup = e; else { tgroup = e; tvalid = 0x00ffffffu; }
             } else {
                 if (ANY_HIT && BRANCH) shadow_settle_branch(p, (int)entry, item, false);
@@ -166,7 +192,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
                     cm |= 1u << popcount32(tvalid & ~(0xffffffffu << b));
                 } while (m);
                 tgroup.y = cm;
-                if (sp < PTB_STACK) stack[sp++] = tgroup;
+                if (sp < PTB_STACK) PTB_STK_PUSH(tgroup);   // never full: ptb_commit refuses trees deeper than PTB_STACK / 2
                 tgroup.y = 0;
             }
             const uint32_t hits_imask = ngroup.y;
@@ -177,7 +203,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
 #endif
             const uint32_t child_base = ngroup.x;
             ngroup.y &= ~(1u << (24u + slot));
-            if (ngroup.y > 0x00ffffffu) { if (sp < PTB_STACK) stack[sp++] = ngroup; }
+            if (ngroup.y > 0x00ffffffu) { if (sp < PTB_STACK) PTB_STK_PUSH(ngroup); }
             const uint32_t rel = popcount32(hits_imask & ~(0xffffffffu << slot));
             const float4* np = reinterpret_cast<const float4*>(nodes) + (size_t)(child_base + rel) * 5;
             const float4 l0 = __ldg(np), l1 = __ldg(np + 1), l2 = __ldg(np + 2), l3 = __ldg(np + 3), l4 = __ldg(np + 4);
@@ -519,6 +545,16 @@ struct ptb_ctx {
     int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
     int tri_min_pct = 25;                      // the triangle phase starts once this share of a warp's live lanes hold triangles
     int tri_den = 6;                           // triangle steps repeat while >= 1/tri_den of the live lanes take part (re-swept r01p: 6 is 0.3 % ahead of 4)
+    // multi-GPU (ptb_multi.inl): this context's place in a tile-sharded render and its NCCL communicator
+    void* comm = nullptr;                      // ncclComm_t
+    int comm_n = 1, comm_rank = 0;
+    bool comm_owned = false;
+    F4* d_pack = nullptr;                      // packed tiles + aprons: what a rank sends, or everything rank 0 receives
+    int64_t pack_n = 0;
+    std::vector<std::pair<void*, int64_t>> pinned;   // host buffers page-locked through ptb_pin_host_buffer
+    int64_t info_n_tri = -1, info_nodes = 0; int info_depth = 0;   // group followers: the leader's scene figures
+    int stack_limit = PTB_STACK;               // PTB_OPT_STACK_LIMIT (tests): refuse trees that need more traversal-stack entries than this
+    int build_threads = 0;                     // PTB_OPT_BUILD_THREADS: OpenMP threads of the BVH build (0: the runtime's default)
     std::vector<cudaEvent_t> ev_pool;          // PTB_OPT_TIME_KERNELS: start/stop pairs, one per launch
     std::vector<int> ev_kind;
     ptb_kernel_times ktimes;
@@ -599,6 +635,66 @@ static int grow(ptb_ctx* c, T** buf, int64_t* have, int64_t want) {
 }
 
 // ------------------------------------------------------------------------------------------------ C-ABI
+extern "C" int ptb_comm_destroy(ptb_ctx* c);
+
+// A C++ exception (std::bad_alloc of a scene too large for the host, a reader's length_error) must not unwind through the C boundary
+#define PTB_GUARD(c, body)                                                                               \
+    try { body }                                                                                         \
+    catch (const std::bad_alloc&) { if (c) (c)->err = "out of host memory"; return PTB_ERR_NOMEM; }      \
+    catch (const std::exception& e_) { if (c) (c)->err = std::string("internal error: ") + e_.what(); return PTB_ERR_INVALID; }
+
+// ptb_commit in three steps, so that a group of devices (ptb_multi.inl) flattens and builds once and uploads N times
+static int commit_flatten(ptb_ctx* c) {
+    if (c->build_threads > 0) omp_set_num_threads(c->build_threads);
+    int rc = c->host.flatten(c->flat, c->err);
+    if (rc) return rc;
+    if (2 * c->flat.bvh.depth > c->stack_limit) {
+        c->err = "commit: the BVH8 is " + std::to_string(c->flat.bvh.depth) + " levels deep; the traversal stack (" + std::to_string(c->stack_limit) +
+                 " entries, two per level) cannot hold it";
+        return PTB_ERR_UNSUPPORTED;
+    }
+    return PTB_OK;
+}
+static int commit_upload(ptb_ctx* c, FlatScene& f, const HostScene& host) {
+    CK(cudaSetDevice(c->device));
+    int rc;
+    free_scene(c);
+    auto t0 = std::chrono::steady_clock::now();
+    SceneDev& sc = c->sc;
+    memset(&sc, 0, sizeof(sc));
+    scene_header(sc, f);        // before the upload: it tags objects that do not fit the inline table
+    if ((rc = scene_modes(sc, host, c->err))) return rc;
+    if (sc.bgW > 0 && (rc = upload(c, host.background.data(), host.background.size(), &sc.background))) return rc;
+    c->has_merl = false;
+    for (const ObjectDev& o : f.objects) if (o.brdf == 1) c->has_merl = true;
+    const Node8* dn; const F4* dt; const uint8_t* de;
+    if ((rc = upload(c, f.nodes.data(), f.nodes.size(), &dn))) return rc;
+    if ((rc = upload(c, f.tris.data(), f.tris.size(), &dt))) return rc;
+    if ((rc = upload(c, f.tri_uv.data(), f.tri_uv.size(), &sc.tri_uv))) return rc;
+    if ((rc = upload(c, f.tri_shade.data(), f.tri_shade.size(), &sc.tri_shade))) return rc;
+    if ((rc = upload(c, f.objects.data(), f.objects.size(), &sc.objects))) return rc;
+    if ((rc = upload(c, f.materials.data(), f.materials.size(), &sc.materials))) return rc;
+    if ((rc = upload(c, f.texels.data(), f.texels.size(), &sc.texels))) return rc;
+    if ((rc = upload(c, f.envmap.data(), f.envmap.size(), &de))) return rc;
+    if ((rc = upload(c, f.merl.data(), f.merl.size(), &sc.merl))) return rc;
+    sc.nodes = reinterpret_cast<const F4*>(dn);
+    sc.tris = dt;
+    sc.envmap = de;
+    CK(cudaStreamSynchronize(c->stream));
+    c->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->bytes_nodes = (int64_t)f.nodes.size() * sizeof(Node8);
+    c->bytes_tris = (int64_t)f.tris.size() * sizeof(F4);
+    c->bytes_attr = (int64_t)f.tri_uv.size() * sizeof(TriUV) + (int64_t)f.tri_shade.size() * sizeof(TriShade);
+    c->bytes_tex = (int64_t)f.texels.size() * 4 + (int64_t)f.envmap.size() + (int64_t)f.merl.size() * 4;
+    c->committed = true;
+    return PTB_OK;
+}
+static void commit_release_host(ptb_ctx* c) {   // the host copies of the big arrays are no longer needed
+    FlatScene& f = c->flat;
+    std::vector<F4>().swap(f.tris); std::vector<TriUV>().swap(f.tri_uv); std::vector<TriShade>().swap(f.tri_shade);
+    std::vector<float>().swap(f.texels); std::vector<float>().swap(f.merl);
+}
+
 extern "C" {
 
 const char* ptb_version(void) { return "ptb200 0.1 (sm_100a wavefront, BVH8)"; }
@@ -646,9 +742,12 @@ void ptb_destroy(ptb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    ptb_comm_destroy(c);
+    for (auto& e : c->pinned) cudaHostUnregister(e.first);
+    c->pinned.clear();
     free_scene(c);
     free_pool(c);
-    void* ptrs[] = {c->d_counters, c->d_totals, c->d_rpp, c->d_accum, c->d_out_img, c->d_out_cnt, c->d_out_u8, c->d_aux, c->d_out_aux, c->d_prog_accum, c->d_lowres};
+    void* ptrs[] = {c->d_counters, c->d_totals, c->d_rpp, c->d_accum, c->d_out_img, c->d_out_cnt, c->d_out_u8, c->d_aux, c->d_out_aux, c->d_prog_accum, c->d_lowres, c->d_pack};
     for (void* p : ptrs) if (p) cudaFree(p);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -674,10 +773,12 @@ int ptb_add_plane(ptb_ctx* c, const float A[3], const float N[3], const ptb_xfor
 int ptb_add_mesh(ptb_ctx* c, const ptb_mesh* m, const ptb_xform* xf, int flags, int* out_id) {
     if (!c) return PTB_ERR_INVALID;
     if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
-    const int id = c->host.add_mesh(m, xf, flags, c->err);
-    if (id < 0) return id;
-    if (out_id) *out_id = id;
-    return PTB_OK;
+    PTB_GUARD(c, {
+        const int id = c->host.add_mesh(m, xf, flags, c->err);
+        if (id < 0) return id;
+        if (out_id) *out_id = id;
+        return PTB_OK;
+    })
 }
 int ptb_set_group_material(ptb_ctx* c, int obj, int group, const ptb_material* m) {
     if (!c) return PTB_ERR_INVALID;
@@ -711,7 +812,7 @@ int ptb_set_light(ptb_ctx* c, float intensite_lumiere, float envmap_intensity) {
     c->host.intensite_lumiere = intensite_lumiere;
     c->host.envmap_intensity = envmap_intensity;
     if (c->committed) {  // light constants live in the by-value scene header: cheap to refresh
-        const float s = c->host.objects[0].xf.scale;
+        const float s = placement_at(c->host.objects[0], c->host.current_frame).scale;   // Object::get_scale at the frame, like flatten
         c->sc.lightPower = intensite_lumiere / (s * s);
         c->sc.envmap_intensity = envmap_intensity;
     }
@@ -752,43 +853,13 @@ int ptb_set_background(ptb_ctx* c, const float* rgb, int W, int H) {
 
 int ptb_commit(ptb_ctx* c) {
     if (!c) return PTB_ERR_INVALID;
-    CK(cudaSetDevice(c->device));
-    int rc = c->host.flatten(c->flat, c->err);
-    if (rc) return rc;
-    free_scene(c);
-    auto t0 = std::chrono::steady_clock::now();
-    FlatScene& f = c->flat;
-    SceneDev& sc = c->sc;
-    memset(&sc, 0, sizeof(sc));
-    scene_header(sc, f);        // before the upload: it tags objects that do not fit the inline table
-    if ((rc = scene_modes(sc, c->host, c->err))) return rc;
-    if (sc.bgW > 0 && (rc = upload(c, c->host.background.data(), c->host.background.size(), &sc.background))) return rc;
-    c->has_merl = false;
-    for (const ObjectDev& o : f.objects) if (o.brdf == 1) c->has_merl = true;
-    const Node8* dn; const F4* dt; const uint8_t* de;
-    if ((rc = upload(c, f.nodes.data(), f.nodes.size(), &dn))) return rc;
-    if ((rc = upload(c, f.tris.data(), f.tris.size(), &dt))) return rc;
-    if ((rc = upload(c, f.tri_uv.data(), f.tri_uv.size(), &sc.tri_uv))) return rc;
-    if ((rc = upload(c, f.tri_shade.data(), f.tri_shade.size(), &sc.tri_shade))) return rc;
-    if ((rc = upload(c, f.objects.data(), f.objects.size(), &sc.objects))) return rc;
-    if ((rc = upload(c, f.materials.data(), f.materials.size(), &sc.materials))) return rc;
-    if ((rc = upload(c, f.texels.data(), f.texels.size(), &sc.texels))) return rc;
-    if ((rc = upload(c, f.envmap.data(), f.envmap.size(), &de))) return rc;
-    if ((rc = upload(c, f.merl.data(), f.merl.size(), &sc.merl))) return rc;
-    sc.nodes = reinterpret_cast<const F4*>(dn);
-    sc.tris = dt;
-    sc.envmap = de;
-    CK(cudaStreamSynchronize(c->stream));
-    c->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    c->bytes_nodes = (int64_t)f.nodes.size() * sizeof(Node8);
-    c->bytes_tris = (int64_t)f.tris.size() * sizeof(F4);
-    c->bytes_attr = (int64_t)f.tri_uv.size() * sizeof(TriUV) + (int64_t)f.tri_shade.size() * sizeof(TriShade);
-    c->bytes_tex = (int64_t)f.texels.size() * 4 + (int64_t)f.envmap.size() + (int64_t)f.merl.size() * 4;
-    // the host copies of the big arrays are no longer needed
-    std::vector<F4>().swap(f.tris); std::vector<TriUV>().swap(f.tri_uv); std::vector<TriShade>().swap(f.tri_shade);
-    std::vector<float>().swap(f.texels); std::vector<float>().swap(f.merl);
-    c->committed = true;
-    return PTB_OK;
+    PTB_GUARD(c, {
+        int rc = commit_flatten(c);
+        if (rc) return rc;
+        if ((rc = commit_upload(c, c->flat, c->host))) return rc;
+        commit_release_host(c);
+        return PTB_OK;
+    })
 }
 
 static int frame_setup(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, FrameDev& f) {
@@ -802,6 +873,8 @@ static int frame_setup(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, F
     filter_setup(f.filter, p->sigma_filter);
     f.W = p->W; f.H = p->H; f.nb_bounces = p->nb_bounces; f.seed = p->seed;
     f.tile = p->tile_size > 0 ? p->tile_size : ptb_default_tile(p->shard_count);
+    // a splat reaches ceil(2 sigma) pixels into the neighbouring tiles and the gather looks at the 3x3 tile neighbourhood only
+    if (f.tile < (int)ceilf(p->sigma_filter * 2) || f.tile > 4096) { c->err = "render: tile_size must lie in [ceil(2*sigma_filter), 4096]"; return PTB_ERR_INVALID; }
     f.tiles_x = (p->W + f.tile - 1) / f.tile; f.tiles_y = (p->H + f.tile - 1) / f.tile;
     f.shard_count = p->shard_count > 0 ? p->shard_count : 1;
     f.shard_rank = p->shard_rank;
@@ -1331,6 +1404,8 @@ int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
     case PTB_OPT_TRACE_BLOCKS: if (value < 1) return PTB_ERR_INVALID; c->trace_blocks = c->trace_blocks_piped = (int)value; return PTB_OK;
     case PTB_OPT_SORT_HITS: c->sort_hits = value != 0; return PTB_OK;
     case PTB_OPT_PIPES: if (value < 1 || value > PTB_MAX_PIPES) return PTB_ERR_INVALID; c->n_pipes = (int)value; return PTB_OK;
+    case PTB_OPT_STACK_LIMIT: if (value < 2 || value > PTB_STACK) return PTB_ERR_INVALID; c->stack_limit = (int)value; return PTB_OK;
+    case PTB_OPT_BUILD_THREADS: if (value < 0 || value > 4096) return PTB_ERR_INVALID; c->build_threads = (int)value; return PTB_OK;
     default: return PTB_OK;  // unknown options (e.g. the CPU checkers' thread count) are ignored
     }
 }
@@ -1338,6 +1413,12 @@ int ptb_set_option(ptb_ctx* c, int option, int64_t value) {
 int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
     if (!c || !info) return PTB_ERR_INVALID;
     memset(info, 0, sizeof(*info));
+    if (c->info_n_tri >= 0) {   // a group follower: the leader flattened the scene
+        info->n_triangles = c->info_n_tri; info->n_bvh_nodes = c->info_nodes; info->bvh_depth = c->info_depth;
+        info->bytes_nodes = c->bytes_nodes; info->bytes_triangles = c->bytes_tris; info->bytes_attributes = c->bytes_attr; info->bytes_textures = c->bytes_tex;
+        info->ms_upload = c->ms_upload;
+        return PTB_OK;
+    }
     info->n_triangles = c->flat.n_tri_scene;   // as handed over; bytes_triangles counts those resident (alpha maps can rule triangles out, scene_host.cpp)
     info->n_bvh_nodes = c->flat.bvh.n_nodes;
     info->bytes_nodes = c->bytes_nodes; info->bytes_triangles = c->bytes_tris; info->bytes_attributes = c->bytes_attr; info->bytes_textures = c->bytes_tex;
@@ -1379,3 +1460,5 @@ int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H, const do
 }
 
 }  // extern "C"
+
+#include "ptb_multi.inl"

@@ -158,11 +158,11 @@ def config_C4(lib, W=1024, H=1024, spp=1024, nv=255, device=0):
     return rt
 
 
-def config_C5(lib, W=3840, H=2160, spp=1024, nv=866, device=0):
-    """8 tori (24M triangles at nv=866) on a 4x2 grid, scale 15, Phong, no envmap."""
+def config_C5(lib, W=3840, H=2160, spp=1024, nv=866, device=0, tori=range(8)):
+    """8 tori (24M triangles at nv=866) on a 4x2 grid, scale 15, Phong, no envmap.  `tori`: which of the eight to place."""
     rt = base(lib, W, H, spp, device=device)
     geo = displaced_torus(nv)
-    for k in range(8):
+    for k in tori:
         m = _place_like_gui(TriMesh(*geo), scale=15.0)
         gx, gz = k % 4, k // 4
         m.max_translation = m.max_translation + np.array([(gx - 1.5) * 17.5, 0, (gz - 0.5) * 17.5 - 10], np.float32)

@@ -281,7 +281,7 @@ def test_full_size_C5_24M_triangles(gpu):
     the sharded halves add up to the whole frame."""
     rt = scenes.config_C5(gpu, spp=1).commit()
     info = rt.scene_info()
-    assert info["n_triangles"] == 8 * 2999824 and info["bvh_depth"] <= 32
+    assert info["n_triangles"] == 8 * 2999824 and 2 * info["bvh_depth"] <= 64   # what ptb_commit enforces (PTB_STACK)
     obj, tri, t = rt.primary_ids(960, 540)
     seen = set(int(o) for o in np.unique(obj)) & set(range(3, 11))
     assert len(seen) >= 6, "the camera sees at least six of the eight tori (the outer two of the 4x2 grid are only reached by bounces)"
@@ -293,6 +293,136 @@ def test_full_size_C5_24M_triangles(gpu):
     total = sum(rt.render_accum(acc.data_ptr(), r, 2)["samples"] for r in range(2))
     assert total == 3840 * 2160
     assert np.allclose(rt.resolve(acc.data_ptr()), img, rtol=2e-5, atol=1e-2)
+
+
+def test_full_size_C5_vs_oracle(gpu, port):
+    """BASELINE.json configs[4] against the oracle AT ITS RESOLUTION (3840x2160, 1 spp): the eight-torus scene with 8 x 250,000
+    triangles (the oracle's eight binary BVHs and 8.3 M pixels finish in under a minute), then ONE torus at its full 2,999,824
+    triangles.  Primary-hit ids >= 99.99 %, fixed-seed single-sample image and ray counters as for C2 / C3."""
+    for kw in (dict(nv=250), dict(nv=866, tori=(1,))):
+        mk = lambda L: scenes.config_C5(L, spp=1, **kw)
+        a, b = mk(port).commit(), mk(gpu).commit()
+        assert b.scene_info()["n_triangles"] == len(kw.get("tori", range(8))) * 4 * kw["nv"] ** 2
+        check_ids(b, a)
+        ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+        check_images(ib, ia, frac=FRAC_FULL)
+        for k in ("rays_closest", "rays_shadow"):
+            assert abs(a.stats[k] - b.stats[k]) <= 0.002 * a.stats[k] + 8, k
+        a.close(); b.close()
+
+
+def test_converged_at_size_C1_and_C2(gpu, port):
+    """north_star: "converged images must match within a stated per-pixel relative-RMSE tolerance at equal spp", at the BASELINE
+    sizes: C1 at 512x512 x 64 spp (configs[0] exactly) against a 256-spp oracle image of another seed, C2 (1 M triangles) at
+    1024x1024 x 16 spp against a 64-spp oracle image.  Bound: relRMSE(gpu_N, oracle_hi) <= 1.1 relRMSE(oracle_N, oracle_hi) + 0.005."""
+    from parity_cases import RRMSE_FACTOR, rrmse
+    for mk, n, n_hi in ((lambda L: scenes.config_C1(L), 64, 256), (lambda L: scenes.config_C2(L, spp=16), 16, 64)):
+        hi = mk(port).commit()
+        hi.nrays, hi.seed = n_hi, 99
+        ref_hi = hi.render_image_nopreviz().copy()
+        hi.close()
+        a, b = mk(port).commit(), mk(gpu).commit()
+        assert a.nrays == b.nrays == n
+        ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
+        ea, eb = rrmse(ia, ref_hi), rrmse(ib, ref_hi)
+        assert eb <= RRMSE_FACTOR * ea + 0.005, (ea, eb)
+        assert rrmse(ib, ia) <= 0.02, "equal-seed images should be nearly the same image"
+        a.close(); b.close()
+
+
+def test_commit_refuses_a_tree_deeper_than_the_traversal_stack(gpu):
+    """A full traversal stack would drop subtrees silently (the reference's 50-entry stack does, TriangleMesh.cpp:1158); here the
+    commit fails instead.  PTB_OPT_STACK_LIMIT lowers the limit so that an ordinary mesh exercises the check."""
+    rt = scenes.config_C2(gpu, 32, 32, 1, nv=40, env=(64, 32)).commit()
+    depth = rt.scene_info()["bvh_depth"]
+    assert 2 <= depth <= 32
+    rt.set_option(_abi.OPT_STACK_LIMIT, 2 * depth)           # exactly enough
+    gpu.check(gpu.commit(rt._ctx), rt._ctx)
+    rt.set_option(_abi.OPT_STACK_LIMIT, 2 * depth - 2)
+    assert gpu.commit(rt._ctx) == -5 and b"levels deep" in gpu.last_error(rt._ctx)
+    assert gpu.set_option(rt._ctx, _abi.OPT_STACK_LIMIT, 65) != 0
+
+
+def _multi_worker(rank, world, port_no, out_path, mode):
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port_no)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import pathtracer_b200
+    from pathtracer_b200 import multi
+    rt = scenes.config_C2(pathtracer_b200.load(), 700, 500, 6, nv=60, env=(128, 64), device=rank).commit()
+    if mode == "library":      # the product route: the gather runs inside ptb_render_sharded
+        multi.init_comm(rt, rank, world)
+        img = rt.render_image_nopreviz()
+        cnt, st = rt.sample_count, rt.stats
+    else:                      # host-orchestrated: ptb_render_accum + ptb_shard_* + torch.distributed.gather
+        img, st = multi.render_sharded(rt, rank, world, torch.device("cuda", rank))
+        cnt = rt.sample_count
+    samples = torch.tensor([st["samples"]], dtype=torch.int64, device=f"cuda:{rank}")
+    dist.all_reduce(samples)
+    if rank == 0:
+        np.savez(out_path, img=img, cnt=cnt, samples=samples.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["library", "host"])
+def test_nccl_sharded_render_equals_single(gpu, tmp_path, mode):
+    """N ranks over NCCL == one GPU (runs when the box shows at least two GPUs)."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    out = str(tmp_path / "out.npz")
+    mp.spawn(_multi_worker, args=(world, 29600 + os.getpid() % 2000, out, mode), nprocs=world, join=True)
+    got = np.load(out)
+    rt = scenes.config_C2(gpu, 700, 500, 6, nv=60, env=(128, 64)).commit()
+    ref = rt.render_image_nopreviz()
+    assert got["samples"][0] == 700 * 500 * 6
+    assert np.allclose(got["img"], ref, rtol=2e-5, atol=1e-3) and np.allclose(got["cnt"], rt.sample_count, rtol=2e-5)
+
+
+def test_group_render_equals_single(gpu):
+    """ptb_group_*: all the GPUs of this process under ONE render_image_nopreviz() call (one GPU: a group of one)."""
+    import torch
+    from pathtracer_b200.api import Raytracer
+    n = min(torch.cuda.device_count(), 8)
+    mk = lambda **kw: scenes.config_C3(gpu, 640, 360, 4, nv=60, tex=128, **kw)
+    one = mk().commit()
+    ref = one.render_image_nopreviz().copy()
+    cnt, st = one.sample_count.copy(), dict(one.stats)
+    grp = mk()
+    grp.devices = list(range(n)) if n > 1 else [0]
+    grp.device = 0
+    grp.commit()
+    if n > 1:
+        assert grp._group is not None and gpu.group_size(grp._group) == n
+    img = grp.render_image_nopreviz()
+    assert np.allclose(img, ref, rtol=2e-5, atol=1e-3) and np.allclose(grp.sample_count, cnt, rtol=2e-5)
+    for k in ("samples", "rays_closest", "rays_shadow"):
+        assert grp.stats[k] == st[k], k
+    grp.close(); one.close()
+
+
+def test_resident_render_and_pinned_outputs(gpu):
+    """ptb_render_sharded without host outputs leaves the frame on the device (ptb_resolve_last reads it); page-locked output
+    buffers give the same bytes as pageable ones."""
+    rt = scenes.config_C2(gpu, 200, 120, 3, nv=30, env=(64, 32)).commit()
+    ref = rt.render_image_nopreviz().copy()
+    im8 = rt.image.copy()
+    rt.comm_init(1, 0, None)
+    rt.render_resident()
+    assert np.allclose(rt.resolve_last(), ref, rtol=1e-5, atol=1e-3)
+    rt.reuse_buffers = True
+    a = rt.render_image_nopreviz()
+    assert len(rt._pinned) == 3
+    b = rt.render_image_nopreviz()
+    assert a is b and np.allclose(b, ref, rtol=1e-5, atol=1e-3) and (np.abs(rt.image.astype(int) - im8.astype(int)) <= 1).all()
+    rt.close()
 
 
 @pytest.mark.parametrize("name", ["C2", "C3"])
