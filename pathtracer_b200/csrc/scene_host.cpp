@@ -62,7 +62,8 @@ int HostScene::add_mesh(const ptb_mesh* m, const ptb_xform* xf, int flags, std::
         const int32_t* t = &o.tri[10 * (size_t)i];
         for (int k = 0; k < 3; k++) {
             if (t[k] < 0 || t[k] >= nv) { err = "add_mesh: vertex index out of range"; return PTB_ERR_INVALID; }
-            if (t[3 + k] >= nuv || t[6 + k] >= nn) { err = "add_mesh: uv/normal index out of range"; return PTB_ERR_INVALID; }
+            // -1 is the only "absent" value (TriangleIndices defaults, TriangleMesh.h:55); anything below it would index before the arrays
+            if (t[3 + k] >= nuv || t[6 + k] >= nn || t[3 + k] < -1 || t[6 + k] < -1) { err = "add_mesh: uv/normal index out of range"; return PTB_ERR_INVALID; }
         }
     }
     // (x,y,z) -> (-z,y,x) on vertices and normals (TriangleMesh.cpp:742-751)

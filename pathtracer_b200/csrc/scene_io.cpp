@@ -69,6 +69,9 @@ int paeth(int a, int b, int c) {
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
+// decoded sizes come straight from file headers: cap them so that a malformed file is an error, not a std::bad_alloc
+static const uint64_t PTB_MAX_IMAGE_PIXELS = (uint64_t)1 << 28;   // 16384 x 16384
+
 int decode_png(const std::vector<uint8_t>& d, Image& im) {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (d.size() < 33 || memcmp(d.data(), sig, 8)) return fail(PTB_ERR_INVALID, "png: bad signature");
@@ -104,6 +107,7 @@ int decode_png(const std::vector<uint8_t>& d, Image& im) {
     }
     if (!(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4))) || (ctype == 3 && depth == 16))
         return fail(PTB_ERR_INVALID, "png: bad bit depth");
+    if ((uint64_t)w * (uint64_t)h > PTB_MAX_IMAGE_PIXELS) return fail(PTB_ERR_UNSUPPORTED, "png: image too large");
     const size_t bits = (size_t)depth * chan, stride = ((size_t)w * bits + 7) / 8, bpp = std::max<size_t>(1, bits / 8);
     std::vector<uint8_t> raw((stride + 1) * (size_t)h);
     uLongf rawlen = (uLongf)raw.size();
@@ -166,15 +170,19 @@ int decode_bmp(const std::vector<uint8_t>& d, Image& im) {
     if (bpp != 8 && bpp != 24 && bpp != 32) return fail(PTB_ERR_UNSUPPORTED, "bmp: only 8, 24 and 32 bits per pixel");
     const size_t stride = (((size_t)w * bpp + 31) / 32) * 4;
     if ((size_t)off + stride * (size_t)h > d.size()) return fail(PTB_ERR_INVALID, "bmp: truncated");
-    const uint8_t* pal = &d[14 + hsz];
     const int pal_entry = hsz == 12 ? 3 : 4;
+    // the palette starts right after the info header, whose size comes from the file: every entry a pixel names must lie inside it
+    if (bpp == 8 && (uint64_t)14 + hsz + (uint64_t)pal_entry > d.size()) return fail(PTB_ERR_INVALID, "bmp: palette outside the file");
+    const size_t pal_entries = bpp == 8 ? (d.size() - 14 - hsz) / pal_entry : 0;
+    if ((uint64_t)w * (uint64_t)h > PTB_MAX_IMAGE_PIXELS) return fail(PTB_ERR_UNSUPPORTED, "bmp: image too large");
+    const uint8_t* pal = d.data() + 14 + (bpp == 8 ? hsz : 0);
     im.W = w; im.H = h;
     im.rgb.resize((size_t)w * h * 3);
     for (int y = 0; y < h; y++) {
         const uint8_t* src = &d[off + stride * (size_t)y];
         uint8_t* dst = &im.rgb[(size_t)(flip ? h - 1 - y : y) * w * 3];
         for (int x = 0; x < w; x++) {
-            if (bpp == 8) { const uint8_t* e = pal + (size_t)src[x] * pal_entry; dst[3 * x] = e[2]; dst[3 * x + 1] = e[1]; dst[3 * x + 2] = e[0]; }
+            if (bpp == 8) { if (src[x] >= pal_entries) return fail(PTB_ERR_INVALID, "bmp: palette index outside the file"); const uint8_t* e = pal + (size_t)src[x] * pal_entry; dst[3 * x] = e[2]; dst[3 * x + 1] = e[1]; dst[3 * x + 2] = e[0]; }
             else { const uint8_t* e = src + (size_t)x * (bpp / 8); dst[3 * x] = e[2]; dst[3 * x + 1] = e[1]; dst[3 * x + 2] = e[0]; }
         }
     }
@@ -189,6 +197,7 @@ int decode_tga(const std::vector<uint8_t>& d, Image& im) {
     if (w <= 0 || h <= 0 || !((grey && bpp == 8) || (!grey && (bpp == 24 || bpp == 32)))) return fail(PTB_ERR_UNSUPPORTED, "tga: unsupported pixel depth");
     const int bytes = bpp / 8;
     size_t pos = 18 + (size_t)idlen;
+    if (!rle && pos + (size_t)w * h * bytes > d.size()) return fail(PTB_ERR_INVALID, "tga: truncated");
     std::vector<uint8_t> px((size_t)w * h * bytes);
     if (!rle) {
         if (pos + px.size() > d.size()) return fail(PTB_ERR_INVALID, "tga: truncated");
@@ -341,6 +350,7 @@ int read_obj(const char* path, ptb_meshfile& m, std::string& mtl) {
     FILE* f = fopen(path, "r");
     if (!f) return fail(PTB_ERR_INVALID, std::string("cannot open mesh file '") + path + "'");
     int cur_group = -1;
+    bool bad_ref = false;
     std::string line;
     char buf[4096];
     while (fgets(buf, sizeof buf, f)) {
@@ -389,6 +399,9 @@ int read_obj(const char* path, ptb_meshfile& m, std::string& mtl) {
                 int32_t r[10] = {resolve(v[a], nv), resolve(v[b], nv), resolve(v[c], nv), -1, -1, -1, -1, -1, -1, cur_group};
                 if (form == 1 || form == 2) { r[3] = resolve(t[a], nt); r[4] = resolve(t[b], nt); r[5] = resolve(t[c], nt); }
                 if (form == 2 || form == 3) { r[6] = resolve(n[a], nn); r[7] = resolve(n[b], nn); r[8] = resolve(n[c], nn); }
+                // a relative reference that points before the start of its list (e.g. "f -5/-5/-5" after two vt lines) resolves below
+                // zero: the reference indexes out of bounds there; this reader refuses the file
+                for (int q = 0; q < 9; q++) if (r[q] < -1 || (q < 3 && r[q] < 0)) bad_ref = true;
                 m.tri.insert(m.tri.end(), r, r + 10);
             };
             emit(0, 1, 2, form0);
@@ -406,6 +419,7 @@ int read_obj(const char* path, ptb_meshfile& m, std::string& mtl) {
         }
     }
     fclose(f);
+    if (bad_ref) return fail(PTB_ERR_INVALID, "obj: a face references an element before the start of its list");
     if (m.group_names.empty()) {                                  // 470-475
         for (size_t i = 9; i < m.tri.size(); i += 10) m.tri[i] = 0;
         m.group_names["Default"] = 0;
@@ -473,6 +487,13 @@ int read_off(const char* path, ptb_meshfile& m) {
     char tag[64];
     int nv = 0, nf = 0, nx = 0;
     if (fscanf(f, "%63s", tag) != 1 || fscanf(f, "%d %d %d", &nv, &nf, &nx) != 3 || nv < 0 || nf < 0) { fclose(f); return fail(PTB_ERR_INVALID, "off: bad header"); }
+    {   // every vertex takes at least six characters of the file: a header that promises more than the file can hold is malformed
+        const long here = ftell(f);
+        fseek(f, 0, SEEK_END);
+        const long size = ftell(f);
+        fseek(f, here, SEEK_SET);
+        if ((int64_t)nv * 6 > (int64_t)size || (int64_t)nf * 8 > (int64_t)size) { fclose(f); return fail(PTB_ERR_INVALID, "off: header counts exceed the file"); }
+    }
     m.vertices.resize((size_t)nv * 3);
     for (int i = 0; i < nv * 3; i++) if (fscanf(f, "%f", &m.vertices[i]) != 1) { fclose(f); return fail(PTB_ERR_INVALID, "off: truncated vertices"); }
     for (int i = 0; i < nf; i++) {
@@ -766,11 +787,17 @@ void fill_tex(ptb_tex& t, const Slot& sl, std::vector<float>& store, bool normal
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ C-ABI
+// A C++ exception (std::bad_alloc on a header that asks for gigabytes, a length_error) must not unwind through the C boundary
+#define PTB_IO_CATCH                                                                                      \
+    catch (const std::bad_alloc&) { return fail(PTB_ERR_NOMEM, "out of host memory"); }                   \
+    catch (const std::exception& e_) { return fail(PTB_ERR_INVALID, std::string("reader failed: ") + e_.what()); }
+
 extern "C" {
 
 const char* ptb_sceneio_last_error(void) { return g_err.c_str(); }
 
 int ptb_image_load(const char* path, uint8_t** rgb, int32_t* W, int32_t* H) {
+    try {
     if (!path || !rgb || !W || !H) return fail(PTB_ERR_INVALID, "image_load: null argument");
     Image im;
     int rc = load_image_flipped(path, im);
@@ -780,10 +807,12 @@ int ptb_image_load(const char* path, uint8_t** rgb, int32_t* W, int32_t* H) {
     memcpy(*rgb, im.rgb.data(), im.rgb.size());
     *W = im.W; *H = im.H;
     return PTB_OK;
+    } PTB_IO_CATCH
 }
 void ptb_image_free(void* p) { free(p); }
 
 int ptb_texture_load(const char* path, int kind, float** values, int32_t* W, int32_t* H) {
+    try {
     if (!path || !values || !W || !H || (kind != 0 && kind != 1)) return fail(PTB_ERR_INVALID, "texture_load: bad argument");
     std::vector<float> v;
     int w = 0, h = 0;
@@ -794,15 +823,18 @@ int ptb_texture_load(const char* path, int kind, float** values, int32_t* W, int
     memcpy(*values, v.data(), v.size() * sizeof(float));
     *W = w; *H = h;
     return PTB_OK;
+    } PTB_IO_CATCH
 }
 
 int ptb_meshfile_read(const char* path, int load_textures, ptb_meshfile** out) {
+    try {
     if (!path || !out) return fail(PTB_ERR_INVALID, "meshfile_read: null argument");
     ptb_meshfile* m = new ptb_meshfile();
     int rc = read_meshfile(path, load_textures, *m);
     if (rc) { delete m; return rc; }
     *out = m;
     return PTB_OK;
+    } PTB_IO_CATCH
 }
 void ptb_meshfile_free(ptb_meshfile* m) { delete m; }
 int ptb_meshfile_get(const ptb_meshfile* m, ptb_meshfile_info* o) {
@@ -831,12 +863,14 @@ int ptb_meshfile_group_slot(const ptb_meshfile* m, int group, int kind, ptb_slot
 }
 
 int ptb_scn_load(const char* path, const char* replaced_names, ptb_scn** out) {
+    try {
     if (!path || !out) return fail(PTB_ERR_INVALID, "scn_load: null argument");
     ptb_scn* s = new ptb_scn();
     int rc = parse_scn(path, replaced_names, *s);
     if (rc) { delete s; return rc; }
     *out = s;
     return PTB_OK;
+    } PTB_IO_CATCH
 }
 void ptb_scn_free(ptb_scn* s) { delete s; }
 int ptb_scn_get_header(const ptb_scn* s, ptb_scn_header* out) {
@@ -872,6 +906,7 @@ int ptb_scn_get_keyframes(const ptb_scn* s, int obj, int kind, float* frames, fl
 }
 
 int ptb_scn_save(const ptb_scn* s, const char* path) {
+    try {
     if (!s || !path) return fail(PTB_ERR_INVALID, "scn_save: null argument");
     FILE* f = fopen(path, "w");
     if (!f) return fail(PTB_ERR_INVALID, std::string("cannot write '") + path + "'");
@@ -920,9 +955,11 @@ int ptb_scn_save(const ptb_scn* s, const char* path) {
             h.fog_density, h.fog_absorption, h.fog_density_decay, h.fog_absorption_decay, h.fog_type, h.fog_phase_type, h.double_frustum_start_t);
     fclose(f);
     return PTB_OK;
+    } PTB_IO_CATCH
 }
 
 int ptb_load_scene(ptb_ctx* ctx, const char* path, const char* replaced_names, ptb_camera* cam, ptb_params* params) {
+    try {
     if (!ctx || !path) return fail(PTB_ERR_INVALID, "load_scene: null argument");
     ptb_scn sc;
     int rc = parse_scn(path, replaced_names, sc);
@@ -1007,6 +1044,7 @@ int ptb_load_scene(ptb_ctx* ctx, const char* path, const char* replaced_names, p
         params->sigma_filter = h.sigma_filter; params->gamma = h.gamma; params->shard_count = 1;
     }
     return PTB_OK;
+    } PTB_IO_CATCH
 }
 
 }  // extern "C"

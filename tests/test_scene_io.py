@@ -137,6 +137,36 @@ def test_reader_errors(io, tmp_path):
     assert io.image_load(str(trunc).encode(), C.byref(p), C.byref(w), C.byref(hh)) == -1
 
 
+def test_malformed_files_are_errors_not_crashes(io, tmp_path):
+    """Sizes and offsets taken from file headers are validated: an over-read, a gigabyte allocation or a C++ exception crossing the
+    C boundary would take the host process down."""
+    import struct
+    p, w, hh = C.POINTER(C.c_uint8)(), C.c_int32(), C.c_int32()
+    h = C.c_void_p()
+    # 8-bpp BMP whose info-header size points the palette far outside the file
+    px = bytes(range(16))
+    bmp = b"BM" + struct.pack("<IHHI", 54 + len(px), 0, 0, 54) + struct.pack("<IiiHHIIiiII", 0x7fffff00, 4, 4, 1, 8, 0, len(px), 0, 0, 0, 0) + px
+    f = tmp_path / "pal.bmp"; f.write_bytes(bmp)
+    assert io.image_load(str(f).encode(), C.byref(p), C.byref(w), C.byref(hh)) == -1 and b"palette" in io.sceneio_last_error()
+    # PNG header that announces 2^24 x 2^24 pixels
+    png = open(os.path.join(sio.ASSETS, "checker.png"), "rb").read()
+    import zlib
+    ihdr = struct.pack(">IIBBBBB", 1 << 24, 1 << 24, 8, 2, 0, 0, 0)
+    big = png[:8] + struct.pack(">I", 13) + b"IHDR" + ihdr + struct.pack(">I", zlib.crc32(b"IHDR" + ihdr)) + png[33:]
+    f = tmp_path / "big.png"; f.write_bytes(big)
+    assert io.image_load(str(f).encode(), C.byref(p), C.byref(w), C.byref(hh)) in (-1, -5)
+    # OFF header that promises two billion vertices
+    f = tmp_path / "big.off"; f.write_text("OFF\n2000000000 1 0\n0 0 0\n")
+    assert io.meshfile_read(str(f).encode(), 0, C.byref(h)) == -1 and b"exceed" in io.sceneio_last_error()
+    # OBJ face with relative references that point before the start of the vt / vn lists
+    f = tmp_path / "neg.obj"
+    f.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvn 0 0 1\nf -3/-5/-5 -2/-1/-1 -1/-2/-1\n")
+    assert io.meshfile_read(str(f).encode(), 0, C.byref(h)) == -1 and b"before the start" in io.sceneio_last_error()
+    f.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvn 0 0 1\nf -3/-2/-1 -2/-1/-1 -1/-2/-1\n")      # in range: fine
+    assert io.meshfile_read(str(f).encode(), 0, C.byref(h)) == 0
+    io.meshfile_free(h)
+
+
 def _scn_with_modes(tmp_path):
     """old.scn with a participating medium, a ghost ground plane and a background photograph switched on."""
     txt = open(os.path.join(sio.ASSETS, "old.scn")).read()
