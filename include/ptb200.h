@@ -158,6 +158,15 @@ int ptb_add_mesh(ptb_ctx*, const ptb_mesh*, const ptb_xform*, int flags, int* ou
 /* replaces: Object::{add,set}_{col_,}{texture,specular,roughness,transp,refr,alpha,normalmap}
  * (Geometry.cpp:56-245) for slot index `group` of object `obj`. */
 int ptb_set_group_material(ptb_ctx*, int obj, int group, const ptb_material*);
+/* replaces: the material presets of the reference's object menu (mainApp.cpp:1499-1597, ID_GOLD ... ID_COPPER_NGAN): Phong constants
+ * {Kd, Ks, Ne}.  "<name>" is the OpenGL-style table entry (Ne = shininess * 128), "<name>_ngan" the Phong fit to the measured BRDF of
+ * that material (Ngan et al. 2005) as the reference lists it: gold, silver, pearl, white_plastic, chrome, bronze, copper.  A menu
+ * entry does set_col_texture(Kd) + set_col_specular(Ks) + set_col_roughness(Ne,Ne,Ne) on one slot index; the host mirrors do the same
+ * (pathtracer_b200/api.py Object.set_preset, ptb_raytracer.hpp Object::set_preset).  ptb_preset_find: index or -1. */
+int ptb_preset_count(void);
+int ptb_preset_get(int index, const char** name, float Kd[3], float Ks[3], float* Ne);
+int ptb_preset_find(const char* name);
+
 /* replaces: `obj->brdf = new IsoMERLBRDF(path)` (mainApp.cpp:2436) / the PhongBRDF default. */
 int ptb_set_brdf(ptb_ctx*, int obj, int brdf_kind, int merl_id);
 /* replaces: read_brdf (MERLBRDFRead.cpp:212-235): table = 3 x (90*90*180) doubles as stored in the file. */

@@ -99,8 +99,8 @@ SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plan
            "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
            "set_option", "get_scene_info", "kat", "get_kernel_times", "render_denoiser_inputs", "progressive_begin", "progressive_pass",
            "progressive_read"]
-# multi-GPU and host-buffer entry points: the CUDA library only (the CPU checkers under oracle/ and tests/devsim do not have them)
-MULTI_SYMBOLS = ["comm_unique_id", "comm_init", "comm_destroy", "render_sharded", "resolve_last", "group_create", "group_destroy", "group_last_error",
+# material presets, multi-GPU and host-buffer entry points: the CUDA library only (the CPU checkers under oracle/ and tests/devsim do not have them)
+MULTI_SYMBOLS = ["preset_count", "preset_get", "preset_find", "comm_unique_id", "comm_init", "comm_destroy", "render_sharded", "resolve_last", "group_create", "group_destroy", "group_last_error",
                  "group_size", "group_ctx", "group_commit", "group_set_option", "group_render", "pin_host_buffer", "unpin_host_buffer"]
 
 
@@ -228,6 +228,9 @@ class Lib:
             setattr(self, name, fn)
         u8p = C.POINTER(C.c_uint8)
         multi = {
+            "preset_count": (C.c_int, []),
+            "preset_get": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), _fp, _fp, _fp]),
+            "preset_find": (C.c_int, [C.c_char_p]),
             "comm_unique_id": (C.c_int, [vp]),
             "comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
             "comm_destroy": (C.c_int, [vp]),

@@ -61,6 +61,27 @@ class Texture:
         return t
 
 
+# Material presets of the reference's object menu (mainApp.cpp:1499-1597): name -> (Kd, Ks, Ne).  "<name>": OpenGL-style table entry
+# (Ne = shininess * 128); "<name>_ngan": Phong fit to the measured BRDF (Ngan et al. 2005).  The same table lives in the library
+# (ptb_preset_get, csrc/scene_host.cpp); tests/test_host_logic.py checks the two against each other and against the reference's source.
+PRESETS = {
+    "gold": ((0.75164, 0.60648, 0.22648), (0.628281, 0.555802, 0.366065), 0.4 * 128),
+    "gold_ngan": ((0.069, 0.0323, 0.00638), (0.0738, 0.0434, 0.0104), 41.9),
+    "silver": ((0.50754, 0.50754, 0.50754), (0.508273, 0.508273, 0.508273), 0.4 * 128),
+    "silver_ngan": ((0.0695, 0.0628, 0.0446), (0.0742, 0.0615, 0.0412), 75.0),
+    "pearl": ((1.0, 0.829, 0.829), (0.296648, 0.296648, 0.296648), 0.088 * 128),
+    "pearl_ngan": ((0.189, 0.146, 0.0861), (0.0485, 0.0346, 0.0161), 27.7),
+    "white_plastic": ((0.55, 0.55, 0.55), (0.70, 0.70, 0.70), 0.25 * 128),
+    "white_plastic_ngan": ((0.102, 0.0887, 0.0573), (0.00699, 0.00566, 0.0036), 1040.0),
+    "chrome": ((0.4, 0.4, 0.4), (0.774597, 0.774597, 0.774597), 0.6 * 128),
+    "chrome_ngan": ((0.00817, 0.0063, 0.00474), (0.0213, 0.0151, 0.00766), 17900.0),
+    "bronze": ((0.714, 0.4284, 0.18144), (0.393548, 0.271906, 0.166721), 0.2 * 128),
+    "bronze_ngan": ((0.0864, 0.0597, 0.0302), (0.015, 0.00818, 0.00381), 1290.0),
+    "copper": ((0.7038, 0.27048, 0.0828), (0.256777, 0.137622, 0.086014), 0.1 * 128),
+    "copper_ngan": ((0.0749, 0.0414, 0.027), (0.0756, 0.0437, 0.0202), 33200.0),
+}
+
+
 def _io():
     from . import sceneio
     return sceneio()
@@ -133,6 +154,29 @@ class Object:
         """e.g. set_material(0, Kd=Texture((.5,.5,.5)), Ks=Texture(.2), Ne=Texture(50))"""
         self.materials.setdefault(group, {}).update(slots)
         return self
+
+    # ---- Object::set_col_texture / set_col_specular / set_col_roughness (Geometry.cpp:165-177, 229-234): the slot KEEPS its texels,
+    #      only its multiplier changes; a slot index that does not exist is left alone, like the reference does ----
+    def _set_col(self, name, col, idx):
+        t = self.materials.get(idx, {}).get(name)
+        if t is not None:
+            t.multiplier = tuple(float(np.float32(x)) for x in col)
+        return self
+
+    def set_col_texture(self, col, idx=0):
+        return self._set_col("Kd", col, idx)
+
+    def set_col_specular(self, col, idx=0):
+        return self._set_col("Ks", col, idx)
+
+    def set_col_roughness(self, col, idx=0):
+        return self._set_col("Ne", col, idx)
+
+    def set_preset(self, name, idx=0):
+        """A material preset of the reference's object menu (mainApp.cpp:1499-1597), e.g. "gold", "gold_ngan" (the Phong fit of
+        Ngan et al. to the measured BRDF), "copper_ngan": set_col_texture + set_col_specular + set_col_roughness on slot `idx`."""
+        kd, ks, ne = PRESETS[name]
+        return self.set_col_texture(kd, idx).set_col_specular(ks, idx).set_col_roughness((ne, ne, ne), idx)
 
     def _flags(self):
         return ((_abi.OBJ_MIRROR if self.miroir else 0) | (_abi.OBJ_FLIP_NORMALS if self.flip_normals else 0)

@@ -401,3 +401,45 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
 }
 
 }  // namespace ptb
+
+// ---- material presets: the Phong constants behind the reference's object menu (mainApp.cpp:1499-1597) --------------------------------
+// "<name>": the classic OpenGL material table the reference cites (Ne = shininess * 128); "<name>_ngan": the Phong lobes fitted to
+// measured BRDFs (Ngan, Durand, Matusik 2005) as the reference lists them.  Each preset does what the menu entry does:
+// set_col_texture(Kd), set_col_specular(Ks), set_col_roughness(Ne, Ne, Ne) on one slot index.
+namespace {
+struct Preset { const char* name; float Kd[3], Ks[3], Ne; };
+const Preset kPresets[] = {
+    {"gold", {0.75164f, 0.60648f, 0.22648f}, {0.628281f, 0.555802f, 0.366065f}, (float)(0.4 * 128)},
+    {"gold_ngan", {0.069f, 0.0323f, 0.00638f}, {0.0738f, 0.0434f, 0.0104f}, 41.9f},
+    {"silver", {0.50754f, 0.50754f, 0.50754f}, {0.508273f, 0.508273f, 0.508273f}, (float)(0.4 * 128)},
+    {"silver_ngan", {0.0695f, 0.0628f, 0.0446f}, {0.0742f, 0.0615f, 0.0412f}, 75.f},
+    {"pearl", {1.f, 0.829f, 0.829f}, {0.296648f, 0.296648f, 0.296648f}, (float)(0.088 * 128)},
+    {"pearl_ngan", {0.189f, 0.146f, 0.0861f}, {0.0485f, 0.0346f, 0.0161f}, 27.7f},
+    {"white_plastic", {0.55f, 0.55f, 0.55f}, {0.70f, 0.70f, 0.70f}, (float)(0.25 * 128)},
+    {"white_plastic_ngan", {0.102f, 0.0887f, 0.0573f}, {0.00699f, 0.00566f, 0.0036f}, 1040.f},
+    {"chrome", {0.4f, 0.4f, 0.4f}, {0.774597f, 0.774597f, 0.774597f}, (float)(0.6 * 128)},
+    {"chrome_ngan", {0.00817f, 0.0063f, 0.00474f}, {0.0213f, 0.0151f, 0.00766f}, 17900.f},
+    {"bronze", {0.714f, 0.4284f, 0.18144f}, {0.393548f, 0.271906f, 0.166721f}, (float)(0.2 * 128)},
+    {"bronze_ngan", {0.0864f, 0.0597f, 0.0302f}, {0.015f, 0.00818f, 0.00381f}, 1290.f},
+    {"copper", {0.7038f, 0.27048f, 0.0828f}, {0.256777f, 0.137622f, 0.086014f}, (float)(0.1 * 128)},
+    {"copper_ngan", {0.0749f, 0.0414f, 0.027f}, {0.0756f, 0.0437f, 0.0202f}, 33200.f},
+};
+const int kNumPresets = (int)(sizeof(kPresets) / sizeof(kPresets[0]));
+}  // namespace
+
+extern "C" {
+int ptb_preset_count(void) { return kNumPresets; }
+int ptb_preset_get(int index, const char** name, float Kd[3], float Ks[3], float* Ne) {
+    if (index < 0 || index >= kNumPresets) return PTB_ERR_INVALID;
+    const Preset& p = kPresets[index];
+    if (name) *name = p.name;
+    for (int k = 0; k < 3; k++) { if (Kd) Kd[k] = p.Kd[k]; if (Ks) Ks[k] = p.Ks[k]; }
+    if (Ne) *Ne = p.Ne;
+    return PTB_OK;
+}
+int ptb_preset_find(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < kNumPresets; i++) if (!strcmp(kPresets[i].name, name)) return i;
+    return -1;
+}
+}

@@ -1,7 +1,9 @@
 // ptb_cli.cpp — headless driver: the `rayTracer <scene> <out>` path of the reference (mainApp.cpp:38-49) over the
 // CUDA library: a .scn file written by Raytracer::save_scene, or the synthetic scenes of SURVEY.md §8d.
-//   ptb_cli <scene.scn> <out.ppm> [W H spp]          (0 keeps the file's value)
-//   ptb_cli <C1|torus>  <out.ppm> [W H spp nv]
+//   ptb_cli [--gpus N] [--preset NAME] <scene.scn> <out.ppm> [W H spp]          (0 keeps the file's value)
+//   ptb_cli [--gpus N] [--preset NAME] <C1|torus>  <out.ppm> [W H spp nv]
+// --gpus N: devices 0..N-1 of this process render the frame together (tile-sharded, NCCL gather inside the library);
+// --preset NAME: a material preset of the reference's object menu on the synthetic scene's objects (gold, gold_ngan, ..., copper_ngan).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -32,9 +34,20 @@ static std::shared_ptr<TriMesh> displaced_torus(int nv) {   // SURVEY.md §8d ge
 }
 
 int main(int argc, char** argv) {
+    int n_gpus = 1;
+    const char* preset = nullptr;
+    while (argc > 2 && argv[1][0] == '-' && argv[1][1] == '-') {
+        if (!std::strcmp(argv[1], "--gpus")) n_gpus = std::atoi(argv[2]);
+        else if (!std::strcmp(argv[1], "--preset")) preset = argv[2];
+        else { std::fprintf(stderr, "ptb_cli: unknown option %s\n", argv[1]); return 2; }
+        argv += 2; argc -= 2;
+    }
+    if (n_gpus < 1 || n_gpus > 64) { std::fprintf(stderr, "ptb_cli: --gpus must be 1..64\n"); return 2; }
     if (argc < 3) { std::fprintf(stderr, "usage: %s <scene.scn|C1|torus> <out.ppm> [W H spp nv]   (PTB_FRAME=<n> renders frame n of a key-framed .scn)\n", argv[0]); return 2; }
     try {
-        Raytracer rt;
+        std::vector<int> devices;
+        for (int i = 0; i < n_gpus; i++) devices.push_back(i);
+        Raytracer rt(devices);
         const size_t len = std::strlen(argv[1]);
         const bool scn = len > 4 && !std::strcmp(argv[1] + len - 4, ".scn");
         if (scn) {
@@ -63,6 +76,7 @@ int main(int argc, char** argv) {
             g->materials.push_back(phong(Vector(.5f, .5f, .5f), .2f, 50.f));
             rt.s.addObject(g);
         }
+        if (preset) for (size_t i = 3; i < rt.s.objects.size(); i++) rt.s.objects[i]->set_preset(preset, 0);
         rt.commit();
         }
         rt.render_image_nopreviz();
@@ -72,7 +86,7 @@ int main(int argc, char** argv) {
         std::fwrite(rt.image.data(), 1, rt.image.size(), f);
         std::fclose(f);
         const double rays = (double)rt.stats.rays_closest + (double)rt.stats.rays_shadow;
-        std::printf("%dx%d %d spp: %.1f ms on the device, %.1f Msamples/s, %.1f Mrays/s, %llu kernel launches\n", rt.W, rt.H, rt.nrays, rt.stats.ms_device,
+        std::printf("%d GPU(s), %dx%d %d spp: %.1f ms on the device, %.1f Msamples/s, %.1f Mrays/s, %llu kernel launches\n", n_gpus, rt.W, rt.H, rt.nrays, rt.stats.ms_device,
                     rt.stats.samples / rt.stats.ms_device / 1e3, rays / rt.stats.ms_device / 1e3, (unsigned long long)rt.stats.kernel_launches);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "ptb_cli: %s\n", e.what());

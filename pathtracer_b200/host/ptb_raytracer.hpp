@@ -88,6 +88,18 @@ struct Object {                  // Geometry.h:240-672
         std::array<float, 9> m; std::memcpy(m.data(), mat_rotation, sizeof(mat_rotation));
         rotation_keyframes[(float)frame] = m; translation_keyframes[(float)frame] = max_translation; scale_keyframes[(float)frame] = scale;
     }
+    // Object::set_col_texture / set_col_specular / set_col_roughness (Geometry.cpp:165-177, 229-234): only the multiplier of an
+    // EXISTING slot changes (its texels stay); an index past the end is ignored like the reference does
+    void set_col_texture(const Vector& col, int idx) { if (idx >= 0 && idx < (int)materials.size() && (materials[idx].present & PTB_SLOT_KD)) materials[idx].Kd.multiplier = col; }
+    void set_col_specular(const Vector& col, int idx) { if (idx >= 0 && idx < (int)materials.size() && (materials[idx].present & PTB_SLOT_KS)) materials[idx].Ks.multiplier = col; }
+    void set_col_roughness(const Vector& col, int idx) { if (idx >= 0 && idx < (int)materials.size() && (materials[idx].present & PTB_SLOT_NE)) materials[idx].Ne.multiplier = col; }
+    // a material preset of the reference's object menu (mainApp.cpp:1499-1597): "gold", "gold_ngan", ..., "copper_ngan" (ptb_preset_get)
+    void set_preset(const char* name, int idx = 0) {
+        const int k = ptb_preset_find(name);
+        float kd[3], ks[3], ne;
+        if (k < 0 || ptb_preset_get(k, nullptr, kd, ks, &ne) != PTB_OK) throw Error(std::string("unknown material preset: ") + name);
+        set_col_texture(Vector(kd[0], kd[1], kd[2]), idx); set_col_specular(Vector(ks[0], ks[1], ks[2]), idx); set_col_roughness(Vector(ne, ne, ne), idx);
+    }
     explicit Object(ObjectType t) : type(t) {}
     virtual ~Object() = default;
 };
@@ -132,7 +144,10 @@ public:
     ptb_stats stats{};
 
     explicit Raytracer(int device = 0) : device_(device) {}
-    ~Raytracer() { if (ctx_) ptb_destroy(ctx_); }
+    // several GPUs of this process under the same single call: the frame is tile-sharded and gathered over NCCL inside the library
+    // (ptb_group_*, include/ptb200.h); `devices` = CUDA device ids
+    explicit Raytracer(const std::vector<int>& devices) : device_(devices.empty() ? 0 : devices[0]), devices_(devices) {}
+    ~Raytracer() { release(); }
     Raytracer(const Raytracer&) = delete;
 
     void loadScene() {               // Raytracer.cpp:1238-1274
@@ -154,28 +169,26 @@ public:
     // environment map it names and feeds the device context; this object receives the camera and frame parameters.
     // The scene is committed on return (`s.objects` stays empty: the description lives in the context).
     void load_scene(const char* filename, const char* replacedNames = nullptr) {
-        if (ctx_) { ptb_destroy(ctx_); ctx_ = nullptr; }
-        if (ptb_create(device_, &ctx_) != PTB_OK) throw Error(std::string("ptb_create: ") + ptb_last_error(nullptr));
+        acquire();
         ptb_camera c; ptb_params p;
         if (ptb_load_scene(ctx_, filename, replacedNames, &c, &p) != PTB_OK) throw Error(std::string("load_scene: ") + ptb_sceneio_last_error());
         W = p.W; H = p.H; nrays = p.nrays; nb_bounces = p.nb_bounces; sigma_filter = p.sigma_filter; gamma = p.gamma;
         cam = Camera(Vector(c.position[0], c.position[1], c.position[2]), Vector(c.direction[0], c.direction[1], c.direction[2]), Vector(c.up[0], c.up[1], c.up[2]));
         cam.fov = c.fov; cam.focus_distance = c.focus_distance; cam.aperture = c.aperture;
         ck(ptb_set_frame(ctx_, (float)s.current_frame));
-        ck(ptb_commit(ctx_));
+        commit_device();
     }
     // One frame of an animation (mainApp.cpp:874-877): key-framed objects are placed at `frame` and the scene is committed again.
     void set_frame(int frame) {
         s.current_frame = frame;
         if (!ctx_) { commit(); return; }
         ck(ptb_set_frame(ctx_, (float)frame));
-        ck(ptb_commit(ctx_));
+        commit_device();
     }
 
     // hands the scene to the device: TriMesh::init + build_bvh + Scene::prepare_render equivalents
     void commit() {
-        if (ctx_) { ptb_destroy(ctx_); ctx_ = nullptr; }
-        if (ptb_create(device_, &ctx_) != PTB_OK) throw Error(std::string("ptb_create: ") + ptb_last_error(nullptr));
+        acquire();
         std::vector<std::pair<const std::vector<double>*, int>> merl_ids;
         for (auto& op : s.objects) {
             Object& o = *op;
@@ -233,7 +246,7 @@ public:
         ck(ptb_set_fog(ctx_, &fog));
         ck(ptb_set_background(ctx_, s.backgroundW > 0 ? s.background.data() : nullptr, s.backgroundW, s.backgroundH));
         ck(ptb_set_frame(ctx_, (float)s.current_frame));
-        ck(ptb_commit(ctx_));
+        commit_device();
     }
 
     // Raytracer::render_image_nopreviz (Raytracer.cpp:1565-1798): fills imagedouble / sample_count / image
@@ -241,8 +254,17 @@ public:
         if (!ctx_) commit();
         ptb_camera c; ptb_params p;
         fill(c, p);
-        image.resize((size_t)W * H * 3); imagedouble.resize((size_t)W * H * 3); sample_count.resize((size_t)W * H);
-        ck(ptb_render(ctx_, &c, &p, imagedouble.data(), sample_count.data(), image.data(), &stats));
+        const bool grown = image.size() != (size_t)W * H * 3;
+        if (grown) {     // the output vectors are members that live across frames (Raytracer.h:90-105): page-lock them once per size
+            unpin();
+            image.resize((size_t)W * H * 3); imagedouble.resize((size_t)W * H * 3); sample_count.resize((size_t)W * H);
+            ptb_pin_host_buffer(ctx_, imagedouble.data(), (int64_t)(imagedouble.size() * sizeof(float)));
+            ptb_pin_host_buffer(ctx_, sample_count.data(), (int64_t)(sample_count.size() * sizeof(float)));
+            ptb_pin_host_buffer(ctx_, image.data(), (int64_t)image.size());
+            pinned_ = true;
+        }
+        if (group_) { if (ptb_group_render(group_, &c, &p, imagedouble.data(), sample_count.data(), image.data(), &stats) != PTB_OK) throw Error(std::string("group render: ") + ptb_group_last_error(group_)); }
+        else ck(ptb_render(ctx_, &c, &p, imagedouble.data(), sample_count.data(), image.data(), &stats));
     }
 
     // Raytracer::render_image (Raytracer.cpp:1424-1563): progressive; `stopped` may be set from `on_pass` (the GUI sets it from
@@ -291,7 +313,31 @@ private:
         p.shard_rank = 0; p.shard_count = 1; p.tile_size = 0;
     }
     void ck(int rc) { if (rc != PTB_OK) throw Error(std::string("ptb error ") + std::to_string(rc) + ": " + ptb_last_error(ctx_)); }
+    void unpin() {
+        if (pinned_ && ctx_) { ptb_unpin_host_buffer(ctx_, imagedouble.data()); ptb_unpin_host_buffer(ctx_, sample_count.data()); ptb_unpin_host_buffer(ctx_, image.data()); }
+        pinned_ = false;
+    }
+    void release() {
+        unpin();
+        image.clear();      // the next render pins afresh
+        if (group_) { ptb_group_destroy(group_); group_ = nullptr; ctx_ = nullptr; }
+        if (ctx_) { ptb_destroy(ctx_); ctx_ = nullptr; }
+    }
+    void acquire() {        // a fresh context (one GPU) or group (several): the scene is handed to ctx_ either way
+        release();
+        if (devices_.size() > 1) {
+            if (ptb_group_create(devices_.data(), (int)devices_.size(), &group_) != PTB_OK) throw Error(std::string("ptb_group_create: ") + ptb_group_last_error(nullptr));
+            ctx_ = ptb_group_ctx(group_, 0);
+        } else if (ptb_create(device_, &ctx_) != PTB_OK) throw Error(std::string("ptb_create: ") + ptb_last_error(nullptr));
+    }
+    void commit_device() {
+        if (group_) { if (ptb_group_commit(group_) != PTB_OK) throw Error(std::string("group commit: ") + ptb_group_last_error(group_)); }
+        else ck(ptb_commit(ctx_));
+    }
     int device_;
+    std::vector<int> devices_;
+    ptb_group* group_ = nullptr;
+    bool pinned_ = false;
     ptb_ctx* ctx_ = nullptr;
 };
 

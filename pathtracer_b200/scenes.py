@@ -127,6 +127,19 @@ def config_C1(lib, W=512, H=512, spp=64, device=0):
     return rt
 
 
+def config_ngan(lib, W=128, H=128, spp=8, nv=24, device=0):
+    """The material presets of the reference's object menu (mainApp.cpp:1499-1597) on real objects: a torus in the Ngan fit of gold,
+    spheres in the Ngan fits of copper (Ne 33200: a needle-sharp lobe) and pearl, and one in the OpenGL-table bronze."""
+    rt = base(lib, W, H, spp, device=device)
+    m = _place_like_gui(TriMesh(*displaced_torus(nv)))
+    m.set_material(0, **phong((.5, .5, .5), (.2, .2, .2), 50.0)).set_preset("gold_ngan", 0)
+    rt.s.addObject(m)
+    for O, R, name in (((-20, -20.3, 8), 7, "copper_ngan"), ((19, -21.3, 10), 6, "pearl_ngan"), ((2, -23.3, 22), 4, "bronze")):
+        rt.s.addObject(Sphere(O, R).set_material(0, **phong((.8, .3, .3), 0.1, 10.0)).set_preset(name, 0))
+    rt.s.objects[1].envmap = sky_envmap(128, 64)
+    return rt
+
+
 def config_C2(lib, W=1024, H=1024, spp=256, nv=500, env=(2048, 1024), device=0):
     """1M-triangle Phong torus + 8-bit sky envmap."""
     rt = base(lib, W, H, spp, device=device)

@@ -99,12 +99,16 @@ def modes_golden(R):
 def main():
     R = ref_lib()
     assert R is not None, "oracle/_ref is not built (needs /root/reference)"
-    sceneio_golden(R)
-    modes_golden(R)
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]      # --only=NGAN,C1: just these scene fixtures
+    if not only:
+        sceneio_golden(R)
+        modes_golden(R)
     todo = {**BRANCH_SCENES, **STAT_SCENES, **ANIM_SCENES}
     if "--new-only" not in sys.argv:
         todo.update(SCENES)
-    if "--new-only" not in sys.argv:
+    if only:
+        todo = {k: v for k, v in {**todo, **SCENES}.items() if k in only[0]}
+    if "--new-only" not in sys.argv and not only:
         rt = scenes.config_C4(R, 32, 32, 1, nv=10).commit()   # any committed scene with a MERL table
         out = {}
         for which, (inp, kw) in KAT_INPUTS().items():

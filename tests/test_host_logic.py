@@ -2,6 +2,7 @@
 tangents, matrices), the BVH8 builder, the shard/tile arithmetic — and, through tests/devsim (the device headers
 compiled for the host, test-only), the device logic itself against the oracle.  No GPU needed."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -12,6 +13,7 @@ from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_erro
 from pathtracer_b200 import _abi, scenes
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_kats_devsim(devsim):
@@ -149,3 +151,55 @@ def test_generators_are_deterministic_and_sized():
     assert env.dtype == np.uint8 and env.shape == (32, 64, 3) and env.max() == 255
     t = scenes.merl_table()
     assert t.shape == (3, 90, 90, 180) and np.allclose(t[0] * (1.0 / 1500), t[1] * (1.15 / 1500)) and np.allclose(t[0] * (1.0 / 1500), t[2] * (1.66 / 1500))
+
+
+def test_material_presets_equal_the_reference_menu():
+    """Phong / Ngan material presets (north_star: "Phong/Ngan/MERL materials"): the table of the Python mirror, the table inside the
+    library (ptb_preset_get) and the constants of the reference's object menu (mainApp.cpp:1499-1597, committed as
+    tests/golden/presets.json by tests/golden/make_presets.py; re-parsed live when /root/reference is present) are the same numbers."""
+    import ctypes as C
+    import json
+    import pathtracer_b200
+    from pathtracer_b200 import api
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "presets.json")))
+    if os.path.exists("/root/reference/mainApp.cpp"):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_presets
+        assert make_presets.parse() == gold
+    assert sorted(gold) == sorted(api.PRESETS) and len(gold) == 14 and sum(k.endswith("_ngan") for k in gold) == 7
+    lib = pathtracer_b200.load()
+    assert lib.preset_count() == 14 and lib.preset_find(b"nope") == -1
+    for name, g in gold.items():
+        kd, ks, ne = api.PRESETS[name]
+        f32 = lambda v: [float(np.float32(x)) for x in v]
+        assert f32(kd) == f32(g["Kd"]) and f32(ks) == f32(g["Ks"]) and f32([ne] * 3) == f32(g["Ne"]), name
+        i = lib.preset_find(name.encode())
+        assert i >= 0
+        nm, a, b, c = C.c_char_p(), (C.c_float * 3)(), (C.c_float * 3)(), C.c_float()
+        assert lib.preset_get(i, C.byref(nm), a, b, C.byref(c)) == 0 and nm.value.decode() == name
+        assert list(a) == f32(g["Kd"]) and list(b) == f32(g["Ks"]) and float(c.value) == f32(g["Ne"])[0], name
+    # Object::set_col_*: only the multiplier of an EXISTING slot changes, the texels stay; a missing slot index is ignored
+    o = api.Sphere((0, 0, 0), 1).set_material(0, Kd=api.Texture((1, 1, 1), np.ones((2, 2, 3), np.float32)), Ks=api.Texture(0.5), Ne=api.Texture(9.0))
+    o.set_preset("gold_ngan", 0).set_preset("chrome", 3)
+    assert o.materials[0]["Kd"].values is not None and o.materials[0]["Kd"].multiplier == tuple(f32(gold["gold_ngan"]["Kd"]))
+    assert o.materials[0]["Ne"].multiplier == tuple(f32(gold["gold_ngan"]["Ne"])) and 3 not in o.materials
+
+
+def test_cpp_host_mirror_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """host/ptb_raytracer.hpp + ptb_cli.cpp (the C++ side of the boundary) build against include/ptb200.h; without a device the
+    driver reports the library's error and exits 1 (no CPU path), with or without --gpus."""
+    import subprocess
+    import torch
+    cli = os.path.join(ROOT, "pathtracer_b200", "csrc", "ptb_cli")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "pathtracer_b200", "csrc"), "-s", "ptb_cli"])
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+    r = subprocess.run([cli, "--gpus", "0", "C1", str(tmp_path / "x.ppm")], capture_output=True, text=True)
+    assert r.returncode == 2
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: tests/test_parity_gpu.py::test_cpp_cli_* cover the render")
+    for extra in ([], ["--gpus", "2"]):
+        r = subprocess.run([cli] + extra + ["C1", str(tmp_path / "x.ppm"), "32", "32", "1"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU path" in r.stderr, r.stderr
+    r = subprocess.run([cli, "--preset", "nope", "C1", str(tmp_path / "x.ppm")], capture_output=True, text=True)
+    assert r.returncode == 1 and "unknown material preset" in r.stderr

@@ -144,6 +144,18 @@ def test_errors_gpu(gpu):
     rt.sigma_filter, rt.nrays = 0.5, 0
     with pytest.raises(_abi.PtbError):
         rt.render_image_nopreviz()
+    rt.nrays = 1
+    p, cam, st = rt.params(0, 2, 0), rt.cam.c_struct(), _abi.Stats()
+    p.tile_size, p.sigma_filter = 1, 1.5                      # a splat would reach past the neighbouring tile: the gather cannot see it
+    import torch
+    acc = torch.zeros(16 * 16 * 4, dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()
+    assert gpu.render_accum(rt._ctx, C.byref(cam), C.byref(p), C.c_void_p(acc.data_ptr()), C.byref(st)) == -1 and b"tile_size" in gpu.last_error(rt._ctx)
+    # a uv / normal index below -1 (-1 is the only "absent" value) is refused instead of read
+    bad = scenes.config_C2(gpu, 16, 16, 1, nv=8, env=(16, 8))
+    bad.s.objects[3].tri[0, 4] = -7
+    with pytest.raises(_abi.PtbError):
+        bad.commit()
 
 
 def test_primary_ids_on_a_quarter_million_triangles(gpu, port):
@@ -423,6 +435,62 @@ def test_resident_render_and_pinned_outputs(gpu):
     b = rt.render_image_nopreviz()
     assert a is b and np.allclose(b, ref, rtol=1e-5, atol=1e-3) and (np.abs(rt.image.astype(int) - im8.astype(int)) <= 1).all()
     rt.close()
+
+
+def _read_ppm(path):
+    parts = open(path, "rb").read().split(b"\n", 3)      # P6 / W H / 255 / bytes
+    w, h = (int(x) for x in parts[1].split())
+    return np.frombuffer(parts[3], np.uint8).reshape(h, w, 3)
+
+
+def test_cpp_cli_renders_like_the_python_mirror(gpu, port, tmp_path):
+    """The C++ side of the boundary (host/ptb_raytracer.hpp + ptb_cli.cpp): a .scn file and a synthetic scene rendered by the
+    headless driver give the 8-bit image the Python mirror gives; --preset reaches the device; --gpus N (when the box has N GPUs)
+    gives the same picture."""
+    import subprocess
+    import sceneio_cases as sio
+    import torch
+    from pathtracer_b200 import api
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pathtracer_b200", "csrc", "ptb_cli")
+    with sio.in_assets():
+        out = str(tmp_path / "full.ppm")
+        r = subprocess.run([cli, "full.scn", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "Msamples/s" in r.stdout
+        rt = api.Raytracer(gpu).load_scene_native("full.scn")
+        rt.render_image_nopreviz()
+    img = _read_ppm(out)
+    assert img.shape == rt.image.shape and (np.abs(img.astype(int) - rt.image.astype(int)) > 1).mean() < 1e-3
+    # synthetic torus (the driver's own generator == scenes.displaced_torus), with and without a Ngan preset
+    mk = lambda L: scenes.base(L, 96, 64, 4)
+    def py_torus(preset):
+        q = mk(gpu)
+        m = scenes.TriMesh(*scenes.displaced_torus(30))
+        m.scale, m.max_translation = 30.0, np.array([0, np.float32(-27.3) + np.float32(0.29) * np.float32(30.0), 0], np.float32)
+        m.set_material(0, Kd=api.Texture((.5, .5, .5)), Ks=api.Texture(.2), Ne=api.Texture(50.0), transp=api.Texture(1.0), refr=api.Texture(1.3))
+        if preset:
+            m.set_preset(preset, 0)
+        q.s.addObject(m)
+        q.commit().render_image_nopreviz()
+        return q.image
+    for preset in (None, "copper_ngan"):
+        out = str(tmp_path / "t.ppm")
+        r = subprocess.run([cli] + (["--preset", preset] if preset else []) + ["torus", out, "96", "64", "4", "30"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        ref = py_torus(preset)
+        assert (np.abs(_read_ppm(out).astype(int) - ref.astype(int)) > 1).mean() < 2e-3, preset
+    plain = _read_ppm(out)
+    n = torch.cuda.device_count()
+    if n >= 2:
+        out2 = str(tmp_path / "t2.ppm")
+        r = subprocess.run([cli, "--gpus", str(min(n, 4)), "--preset", "copper_ngan", "torus", out2, "96", "64", "4", "30"], capture_output=True, text=True)
+        assert r.returncode == 0 and f"{min(n, 4)} GPU(s)" in r.stdout, r.stderr
+        assert (np.abs(_read_ppm(out2).astype(int) - plain.astype(int)) > 1).mean() < 1e-3
+
+
+def test_ngan_preset_scene_vs_oracle_and_golden(gpu, port):
+    """Phong / Ngan material presets on a mesh and three spheres: against the oracle at equal seed and against the reference's own image."""
+    case_scene(gpu, port, SCENES["NGAN"])
 
 
 @pytest.mark.parametrize("name", ["C2", "C3"])
