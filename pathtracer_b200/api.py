@@ -553,21 +553,23 @@ class Raytracer:
         if ctx is None:
             self.commit()
             ctx = self._ctx
-        n = self.W * self.H
+        st, cam, p = _abi.Stats(), self.cam.c_struct(), self.params()
+        if self._group is None and self._comm[0] > 1 and self._comm[1] != 0:
+            # one process per GPU, not rank 0: this rank renders its tiles and sends them; the frame lands on rank 0
+            L.check(L.render_sharded(ctx, C.byref(cam), C.byref(p), None, None, None, C.byref(st)), ctx)
+            self.stats = st.as_dict()
+            return None
         self._out("imagedouble", (self.H, self.W, 3), np.float32)
         self._out("sample_count", (self.H, self.W), np.float32)
         if want_image:
             self._out("image", (self.H, self.W, 3), np.uint8)
         else:
             self.image = None
-        st, cam, p = _abi.Stats(), self.cam.c_struct(), self.params()
         u8 = self.image.ctypes.data_as(C.POINTER(C.c_uint8)) if want_image else None
         if self._group is not None:        # several GPUs of this process under the one call
             L.check_group(L.group_render(self._group, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count), u8, C.byref(st)), self._group)
-        elif self._comm[0] > 1:            # one process per GPU: this rank's share; rank 0 receives the frame
+        elif self._comm[0] > 1:            # one process per GPU, rank 0: its own tiles + the gather
             L.check(L.render_sharded(ctx, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count), u8, C.byref(st)), ctx)
-            if self._comm[1] != 0:
-                self.imagedouble = self.sample_count = self.image = None
         else:
             L.check(L.render(ctx, C.byref(cam), C.byref(p), fptr(self.imagedouble), fptr(self.sample_count), u8, C.byref(st)), ctx)
         self.stats = st.as_dict()

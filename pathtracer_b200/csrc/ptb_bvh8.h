@@ -38,6 +38,9 @@ struct alignas(16) Node8 {
 };
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 
+#if !defined(PTB_EDGE_EPS_ON)
+#define PTB_EDGE_EPS_ON 1      /* 0: the fast triangle test decides everything (A/B: profiles/r02d_ab_exact_edges.txt) */
+#endif
 #define PTB_TRI_FLAG_ALPHA 1u  /* tri.w0 bit: this triangle's group has an alpha map that can reject */
 #define PTB_TRI_FLAG_GHOST 2u  /* tri.w0 bit: the triangle belongs to a ghost object; shadow rays pass through it (Geometry.cpp:722) */
 
@@ -90,6 +93,10 @@ PTB_HD RayPrep ray_prep(V3 o, V3 d) {
 // Alpha callback data: uv + group + object of a triangle, and the material table (see ptb_scene.h).
 struct AlphaCtx;
 PTB_HD bool alpha_rejects(const AlphaCtx* ctx, int prim, float b1, float b2);
+// Triangle::intersection (TriangleMesh.h:82-104) in the reference's own arithmetic: object-space ray, plane + Gram barycentrics, every
+// operation rounded separately (ptb_scene.h).  Decides the hits the fast test below cannot call: rays within PTB_EDGE_EPS of an edge.
+PTB_HD bool tri_exact_available(const AlphaCtx* ctx);
+PTB_HD_NOINLINE bool tri_exact(const AlphaCtx* ctx, int prim, V3 o, V3 d, float tbest, float& t, float& b1, float& b2);   // out of line: the hot loop keeps its registers
 
 // Tests the 8 children of `n` against the ray; returns the hit mask in SLOT order: bit 24 + s = the internal child in slot s,
 // bits 3s..3s+2 = the triangles of the leaf in slot s (only bits that exist: valid24 / imask).
@@ -189,8 +196,16 @@ inline uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4&
 }
 #endif
 
+// Barycentric band around the triangle's edges inside which the fast test defers to tri_exact.  The fast test works on world-space
+// float vertices, the reference on object-space ones: their barycentrics differ by up to a few 1e-5 (coordinates of magnitude 50
+// against edges of 0.1), so a ray that close to an edge can land on either side.  A ray near a SHARED edge is near it in both
+// triangles, so both get the reference's t and the reference's accept decision, and the nearer one wins as it does there.
+#if !defined(PTB_EDGE_EPS)
+#define PTB_EDGE_EPS 5e-4f
+#endif
+
 // Möller–Trumbore on {v0,e1,e2}; two-sided; accepts b1,b2 >= 0, b1+b2 <= 1, 0 <= t < tbest.
-PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, float tbest, float& t, float& b1, float& b2) {
+PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, float tbest, float& t, float& b1, float& b2, const AlphaCtx* ex, int prim) {
     const V3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
     const V3 pvec = cross(r.d, e2);
     const float det = dot(e1, pvec);
@@ -208,7 +223,13 @@ PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, fl
     const float v = dot(r.d, qvec) * inv;
     const float tt = dot(e2, qvec) * inv;
     // written so that NaN (degenerate triangle, det == 0) fails every test
-    if (!(u >= 0.f) || !(v >= 0.f) || !(1.f - u - v >= 0.f) || !(tt >= 0.f) || !(tt < tbest)) return false;
+    const float m = fminf(fminf(u, v), 1.f - u - v);
+#if PTB_EDGE_EPS_ON
+    if (!(m >= -PTB_EDGE_EPS)) return false;                 // clearly outside
+    // near an edge, or an alpha-mapped triangle (the texel its uv lands on must be the reference's): the reference's arithmetic decides
+    if ((m < PTB_EDGE_EPS || (f2u(a.w) & PTB_TRI_FLAG_ALPHA)) && tri_exact_available(ex)) return tri_exact(ex, prim, r.o, r.d, tbest, t, b1, b2);
+#endif
+    if (!(m >= 0.f) || !(tt >= 0.f) || !(tt < tbest)) return false;
     t = tt; b1 = u; b2 = v;
     return true;
 }
@@ -292,7 +313,7 @@ PTB_HD bool traverse(const F4* __restrict__ nodes, const F4* __restrict__ tris, 
             }
             if (COUNT) cnt->tris++;
             float t, b1, b2;
-            if (tri_test(a, b, c, r, tbest, t, b1, b2)) {
+            if (tri_test(a, b, c, r, tbest, t, b1, b2, actx, (int)prim)) {
                 if ((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(actx, (int)prim, b1, b2)) continue;
                 if (ANY_HIT && (f2u(a.w) & PTB_TRI_FLAG_GHOST)) continue;
                 tbest = t;
@@ -358,7 +379,7 @@ PTB_HD void traverse_all(const F4* __restrict__ nodes, const F4* __restrict__ tr
                 c.x = l2.x; c.y = l2.y; c.z = l2.z; c.w = l2.w;
             }
             float t, b1, b2;
-            if (tri_test(a, b, c, r, tmax, t, b1, b2)) {
+            if (tri_test(a, b, c, r, tmax, t, b1, b2, actx, (int)prim)) {
                 if ((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(actx, (int)prim, b1, b2)) continue;
                 on_hit((int32_t)prim, t, b1, b2);
             }

@@ -68,6 +68,36 @@ PTB_HD V3 normalize(V3 a) {
 // VectorT::reflect (Vector.h:388-391): d - 2 (d.N) N
 PTB_HD V3 reflect(V3 d, V3 N) { return d - (2.f * dot(d, N)) * N; }
 
+// ---- the reference's float arithmetic, operation by operation ---------------------------------------------------------------------
+// nvcc contracts a*b+c into one FMA (one rounding), the reference's x86-64 build rounds twice.  Where a DECISION of the reference has
+// to be reproduced and not just its value (which triangle a ray near a shared edge hits, which texel an alpha lookup reads), the
+// operations are spelled with the round-to-nearest intrinsics, which are never contracted, in the reference's order.  (The host
+// compilations of these headers, tests/devsim, use -ffp-contract=off.)
+#if defined(__CUDA_ARCH__)
+PTB_HD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+PTB_HD float add_rn(float a, float b) { return __fadd_rn(a, b); }
+PTB_HD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+PTB_HD float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+PTB_HD float sqrt_rn(float a) { return __fsqrt_rn(a); }
+#else
+PTB_HD float mul_rn(float a, float b) { return a * b; }
+PTB_HD float add_rn(float a, float b) { return a + b; }
+PTB_HD float sub_rn(float a, float b) { return a - b; }
+PTB_HD float div_rn(float a, float b) { return a / b; }
+PTB_HD float sqrt_rn(float a) { return sqrtf(a); }
+#endif
+PTB_HD float dot_rn(V3 a, V3 b) { return add_rn(add_rn(mul_rn(a.x, b.x), mul_rn(a.y, b.y)), mul_rn(a.z, b.z)); }     // Vector.h:553-556
+PTB_HD V3 cross_rn(V3 a, V3 b) {
+    return v3(sub_rn(mul_rn(a.y, b.z), mul_rn(a.z, b.y)), sub_rn(mul_rn(a.z, b.x), mul_rn(a.x, b.z)), sub_rn(mul_rn(a.x, b.y), mul_rn(a.y, b.x)));
+}
+PTB_HD V3 add3_rn(V3 a, V3 b) { return v3(add_rn(a.x, b.x), add_rn(a.y, b.y), add_rn(a.z, b.z)); }
+PTB_HD V3 sub3_rn(V3 a, V3 b) { return v3(sub_rn(a.x, b.x), sub_rn(a.y, b.y), sub_rn(a.z, b.z)); }
+PTB_HD V3 scale_rn(float s, V3 a) { return v3(mul_rn(s, a.x), mul_rn(s, a.y), mul_rn(s, a.z)); }
+PTB_HD V3 normalize_rn(V3 a) {                                                                                       // Vector.h:371-376
+    const float n = sqrt_rn(dot_rn(a, a));
+    return v3(div_rn(a.x, n), div_rn(a.y, n), div_rn(a.z, n));
+}
+
 PTB_HD uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 PTB_HD float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
@@ -453,7 +483,7 @@ PTB_HD void camera_setup(CameraDev& c, const float* pos, const float* dir, const
     c.position = v3(pos[0], pos[1], pos[2]);
     c.direction = v3(dir[0], dir[1], dir[2]);
     c.up = v3(up[0], up[1], up[2]);
-    c.right = cross(c.direction, c.up);
+    c.right = cross_rn(c.direction, c.up);
     c.k = (float)W / (2 * tanf(fov / 2));
     c.focus_distance = focus;
     c.aperture = aperture;
@@ -462,14 +492,17 @@ PTB_HD void camera_setup(CameraDev& c, const float* pos, const float* dir, const
 }
 PTB_HD void camera_ray(const CameraDev& c, int i, int j, float dx, float dy, float ax, float ay, V3& o, V3& d) {
     // j - W/2 + 0.5 + dx : integer W/2, sum in double, narrowed to float by the Vector ctor
+    // every operation rounded like the reference's (no FMA contraction): camera rays are BIT-IDENTICAL to generateDirection's, so a
+    // primary ray that grazes an edge grazes it on the same side in both implementations
     V3 dv = v3((float)((double)(j - c.W / 2) + 0.5 + (double)dx), (float)((double)(i - c.H / 2) + 0.5 + (double)dy), c.k);
-    dv = normalize(dv);
-    dv = c.right * dv.x + c.up * dv.y + c.direction * dv.z;
-    V3 dest = c.position + (c.focus_distance / fabsf(dot(dv, c.direction))) * dv;
-    o = c.position + ax * c.right + ay * c.up;
-    d = normalize(dest - o);
+    dv = normalize_rn(dv);
+    dv = add3_rn(add3_rn(scale_rn(dv.x, c.right), scale_rn(dv.y, c.up)), scale_rn(dv.z, c.direction));
+    const V3 dest = add3_rn(c.position, scale_rn(div_rn(c.focus_distance, fabsf(dot_rn(dv, c.direction))), dv));
+    o = add3_rn(add3_rn(c.position, scale_rn(ax, c.right)), scale_rn(ay, c.up));
+    d = normalize_rn(sub3_rn(dest, o));
     // + init_t * d / dot(d, direction) with init_t == 0 (Scene::double_frustum_start_t)
-    o = o + (0.f * d) / dot(d, c.direction);
+    const float dd = dot_rn(d, c.direction);
+    o = add3_rn(o, v3(div_rn(mul_rn(0.f, d.x), dd), div_rn(mul_rn(0.f, d.y), dd), div_rn(mul_rn(0.f, d.z), dd)));
 }
 
 // ---- pixel-filter tables (Raytracer.cpp:1354-1374) and the border ratio (1604-1609) -----------------

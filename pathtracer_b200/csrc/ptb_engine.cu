@@ -50,6 +50,10 @@ using namespace ptb;
 #define PTB_N_TOTALS 6
 #define PTB_BRANCH_MAX_LEVELS 512
 #define PTB_MAX_PIPES 4
+#ifndef PTB_TRACE_MINB
+#define PTB_TRACE_MINB 9    /* resident k_trace blocks per SM the register allocation must allow: 9 x 128 threads x 56 registers (the out-of-line
+                               tri_exact call would otherwise push the kernel to 64 registers / 8 blocks) */
+#endif
 #ifndef PTB_SMEM_STACK
 #define PTB_SMEM_STACK 0   /* entries of k_trace's traversal stack held in shared memory (A/B: profiles/r02a_ab_smem_stack.txt) */
 #endif
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev sc, FrameDev f, PoolDev
 // ANY_HIT = shadow rays (queue = shadow entries, first accepted triangle ends the ray; an unoccluded ray adds its deferred
 // direct term to the path's radiance).  Closest-hit results overwrite the analytic hit record the ray's producer wrote.
 template <bool ANY_HIT, bool COUNT, bool BRANCH = false>
-__global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
+__global__ void __launch_bounds__(128, PTB_TRACE_MINB) k_trace(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below, int tri_den, int tri_min_pct) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, PoolDev p, const uin
                     c.x = l2.x; c.y = l2.y; c.z = l2.z; c.w = l2.w;
                     if (COUNT) ct++;
                     float t, b1, b2;
-                    if (tri_test(a, b, c, r, tbest, t, b1, b2)) {
+                    if (tri_test(a, b, c, r, tbest, t, b1, b2, &ac, (int)prim)) {
                         if (!((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(&ac, (int)prim, b1, b2)) && !(ANY_HIT && (f2u(a.w) & PTB_TRI_FLAG_GHOST))) {
                             tbest = t; hb1 = b1; hb2 = b2; hprim = (int32_t)prim;
                             if (ANY_HIT) { live = false; tgroup.y = 0; if (BRANCH) shadow_settle_branch(p, (int)entry, item, true); }   // occluded: nothing to deliver
@@ -670,6 +674,7 @@ static int commit_upload(ptb_ctx* c, FlatScene& f, const HostScene& host) {
     const Node8* dn; const F4* dt; const uint8_t* de;
     if ((rc = upload(c, f.nodes.data(), f.nodes.size(), &dn))) return rc;
     if ((rc = upload(c, f.tris.data(), f.tris.size(), &dt))) return rc;
+    if (!f.tris_obj.empty() && (rc = upload(c, f.tris_obj.data(), f.tris_obj.size(), &sc.tris_obj))) return rc;
     if ((rc = upload(c, f.tri_uv.data(), f.tri_uv.size(), &sc.tri_uv))) return rc;
     if ((rc = upload(c, f.tri_shade.data(), f.tri_shade.size(), &sc.tri_shade))) return rc;
     if ((rc = upload(c, f.objects.data(), f.objects.size(), &sc.objects))) return rc;
@@ -683,7 +688,7 @@ static int commit_upload(ptb_ctx* c, FlatScene& f, const HostScene& host) {
     CK(cudaStreamSynchronize(c->stream));
     c->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     c->bytes_nodes = (int64_t)f.nodes.size() * sizeof(Node8);
-    c->bytes_tris = (int64_t)f.tris.size() * sizeof(F4);
+    c->bytes_tris = (int64_t)(f.tris.size() + f.tris_obj.size()) * sizeof(F4);
     c->bytes_attr = (int64_t)f.tri_uv.size() * sizeof(TriUV) + (int64_t)f.tri_shade.size() * sizeof(TriShade);
     c->bytes_tex = (int64_t)f.texels.size() * 4 + (int64_t)f.envmap.size() + (int64_t)f.merl.size() * 4;
     c->committed = true;
@@ -691,7 +696,7 @@ static int commit_upload(ptb_ctx* c, FlatScene& f, const HostScene& host) {
 }
 static void commit_release_host(ptb_ctx* c) {   // the host copies of the big arrays are no longer needed
     FlatScene& f = c->flat;
-    std::vector<F4>().swap(f.tris); std::vector<TriUV>().swap(f.tri_uv); std::vector<TriShade>().swap(f.tri_shade);
+    std::vector<F4>().swap(f.tris); std::vector<F4>().swap(f.tris_obj); std::vector<TriUV>().swap(f.tri_uv); std::vector<TriShade>().swap(f.tri_shade);
     std::vector<float>().swap(f.texels); std::vector<float>().swap(f.merl);
 }
 

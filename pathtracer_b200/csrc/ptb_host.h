@@ -52,6 +52,7 @@ inline ptb_xform placement_at(const HostObject& o, float frame) {
 struct FlatScene {
     std::vector<Node8> nodes;
     std::vector<F4> tris;                  // 3 per triangle, leaf order
+    std::vector<F4> tris_obj;              // 3 per triangle, leaf order: object-space corners, .w of the first = object id
     std::vector<TriUV> tri_uv;
     std::vector<TriShade> tri_shade;
     std::vector<ObjectDev> objects;

@@ -64,6 +64,8 @@ struct FogDev {                 // Scene::fog_* (Geometry.h:1371-1377) + the gro
 struct SceneDev {
     const F4* nodes;            // 5 x F4 per Node8
     const F4* tris;             // 3 x F4 per triangle, leaf order
+    const F4* tris_obj;         // the same triangles as the reference holds them: OBJECT-space corners A, B, C (A.w = object id); read by
+                                // tri_exact for rays near an edge and by the key-frame refit (null: the fast test decides everything)
     const TriUV* tri_uv;
     const TriShade* tri_shade;
     const ObjectDev* objects;
@@ -88,7 +90,48 @@ struct AlphaCtx {
     const ObjectDev* objects;
     const MaterialDev* materials;
     const float* texels;
+    const F4* tris_obj;         // object-space corners, see SceneDev
 };
+
+PTB_HD bool tri_exact_available(const AlphaCtx* c) { return c != nullptr && c->tris_obj != nullptr; }
+
+// Scene::intersection's ray transform (Geometry.cpp:603-605, Geometry.h:383-397) + the Triangle constructor and
+// Triangle::intersection (TriangleMesh.h:70-104) + the `localt < t` of the traversal (TriangleMesh.cpp:1197), one rounding per operation.
+PTB_HD_NOINLINE bool tri_exact(const AlphaCtx* c, int prim, V3 o, V3 d, float tbest, float& t, float& b1, float& b2) {
+#if defined(__CUDA_ARCH__)
+    const float4 qa = __ldg(reinterpret_cast<const float4*>(c->tris_obj) + 3 * (size_t)prim), qb = __ldg(reinterpret_cast<const float4*>(c->tris_obj) + 3 * (size_t)prim + 1),
+                 qc = __ldg(reinterpret_cast<const float4*>(c->tris_obj) + 3 * (size_t)prim + 2);
+    const int obj = __float_as_int(qa.w);
+#else
+    const F4 qa = c->tris_obj[3 * (size_t)prim], qb = c->tris_obj[3 * (size_t)prim + 1], qc = c->tris_obj[3 * (size_t)prim + 2];
+    const int obj = (int)f2u(qa.w);
+#endif
+    const float* m = c->objects[obj].inv_trans;
+    const V3 dl = v3(add_rn(add_rn(mul_rn(m[0], d.x), mul_rn(m[1], d.y)), mul_rn(m[2], d.z)), add_rn(add_rn(mul_rn(m[4], d.x), mul_rn(m[5], d.y)), mul_rn(m[6], d.z)),
+                     add_rn(add_rn(mul_rn(m[8], d.x), mul_rn(m[9], d.y)), mul_rn(m[10], d.z)));
+    const V3 ol = v3(add_rn(add_rn(add_rn(mul_rn(m[0], o.x), mul_rn(m[1], o.y)), mul_rn(m[2], o.z)), m[3]),
+                     add_rn(add_rn(add_rn(mul_rn(m[4], o.x), mul_rn(m[5], o.y)), mul_rn(m[6], o.z)), m[7]),
+                     add_rn(add_rn(add_rn(mul_rn(m[8], o.x), mul_rn(m[9], o.y)), mul_rn(m[10], o.z)), m[11]));
+    const V3 A = v3(qa.x, qa.y, qa.z);
+    const V3 u = sub3_rn(v3(qb.x, qb.y, qb.z), A), v = sub3_rn(v3(qc.x, qc.y, qc.z), A);
+    const V3 N = cross_rn(u, v);
+    const float m11 = dot_rn(u, u), m22 = dot_rn(v, v), m12 = dot_rn(u, v);
+    const float invdetm = (float)(1. / (double)sub_rn(mul_rn(m11, m22), mul_rn(m12, m12)));
+    const float tt = div_rn(dot_rn(sub3_rn(A, ol), N), dot_rn(dl, N));
+    if (tt < 0 || tt != tt) return false;
+    const V3 w = sub3_rn(add3_rn(ol, scale_rn(tt, dl)), A);
+    const float b11 = dot_rn(w, u), b21 = dot_rn(w, v);
+    const float beta = mul_rn(sub_rn(mul_rn(b11, m22), mul_rn(b21, m12)), invdetm);
+    if (beta < 0) return false;
+    const float gamma = mul_rn(sub_rn(mul_rn(b21, m11), mul_rn(b11, m12)), invdetm);
+    if (gamma < 0) return false;
+    const float alpha = sub_rn(sub_rn(1.f, beta), gamma);
+    if (alpha < 0) return false;
+    if (!(tt < tbest)) return false;
+    if (beta != beta || gamma != gamma) return false;   // (sliver: the reference accepts NaN barycentrics and patches them up later, App. D#17)
+    t = tt; b1 = beta; b2 = gamma;
+    return true;
+}
 
 // TriangleMesh.cpp:1198-1205: reject the hit when the group's alpha map reads < 0.5 at the hit's uv
 PTB_HD bool alpha_rejects(const AlphaCtx* c, int prim, float b1, float b2) {
@@ -105,9 +148,10 @@ PTB_HD bool alpha_rejects(const AlphaCtx* c, int prim, float b1, float b2) {
     if (tu.group >= ob.n_groups) return false;
     const MaterialDev& m = c->materials[ob.mat_base + tu.group];
     if (!(m.present & SLOT_ALPHA)) return false;
-    const float alpha = 1.f - b1 - b2;
-    float u = tu.u0 * alpha + tu.u1 * b1 + tu.u2 * b2;
-    float v = tu.v0 * alpha + tu.v1 * b1 + tu.v2 * b2;
+    // rounded operation by operation (TriangleMesh.cpp:1200-1201): which texel (int)(u * (W - 1)) names must not depend on an FMA
+    const float alpha = sub_rn(sub_rn(1.f, b1), b2);
+    float u = add_rn(add_rn(mul_rn(tu.u0, alpha), mul_rn(tu.u1, b1)), mul_rn(tu.u2, b2));
+    float v = add_rn(add_rn(mul_rn(tu.v0, alpha), mul_rn(tu.v1, b1)), mul_rn(tu.v2, b2));
     u = tex_wrap(u); v = tex_wrap(v);
     return tex_red(m.alpha, c->texels, u, v) < 0.5f;
 }
@@ -204,7 +248,7 @@ PTB_HD bool analytic_occluded(const SceneDev& sc, V3 o, V3 d, float dist_light) 
     return false;
 }
 PTB_HD AlphaCtx alpha_ctx(const SceneDev& sc) {
-    AlphaCtx ac; ac.tri_uv = sc.tri_uv; ac.objects = sc.objects; ac.materials = sc.materials; ac.texels = sc.texels;
+    AlphaCtx ac; ac.tri_uv = sc.tri_uv; ac.objects = sc.objects; ac.materials = sc.materials; ac.texels = sc.texels; ac.tris_obj = sc.tris_obj;
     return ac;
 }
 

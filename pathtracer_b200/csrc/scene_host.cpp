@@ -349,7 +349,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
         std::vector<uint32_t> order;
         build_bvh8(verts9.data(), n_tri, out.nodes, order, out.bvh);
         out.ms_bvh = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        out.tris.resize(3 * (size_t)n_tri); out.tri_uv.resize(n_tri); out.tri_shade.resize(n_tri);
+        out.tris.resize(3 * (size_t)n_tri); out.tris_obj.resize(3 * (size_t)n_tri); out.tri_uv.resize(n_tri); out.tri_shade.resize(n_tri);
 #pragma omp parallel for schedule(static)
         for (int64_t k = 0; k < n_tri; k++) {
             const uint32_t in = order[k];
@@ -367,6 +367,11 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
             q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = u2f(flags); out.tris[3 * (size_t)k] = q;
             q.x = v[3] - v[0]; q.y = v[4] - v[1]; q.z = v[5] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 1] = q;
             q.x = v[6] - v[0]; q.y = v[7] - v[1]; q.z = v[8] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 2] = q;
+            for (int c = 0; c < 3; c++) {      // what Triangle(vertices[vtxi], vertices[vtxj], vertices[vtxk]) is built from (TriangleMesh.cpp:812-815)
+                const V3 pv = V(o.vertices, t[c]);
+                q.x = pv.x; q.y = pv.y; q.z = pv.z; q.w = c == 0 ? u2f((uint32_t)src[in].obj) : 0.f;
+                out.tris_obj[3 * (size_t)k + c] = q;
+            }
             TriUV tu;
             memset(&tu, 0, sizeof(tu));
             auto uvc = [&](int idx, float& u, float& vv) {

@@ -64,7 +64,7 @@ int ptb_commit(ptb_ctx* c) {
     int rc = c->host.flatten(c->flat, c->err);
     if (rc) return rc;
     FlatScene& f = c->flat; SceneDev& sc = c->sc;
-    sc.nodes = reinterpret_cast<const F4*>(f.nodes.data()); sc.tris = f.tris.data(); sc.tri_uv = f.tri_uv.data(); sc.tri_shade = f.tri_shade.data();
+    sc.nodes = reinterpret_cast<const F4*>(f.nodes.data()); sc.tris = f.tris.data(); sc.tris_obj = f.tris_obj.empty() ? nullptr : f.tris_obj.data(); sc.tri_uv = f.tri_uv.data(); sc.tri_shade = f.tri_shade.data();
     sc.objects = f.objects.data(); sc.materials = f.materials.data(); sc.texels = f.texels.data(); sc.envmap = f.envmap.data(); sc.merl = f.merl.data();
     scene_header(sc, f);
     if ((rc = scene_modes(sc, c->host, c->err))) return rc;
