@@ -152,6 +152,11 @@ const char* ptb_version(void);
 int ptb_add_sphere(ptb_ctx*, const float O[3], float R, const ptb_xform*, int flags, int* out_id);
 /* replaces: `new Plane(A,N)` + addObject (Geometry.h:1130-1140). */
 int ptb_add_plane(ptb_ctx*, const float A[3], const float N[3], const ptb_xform*, int flags, int* out_id);
+/* replaces: `new Cylinder(A, B, R)` + addObject (Geometry.h:731-846): the open tube of radius R around the segment A-B (no caps; a
+ * ray that meets the infinite cylinder outside the segment first is a miss even if its second root lies inside, like the
+ * reference's test).  Material slot 0 is looked up at (u, v) = (position along the axis / length, 0.5).  The reference builds
+ * these for its yarn curves (TriangleMesh.h:281); its default rotation centre is the origin. */
+int ptb_add_cylinder(ptb_ctx*, const float A[3], const float B[3], float R, const ptb_xform*, int flags, int* out_id);
 /* replaces: `new TriMesh(scene, file, scaling, offset, mirror, NULL, false, center)` + addObject
  * (TriangleMesh.cpp:714-841), with the reader's arrays passed in memory. */
 int ptb_add_mesh(ptb_ctx*, const ptb_mesh*, const ptb_xform*, int flags, int* out_id);
@@ -199,7 +204,12 @@ int ptb_set_background(ptb_ctx*, const float* rgb, int W, int H);
  * nb_transforms rows each in a .scn) and Scene::current_frame (mainApp.cpp:790).  At ptb_commit every object with keys is placed
  * by Object::get_scale / get_translation / get_rotation at the current frame (Geometry.h:258-312: clamped outside the keyed
  * range, linear inside, quaternion Slerp between rotation keys, Vector.h:222-269) exactly like Scene::prepare_render ->
- * Object::build_matrix(current_frame) (Geometry.cpp:283).  An animation is: set_frame, commit, render, per frame.
+ * Object::build_matrix(current_frame) (Geometry.cpp:283).
+ * An animation is: commit once, then per frame ptb_set_frame + ptb_render.  ptb_set_frame on a committed scene does NOT rebuild: the
+ * next render (or picking query) first re-poses the scene on the device: object matrices and light constants are recomputed, the
+ * world-space triangles are re-derived from the object-space corners resident on the device and the BVH8 boxes are refitted
+ * bottom-up with the builder's conservative quantisation (well under a millisecond per million triangles; ptb_scene_info.ms_refit).
+ * The tree keeps the topology of the commit frame, which rigid motion preserves; ptb_commit again rebuilds it for the current frame.
  * values: n x 1 (scale), n x 3 (translation), n x 9 (rotation, row-major Matrix33); n == 0 clears the track. */
 #define PTB_KEY_SCALE        0
 #define PTB_KEY_TRANSLATION  1
@@ -346,6 +356,7 @@ typedef struct ptb_scene_info {
     int64_t n_triangles, n_bvh_nodes, bytes_nodes, bytes_triangles, bytes_attributes, bytes_textures;
     int32_t n_objects, bvh_depth;
     double  ms_bvh_build, ms_upload;
+    double  ms_refit;        /* device time of the last key-frame re-pose (ptb_set_frame after ptb_commit), 0 if none */
 } ptb_scene_info;
 int ptb_get_scene_info(const ptb_ctx*, ptb_scene_info*);
 

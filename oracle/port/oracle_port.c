@@ -212,7 +212,7 @@ typedef struct { vec lo, hi; } box;
 typedef struct { int isleaf, fg, fd; box bb; } bnode;                       /* BVHNodesT, TriangleMesh.h:6-13 */
 typedef struct { int vtx[3], uv[3], n[3], group; } tindex;                  /* TriangleIndices, TriangleMesh.h:53-65 */
 typedef struct { vec A, u, v, N; float m11, m12, m22, invdetm; float uvs[3][2]; vec normals[3]; } tsoup; /* Triangle, 67-111 */
-enum { T_MESH, T_SPHERE, T_PLANE };
+enum { T_MESH, T_SPHERE, T_PLANE, T_CYLINDER };
 typedef struct {
     int type, miroir, flip_normals, interp_normals, brdf, ghost;
     const double* merl;
@@ -222,7 +222,8 @@ typedef struct {
     float trans[12], inv[12], rotm[9];
     slotv slots[S_COUNT];
     vec O; float R, R2; int has_envmap; const uint8_t* envtex; int envW, envH;   /* Sphere */
-    vec A, vecN;                                                              /* Plane */
+    vec A, vecN;                                                              /* Plane (Cylinder: A) */
+    vec cylB, cyld; float cyllen;                                             /* Cylinder: B, d, len (Geometry.h:734-738, 843-844) */
     int nv, nn, nuv, nt;                                                      /* TriMesh */
     vec *vertices, *normals; float* uvs; tindex* indices; tsoup* soup; vec* tangent_soup; int* permuted;
     bnode* nodes; int n_nodes, cap_nodes; box bvh_bbox; int bvh_depth;
@@ -708,6 +709,31 @@ static int plane_hit(const object* pl, vec o, vec d, vec* P, float* t, matvals* 
     return 1;
 }
 
+/* Cylinder::intersection (Geometry.h:740-766); intersection_shadow is the same call (836-841) */
+static int cylinder_hit(const object* cy, vec o, vec d, vec* P, float* t, matvals* mat) {
+    vec X = vsub(d, vscale(vdot(d, cy->cyld), cy->cyld));
+    vec oa = vsub(o, cy->A);
+    vec Y = vsub(oa, vscale(vdot(oa, cy->cyld), cy->cyld));
+    float a = vnorm2(X);
+    float b = 2 * vdot(X, Y);
+    float c = vnorm2(Y) - cy->R * cy->R;
+    float delta = b * b - 4 * a * c;
+    if (delta < 0) return 0;
+    float sdelta = sqrtf(delta);
+    float t2 = (-b + sdelta) / (2 * a);
+    if (t2 < 0) return 0;
+    float t1 = (-b - sdelta) / (2 * a);
+    if (t1 > 0) *t = t1; else *t = t2;
+    *P = vadd(o, vscale(*t, d));
+    float dP = vdot(vsub(*P, cy->A), cy->cyld);
+    if (dP < 0 || dP > cy->cyllen) return 0;
+    vec proj = vadd(cy->A, vscale(dP, cy->cyld));
+    query_material(cy, 0, dP / cy->cyllen, 0.5f, mat);
+    mat->shadingN = vsub(*P, proj);
+    if (cy->flip_normals) mat->shadingN = vneg(mat->shadingN);
+    return 1;
+}
+
 /* Scene::intersection (Geometry.cpp:589-688) */
 static int scene_hit(const struct ptb_ctx* c, vec o, vec d, vec* P, int* id, float* min_t, matvals* mat, int* tri_id, unsigned long long* counter) {
     int has = 0;
@@ -720,6 +746,7 @@ static int scene_hit(const struct ptb_ctx* c, vec o, vec d, vec* P, int* id, flo
         int h;
         if (ob->type == T_MESH) h = mesh_hit(ob, ol, dl, &lp, &t, &lm, *min_t, tri_id, 0, 0);
         else if (ob->type == T_SPHERE) { h = sphere_hit(ob, ol, dl, &lp, &t, &lm, 0); if (h) *tri_id = -1; }
+        else if (ob->type == T_CYLINDER) { h = cylinder_hit(ob, ol, dl, &lp, &t, &lm); if (h) *tri_id = -1; }
         else { h = plane_hit(ob, ol, dl, &lp, &t, &lm, 0); if (h) *tri_id = -1; }
         if (h && t < *min_t) { has = 1; *min_t = t; *P = lp; *id = i; *mat = lm; }
     }
@@ -738,6 +765,7 @@ static int scene_shadow(const struct ptb_ctx* c, vec o, vec d, float dist_light,
         float t; int h, tid; vec P; matvals m;
         if (ob->type == T_MESH) h = mesh_hit(ob, ol, dl, &P, &t, &m, min_t, &tid, 1, dist_light);
         else if (ob->type == T_SPHERE) h = sphere_hit(ob, ol, dl, &P, &t, &m, 1);
+        else if (ob->type == T_CYLINDER) { m = matvals_default(); h = cylinder_hit(ob, ol, dl, &P, &t, &m); }
         else h = plane_hit(ob, ol, dl, &P, &t, &m, 1);
         if (h && t < dist_light * 0.999) return 1;
     }
@@ -1143,6 +1171,15 @@ int ptb_add_sphere(ptb_ctx* c, const float O[3], float R, const ptb_xform* xf, i
     if (!c || !O) return PTB_ERR_INVALID;
     object* o = new_object(c, T_SPHERE, xf, flags, V(O[0], O[1], O[2]));
     o->O = V(O[0], O[1], O[2]); o->R = R; o->R2 = R * R;
+    if (out_id) *out_id = c->n_objs - 1;
+    return PTB_OK;
+}
+int ptb_add_cylinder(ptb_ctx* c, const float A[3], const float B[3], float R, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !A || !B) return PTB_ERR_INVALID;
+    object* o = new_object(c, T_CYLINDER, xf, flags, V(0, 0, 0));
+    o->A = V(A[0], A[1], A[2]); o->cylB = V(B[0], B[1], B[2]); o->R = R;
+    o->cyld = vnormalize(vsub(o->cylB, o->A));
+    o->cyllen = sqrtf(vnorm2(vsub(o->cylB, o->A)));
     if (out_id) *out_id = c->n_objs - 1;
     return PTB_OK;
 }

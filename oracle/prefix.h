@@ -15,6 +15,7 @@
 #define ptb_version            ORC_NAME(version)
 #define ptb_add_sphere         ORC_NAME(add_sphere)
 #define ptb_add_plane          ORC_NAME(add_plane)
+#define ptb_add_cylinder       ORC_NAME(add_cylinder)
 #define ptb_add_mesh           ORC_NAME(add_mesh)
 #define ptb_set_group_material ORC_NAME(set_group_material)
 #define ptb_set_brdf           ORC_NAME(set_brdf)

@@ -128,6 +128,16 @@ int ptb_add_plane(ptb_ctx* c, const float A[3], const float N[3], const ptb_xfor
     return PTB_OK;
 }
 
+int ptb_add_cylinder(ptb_ctx* c, const float A[3], const float B[3], float R, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !A || !B) return PTB_ERR_INVALID;
+    Cylinder* cy = new Cylinder(Vector(A[0], A[1], A[2]), Vector(B[0], B[1], B[2]), R);
+    apply_flags(cy, flags);
+    apply_xform(cy, xf, false);
+    c->rt->s.addObject(cy);
+    if (out_id) *out_id = (int)c->rt->s.objects.size() - 1;
+    return PTB_OK;
+}
+
 int ptb_add_mesh(ptb_ctx* c, const ptb_mesh* m, const ptb_xform* xf, int flags, int* out_id) {
     if (!c || !m || !m->vertices || !m->tri || m->n_tri <= 0) return PTB_ERR_INVALID;
     auto t0 = std::chrono::steady_clock::now();

@@ -79,7 +79,7 @@ class SceneInfo(C.Structure):
     _fields_ = [("n_triangles", C.c_int64), ("n_bvh_nodes", C.c_int64), ("bytes_nodes", C.c_int64),
                 ("bytes_triangles", C.c_int64), ("bytes_attributes", C.c_int64), ("bytes_textures", C.c_int64),
                 ("n_objects", C.c_int32), ("bvh_depth", C.c_int32), ("ms_bvh_build", C.c_double),
-                ("ms_upload", C.c_double)]
+                ("ms_upload", C.c_double), ("ms_refit", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -94,7 +94,7 @@ class KernelTimes(C.Structure):
 
 
 # every symbol include/ptb200.h declares (tests check the product library exports all of them)
-SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_mesh",
+SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_cylinder", "add_mesh",
            "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "set_fog", "set_background", "set_keyframes", "set_frame", "commit", "render",
            "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
            "set_option", "get_scene_info", "kat", "get_kernel_times", "render_denoiser_inputs", "progressive_begin", "progressive_pass",
@@ -194,6 +194,7 @@ class Lib:
             "version": (C.c_char_p, []),
             "add_sphere": (C.c_int, [vp, _fp, C.c_float, C.POINTER(Xform), C.c_int, ip]),
             "add_plane": (C.c_int, [vp, _fp, _fp, C.POINTER(Xform), C.c_int, ip]),
+            "add_cylinder": (C.c_int, [vp, _fp, _fp, C.c_float, C.POINTER(Xform), C.c_int, ip]),
             "add_mesh": (C.c_int, [vp, C.POINTER(Mesh), C.POINTER(Xform), C.c_int, ip]),
             "set_group_material": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(Material)]),
             "set_brdf": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),

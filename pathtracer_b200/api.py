@@ -207,6 +207,15 @@ class Plane(Object):
         self.miroir = mirror
 
 
+class Cylinder(Object):
+    """Geometry.h:731-846: the open tube of radius R around the segment A-B (the reference's yarn segments, TriangleMesh.h:281)."""
+
+    def __init__(self, A, B, R, mirror=False):
+        super().__init__()
+        self.A, self.B, self.R = np.array(A, np.float32), np.array(B, np.float32), float(R)
+        self.miroir = mirror
+
+
 class TriMesh(Object):
     """In-memory equivalent of `new TriMesh(scene, file, scaling, offset, mirror, NULL, false, center)`
     (TriangleMesh.cpp:714-841): arrays as a file reader would have produced them."""
@@ -457,6 +466,8 @@ class Raytracer:
                 L.check(L.add_sphere(ctx, fptr(f32(o.O)), o.R, C.byref(xf), o._flags(), C.byref(oid)), ctx)
             elif isinstance(o, Plane):
                 L.check(L.add_plane(ctx, fptr(f32(o.A)), fptr(f32(o.vecN)), C.byref(xf), o._flags(), C.byref(oid)), ctx)
+            elif isinstance(o, Cylinder):
+                L.check(L.add_cylinder(ctx, fptr(f32(o.A)), fptr(f32(o.B)), o.R, C.byref(xf), o._flags(), C.byref(oid)), ctx)
             elif isinstance(o, TriMesh):
                 m = _abi.Mesh()
                 m.vertices, m.n_vertices = fptr(o.vertices), len(o.vertices)
@@ -526,6 +537,14 @@ class Raytracer:
         buf = C.create_string_buffer(_abi.COMM_ID_BYTES)
         self.lib.check(self.lib.comm_unique_id(buf), None)
         return buf.raw
+
+    def set_frame(self, frame):
+        """Scene::current_frame for the next render (mainApp.cpp:790, 874-877).  On a committed scene nothing is rebuilt: the library
+        re-poses the key-framed objects on the device before the next render (ptb_set_frame: matrices, triangles, BVH8 refit)."""
+        self.s.current_frame = frame
+        if self._ctx is not None:
+            self.lib.check(self.lib.set_frame(self._ctx, float(int(frame))), self._ctx)
+        return self
 
     def params(self, shard_rank=0, shard_count=1, tile_size=0):
         p = _abi.Params()

@@ -227,6 +227,7 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
     size_t head = 0;
     while (head < queue.size()) {
         const Work w = queue[head++];
+        if (w.depth > stats.depth) stats.level_start.push_back(w.wide);     // breadth-first emission: the first node of a new level
         stats.depth = std::max(stats.depth, w.depth);
         int32_t ch[8]; bool ch_leaf[8]; int nc = 0;
         const BNode& root = B.nodes[w.bnode];
@@ -343,6 +344,7 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
         out_nodes[w.wide] = nd;
     }
     stats.n_nodes = (int64_t)out_nodes.size();
+    stats.level_start.push_back((uint32_t)out_nodes.size());
     stats.n_binary_nodes = B.n_nodes.load();
 }
 

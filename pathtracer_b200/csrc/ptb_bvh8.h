@@ -16,8 +16,9 @@
 //         27-31  reserved (0)
 //         32-79  qlo_x[8] qlo_y[8] qlo_z[8] qhi_x[8] qhi_y[8] qhi_z[8]
 //
-// Triangles are stored in leaf order as 3 x float4 = 48 bytes {v0, e1 = v1-v0, e2 = v2-v0}; the .w
-// lanes carry flags.  Semantics mirrored from the reference: two-sided, barycentrics >= 0 inclusive,
+// Triangles are stored in leaf order as 3 x float4 = 48 bytes {v0, e1 = v1-v0, e2 = v2-v0}; v0.w carries
+// the flags, e1.w the barycentric distance from an edge below which the reference's own arithmetic
+// decides the hit (PTB_EDGE_EPS, or +inf for alpha-tested triangles; tri_exact).  Semantics mirrored from the reference: two-sided, barycentrics >= 0 inclusive,
 // t >= 0 accepted, strictly nearer than the current best wins (TriangleMesh.h:82-104,
 // TriangleMesh.cpp:1196-1209); alpha-mapped hits are rejected inside traversal (1198-1205).
 #pragma once
@@ -96,7 +97,12 @@ PTB_HD bool alpha_rejects(const AlphaCtx* ctx, int prim, float b1, float b2);
 // Triangle::intersection (TriangleMesh.h:82-104) in the reference's own arithmetic: object-space ray, plane + Gram barycentrics, every
 // operation rounded separately (ptb_scene.h).  Decides the hits the fast test below cannot call: rays within PTB_EDGE_EPS of an edge.
 PTB_HD bool tri_exact_available(const AlphaCtx* ctx);
-PTB_HD_NOINLINE bool tri_exact(const AlphaCtx* ctx, int prim, V3 o, V3 d, float tbest, float& t, float& b1, float& b2);   // out of line: the hot loop keeps its registers
+#if defined(PTB_EXACT_INLINE)
+#define PTB_EXACT_LINKAGE PTB_HD
+#else
+#define PTB_EXACT_LINKAGE PTB_HD_NOINLINE     /* out of line: the hot loop keeps its registers */
+#endif
+PTB_EXACT_LINKAGE bool tri_exact(const AlphaCtx* ctx, int prim, V3 o, V3 d, float tbest, float& t, float& b1, float& b2);
 
 // Tests the 8 children of `n` against the ray; returns the hit mask in SLOT order: bit 24 + s = the internal child in slot s,
 // bits 3s..3s+2 = the triangles of the leaf in slot s (only bits that exist: valid24 / imask).
@@ -225,13 +231,49 @@ PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, fl
     // written so that NaN (degenerate triangle, det == 0) fails every test
     const float m = fminf(fminf(u, v), 1.f - u - v);
 #if PTB_EDGE_EPS_ON
-    if (!(m >= -PTB_EDGE_EPS)) return false;                 // clearly outside
-    // near an edge, or an alpha-mapped triangle (the texel its uv lands on must be the reference's): the reference's arithmetic decides
-    if ((m < PTB_EDGE_EPS || (f2u(a.w) & PTB_TRI_FLAG_ALPHA)) && tri_exact_available(ex)) return tri_exact(ex, prim, r.o, r.d, tbest, t, b1, b2);
-#endif
+    // inside the triangle grown by PTB_EDGE_EPS, in front of the origin and not clearly beyond the best hit ...
+    if (!(m >= -PTB_EDGE_EPS) || !(tt >= 0.f) || !(tt * (1.f - 1e-4f) < tbest)) return false;
+    // ... and near an edge, or alpha-tested (b.w = PTB_EDGE_EPS, or +inf when the texel the uv lands on must be the reference's):
+    // the reference's arithmetic decides
+    if (m < b.w && tri_exact_available(ex)) return tri_exact(ex, prim, r.o, r.d, tbest, t, b1, b2);
+    if (!(m >= 0.f) || !(tt < tbest)) return false;
+#else
     if (!(m >= 0.f) || !(tt >= 0.f) || !(tt < tbest)) return false;
+#endif
     t = tt; b1 = u; b2 = v;
     return true;
+}
+
+// The same test for the persistent traversal kernel (k_trace), which must not carry tri_exact's registers through its hot loop:
+// returns 0 miss, 1 hit (t, b1, b2 set), 2 "the reference's arithmetic has to decide" (a ray within PTB_EDGE_EPS of an edge, or an
+// alpha-mapped triangle, whose texel must be the reference's).  k_trace pushes case 2 on the traversal stack as a deferred
+// candidate and runs tri_exact when it pops it (a few node visits later: t_best is simply not shrunk in the meantime).
+PTB_HD int tri_test_classify(const F4& a, const F4& b, const F4& c, const RayPrep& r, float tbest, float& t, float& b1, float& b2) {
+    const V3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
+    const V3 pvec = cross(r.d, e2);
+    const float det = dot(e1, pvec);
+#if defined(__CUDA_ARCH__) && !defined(PTB_TRI_RCP_EXACT)
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(det));
+#else
+    const float inv = 1.f / det;
+#endif
+    const V3 tvec = r.o - v0;
+    const float u = dot(tvec, pvec) * inv;
+    const V3 qvec = cross(tvec, e1);
+    const float v = dot(r.d, qvec) * inv;
+    const float tt = dot(e2, qvec) * inv;
+    const float m = fminf(fminf(u, v), 1.f - u - v);
+#if PTB_EDGE_EPS_ON
+    // same instruction count as the plain accept test for the common outcome (a miss): one min3 and three compares
+    if (!(m >= -PTB_EDGE_EPS) || !(tt >= 0.f) || !(tt * (1.f - 1e-4f) < tbest)) return 0;   // (t of the two formulations differs in the last bits)
+    if (m < b.w) return 2;            // b.w = PTB_EDGE_EPS, or +inf on alpha-tested triangles
+    if (!(tt < tbest)) return 0;
+#else
+    if (!(m >= 0.f) || !(tt >= 0.f) || !(tt < tbest)) return 0;
+#endif
+    t = tt; b1 = u; b2 = v;
+    return 1;
 }
 
 // The hit internal child (bits 24..31 of a node group, slot order) that the ray meets first: the slot s with the largest s ^ oinv.
@@ -247,7 +289,9 @@ PTB_HD uint32_t pick_slot(uint32_t hits8, uint32_t oct_inv4) {
 // Traversal stack entries per ray.  A node step pushes at most two entries (the node's other hit children and the triangle group it
 // postpones), so a BVH8 of `depth` wide levels needs at most 2 * depth; ptb_commit refuses deeper trees (PTB_ERR_UNSUPPORTED) instead
 // of dropping subtrees the way a full stack would (the reference's own 50-entry stack overflows silently, TriangleMesh.cpp:1158).
+#if !defined(PTB_STACK)
 #define PTB_STACK 64
+#endif
 
 struct TraverseCounters {
     uint32_t nodes, tris;

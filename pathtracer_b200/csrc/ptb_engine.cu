@@ -51,8 +51,8 @@ using namespace ptb;
 #define PTB_BRANCH_MAX_LEVELS 512
 #define PTB_MAX_PIPES 4
 #ifndef PTB_TRACE_MINB
-#define PTB_TRACE_MINB 9    /* resident k_trace blocks per SM the register allocation must allow: 9 x 128 threads x 56 registers (the out-of-line
-                               tri_exact call would otherwise push the kernel to 64 registers / 8 blocks) */
+#define PTB_TRACE_MINB 0    /* > 0: force the register allocation of k_trace to allow this many resident blocks per SM (A/B only: a forced 9
+                               costs 2 % by itself, profiles/r02e_ab_exact_variants.txt); the kernel compiles to 56 registers = 9 blocks unforced */
 #endif
 #ifndef PTB_SMEM_STACK
 #define PTB_SMEM_STACK 0   /* entries of k_trace's traversal stack held in shared memory (A/B: profiles/r02a_ab_smem_stack.txt) */
@@ -85,7 +85,12 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev sc, FrameDev f, PoolDev
 // ANY_HIT = shadow rays (queue = shadow entries, first accepted triangle ends the ray; an unoccluded ray adds its deferred
 // direct term to the path's radiance).  Closest-hit results overwrite the analytic hit record the ray's producer wrote.
 template <bool ANY_HIT, bool COUNT, bool BRANCH = false>
-__global__ void __launch_bounds__(128, PTB_TRACE_MINB) k_trace(SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
+#if PTB_TRACE_MINB > 0
+__global__ void __launch_bounds__(128, PTB_TRACE_MINB) k_trace(
+#else
+__global__ void __launch_bounds__(128) k_trace(
+#endif
+SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below, int tri_den, int tri_min_pct) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
@@ -171,7 +176,22 @@ __global__ void __launch_bounds__(128, PTB_TRACE_MINB) k_trace(SceneDev sc, Pool
             if (sp > 0) {
                 U2 e;
                 PTB_STK_POP(e);
-                if (e.y > 0x00ffffffu) ngroup = e; else { tgroup = e; tvalid = 0x00ffffffu; }
+                if (e.y > 0x00ffffffu) ngroup = e;
+                else if (e.y != 0) { tgroup = e; tvalid = 0x00ffffffu; }
+#if PTB_EDGE_EPS_ON
+                else {
+                    // a deferred candidate (tri_test_classify case 2): the reference's own arithmetic decides it, here, where the
+                    // lane holds neither node nor triangle temporaries.  e.x = triangle | flags << 28
+                    const uint32_t prim = e.x & 0x0fffffffu, fl = e.x >> 28;
+                    float t, b1, b2;
+                    if (tri_exact(&ac, (int)prim, r.o, r.d, tbest, t, b1, b2)) {
+                        if (!((fl & PTB_TRI_FLAG_ALPHA) && alpha_rejects(&ac, (int)prim, b1, b2)) && !(ANY_HIT && (fl & PTB_TRI_FLAG_GHOST))) {
+                            tbest = t; hb1 = b1; hb2 = b2; hprim = (int32_t)prim;
+                            if (ANY_HIT) { live = false; sp = 0; if (BRANCH) shadow_settle_branch(p, (int)entry, item, true); }
+                        }
+                    }
+                }
+#endif
             } else {
                 if (ANY_HIT && BRANCH) shadow_settle_branch(p, (int)entry, item, false);
                 else if (ANY_HIT) {   // unoccluded: deliver the deferred direct term (Raytracer.cpp:545-566)
@@ -242,8 +262,16 @@ __global__ void __launch_bounds__(128, PTB_TRACE_MINB) k_trace(SceneDev sc, Pool
                     c.x = l2.x; c.y = l2.y; c.z = l2.z; c.w = l2.w;
                     if (COUNT) ct++;
                     float t, b1, b2;
-                    if (tri_test(a, b, c, r, tbest, t, b1, b2, &ac, (int)prim)) {
+                    const int res = tri_test_classify(a, b, c, r, tbest, t, b1, b2);
+                    if (res == 2) {            // near an edge / alpha-tested: deferred to the pop branch (tri_exact)
+                        U2 e; e.x = prim | ((f2u(a.w) & 3u) << 28); e.y = 0;
+                        if (sp < PTB_STACK) PTB_STK_PUSH(e);
+                    } else if (res == 1) {
+#if PTB_EDGE_EPS_ON
+                        if (!(ANY_HIT && (f2u(a.w) & PTB_TRI_FLAG_GHOST))) {     // (alpha-tested triangles always take the deferred route)
+#else
                         if (!((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(&ac, (int)prim, b1, b2)) && !(ANY_HIT && (f2u(a.w) & PTB_TRI_FLAG_GHOST))) {
+#endif
                             tbest = t; hb1 = b1; hb2 = b2; hprim = (int32_t)prim;
                             if (ANY_HIT) { live = false; tgroup.y = 0; if (BRANCH) shadow_settle_branch(p, (int)entry, item, true); }   // occluded: nothing to deliver
                         }
@@ -371,6 +399,97 @@ __global__ void __launch_bounds__(128) k_splat(FrameDev f, PoolDev p, F4* accum)
     const int ps = blockIdx.x * blockDim.x + threadIdx.x;
     if (ps >= f.n_pixel_slots) return;
     splat_pixel(f, p, ps, accum, RedAddV4());
+}
+
+// ---- key-frame refit: a new frame of an animation without a rebuild -------------------------------------------------------------------
+// Object::build_matrix(current_frame) moves whole objects rigidly (scale, rotation, translation keys, Geometry.h:322-360).  The BVH8
+// keeps its topology; the world-space triangles are re-derived from the object-space corners that live on the device (tris_obj) with
+// the roundings of the host's xf_point, and the node boxes are recomputed bottom-up, one launch per level (nodes are stored breadth
+// first), with the builder's conservative quantisation (bvh8_build.cpp).  The reference re-poses by changing the matrices only (its BVH
+// is in object space); here the re-pose costs one pass over the triangles and the nodes: well under a millisecond per million triangles.
+__device__ __forceinline__ V3 xf_point_rn(const float* m, V3 v) {
+    return v3(add_rn(add_rn(add_rn(mul_rn(m[0], v.x), mul_rn(m[1], v.y)), mul_rn(m[2], v.z)), m[3]),
+              add_rn(add_rn(add_rn(mul_rn(m[4], v.x), mul_rn(m[5], v.y)), mul_rn(m[6], v.z)), m[7]),
+              add_rn(add_rn(add_rn(mul_rn(m[8], v.x), mul_rn(m[9], v.y)), mul_rn(m[10], v.z)), m[11]));
+}
+__global__ void __launch_bounds__(256) k_refit_tris(const F4* __restrict__ tris_obj, const ObjectDev* __restrict__ objects, F4* tris, size_t n_tri) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_tri) return;
+    const F4 A = tris_obj[3 * k], B = tris_obj[3 * k + 1], C = tris_obj[3 * k + 2];
+    const float* m = objects[f2u(A.w)].trans;
+    const V3 v0 = xf_point_rn(m, v3(A.x, A.y, A.z)), v1 = xf_point_rn(m, v3(B.x, B.y, B.z)), v2 = xf_point_rn(m, v3(C.x, C.y, C.z));
+    F4 q;
+    q.x = v0.x; q.y = v0.y; q.z = v0.z; q.w = tris[3 * k].w; tris[3 * k] = q;                       // .w: the triangle's flags stay
+    q.x = v1.x - v0.x; q.y = v1.y - v0.y; q.z = v1.z - v0.z; q.w = tris[3 * k + 1].w; tris[3 * k + 1] = q;   // .w: the edge threshold stays
+    q.x = v2.x - v0.x; q.y = v2.y - v0.y; q.z = v2.z - v0.z; q.w = 0; tris[3 * k + 2] = q;
+}
+__device__ __forceinline__ uint32_t refit_exponent_byte(float extent) {   // smallest e with extent * 1.0001 <= 255 * 2^e (bvh8_build.cpp exponent_byte)
+    int e = -100;
+    if (extent > 0.f) {
+        const float x = extent * (1.0001f / 255.f) * 1.000001f;       // the host evaluates this in double: stay on the safe side of its rounding
+        const uint32_t b = f2u(x);
+        const int k = (int)((b >> 23) & 0xffu) - 127;
+        e = (b & 0x7fffffu) ? k + 1 : k;
+        e = max(-100, min(100, e));
+    }
+    return (uint32_t)(e + 127);
+}
+__global__ void __launch_bounds__(128) k_refit_level(Node8* nodes, F4* node_box, const F4* __restrict__ tris_obj, const ObjectDev* __restrict__ objects,
+                                                     uint32_t first, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Node8 nd = nodes[first + i];
+    const uint32_t valid24 = (uint32_t)nd.valid24[0] | ((uint32_t)nd.valid24[1] << 8) | ((uint32_t)nd.valid24[2] << 16);
+    float lo[8][3], hi[8][3];
+    float nlo[3] = {INFINITY, INFINITY, INFINITY}, nhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    uint32_t used = 0;
+    for (int s = 0; s < 8; s++) {
+        for (int k = 0; k < 3; k++) { lo[s][k] = INFINITY; hi[s][k] = -INFINITY; }
+        if (nd.imask & (1u << s)) {
+            const uint32_t ci = nd.child_base + __popc((uint32_t)nd.imask & ((1u << s) - 1u));
+            const F4 a = node_box[2 * (size_t)ci], b = node_box[2 * (size_t)ci + 1];
+            lo[s][0] = a.x; lo[s][1] = a.y; lo[s][2] = a.z; hi[s][0] = b.x; hi[s][1] = b.y; hi[s][2] = b.z;
+            used |= 1u << s;
+        } else if ((valid24 >> (3 * s)) & 7u) {
+            const uint32_t cnt = __popc((valid24 >> (3 * s)) & 7u), t0 = nd.tri_base + __popc(valid24 & ((1u << (3 * s)) - 1u));
+            for (uint32_t t = t0; t < t0 + cnt; t++) {
+                const F4 A = tris_obj[3 * (size_t)t];
+                const float* m = objects[f2u(A.w)].trans;
+                for (int c = 0; c < 3; c++) {
+                    const F4 P = c == 0 ? A : tris_obj[3 * (size_t)t + c];
+                    const V3 w = xf_point_rn(m, v3(P.x, P.y, P.z));
+                    lo[s][0] = fminf(lo[s][0], w.x); lo[s][1] = fminf(lo[s][1], w.y); lo[s][2] = fminf(lo[s][2], w.z);
+                    hi[s][0] = fmaxf(hi[s][0], w.x); hi[s][1] = fmaxf(hi[s][1], w.y); hi[s][2] = fmaxf(hi[s][2], w.z);
+                }
+            }
+            used |= 1u << s;
+        }
+        if (used & (1u << s)) for (int k = 0; k < 3; k++) { nlo[k] = fminf(nlo[k], lo[s][k]); nhi[k] = fmaxf(nhi[k], hi[s][k]); }
+    }
+    F4 q;
+    q.x = nlo[0]; q.y = nlo[1]; q.z = nlo[2]; q.w = 0; node_box[2 * (size_t)(first + i)] = q;
+    q.x = nhi[0]; q.y = nhi[1]; q.z = nhi[2]; node_box[2 * (size_t)(first + i) + 1] = q;
+    const uint32_t eb[3] = {refit_exponent_byte(nhi[0] - nlo[0]), refit_exponent_byte(nhi[1] - nlo[1]), refit_exponent_byte(nhi[2] - nlo[2])};
+    nd.ex = (uint8_t)eb[0]; nd.ey = (uint8_t)eb[1]; nd.ez = (uint8_t)eb[2];
+    float cell[3], eps[3], p[3];
+    for (int k = 0; k < 3; k++) {
+        cell[k] = u2f(eb[k] << 23);                                                       // 2^(e - 127 + 127 - 127)... the byte IS the float's exponent field
+        eps[k] = cell[k] * 4e-3f + 4e-7f * fmaxf(fabsf(nlo[k]), fabsf(nhi[k]));          // the builder's conservative slack
+        p[k] = nlo[k] - eps[k];
+    }
+    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
+    uint8_t* ql[3] = {nd.qlox, nd.qloy, nd.qloz};
+    uint8_t* qh[3] = {nd.qhix, nd.qhiy, nd.qhiz};
+    for (int s = 0; s < 8; s++)
+        for (int k = 0; k < 3; k++) {
+            float a = 0.f, b = 0.f;
+            if (used & (1u << s)) {
+                a = fminf(fmaxf(floorf((lo[s][k] - eps[k] - p[k]) / cell[k]), 0.f), 255.f);
+                b = fminf(fmaxf(ceilf((hi[s][k] + eps[k] - p[k]) / cell[k]), 0.f), 255.f);
+            }
+            ql[k][s] = (uint8_t)a; qh[k][s] = (uint8_t)b;
+        }
+    nodes[first + i] = nd;
 }
 
 __global__ void k_totals(const uint32_t* counters, int nb, unsigned long long valid_paths, unsigned long long* totals) {
@@ -557,6 +676,10 @@ struct ptb_ctx {
     int64_t pack_n = 0;
     std::vector<std::pair<void*, int64_t>> pinned;   // host buffers page-locked through ptb_pin_host_buffer
     int64_t info_n_tri = -1, info_nodes = 0; int info_depth = 0;   // group followers: the leader's scene figures
+    bool frame_dirty = false;                  // ptb_set_frame after the commit: the next device query re-poses the scene first (refit)
+    F4* d_node_box = nullptr;                  // refit scratch: every node's own float box (2 x F4 per node)
+    int64_t node_box_n = 0;
+    double ms_refit = 0;                       // device time of the last refit
     int stack_limit = PTB_STACK;               // PTB_OPT_STACK_LIMIT (tests): refuse trees that need more traversal-stack entries than this
     int build_threads = 0;                     // PTB_OPT_BUILD_THREADS: OpenMP threads of the BVH build (0: the runtime's default)
     std::vector<cudaEvent_t> ev_pool;          // PTB_OPT_TIME_KERNELS: start/stop pairs, one per launch
@@ -688,16 +811,60 @@ static int commit_upload(ptb_ctx* c, FlatScene& f, const HostScene& host) {
     CK(cudaStreamSynchronize(c->stream));
     c->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     c->bytes_nodes = (int64_t)f.nodes.size() * sizeof(Node8);
-    c->bytes_tris = (int64_t)(f.tris.size() + f.tris_obj.size()) * sizeof(F4);
-    c->bytes_attr = (int64_t)f.tri_uv.size() * sizeof(TriUV) + (int64_t)f.tri_shade.size() * sizeof(TriShade);
+    c->bytes_tris = (int64_t)f.tris.size() * sizeof(F4);     // what the traversal streams; the object-space corners count as attributes
+    c->bytes_attr = (int64_t)f.tri_uv.size() * sizeof(TriUV) + (int64_t)f.tri_shade.size() * sizeof(TriShade) + (int64_t)f.tris_obj.size() * sizeof(F4);
     c->bytes_tex = (int64_t)f.texels.size() * 4 + (int64_t)f.envmap.size() + (int64_t)f.merl.size() * 4;
     c->committed = true;
+    c->frame_dirty = false;
     return PTB_OK;
 }
 static void commit_release_host(ptb_ctx* c) {   // the host copies of the big arrays are no longer needed
     FlatScene& f = c->flat;
     std::vector<F4>().swap(f.tris); std::vector<F4>().swap(f.tris_obj); std::vector<TriUV>().swap(f.tri_uv); std::vector<TriShade>().swap(f.tri_shade);
     std::vector<float>().swap(f.texels); std::vector<float>().swap(f.merl);
+}
+
+// Re-pose a committed scene at HostScene::current_frame without rebuilding: host part (matrices, light, header) ...
+static int refit_host(ptb_ctx* lead) {
+    lead->host.replace_placements(lead->flat);
+    return PTB_OK;
+}
+// ... and device part, from the (leader's) flattened scene: by-value header, object table, triangles, node boxes
+static int refit_device(ptb_ctx* c, FlatScene& f, const HostScene& host) {
+    CK(cudaSetDevice(c->device));
+    SceneDev& sc = c->sc;
+    const float* bg = sc.background;
+    scene_header(sc, f);
+    int rc = scene_modes(sc, host, c->err);
+    sc.background = bg;
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemcpyAsync(const_cast<ObjectDev*>(sc.objects), f.objects.data(), f.objects.size() * sizeof(ObjectDev), cudaMemcpyHostToDevice, c->stream));
+    const size_t n_tri = (size_t)(c->bytes_tris / (3 * (int64_t)sizeof(F4)));
+    if (sc.has_mesh && n_tri > 0) {
+        if (!sc.tris_obj) { c->err = "refit: the scene was committed without object-space triangles"; return PTB_ERR_STATE; }
+        if ((rc = grow(c, &c->d_node_box, &c->node_box_n, 2 * (int64_t)f.bvh.n_nodes))) return rc;
+        k_refit_tris<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(sc.tris_obj, sc.objects, const_cast<F4*>(sc.tris), n_tri);
+        const std::vector<uint32_t>& ls = f.bvh.level_start;
+        for (int l = (int)ls.size() - 2; l >= 0; l--) {
+            const uint32_t first = ls[l], count = ls[l + 1] - ls[l];
+            if (count) k_refit_level<<<(count + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<Node8*>(const_cast<F4*>(sc.nodes)), c->d_node_box, sc.tris_obj, sc.objects, first, count);
+        }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->ms_refit = ms;
+    c->frame_dirty = false;
+    return PTB_OK;
+}
+static int ensure_frame(ptb_ctx* c) {      // every device query of a single context starts here
+    if (!c->frame_dirty) return PTB_OK;
+    if (c->info_n_tri >= 0) { c->err = "a group member is re-posed by ptb_group_render"; return PTB_ERR_STATE; }
+    int rc = refit_host(c);
+    return rc ? rc : refit_device(c, c->flat, c->host);
 }
 
 extern "C" {
@@ -752,7 +919,7 @@ void ptb_destroy(ptb_ctx* c) {
     c->pinned.clear();
     free_scene(c);
     free_pool(c);
-    void* ptrs[] = {c->d_counters, c->d_totals, c->d_rpp, c->d_accum, c->d_out_img, c->d_out_cnt, c->d_out_u8, c->d_aux, c->d_out_aux, c->d_prog_accum, c->d_lowres, c->d_pack};
+    void* ptrs[] = {c->d_counters, c->d_totals, c->d_rpp, c->d_accum, c->d_out_img, c->d_out_cnt, c->d_out_u8, c->d_aux, c->d_out_aux, c->d_prog_accum, c->d_lowres, c->d_pack, c->d_node_box};
     for (void* p : ptrs) if (p) cudaFree(p);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -772,6 +939,14 @@ int ptb_add_plane(ptb_ctx* c, const float A[3], const float N[3], const ptb_xfor
     if (!c || !A || !N) return PTB_ERR_INVALID;
     if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
     const int id = c->host.add_plane(A, N, xf, flags);
+    if (out_id) *out_id = id;
+    return PTB_OK;
+}
+int ptb_add_cylinder(ptb_ctx* c, const float A[3], const float B[3], float R, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !A || !B) return PTB_ERR_INVALID;
+    if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
+    if (!(R > 0) || (A[0] == B[0] && A[1] == B[1] && A[2] == B[2])) { c->err = "add_cylinder: needs a radius > 0 and two distinct end points"; return PTB_ERR_INVALID; }
+    const int id = c->host.add_cylinder(A, B, R, xf, flags);
     if (out_id) *out_id = id;
     return PTB_OK;
 }
@@ -836,6 +1011,7 @@ int ptb_set_keyframes(ptb_ctx* c, int obj, int kind, const float* frames, const 
 
 int ptb_set_frame(ptb_ctx* c, float frame) {
     if (!c) return PTB_ERR_INVALID;
+    if (c->committed && frame != c->host.current_frame) c->frame_dirty = true;   // re-posed (refit, no rebuild) by the next render / picking query
     c->host.current_frame = frame;
     return PTB_OK;
 }
@@ -1191,6 +1367,7 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
 int ptb_render_accum(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* d_rgbw, ptb_stats* stats) {
     if (!c) return PTB_ERR_INVALID;
     if (!c->committed) { c->err = "render before commit"; return PTB_ERR_STATE; }
+    { const int rf = ensure_frame(c); if (rf) return rf; }
     if (!d_rgbw) { c->err = "render_accum: null device buffer"; return PTB_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
     FrameDev f;
@@ -1229,6 +1406,7 @@ int ptb_resolve(ptb_ctx* c, const float* d_rgbw, int W, int H, float gamma, floa
 int ptb_render(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats) {
     if (!c) return PTB_ERR_INVALID;
     if (!c->committed) { c->err = "render before commit"; return PTB_ERR_STATE; }
+    { const int rf = ensure_frame(c); if (rf) return rf; }
     CK(cudaSetDevice(c->device));
     auto w0 = std::chrono::steady_clock::now();
     FrameDev f;
@@ -1256,6 +1434,7 @@ int ptb_render_denoiser_inputs(ptb_ctx* c, const ptb_camera* cam, const ptb_para
                                float* normalImage, float* first_hit_normal, ptb_stats* stats) {
     if (!c) return PTB_ERR_INVALID;
     if (!c->committed) { c->err = "render before commit"; return PTB_ERR_STATE; }
+    { const int rf = ensure_frame(c); if (rf) return rf; }
     CK(cudaSetDevice(c->device));
     FrameDev f;
     int rc = frame_setup(c, cam, p, f);
@@ -1284,6 +1463,7 @@ int ptb_render_denoiser_inputs(ptb_ctx* c, const ptb_camera* cam, const ptb_para
 int ptb_progressive_begin(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p) {
     if (!c) return PTB_ERR_INVALID;
     if (!c->committed) { c->err = "render before commit"; return PTB_ERR_STATE; }
+    { const int rf = ensure_frame(c); if (rf) return rf; }
     CK(cudaSetDevice(c->device));
     c->prog_active = false;
     int rc = frame_setup(c, cam, p, c->prog_f);
@@ -1380,6 +1560,7 @@ int ptb_shard_unpack_add(ptb_ctx* c, const ptb_params* p, int shard_rank, const 
 int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* obj_id, int32_t* tri_id, float* t) {
     if (!c || !cam || W <= 0 || H <= 0) return PTB_ERR_INVALID;
     if (!c->committed) { c->err = "primary_ids before commit"; return PTB_ERR_STATE; }
+    { const int rf = ensure_frame(c); if (rf) return rf; }
     CK(cudaSetDevice(c->device));
     CameraDev cd;
     camera_from_abi(cd, cam, W, H);
@@ -1421,7 +1602,7 @@ int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
     if (c->info_n_tri >= 0) {   // a group follower: the leader flattened the scene
         info->n_triangles = c->info_n_tri; info->n_bvh_nodes = c->info_nodes; info->bvh_depth = c->info_depth;
         info->bytes_nodes = c->bytes_nodes; info->bytes_triangles = c->bytes_tris; info->bytes_attributes = c->bytes_attr; info->bytes_textures = c->bytes_tex;
-        info->ms_upload = c->ms_upload;
+        info->ms_upload = c->ms_upload; info->ms_refit = c->ms_refit;
         return PTB_OK;
     }
     info->n_triangles = c->flat.n_tri_scene;   // as handed over; bytes_triangles counts those resident (alpha maps can rule triangles out, scene_host.cpp)
@@ -1429,7 +1610,7 @@ int ptb_get_scene_info(const ptb_ctx* c, ptb_scene_info* info) {
     info->bytes_nodes = c->bytes_nodes; info->bytes_triangles = c->bytes_tris; info->bytes_attributes = c->bytes_attr; info->bytes_textures = c->bytes_tex;
     info->n_objects = (int32_t)c->host.objects.size();
     info->bvh_depth = c->flat.bvh.depth;
-    info->ms_bvh_build = c->flat.ms_bvh; info->ms_upload = c->ms_upload;
+    info->ms_bvh_build = c->flat.ms_bvh; info->ms_upload = c->ms_upload; info->ms_refit = c->ms_refit;
     return PTB_OK;
 }
 

@@ -14,6 +14,7 @@ namespace ptb {
 struct Bvh8Stats {
     int64_t n_nodes = 0, n_binary_nodes = 0, leaves = 0;
     int depth = 0;
+    std::vector<uint32_t> level_start;     // nodes are emitted breadth first: level l is [level_start[l], level_start[l + 1]) (refit walks them bottom-up)
 };
 // verts9: 9 floats per triangle (world space).  leaf_order[k] = input index of the k-th stored triangle.
 void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& nodes, std::vector<uint32_t>& leaf_order, Bvh8Stats& stats);
@@ -30,7 +31,7 @@ struct HostMaterial {
 struct HostObject {
     int type = OBJ_SPHERE, flags = 0, brdf = 0, merl = 0;
     ptb_xform xf;
-    float a[3] = {0, 0, 0}, n[3] = {0, 1, 0}, R = 0;
+    float a[3] = {0, 0, 0}, n[3] = {0, 1, 0}, R = 0, len = 0;
     std::vector<HostMaterial> groups;      // index = group
     // mesh data AFTER TriMesh::init processing (object space)
     std::vector<float> vertices, normals, uvs, tangents;   // tangents: per vertex
@@ -82,9 +83,14 @@ struct HostScene {
 
     int add_sphere(const float O[3], float R, const ptb_xform* xf, int flags);
     int add_plane(const float A[3], const float N[3], const ptb_xform* xf, int flags);
+    int add_cylinder(const float A[3], const float B[3], float R, const ptb_xform* xf, int flags);
     int add_mesh(const ptb_mesh* m, const ptb_xform* xf, int flags, std::string& err);
     int set_group_material(int obj, int group, const ptb_material* m, std::string& err);
     int flatten(FlatScene& out, std::string& err);
+    // Scene::prepare_render at another frame for an already flattened scene: every object's matrices (build_matrix(current_frame)) and
+    // the light constants are recomputed into `f.objects` / `f`; geometry, materials and the BVH topology are untouched (refit).
+    void replace_placements(FlatScene& f);
+    bool has_keyframes() const { for (const HostObject& o : objects) for (int k = 0; k < 3; k++) if (!o.keys[k].frames.empty()) return true; return false; }
 };
 
 void build_matrix(HostObject& o);          // Object::build_matrix (Geometry.h:322-360)
@@ -113,6 +119,7 @@ inline void scene_header(SceneDev& sc, FlatScene& f) {
             if (m[0] == 1.f && m[1] == 0.f && m[2] == 0.f && m[4] == 0.f && m[5] == 1.f && m[6] == 0.f && m[8] == 0.f && m[9] == 0.f && m[10] == 1.f)
                 a.type |= PTB_ANALYTIC_LINEAR_ID;
             for (int k = 0; k < 3; k++) { a.a[k] = o.a[k]; a.n[k] = o.n[k]; }
+            a.len = o.len;
         } else { o.flags |= FLAG_NOT_INLINE; sc.n_extra++; }
     }
 }

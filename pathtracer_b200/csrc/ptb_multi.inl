@@ -118,6 +118,7 @@ int ptb_unpin_host_buffer(ptb_ctx* c, void* ptr) {
 int ptb_render_sharded(ptb_ctx* c, const ptb_camera* cam, const ptb_params* p, float* imagedouble, float* sample_count, uint8_t* image, ptb_stats* stats) {
     if (!c || !p) return PTB_ERR_INVALID;
     if (!c->committed) { c->err = "render before commit"; return PTB_ERR_STATE; }
+    if (c->info_n_tri < 0) { const int rf = ensure_frame(c); if (rf) return rf; }     // (group members are re-posed by ptb_group_render)
     CK(cudaSetDevice(c->device));
     auto w0 = std::chrono::steady_clock::now();
     const int n = c->comm_n, rank = c->comm_rank;
@@ -261,6 +262,14 @@ int ptb_group_render(ptb_group* g, const ptb_camera* cam, const ptb_params* p, f
     auto w0 = std::chrono::steady_clock::now();
     const size_t n = g->ctx.size();
     std::vector<int> rcs(n, PTB_OK);
+    ptb_ctx* lead = g->ctx[0];
+    if (lead->frame_dirty) {     // ptb_set_frame on the leader: matrices once on the host, triangles and node boxes on every device
+        refit_host(lead);
+        std::vector<std::thread> rt;
+        for (size_t i = 0; i < n; i++) rt.emplace_back([&, i] { rcs[i] = refit_device(g->ctx[i], lead->flat, lead->host); });
+        for (auto& t : rt) t.join();
+        for (size_t i = 0; i < n; i++) if (rcs[i]) { g->err = "device " + std::to_string(g->ctx[i]->device) + " (refit): " + g->ctx[i]->err; return rcs[i]; }
+    }
     std::vector<ptb_stats> st(n);
     std::vector<std::thread> th;
     for (size_t i = 1; i < n; i++)

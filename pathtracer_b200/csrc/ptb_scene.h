@@ -16,7 +16,7 @@
 
 namespace ptb {
 
-enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2 };
+enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2, OBJ_CYLINDER = 3 };
 enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4, FLAG_GHOST = 8, FLAG_NOT_INLINE = 1 << 16 };
 enum { SLOT_KD = 1, SLOT_KS = 2, SLOT_NE = 4, SLOT_TRANSP = 8, SLOT_REFR = 16, SLOT_NORMAL = 32, SLOT_ALPHA = 64, SLOT_KSUB = 128 };
 
@@ -26,9 +26,10 @@ struct ObjectDev {          // Object / Sphere / Plane fields the path reads (Ge
     int32_t slot_mask;            // union of the slots present on the object (Geometry.h:979 test for spheres)
     int32_t pad;
     float trans[12], inv_trans[12], rot[9];
-    float a[3];                   // Sphere::O / Plane::A
-    float n[3];                   // Plane::vecN
+    float a[3];                   // Sphere::O / Plane::A / Cylinder::A
+    float n[3];                   // Plane::vecN / Cylinder::d (unit axis)
     float R, R2;
+    float len, pad2;              // Cylinder::len
 };
 struct MaterialDev {
     uint32_t present;
@@ -52,6 +53,7 @@ struct AnalyticDev {
     int32_t type, id;           // OBJ_SPHERE / OBJ_PLANE, scene object id (bit 30 of `type`: Object::ghost, skipped by shadow rays)
     float inv_trans[12];
     float a[3], n[3], R2;
+    float len;                  // Cylinder::len
 };
 
 #define PTB_ANALYTIC_GHOST (1 << 30)
@@ -97,7 +99,7 @@ PTB_HD bool tri_exact_available(const AlphaCtx* c) { return c != nullptr && c->t
 
 // Scene::intersection's ray transform (Geometry.cpp:603-605, Geometry.h:383-397) + the Triangle constructor and
 // Triangle::intersection (TriangleMesh.h:70-104) + the `localt < t` of the traversal (TriangleMesh.cpp:1197), one rounding per operation.
-PTB_HD_NOINLINE bool tri_exact(const AlphaCtx* c, int prim, V3 o, V3 d, float tbest, float& t, float& b1, float& b2) {
+PTB_EXACT_LINKAGE bool tri_exact(const AlphaCtx* c, int prim, V3 o, V3 d, float tbest, float& t, float& b1, float& b2) {
 #if defined(__CUDA_ARCH__)
     const float4 qa = __ldg(reinterpret_cast<const float4*>(c->tris_obj) + 3 * (size_t)prim), qb = __ldg(reinterpret_cast<const float4*>(c->tris_obj) + 3 * (size_t)prim + 1),
                  qc = __ldg(reinterpret_cast<const float4*>(c->tris_obj) + 3 * (size_t)prim + 2);
@@ -116,7 +118,9 @@ PTB_HD_NOINLINE bool tri_exact(const AlphaCtx* c, int prim, V3 o, V3 d, float tb
     const V3 u = sub3_rn(v3(qb.x, qb.y, qb.z), A), v = sub3_rn(v3(qc.x, qc.y, qc.z), A);
     const V3 N = cross_rn(u, v);
     const float m11 = dot_rn(u, u), m22 = dot_rn(v, v), m12 = dot_rn(u, v);
-    const float invdetm = (float)(1. / (double)sub_rn(mul_rn(m11, m22), mul_rn(m12, m12)));
+    // `1. / (m11*m22 - m12*m12)` narrowed to float (TriangleMesh.h:77): the correctly rounded float quotient equals the narrowed double
+    // quotient except when the latter falls within 2^-29 of a rounding midpoint
+    const float invdetm = div_rn(1.f, sub_rn(mul_rn(m11, m22), mul_rn(m12, m12)));
     const float tt = div_rn(dot_rn(sub3_rn(A, ol), N), dot_rn(dl, N));
     if (tt < 0 || tt != tt) return false;
     const V3 w = sub3_rn(add3_rn(ol, scale_rn(tt, dl)), A);
@@ -194,12 +198,36 @@ PTB_HD bool plane_t(const float* A, const float* Nn, V3 o, V3 d, float& t) {
     return true;
 }
 
+// Cylinder::intersection (Geometry.h:740-766): roots of |X t + Y|^2 = R^2 with X, Y the parts of direction / origin - A orthogonal to
+// the axis; the nearer positive root must lie between the end planes (the farther one is never tried).  No test against the best t
+// so far; a ray parallel to the axis yields NaN, which the caller's `t < min_t` discards.
+PTB_HD bool cylinder_t(const float* A, const float* D, float R2, float len, V3 o, V3 d, float& t) {
+    const V3 a0 = v3(A[0], A[1], A[2]), ax = v3(D[0], D[1], D[2]);
+    const V3 X = d - dot(d, ax) * ax;
+    const V3 oa = o - a0;
+    const V3 Y = oa - dot(oa, ax) * ax;
+    const float a = norm2(X);
+    const float b = 2 * dot(X, Y);
+    const float c = norm2(Y) - R2;
+    const float delta = b * b - 4 * a * c;
+    if (delta < 0) return false;
+    const float sdelta = sqrtf(delta);
+    const float t2 = (-b + sdelta) / (2 * a);
+    if (t2 < 0) return false;
+    const float t1 = (-b - sdelta) / (2 * a);
+    t = (t1 > 0) ? t1 : t2;
+    const V3 P = o + t * d;
+    const float dP = dot(P - a0, ax);
+    if (dP < 0 || dP > len) return false;
+    return true;
+}
+
 #define PTB_HIT_MISS (-1)
 PTB_HD int32_t hit_id_analytic(int obj) { return -2 - obj; }
 
 // Nearest hit over the analytic objects (Sphere / Plane) of Scene::intersection's loop (Geometry.cpp:601-626):
 // object-space rays, world t.  Meshes are handled by the wide BVH afterwards.
-PTB_HD bool analytic_t(int type, const float* inv_trans, const float* A, const float* N, float R2, V3 o, V3 d, float& t) {
+PTB_HD bool analytic_t(int type, const float* inv_trans, const float* A, const float* N, float R2, float len, V3 o, V3 d, float& t) {
     V3 dl, ol;
     if (type & PTB_ANALYTIC_LINEAR_ID) {   // uniform per object; same bits as the general form for m = [I | t]
         dl = d;
@@ -208,6 +236,7 @@ PTB_HD bool analytic_t(int type, const float* inv_trans, const float* A, const f
         dl = xf_dir(inv_trans, d);
         ol = xf_point(inv_trans, o);
     }
+    if ((type & 0xff) == OBJ_CYLINDER) return cylinder_t(A, N, R2, len, ol, dl, t);
     return ((type & 0xff) == OBJ_SPHERE) ? sphere_t(A, R2, ol, dl, t) : plane_t(A, N, ol, dl, t);
 }
 PTB_HD void analytic_closest(const SceneDev& sc, V3 o, V3 d, float& tmin, int32_t& id) {
@@ -218,14 +247,14 @@ PTB_HD void analytic_closest(const SceneDev& sc, V3 o, V3 d, float& tmin, int32_
     for (int i = 0; i < sc.n_inline; i++) {
         const AnalyticDev& ob = sc.analytic[i];
         float t;
-        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && t < tmin) { tmin = t; best = ob.id; }
+        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && t < tmin) { tmin = t; best = ob.id; }
     }
     if (sc.n_extra > 0)
         for (int i = 0; i < sc.n_objects; i++) {
             const ObjectDev& ob = sc.objects[i];
             if (ob.type == OBJ_MESH || !(ob.flags & FLAG_NOT_INLINE)) continue;
             float t;
-            if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (t < tmin || (t == tmin && i < best))) { tmin = t; best = i; }
+            if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && (t < tmin || (t == tmin && i < best))) { tmin = t; best = i; }
         }
     if (best >= 0) id = hit_id_analytic(best);
 }
@@ -236,14 +265,14 @@ PTB_HD bool analytic_occluded(const SceneDev& sc, V3 o, V3 d, float dist_light) 
         const AnalyticDev& ob = sc.analytic[i];
         if (ob.type & PTB_ANALYTIC_GHOST) continue;   // avoid_ghosts (Geometry.cpp:722)
         float t;
-        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (double)t < lim) return true;
+        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && (double)t < lim) return true;
     }
     if (sc.n_extra > 0)
         for (int i = 0; i < sc.n_objects; i++) {
             const ObjectDev& ob = sc.objects[i];
             if (ob.type == OBJ_MESH || !(ob.flags & FLAG_NOT_INLINE) || (ob.flags & FLAG_GHOST)) continue;
             float t;
-            if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, o, d, t) && (double)t < lim) return true;
+            if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && (double)t < lim) return true;
         }
     return false;
 }
@@ -353,6 +382,13 @@ PTB_HD void surface_from_hit(const SceneDev& sc, V3 o, V3 d, const Hit& hit, int
                 s.Ke = v3(0, 0, 0);
                 Nl = (ob.flags & FLAG_FLIP) ? -N : N;
             }
+        } else if (ob.type == OBJ_CYLINDER) {   // Geometry.h:758-763
+            const V3 a0 = v3(ob.a[0], ob.a[1], ob.a[2]), ax = v3(ob.n[0], ob.n[1], ob.n[2]);
+            const float dP = dot(Pl - a0, ax);
+            const V3 proj = a0 + dP * ax;
+            query_material(sc, ob, 0, dP / ob.len, 0.5f, s);
+            Nl = Pl - proj;                      // not normalised here: Scene::intersection's fast_normalize does it
+            if (ob.flags & FLAG_FLIP) Nl = -Nl;
         } else {
             Nl = v3(ob.n[0], ob.n[1], ob.n[2]);
             query_material(sc, ob, 0, Pl.x * 0.1f, Pl.z * 0.1f, s);

@@ -47,6 +47,21 @@ int HostScene::add_plane(const float A[3], const float N[3], const ptb_xform* xf
     return (int)objects.size() - 1;
 }
 
+// Cylinder(A, B, R) (Geometry.h:734-738): d = (B - A).getNormalized(), len = sqrt((B - A).getNorm2())
+int HostScene::add_cylinder(const float A[3], const float B[3], float R, const ptb_xform* xf, int flags) {
+    HostObject o;
+    o.type = OBJ_CYLINDER; o.flags = flags;
+    const V3 ab = v3(B[0], B[1], B[2]) - v3(A[0], A[1], A[2]);
+    const V3 d = normalize(ab);
+    o.a[0] = A[0]; o.a[1] = A[1]; o.a[2] = A[2];
+    o.n[0] = d.x; o.n[1] = d.y; o.n[2] = d.z;
+    o.R = R; o.len = sqrtf(norm2(ab));
+    const float zero[3] = {0, 0, 0};
+    take_xform(o, xf, zero);   // Object(): rotation_center = Vector() = 0
+    objects.push_back(std::move(o));
+    return (int)objects.size() - 1;
+}
+
 static inline V3 V(const std::vector<float>& a, int i) { return v3(a[3 * (size_t)i], a[3 * (size_t)i + 1], a[3 * (size_t)i + 2]); }
 
 int HostScene::add_mesh(const ptb_mesh* m, const ptb_xform* xf, int flags, std::string& err) {
@@ -244,6 +259,25 @@ static int alpha_class(const AlphaSat& s, const float* uv0, const float* uv1, co
     return n == 0 ? ALPHA_OPAQUE : (n == area ? ALPHA_INVISIBLE : ALPHA_TEST);
 }
 
+void HostScene::replace_placements(FlatScene& f) {
+    for (size_t i = 0; i < objects.size() && i < f.objects.size(); i++) {
+        HostObject& o = objects[i];
+        const ptb_xform static_xf = o.xf;
+        o.xf = placement_at(o, current_frame);          // Object::build_matrix(current_frame), Geometry.cpp:283
+        build_matrix(o);
+        o.xf = static_xf;
+        ObjectDev& d = f.objects[i];
+        memcpy(d.trans, o.trans, sizeof(d.trans)); memcpy(d.inv_trans, o.inv_trans, sizeof(d.inv_trans)); memcpy(d.rot, o.rot, sizeof(d.rot));
+    }
+    const HostObject& L = objects[0];                   // light constants (Raytracer.cpp:1377-1380)
+    const V3 c = xf_point(L.trans, v3(L.a[0], L.a[1], L.a[2]));
+    f.centerLight[0] = c.x; f.centerLight[1] = c.y; f.centerLight[2] = c.z;
+    const float lum_scale = placement_at(L, current_frame).scale;
+    f.radiusLight = lum_scale * L.R;
+    f.lightPower = intensite_lumiere / (lum_scale * lum_scale);
+    f.envmap_intensity = envmap_intensity;
+}
+
 int HostScene::flatten(FlatScene& out, std::string& err) {
     if (objects.size() < 2 || objects[0].type != OBJ_SPHERE || objects[1].type != OBJ_SPHERE) {
         err = "commit: object 0 must be the spherical light and object 1 the environment dome (Raytracer.cpp:1257-1266)";
@@ -273,7 +307,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
         }
         memcpy(d.trans, o.trans, sizeof(d.trans)); memcpy(d.inv_trans, o.inv_trans, sizeof(d.inv_trans)); memcpy(d.rot, o.rot, sizeof(d.rot));
         for (int k = 0; k < 3; k++) { d.a[k] = o.a[k]; d.n[k] = o.n[k]; }
-        d.R = o.R; d.R2 = o.R * o.R;
+        d.R = o.R; d.R2 = o.R * o.R; d.len = o.len;
         out.objects.push_back(d);
         if (o.type == OBJ_MESH) n_tri += (int64_t)o.tri.size() / 10;
     }
@@ -365,7 +399,9 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
             if (o.flags & FLAG_GHOST) flags |= PTB_TRI_FLAG_GHOST;
             F4 q;
             q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = u2f(flags); out.tris[3 * (size_t)k] = q;
-            q.x = v[3] - v[0]; q.y = v[4] - v[1]; q.z = v[5] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 1] = q;
+            q.x = v[3] - v[0]; q.y = v[4] - v[1]; q.z = v[5] - v[2];
+            q.w = (flags & PTB_TRI_FLAG_ALPHA) ? INFINITY : PTB_EDGE_EPS;     // see tri_test_classify (ptb_bvh8.h)
+            out.tris[3 * (size_t)k + 1] = q;
             q.x = v[6] - v[0]; q.y = v[7] - v[1]; q.z = v[8] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 2] = q;
             for (int c = 0; c < 3; c++) {      // what Triangle(vertices[vtxi], vertices[vtxj], vertices[vtxk]) is built from (TriangleMesh.cpp:812-815)
                 const V3 pv = V(o.vertices, t[c]);

@@ -69,7 +69,7 @@ struct Material {                // one slot index of Object::textures / specula
     }
 };
 
-enum ObjectType { OT_TRIMESH, OT_SPHERE, OT_PLANE };
+enum ObjectType { OT_TRIMESH, OT_SPHERE, OT_PLANE, OT_POINTSET, OT_CYLINDER };   // Geometry.h:29
 
 struct Object {                  // Geometry.h:240-672
     ObjectType type;
@@ -113,6 +113,10 @@ struct Sphere : Object {
 struct Plane : Object {
     Vector A, vecN;
     Plane(const Vector& a, const Vector& n, bool mirror = false) : Object(OT_PLANE), A(a), vecN(n) { miroir = mirror; }
+};
+struct Cylinder : Object {       // Geometry.h:731-846
+    Vector A, B; float R;
+    Cylinder(const Vector& a, const Vector& b, float r) : Object(OT_CYLINDER), A(a), B(b), R(r) {}
 };
 struct TriMesh : Object {        // arrays as a reader fills them (TriangleMesh.cpp:240-569), before init's processing
     std::vector<float> vertices, normals, uvs;   // x3, x3, x2
@@ -178,12 +182,12 @@ public:
         ck(ptb_set_frame(ctx_, (float)s.current_frame));
         commit_device();
     }
-    // One frame of an animation (mainApp.cpp:874-877): key-framed objects are placed at `frame` and the scene is committed again.
+    // One frame of an animation (mainApp.cpp:874-877): key-framed objects are placed at `frame`.  Nothing is rebuilt: the library
+    // re-poses the scene on the device before the next render (matrices, world-space triangles, BVH8 refit).
     void set_frame(int frame) {
         s.current_frame = frame;
         if (!ctx_) { commit(); return; }
         ck(ptb_set_frame(ctx_, (float)frame));
-        commit_device();
     }
 
     // hands the scene to the device: TriMesh::init + build_bvh + Scene::prepare_render equivalents
@@ -199,6 +203,7 @@ public:
             int id = -1;
             if (o.type == OT_SPHERE) { auto& sp = static_cast<Sphere&>(o); ck(ptb_add_sphere(ctx_, sp.O.v, sp.R, &xf, flags, &id)); }
             else if (o.type == OT_PLANE) { auto& pl = static_cast<Plane&>(o); ck(ptb_add_plane(ctx_, pl.A.v, pl.vecN.v, &xf, flags, &id)); }
+            else if (o.type == OT_CYLINDER) { auto& cy = static_cast<Cylinder&>(o); ck(ptb_add_cylinder(ctx_, cy.A.v, cy.B.v, cy.R, &xf, flags, &id)); }
             else {
                 auto& g = static_cast<TriMesh&>(o);
                 ptb_mesh m;

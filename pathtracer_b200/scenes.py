@@ -9,7 +9,7 @@ import math
 
 import numpy as np
 
-from .api import Plane, Raytracer, Sphere, Texture, TriMesh
+from .api import Cylinder, Plane, Raytracer, Sphere, Texture, TriMesh
 
 
 def displaced_torus(nv):
@@ -137,6 +137,30 @@ def config_ngan(lib, W=128, H=128, spp=8, nv=24, device=0):
     for O, R, name in (((-20, -20.3, 8), 7, "copper_ngan"), ((19, -21.3, 10), 6, "pearl_ngan"), ((2, -23.3, 22), 4, "bronze")):
         rt.s.addObject(Sphere(O, R).set_material(0, **phong((.8, .3, .3), 0.1, 10.0)).set_preset(name, 0))
     rt.s.objects[1].envmap = sky_envmap(128, 64)
+    return rt
+
+
+def config_cyl(lib, W=128, H=128, spp=8, nv=16, device=0):
+    """Cylinder objects (Geometry.h:731-846, the reference's yarn segments): a standing textured tube, a tilted one that is scaled and
+    rotated by its object matrix, a mirror tube lying on the ground, one seen through its open end, plus a small torus that casts
+    and receives their shadows."""
+    rt = base(lib, W, H, spp, device=device)
+    t = np.linspace(0, 1, 32, dtype=np.float64)
+    stripes = np.repeat(np.repeat((0.25 + 0.7 * (np.floor(t * 8) % 2))[None, :, None], 4, 0), 3, 2).astype(np.float32)   # varies along the axis (u = dP/len)
+    a = Cylinder((-14, -27.3, 6), (-14, -9, 6), 4.0).set_material(0, **phong((.9, .5, .2), 0.2, 30.0))
+    a.materials[0]["Kd"] = Texture((.9, .5, .2), stripes)
+    b = Cylinder((6, -25, -4), (16, -12, 4), 2.5).set_material(0, **phong((.3, .5, .9), 0.4, 80.0))
+    b.scale, b.mat_rotation = 1.2, _rot(0.3, 0.5)
+    b.max_translation = np.array([2, 1, -3], np.float32)
+    c = Cylinder((-6, -24.8, 16), (8, -24.8, 20), 2.5, mirror=True).set_material(0, **phong((.8, .8, .8), 0.0, 1.0))
+    d = Cylinder((18, -20, 26), (24, -16, 6), 3.0).set_material(0, **phong((.6, .8, .3), 0.1, 10.0))   # roughly along the view: the open end
+    d.flip_normals = True
+    for o in (a, b, c, d):
+        rt.s.addObject(o)
+    m = _place_like_gui(TriMesh(*displaced_torus(nv)), scale=14.0)
+    m.max_translation = m.max_translation + np.array([0, 0, 2], np.float32)
+    m.set_material(0, **phong((.5, .5, .5), (.2, .2, .2), 50.0))
+    rt.s.addObject(m)
     return rt
 
 
