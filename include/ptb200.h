@@ -157,6 +157,23 @@ int ptb_add_plane(ptb_ctx*, const float A[3], const float N[3], const ptb_xform*
  * reference's test).  Material slot 0 is looked up at (u, v) = (position along the axis / length, 0.5).  The reference builds
  * these for its yarn curves (TriangleMesh.h:281); its default rotation centre is the origin. */
 int ptb_add_cylinder(ptb_ctx*, const float A[3], const float B[3], float R, const ptb_xform*, int flags, int* out_id);
+/* replaces: `new PointSet(file, nbcols, cols, mirror, normal_swapped, centered)` + addObject (PointSet.h:38-122, PointSet.cpp) with the
+ * results of its reader and of estimate_normals (PointSet.h:124-176: nanoflann 10-NN + CImg eigen-solver, not part of this library)
+ * passed in memory, as PointSet holds them after init: every point is a DISC (Disk, Geometry.h:1106-1122) with a centre, a normal
+ * (used as stored: not normalised for the plane test, normalised for shading), a radius and a colour (PointSet::colors, already
+ * /255; NULL = 0.5 grey, the reference's `colors.size() > i` fallback).  Material slot 0 is looked up at uv (0,0) and Kd replaced
+ * by the point's colour; the shading normal is turned towards the ray unless the slot is transparent (PointSet.cpp:192-206).
+ * PTB_OBJ_DISPLAY_EDGES blackens the outer 5 % ring of every disc (Object::display_edges, PointSet.cpp:212-216).  Triangle ids
+ * reported for a point set are point indices into these arrays.  xform->rotation_center NaN: the mean of the points (PointSet.h:113-121). */
+typedef struct ptb_pointset {
+    const float* points;    /* n x 3  PointSet::vertices */
+    const float* normals;   /* n x 3  PointSet::normals  */
+    const float* radii;     /* n      PointSet::radius   */
+    const float* colors;    /* n x 3  PointSet::colors, or NULL */
+    int32_t      n;
+} ptb_pointset;
+#define PTB_OBJ_DISPLAY_EDGES (1 << 4)
+int ptb_add_pointset(ptb_ctx*, const ptb_pointset*, const ptb_xform*, int flags, int* out_id);
 /* replaces: `new TriMesh(scene, file, scaling, offset, mirror, NULL, false, center)` + addObject
  * (TriangleMesh.cpp:714-841), with the reader's arrays passed in memory. */
 int ptb_add_mesh(ptb_ctx*, const ptb_mesh*, const ptb_xform*, int flags, int* out_id);

@@ -212,7 +212,7 @@ typedef struct { vec lo, hi; } box;
 typedef struct { int isleaf, fg, fd; box bb; } bnode;                       /* BVHNodesT, TriangleMesh.h:6-13 */
 typedef struct { int vtx[3], uv[3], n[3], group; } tindex;                  /* TriangleIndices, TriangleMesh.h:53-65 */
 typedef struct { vec A, u, v, N; float m11, m12, m22, invdetm; float uvs[3][2]; vec normals[3]; } tsoup; /* Triangle, 67-111 */
-enum { T_MESH, T_SPHERE, T_PLANE, T_CYLINDER };
+enum { T_MESH, T_SPHERE, T_PLANE, T_CYLINDER, T_POINTSET };
 typedef struct {
     int type, miroir, flip_normals, interp_normals, brdf, ghost;
     const double* merl;
@@ -223,6 +223,7 @@ typedef struct {
     slotv slots[S_COUNT];
     vec O; float R, R2; int has_envmap; const uint8_t* envtex; int envW, envH;   /* Sphere */
     vec A, vecN;                                                              /* Plane (Cylinder: A) */
+    int np, display_edges; vec *pt_pos, *pt_nrm, *pt_col; double* pt_rad; int* pt_perm;   /* PointSet: vertices, normals, colors (NULL: none), radius; perm: original index */
     vec cylB, cyld; float cyllen;                                             /* Cylinder: B, d, len (Geometry.h:734-738, 843-844) */
     int nv, nn, nuv, nt;                                                      /* TriMesh */
     vec *vertices, *normals; float* uvs; tindex* indices; tsoup* soup; vec* tangent_soup; int* permuted;
@@ -709,6 +710,119 @@ static int plane_hit(const object* pl, vec o, vec d, vec* P, float* t, matvals* 
     return 1;
 }
 
+/* ---- PointSet (PointSet.cpp): its own binary BVH over discs ---------------------------------------------- */
+static vec rad3(const object* g, int i) { float r = (float)g->pt_rad[i]; return V(r, r, r); }   /* Vector(radius[i], radius[i], radius[i]) */
+static box pts_bbox(const object* g, int i0, int i1) {                                            /* build_bbox, 4-14 */
+    box r; r.hi = vadd(g->pt_pos[i0], rad3(g, i0)); r.lo = vsub(g->pt_pos[i0], rad3(g, i0));
+    for (int i = i0; i < i1; i++) { r.lo = vmin3(r.lo, vsub(g->pt_pos[i], rad3(g, i))); r.hi = vmax3(r.hi, vadd(g->pt_pos[i], rad3(g, i))); }
+    return r;
+}
+static box pts_centers_bbox(const object* g, int i0, int i1) {                                    /* build_centers_bbox, 16-26 */
+    box r; r.hi = g->pt_pos[i0]; r.lo = g->pt_pos[i0];
+    for (int i = i0; i < i1; i++) { r.lo = vmin3(r.lo, g->pt_pos[i]); r.hi = vmax3(r.hi, g->pt_pos[i]); }
+    return r;
+}
+static void pts_bvh_recur(object* g, int node, int i0, int i1, int depth) {                       /* build_bvh_recur, 34-122 */
+    if (g->n_nodes == g->cap_nodes) { g->cap_nodes *= 2; g->nodes = (bnode*)realloc(g->nodes, sizeof(bnode) * (size_t)g->cap_nodes); }
+    bnode n; n.bb = pts_bbox(g, i0, i1); n.fg = i0; n.fd = i1; n.isleaf = 1;
+    g->nodes[g->n_nodes++] = n;
+    if (depth > g->bvh_depth) g->bvh_depth = depth;
+    box cb = pts_centers_bbox(g, i0, i1);
+    vec diag = vsub(cb.hi, cb.lo);
+    int dim;
+    if (diag.x >= diag.y && diag.x >= diag.z) dim = 0; else if (diag.y >= diag.x && diag.y >= diag.z) dim = 1; else dim = 2;
+    double best_factor = 0.5, best_area = 1E50;
+    for (int k = 0; k < 16; k++) {
+        double f = (k + 1) / (double)(16 + 1);
+        double split = vget(cb.lo, dim) + vget(diag, dim) * f;
+        box L = {V(1E10f, 1E10f, 1E10f), V(-1E10f, -1E10f, -1E10f)}, Rb = L;
+        int nl = 0, nr = 0;
+        for (int i = i0; i < i1; i++) {
+            double c = vget(g->pt_pos[i], dim);
+            if (c <= split) { L.lo = vmin3(L.lo, vsub(g->pt_pos[i], rad3(g, i))); L.hi = vmax3(L.hi, vadd(g->pt_pos[i], rad3(g, i))); nl++; }
+            else { Rb.lo = vmin3(Rb.lo, vsub(g->pt_pos[i], rad3(g, i))); Rb.hi = vmax3(Rb.hi, vadd(g->pt_pos[i], rad3(g, i))); nr++; }
+        }
+        double sum = box_area(&L) * nl + box_area(&Rb) * nr;       /* float area() * int, summed in float, widened */
+        if (sum < best_area) { best_factor = f; best_area = sum; }
+    }
+    double split = vget(cb.lo, dim) + vget(diag, dim) * best_factor;
+    int pivot = i0 - 1;
+    for (int i = i0; i < i1; i++) {
+        double c = vget(g->pt_pos[i], dim);
+        if (c <= split) {
+            pivot++;
+            vec tv = g->pt_pos[i]; g->pt_pos[i] = g->pt_pos[pivot]; g->pt_pos[pivot] = tv;
+            if (g->pt_col) { tv = g->pt_col[i]; g->pt_col[i] = g->pt_col[pivot]; g->pt_col[pivot] = tv; }
+            tv = g->pt_nrm[i]; g->pt_nrm[i] = g->pt_nrm[pivot]; g->pt_nrm[pivot] = tv;
+            double tr = g->pt_rad[i]; g->pt_rad[i] = g->pt_rad[pivot]; g->pt_rad[pivot] = tr;
+            int tp = g->pt_perm[i]; g->pt_perm[i] = g->pt_perm[pivot]; g->pt_perm[pivot] = tp;
+        }
+    }
+    if (pivot < i0 || pivot >= i1 - 1 || i1 <= i0 + 4) return;
+    g->nodes[node].isleaf = 0;
+    g->nodes[node].fg = g->n_nodes;
+    pts_bvh_recur(g, g->nodes[node].fg, i0, pivot + 1, depth + 1);
+    g->nodes[node].fd = g->n_nodes;
+    pts_bvh_recur(g, g->nodes[node].fd, pivot + 1, i1, depth + 1);
+}
+/* Disk::intersection (Geometry.h:1110-1118) */
+static int disk_hit(vec c, vec n, float r, vec o, vec d, vec* P, float* t) {
+    *t = vdot(vsub(c, o), n) / vdot(d, n);
+    if (*t < 0 || *t != *t) return 0;
+    *P = vadd(o, vscale(*t, d));
+    float r2 = vnorm2(vsub(*P, c));
+    return r2 <= r * r;
+}
+/* PointSet::intersection (PointSet.cpp:124-220) / intersection_shadow (247-315) */
+static int pts_hit(const object* g, vec o, vec d, vec* P, float* t, matvals* mat, float cur_best_t, int* tri_id, int shadow, float dist_light) {
+    *t = cur_best_t;
+    int has = 0, best = -1;
+    float tl, tr_, lt;
+    vec lp;
+    invray r; r.o = o; r.id = V(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    char s[3] = {(char)(r.id.x >= 0 ? 1 : 0), (char)(r.id.y >= 0 ? 1 : 0), (char)(r.id.z >= 0 ? 1 : 0)};
+    if (!box_invd(&g->bvh_bbox, &r, s, &tl)) return 0;
+    if (tl > cur_best_t || (shadow && tl > dist_light)) return 0;
+    int l[50]; float tn[50]; int top = -1;
+    l[++top] = 0; tn[top] = tl;
+    while (top >= 0) {
+        if (tn[top] > *t) { top--; continue; }
+        int cur = l[top--];
+        int fg = g->nodes[cur].fg, fd = g->nodes[cur].fd;
+        if (!g->nodes[cur].isleaf) {
+            int gl = box_invd(&g->nodes[fg].bb, &r, s, &tl) && tl < *t && (!shadow || tl < dist_light);
+            int gr = box_invd(&g->nodes[fd].bb, &r, s, &tr_) && tr_ < *t && (!shadow || tr_ < dist_light);
+            if (gl && gr) {
+                if (tl < tr_) { l[++top] = fd; tn[top] = tr_; l[++top] = fg; tn[top] = tl; }
+                else { l[++top] = fg; tn[top] = tl; l[++top] = fd; tn[top] = tr_; }
+            } else {
+                if (gl) { l[++top] = fg; tn[top] = tl; }
+                if (gr) { l[++top] = fd; tn[top] = tr_; }
+            }
+        } else {
+            for (int i = fg; i < fd; i++)
+                if (disk_hit(g->pt_pos[i], g->pt_nrm[i], (float)g->pt_rad[i], o, d, &lp, &lt) && lt < *t) { has = 1; best = i; *t = lt; }
+        }
+    }
+    if (has && !shadow) {
+        int i = best;
+        *tri_id = best;
+        disk_hit(g->pt_pos[i], g->pt_nrm[i], (float)g->pt_rad[i], o, d, &lp, &lt);
+        vec N = vnormalize(g->pt_nrm[i]);
+        *P = lp;
+        query_material(g, 0, 0, 0, mat);
+        mat->shadingN = N;
+        if (vdot(mat->shadingN, d) > 0 && !mat->transp) mat->shadingN = vneg(mat->shadingN);
+        if (g->flip_normals) mat->shadingN = vneg(mat->shadingN);
+        if (g->pt_col) mat->Kd = g->pt_col[i]; else mat->Kd = V(0.5f, 0.5f, 0.5f);
+        if (g->display_edges) {
+            float r2 = vnorm2(vsub(lp, g->pt_pos[i]));
+            if (r2 > (g->pt_rad[i] * g->pt_rad[i] * 0.95 * 0.95)) mat->Kd = V(0, 0, 0);
+        }
+    }
+    return has;
+}
+
 /* Cylinder::intersection (Geometry.h:740-766); intersection_shadow is the same call (836-841) */
 static int cylinder_hit(const object* cy, vec o, vec d, vec* P, float* t, matvals* mat) {
     vec X = vsub(d, vscale(vdot(d, cy->cyld), cy->cyld));
@@ -747,6 +861,7 @@ static int scene_hit(const struct ptb_ctx* c, vec o, vec d, vec* P, int* id, flo
         if (ob->type == T_MESH) h = mesh_hit(ob, ol, dl, &lp, &t, &lm, *min_t, tri_id, 0, 0);
         else if (ob->type == T_SPHERE) { h = sphere_hit(ob, ol, dl, &lp, &t, &lm, 0); if (h) *tri_id = -1; }
         else if (ob->type == T_CYLINDER) { h = cylinder_hit(ob, ol, dl, &lp, &t, &lm); if (h) *tri_id = -1; }
+        else if (ob->type == T_POINTSET) h = pts_hit(ob, ol, dl, &lp, &t, &lm, *min_t, tri_id, 0, 0);
         else { h = plane_hit(ob, ol, dl, &lp, &t, &lm, 0); if (h) *tri_id = -1; }
         if (h && t < *min_t) { has = 1; *min_t = t; *P = lp; *id = i; *mat = lm; }
     }
@@ -766,6 +881,7 @@ static int scene_shadow(const struct ptb_ctx* c, vec o, vec d, float dist_light,
         if (ob->type == T_MESH) h = mesh_hit(ob, ol, dl, &P, &t, &m, min_t, &tid, 1, dist_light);
         else if (ob->type == T_SPHERE) h = sphere_hit(ob, ol, dl, &P, &t, &m, 1);
         else if (ob->type == T_CYLINDER) { m = matvals_default(); h = cylinder_hit(ob, ol, dl, &P, &t, &m); }
+        else if (ob->type == T_POINTSET) h = pts_hit(ob, ol, dl, &P, &t, &m, min_t, &tid, 1, dist_light);
         else h = plane_hit(ob, ol, dl, &P, &t, &m, 1);
         if (h && t < dist_light * 0.999) return 1;
     }
@@ -1143,6 +1259,7 @@ static void free_object(object* o) {
     for (int s = 0; s < S_COUNT; s++) { for (int i = 0; i < o->slots[s].n; i++) free(o->slots[s].t[i].values); free(o->slots[s].t); }
     for (int k = 0; k < 3; k++) { free(o->kframe[k]); free(o->kval[k]); }
     free(o->vertices); free(o->normals); free(o->uvs); free(o->indices); free(o->soup); free(o->tangent_soup); free(o->permuted); free(o->nodes);
+    free(o->pt_pos); free(o->pt_nrm); free(o->pt_col); free(o->pt_rad); free(o->pt_perm);
     free(o);
 }
 static void prog_free(ptb_ctx* c);
@@ -1171,6 +1288,30 @@ int ptb_add_sphere(ptb_ctx* c, const float O[3], float R, const ptb_xform* xf, i
     if (!c || !O) return PTB_ERR_INVALID;
     object* o = new_object(c, T_SPHERE, xf, flags, V(O[0], O[1], O[2]));
     o->O = V(O[0], O[1], O[2]); o->R = R; o->R2 = R * R;
+    if (out_id) *out_id = c->n_objs - 1;
+    return PTB_OK;
+}
+int ptb_add_pointset(ptb_ctx* c, const ptb_pointset* p, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !p || !p->points || !p->normals || !p->radii || p->n <= 0) return PTB_ERR_INVALID;
+    int n = p->n;
+    vec rc = V(0, 0, 0);                                                   /* init: rotation_center = mean of the points (PointSet.h:113-121) */
+    for (int i = 0; i < n; i++) rc = vadd(rc, V(p->points[3 * i], p->points[3 * i + 1], p->points[3 * i + 2]));
+    rc = vdiv(rc, (float)n);
+    object* g = new_object(c, T_POINTSET, xf, flags, rc);
+    g->display_edges = (flags & PTB_OBJ_DISPLAY_EDGES) != 0;
+    g->np = n;
+    g->pt_pos = (vec*)malloc(sizeof(vec) * (size_t)n); g->pt_nrm = (vec*)malloc(sizeof(vec) * (size_t)n);
+    g->pt_col = p->colors ? (vec*)malloc(sizeof(vec) * (size_t)n) : NULL;
+    g->pt_rad = (double*)malloc(sizeof(double) * (size_t)n); g->pt_perm = (int*)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        g->pt_pos[i] = V(p->points[3 * i], p->points[3 * i + 1], p->points[3 * i + 2]);
+        g->pt_nrm[i] = V(p->normals[3 * i], p->normals[3 * i + 1], p->normals[3 * i + 2]);
+        if (g->pt_col) g->pt_col[i] = V(p->colors[3 * i], p->colors[3 * i + 1], p->colors[3 * i + 2]);
+        g->pt_rad[i] = p->radii[i]; g->pt_perm[i] = i;
+    }
+    g->cap_nodes = 64; g->nodes = (bnode*)malloc(sizeof(bnode) * (size_t)g->cap_nodes); g->n_nodes = 0; g->bvh_depth = 0;
+    g->bvh_bbox = pts_bbox(g, 0, n);                                       /* build_bvh, 28-32 */
+    pts_bvh_recur(g, 0, 0, n, 0);
     if (out_id) *out_id = c->n_objs - 1;
     return PTB_OK;
 }
@@ -1632,7 +1773,8 @@ int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* ob
             camera_ray(c, 0, i, j, 0, 0, 0, 0, W, H, &ro, &rd);
             int hit = scene_hit(c, ro, rd, &P, &id, &t, &m, &tri, NULL);
             int32_t oid = -1, tid = -1;
-            if (hit) { oid = id; if (c->objs[id]->type == T_MESH && tri >= 0) tid = c->objs[id]->permuted[tri]; }
+            if (hit) { oid = id; if (c->objs[id]->type == T_MESH && tri >= 0) tid = c->objs[id]->permuted[tri];
+                       if (c->objs[id]->type == T_POINTSET && tri >= 0) tid = c->objs[id]->pt_perm[tri]; }
             if (obj_id) obj_id[(size_t)i * W + j] = oid;
             if (tri_id) tri_id[(size_t)i * W + j] = tid;
             if (tout) tout[(size_t)i * W + j] = hit ? t : -1.f;

@@ -16,7 +16,9 @@
 #include "prefix.h"
 #include "ptb200.h"
 
+#include <array>
 #include <chrono>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -32,6 +34,7 @@ struct ptb_ctx {
     double ms_build;
     long long n_tri;
     int frame = 0;
+    std::map<const Object*, std::vector<int>> pts_perm;   // PointSet: position after build_bvh -> index handed in (the reference keeps no such map)
 };
 
 static std::string g_create_err;
@@ -124,6 +127,42 @@ int ptb_add_plane(ptb_ctx* c, const float A[3], const float N[3], const ptb_xfor
     apply_flags(p, flags);
     apply_xform(p, xf, false);
     c->rt->s.addObject(p);
+    if (out_id) *out_id = (int)c->rt->s.objects.size() - 1;
+    return PTB_OK;
+}
+
+int ptb_add_pointset(ptb_ctx* c, const ptb_pointset* p, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !p || !p->points || !p->normals || !p->radii || p->n <= 0) return PTB_ERR_INVALID;
+    PointSet* ps = new PointSet();                       // what PointSet::init leaves behind, without its file reader / estimate_normals
+    const int n = p->n;
+    ps->nbcols = 0; ps->is_centered = false;
+    Vector center(0., 0., 0.);
+    std::map<std::array<float, 7>, std::vector<int>> where;
+    for (int i = 0; i < n; i++) {
+        ps->vertices.push_back(Vector(p->points[3 * i], p->points[3 * i + 1], p->points[3 * i + 2]));
+        ps->normals.push_back(Vector(p->normals[3 * i], p->normals[3 * i + 1], p->normals[3 * i + 2]));
+        if (p->colors) ps->colors.push_back(Vector(p->colors[3 * i], p->colors[3 * i + 1], p->colors[3 * i + 2]));
+        else ps->colors.push_back(Vector(0.5, 0.5, 0.5));     // build_bvh_recur swaps colors[i] unconditionally; 0.5 grey is the `colors.size() > i` fallback's value
+        ps->radius.push_back(p->radii[i]);
+        center += ps->vertices[i];
+        where[{p->points[3 * i], p->points[3 * i + 1], p->points[3 * i + 2], p->normals[3 * i], p->normals[3 * i + 1], p->normals[3 * i + 2], p->radii[i]}].push_back(i);
+    }
+    center = center / (float)n;
+    ps->rotation_center = center;                        // PointSet.h:113-121
+    ps->name = "in-memory";
+    ps->build_bvh(0, n);
+    std::vector<int>& perm = c->pts_perm[ps];
+    perm.resize(n);
+    for (int j = 0; j < n; j++) {
+        std::vector<int>& v = where[{(float)ps->vertices[j][0], (float)ps->vertices[j][1], (float)ps->vertices[j][2], (float)ps->normals[j][0], (float)ps->normals[j][1],
+                                     (float)ps->normals[j][2], (float)ps->radius[j]}];
+        perm[j] = v.empty() ? -1 : v.back();
+        if (!v.empty()) v.pop_back();
+    }
+    apply_flags(ps, flags);
+    ps->display_edges = (flags & PTB_OBJ_DISPLAY_EDGES) != 0;
+    apply_xform(ps, xf, false);
+    c->rt->s.addObject(ps);
     if (out_id) *out_id = (int)c->rt->s.objects.size() - 1;
     return PTB_OK;
 }
@@ -403,6 +442,8 @@ int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* ob
                 oid = id;
                 TriMesh* g = rt->s.castToMesh[id];
                 if (g && tri >= 0) tid = g->permuted_triangle_index[tri];
+                auto it = c->pts_perm.find(rt->s.objects[id]);
+                if (it != c->pts_perm.end() && tri >= 0 && tri < (int)it->second.size()) tid = it->second[tri];
             }
             if (obj_id) obj_id[(size_t)i * W + j] = oid;
             if (tri_id) tri_id[(size_t)i * W + j] = tid;

@@ -11,7 +11,7 @@ import numpy as np
 
 OK = 0
 SLOT_KD, SLOT_KS, SLOT_NE, SLOT_TRANSP, SLOT_REFR, SLOT_NORMAL, SLOT_ALPHA, SLOT_KSUB = (1 << i for i in range(8))
-OBJ_MIRROR, OBJ_FLIP_NORMALS, OBJ_FLAT_NORMALS, OBJ_GHOST = 1, 2, 4, 8
+OBJ_MIRROR, OBJ_FLIP_NORMALS, OBJ_FLAT_NORMALS, OBJ_GHOST, OBJ_DISPLAY_EDGES = 1, 2, 4, 8, 16
 BRDF_PHONG, BRDF_MERL = 0, 1
 KEY_SCALE, KEY_TRANSLATION, KEY_ROTATION = 0, 1, 2
 OPT_COUNT_TRAVERSAL, OPT_POOL_PATHS, OPT_TIME_KERNELS, OPT_REFILL_BELOW, OPT_TRACE_BLOCKS, OPT_TRI_FRACTION, OPT_TRI_MIN_PCT, OPT_SORT_HITS, OPT_PIPES = 1, 2, 3, 4, 5, 6, 7, 8, 9
@@ -55,6 +55,10 @@ class Mesh(C.Structure):
                 ("scaling", C.c_float), ("offset", C.c_float * 3), ("center", C.c_int32)]
 
 
+class PointSetDesc(C.Structure):
+    _fields_ = [("points", _fp), ("normals", _fp), ("radii", _fp), ("colors", _fp), ("n", C.c_int32)]
+
+
 class Camera(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("direction", C.c_float * 3), ("up", C.c_float * 3),
                 ("fov", C.c_float), ("focus_distance", C.c_float), ("aperture", C.c_float)]
@@ -94,7 +98,7 @@ class KernelTimes(C.Structure):
 
 
 # every symbol include/ptb200.h declares (tests check the product library exports all of them)
-SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_cylinder", "add_mesh",
+SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_cylinder", "add_pointset", "add_mesh",
            "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "set_fog", "set_background", "set_keyframes", "set_frame", "commit", "render",
            "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
            "set_option", "get_scene_info", "kat", "get_kernel_times", "render_denoiser_inputs", "progressive_begin", "progressive_pass",
@@ -195,6 +199,7 @@ class Lib:
             "add_sphere": (C.c_int, [vp, _fp, C.c_float, C.POINTER(Xform), C.c_int, ip]),
             "add_plane": (C.c_int, [vp, _fp, _fp, C.POINTER(Xform), C.c_int, ip]),
             "add_cylinder": (C.c_int, [vp, _fp, _fp, C.c_float, C.POINTER(Xform), C.c_int, ip]),
+            "add_pointset": (C.c_int, [vp, C.POINTER(PointSetDesc), C.POINTER(Xform), C.c_int, ip]),
             "add_mesh": (C.c_int, [vp, C.POINTER(Mesh), C.POINTER(Xform), C.c_int, ip]),
             "set_group_material": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(Material)]),
             "set_brdf": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),

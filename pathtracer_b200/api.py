@@ -180,7 +180,8 @@ class Object:
 
     def _flags(self):
         return ((_abi.OBJ_MIRROR if self.miroir else 0) | (_abi.OBJ_FLIP_NORMALS if self.flip_normals else 0)
-                | (0 if self.interp_normals else _abi.OBJ_FLAT_NORMALS) | (_abi.OBJ_GHOST if self.ghost else 0))
+                | (0 if self.interp_normals else _abi.OBJ_FLAT_NORMALS) | (_abi.OBJ_GHOST if self.ghost else 0)
+                | (_abi.OBJ_DISPLAY_EDGES if getattr(self, "display_edges", False) else 0))
 
     def _xform(self):
         x = _abi.Xform()
@@ -214,6 +215,20 @@ class Cylinder(Object):
         super().__init__()
         self.A, self.B, self.R = np.array(A, np.float32), np.array(B, np.float32), float(R)
         self.miroir = mirror
+
+
+class PointSet(Object):
+    """PointSet.h / PointSet.cpp as the object stands after init: every point a disc (centre, normal, radius, colour).  The
+    reference fills normals and radii with estimate_normals (k-NN + PCA, PointSet.h:124-176); here they are given."""
+
+    def __init__(self, points, normals, radii, colors=None, mirror=False, normal_swapped=False, display_edges=False):
+        super().__init__()
+        self.points, self.normals = f32(points).reshape(-1, 3), f32(normals).reshape(-1, 3)
+        self.radii = f32(radii).reshape(-1)
+        self.colors = None if colors is None else f32(colors).reshape(-1, 3)
+        assert len(self.points) == len(self.normals) == len(self.radii) and (self.colors is None or len(self.colors) == len(self.points))
+        self.miroir, self.flip_normals, self.display_edges = mirror, normal_swapped, display_edges
+        self.rotation_center = np.full(3, np.nan, np.float32)      # init: the mean of the points
 
 
 class TriMesh(Object):
@@ -466,6 +481,9 @@ class Raytracer:
                 L.check(L.add_sphere(ctx, fptr(f32(o.O)), o.R, C.byref(xf), o._flags(), C.byref(oid)), ctx)
             elif isinstance(o, Plane):
                 L.check(L.add_plane(ctx, fptr(f32(o.A)), fptr(f32(o.vecN)), C.byref(xf), o._flags(), C.byref(oid)), ctx)
+            elif isinstance(o, PointSet):
+                d = _abi.PointSetDesc(fptr(o.points), fptr(o.normals), fptr(o.radii), fptr(o.colors), len(o.points))
+                L.check(L.add_pointset(ctx, C.byref(d), C.byref(xf), o._flags(), C.byref(oid)), ctx)
             elif isinstance(o, Cylinder):
                 L.check(L.add_cylinder(ctx, fptr(f32(o.A)), fptr(f32(o.B)), o.R, C.byref(xf), o._flags(), C.byref(oid)), ctx)
             elif isinstance(o, TriMesh):

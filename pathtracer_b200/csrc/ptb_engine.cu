@@ -51,8 +51,9 @@ using namespace ptb;
 #define PTB_BRANCH_MAX_LEVELS 512
 #define PTB_MAX_PIPES 4
 #ifndef PTB_TRACE_MINB
-#define PTB_TRACE_MINB 0    /* > 0: force the register allocation of k_trace to allow this many resident blocks per SM (A/B only: a forced 9
-                               costs 2 % by itself, profiles/r02e_ab_exact_variants.txt); the kernel compiles to 56 registers = 9 blocks unforced */
+#define PTB_TRACE_MINB 9    /* resident k_trace blocks per SM the register allocation must allow (9 x 128 threads x 56 registers).  Without the
+                               bound the out-of-line tri_exact call makes ptxas pick 64-72 registers = 8 blocks, which measured slower
+                               (profiles/r02g_ab_exact_deferred.txt); 0 = unforced */
 #endif
 #ifndef PTB_SMEM_STACK
 #define PTB_SMEM_STACK 0   /* entries of k_trace's traversal stack held in shared memory (A/B: profiles/r02a_ab_smem_stack.txt) */
@@ -85,7 +86,9 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev sc, FrameDev f, PoolDev
 // ANY_HIT = shadow rays (queue = shadow entries, first accepted triangle ends the ray; an unoccluded ray adds its deferred
 // direct term to the path's radiance).  Closest-hit results overwrite the analytic hit record the ray's producer wrote.
 template <bool ANY_HIT, bool COUNT, bool BRANCH = false>
-#if PTB_TRACE_MINB > 0
+#if defined(PTB_TRACE_MAXNREG)
+__global__ void __maxnreg__(PTB_TRACE_MAXNREG) k_trace(
+#elif PTB_TRACE_MINB > 0
 __global__ void __launch_bounds__(128, PTB_TRACE_MINB) k_trace(
 #else
 __global__ void __launch_bounds__(128) k_trace(
@@ -107,6 +110,7 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
 #endif
     const uint32_t n = count ? *count : (uint32_t)n_static;
     const AlphaCtx ac = alpha_ctx(sc);
+    const bool has_discs = sc.has_discs != 0;      // uniform: point-set discs always take the deferred route (tri_exact)
     const F4* __restrict__ nodes = sc.nodes;
     const F4* __restrict__ tris = sc.tris;
     bool live = false, exhausted = false;
@@ -262,9 +266,9 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                     c.x = l2.x; c.y = l2.y; c.z = l2.z; c.w = l2.w;
                     if (COUNT) ct++;
                     float t, b1, b2;
-                    const int res = tri_test_classify(a, b, c, r, tbest, t, b1, b2);
+                    const int res = (has_discs && (f2u(a.w) & PTB_TRI_FLAG_DISC)) ? 2 : tri_test_classify(a, b, c, r, tbest, t, b1, b2);
                     if (res == 2) {            // near an edge / alpha-tested: deferred to the pop branch (tri_exact)
-                        U2 e; e.x = prim | ((f2u(a.w) & 3u) << 28); e.y = 0;
+                        U2 e; e.x = prim | ((f2u(a.w) & 7u) << 28); e.y = 0;
                         if (sp < PTB_STACK) PTB_STK_PUSH(e);
                     } else if (res == 1) {
 #if PTB_EDGE_EPS_ON
@@ -415,6 +419,7 @@ __device__ __forceinline__ V3 xf_point_rn(const float* m, V3 v) {
 __global__ void __launch_bounds__(256) k_refit_tris(const F4* __restrict__ tris_obj, const ObjectDev* __restrict__ objects, F4* tris, size_t n_tri) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_tri) return;
+    if (f2u(tris[3 * k].w) & PTB_TRI_FLAG_DISC) return;          // discs are tested in object space: nothing world-space to update
     const F4 A = tris_obj[3 * k], B = tris_obj[3 * k + 1], C = tris_obj[3 * k + 2];
     const float* m = objects[f2u(A.w)].trans;
     const V3 v0 = xf_point_rn(m, v3(A.x, A.y, A.z)), v1 = xf_point_rn(m, v3(B.x, B.y, B.z)), v2 = xf_point_rn(m, v3(C.x, C.y, C.z));
@@ -455,6 +460,13 @@ __global__ void __launch_bounds__(128) k_refit_level(Node8* nodes, F4* node_box,
             for (uint32_t t = t0; t < t0 + cnt; t++) {
                 const F4 A = tris_obj[3 * (size_t)t];
                 const float* m = objects[f2u(A.w)].trans;
+                if (objects[f2u(A.w)].type == OBJ_POINTSET) {      // a disc: the cube centre +- radius x scale (the builder's box)
+                    const V3 w = xf_point_rn(m, v3(A.x, A.y, A.z));
+                    const float rr = tris_obj[3 * (size_t)t + 1].w * sqrtf(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]) * 1.0001f;
+                    lo[s][0] = fminf(lo[s][0], w.x - rr); lo[s][1] = fminf(lo[s][1], w.y - rr); lo[s][2] = fminf(lo[s][2], w.z - rr);
+                    hi[s][0] = fmaxf(hi[s][0], w.x + rr); hi[s][1] = fmaxf(hi[s][1], w.y + rr); hi[s][2] = fmaxf(hi[s][2], w.z + rr);
+                    continue;
+                }
                 for (int c = 0; c < 3; c++) {
                     const F4 P = c == 0 ? A : tris_obj[3 * (size_t)t + c];
                     const V3 w = xf_point_rn(m, v3(P.x, P.y, P.z));
@@ -949,6 +961,16 @@ int ptb_add_cylinder(ptb_ctx* c, const float A[3], const float B[3], float R, co
     const int id = c->host.add_cylinder(A, B, R, xf, flags);
     if (out_id) *out_id = id;
     return PTB_OK;
+}
+int ptb_add_pointset(ptb_ctx* c, const ptb_pointset* ps, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c) return PTB_ERR_INVALID;
+    if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
+    PTB_GUARD(c, {
+        const int id = c->host.add_pointset(ps, xf, flags, c->err);
+        if (id < 0) return id;
+        if (out_id) *out_id = id;
+        return PTB_OK;
+    })
 }
 int ptb_add_mesh(ptb_ctx* c, const ptb_mesh* m, const ptb_xform* xf, int flags, int* out_id) {
     if (!c) return PTB_ERR_INVALID;

@@ -36,6 +36,7 @@ struct HostObject {
     // mesh data AFTER TriMesh::init processing (object space)
     std::vector<float> vertices, normals, uvs, tangents;   // tangents: per vertex
     std::vector<int32_t> tri;              // n x 10
+    std::vector<float> pt_pos, pt_nrm, pt_rad, pt_col;     // point set (PointSet::vertices / normals / radius / colors)
     float trans[12], inv_trans[12], rot[9];
     KeyTrack keys[3];                      // PTB_KEY_SCALE / _TRANSLATION / _ROTATION (Geometry.h:318-320)
 };
@@ -85,6 +86,7 @@ struct HostScene {
     int add_plane(const float A[3], const float N[3], const ptb_xform* xf, int flags);
     int add_cylinder(const float A[3], const float B[3], float R, const ptb_xform* xf, int flags);
     int add_mesh(const ptb_mesh* m, const ptb_xform* xf, int flags, std::string& err);
+    int add_pointset(const ptb_pointset* p, const ptb_xform* xf, int flags, std::string& err);
     int set_group_material(int obj, int group, const ptb_material* m, std::string& err);
     int flatten(FlatScene& out, std::string& err);
     // Scene::prepare_render at another frame for an already flattened scene: every object's matrices (build_matrix(current_frame)) and
@@ -103,12 +105,13 @@ inline void scene_header(SceneDev& sc, FlatScene& f) {
     sc.envmap_intensity = f.envmap_intensity; sc.lightPower = f.lightPower; sc.radiusLight = f.radiusLight;
     sc.centerLight = v3(f.centerLight[0], f.centerLight[1], f.centerLight[2]);
     sc.n_inline = 0; sc.n_extra = 0;
-    sc.has_ghost = 0;
+    sc.has_ghost = 0; sc.has_discs = 0;
     sc.has_sss = f.has_sss ? 1 : 0;
     for (size_t i = 0; i < f.objects.size(); i++) {
         ObjectDev& o = f.objects[i];
         if (o.flags & FLAG_GHOST) sc.has_ghost = 1;
-        if (o.type == OBJ_MESH) continue;
+        if (o.type == OBJ_POINTSET) sc.has_discs = 1;
+        if (o.type == OBJ_MESH || o.type == OBJ_POINTSET) continue;
         if (sc.n_inline < PTB_INLINE_ANALYTIC) {
             AnalyticDev& a = sc.analytic[sc.n_inline++];
             a.type = o.type | ((o.flags & FLAG_GHOST) ? PTB_ANALYTIC_GHOST : 0); a.id = (int32_t)i; a.R2 = o.R2;

@@ -16,8 +16,9 @@
 
 namespace ptb {
 
-enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2, OBJ_CYLINDER = 3 };
-enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4, FLAG_GHOST = 8, FLAG_NOT_INLINE = 1 << 16 };
+enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2, OBJ_CYLINDER = 3, OBJ_POINTSET = 4 };
+enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4, FLAG_GHOST = 8, FLAG_DISPLAY_EDGES = 16, FLAG_NOT_INLINE = 1 << 16 };
+#define PTB_GROUP_DISC (-2)   /* TriUV::group of a point-set disc (its TriShade holds normal, colour, centre, radius) */
 enum { SLOT_KD = 1, SLOT_KS = 2, SLOT_NE = 4, SLOT_TRANSP = 8, SLOT_REFR = 16, SLOT_NORMAL = 32, SLOT_ALPHA = 64, SLOT_KSUB = 128 };
 
 struct ObjectDev {          // Object / Sphere / Plane fields the path reads (Geometry.h:240-672, 849-1217)
@@ -80,7 +81,7 @@ struct SceneDev {
     V3 centerLight;
     int32_t n_inline, n_extra;  // analytic objects held inline below / left in `objects` (flag FLAG_NOT_INLINE)
     int32_t has_fog, has_ghost; // fog_density > 1e-8 (Raytracer.cpp:206) / any Object::ghost
-    int32_t has_sss, pad1;      // some mesh group carries a non-zero subsurface albedo Ksub (Raytracer.cpp:270)
+    int32_t has_sss, has_discs; // some mesh group carries a non-zero subsurface albedo Ksub (Raytracer.cpp:270)
     const float* background;    // Scene::background (Geometry.h:1365), bgW*bgH*3 floats, or null
     int32_t bgW, bgH;
     FogDev fog;
@@ -94,6 +95,17 @@ struct AlphaCtx {
     const float* texels;
     const F4* tris_obj;         // object-space corners, see SceneDev
 };
+
+PTB_HD V3 xf_point(const float* m, V3 v) {   // Object::apply_transformation (Geometry.h:362-368)
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3], m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7],
+              m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11]);
+}
+PTB_HD V3 xf_dir(const float* m, V3 v) {     // apply_rotation_scaling (369-375)
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+PTB_HD V3 xf_rot(const float* m, V3 v) {     // apply_rotation (376-382), 3x3
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
+}
 
 PTB_HD bool tri_exact_available(const AlphaCtx* c) { return c != nullptr && c->tris_obj != nullptr; }
 
@@ -109,6 +121,19 @@ PTB_EXACT_LINKAGE bool tri_exact(const AlphaCtx* c, int prim, V3 o, V3 d, float 
     const int obj = (int)f2u(qa.w);
 #endif
     const float* m = c->objects[obj].inv_trans;
+    if (c->objects[obj].type == OBJ_POINTSET) {
+        // Disk::intersection (Geometry.h:1110-1118) on the object-space ray (xf_dir / xf_point are the reference's own expressions;
+        // this path is not compared bit for bit): A = centre, B.xyz = normal, B.w = radius
+        const V3 dl = xf_dir(m, d), ol = xf_point(m, o);
+        const V3 ctr = v3(qa.x, qa.y, qa.z), N = v3(qb.x, qb.y, qb.z);
+        const float tt = dot(ctr - ol, N) / dot(dl, N);
+        if (tt < 0 || tt != tt) return false;
+        const V3 P = ol + tt * dl;
+        if (!(norm2(P - ctr) <= qb.w * qb.w)) return false;
+        if (!(tt < tbest)) return false;
+        t = tt; b1 = 0; b2 = 0;
+        return true;
+    }
     const V3 dl = v3(add_rn(add_rn(mul_rn(m[0], d.x), mul_rn(m[1], d.y)), mul_rn(m[2], d.z)), add_rn(add_rn(mul_rn(m[4], d.x), mul_rn(m[5], d.y)), mul_rn(m[6], d.z)),
                      add_rn(add_rn(mul_rn(m[8], d.x), mul_rn(m[9], d.y)), mul_rn(m[10], d.z)));
     const V3 ol = v3(add_rn(add_rn(add_rn(mul_rn(m[0], o.x), mul_rn(m[1], o.y)), mul_rn(m[2], o.z)), m[3]),
@@ -158,17 +183,6 @@ PTB_HD bool alpha_rejects(const AlphaCtx* c, int prim, float b1, float b2) {
     float v = add_rn(add_rn(mul_rn(tu.v0, alpha), mul_rn(tu.v1, b1)), mul_rn(tu.v2, b2));
     u = tex_wrap(u); v = tex_wrap(v);
     return tex_red(m.alpha, c->texels, u, v) < 0.5f;
-}
-
-PTB_HD V3 xf_point(const float* m, V3 v) {   // Object::apply_transformation (Geometry.h:362-368)
-    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3], m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7],
-              m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11]);
-}
-PTB_HD V3 xf_dir(const float* m, V3 v) {     // apply_rotation_scaling (369-375)
-    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
-}
-PTB_HD V3 xf_rot(const float* m, V3 v) {     // apply_rotation (376-382), 3x3
-    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
 }
 
 // Sphere::intersection roots (Geometry.h:943-962): object-space ray, non-unit direction
@@ -327,6 +341,23 @@ PTB_HD void surface_from_hit(const SceneDev& sc, V3 o, V3 d, const Hit& hit, int
         const TriShade ts = sc.tri_shade[id];
         s.object = tu.object_has_uv & 0x7fffffff;
         obp = &sc.objects[s.object];
+        if (tu.group == PTB_GROUP_DISC) {
+            // ---- PointSet::intersection's tail (PointSet.cpp:192-217): n0 = normal, t0 = colour, n1 = centre, n2[0] = radius ----
+            const V3 dl = xf_dir(obp->inv_trans, d), ol = xf_point(obp->inv_trans, o);
+            const V3 Pl = ol + hit.t * dl;
+            Nl = normalize(v3(ts.n0[0], ts.n0[1], ts.n0[2]));
+            query_material(sc, *obp, 0, 0.f, 0.f, s);
+            if (dot(Nl, dl) > 0 && !s.transp) Nl = -Nl;
+            if (obp->flags & FLAG_FLIP) Nl = -Nl;
+            s.Kd = v3(ts.t0[0], ts.t0[1], ts.t0[2]);
+            if (obp->flags & FLAG_DISPLAY_EDGES) {
+                const float r2 = norm2(Pl - v3(ts.n1[0], ts.n1[1], ts.n1[2]));
+                if ((double)r2 > (double)ts.n2[0] * (double)ts.n2[0] * 0.95 * 0.95) s.Kd = v3(0, 0, 0);
+            }
+            s.P = xf_point(obp->trans, Pl);
+            s.N = fast_normalize(xf_rot(obp->rot, Nl));
+            return;
+        }
         float beta = hit.b1, gamma = hit.b2;
         float alpha = 1.f - beta - gamma;
         const bool has_uv = tu.object_has_uv < 0;

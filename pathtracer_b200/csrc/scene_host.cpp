@@ -62,6 +62,22 @@ int HostScene::add_cylinder(const float A[3], const float B[3], float R, const p
     return (int)objects.size() - 1;
 }
 
+int HostScene::add_pointset(const ptb_pointset* p, const ptb_xform* xf, int flags, std::string& err) {
+    if (!p || !p->points || !p->normals || !p->radii || p->n <= 0) { err = "add_pointset: points, normals and radii are needed"; return PTB_ERR_INVALID; }
+    HostObject o;
+    o.type = OBJ_POINTSET; o.flags = flags;
+    const size_t n = (size_t)p->n;
+    o.pt_pos.assign(p->points, p->points + 3 * n); o.pt_nrm.assign(p->normals, p->normals + 3 * n); o.pt_rad.assign(p->radii, p->radii + n);
+    if (p->colors) o.pt_col.assign(p->colors, p->colors + 3 * n);
+    for (size_t i = 0; i < n; i++) if (!(o.pt_rad[i] >= 0.f)) { err = "add_pointset: negative or NaN radius"; return PTB_ERR_INVALID; }
+    float rc[3] = {0, 0, 0};      // PointSet::init: rotation_center = mean of the points, accumulated in float (PointSet.h:113-121)
+    for (size_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) rc[k] += o.pt_pos[3 * i + k];
+    for (int k = 0; k < 3; k++) rc[k] = rc[k] / (float)n;
+    take_xform(o, xf, rc);
+    objects.push_back(std::move(o));
+    return (int)objects.size() - 1;
+}
+
 static inline V3 V(const std::vector<float>& a, int i) { return v3(a[3 * (size_t)i], a[3 * (size_t)i + 1], a[3 * (size_t)i + 2]); }
 
 int HostScene::add_mesh(const ptb_mesh* m, const ptb_xform* xf, int flags, std::string& err) {
@@ -310,6 +326,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
         d.R = o.R; d.R2 = o.R * o.R; d.len = o.len;
         out.objects.push_back(d);
         if (o.type == OBJ_MESH) n_tri += (int64_t)o.tri.size() / 10;
+        if (o.type == OBJ_POINTSET) n_tri += (int64_t)o.pt_rad.size();
     }
     if (out.texels.size() >= (size_t)4294967295u) { err = "commit: texture pool exceeds 2^32 floats"; return PTB_ERR_UNSUPPORTED; }
     if (out.materials.empty()) out.materials.emplace_back();  // keep pointers valid
@@ -345,6 +362,19 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
         int64_t w = 0;
         for (int oi = 0; oi < (int)objects.size(); oi++) {
             const HostObject& o = objects[oi];
+            if (o.type == OBJ_POINTSET) {
+                // a disc enters the builder as three points spanning the cube centre +- radius (PointSet::build_bbox, PointSet.cpp:4-14)
+                const float sc_ = placement_at(o, current_frame).scale;
+                for (size_t i = 0; i < o.pt_rad.size(); i++) {
+                    const V3 cw = xf_point(o.trans, v3(o.pt_pos[3 * i], o.pt_pos[3 * i + 1], o.pt_pos[3 * i + 2]));
+                    const float r = o.pt_rad[i] * fabsf(sc_) * 1.0001f;
+                    float* v = &verts9[9 * (size_t)w];
+                    v[0] = cw.x - r; v[1] = cw.y - r; v[2] = cw.z - r; v[3] = cw.x + r; v[4] = cw.y + r; v[5] = cw.z + r; v[6] = cw.x; v[7] = cw.y; v[8] = cw.z;
+                    src[w].obj = oi; src[w].tri = (int)i; src[w].alpha = ALPHA_OPAQUE;
+                    w++;
+                }
+                continue;
+            }
             if (o.type != OBJ_MESH) continue;
             const int nt = (int)(o.tri.size() / 10);
             std::vector<AlphaSat> sats(o.groups.size());
@@ -388,6 +418,29 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
         for (int64_t k = 0; k < n_tri; k++) {
             const uint32_t in = order[k];
             const HostObject& o = objects[src[in].obj];
+            if (o.type == OBJ_POINTSET) {
+                const size_t i = (size_t)src[in].tri;
+                uint32_t fl = PTB_TRI_FLAG_DISC | ((o.flags & FLAG_GHOST) ? PTB_TRI_FLAG_GHOST : 0u);
+                F4 q;
+                q.x = q.y = q.z = 0; q.w = u2f(fl); out.tris[3 * (size_t)k] = q;            // never read as a triangle: the flag routes it to tri_exact
+                q.w = INFINITY; out.tris[3 * (size_t)k + 1] = q;
+                q.w = 0; out.tris[3 * (size_t)k + 2] = q;
+                q.x = o.pt_pos[3 * i]; q.y = o.pt_pos[3 * i + 1]; q.z = o.pt_pos[3 * i + 2]; q.w = u2f((uint32_t)src[in].obj); out.tris_obj[3 * (size_t)k] = q;
+                q.x = o.pt_nrm[3 * i]; q.y = o.pt_nrm[3 * i + 1]; q.z = o.pt_nrm[3 * i + 2]; q.w = o.pt_rad[i]; out.tris_obj[3 * (size_t)k + 1] = q;
+                q.x = q.y = q.z = q.w = 0; out.tris_obj[3 * (size_t)k + 2] = q;
+                TriUV tu; memset(&tu, 0, sizeof(tu));
+                tu.group = PTB_GROUP_DISC; tu.object_has_uv = src[in].obj;
+                out.tri_uv[k] = tu;
+                TriShade ts; memset(&ts, 0, sizeof(ts));
+                for (int c = 0; c < 3; c++) {
+                    ts.n0[c] = o.pt_nrm[3 * i + c]; ts.n1[c] = o.pt_pos[3 * i + c];
+                    ts.t0[c] = o.pt_col.empty() ? 0.5f : o.pt_col[3 * i + c];
+                }
+                ts.n2[0] = o.pt_rad[i];
+                ts.orig = (int32_t)i;
+                out.tri_shade[k] = ts;
+                continue;
+            }
             const int32_t* t = &o.tri[10 * (size_t)src[in].tri];
             const float* v = &verts9[9 * (size_t)in];
             const int group = t[9];

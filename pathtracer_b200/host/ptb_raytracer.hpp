@@ -114,6 +114,12 @@ struct Plane : Object {
     Vector A, vecN;
     Plane(const Vector& a, const Vector& n, bool mirror = false) : Object(OT_PLANE), A(a), vecN(n) { miroir = mirror; }
 };
+struct PointSet : Object {       // PointSet.h as it stands after init: one disc per point
+    std::vector<float> vertices, normals, colors;   // x3 (colors may stay empty: 0.5 grey)
+    std::vector<float> radius;
+    bool display_edges = false;
+    PointSet() : Object(OT_POINTSET) {}
+};
 struct Cylinder : Object {       // Geometry.h:731-846
     Vector A, B; float R;
     Cylinder(const Vector& a, const Vector& b, float r) : Object(OT_CYLINDER), A(a), B(b), R(r) {}
@@ -203,6 +209,13 @@ public:
             int id = -1;
             if (o.type == OT_SPHERE) { auto& sp = static_cast<Sphere&>(o); ck(ptb_add_sphere(ctx_, sp.O.v, sp.R, &xf, flags, &id)); }
             else if (o.type == OT_PLANE) { auto& pl = static_cast<Plane&>(o); ck(ptb_add_plane(ctx_, pl.A.v, pl.vecN.v, &xf, flags, &id)); }
+            else if (o.type == OT_POINTSET) {
+                auto& ps = static_cast<PointSet&>(o);
+                ptb_pointset d;
+                d.points = ps.vertices.data(); d.normals = ps.normals.data(); d.radii = ps.radius.data(); d.colors = ps.colors.empty() ? nullptr : ps.colors.data();
+                d.n = (int32_t)ps.radius.size();
+                ck(ptb_add_pointset(ctx_, &d, &xf, flags | (ps.display_edges ? PTB_OBJ_DISPLAY_EDGES : 0), &id));
+            }
             else if (o.type == OT_CYLINDER) { auto& cy = static_cast<Cylinder&>(o); ck(ptb_add_cylinder(ctx_, cy.A.v, cy.B.v, cy.R, &xf, flags, &id)); }
             else {
                 auto& g = static_cast<TriMesh&>(o);

@@ -9,7 +9,7 @@ import math
 
 import numpy as np
 
-from .api import Cylinder, Plane, Raytracer, Sphere, Texture, TriMesh
+from .api import Cylinder, Plane, PointSet, Raytracer, Sphere, Texture, TriMesh
 
 
 def displaced_torus(nv):
@@ -161,6 +161,44 @@ def config_cyl(lib, W=128, H=128, spp=8, nv=16, device=0):
     m.max_translation = m.max_translation + np.array([0, 0, 2], np.float32)
     m.set_material(0, **phong((.5, .5, .5), (.2, .2, .2), 50.0))
     rt.s.addObject(m)
+    return rt
+
+
+def torus_points(nv):
+    """The vertices of displaced_torus(nv) as an oriented point set in the state PointSet::init leaves: positions centred and
+    normalised to a unit extent, analytic normals, one radius per point from the local vertex spacing, colours from the position."""
+    v, n, uv, _ = displaced_torus(nv)
+    v, n = v.astype(np.float64), n.astype(np.float64)
+    lo, hi = v.min(0), v.max(0)
+    p = (v - (lo + hi) / 2) / (hi - lo).max()
+    grid = p.reshape(nv + 1, 2 * nv + 1, 3)
+    du = np.linalg.norm(np.diff(grid, axis=1, append=grid[:, -2:-1]), axis=-1)
+    dv = np.linalg.norm(np.diff(grid, axis=0, append=grid[-2:-1]), axis=-1)
+    rad = 0.75 * np.maximum(du, dv)
+    col = np.stack([0.25 + 0.7 * uv[:, 0], 0.3 + 0.6 * uv[:, 1], 0.9 - 0.6 * uv[:, 0]], -1)
+    keep = np.zeros((nv + 1, 2 * nv + 1), bool)
+    keep[:-1, :-1] = True                         # the seam rows / columns repeat the first ones: coincident discs would tie
+    keep = keep.reshape(-1)
+    return p[keep].astype(np.float32), n[keep].astype(np.float32), rad.reshape(-1)[keep].astype(np.float32), col[keep].astype(np.float32)
+
+
+def config_points(lib, W=128, H=128, spp=8, nv=40, device=0, display_edges=False):
+    """A PointSet (PointSet.cpp: discs in the object's own space, its colour per point, normals turned to the viewer) placed like the
+    GUI places a mesh, a second, mirror-flagged coarse one, next to a sphere that casts and receives shadows with them."""
+    rt = base(lib, W, H, spp, device=device)
+    ps = PointSet(*torus_points(nv), display_edges=display_edges)
+    ps.set_material(0, **phong((.5, .5, .5), (.15, .15, .15), 40.0))
+    ps.scale = 30.0
+    miny = float(ps.points[:, 1].min())
+    ps.max_translation = np.array([0, np.float32(-27.3) - np.float32(miny) * np.float32(30.0), 0], np.float32)
+    ps.mat_rotation = _rot(0.0, 0.6)
+    rt.s.addObject(ps)
+    small = PointSet(*torus_points(max(6, nv // 4))[:3], mirror=False, normal_swapped=True)
+    small.set_material(0, **phong((.5, .5, .5), 0.0, 1.0))
+    small.scale = 10.0
+    small.max_translation = np.array([-22, -20, 10], np.float32)
+    rt.s.addObject(small)
+    rt.s.addObject(Sphere((17, -21.3, 14), 6).set_material(0, **phong((.3, .8, .3), 0.3, 50.0)))
     return rt
 
 

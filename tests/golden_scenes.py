@@ -10,7 +10,9 @@ SCENES = {
     "C4": lambda L, **kw: scenes.config_C4(L, 48, 48, 2, nv=24, **kw),
     "C5": lambda L, **kw: scenes.config_C5(L, 64, 40, 1, nv=12, **kw),
     "NGAN": lambda L, **kw: scenes.config_ngan(L, 48, 48, 2, **kw),
-    "CYL": lambda L, **kw: scenes.config_cyl(L, 48, 48, 2, **kw),       # Cylinder objects (Geometry.h:731-846)     # Phong / Ngan material presets (mainApp.cpp:1499-1597)
+    "CYL": lambda L, **kw: scenes.config_cyl(L, 48, 48, 2, **kw),
+    "PTS": lambda L, **kw: scenes.config_points(L, 48, 48, 2, nv=24, **kw),                        # PointSet discs (PointSet.cpp)
+    "PTS_EDGES": lambda L, **kw: scenes.config_points(L, 48, 48, 2, nv=16, display_edges=True, **kw),       # Cylinder objects (Geometry.h:731-846)     # Phong / Ngan material presets (mainApp.cpp:1499-1597)
 }
 
 # getColor's branching modes: background photograph, ghost objects, participating medium
