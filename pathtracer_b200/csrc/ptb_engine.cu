@@ -45,15 +45,16 @@ using namespace ptb;
 #define PTB_CNT_DROPS (5 * (PTB_MAX_BOUNCES + 1) + 1)   // side branches that found the pool full
 #define PTB_CNT_PROBE (5 * (PTB_MAX_BOUNCES + 1) + 2)   // subsurface probes emitted at the current level
 #define PTB_CNT_SURF (5 * (PTB_MAX_BOUNCES + 1) + 3)    // [+ b] surface hits of bounce b (the queue k_sort_hits leaves for k_shade)
-#define PTB_N_COUNTERS (6 * (PTB_MAX_BOUNCES + 1) + 3)
+#define PTB_CNT_DEFER (6 * (PTB_MAX_BOUNCES + 1) + 3)   // [+ 2*b] / [+ 2*b + 1]: rays of bounce b (closest / any-hit) that left candidates for k_exact
+#define PTB_N_COUNTERS (8 * (PTB_MAX_BOUNCES + 1) + 3)
+#define PTB_DEFER_K 4    /* candidates a ray can leave for k_exact; a ray with more is re-traced there with the immediate exact test */
 // 64-bit totals: 0 closest rays, 1 shadow rays, 2/3 node visits / triangle tests of the closest-hit trace, 4/5 of the any-hit trace
 #define PTB_N_TOTALS 6
 #define PTB_BRANCH_MAX_LEVELS 512
 #define PTB_MAX_PIPES 4
 #ifndef PTB_TRACE_MINB
-#define PTB_TRACE_MINB 9    /* resident k_trace blocks per SM the register allocation must allow (9 x 128 threads x 56 registers).  Without the
-                               bound the out-of-line tri_exact call makes ptxas pick 64-72 registers = 8 blocks, which measured slower
-                               (profiles/r02g_ab_exact_deferred.txt); 0 = unforced */
+#define PTB_TRACE_MINB 0    /* > 0 forces the register allocation of k_trace to allow that many resident blocks per SM (A/B only: the kernel
+                               compiles to 56 registers = 9 blocks of 128 threads by itself, and a forced 9 measured 2 % slower) */
 #endif
 #ifndef PTB_SMEM_STACK
 #define PTB_SMEM_STACK 0   /* entries of k_trace's traversal stack held in shared memory (A/B: profiles/r02a_ab_smem_stack.txt) */
@@ -94,7 +95,8 @@ __global__ void __launch_bounds__(128, PTB_TRACE_MINB) k_trace(
 __global__ void __launch_bounds__(128) k_trace(
 #endif
 SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
-                                               int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below, int tri_den, int tri_min_pct) {
+                                               int n_static, uint32_t* cursor, unsigned long long* totals, int refill_below, int tri_den, int tri_min_pct,
+                                               uint32_t* defer_count) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
 #if !defined(PTB_NO_PICK_LUT)
@@ -135,6 +137,7 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
 #define PTB_STK_PUSH(e) do { lstack[sp++] = (e); } while (0)
 #define PTB_STK_POP(e) do { (e) = lstack[--sp]; } while (0)
 #endif
+    uint32_t ndef = 0;     // candidates this ray has left for k_exact (tri_test_classify case 2)
     uint32_t tvalid = 0;   // valid24 of the node the live triangle group came from (all ones for a group popped from the stack: compact bits)
     int sp = 0;
     ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
@@ -162,7 +165,7 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                     }
                     if (ok) {
                         r = ray_prep(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
-                        tbest = tmax; hprim = -1; sp = 0;
+                        tbest = tmax; hprim = -1; sp = 0; ndef = 0;
                         ngroup.x = 0; ngroup.y = 0x80000000u; tgroup.x = 0; tgroup.y = 0;
                         if (ANY_HIT) item = f2u(d.w);   // the path the shadow ray belongs to
                         live = true;
@@ -180,24 +183,17 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
             if (sp > 0) {
                 U2 e;
                 PTB_STK_POP(e);
-                if (e.y > 0x00ffffffu) ngroup = e;
-                else if (e.y != 0) { tgroup = e; tvalid = 0x00ffffffu; }
-#if PTB_EDGE_EPS_ON
-                else {
-                    // a deferred candidate (tri_test_classify case 2): the reference's own arithmetic decides it, here, where the
-                    // lane holds neither node nor triangle temporaries.  e.x = triangle | flags << 28
-                    const uint32_t prim = e.x & 0x0fffffffu, fl = e.x >> 28;
-                    float t, b1, b2;
-                    if (tri_exact(&ac, (int)prim, r.o, r.d, tbest, t, b1, b2)) {
-                        if (!((fl & PTB_TRI_FLAG_ALPHA) && alpha_rejects(&ac, (int)prim, b1, b2)) && !(ANY_HIT && (fl & PTB_TRI_FLAG_GHOST))) {
-                            tbest = t; hb1 = b1; hb2 = b2; hprim = (int32_t)prim;
-                            if (ANY_HIT) { live = false; sp = 0; if (BRANCH) shadow_settle_branch(p, (int)entry, item, true); }
-                        }
-                    }
-                }
-#endif
+                if (e.y > 0x00ffffffu) ngroup = e; else { tgroup = e; tvalid = 0x00ffffffu; }
             } else {
-                if (ANY_HIT && BRANCH) shadow_settle_branch(p, (int)entry, item, false);
+                // candidates left for k_exact: it finishes the ray (the nearest of them may beat the hit found here; a shadow ray is only
+                // unoccluded if none of them blocks it)
+                if (ndef) {
+                    const uint32_t qi = atomicAdd(defer_count, 1u);
+                    U2 dr; dr.x = ANY_HIT ? entry : item; dr.y = ndef;
+                    p.defer_rays[qi] = dr;
+                }
+                if (ANY_HIT && ndef) { /* k_exact delivers or settles */ }
+                else if (ANY_HIT && BRANCH) shadow_settle_branch(p, (int)entry, item, false);
                 else if (ANY_HIT) {   // unoccluded: deliver the deferred direct term (Raytracer.cpp:545-566)
                     const F4 c = p.sh_c[entry];
                     F4 L = p.radiance[item];
@@ -267,9 +263,9 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                     if (COUNT) ct++;
                     float t, b1, b2;
                     const int res = (has_discs && (f2u(a.w) & PTB_TRI_FLAG_DISC)) ? 2 : tri_test_classify(a, b, c, r, tbest, t, b1, b2);
-                    if (res == 2) {            // near an edge / alpha-tested: deferred to the pop branch (tri_exact)
-                        U2 e; e.x = prim | ((f2u(a.w) & 7u) << 28); e.y = 0;
-                        if (sp < PTB_STACK) PTB_STK_PUSH(e);
+                    if (res == 2) {            // near an edge / alpha-tested / a disc: left for k_exact (the reference's own arithmetic)
+                        if (ndef < PTB_DEFER_K) p.defer_prims[(size_t)(ANY_HIT ? entry : item) * PTB_DEFER_K + ndef] = prim | ((f2u(a.w) & 7u) << 28);
+                        ndef++;
                     } else if (res == 1) {
 #if PTB_EDGE_EPS_ON
                         if (!(ANY_HIT && (f2u(a.w) & PTB_TRI_FLAG_GHOST))) {     // (alpha-tested triangles always take the deferred route)
@@ -288,6 +284,54 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) { cn += __shfl_down_sync(FULL, cn, o); ct += __shfl_down_sync(FULL, ct, o); }
         if (lane == 0 && (cn | ct)) { atomicAdd(&totals[ANY_HIT ? 4 : 2], (unsigned long long)cn); atomicAdd(&totals[ANY_HIT ? 5 : 3], (unsigned long long)ct); }
+    }
+}
+
+// ---- k_exact: the candidates k_trace could not call (tri_test_classify case 2) ---------------------------------------------------------
+// A ray within PTB_EDGE_EPS (barycentric) of a triangle edge, an alpha-tested triangle or a point-set disc is decided by the
+// reference's own arithmetic (tri_exact, ptb_scene.h).  k_trace keeps that code out of its loop: it leaves up to PTB_DEFER_K candidates
+// per ray in `defer_prims` and the ray in `defer_rays`; here one thread finishes one such ray: the nearest accepted candidate replaces
+// the hit k_trace found if it is nearer (closest hit), or blocks the shadow ray, which otherwise delivers its direct term (any hit).
+// About one ray in two hundred comes through here; a ray that left more than PTB_DEFER_K candidates is re-traced with the immediate test.
+template <bool ANY_HIT, bool BRANCH>
+__global__ void __launch_bounds__(128) k_exact(SceneDev sc, PoolDev p, const uint32_t* __restrict__ defer_count) {
+    const uint32_t n = *defer_count;
+    const AlphaCtx ac = alpha_ctx(sc);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const U2 e = p.defer_rays[i];
+        const uint32_t ref = e.x, nd = e.y;
+        uint32_t item;
+        F4 o, d;
+        float tbest;
+        F4 best; best.x = best.y = best.z = best.w = 0;
+        if (ANY_HIT) { o = p.sh_o[ref]; d = p.sh_d[ref]; tbest = o.w; item = f2u(d.w); }
+        else { item = ref; o = p.ray_o[item]; d = p.ray_d[item]; best = p.hit[item]; tbest = best.x; }
+        const V3 ro = v3(o.x, o.y, o.z), rd = v3(d.x, d.y, d.z);
+        bool found = false;
+        if (nd > PTB_DEFER_K) {
+            Hit h;
+            if (traverse<ANY_HIT, false>(sc.nodes, sc.tris, &ac, ro, rd, tbest, h, nullptr)) { found = true; best.x = h.t; best.y = h.b1; best.z = h.b2; best.w = u2f((uint32_t)h.prim); }
+        } else {
+            for (uint32_t k = 0; k < nd; k++) {
+                const uint32_t w = p.defer_prims[(size_t)ref * PTB_DEFER_K + k], prim = w & 0x0fffffffu, fl = w >> 28;
+                float t, b1, b2;
+                if (!tri_exact(&ac, (int)prim, ro, rd, tbest, t, b1, b2)) continue;
+                if ((fl & PTB_TRI_FLAG_ALPHA) && alpha_rejects(&ac, (int)prim, b1, b2)) continue;
+                if (ANY_HIT && (fl & PTB_TRI_FLAG_GHOST)) continue;
+                tbest = t; found = true;
+                best.x = t; best.y = b1; best.z = b2; best.w = u2f(prim);
+                if (ANY_HIT) break;
+            }
+        }
+        if (ANY_HIT) {
+            if (BRANCH) shadow_settle_branch(p, (int)ref, item, found);
+            else if (!found) {   // unoccluded after all: deliver the deferred direct term (Raytracer.cpp:545-566)
+                const F4 c = p.sh_c[ref];
+                F4 L = p.radiance[item];
+                L.x += c.x; L.y += c.y; L.z += c.z;
+                p.radiance[item] = L;
+            }
+        } else if (found) p.hit[item] = best;
     }
 }
 
@@ -676,6 +720,7 @@ struct ptb_ctx {
     bool has_merl = false;
     int shade_minb_merl = 8;                   // the same for scenes with a MERL object (PTB_SHADE_MINB_MERL: 5, 6 or 8; measured r01m: 89.0 / 81.2 / 76.8 ms on C4)
     int shade_minb = 8;                        // k_shade variant (resident blocks/SM the compiler must allow); PTB_SHADE_MINB overrides for experiments
+    int exact_blocks = 148 * 2;                // grid of k_exact (it strides over the few rays that left candidates)
     int trace_blocks = 148 * 8;                // persistent grid of k_trace, set from the occupancy query in ptb_create
     int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
     int tri_min_pct = 25;                      // the triangle phase starts once this share of a warp's live lanes hold triangles
@@ -707,7 +752,7 @@ static void free_scene(ptb_ctx* c) {
 }
 static void free_pool(ptb_ctx* c) {
     void* ptrs[] = {c->pool.ray_o, c->pool.ray_d, c->pool.weight, c->pool.radiance, c->pool.hit, c->pool.rng, c->pool.pixel,
-                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1], c->d_queue_surf, c->pool.aov_n, c->pool.aov_kd, c->pool.root, c->pool.probe_o, c->pool.probe_d, c->pool.probe_x, c->pool.hit2};
+                    c->pool.sh_o, c->pool.sh_d, c->pool.sh_c, c->d_queue[0], c->d_queue[1], c->d_queue_surf, c->pool.aov_n, c->pool.aov_kd, c->pool.root, c->pool.probe_o, c->pool.probe_d, c->pool.probe_x, c->pool.hit2, c->pool.defer_prims, c->pool.defer_rays};
     for (void* p : ptrs) if (p) cudaFree(p);
     memset(&c->pool, 0, sizeof(c->pool));
     c->d_queue[0] = c->d_queue[1] = nullptr; c->d_queue_surf = nullptr;
@@ -744,6 +789,8 @@ static int ensure_pool(ptb_ctx* c, int64_t paths, bool aov = false, bool branch 
     CK(cudaMalloc((void**)&c->d_queue[0], n * sizeof(uint32_t)));
     CK(cudaMalloc((void**)&c->d_queue[1], n * sizeof(uint32_t)));
     CK(cudaMalloc((void**)&c->d_queue_surf, n * sizeof(uint32_t)));
+    CK(cudaMalloc((void**)&c->pool.defer_prims, n * PTB_DEFER_K * sizeof(uint32_t)));
+    CK(cudaMalloc((void**)&c->pool.defer_rays, n * sizeof(U2)));
     if (aov) {
         CK(cudaMalloc((void**)&c->pool.aov_n, n * sizeof(F4)));
         CK(cudaMalloc((void**)&c->pool.aov_kd, n * sizeof(F4)));
@@ -1126,6 +1173,8 @@ static PoolDev pool_slice(const PoolDev& p, size_t off) {
     if (s.rng) s.rng += off;
     if (s.pixel) s.pixel += off;
     if (s.root) s.root += off;
+    if (s.defer_prims) s.defer_prims += off * PTB_DEFER_K;
+    if (s.defer_rays) s.defer_rays += off;
     return s;
 }
 
@@ -1223,12 +1272,14 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         const int s = b & 1, ns = (b + 1) & 1;
                         uint32_t* cnt_q = c->d_counters + 2 * s; uint32_t* cnt_sh = c->d_counters + 2 * s + 1; uint32_t* cnt_next = c->d_counters + 2 * ns;
                         uint32_t* cur = c->d_counters + PTB_CNT_CUR + 2 * s; uint32_t* cnt_sq = c->d_counters + PTB_CNT_SQ + s;
+                        uint32_t* cnt_def = c->d_counters + PTB_CNT_DEFER + 2 * s;
                         if (b >= 1) {
                             CK(cudaMemsetAsync(cnt_next, 0, sizeof(uint32_t), c->stream));
                             if (b >= 2) {
                                 CK(cudaMemsetAsync(cnt_sh, 0, sizeof(uint32_t), c->stream));
                                 CK(cudaMemsetAsync(cur, 0, 2 * sizeof(uint32_t), c->stream));
                                 CK(cudaMemsetAsync(cnt_sq, 0, sizeof(uint32_t), c->stream));
+                                CK(cudaMemsetAsync(cnt_def, 0, 2 * sizeof(uint32_t), c->stream));
                             }
                             CK(cudaMemsetAsync(c->d_counters + PTB_CNT_PROBE, 0, sizeof(uint32_t), c->stream));
                         }
@@ -1238,10 +1289,11 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         const unsigned gs = (unsigned)((n_level + 127) / 128);
                         if (mesh) {
                             lt.begin(1 | (std::min(b, 63) << 8));
-                            if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, cur, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
-                            else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, cur, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                            if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, cur, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct, cnt_def);
+                            else k_trace<false, false><<<gt, 128, 0, c->stream>>>(c->sc, c->pool, q, cnt, n_paths, cur, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct, cnt_def);
+                            k_exact<false, false><<<c->exact_blocks, 128, 0, c->stream>>>(c->sc, c->pool, cnt_def);
                             lt.end();
-                            launches++;
+                            launches += 2;
                         }
                         lt.begin(2 | (std::min(b, 63) << 8));
 #define PTB_SHADE_BRANCH(M, GRID, Q, CNT, NSTATIC, RESUME) k_shade_branch<M><<<GRID, 128, 0, c->stream>>>(c->sc, f, c->pool, Q, CNT, NSTATIC, c->d_queue[ns], cnt_next, cnt_sh, cnt_sq, \
@@ -1271,10 +1323,11 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         if (mesh && h_sh > 0) {
                             const unsigned ga = (unsigned)std::max(1, std::min<int>(c->trace_blocks, (int)((h_sh + 127) / 128)));
                             lt.begin(3 | (std::min(b, 63) << 8));
-                            if (c->count_traversal) k_trace<true, true, true><<<ga, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, cnt_sh, 0, cur + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
-                            else k_trace<true, false, true><<<ga, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, cnt_sh, 0, cur + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                            if (c->count_traversal) k_trace<true, true, true><<<ga, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, cnt_sh, 0, cur + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct, cnt_def + 1);
+                            else k_trace<true, false, true><<<ga, 128, 0, c->stream>>>(c->sc, c->pool, nullptr, cnt_sh, 0, cur + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct, cnt_def + 1);
+                            k_exact<true, true><<<c->exact_blocks, 128, 0, c->stream>>>(c->sc, c->pool, cnt_def + 1);
                             lt.end();
-                            launches++;
+                            launches += 2;
                         }
                         branch_closest += b == 0 ? valid_here * (unsigned long long)f.spp_pass : (unsigned long long)n_level;
                         branch_shadow += h_sq;
@@ -1297,10 +1350,11 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     const unsigned gt = (unsigned)std::max(1, std::min<int>(n_pipes > 1 ? c->trace_blocks_piped : c->trace_blocks, (n_paths + 127) / 128));
                     if (mesh) {
                         lt.begin(1 | (b << 8), ps);
-                        if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, ps>>>(c->sc, pp, q, cnt, n_paths, pc + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
-                        else k_trace<false, false><<<gt, 128, 0, ps>>>(c->sc, pp, q, cnt, n_paths, pc + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                        if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, ps>>>(c->sc, pp, q, cnt, n_paths, pc + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct, pc + PTB_CNT_DEFER + 2 * b);
+                        else k_trace<false, false><<<gt, 128, 0, ps>>>(c->sc, pp, q, cnt, n_paths, pc + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct, pc + PTB_CNT_DEFER + 2 * b);
+                        k_exact<false, false><<<c->exact_blocks, 128, 0, ps>>>(c->sc, pp, pc + PTB_CNT_DEFER + 2 * b);
                         lt.end();
-                        launches++;
+                        launches += 2;
                     }
                     lt.begin(2 | (b << 8), ps);
                     // optional: terminal hits (miss / light / dome) shaded by a compaction pass, k_shade sees surface hits only (off: measured slower)
@@ -1322,10 +1376,11 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     launches++;
                     if (mesh) {
                         lt.begin(3 | (b << 8), ps);
-                        if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, ps>>>(c->sc, pp, nullptr, pc + 2 * b + 1, 0, pc + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
-                        else k_trace<true, false><<<gt, 128, 0, ps>>>(c->sc, pp, nullptr, pc + 2 * b + 1, 0, pc + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct);
+                        if (c->count_traversal) k_trace<true, true><<<gt, 128, 0, ps>>>(c->sc, pp, nullptr, pc + 2 * b + 1, 0, pc + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct, pc + PTB_CNT_DEFER + 2 * b + 1);
+                        else k_trace<true, false><<<gt, 128, 0, ps>>>(c->sc, pp, nullptr, pc + 2 * b + 1, 0, pc + PTB_CNT_CUR + 2 * b + 1, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct, pc + PTB_CNT_DEFER + 2 * b + 1);
+                        k_exact<true, false><<<c->exact_blocks, 128, 0, ps>>>(c->sc, pp, pc + PTB_CNT_DEFER + 2 * b + 1);
                         lt.end();
-                        launches++;
+                        launches += 2;
                     }
                 }
                 lt.begin(4, ps);

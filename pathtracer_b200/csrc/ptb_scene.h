@@ -447,6 +447,8 @@ struct PoolDev {
     F4* probe_o;      // subsurface probes (entry-indexed): xyz origin, w = tmax
     F4* probe_d;      // xyz axis, w = path slot bits
     F4* probe_x;      // x,y = pcg32 state of the probe's own stream (lo, hi), z = object id bits
+    uint32_t* defer_prims;  // PTB_DEFER_K per ray (closest: path slot, any hit: shadow entry): triangle | flags << 28 left for k_exact
+    U2* defer_rays;         // queue of the rays that left some: {path slot or shadow entry, how many}
     F4* hit2;         // slot-indexed: the probe's answer t, b1, b2, prim bits (prim -1: nothing found)
 };
 

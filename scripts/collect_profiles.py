@@ -68,6 +68,7 @@ def traffic(tag, rep):
         r = rows.get(metric)
         xs = [float(r[2 + i]) for i, n in enumerate(names) if "k_trace<0" in n] if r else []
         return sum(xs) / len(xs) if xs else None
+    keep_shade = d.get(w, {}).get("shade")
     d[w] = {"k_trace_closest_dram_bytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals), "ncu_ms_per_launch": sum(ms) / len(ms),
             # what bounds the kernel (the algorithmic-byte figure of bench.py is a model; these are the counters)
             "issue_active_pct": mean_of("smsp__issue_active.avg.pct_of_peak_sustained_active"),
@@ -77,8 +78,33 @@ def traffic(tag, rep):
             "l2_throughput_pct": mean_of("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
             "l1_hit_pct": mean_of("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": mean_of("lts__t_sector_hit_rate.pct"),
             "source": f"profiles/{tag}_k_trace_{w}.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, closest-hit launches of bounces 0 and 1 of one pass)"}
+    if keep_shade:
+        d[w]["shade"] = keep_shade
     json.dump(d, open(tpath, "w"), indent=1)
     print(w, d[w])
+
+
+def shade_record(tag, w, out):
+    """k_shade counters (mean over the captured launches: camera rays and the first bounce) -> roofline_traffic.json[w]["shade"]"""
+    rows = {r[0]: r for r in csv.reader(open(out))}
+    n = len(rows["Kernel Name"]) - 2
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    rd, wr = rows["dram__bytes_read.sum"], rows["dram__bytes_write.sum"]
+    mean = lambda m: (sum(float(rows[m][2 + i]) for i in range(n)) / n) if m in rows else None
+    tpath = os.path.join(PROF, "roofline_traffic.json")
+    d = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    d.setdefault(w, {})["shade"] = {
+        "dram_bytes_per_launch": sum(float(rd[2 + i]) * scale[rd[1]] + float(wr[2 + i]) * scale[wr[1]] for i in range(n)) / n, "launches_captured": n,
+        "ncu_ms_per_launch": mean("gpu__time_duration.sum"),
+        "issue_active_pct": mean("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "active_lanes_per_instruction": mean("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "fma_pipe_active_pct": mean("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+        "dram_throughput_pct": mean("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        "l2_throughput_pct": mean("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+        "l1_hit_pct": mean("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": mean("lts__t_sector_hit_rate.pct"),
+        "source": f"profiles/{tag}_k_shade_{w}.csv (ncu --set full, k_shade launches of bounces 0 and 1 of one pass)"}
+    json.dump(d, open(tpath, "w"), indent=1)
+    print(w, "shade", d[w]["shade"])
 
 
 def main():
@@ -89,7 +115,9 @@ def main():
         traffic(tag, p)
     for p in sorted(glob.glob(os.path.join(OUT, "prof_shade_*.ncu-rep"))):
         w = re.search(r"prof_shade_(\w+)\.ncu-rep", p).group(1)
-        subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), p, os.path.join(PROF, f"{tag}_k_shade_{w}.csv")], stdout=subprocess.DEVNULL, check=True)
+        out = os.path.join(PROF, f"{tag}_k_shade_{w}.csv")
+        subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), p, out], stdout=subprocess.DEVNULL, check=True)
+        shade_record(tag, w, out)
     with open(os.path.join(PROF, f"{tag}_bench.jsonl"), "w") as f:
         for p in sorted(glob.glob(os.path.join(OUT, "bench_*.json"))):
             for l in open(p):
