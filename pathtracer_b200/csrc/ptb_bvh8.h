@@ -43,7 +43,7 @@ static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 #define PTB_EDGE_EPS_ON 1      /* 0: the fast triangle test decides everything (A/B: profiles/r02d_ab_exact_edges.txt) */
 #endif
 #define PTB_TRI_FLAG_ALPHA 1u  /* tri.w0 bit: this triangle's group has an alpha map that can reject */
-#define PTB_TRI_FLAG_DISC 4u   /* tri.w0 bit: not a triangle but a disc of a point set (PointSet.cpp): always decided by prim_exact */
+#define PTB_TRI_FLAG_DISC 4u   /* tri.w0 bit: the triangle covers a disc of a point set (disc_cover_triangle, ptb_scene.h); tri_exact runs the disc test */
 #define PTB_TRI_FLAG_GHOST 2u  /* tri.w0 bit: the triangle belongs to a ghost object; shadow rays pass through it (Geometry.cpp:722) */
 
 struct Hit {
@@ -213,7 +213,6 @@ inline uint32_t node_hitmask(const F4& n0, const F4& n1, const F4& n2, const F4&
 
 // Möller–Trumbore on {v0,e1,e2}; two-sided; accepts b1,b2 >= 0, b1+b2 <= 1, 0 <= t < tbest.
 PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, float tbest, float& t, float& b1, float& b2, const AlphaCtx* ex, int prim) {
-    if (f2u(a.w) & PTB_TRI_FLAG_DISC) return tri_exact(ex, prim, r.o, r.d, tbest, t, b1, b2);
     const V3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
     const V3 pvec = cross(r.d, e2);
     const float det = dot(e1, pvec);

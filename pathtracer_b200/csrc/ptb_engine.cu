@@ -112,7 +112,6 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
 #endif
     const uint32_t n = count ? *count : (uint32_t)n_static;
     const AlphaCtx ac = alpha_ctx(sc);
-    const bool has_discs = sc.has_discs != 0;      // uniform: point-set discs always take the deferred route (tri_exact)
     const F4* __restrict__ nodes = sc.nodes;
     const F4* __restrict__ tris = sc.tris;
     bool live = false, exhausted = false;
@@ -137,7 +136,8 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
 #define PTB_STK_PUSH(e) do { lstack[sp++] = (e); } while (0)
 #define PTB_STK_POP(e) do { (e) = lstack[--sp]; } while (0)
 #endif
-    uint32_t ndef = 0;     // candidates this ray has left for k_exact (tri_test_classify case 2)
+    // candidates the ray has left for k_exact (tri_test_classify case 2) are counted in a register the variant has no other use for:
+    // `entry` for closest-hit rays, `hprim` for any-hit rays
     uint32_t tvalid = 0;   // valid24 of the node the live triangle group came from (all ones for a group popped from the stack: compact bits)
     int sp = 0;
     ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
@@ -165,7 +165,8 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                     }
                     if (ok) {
                         r = ray_prep(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
-                        tbest = tmax; hprim = -1; sp = 0; ndef = 0;
+                        tbest = tmax; hprim = ANY_HIT ? 0 : -1; sp = 0;
+                        if (!ANY_HIT) entry = 0;
                         ngroup.x = 0; ngroup.y = 0x80000000u; tgroup.x = 0; tgroup.y = 0;
                         if (ANY_HIT) item = f2u(d.w);   // the path the shadow ray belongs to
                         live = true;
@@ -187,12 +188,13 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
             } else {
                 // candidates left for k_exact: it finishes the ray (the nearest of them may beat the hit found here; a shadow ray is only
                 // unoccluded if none of them blocks it)
-                if (ndef) {
+                const uint32_t nd = ANY_HIT ? (uint32_t)hprim : entry;
+                if (PTB_EDGE_EPS_ON && nd) {
                     const uint32_t qi = atomicAdd(defer_count, 1u);
-                    U2 dr; dr.x = ANY_HIT ? entry : item; dr.y = ndef;
+                    U2 dr; dr.x = ANY_HIT ? entry : item; dr.y = nd;
                     p.defer_rays[qi] = dr;
                 }
-                if (ANY_HIT && ndef) { /* k_exact delivers or settles */ }
+                if (PTB_EDGE_EPS_ON && ANY_HIT && nd) { /* k_exact delivers or settles */ }
                 else if (ANY_HIT && BRANCH) shadow_settle_branch(p, (int)entry, item, false);
                 else if (ANY_HIT) {   // unoccluded: deliver the deferred direct term (Raytracer.cpp:545-566)
                     const F4 c = p.sh_c[entry];
@@ -262,18 +264,19 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                     c.x = l2.x; c.y = l2.y; c.z = l2.z; c.w = l2.w;
                     if (COUNT) ct++;
                     float t, b1, b2;
-                    const int res = (has_discs && (f2u(a.w) & PTB_TRI_FLAG_DISC)) ? 2 : tri_test_classify(a, b, c, r, tbest, t, b1, b2);
-                    if (res == 2) {            // near an edge / alpha-tested / a disc: left for k_exact (the reference's own arithmetic)
-                        if (ndef < PTB_DEFER_K) p.defer_prims[(size_t)(ANY_HIT ? entry : item) * PTB_DEFER_K + ndef] = prim | ((f2u(a.w) & 7u) << 28);
-                        ndef++;
+                    const int res = tri_test_classify(a, b, c, r, tbest, t, b1, b2);
+                    if (PTB_EDGE_EPS_ON && res == 2) {            // near an edge / alpha-tested / a disc: left for k_exact (the reference's own arithmetic)
+                        const uint32_t nd = ANY_HIT ? (uint32_t)hprim : entry;
+                        if (nd < PTB_DEFER_K) p.defer_prims[(size_t)(ANY_HIT ? entry : item) * PTB_DEFER_K + nd] = prim | ((f2u(a.w) & 7u) << 28);
+                        if (ANY_HIT) hprim++; else entry++;
                     } else if (res == 1) {
 #if PTB_EDGE_EPS_ON
                         if (!(ANY_HIT && (f2u(a.w) & PTB_TRI_FLAG_GHOST))) {     // (alpha-tested triangles always take the deferred route)
 #else
                         if (!((f2u(a.w) & PTB_TRI_FLAG_ALPHA) && alpha_rejects(&ac, (int)prim, b1, b2)) && !(ANY_HIT && (f2u(a.w) & PTB_TRI_FLAG_GHOST))) {
 #endif
-                            tbest = t; hb1 = b1; hb2 = b2; hprim = (int32_t)prim;
                             if (ANY_HIT) { live = false; tgroup.y = 0; if (BRANCH) shadow_settle_branch(p, (int)entry, item, true); }   // occluded: nothing to deliver
+                            else { tbest = t; hb1 = b1; hb2 = b2; hprim = (int32_t)prim; }
                         }
                     }
                 }
@@ -463,10 +466,14 @@ __device__ __forceinline__ V3 xf_point_rn(const float* m, V3 v) {
 __global__ void __launch_bounds__(256) k_refit_tris(const F4* __restrict__ tris_obj, const ObjectDev* __restrict__ objects, F4* tris, size_t n_tri) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_tri) return;
-    if (f2u(tris[3 * k].w) & PTB_TRI_FLAG_DISC) return;          // discs are tested in object space: nothing world-space to update
     const F4 A = tris_obj[3 * k], B = tris_obj[3 * k + 1], C = tris_obj[3 * k + 2];
-    const float* m = objects[f2u(A.w)].trans;
-    const V3 v0 = xf_point_rn(m, v3(A.x, A.y, A.z)), v1 = xf_point_rn(m, v3(B.x, B.y, B.z)), v2 = xf_point_rn(m, v3(C.x, C.y, C.z));
+    const ObjectDev& ob = objects[f2u(A.w)];
+    const float* m = ob.trans;
+    V3 v0, v1, v2;
+    if (ob.type == OBJ_POINTSET) {      // a disc: its covering triangle at the new pose (centre A, normal B.xyz, radius B.w)
+        const float sc_ = sqrtf(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]);
+        disc_cover_triangle(xf_point_rn(m, v3(A.x, A.y, A.z)), xf_rot(ob.rot, v3(B.x, B.y, B.z)), B.w * sc_, v0, v1, v2);
+    } else { v0 = xf_point_rn(m, v3(A.x, A.y, A.z)); v1 = xf_point_rn(m, v3(B.x, B.y, B.z)); v2 = xf_point_rn(m, v3(C.x, C.y, C.z)); }
     F4 q;
     q.x = v0.x; q.y = v0.y; q.z = v0.z; q.w = tris[3 * k].w; tris[3 * k] = q;                       // .w: the triangle's flags stay
     q.x = v1.x - v0.x; q.y = v1.y - v0.y; q.z = v1.z - v0.z; q.w = tris[3 * k + 1].w; tris[3 * k + 1] = q;   // .w: the edge threshold stays
@@ -504,11 +511,15 @@ __global__ void __launch_bounds__(128) k_refit_level(Node8* nodes, F4* node_box,
             for (uint32_t t = t0; t < t0 + cnt; t++) {
                 const F4 A = tris_obj[3 * (size_t)t];
                 const float* m = objects[f2u(A.w)].trans;
-                if (objects[f2u(A.w)].type == OBJ_POINTSET) {      // a disc: the cube centre +- radius x scale (the builder's box)
-                    const V3 w = xf_point_rn(m, v3(A.x, A.y, A.z));
-                    const float rr = tris_obj[3 * (size_t)t + 1].w * sqrtf(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]) * 1.0001f;
-                    lo[s][0] = fminf(lo[s][0], w.x - rr); lo[s][1] = fminf(lo[s][1], w.y - rr); lo[s][2] = fminf(lo[s][2], w.z - rr);
-                    hi[s][0] = fmaxf(hi[s][0], w.x + rr); hi[s][1] = fmaxf(hi[s][1], w.y + rr); hi[s][2] = fmaxf(hi[s][2], w.z + rr);
+                if (objects[f2u(A.w)].type == OBJ_POINTSET) {      // a disc: the box of its covering triangle
+                    const F4 Bq = tris_obj[3 * (size_t)t + 1];
+                    V3 q0, q1, q2;
+                    disc_cover_triangle(xf_point_rn(m, v3(A.x, A.y, A.z)), xf_rot(objects[f2u(A.w)].rot, v3(Bq.x, Bq.y, Bq.z)), Bq.w * sqrtf(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]), q0, q1, q2);
+                    const V3 qq[3] = {q0, q1, q2};
+                    for (int c = 0; c < 3; c++) {
+                        lo[s][0] = fminf(lo[s][0], qq[c].x); lo[s][1] = fminf(lo[s][1], qq[c].y); lo[s][2] = fminf(lo[s][2], qq[c].z);
+                        hi[s][0] = fmaxf(hi[s][0], qq[c].x); hi[s][1] = fmaxf(hi[s][1], qq[c].y); hi[s][2] = fmaxf(hi[s][2], qq[c].z);
+                    }
                     continue;
                 }
                 for (int c = 0; c < 3; c++) {

@@ -18,6 +18,19 @@ namespace ptb {
 
 enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2, OBJ_CYLINDER = 3, OBJ_POINTSET = 4 };
 enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4, FLAG_GHOST = 8, FLAG_DISPLAY_EDGES = 16, FLAG_NOT_INLINE = 1 << 16 };
+// A point-set disc sits in the BVH8 as the triangle circumscribed about it (in its plane, inscribed radius 1.1 r): every ray that can
+// hit the disc hits that triangle's interior, the threshold in its e1.w is +inf, so k_trace classifies it "left for k_exact" like a
+// near-edge candidate, with no disc code and no extra test in the traversal loop; k_exact runs the reference's disc test.
+PTB_HD void disc_cover_triangle(V3 c, V3 n, float r, V3& v0, V3& v1, V3& v2) {
+    const float nn = sqrtf(norm2(n));
+    const V3 z = nn > 0.f ? n / nn : v3(0, 0, 1);
+    const V3 a = fabsf(z.x) < 0.57f ? v3(1, 0, 0) : (fabsf(z.y) < 0.57f ? v3(0, 1, 0) : v3(0, 0, 1));
+    const V3 u = normalize(cross(z, a)), w = cross(z, u);
+    const float R = 2.2f * r;
+    v0 = c + R * w;
+    v1 = c + R * (-0.8660254f * u - 0.5f * w);
+    v2 = c + R * (0.8660254f * u - 0.5f * w);
+}
 #define PTB_GROUP_DISC (-2)   /* TriUV::group of a point-set disc (its TriShade holds normal, colour, centre, radius) */
 enum { SLOT_KD = 1, SLOT_KS = 2, SLOT_NE = 4, SLOT_TRANSP = 8, SLOT_REFR = 16, SLOT_NORMAL = 32, SLOT_ALPHA = 64, SLOT_KSUB = 128 };
 
@@ -447,9 +460,9 @@ struct PoolDev {
     F4* probe_o;      // subsurface probes (entry-indexed): xyz origin, w = tmax
     F4* probe_d;      // xyz axis, w = path slot bits
     F4* probe_x;      // x,y = pcg32 state of the probe's own stream (lo, hi), z = object id bits
+    F4* hit2;         // slot-indexed: the probe's answer t, b1, b2, prim bits (prim -1: nothing found)
     uint32_t* defer_prims;  // PTB_DEFER_K per ray (closest: path slot, any hit: shadow entry): triangle | flags << 28 left for k_exact
     U2* defer_rays;         // queue of the rays that left some: {path slot or shadow entry, how many}
-    F4* hit2;         // slot-indexed: the probe's answer t, b1, b2, prim bits (prim -1: nothing found)
 };
 
 struct FrameDev {     // per-render constants (Raytracer fields + prepare_render results)

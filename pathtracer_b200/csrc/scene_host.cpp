@@ -363,13 +363,15 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
         for (int oi = 0; oi < (int)objects.size(); oi++) {
             const HostObject& o = objects[oi];
             if (o.type == OBJ_POINTSET) {
-                // a disc enters the builder as three points spanning the cube centre +- radius (PointSet::build_bbox, PointSet.cpp:4-14)
+                // a disc enters the BVH as the triangle circumscribed about it (disc_cover_triangle, ptb_scene.h)
                 const float sc_ = placement_at(o, current_frame).scale;
                 for (size_t i = 0; i < o.pt_rad.size(); i++) {
                     const V3 cw = xf_point(o.trans, v3(o.pt_pos[3 * i], o.pt_pos[3 * i + 1], o.pt_pos[3 * i + 2]));
-                    const float r = o.pt_rad[i] * fabsf(sc_) * 1.0001f;
+                    const V3 nw = xf_rot(o.rot, v3(o.pt_nrm[3 * i], o.pt_nrm[3 * i + 1], o.pt_nrm[3 * i + 2]));
+                    V3 p0, p1, p2;
+                    disc_cover_triangle(cw, nw, o.pt_rad[i] * fabsf(sc_), p0, p1, p2);
                     float* v = &verts9[9 * (size_t)w];
-                    v[0] = cw.x - r; v[1] = cw.y - r; v[2] = cw.z - r; v[3] = cw.x + r; v[4] = cw.y + r; v[5] = cw.z + r; v[6] = cw.x; v[7] = cw.y; v[8] = cw.z;
+                    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p1.x; v[4] = p1.y; v[5] = p1.z; v[6] = p2.x; v[7] = p2.y; v[8] = p2.z;
                     src[w].obj = oi; src[w].tri = (int)i; src[w].alpha = ALPHA_OPAQUE;
                     w++;
                 }
@@ -422,9 +424,10 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
                 const size_t i = (size_t)src[in].tri;
                 uint32_t fl = PTB_TRI_FLAG_DISC | ((o.flags & FLAG_GHOST) ? PTB_TRI_FLAG_GHOST : 0u);
                 F4 q;
-                q.x = q.y = q.z = 0; q.w = u2f(fl); out.tris[3 * (size_t)k] = q;            // never read as a triangle: the flag routes it to tri_exact
-                q.w = INFINITY; out.tris[3 * (size_t)k + 1] = q;
-                q.w = 0; out.tris[3 * (size_t)k + 2] = q;
+                const float* v = &verts9[9 * (size_t)in];                                   // the covering triangle; e1.w = +inf: always left for k_exact
+                q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = u2f(fl); out.tris[3 * (size_t)k] = q;
+                q.x = v[3] - v[0]; q.y = v[4] - v[1]; q.z = v[5] - v[2]; q.w = INFINITY; out.tris[3 * (size_t)k + 1] = q;
+                q.x = v[6] - v[0]; q.y = v[7] - v[1]; q.z = v[8] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 2] = q;
                 q.x = o.pt_pos[3 * i]; q.y = o.pt_pos[3 * i + 1]; q.z = o.pt_pos[3 * i + 2]; q.w = u2f((uint32_t)src[in].obj); out.tris_obj[3 * (size_t)k] = q;
                 q.x = o.pt_nrm[3 * i]; q.y = o.pt_nrm[3 * i + 1]; q.z = o.pt_nrm[3 * i + 2]; q.w = o.pt_rad[i]; out.tris_obj[3 * (size_t)k + 1] = q;
                 q.x = q.y = q.z = q.w = 0; out.tris_obj[3 * (size_t)k + 2] = q;
