@@ -70,10 +70,11 @@ __global__ void __launch_bounds__(256) k_rpp(float* rpp, int n) {
     rpp[2 * p + 1] = y;
 }
 
+template <bool EXOTIC>
 __global__ void __launch_bounds__(256) k_raygen(SceneDev sc, FrameDev f, PoolDev p, int n_paths) {
     const int path = blockIdx.x * blockDim.x + threadIdx.x;
     if (path >= n_paths) return;
-    raygen_one(sc, f, p, path);
+    raygen_one<EXOTIC>(sc, f, p, path);
 }
 
 // ---- BVH8 traversal: persistent warps, dynamic ray fetch, postponed triangle tests -------------------------------------
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(256) k_sort_hits(SceneDev sc, PoolDev p, const
     if (surface) out_queue[qi] = (uint32_t)path;
 }
 
-template <bool MERL, int MINB, bool AOV>
+template <bool MERL, int MINB, bool AOV, bool EXOTIC = false>
 __global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
                                                const uint32_t* __restrict__ count, int n_static, uint32_t* __restrict__ next_queue,
                                                uint32_t* next_count, uint32_t* shadow_count, uint32_t* shadow_queries) {
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, Po
     int path = 0;
     if (tid < n) {
         path = queue ? (int)queue[tid] : tid;
-        shade_one<MERL, AOV>(sc, f, p, path, out);
+        shade_one<MERL, AOV, EXOTIC>(sc, f, p, path, out);
     }
     const uint32_t qi = warp_push(next_count, out.cont);
     if (out.cont) next_queue[qi] = (uint32_t)path;
@@ -1266,7 +1267,8 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                 uint32_t* const pc = c->d_counters + (size_t)pi * PTB_N_COUNTERS;
                 CK(cudaMemsetAsync(pc, 0, PTB_N_COUNTERS * sizeof(uint32_t), ps));
                 lt.begin(0, ps);
-                k_raygen<<<g256, 256, 0, ps>>>(c->sc, f, pp, n_paths);
+                if (c->sc.has_exotic) k_raygen<true><<<g256, 256, 0, ps>>>(c->sc, f, pp, n_paths);
+                else k_raygen<false><<<g256, 256, 0, ps>>>(c->sc, f, pp, n_paths);
                 lt.end();
                 launches++;
                 int levels = nb;
@@ -1377,12 +1379,19 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         launches++;
                     }
 #define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<g128, 128, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
+#define PTB_SHADE_X(M, MB, A) k_shade<M, MB, A, true><<<g128, 128, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
+                    if (c->sc.has_exotic) {      // scenes with Cylinder / PointSet objects: the kernels that carry their code (not register-squeezed)
+                        if (aov && b == 0) { if (c->has_merl) PTB_SHADE_X(true, 5, true); else PTB_SHADE_X(false, 6, true); }
+                        else if (c->has_merl) PTB_SHADE_X(true, 5, false);
+                        else PTB_SHADE_X(false, 6, false);
+                    } else
                     if (aov && b == 0) { if (c->has_merl) PTB_SHADE(true, 5, true); else PTB_SHADE(false, 6, true); }   // camera rays of a denoiser-input render
                     else if (c->has_merl) { if (c->shade_minb_merl == 8) PTB_SHADE(true, 8, false); else if (c->shade_minb_merl == 6) PTB_SHADE(true, 6, false); else PTB_SHADE(true, 5, false); }
                     else if (c->shade_minb == 8) PTB_SHADE(false, 8, false);
                     else if (c->shade_minb == 10) PTB_SHADE(false, 10, false);
                     else PTB_SHADE(false, 6, false);
 #undef PTB_SHADE
+#undef PTB_SHADE_X
                     lt.end();
                     launches++;
                     if (mesh) {

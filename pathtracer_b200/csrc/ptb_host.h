@@ -105,12 +105,12 @@ inline void scene_header(SceneDev& sc, FlatScene& f) {
     sc.envmap_intensity = f.envmap_intensity; sc.lightPower = f.lightPower; sc.radiusLight = f.radiusLight;
     sc.centerLight = v3(f.centerLight[0], f.centerLight[1], f.centerLight[2]);
     sc.n_inline = 0; sc.n_extra = 0;
-    sc.has_ghost = 0; sc.has_discs = 0;
+    sc.has_ghost = 0; sc.has_exotic = 0;
     sc.has_sss = f.has_sss ? 1 : 0;
     for (size_t i = 0; i < f.objects.size(); i++) {
         ObjectDev& o = f.objects[i];
         if (o.flags & FLAG_GHOST) sc.has_ghost = 1;
-        if (o.type == OBJ_POINTSET) sc.has_discs = 1;
+        if (o.type == OBJ_POINTSET || o.type == OBJ_CYLINDER) sc.has_exotic = 1;   // kernels with the Cylinder / PointSet code
         if (o.type == OBJ_MESH || o.type == OBJ_POINTSET) continue;
         if (sc.n_inline < PTB_INLINE_ANALYTIC) {
             AnalyticDev& a = sc.analytic[sc.n_inline++];

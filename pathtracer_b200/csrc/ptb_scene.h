@@ -94,7 +94,7 @@ struct SceneDev {
     V3 centerLight;
     int32_t n_inline, n_extra;  // analytic objects held inline below / left in `objects` (flag FLAG_NOT_INLINE)
     int32_t has_fog, has_ghost; // fog_density > 1e-8 (Raytracer.cpp:206) / any Object::ghost
-    int32_t has_sss, has_discs; // some mesh group carries a non-zero subsurface albedo Ksub (Raytracer.cpp:270)
+    int32_t has_sss, has_exotic; // some mesh group carries a non-zero subsurface albedo Ksub (Raytracer.cpp:270)
     const float* background;    // Scene::background (Geometry.h:1365), bgW*bgH*3 floats, or null
     int32_t bgW, bgH;
     FogDev fog;
@@ -254,6 +254,9 @@ PTB_HD int32_t hit_id_analytic(int obj) { return -2 - obj; }
 
 // Nearest hit over the analytic objects (Sphere / Plane) of Scene::intersection's loop (Geometry.cpp:601-626):
 // object-space rays, world t.  Meshes are handled by the wide BVH afterwards.
+// EXOTIC = the scene holds Cylinder or PointSet objects.  The kernels of the linear path are also compiled without their code
+// (EXOTIC = false; the benchmark configurations have none): it costs the 64-register k_shade spills otherwise (+3 %, profiles/r02j).
+template <bool EXOTIC = true>
 PTB_HD bool analytic_t(int type, const float* inv_trans, const float* A, const float* N, float R2, float len, V3 o, V3 d, float& t) {
     V3 dl, ol;
     if (type & PTB_ANALYTIC_LINEAR_ID) {   // uniform per object; same bits as the general form for m = [I | t]
@@ -263,9 +266,10 @@ PTB_HD bool analytic_t(int type, const float* inv_trans, const float* A, const f
         dl = xf_dir(inv_trans, d);
         ol = xf_point(inv_trans, o);
     }
-    if ((type & 0xff) == OBJ_CYLINDER) return cylinder_t(A, N, R2, len, ol, dl, t);
+    if (EXOTIC && (type & 0xff) == OBJ_CYLINDER) return cylinder_t(A, N, R2, len, ol, dl, t);
     return ((type & 0xff) == OBJ_SPHERE) ? sphere_t(A, R2, ol, dl, t) : plane_t(A, N, ol, dl, t);
 }
+template <bool EXOTIC = true>
 PTB_HD void analytic_closest(const SceneDev& sc, V3 o, V3 d, float& tmin, int32_t& id) {
     tmin = INFINITY;
     id = PTB_HIT_MISS;
@@ -274,32 +278,33 @@ PTB_HD void analytic_closest(const SceneDev& sc, V3 o, V3 d, float& tmin, int32_
     for (int i = 0; i < sc.n_inline; i++) {
         const AnalyticDev& ob = sc.analytic[i];
         float t;
-        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && t < tmin) { tmin = t; best = ob.id; }
+        if (analytic_t<EXOTIC>(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && t < tmin) { tmin = t; best = ob.id; }
     }
     if (sc.n_extra > 0)
         for (int i = 0; i < sc.n_objects; i++) {
             const ObjectDev& ob = sc.objects[i];
             if (ob.type == OBJ_MESH || !(ob.flags & FLAG_NOT_INLINE)) continue;
             float t;
-            if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && (t < tmin || (t == tmin && i < best))) { tmin = t; best = i; }
+            if (analytic_t<EXOTIC>(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && (t < tmin || (t == tmin && i < best))) { tmin = t; best = i; }
         }
     if (best >= 0) id = hit_id_analytic(best);
 }
 // Analytic part of Scene::intersection_shadow (Geometry.cpp:721-741): any object closer than 0.999*dist_light
+template <bool EXOTIC = true>
 PTB_HD bool analytic_occluded(const SceneDev& sc, V3 o, V3 d, float dist_light) {
     const double lim = (double)dist_light * 0.999;
     for (int i = 0; i < sc.n_inline; i++) {
         const AnalyticDev& ob = sc.analytic[i];
         if (ob.type & PTB_ANALYTIC_GHOST) continue;   // avoid_ghosts (Geometry.cpp:722)
         float t;
-        if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && (double)t < lim) return true;
+        if (analytic_t<EXOTIC>(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && (double)t < lim) return true;
     }
     if (sc.n_extra > 0)
         for (int i = 0; i < sc.n_objects; i++) {
             const ObjectDev& ob = sc.objects[i];
             if (ob.type == OBJ_MESH || !(ob.flags & FLAG_NOT_INLINE) || (ob.flags & FLAG_GHOST)) continue;
             float t;
-            if (analytic_t(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && (double)t < lim) return true;
+            if (analytic_t<EXOTIC>(ob.type, ob.inv_trans, ob.a, ob.n, ob.R2, ob.len, o, d, t) && (double)t < lim) return true;
         }
     return false;
 }
@@ -345,6 +350,7 @@ PTB_HD void query_material(const SceneDev& sc, const ObjectDev& ob, int group, f
 }
 
 // Rebuild the shading point of a hit: Object::intersection's material part + the tail of Scene::intersection.
+template <bool EXOTIC = true>
 PTB_HD void surface_from_hit(const SceneDev& sc, V3 o, V3 d, const Hit& hit, int32_t id, Surface& s) {
     V3 Nl;  // object-space shading normal before rotation
     const ObjectDev* obp;
@@ -354,7 +360,7 @@ PTB_HD void surface_from_hit(const SceneDev& sc, V3 o, V3 d, const Hit& hit, int
         const TriShade ts = sc.tri_shade[id];
         s.object = tu.object_has_uv & 0x7fffffff;
         obp = &sc.objects[s.object];
-        if (tu.group == PTB_GROUP_DISC) {
+        if (EXOTIC && tu.group == PTB_GROUP_DISC) {
             // ---- PointSet::intersection's tail (PointSet.cpp:192-217): n0 = normal, t0 = colour, n1 = centre, n2[0] = radius ----
             const V3 dl = xf_dir(obp->inv_trans, d), ol = xf_point(obp->inv_trans, o);
             const V3 Pl = ol + hit.t * dl;
@@ -426,7 +432,7 @@ PTB_HD void surface_from_hit(const SceneDev& sc, V3 o, V3 d, const Hit& hit, int
                 s.Ke = v3(0, 0, 0);
                 Nl = (ob.flags & FLAG_FLIP) ? -N : N;
             }
-        } else if (ob.type == OBJ_CYLINDER) {   // Geometry.h:758-763
+        } else if (EXOTIC && ob.type == OBJ_CYLINDER) {   // Geometry.h:758-763
             const V3 a0 = v3(ob.a[0], ob.a[1], ob.a[2]), ax = v3(ob.n[0], ob.n[1], ob.n[2]);
             const float dP = dot(Pl - a0, ax);
             const V3 proj = a0 + dP * ax;
@@ -549,6 +555,7 @@ enum { ST_SHOW_LIGHTS = 0x10000u, ST_SHOW_ENV = 0x20000u, ST_HAD_SS = 0x40000u, 
 PTB_HD uint32_t pack_state(int depth, bool show_lights) { return (uint32_t)depth | (show_lights ? ST_SHOW_LIGHTS : 0u) | ST_SHOW_ENV; }
 
 // ---- stage 1: camera samples --------------------------------------------------------------------------
+template <bool EXOTIC = true>
 PTB_HD void raygen_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path) {
     const int ps = path / f.spp_pass, s = path - ps * f.spp_pass;
     int i, j;
@@ -574,7 +581,7 @@ PTB_HD void raygen_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pa
     q.x = 0; q.y = 0; q.z = 0; q.w = 0; p.radiance[path] = q;
     if (f.accum_albedo) { p.aov_n[path] = q; p.aov_kd[path] = q; }   // `Vector normal, albedo;` start at zero (Vector.h:45) and stay there on a miss
     float ta; int32_t ida;
-    analytic_closest(sc, o, d, ta, ida);        // the analytic half of Scene::intersection rides with the ray producer
+    analytic_closest<EXOTIC>(sc, o, d, ta, ida);        // the analytic half of Scene::intersection rides with the ray producer
     q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
     p.rng[path] = e.state;
     p.pixel[path] = pix;
@@ -637,7 +644,7 @@ PTB_HD bool shade_terminal_one(const SceneDev& sc, PoolDev& p, int path) {
     return true;
 }
 
-template <bool MERL, bool AOV = false>
+template <bool MERL, bool AOV = false, bool EXOTIC = true>
 PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path, ShadeOut& out) {
     out.cont = false; out.shadow = false; out.shadow_query = false;
     const F4 hq = p.hit[path];
@@ -653,7 +660,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
     F4 Lq = p.radiance[path];
     if (AOV && depth == f.nb_bounces) {
         Surface s0;
-        surface_from_hit(sc, ro, rd, hit, id, s0);
+        surface_from_hit<EXOTIC>(sc, ro, rd, hit, id, s0);
         F4 q; q.w = 0;
         q.x = s0.N.x; q.y = s0.N.y; q.z = s0.N.z; p.aov_n[path] = q;
         q.x = s0.Kd.x; q.y = s0.Kd.y; q.z = s0.Kd.z; p.aov_kd[path] = q;
@@ -666,7 +673,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
     }
     if (id == hit_id_analytic(1) && !sc.has_envmap) return;          // dome without a map: Ke = 0
     Surface s;
-    surface_from_hit(sc, ro, rd, hit, id, s);
+    surface_from_hit<EXOTIC>(sc, ro, rd, hit, id, s);
     if (s.object == 1) {                                             // env dome, Raytracer.cpp:275-301
         const V3 c = (w * sc.envmap_intensity) * s.Ke;
         Lq.x += c.x; Lq.y += c.y; Lq.z += c.z;
@@ -731,7 +738,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
                 out.shadow_query = true;
                 // analytic occluders (incl. the light itself and the dome, App. D#8) are tested here, coherently;
                 // only rays they do not block go on to the BVH
-                if (!analytic_occluded(sc, so, wi, dist)) {
+                if (!analytic_occluded<EXOTIC>(sc, so, wi, dist)) {
                     if (sc.has_mesh) {
                         out.shadow = true;
                         out.sh_o.x = so.x; out.sh_o.y = so.y; out.sh_o.z = so.z; out.sh_o.w = (float)((double)dist * 0.999);
@@ -781,7 +788,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
     q.x = nd.x; q.y = nd.y; q.z = nd.z; q.w = 0; p.ray_d[path] = q;
     q.x = nw.x; q.y = nw.y; q.z = nw.z; q.w = u2f(pack_state(ndepth, nshow)); p.weight[path] = q;
     float ta; int32_t ida;
-    analytic_closest(sc, no, nd, ta, ida);
+    analytic_closest<EXOTIC>(sc, no, nd, ta, ida);
     q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
     out.cont = true;
 }
