@@ -732,7 +732,7 @@ struct ptb_ctx {
     bool has_merl = false;
     int shade_minb_merl = 8;                   // the same for scenes with a MERL object (PTB_SHADE_MINB_MERL: 5, 6 or 8; measured r01m: 89.0 / 81.2 / 76.8 ms on C4)
     int shade_minb = 8;                        // k_shade variant (resident blocks/SM the compiler must allow); PTB_SHADE_MINB overrides for experiments
-    int exact_blocks = 148 * 2;                // grid of k_exact (it strides over the few rays that left candidates)
+    int exact_blocks = 148 * 8;                // grid of k_exact: one thread per ray that left candidates for the usual counts (it strides beyond that); most threads exit at once
     int trace_blocks = 148 * 8;                // persistent grid of k_trace, set from the occupancy query in ptb_create
     int refill_below = 24;                     // a warp refills its idle lanes once fewer than this many are live
     int tri_min_pct = 25;                      // the triangle phase starts once this share of a warp's live lanes hold triangles
