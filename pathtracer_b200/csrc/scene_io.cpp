@@ -970,8 +970,6 @@ int ptb_load_scene(ptb_ctx* ctx, const char* path, const char* replaced_names, p
     for (size_t i = 0; i < sc.objects.size(); i++) {
         const ScnObject& so = sc.objects[i];
         const ptb_scn_object& o = so.o;
-        for (const Slot& sl : so.slots[PTB_KIND_SUBSURF])
-            if (!sl.file.empty() || sl.mult[0] * sl.mult[0] + sl.mult[1] * sl.mult[1] + sl.mult[2] * sl.mult[2] > 1e-8f) return fail(PTB_ERR_UNSUPPORTED, "load_scene: subsurface scattering is not rendered");
         int flags = (o.miroir ? PTB_OBJ_MIRROR : 0) | (o.flip_normals ? PTB_OBJ_FLIP_NORMALS : 0) | (o.interp_normals ? 0 : PTB_OBJ_FLAT_NORMALS) |
                     (o.ghost ? PTB_OBJ_GHOST : 0);
         int id = -1;
@@ -1007,14 +1005,16 @@ int ptb_load_scene(ptb_ctx* ctx, const char* path, const char* replaced_names, p
         }
         // per-group slots: a kind is present for group g iff g < its vector's length (Object::queryMaterial, Geometry.h:399-445)
         size_t ng = 0;
-        for (int k = 0; k < PTB_N_KINDS; k++) if (k != PTB_KIND_SUBSURF) ng = std::max(ng, so.slots[k].size());
+        for (int k = 0; k < PTB_N_KINDS; k++) ng = std::max(ng, so.slots[k].size());
         for (size_t g = 0; g < ng; g++) {
             ptb_material mat;
             memset(&mat, 0, sizeof mat);
             std::vector<float> store[PTB_N_KINDS];
             struct { int kind; uint32_t bit; ptb_tex* t; } map[] = {
                 {PTB_KIND_KD, PTB_SLOT_KD, &mat.Kd}, {PTB_KIND_KS, PTB_SLOT_KS, &mat.Ks}, {PTB_KIND_NE, PTB_SLOT_NE, &mat.Ne}, {PTB_KIND_TRANSP, PTB_SLOT_TRANSP, &mat.transp},
-                {PTB_KIND_REFR, PTB_SLOT_REFR, &mat.refr}, {PTB_KIND_NORMAL, PTB_SLOT_NORMAL, &mat.normal}, {PTB_KIND_ALPHA, PTB_SLOT_ALPHA, &mat.alpha}};
+                {PTB_KIND_REFR, PTB_SLOT_REFR, &mat.refr}, {PTB_KIND_NORMAL, PTB_SLOT_NORMAL, &mat.normal}, {PTB_KIND_ALPHA, PTB_SLOT_ALPHA, &mat.alpha},
+                // Object::subsurface: rendered on triangle meshes (Raytracer.cpp:318-406); ptb_set_group_material refuses a non-zero one elsewhere
+                {PTB_KIND_SUBSURF, PTB_SLOT_KSUB, &mat.Ksub}};
             for (auto& e : map) {
                 if (g >= so.slots[e.kind].size()) continue;
                 Slot sl = so.slots[e.kind][g];
