@@ -392,6 +392,9 @@ int ptb_get_scene_info(const ptb_ctx*, ptb_scene_info*);
 #define PTB_KAT_FILTER_RATIO   11  /* in: i,j,W,H,sigma        -> out: ratio                 (Raytracer.cpp:1604-1608) */
 #define PTB_KAT_MERL_INDEX     12  /* in: wi3,wo3 (local frame, z = normal) -> out: bin index of the float path (-1: it declined), bin index of
                                       the double path (MERLBRDFRead.cpp:76-207); the two must agree wherever the first is >= 0 */
+#define PTB_KAT_NODE_HALF      13  /* in: o3, d3, tmax, node index (committed mesh scene) -> out: child hit mask of the float slab test, of the
+                                      half-factor test the traversal kernel runs (slab test of Geometry.h:114-204 on a BVH8 node); the
+                                      second must contain the first */
 int ptb_kat(ptb_ctx*, int which, const ptb_camera* cam, int W, int H,
             const double* in, int n, int in_stride, double* out, int out_stride);
 

@@ -177,15 +177,14 @@ void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
     if (!dp.empty()) solve(node);
 }
 
-inline uint8_t exponent_byte(float extent) {
-    // smallest e with extent <= 255 * 2^e (a little slack keeps the rounded-up far planes inside 255)
-    int e;
-    if (!(extent > 0)) e = -100;
-    else {
-        e = (int)std::ceil(std::log2((double)extent * 1.0001 / 255.0));
-        if (e < -100) e = -100;
-        if (e > 100) e = 100;
-    }
+inline uint8_t exponent_byte(float extent, float coord_slack, int e_lo) {
+    // smallest e with extent + 2 * slack <= 255 * 2^e, where slack = 4e-3 cells + coord_slack is what the quantisation adds on either
+    // side (the 1.0001 pays for the cell-relative part: 255 / 1.0001 + 0.008 < 255).  Never below e_lo: the cell must have a half
+    // exponent byte (ptb_bvh8.h half_exp_byte); a flat or tiny box simply gets cells coarser than it needs.
+    const double x = ((double)extent + 2.0 * (double)coord_slack) * 1.0001 / 255.0;
+    int e = x > 0 ? (int)std::ceil(std::log2(x)) : e_lo;
+    if (e < e_lo) e = e_lo;
+    if (e > 100) e = 100;
     return (uint8_t)(e + 127);
 }
 
@@ -225,6 +224,14 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
     out_nodes.emplace_back();
     queue.push_back({0, 0, 1});
     size_t head = 0;
+    {   // the half grid of the scene (ptb_bvh8.h half_grid_c): fixed by the root box, whose cells are the largest of the tree
+        const Box& rb = B.nodes[0].box;
+        int e_root = -100;
+        for (int k = 0; k < 3; k++)
+            e_root = std::max(e_root, (int)exponent_byte(rb.hi[k] - rb.lo[k], node_coord_slack(rb.lo[k], rb.hi[k]), -100) - 127);
+        stats.half_c = half_grid_c(e_root);
+    }
+    const int e_lo = PTB_HALF_E_LO - stats.half_c;
     while (head < queue.size()) {
         const Work w = queue[head++];
         if (w.depth > stats.depth) stats.level_start.push_back(w.wide);     // breadth-first emission: the first node of a new level
@@ -294,15 +301,16 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
         // ---- emit
         Node8 nd;
         memset(&nd, 0, sizeof(nd));
-        nd.ex = exponent_byte(nb.hi[0] - nb.lo[0]);
-        nd.ey = exponent_byte(nb.hi[1] - nb.lo[1]);
-        nd.ez = exponent_byte(nb.hi[2] - nb.lo[2]);
+        nd.ex = exponent_byte(nb.hi[0] - nb.lo[0], node_coord_slack(nb.lo[0], nb.hi[0]), e_lo);
+        nd.ey = exponent_byte(nb.hi[1] - nb.lo[1], node_coord_slack(nb.lo[1], nb.hi[1]), e_lo);
+        nd.ez = exponent_byte(nb.hi[2] - nb.lo[2], node_coord_slack(nb.lo[2], nb.hi[2]), e_lo);
+        nd.hx = half_exp_byte((int)nd.ex - 127, stats.half_c); nd.hy = half_exp_byte((int)nd.ey - 127, stats.half_c); nd.hz = half_exp_byte((int)nd.ez - 127, stats.half_c);
         const float cell[3] = {std::ldexp(1.f, (int)nd.ex - 127), std::ldexp(1.f, (int)nd.ey - 127), std::ldexp(1.f, (int)nd.ez - 127)};
         // conservative slack: 4e-3 of a cell (covers the rounding of the traversal's folded plane bias in either form of
         // ptb_bvh8.h planes4) plus a few ulps of the coordinate
         float eps[3], p[3];
         for (int k = 0; k < 3; k++) {
-            eps[k] = cell[k] * 4e-3f + 4e-7f * std::max(std::fabs(nb.lo[k]), std::fabs(nb.hi[k]));
+            eps[k] = cell[k] * 4e-3f + node_coord_slack(nb.lo[k], nb.hi[k]);
             p[k] = nb.lo[k] - eps[k];
         }
         nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];

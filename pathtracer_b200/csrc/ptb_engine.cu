@@ -144,6 +144,10 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
     ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
     uint32_t cn = 0, ct = 0;
     r.o = r.d = r.idir = v3(0, 0, 0); r.oct_inv4 = 0;
+#if PTB_NODE_HALF
+    RaySlopes rs; rs.x = rs.y = rs.z = 0;
+    const int half_c = sc.half_c;
+#endif
     for (;;) {
         // ---- refill idle lanes from the queue
         const uint32_t live_mask = __ballot_sync(FULL, live);
@@ -166,6 +170,9 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                     }
                     if (ok) {
                         r = ray_prep(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
+#if PTB_NODE_HALF
+                        rs = ray_slopes(r, half_c);
+#endif
                         tbest = tmax; hprim = ANY_HIT ? 0 : -1; sp = 0;
                         if (!ANY_HIT) entry = 0;
                         ngroup.x = 0; ngroup.y = 0x80000000u; tgroup.x = 0; tgroup.y = 0;
@@ -239,7 +246,11 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
             n2.x = l2.x; n2.y = l2.y; n2.z = l2.z; n2.w = l2.w; n3.x = l3.x; n3.y = l3.y; n3.z = l3.z; n3.w = l3.w;
             n4.x = l4.x; n4.y = l4.y; n4.z = l4.z; n4.w = l4.w;
             if (COUNT) cn++;
+#if PTB_NODE_HALF
+            const uint32_t hm = node_hitmask_k(n0, n1, n2, n3, n4, r, rs, tbest);
+#else
             const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, tbest);
+#endif
             ngroup.x = f2u(n1.x);
             tgroup.x = f2u(n1.y);
             ngroup.y = (hm & 0xff000000u) | (f2u(n0.w) >> 24);
@@ -480,19 +491,19 @@ __global__ void __launch_bounds__(256) k_refit_tris(const F4* __restrict__ tris_
     q.x = v1.x - v0.x; q.y = v1.y - v0.y; q.z = v1.z - v0.z; q.w = tris[3 * k + 1].w; tris[3 * k + 1] = q;   // .w: the edge threshold stays
     q.x = v2.x - v0.x; q.y = v2.y - v0.y; q.z = v2.z - v0.z; q.w = 0; tris[3 * k + 2] = q;
 }
-__device__ __forceinline__ uint32_t refit_exponent_byte(float extent) {   // smallest e with extent * 1.0001 <= 255 * 2^e (bvh8_build.cpp exponent_byte)
-    int e = -100;
-    if (extent > 0.f) {
-        const float x = extent * (1.0001f / 255.f) * 1.000001f;       // the host evaluates this in double: stay on the safe side of its rounding
+__device__ __forceinline__ uint32_t refit_exponent_byte(float extent, float coord_slack, int e_lo) {   // bvh8_build.cpp exponent_byte
+    int e = e_lo;
+    const float x = (extent + 2.f * coord_slack) * (1.0001f / 255.f) * 1.000001f;       // the host evaluates this in double: stay on the safe side of its rounding
+    if (x > 0.f) {
         const uint32_t b = f2u(x);
         const int k = (int)((b >> 23) & 0xffu) - 127;
         e = (b & 0x7fffffu) ? k + 1 : k;
-        e = max(-100, min(100, e));
+        e = max(e_lo, min(100, e));
     }
     return (uint32_t)(e + 127);
 }
 __global__ void __launch_bounds__(128) k_refit_level(Node8* nodes, F4* node_box, const F4* __restrict__ tris_obj, const ObjectDev* __restrict__ objects,
-                                                     uint32_t first, uint32_t count) {
+                                                     uint32_t first, uint32_t count, int half_c, uint32_t* outgrown) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     Node8 nd = nodes[first + i];
@@ -537,12 +548,17 @@ __global__ void __launch_bounds__(128) k_refit_level(Node8* nodes, F4* node_box,
     F4 q;
     q.x = nlo[0]; q.y = nlo[1]; q.z = nlo[2]; q.w = 0; node_box[2 * (size_t)(first + i)] = q;
     q.x = nhi[0]; q.y = nhi[1]; q.z = nhi[2]; node_box[2 * (size_t)(first + i) + 1] = q;
-    const uint32_t eb[3] = {refit_exponent_byte(nhi[0] - nlo[0]), refit_exponent_byte(nhi[1] - nlo[1]), refit_exponent_byte(nhi[2] - nlo[2])};
+    const int e_lo = PTB_HALF_E_LO - half_c;
+    const uint32_t eb[3] = {refit_exponent_byte(nhi[0] - nlo[0], node_coord_slack(nlo[0], nhi[0]), e_lo), refit_exponent_byte(nhi[1] - nlo[1], node_coord_slack(nlo[1], nhi[1]), e_lo),
+                            refit_exponent_byte(nhi[2] - nlo[2], node_coord_slack(nlo[2], nhi[2]), e_lo)};
     nd.ex = (uint8_t)eb[0]; nd.ey = (uint8_t)eb[1]; nd.ez = (uint8_t)eb[2];
+    // cells too large for the scene's half grid (the re-posed scene is more than 16x the size it was committed at): the caller refuses the frame
+    if ((int)max(eb[0], max(eb[1], eb[2])) - 127 + half_c > PTB_HALF_E_HI) *outgrown = 1u;
+    nd.hx = half_exp_byte((int)eb[0] - 127, half_c); nd.hy = half_exp_byte((int)eb[1] - 127, half_c); nd.hz = half_exp_byte((int)eb[2] - 127, half_c);
     float cell[3], eps[3], p[3];
     for (int k = 0; k < 3; k++) {
         cell[k] = u2f(eb[k] << 23);                                                       // 2^(e - 127 + 127 - 127)... the byte IS the float's exponent field
-        eps[k] = cell[k] * 4e-3f + 4e-7f * fmaxf(fabsf(nlo[k]), fabsf(nhi[k]));          // the builder's conservative slack
+        eps[k] = cell[k] * 4e-3f + node_coord_slack(nlo[k], nhi[k]);                      // the builder's conservative slack
         p[k] = nlo[k] - eps[k];
     }
     nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
@@ -676,6 +692,15 @@ __global__ void k_kat(int which, SceneDev sc, CameraDev cam, FilterDev filt, int
     case PTB_KAT_RANDOM_PER_PIXEL: { float x, y; random_per_pixel((uint32_t)a[0], x, y); o[0] = x; o[1] = y; } break;
     case PTB_KAT_FILTER_RATIO: { int b0, b1, b2, b3; o[0] = filter_ratio(filt, (int)a[0], (int)a[1], W, H, b0, b1, b2, b3); } break;
     case PTB_KAT_MERL_INDEX: { int f, e; merl_index_both(v3((float)a[0], (float)a[1], (float)a[2]), v3((float)a[3], (float)a[4], (float)a[5]), f, e); o[0] = f; o[1] = e; } break;
+#if PTB_NODE_HALF
+    case PTB_KAT_NODE_HALF: {      // the node test of k_trace (half factors) next to the float form: it may only ever see MORE children
+        RayPrep r = ray_prep(v3((float)a[0], (float)a[1], (float)a[2]), v3((float)a[3], (float)a[4], (float)a[5]));
+        const RaySlopes rs = ray_slopes(r, sc.half_c);
+        const F4* np = sc.nodes + (size_t)a[7] * 5;
+        o[0] = (double)node_hitmask(np[0], np[1], np[2], np[3], np[4], r, (float)a[6]);
+        o[1] = (double)node_hitmask_k(np[0], np[1], np[2], np[3], np[4], r, rs, (float)a[6]);
+    } break;
+#endif
     default: break;
     }
 }
@@ -914,14 +939,24 @@ static int refit_device(ptb_ctx* c, FlatScene& f, const HostScene& host) {
     const size_t n_tri = (size_t)(c->bytes_tris / (3 * (int64_t)sizeof(F4)));
     if (sc.has_mesh && n_tri > 0) {
         if (!sc.tris_obj) { c->err = "refit: the scene was committed without object-space triangles"; return PTB_ERR_STATE; }
-        if ((rc = grow(c, &c->d_node_box, &c->node_box_n, 2 * (int64_t)f.bvh.n_nodes))) return rc;
+        if ((rc = grow(c, &c->d_node_box, &c->node_box_n, 2 * (int64_t)f.bvh.n_nodes + 1))) return rc;
+        uint32_t* outgrown = reinterpret_cast<uint32_t*>(c->d_node_box + 2 * (size_t)f.bvh.n_nodes);      // one flag behind the boxes
+        CK(cudaMemsetAsync(outgrown, 0, sizeof(uint32_t), c->stream));
         k_refit_tris<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(sc.tris_obj, sc.objects, const_cast<F4*>(sc.tris), n_tri);
         const std::vector<uint32_t>& ls = f.bvh.level_start;
         for (int l = (int)ls.size() - 2; l >= 0; l--) {
             const uint32_t first = ls[l], count = ls[l + 1] - ls[l];
-            if (count) k_refit_level<<<(count + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<Node8*>(const_cast<F4*>(sc.nodes)), c->d_node_box, sc.tris_obj, sc.objects, first, count);
+            if (count) k_refit_level<<<(count + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<Node8*>(const_cast<F4*>(sc.nodes)), c->d_node_box, sc.tris_obj, sc.objects, first, count, sc.half_c, outgrown);
         }
         CK(cudaGetLastError());
+        uint32_t flag = 0;
+        CK(cudaMemcpyAsync(&flag, outgrown, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (flag) {
+            c->committed = false;      // the node planes of this frame are not usable
+            c->err = "refit: the re-posed scene is more than 16x larger than the committed one (the half grid of the BVH8 cannot hold its cells); commit it at this frame instead";
+            return PTB_ERR_UNSUPPORTED;
+        }
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1721,6 +1756,12 @@ int ptb_kat(ptb_ctx* c, int which, const ptb_camera* cam, int W, int H, const do
     if (!c || !in || !out || n <= 0) return PTB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
     if (which == PTB_KAT_MERL_EVAL && (!c->committed || c->host.merl_tables.empty())) { c->err = "kat: MERL needs a committed scene with a table"; return PTB_ERR_STATE; }
+    if (which == PTB_KAT_NODE_HALF) {
+        if (!PTB_NODE_HALF) { c->err = "kat: this build traverses with the float node test"; return PTB_ERR_UNSUPPORTED; }
+        if (!c->committed || !c->sc.has_mesh) { c->err = "kat: the node test needs a committed scene with a mesh"; return PTB_ERR_STATE; }
+        const double n_nodes = (double)(c->bytes_nodes / (int64_t)sizeof(Node8));
+        for (int k = 0; k < n; k++) if (!(in[(size_t)k * is + 7] >= 0 && in[(size_t)k * is + 7] < n_nodes)) { c->err = "kat: node index out of range"; return PTB_ERR_INVALID; }
+    }
     CameraDev cd;
     memset(&cd, 0, sizeof(cd));
     if (cam) camera_from_abi(cd, cam, W, H);

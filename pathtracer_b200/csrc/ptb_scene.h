@@ -89,7 +89,8 @@ struct SceneDev {
     const float* texels;
     const uint8_t* envmap;
     const float* merl;          // per table 3*PTB_MERL_N floats, pre-scaled (see merl_eval)
-    int32_t n_objects, has_mesh, envW, envH, has_envmap, pad0;
+    int32_t n_objects, has_mesh, envW, envH, has_envmap;
+    int32_t half_c;             // the BVH8's half grid (ptb_bvh8.h half_grid_c): the traversal scales 1 / d by 2^-half_c
     float envmap_intensity, lightPower, radiusLight;
     V3 centerLight;
     int32_t n_inline, n_extra;  // analytic objects held inline below / left in `objects` (flag FLAG_NOT_INLINE)

@@ -19,7 +19,7 @@ for spec in specs:
     kt = rt.kernel_times(); rt.nrays = full; rt.set_option(_abi.OPT_COUNT_TRAVERSAL, 0)
     n_node = kt["extend"]["node_visits"] / max(1, kt["extend"]["items"]); n_tri = kt["extend"]["tri_tests"] / max(1, kt["extend"]["items"])
     print(f"[{tag}] {wl}: nodes={info['n_bvh_nodes']} depth={info['bvh_depth']} build_ms={info['ms_bvh_build']:.0f} closest: n_node={n_node:.2f} n_tri={n_tri:.2f}", flush=True)
-    for pipes, tb in ((1, 9), (2, 6)):
+    for pipes, tb in ((1, int(os.environ.get("PTB_AB_TB", 9))), (2, 6)):
         rt.set_option(_abi.OPT_PIPES, pipes)
         rt.set_option(_abi.OPT_TRACE_BLOCKS, 148 * tb)
         best = 1e30

@@ -232,6 +232,49 @@ def case_merl_index_fast(test_lib, n=400000):
     assert (exact >= 0).all() and (exact < 90 * 90 * 180).all()
 
 
+def case_node_test_half(test_lib, n=300000):
+    """k_trace tests a ray against the 8 child boxes of a BVH8 node with half-precision factors rounded outwards (ptb_bvh8.h
+    node_hitmask_h): it may report children the float slab test rejects (Geometry.h:114-204 on the quantised boxes), never the other
+    way round, and only a few more.  Rays as a render makes them plus the awkward ones: along an axis (a zero or denormal component),
+    starting on a plane of the grid, from far outside, with a short t_max."""
+    rng = np.random.default_rng(20261018)
+    def flat_sheet():          # every node box has zero extent on one axis
+        v, nrm, uv, tri = quad_mesh(n=24)
+        v = v.copy(); v[:, 1] = 0.25
+        return v, nrm, uv, tri
+    meshes = {"torus": None, "soup": triangle_soup(4000), "sheet": flat_sheet()}
+    for name, mesh in meshes.items():
+        if mesh is None: rt = scenes.config_C2(test_lib, 16, 16, 1, nv=120, env=(16, 8)).commit()
+        else:
+            rt = scenes.base(test_lib, 16, 16, 1)
+            rt.s.addObject(scenes._place_like_gui(TriMesh(*mesh), scale=22.0).set_material(0, **scenes.phong((.6, .5, .4), 0.1, 20.0)))
+            rt.commit()
+        n_nodes = int(rt.scene_info()["n_bvh_nodes"])
+        o = (rng.random((n, 3)) - .5) * np.array([60., 60., 60.])
+        d = rng.normal(size=(n, 3))
+        k = n // 10
+        o[:k] *= 40                                                   # from far outside
+        d[k:2 * k, rng.integers(0, 3)] = 0.0                          # along the planes of an axis
+        d[2 * k:3 * k, 0] *= 1e-7; d[2 * k:3 * k, 2] *= 1e-9          # nearly
+        d[3 * k:4 * k] = np.eye(3)[rng.integers(0, 3, k)] * rng.choice([-1., 1.], (k, 1))      # an axis itself
+        d[4 * k:5 * k, 1] = 1e-38 * rng.random(k)                     # denormal component
+        o[5 * k:6 * k] = np.round(o[5 * k:6 * k] * 4) / 4             # origins on round coordinates
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        tmax = np.where(rng.random(n) < .5, 1e30, 80 * rng.random(n) ** 2)
+        node = rng.integers(0, n_nodes, n)
+        node[:: 7] = 0                                                # the root: the largest cells
+        inp = np.concatenate([o, d, tmax[:, None], node[:, None]], -1).astype(np.float32).astype(np.float64)
+        out = rt.kat(_abi.KAT_NODE_HALF, inp).astype(np.int64)
+        rt.close()
+        f32, h16 = out[:, 0], out[:, 1]
+        lost = f32 & ~h16
+        assert not lost.any(), f"{name}: the half node test lost children of {np.count_nonzero(lost)} (ray, node) pairs, e.g. {inp[np.flatnonzero(lost)[0]]}"
+        kids = lambda m: sum(((m >> (24 + s)) & 1) | (((m >> (3 * s)) & 7) != 0) for s in range(8))
+        ordinary = np.abs(d).min(1) > 1e-3             # no component steep enough to overflow a half: these must stay tight
+        kids_f, kids_h = kids(f32[ordinary]).sum(), kids(h16[ordinary]).sum()
+        assert kids_h <= 1.03 * kids_f + 10, f"{name}: {kids_h} children hit with half factors against {kids_f}"
+
+
 def triangle_soup(n, seed=7):
     """n unconnected random triangles of very different sizes in a unit cube (file axes): irregular trees, leaves of 1-3 triangles in
     arbitrary slots, overlapping boxes - what a displaced torus never produces."""

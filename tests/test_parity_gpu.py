@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
-from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_triangle_soup, case_passes_and_shards,
+from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_node_test_half, case_triangle_soup, case_passes_and_shards,
                           case_progressive, case_scene, check_ids, check_images)
 
 from pathtracer_b200 import _abi, scenes
@@ -33,6 +33,20 @@ def test_kats_gpu(gpu):
 def test_triangle_soup_gpu(gpu, port):
     """irregular trees (random unconnected triangles): persistent-warp traversal, valid24 / compact indices, postponed triangle groups"""
     case_triangle_soup(gpu, port, n=20000, agree=0.998)   # 6912 pixels full of silhouette edges: a handful may flip under FMA contraction
+
+
+def test_node_test_with_half_factors_is_conservative(gpu):
+    """FHFMA node step of k_trace (an optional build, -DPTB_NODE_HALF=1) against the float slab test on the same quantised boxes"""
+    from pathtracer_b200 import scenes as _sc, _abi as _ab
+    rt = _sc.config_C2(gpu, 8, 8, 1, nv=8, env=(8, 4)).commit()
+    try:
+        rt.kat(_ab.KAT_NODE_HALF, np.array([[0, 0, 0, 0, 0, 1, 1e30, 0]], np.float64))
+    except Exception as e:
+        if "float node test" in str(e): pytest.skip("this build traverses with the float node test (the default)")
+        raise
+    finally:
+        rt.close()
+    case_node_test_half(gpu)
 
 
 def test_merl_index_fast_gpu(gpu):
