@@ -210,7 +210,7 @@ def main():
     also = [w for w in also.split(",") if w and w != args.workload]
     base_line = {"metric": "Msamples/s", "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                  "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                 "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "spp_sharding": "image tiles (32x32 when shared, rows rotated), tile_id % n_gpus",
+                 "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "spp_sharding": "image tiles (32x32 when shared, 16x16 among 8 GPUs, rows rotated), tile_id % n_gpus",
                             "pass_pipelines": int(os.environ.get("PTB_PIPES", "2")),
                             "l2": "working set per step (BVH + triangles + path pool, >2 GB) exceeds the 126 MB L2; no flush needed"}}
 
@@ -283,8 +283,27 @@ def main():
         rt.set_option(_abi.OPT_COUNT_TRAVERSAL, 0)
 
         rt.nrays = short_spp
+        t_w = time.perf_counter()
         for _ in range(warmup):
             rt.render_resident()
+        if brief:
+            # A sharded short-spp step is a few tens of ms: two of them after a multi-second BVH build leave the clocks below boost
+            # and the first timed step pays for it (r02m: C3 at N=8 193 ms per step against 157 ms through the host route measured
+            # right after).  Warm up for at least a second, then time enough full steps for about two seconds of rendering.
+            n_w = warmup
+            while True:
+                el = torch.tensor([time.perf_counter() - t_w], dtype=torch.float64, device=device)
+                if world > 1:
+                    dist.all_reduce(el, op=dist.ReduceOp.MAX)
+                if float(el[0]) >= 1.0 or n_w >= 64:
+                    break
+                rt.render_resident(); n_w += 1
+            warmup = n_w
+            sync(); t1 = time.perf_counter(); rt.render_resident(); sync()
+            est = torch.tensor([(time.perf_counter() - t1) * full_spp / short_spp], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(est, op=dist.ReduceOp.MAX)
+            steps = max(steps, min(6, int(2.0 / max(float(est[0]), 1e-3))))
         rt.nrays = full_spp
         sampler = ClockSampler(local)
         if rank == 0:

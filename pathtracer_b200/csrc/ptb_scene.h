@@ -495,9 +495,10 @@ struct FrameDev {     // per-render constants (Raytracer fields + prepare_render
 // Without the rotation a frame whose tile columns are a multiple of n (1024 / 64 = 16 tiles for 2, 4, 8 GPUs) is cut into vertical
 // stripes, and the GPUs that get the columns with the mesh finish last (measured at 8 GPUs on C2: slowest rank 7 % over the mean).
 // The shift is chosen so that owners advance by a step coprime to n from one row to the next; one shard keeps the plain order.
-// default tile edge: 64 for a whole frame, 32 when the frame is shared (finer granularity balances the shards better: slowest of
-// 8 shards of C2 at 1.034 of the mean with 64-pixel tiles, 1.020 with 32; profiles/r01m_shard_balance.txt)
-inline int ptb_default_tile(int shard_count) { return shard_count > 1 ? 32 : 64; }
+// default tile edge: 64 for a whole frame, 32 when the frame is shared, 16 among 8 or more (finer granularity balances the shards
+// better: slowest of 8 shards of C2 at 1.034 of the mean with 64-pixel tiles, 1.020 with 32, 1.004 with 16, where the mean itself
+// is 0.6 % up for the shorter tile rows; profiles/r01m_shard_balance.txt, r02s_shard_balance.txt)
+inline int ptb_default_tile(int shard_count) { return shard_count >= 8 ? 16 : shard_count > 1 ? 32 : 64; }
 PTB_HD int shard_tile_shift(int tiles_x, int count) {
     if (count <= 1 || tiles_x <= 1) return 0;
     for (int s = 1; s <= count; s++) {

@@ -11,7 +11,8 @@ G = ptb.load()
 rt = scenes.CONFIGS[wl](G); rt.commit()
 rgbw = torch.zeros(rt.H * rt.W * 4, dtype=torch.float32, device="cuda")
 for N in [int(a) for a in sys.argv[2:]] or [8, 4, 2]:
-    for pipes, tile in ((1, 64), (2, 64), (2, 32)):
+    combos = [(2, int(t)) for t in os.environ["PTB_TILES"].split(",")] if os.environ.get("PTB_TILES") else ((1, 64), (2, 64), (2, 32))
+    for pipes, tile in combos:
         rt.set_option(_abi.OPT_PIPES, pipes)
         times = []
         for r in range(N):
