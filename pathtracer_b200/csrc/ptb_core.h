@@ -197,6 +197,24 @@ PTB_HD double fast_exp(double y) {
     return d;
 }
 
+// x^y, x >= 0, as the device affords it: exp2f(y * log2f(x)), each accurate to an ulp, so the result is off the correctly rounded power by
+// about |y log2 x| * 6e-8 relative (Ne = 100 at d = 0.9: 1e-6, far inside the 1e-4 of the phong_eval KAT), in 40 instructions where
+// powf takes 96 (ncu r02t: the powf calls were 13 % of k_shade's instructions).  0^0 = 1 like powf; a negative x gives NaN where powf
+// has a value for integer y: both callers discard the sample then (phong_eval returns before, phong_sample's caller tests dot(R, dir) < 0).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float pow_pos(float x, float y) { const float r = exp2f(y * log2f(x)); return y == 0.f ? 1.f : r; }
+#else
+inline float pow_pos(float x, float y) { return powf(x, y); }
+#endif
+PTB_HD float pow5(float x) {      // Schlick's (1 - cos)^5 (Raytracer.cpp:459-462: std::pow(x, 5.f))
+#if defined(__CUDA_ARCH__)
+    const float x2 = x * x;
+    return x2 * x2 * x;
+#else
+    return powf(x, 5.f);
+#endif
+}
+
 // ---- getTangent / random_cos (Vector.h:566-600), random_Phong (BRDF.h:41-61) -----------------------
 PTB_HD V3 get_tangent(V3 N) {
     float ax = fabsf(N.x), ay = fabsf(N.y), az = fabsf(N.z);
@@ -212,8 +230,10 @@ PTB_HD V3 random_cos(V3 N, float r1, float r2) {
 #if defined(__CUDA_ARCH__)
     // one shared argument reduction instead of two (measured r01k: k_shade -3.5 % on C2, -2.3 % on C4; out-of-lining random_cos /
     // phong_eval to shrink the 84 KB kernel was measured too and is SLOWER by 2 %)
+    // (r02u: sincospif of 2 r1: no Payne-Hanek path, a third of the instructions; the angle is not rounded to float first, which moves
+    // the direction by at most 4e-7, inside the KAT's 2e-6)
     float sn, cs;
-    sincosf(a, &sn, &cs);
+    sincospif(2.f * r1, &sn, &cs);
     float lx = cs * sr2, ly = sn * sr2, lz = sqrtf(r2);
 #else
     float lx = cosf(a) * sr2, ly = sinf(a) * sr2, lz = sqrtf(r2);
@@ -223,14 +243,14 @@ PTB_HD V3 random_cos(V3 N, float r1, float r2) {
     return lz * N + lx * t1 + ly * t2;
 }
 PTB_HD V3 random_phong(V3 R, float n, float r1, float r2) {
-    float facteur = sqrtf(1.f - powf(r2, 2.f / (n + 1.f)));
+    float facteur = sqrtf(1.f - pow_pos(r2, 2.f / (n + 1.f)));
 #if defined(__CUDA_ARCH__)
     // The reference evaluates cos/sin(2*pi*r1) and r2^(1/(n+1)) in double and narrows (BRDF.h:44).  On the device the
     // float functions are used: the results agree to 2 ulp (KAT tolerance 2e-5) and the double versions cost ~500
     // instructions for the fifth of the lanes that take the specular lobe.
     float sn, cs;
-    sincosf(2.f * PTB_PI_F * r1, &sn, &cs);
-    float lx = cs * facteur, ly = sn * facteur, lz = powf(r2, 1.f / (n + 1.f));
+    sincospif(2.f * r1, &sn, &cs);
+    float lx = cs * facteur, ly = sn * facteur, lz = pow_pos(r2, 1.f / (n + 1.f));
 #else
     double a = 2 * PTB_PI_D * (double)r1;
     float lx = (float)(cos(a) * (double)facteur);
@@ -253,9 +273,9 @@ PTB_HD V3 phong_eval(V3 Kd, V3 Ks, V3 Ne, V3 wi, V3 wo, V3 N) {
     // float division by float(M_TWO_PI): within 1 ulp of the reference's double division + narrowing
     const float two_pi = (float)PTB_TWO_PI_REF;
     const bool same = (Ne.x == Ne.y) && (Ne.y == Ne.z);
-    lobe.x = powf(d, Ne.x) * (Ne.x + 2.f) / two_pi;
-    lobe.y = same ? lobe.x : powf(d, Ne.y) * (Ne.y + 2.f) / two_pi;
-    lobe.z = same ? lobe.x : powf(d, Ne.z) * (Ne.z + 2.f) / two_pi;
+    lobe.x = pow_pos(d, Ne.x) * (Ne.x + 2.f) / two_pi;
+    lobe.y = same ? lobe.x : pow_pos(d, Ne.y) * (Ne.y + 2.f) / two_pi;
+    lobe.z = same ? lobe.x : pow_pos(d, Ne.z) * (Ne.z + 2.f) / two_pi;
 #else
     lobe.x = (float)((double)(powf(d, Ne.x) * (Ne.x + 2.f)) / PTB_TWO_PI_REF);
     lobe.y = (float)((double)(powf(d, Ne.y) * (Ne.y + 2.f)) / PTB_TWO_PI_REF);
@@ -272,7 +292,7 @@ PTB_HD V3 phong_sample(V3 Ks, V3 Ne, V3 wo, V3 N, float r1, float r2, float u, f
     if (u < p) { diffuse = true; dir = random_cos(N, r1, r2); }
     else { diffuse = false; dir = random_phong(R, avgNe, r1, r2); }
 #if defined(__CUDA_ARCH__)
-    float proba_phong = (avgNe + 1) / (2.f * PTB_PI_F) * powf(dot(R, dir), avgNe);
+    float proba_phong = (avgNe + 1) / (2.f * PTB_PI_F) * pow_pos(dot(R, dir), avgNe);
     pdf = (p * dot(N, dir)) / PTB_PI_F + (1.f - p) * proba_phong;
 #else
     float proba_phong = (float)((double)(avgNe + 1) / (2.f * PTB_PI_D) * (double)powf(dot(R, dir), avgNe));
@@ -540,7 +560,7 @@ PTB_HD float filter_ratio(const FilterDev& f, int i, int j, int W, int H, int& b
     bmax_i = i + f.size < H - 1 ? i + f.size : H - 1;
     bmin_j = j - f.size > 0 ? j - f.size : 0;
     bmax_j = j + f.size < W - 1 ? j + f.size : W - 1;
-    return 1.f / filter_sat(f.integral, f.width, bmin_i - i + f.size, bmax_i - i + f.size, bmin_j - j + f.size, bmax_j - j + f.size);
+    return div_rn(1.f, filter_sat(f.integral, f.width, bmin_i - i + f.size, bmax_i - i + f.size, bmin_j - j + f.size, bmax_j - j + f.size));   // bit-exact block: IEEE division whatever -prec-div says
 }
 // splat weight of sample (i,j,dx,dy) into pixel (i2,j2), Raytracer.cpp:1652
 PTB_HD float filter_weight(const FilterDev& f, float denom1, int i2, int j2, int i, int j, float dx, float dy) {

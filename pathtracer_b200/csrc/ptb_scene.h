@@ -701,8 +701,8 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
             const float r0 = (n1 - n2) / (n1 + n2);
             const float R0 = r0 * r0;
             float R;
-            if (entering) R = R0 + (1 - R0) * powf(1.f + dot(rd, N), 5.f);
-            else R = R0 + (1 - R0) * powf(1.f - dot(refr, N), 5.f);
+            if (entering) R = R0 + (1 - R0) * pow5(1.f + dot(rd, N));
+            else R = R0 + (1 - R0) * pow5(1.f - dot(refr, N));
             Pcg32 e; e.state = p.rng[path]; e.inc = path_inc(f, path);
             const float u = pcg32_uniform(e);
             p.rng[path] = e.state;
@@ -1082,8 +1082,8 @@ PTB_HD void shade_branch_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, 
             const float r0 = (n1 - n2) / (n1 + n2);
             const float R0 = r0 * r0;
             float R;
-            if (entering) R = R0 + (1 - R0) * powf(1.f + dot(sd, N), 5.f);
-            else R = R0 + (1 - R0) * powf(1.f - dot(refr, N), 5.f);
+            if (entering) R = R0 + (1 - R0) * pow5(1.f + dot(sd, N));
+            else R = R0 + (1 - R0) * pow5(1.f - dot(refr, N));
             const float u = pcg32_uniform(e);
             if (u < R) { no = P + 0.001f * Nt; nd = reflect(sd, N); }
             else { no = P - 0.001f * Nt; nd = refr; }
@@ -1331,11 +1331,11 @@ PTB_HD void splat_pixel(const FrameDev& f, const PoolDev& p, int ps, F4* accum, 
 // ---- resolve: normalise by the weight and tonemap (Raytracer.cpp:1687-1708) ----------------------------------------
 PTB_HD void resolve_pixel(const F4* accum, size_t idx, float gamma, float* imagedouble, float* sample_count, uint8_t* image) {
     const F4 a = accum[idx];
-    const float r = a.x / a.w, g = a.y / a.w, b = a.z / a.w;
+    const float r = div_rn(a.x, a.w), g = div_rn(a.y, a.w), b = div_rn(a.z, a.w);     // (the library is compiled with -prec-div=false)
     if (imagedouble) { imagedouble[idx * 3] = r; imagedouble[idx * 3 + 1] = g; imagedouble[idx * 3 + 2] = b; }
     if (sample_count) sample_count[idx] = a.w;
     if (image) {
-        const double ig = (double)(1 / gamma);
+        const double ig = (double)div_rn(1.f, gamma);
         const float c[3] = {r, g, b};
         for (int q = 0; q < 3; q++) {
             double v = 255. * pow((double)c[q] / 196964.7, ig);

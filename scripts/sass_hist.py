@@ -6,7 +6,7 @@ cur, fn = None, {}
 for line in out.splitlines():
     m = re.match(r"\s+Function : (\S+)", line)
     if m: cur = m.group(1); fn[cur] = []; continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
     if m and cur: fn[cur].append(m.group(1))
 for name, ins in fn.items():
     if sys.argv[2] not in name: continue
