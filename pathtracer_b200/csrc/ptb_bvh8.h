@@ -171,7 +171,11 @@ __device__ __forceinline__ uint32_t node_hitmask(const F4& n0, const F4& n1, con
     // The mask is built in SLOT order with immediates (slot s: its three triangle bits and its internal-child bit) and cut down to
     // what exists with one AND; the octant order is applied when a child is picked (pick_slot).  The per-child byte extracts and
     // variable shifts of a traversal-ordered mask were a quarter of the node step's instructions.
+#if defined(PTB_MASK_FMA)
+    uint32_t hitmask = 0xffffffffu;     // A/B: the mask accumulated on the fma pipe (FADD, IMAD.HI, IMAD per child instead of FSETP + predicated add)
+#else
     uint32_t hitmask = 0;
+#endif
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const uint32_t lox = f2u(half ? n2.y : n2.x), loy = f2u(half ? n2.w : n2.z), loz = f2u(half ? n3.y : n3.x);
@@ -188,7 +192,13 @@ __device__ __forceinline__ uint32_t node_hitmask(const F4& n0, const F4& n1, con
             const float tn = fmaxf(fmaxf(tnx[j], tny[j]), fmaxf(tnz[j], 0.f));
             const float tf = fminf(fminf(tfx[j], tfy[j]), fminf(tfz[j], tmax));
             const int s = 4 * half + j;
+#if defined(PTB_MASK_FMA)
+            // tn <= tf  <=>  the sign of tf - tn is clear (both finite or tf = +inf; never NaN: the min / max drop NaNs and 0, tmax are numbers)
+            const int32_t miss = __mulhi((int32_t)f2u(tf - tn), 2);                 // 0 or -1, IMAD.HI
+            hitmask += (uint32_t)miss * ((7u << (3 * s)) | (1u << (24 + s)));        // IMAD: a missed child takes its bits out of the full mask
+#else
             if (tn <= tf) hitmask |= (7u << (3 * s)) | (1u << (24 + s));
+#endif
         }
     }
     return hitmask & ((e_imask & 0xff000000u) | (f2u(n1.z) & 0x00ffffffu));

@@ -377,8 +377,11 @@ __global__ void __launch_bounds__(256) k_sort_hits(SceneDev sc, PoolDev p, const
     if (surface) out_queue[qi] = (uint32_t)path;
 }
 
+#ifndef PTB_SHADE_BLOCK
+#define PTB_SHADE_BLOCK 256    /* threads per k_shade block: half as many blocks for a later bounce to launch only to see them return (r02w: k_shade -4 % on C2, -3 % on C4 against 128; 512 is no better) */
+#endif
 template <bool MERL, int MINB, bool AOV, bool EXOTIC = false>
-__global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
+__global__ void __launch_bounds__(PTB_SHADE_BLOCK, (MINB * 128) / PTB_SHADE_BLOCK) k_shade(SceneDev sc, FrameDev f, PoolDev p, const uint32_t* __restrict__ queue,
                                                const uint32_t* __restrict__ count, int n_static, uint32_t* __restrict__ next_queue,
                                                uint32_t* next_count, uint32_t* shadow_count, uint32_t* shadow_queries) {
     // one thread per pool slot; the queue length lives in device memory, so after the first bounce most blocks return at once.
@@ -393,12 +396,20 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneDev sc, FrameDev f, Po
         path = queue ? (int)queue[tid] : tid;
         shade_one<MERL, AOV, EXOTIC>(sc, f, p, path, out);
     }
-    const uint32_t qi = warp_push(next_count, out.cont);
-    if (out.cont) next_queue[qi] = (uint32_t)path;
-    const uint32_t si = warp_push(shadow_count, out.shadow);
-    if (out.shadow) { p.sh_o[si] = out.sh_o; p.sh_d[si] = out.sh_d; p.sh_c[si] = out.sh_c; }
-    const uint32_t sq = __ballot_sync(0xffffffffu, out.shadow_query);
-    if ((threadIdx.x & 31) == 0 && sq) atomicAdd(shadow_queries, (uint32_t)__popc(sq));
+    // both appends of the warp in one go: lane 0 issues the two returning atomics back to back, so their round trips to L2 overlap
+    // (ncu r02t: 6.7 % of the kernel's stall samples sat on the first one's return before the second was even issued)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t mc = __ballot_sync(0xffffffffu, out.cont), ms = __ballot_sync(0xffffffffu, out.shadow), sq = __ballot_sync(0xffffffffu, out.shadow_query);
+    uint32_t bc = 0, bs = 0;
+    if (lane == 0) {
+        if (mc) bc = atomicAdd(next_count, (uint32_t)__popc(mc));
+        if (ms) bs = atomicAdd(shadow_count, (uint32_t)__popc(ms));
+        if (sq) atomicAdd(shadow_queries, (uint32_t)__popc(sq));
+    }
+    bc = __shfl_sync(0xffffffffu, bc, 0); bs = __shfl_sync(0xffffffffu, bs, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    if (out.cont) next_queue[bc + __popc(mc & below)] = (uint32_t)path;
+    if (out.shadow) { const uint32_t si = bs + __popc(ms & below); p.sh_o[si] = out.sh_o; p.sh_d[si] = out.sh_d; p.sh_c[si] = out.sh_c; }
 }
 
 // Branching renders (fog, ghost objects, background photograph): one getColor loop iteration per queue entry; side branches
@@ -1413,16 +1424,17 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                         sq = pqs; scnt = pc + PTB_CNT_SURF + b;
                         launches++;
                     }
-#define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<g128, 128, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
-#define PTB_SHADE_X(M, MB, A) k_shade<M, MB, A, true><<<g128, 128, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
+#define PTB_SHADE(M, MB, A) k_shade<M, MB, A><<<(unsigned)((n_paths + PTB_SHADE_BLOCK - 1) / PTB_SHADE_BLOCK), PTB_SHADE_BLOCK, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
+#define PTB_SHADE_X(M, MB, A) k_shade<M, MB, A, true><<<(unsigned)((n_paths + PTB_SHADE_BLOCK - 1) / PTB_SHADE_BLOCK), PTB_SHADE_BLOCK, 0, ps>>>(c->sc, f, pp, sq, scnt, n_paths, pq[(b + 1) & 1], pc + 2 * (b + 1), pc + 2 * b + 1, pc + PTB_CNT_SQ + b)
                     if (c->sc.has_exotic) {      // scenes with Cylinder / PointSet objects: the kernels that carry their code (not register-squeezed)
                         if (aov && b == 0) { if (c->has_merl) PTB_SHADE_X(true, 5, true); else PTB_SHADE_X(false, 6, true); }
                         else if (c->has_merl) PTB_SHADE_X(true, 5, false);
                         else PTB_SHADE_X(false, 6, false);
                     } else
                     if (aov && b == 0) { if (c->has_merl) PTB_SHADE(true, 5, true); else PTB_SHADE(false, 6, true); }   // camera rays of a denoiser-input render
-                    else if (c->has_merl) { if (c->shade_minb_merl == 8) PTB_SHADE(true, 8, false); else if (c->shade_minb_merl == 6) PTB_SHADE(true, 6, false); else PTB_SHADE(true, 5, false); }
+                    else if (c->has_merl) { if (c->shade_minb_merl == 8) PTB_SHADE(true, 8, false); else if (c->shade_minb_merl == 7) PTB_SHADE(true, 7, false); else if (c->shade_minb_merl == 6) PTB_SHADE(true, 6, false); else PTB_SHADE(true, 5, false); }
                     else if (c->shade_minb == 8) PTB_SHADE(false, 8, false);
+                    else if (c->shade_minb == 7) PTB_SHADE(false, 7, false);
                     else if (c->shade_minb == 10) PTB_SHADE(false, 10, false);
                     else PTB_SHADE(false, 6, false);
 #undef PTB_SHADE
