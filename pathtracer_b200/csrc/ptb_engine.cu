@@ -226,7 +226,7 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                     cm |= 1u << popcount32(tvalid & ~(0xffffffffu << b));
                 } while (m);
                 tgroup.y = cm;
-                if (sp < PTB_STACK) PTB_STK_PUSH(tgroup);   // never full: ptb_commit refuses trees deeper than PTB_STACK / 2
+                PTB_STK_PUSH(tgroup);   // never full: ptb_commit refuses trees deeper than PTB_STACK / 2
                 tgroup.y = 0;
             }
             const uint32_t hits_imask = ngroup.y;
@@ -237,7 +237,7 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
 #endif
             const uint32_t child_base = ngroup.x;
             ngroup.y &= ~(1u << (24u + slot));
-            if (ngroup.y > 0x00ffffffu) { if (sp < PTB_STACK) PTB_STK_PUSH(ngroup); }
+            if (ngroup.y > 0x00ffffffu) PTB_STK_PUSH(ngroup);
             const uint32_t rel = popcount32(hits_imask & ~(0xffffffffu << slot));
             const float4* np = reinterpret_cast<const float4*>(nodes) + (size_t)(child_base + rel) * 5;
             const float4 l0 = __ldg(np), l1 = __ldg(np + 1), l2 = __ldg(np + 2), l3 = __ldg(np + 3), l4 = __ldg(np + 4);
@@ -261,9 +261,9 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
         //      further was measured to cost more node visits than it saves issue slots) or when nobody can do anything else;
         //      repeats while >= 1/tri_den of the live lanes take part.
         uint32_t tm = __ballot_sync(FULL, live && tgroup.y != 0);
-        const uint32_t other = __ballot_sync(FULL, live && (ngroup.y > 0x00ffffffu || tgroup.y == 0));   // lanes that progress without it
         const int live_n = __popc(__ballot_sync(FULL, live));
-        if (tm != 0 && (__popc(tm) * 100 >= tri_min_pct * live_n || other == 0)) {
+        // (when no live lane can do anything else, every live lane holds triangles and the quorum is met: tri_min_pct <= 100)
+        if (tm != 0 && __popc(tm) * 100 >= tri_min_pct * live_n) {
             do {
                 if (live && tgroup.y != 0) {
                     const uint32_t ti = highest_bit(tgroup.y);

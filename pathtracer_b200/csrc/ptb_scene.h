@@ -547,8 +547,14 @@ PTB_HD bool shard_block_sends(int tile_id, int i, int j, int W, int H, int tile,
     return false;
 }
 
+// sample index of a path within its pass: path % spp_pass.  spp_pass is a power of two for every frame whose pixel count is one (pool / pixels);
+// the general remainder is 30 instructions and was taken twice per shaded path (ncu r02x: 5 % of k_shade's instructions).
+PTB_HD int path_sample(const FrameDev& f, int path) {
+    const int m = f.spp_pass - 1;
+    return (f.spp_pass & m) == 0 ? (path & m) : path % f.spp_pass;
+}
 PTB_HD uint64_t path_inc(const FrameDev& f, int path) {  // pcg32 stream increment of the path's (pixel,sample) stream
-    return (((uint64_t)(uint32_t)(f.k0 + (path % f.spp_pass)) ^ ((uint64_t)f.seed << 32)) << 1) | 1ULL;
+    return (((uint64_t)(uint32_t)(f.k0 + path_sample(f, path)) ^ ((uint64_t)f.seed << 32)) << 1) | 1ULL;
 }
 // path state word (weight.w): depth (low 16) | show_lights | showenvmap | has_had_subsurface_interaction | pcg32 stream kind
 // (0: the sample's own stream, 1: fog fork, 2: ghost fork; oracle/build_ref.py patch 7) | fog contribution awaiting its hit
@@ -758,7 +764,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
         // -- continuation (570-632)
         const uint32_t pix = p.pixel[path];
         float sx, sy;
-        extensible_lattice_2d((uint32_t)(f.k0 + (path % f.spp_pass)), sx, sy);
+        extensible_lattice_2d((uint32_t)(f.k0 + path_sample(f, path)), sx, sy);
         const float r1 = frac_pos(f.rpp[2 * pix] + sx);
         const float r2 = frac_pos(f.rpp[2 * pix + 1] + sy);
         float pdf;
@@ -1155,7 +1161,7 @@ PTB_HD void shade_branch_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, 
         }
         // -- continuation (570-632)
         float sx, sy;
-        extensible_lattice_2d((uint32_t)(f.k0 + ((int)root % f.spp_pass)), sx, sy);
+        extensible_lattice_2d((uint32_t)(f.k0 + path_sample(f, (int)root)), sx, sy);
         const float r1 = frac_pos(f.rpp[2 * pix] + sx);
         const float r2 = frac_pos(f.rpp[2 * pix + 1] + sy);
         float pdf;

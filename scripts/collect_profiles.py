@@ -74,6 +74,7 @@ def traffic(tag, rep):
             "issue_active_pct": mean_of("smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "active_lanes_per_instruction": mean_of("smsp__thread_inst_executed_per_inst_executed.ratio"),
             "fma_pipe_active_pct": mean_of("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+            "alu_pipe_active_pct": mean_of("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
             "dram_throughput_pct": mean_of("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
             "l2_throughput_pct": mean_of("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
             "l1_hit_pct": mean_of("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": mean_of("lts__t_sector_hit_rate.pct"),
@@ -99,6 +100,7 @@ def shade_record(tag, w, out):
         "issue_active_pct": mean("smsp__issue_active.avg.pct_of_peak_sustained_active"),
         "active_lanes_per_instruction": mean("smsp__thread_inst_executed_per_inst_executed.ratio"),
         "fma_pipe_active_pct": mean("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+        "alu_pipe_active_pct": mean("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
         "dram_throughput_pct": mean("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         "l2_throughput_pct": mean("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
         "l1_hit_pct": mean("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": mean("lts__t_sector_hit_rate.pct"),
