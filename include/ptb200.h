@@ -174,6 +174,22 @@ typedef struct ptb_pointset {
 } ptb_pointset;
 #define PTB_OBJ_DISPLAY_EDGES (1 << 4)
 int ptb_add_pointset(ptb_ctx*, const ptb_pointset*, const ptb_xform*, int flags, int* out_id);
+/* replaces: `new Yarns(file)` + addObject (TriangleMesh.h:265-312, TriangleMesh.cpp:1519-1737; the GUI adds one for a dropped `.yarn`
+ * file, mainApp.cpp:2413-2416) with the segments passed in memory, as Yarns holds them in `cyls` after its constructor: segment i is
+ * the open tube `Cylinder(A[i], B[i], R[i])` (Geometry.h:731-846: no caps, only the nearer positive root is tried).  The reference's
+ * constructor scales the file's points by 50 and uses R = 0.1 (ptb_yarnfile_read does the same).  Every segment is its own
+ * default-constructed Object there, so a yarn is always shaded with queryMaterial's no-texture defaults (Kd = 1, Ks = 0, Ne = 1,
+ * opaque: Geometry.h:404-441) and the unnormalised radial normal, never flipped; the Yarns object contributes its transform, its
+ * BRDF and its mirror / ghost flags.  Materials set on a yarns object are therefore ignored, like there.  Segments are a third leaf
+ * type of the BVH8 (each enters as the triangles of a prism around it and is decided by Cylinder::intersection's arithmetic on the
+ * object-space ray).  Triangle ids reported for a yarns object are segment indices into these arrays. */
+typedef struct ptb_yarns {
+    const float* A;         /* n x 3  cyls[i]->A */
+    const float* B;         /* n x 3  cyls[i]->B */
+    const float* R;         /* n      cyls[i]->R */
+    int32_t      n;
+} ptb_yarns;
+int ptb_add_yarns(ptb_ctx*, const ptb_yarns*, const ptb_xform*, int flags, int* out_id);
 /* replaces: `new TriMesh(scene, file, scaling, offset, mirror, NULL, false, center)` + addObject
  * (TriangleMesh.cpp:714-841), with the reader's arrays passed in memory. */
 int ptb_add_mesh(ptb_ctx*, const ptb_mesh*, const ptb_xform*, int flags, int* out_id);

@@ -18,6 +18,7 @@
 #include "../prefix.h"
 #include "../../include/ptb200.h"
 
+#include <float.h>
 #include <math.h>
 #include <omp.h>
 #include <stdio.h>
@@ -212,7 +213,7 @@ typedef struct { vec lo, hi; } box;
 typedef struct { int isleaf, fg, fd; box bb; } bnode;                       /* BVHNodesT, TriangleMesh.h:6-13 */
 typedef struct { int vtx[3], uv[3], n[3], group; } tindex;                  /* TriangleIndices, TriangleMesh.h:53-65 */
 typedef struct { vec A, u, v, N; float m11, m12, m22, invdetm; float uvs[3][2]; vec normals[3]; } tsoup; /* Triangle, 67-111 */
-enum { T_MESH, T_SPHERE, T_PLANE, T_CYLINDER, T_POINTSET };
+enum { T_MESH, T_SPHERE, T_PLANE, T_CYLINDER, T_POINTSET, T_YARNS };
 typedef struct {
     int type, miroir, flip_normals, interp_normals, brdf, ghost;
     const double* merl;
@@ -224,6 +225,7 @@ typedef struct {
     vec O; float R, R2; int has_envmap; const uint8_t* envtex; int envW, envH;   /* Sphere */
     vec A, vecN;                                                              /* Plane (Cylinder: A) */
     int np, display_edges; vec *pt_pos, *pt_nrm, *pt_col; double* pt_rad; int* pt_perm;   /* PointSet: vertices, normals, colors (NULL: none), radius; perm: original index */
+    int ny; vec *yA, *yB, *yd; float *yR, *ylen; int* y_perm;                 /* Yarns: cyls[i]->A, B, d, R, len (TriangleMesh.h:265-312); perm: index handed in */
     vec cylB, cyld; float cyllen;                                             /* Cylinder: B, d, len (Geometry.h:734-738, 843-844) */
     int nv, nn, nuv, nt;                                                      /* TriMesh */
     vec *vertices, *normals; float* uvs; tindex* indices; tsoup* soup; vec* tangent_soup; int* permuted;
@@ -848,6 +850,131 @@ static int cylinder_hit(const object* cy, vec o, vec d, vec* P, float* t, matval
     return 1;
 }
 
+/* ---- Yarns (TriangleMesh.h:265-312, TriangleMesh.cpp:1519-1737): a binary BVH over Cylinder segments --------------------- */
+static vec yr3(const object* g, int i) { return V(g->yR[i], g->yR[i], g->yR[i]); }
+static box yarn_bbox(const object* g, int i0, int i1) {                                           /* build_bbox, 1519-1533 */
+    box r; r.hi = V(-FLT_MAX, -FLT_MAX, -FLT_MAX); r.lo = V(FLT_MAX, FLT_MAX, FLT_MAX);
+    for (int i = i0; i < i1; i++) {
+        r.lo = vmin3(r.lo, vsub(g->yA[i], yr3(g, i))); r.hi = vmax3(r.hi, vadd(g->yA[i], yr3(g, i)));
+        r.lo = vmin3(r.lo, vsub(g->yB[i], yr3(g, i))); r.hi = vmax3(r.hi, vadd(g->yB[i], yr3(g, i)));
+    }
+    return r;
+}
+static vec yarn_center(const object* g, int i) { return vdiv(vadd(g->yA[i], g->yB[i]), 2.f); }
+static box yarn_centers_bbox(const object* g, int i0, int i1) {                                   /* build_centers_bbox, 1535-1548 */
+    box r; r.hi = yarn_center(g, i0); r.lo = r.hi;
+    for (int i = i0; i < i1; i++) { vec c = yarn_center(g, i); r.lo = vmin3(r.lo, c); r.hi = vmax3(r.hi, c); }
+    return r;
+}
+static float yarn_center_dim(const object* g, int i, int dim) { return (float)((vget(g->yA[i], dim) + vget(g->yB[i], dim)) / 2.); }
+static void yarn_bvh_recur(object* g, int node, int i0, int i1, int depth) {                      /* build_bvh_recur, 1556-1647 */
+    if (g->n_nodes == g->cap_nodes) { g->cap_nodes *= 2; g->nodes = (bnode*)realloc(g->nodes, sizeof(bnode) * (size_t)g->cap_nodes); }
+    bnode n; n.bb = yarn_bbox(g, i0, i1); n.fg = i0; n.fd = i1; n.isleaf = 1;
+    g->nodes[g->n_nodes++] = n;
+    if (depth > g->bvh_depth) g->bvh_depth = depth;
+    box cb = yarn_centers_bbox(g, i0, i1);
+    vec diag = vsub(cb.hi, cb.lo);
+    int dim;
+    if (diag.x >= diag.y && diag.x >= diag.z) dim = 0; else if (diag.y >= diag.x && diag.y >= diag.z) dim = 1; else dim = 2;
+    float best_factor = 0.5f, best_area = INFINITY; /* 1E50 as float */
+    for (int k = 0; k < 16; k++) {
+        float f = (k + 1) / (float)(16 + 1);
+        float split = vget(cb.lo, dim) + vget(diag, dim) * f;
+        box L = {V(1E10f, 1E10f, 1E10f), V(-1E10f, -1E10f, -1E10f)}, Rb = L;
+        int nl = 0, nr = 0;
+        for (int i = i0; i < i1; i++) {
+            box* bb = (yarn_center_dim(g, i, dim) <= split) ? &L : &Rb;
+            bb->lo = vmin3(bb->lo, vsub(g->yA[i], yr3(g, i))); bb->lo = vmin3(bb->lo, vsub(g->yB[i], yr3(g, i)));
+            bb->hi = vmax3(bb->hi, vadd(g->yA[i], yr3(g, i))); bb->hi = vmax3(bb->hi, vadd(g->yB[i], yr3(g, i)));
+            if (bb == &L) nl++; else nr++;
+        }
+        float sum = box_area(&L) * nl + box_area(&Rb) * nr;
+        if (sum < best_area) { best_factor = f; best_area = sum; }
+    }
+    float split = vget(cb.lo, dim) + vget(diag, dim) * best_factor;
+    int pivot = i0 - 1;
+    for (int i = i0; i < i1; i++) {
+        if (yarn_center_dim(g, i, dim) <= split) {
+            pivot++;                                                  /* std::swap(cyls[i], cyls[pivot]) */
+            vec tv = g->yA[i]; g->yA[i] = g->yA[pivot]; g->yA[pivot] = tv;
+            tv = g->yB[i]; g->yB[i] = g->yB[pivot]; g->yB[pivot] = tv;
+            tv = g->yd[i]; g->yd[i] = g->yd[pivot]; g->yd[pivot] = tv;
+            float tf = g->yR[i]; g->yR[i] = g->yR[pivot]; g->yR[pivot] = tf;
+            tf = g->ylen[i]; g->ylen[i] = g->ylen[pivot]; g->ylen[pivot] = tf;
+            int tp = g->y_perm[i]; g->y_perm[i] = g->y_perm[pivot]; g->y_perm[pivot] = tp;
+        }
+    }
+    if (pivot < i0 || pivot >= i1 - 1 || i1 <= i0 + 4) return;
+    g->nodes[node].isleaf = 0;
+    g->nodes[node].fg = g->n_nodes;
+    yarn_bvh_recur(g, g->nodes[node].fg, i0, pivot + 1, depth + 1);
+    g->nodes[node].fd = g->n_nodes;
+    yarn_bvh_recur(g, g->nodes[node].fd, pivot + 1, i1, depth + 1);
+}
+/* cyls[i]->intersection (Geometry.h:740-766): the segment's own Object is default-constructed, so queryMaterial answers with its
+ * no-texture defaults (white diffuse, Geometry.h:404-441) and flip_normals is false whatever the Yarns object's flags say */
+static int yarn_cyl_hit(const object* g, int i, vec o, vec d, vec* P, float* t, matvals* mat) {
+    vec ax = g->yd[i];
+    vec X = vsub(d, vscale(vdot(d, ax), ax));
+    vec oa = vsub(o, g->yA[i]);
+    vec Y = vsub(oa, vscale(vdot(oa, ax), ax));
+    float a = vnorm2(X);
+    float b = 2 * vdot(X, Y);
+    float c = vnorm2(Y) - g->yR[i] * g->yR[i];
+    float delta = b * b - 4 * a * c;
+    if (delta < 0) return 0;
+    float sdelta = sqrtf(delta);
+    float t2 = (-b + sdelta) / (2 * a);
+    if (t2 < 0) return 0;
+    float t1 = (-b - sdelta) / (2 * a);
+    if (t1 > 0) *t = t1; else *t = t2;
+    *P = vadd(o, vscale(*t, d));
+    float dP = vdot(vsub(*P, g->yA[i]), ax);
+    if (dP < 0 || dP > g->ylen[i]) return 0;
+    vec proj = vadd(g->yA[i], vscale(dP, ax));
+    mat->Kd = V(1, 1, 1); mat->Ks = V(0, 0, 0); mat->Ksub = V(0, 0, 0); mat->Ne = V(1, 1, 1); mat->transp = 0; mat->refr_index = 1.3f; mat->Ke = V(0, 0, 0);
+    mat->shadingN = vsub(*P, proj);
+    return 1;
+}
+/* Yarns::intersection (TriangleMesh.cpp:1652-1737); intersection_shadow is the same call (TriangleMesh.h:293-298) */
+static int yarn_hit(const object* g, vec o, vec d, vec* P, float* t, matvals* mat, float cur_best_t, int* tri_id) {
+    *t = cur_best_t;
+    int has = 0, best = -1;
+    float tl, tr_, lt;
+    vec lp;
+    invray r; r.o = o; r.id = V(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    char s[3] = {(char)(r.id.x >= 0 ? 1 : 0), (char)(r.id.y >= 0 ? 1 : 0), (char)(r.id.z >= 0 ? 1 : 0)};
+    if (!box_invd(&g->bvh_bbox, &r, s, &tl)) return 0;
+    if (tl > cur_best_t) return 0;
+    int l[50]; float tn[50]; int top = -1;
+    l[++top] = 0; tn[top] = tl;
+    while (top >= 0) {
+        if (tn[top] > *t) { top--; continue; }
+        int cur = l[top--];
+        int fg = g->nodes[cur].fg, fd = g->nodes[cur].fd;
+        if (!g->nodes[cur].isleaf) {
+            int gl = box_invd_x(&g->nodes[fg].bb, &r, s, &tl, s[0] == 1) && tl < *t;
+            int gr = box_invd_x(&g->nodes[fd].bb, &r, s, &tr_, s[0] == 1) && tr_ < *t;
+            if (gl && gr) {
+                if (tl < tr_) { l[++top] = fd; tn[top] = tr_; l[++top] = fg; tn[top] = tl; }
+                else { l[++top] = fg; tn[top] = tl; l[++top] = fd; tn[top] = tr_; }
+            } else {
+                if (gl) { l[++top] = fg; tn[top] = tl; }
+                if (gr) { l[++top] = fd; tn[top] = tr_; }
+            }
+        } else {
+            for (int i = fg; i < fd; i++)
+                if (yarn_cyl_hit(g, i, o, d, &lp, &lt, mat) && lt < *t) { has = 1; best = i; *t = lt; }
+        }
+    }
+    if (has) {
+        *tri_id = best;
+        yarn_cyl_hit(g, best, o, d, &lp, &lt, mat);
+        *P = lp;
+    }
+    return has;
+}
+
 /* Scene::intersection (Geometry.cpp:589-688) */
 static int scene_hit(const struct ptb_ctx* c, vec o, vec d, vec* P, int* id, float* min_t, matvals* mat, int* tri_id, unsigned long long* counter) {
     int has = 0;
@@ -862,6 +989,7 @@ static int scene_hit(const struct ptb_ctx* c, vec o, vec d, vec* P, int* id, flo
         else if (ob->type == T_SPHERE) { h = sphere_hit(ob, ol, dl, &lp, &t, &lm, 0); if (h) *tri_id = -1; }
         else if (ob->type == T_CYLINDER) { h = cylinder_hit(ob, ol, dl, &lp, &t, &lm); if (h) *tri_id = -1; }
         else if (ob->type == T_POINTSET) h = pts_hit(ob, ol, dl, &lp, &t, &lm, *min_t, tri_id, 0, 0);
+        else if (ob->type == T_YARNS) h = yarn_hit(ob, ol, dl, &lp, &t, &lm, *min_t, tri_id);
         else { h = plane_hit(ob, ol, dl, &lp, &t, &lm, 0); if (h) *tri_id = -1; }
         if (h && t < *min_t) { has = 1; *min_t = t; *P = lp; *id = i; *mat = lm; }
     }
@@ -882,6 +1010,7 @@ static int scene_shadow(const struct ptb_ctx* c, vec o, vec d, float dist_light,
         else if (ob->type == T_SPHERE) h = sphere_hit(ob, ol, dl, &P, &t, &m, 1);
         else if (ob->type == T_CYLINDER) { m = matvals_default(); h = cylinder_hit(ob, ol, dl, &P, &t, &m); }
         else if (ob->type == T_POINTSET) h = pts_hit(ob, ol, dl, &P, &t, &m, min_t, &tid, 1, dist_light);
+        else if (ob->type == T_YARNS) { m = matvals_default(); h = yarn_hit(ob, ol, dl, &P, &t, &m, min_t, &tid); }
         else h = plane_hit(ob, ol, dl, &P, &t, &m, 1);
         if (h && t < dist_light * 0.999) return 1;
     }
@@ -1260,6 +1389,7 @@ static void free_object(object* o) {
     for (int k = 0; k < 3; k++) { free(o->kframe[k]); free(o->kval[k]); }
     free(o->vertices); free(o->normals); free(o->uvs); free(o->indices); free(o->soup); free(o->tangent_soup); free(o->permuted); free(o->nodes);
     free(o->pt_pos); free(o->pt_nrm); free(o->pt_col); free(o->pt_rad); free(o->pt_perm);
+    free(o->yA); free(o->yB); free(o->yd); free(o->yR); free(o->ylen); free(o->y_perm);
     free(o);
 }
 static void prog_free(ptb_ctx* c);
@@ -1312,6 +1442,26 @@ int ptb_add_pointset(ptb_ctx* c, const ptb_pointset* p, const ptb_xform* xf, int
     g->cap_nodes = 64; g->nodes = (bnode*)malloc(sizeof(bnode) * (size_t)g->cap_nodes); g->n_nodes = 0; g->bvh_depth = 0;
     g->bvh_bbox = pts_bbox(g, 0, n);                                       /* build_bvh, 28-32 */
     pts_bvh_recur(g, 0, 0, n, 0);
+    if (out_id) *out_id = c->n_objs - 1;
+    return PTB_OK;
+}
+/* `new Yarns(file)` (TriangleMesh.h:268-290) with the segments passed in memory: cyls[i] = Cylinder(A, B, R), then build_bvh */
+int ptb_add_yarns(ptb_ctx* c, const ptb_yarns* y, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !y || !y->A || !y->B || !y->R || y->n <= 0) return PTB_ERR_INVALID;
+    int n = y->n;
+    object* g = new_object(c, T_YARNS, xf, flags, V(0, 0, 0));
+    g->ny = n;
+    g->yA = (vec*)malloc(sizeof(vec) * (size_t)n); g->yB = (vec*)malloc(sizeof(vec) * (size_t)n); g->yd = (vec*)malloc(sizeof(vec) * (size_t)n);
+    g->yR = (float*)malloc(sizeof(float) * (size_t)n); g->ylen = (float*)malloc(sizeof(float) * (size_t)n); g->y_perm = (int*)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        g->yA[i] = V(y->A[3 * i], y->A[3 * i + 1], y->A[3 * i + 2]); g->yB[i] = V(y->B[3 * i], y->B[3 * i + 1], y->B[3 * i + 2]); g->yR[i] = y->R[i];
+        g->yd[i] = vnormalize(vsub(g->yB[i], g->yA[i]));                       /* Cylinder(A, B, R), Geometry.h:734-738 */
+        g->ylen[i] = sqrtf(vnorm2(vsub(g->yB[i], g->yA[i])));
+        g->y_perm[i] = i;
+    }
+    g->cap_nodes = 64; g->nodes = (bnode*)malloc(sizeof(bnode) * (size_t)g->cap_nodes); g->n_nodes = 0; g->bvh_depth = 0;
+    g->bvh_bbox = yarn_bbox(g, 0, n);                                      /* build_bvh, 1550-1554 */
+    yarn_bvh_recur(g, 0, 0, n, 0);
     if (out_id) *out_id = c->n_objs - 1;
     return PTB_OK;
 }
@@ -1774,7 +1924,8 @@ int ptb_primary_ids(ptb_ctx* c, const ptb_camera* cam, int W, int H, int32_t* ob
             int hit = scene_hit(c, ro, rd, &P, &id, &t, &m, &tri, NULL);
             int32_t oid = -1, tid = -1;
             if (hit) { oid = id; if (c->objs[id]->type == T_MESH && tri >= 0) tid = c->objs[id]->permuted[tri];
-                       if (c->objs[id]->type == T_POINTSET && tri >= 0) tid = c->objs[id]->pt_perm[tri]; }
+                       if (c->objs[id]->type == T_POINTSET && tri >= 0) tid = c->objs[id]->pt_perm[tri];
+                       if (c->objs[id]->type == T_YARNS && tri >= 0) tid = c->objs[id]->y_perm[tri]; }
             if (obj_id) obj_id[(size_t)i * W + j] = oid;
             if (tri_id) tri_id[(size_t)i * W + j] = tid;
             if (tout) tout[(size_t)i * W + j] = hit ? t : -1.f;

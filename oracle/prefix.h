@@ -17,6 +17,7 @@
 #define ptb_add_plane          ORC_NAME(add_plane)
 #define ptb_add_cylinder       ORC_NAME(add_cylinder)
 #define ptb_add_pointset       ORC_NAME(add_pointset)
+#define ptb_add_yarns          ORC_NAME(add_yarns)
 #define ptb_add_mesh           ORC_NAME(add_mesh)
 #define ptb_set_group_material ORC_NAME(set_group_material)
 #define ptb_set_brdf           ORC_NAME(set_brdf)

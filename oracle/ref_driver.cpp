@@ -167,6 +167,27 @@ int ptb_add_pointset(ptb_ctx* c, const ptb_pointset* p, const ptb_xform* xf, int
     return PTB_OK;
 }
 
+int ptb_add_yarns(ptb_ctx* c, const ptb_yarns* y, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c || !y || !y->A || !y->B || !y->R || y->n <= 0) return PTB_ERR_INVALID;
+    Yarns* ys = new Yarns();                             // what Yarns(filename) leaves behind (TriangleMesh.h:268-290), without its file reader
+    std::map<const Cylinder*, int> handed;
+    for (int i = 0; i < y->n; i++) {
+        Cylinder* cy = new Cylinder(Vector(y->A[3 * i], y->A[3 * i + 1], y->A[3 * i + 2]), Vector(y->B[3 * i], y->B[3 * i + 1], y->B[3 * i + 2]), y->R[i]);
+        ys->cyls.push_back(cy);
+        handed[cy] = i;
+    }
+    ys->build_bvh(&ys->bvh, 0, (int)ys->cyls.size());
+    std::vector<int>& perm = c->pts_perm[ys];            // position after build_bvh -> index handed in
+    perm.resize(ys->cyls.size());
+    for (size_t j = 0; j < ys->cyls.size(); j++) perm[j] = handed[ys->cyls[j]];
+    ys->name = "in-memory";
+    apply_flags(ys, flags);
+    apply_xform(ys, xf, false);
+    c->rt->s.addObject(ys);
+    if (out_id) *out_id = (int)c->rt->s.objects.size() - 1;
+    return PTB_OK;
+}
+
 int ptb_add_cylinder(ptb_ctx* c, const float A[3], const float B[3], float R, const ptb_xform* xf, int flags, int* out_id) {
     if (!c || !A || !B) return PTB_ERR_INVALID;
     Cylinder* cy = new Cylinder(Vector(A[0], A[1], A[2]), Vector(B[0], B[1], B[2]), R);

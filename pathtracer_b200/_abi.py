@@ -59,6 +59,10 @@ class PointSetDesc(C.Structure):
     _fields_ = [("points", _fp), ("normals", _fp), ("radii", _fp), ("colors", _fp), ("n", C.c_int32)]
 
 
+class YarnsDesc(C.Structure):
+    _fields_ = [("A", _fp), ("B", _fp), ("R", _fp), ("n", C.c_int32)]
+
+
 class Camera(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("direction", C.c_float * 3), ("up", C.c_float * 3),
                 ("fov", C.c_float), ("focus_distance", C.c_float), ("aperture", C.c_float)]
@@ -98,7 +102,7 @@ class KernelTimes(C.Structure):
 
 
 # every symbol include/ptb200.h declares (tests check the product library exports all of them)
-SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_cylinder", "add_pointset", "add_mesh",
+SYMBOLS = ["create", "destroy", "last_error", "version", "add_sphere", "add_plane", "add_cylinder", "add_pointset", "add_yarns", "add_mesh",
            "set_group_material", "set_brdf", "add_merl", "set_envmap", "set_light", "set_fog", "set_background", "set_keyframes", "set_frame", "commit", "render",
            "render_accum", "resolve", "shard_pack_size", "shard_pack", "shard_unpack_add", "primary_ids",
            "set_option", "get_scene_info", "kat", "get_kernel_times", "render_denoiser_inputs", "progressive_begin", "progressive_pass",
@@ -200,6 +204,7 @@ class Lib:
             "add_plane": (C.c_int, [vp, _fp, _fp, C.POINTER(Xform), C.c_int, ip]),
             "add_cylinder": (C.c_int, [vp, _fp, _fp, C.c_float, C.POINTER(Xform), C.c_int, ip]),
             "add_pointset": (C.c_int, [vp, C.POINTER(PointSetDesc), C.POINTER(Xform), C.c_int, ip]),
+            "add_yarns": (C.c_int, [vp, C.POINTER(YarnsDesc), C.POINTER(Xform), C.c_int, ip]),
             "add_mesh": (C.c_int, [vp, C.POINTER(Mesh), C.POINTER(Xform), C.c_int, ip]),
             "set_group_material": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(Material)]),
             "set_brdf": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),

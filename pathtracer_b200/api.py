@@ -231,6 +231,34 @@ class PointSet(Object):
         self.rotation_center = np.full(3, np.nan, np.float32)      # init: the mean of the points
 
 
+class Yarns(Object):
+    """TriangleMesh.h:265-312: a bundle of yarn curves, every segment an open Cylinder under one BVH.  The reference shades a yarn
+    with its segments' default material (white diffuse) whatever the object's slots hold; transform, BRDF, mirror and ghost flags
+    are the object's."""
+
+    def __init__(self, A, B, R, mirror=False):
+        super().__init__()
+        self.A, self.B = f32(A).reshape(-1, 3), f32(B).reshape(-1, 3)
+        self.R = f32(np.broadcast_to(np.asarray(R, np.float32), (len(self.A),))).reshape(-1)
+        assert len(self.A) == len(self.B) == len(self.R) and len(self.A) > 0
+        self.miroir = mirror
+        self.rotation_center = np.zeros(3, np.float32)
+
+    @classmethod
+    def from_file(cls, path):
+        """`new Yarns(file)` (TriangleMesh.h:268-290): `nbyarns`, then per yarn `nbsegments` and that many points; consecutive points
+        times 50 are joined by cylinders of radius 0.1."""
+        tok = open(path).read().split()
+        pos, A, B = 1, [], []
+        for _ in range(int(tok[0])):
+            n = int(tok[pos]); pos += 1
+            pts = np.array(tok[pos:pos + 3 * n], np.float32).reshape(n, 3) * np.float32(50.0)
+            pos += 3 * n
+            A.append(pts[:-1]); B.append(pts[1:])
+        A, B = np.concatenate(A), np.concatenate(B)
+        return cls(A, B, np.full(len(A), 0.1, np.float32))
+
+
 class TriMesh(Object):
     """In-memory equivalent of `new TriMesh(scene, file, scaling, offset, mirror, NULL, false, center)`
     (TriangleMesh.cpp:714-841): arrays as a file reader would have produced them."""
@@ -484,6 +512,9 @@ class Raytracer:
             elif isinstance(o, PointSet):
                 d = _abi.PointSetDesc(fptr(o.points), fptr(o.normals), fptr(o.radii), fptr(o.colors), len(o.points))
                 L.check(L.add_pointset(ctx, C.byref(d), C.byref(xf), o._flags(), C.byref(oid)), ctx)
+            elif isinstance(o, Yarns):
+                d = _abi.YarnsDesc(fptr(o.A), fptr(o.B), fptr(o.R), len(o.A))
+                L.check(L.add_yarns(ctx, C.byref(d), C.byref(xf), o._flags(), C.byref(oid)), ctx)
             elif isinstance(o, Cylinder):
                 L.check(L.add_cylinder(ctx, fptr(f32(o.A)), fptr(f32(o.B)), o.R, C.byref(xf), o._flags(), C.byref(oid)), ctx)
             elif isinstance(o, TriMesh):

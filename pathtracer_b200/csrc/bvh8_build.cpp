@@ -190,7 +190,7 @@ inline uint8_t exponent_byte(float extent, float coord_slack, int e_lo) {
 
 }  // namespace
 
-void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_nodes, std::vector<uint32_t>& leaf_order, Bvh8Stats& stats) {
+void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_nodes, std::vector<uint32_t>& leaf_order, Bvh8Stats& stats, const float* boxes6) {
     out_nodes.clear(); leaf_order.clear();
     stats = Bvh8Stats();
     if (n_tri <= 0) return;
@@ -202,6 +202,9 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
         Box bx; bx.reset();
         const float* v = verts9 + 9 * (size_t)i;
         bx.grow(v); bx.grow(v + 3); bx.grow(v + 6);
+        // a primitive that stands for a volume (the covering triangles of a yarn segment, ptb_scene.h) brings the volume's box: a ray
+        // must reach its triangles whenever it can reach the volume, wherever the triangles themselves lie
+        if (boxes6 && boxes6[6 * (size_t)i] <= boxes6[6 * (size_t)i + 3]) { bx.reset(); bx.grow(boxes6 + 6 * (size_t)i); bx.grow(boxes6 + 6 * (size_t)i + 3); }
         B.pbox[i] = bx;
         for (int k = 0; k < 3; k++) B.pcen[3 * (size_t)i + k] = 0.5f * (bx.lo[k] + bx.hi[k]);
         B.idx[i] = (uint32_t)i;

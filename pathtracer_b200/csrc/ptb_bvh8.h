@@ -50,6 +50,7 @@ static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 #endif
 #define PTB_TRI_FLAG_ALPHA 1u  /* tri.w0 bit: this triangle's group has an alpha map that can reject */
 #define PTB_TRI_FLAG_DISC 4u   /* tri.w0 bit: the triangle covers a disc of a point set (disc_cover_triangle, ptb_scene.h); tri_exact runs the disc test */
+#define PTB_TRI_T_CUT (1.f - 1e-4f)   /* tri.w2 (e2.w) of an ordinary triangle: the fast test drops a hit when t * w2 >= t_best; 0 = never (volume covers, ptb_scene.h) */
 #define PTB_TRI_FLAG_GHOST 2u  /* tri.w0 bit: the triangle belongs to a ghost object; shadow rays pass through it (Geometry.cpp:722) */
 
 // ---- the half grid ---------------------------------------------------------------------------------------------------------------
@@ -379,7 +380,8 @@ PTB_HD bool tri_test(const F4& a, const F4& b, const F4& c, const RayPrep& r, fl
     const float m = fminf(fminf(u, v), 1.f - u - v);
 #if PTB_EDGE_EPS_ON
     // inside the triangle grown by PTB_EDGE_EPS, in front of the origin and not clearly beyond the best hit ...
-    if (!(m >= -PTB_EDGE_EPS) || !(tt >= 0.f) || !(tt * (1.f - 1e-4f) < tbest)) return false;
+    // (c.w = PTB_TRI_T_CUT, or 0 on the covering triangles of a volume, whose own hit may be nearer than the face the ray crosses)
+    if (!(m >= -PTB_EDGE_EPS) || !(tt >= 0.f) || !(tt * c.w < tbest)) return false;
     // ... and near an edge, or alpha-tested (b.w = PTB_EDGE_EPS, or +inf when the texel the uv lands on must be the reference's):
     // the reference's arithmetic decides
     if (m < b.w && tri_exact_available(ex)) return tri_exact(ex, prim, r.o, r.d, tbest, t, b1, b2);
@@ -413,7 +415,7 @@ PTB_HD int tri_test_classify(const F4& a, const F4& b, const F4& c, const RayPre
     const float m = fminf(fminf(u, v), 1.f - u - v);
 #if PTB_EDGE_EPS_ON
     // same instruction count as the plain accept test for the common outcome (a miss): one min3 and three compares
-    if (!(m >= -PTB_EDGE_EPS) || !(tt >= 0.f) || !(tt * (1.f - 1e-4f) < tbest)) return 0;   // (t of the two formulations differs in the last bits)
+    if (!(m >= -PTB_EDGE_EPS) || !(tt >= 0.f) || !(tt * c.w < tbest)) return 0;   // c.w = PTB_TRI_T_CUT (t of the two formulations differs in the last bits) or 0 (yarn covers)
     if (m < b.w) return 2;            // b.w = PTB_EDGE_EPS, or +inf on alpha-tested triangles
     if (!(tt < tbest)) return 0;
 #else

@@ -486,21 +486,33 @@ __device__ __forceinline__ V3 xf_point_rn(const float* m, V3 v) {
               add_rn(add_rn(add_rn(mul_rn(m[4], v.x), mul_rn(m[5], v.y)), mul_rn(m[6], v.z)), m[7]),
               add_rn(add_rn(add_rn(mul_rn(m[8], v.x), mul_rn(m[9], v.y)), mul_rn(m[10], v.z)), m[11]));
 }
+// world-space corners of stored triangle `t` at the objects' current matrices: a mesh triangle's own corners, the covering triangle of a
+// point-set disc (centre A, normal B.xyz, radius B.w) or one of the covering triangles of a yarn segment (A, B, radius B.w; which one in
+// bits 28..30 of A.w)
+__device__ __forceinline__ void refit_corners(const F4* __restrict__ tris_obj, const ObjectDev* __restrict__ objects, size_t t, V3& v0, V3& v1, V3& v2) {
+    const F4 A = tris_obj[3 * t], B = tris_obj[3 * t + 1];
+    const ObjectDev& ob = objects[f2u(A.w) & 0x0fffffffu];
+    const float* m = ob.trans;
+    if (ob.type == OBJ_POINTSET) {
+        const float sc_ = sqrtf(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]);
+        disc_cover_triangle(xf_point_rn(m, v3(A.x, A.y, A.z)), xf_rot(ob.rot, v3(B.x, B.y, B.z)), B.w * sc_, v0, v1, v2);
+    } else if (ob.type == OBJ_YARNS) {
+        const float sc_ = sqrtf(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]);
+        yarn_cover_triangle(xf_point_rn(m, v3(A.x, A.y, A.z)), xf_point_rn(m, v3(B.x, B.y, B.z)), B.w * sc_, (int)(f2u(A.w) >> 28), v0, v1, v2);
+    } else {
+        const F4 C = tris_obj[3 * t + 2];
+        v0 = xf_point_rn(m, v3(A.x, A.y, A.z)); v1 = xf_point_rn(m, v3(B.x, B.y, B.z)); v2 = xf_point_rn(m, v3(C.x, C.y, C.z));
+    }
+}
 __global__ void __launch_bounds__(256) k_refit_tris(const F4* __restrict__ tris_obj, const ObjectDev* __restrict__ objects, F4* tris, size_t n_tri) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_tri) return;
-    const F4 A = tris_obj[3 * k], B = tris_obj[3 * k + 1], C = tris_obj[3 * k + 2];
-    const ObjectDev& ob = objects[f2u(A.w)];
-    const float* m = ob.trans;
     V3 v0, v1, v2;
-    if (ob.type == OBJ_POINTSET) {      // a disc: its covering triangle at the new pose (centre A, normal B.xyz, radius B.w)
-        const float sc_ = sqrtf(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]);
-        disc_cover_triangle(xf_point_rn(m, v3(A.x, A.y, A.z)), xf_rot(ob.rot, v3(B.x, B.y, B.z)), B.w * sc_, v0, v1, v2);
-    } else { v0 = xf_point_rn(m, v3(A.x, A.y, A.z)); v1 = xf_point_rn(m, v3(B.x, B.y, B.z)); v2 = xf_point_rn(m, v3(C.x, C.y, C.z)); }
+    refit_corners(tris_obj, objects, k, v0, v1, v2);
     F4 q;
     q.x = v0.x; q.y = v0.y; q.z = v0.z; q.w = tris[3 * k].w; tris[3 * k] = q;                       // .w: the triangle's flags stay
     q.x = v1.x - v0.x; q.y = v1.y - v0.y; q.z = v1.z - v0.z; q.w = tris[3 * k + 1].w; tris[3 * k + 1] = q;   // .w: the edge threshold stays
-    q.x = v2.x - v0.x; q.y = v2.y - v0.y; q.z = v2.z - v0.z; q.w = 0; tris[3 * k + 2] = q;
+    q.x = v2.x - v0.x; q.y = v2.y - v0.y; q.z = v2.z - v0.z; q.w = tris[3 * k + 2].w; tris[3 * k + 2] = q;   // .w: the t cut stays
 }
 __device__ __forceinline__ uint32_t refit_exponent_byte(float extent, float coord_slack, int e_lo) {   // bvh8_build.cpp exponent_byte
     int e = e_lo;
@@ -533,23 +545,21 @@ __global__ void __launch_bounds__(128) k_refit_level(Node8* nodes, F4* node_box,
             const uint32_t cnt = __popc((valid24 >> (3 * s)) & 7u), t0 = nd.tri_base + __popc(valid24 & ((1u << (3 * s)) - 1u));
             for (uint32_t t = t0; t < t0 + cnt; t++) {
                 const F4 A = tris_obj[3 * (size_t)t];
-                const float* m = objects[f2u(A.w)].trans;
-                if (objects[f2u(A.w)].type == OBJ_POINTSET) {      // a disc: the box of its covering triangle
+                const ObjectDev& ob = objects[f2u(A.w) & 0x0fffffffu];
+                if (ob.type == OBJ_YARNS) {      // a covering triangle of a yarn segment: the tube's box (yarn_box), as at commit
                     const F4 Bq = tris_obj[3 * (size_t)t + 1];
-                    V3 q0, q1, q2;
-                    disc_cover_triangle(xf_point_rn(m, v3(A.x, A.y, A.z)), xf_rot(objects[f2u(A.w)].rot, v3(Bq.x, Bq.y, Bq.z)), Bq.w * sqrtf(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]), q0, q1, q2);
-                    const V3 qq[3] = {q0, q1, q2};
-                    for (int c = 0; c < 3; c++) {
-                        lo[s][0] = fminf(lo[s][0], qq[c].x); lo[s][1] = fminf(lo[s][1], qq[c].y); lo[s][2] = fminf(lo[s][2], qq[c].z);
-                        hi[s][0] = fmaxf(hi[s][0], qq[c].x); hi[s][1] = fmaxf(hi[s][1], qq[c].y); hi[s][2] = fmaxf(hi[s][2], qq[c].z);
-                    }
+                    const float* m = ob.trans;
+                    float blo[3], bhi[3];
+                    yarn_box(xf_point_rn(m, v3(A.x, A.y, A.z)), xf_point_rn(m, v3(Bq.x, Bq.y, Bq.z)), Bq.w * sqrtf(m[0] * m[0] + m[4] * m[4] + m[8] * m[8]), blo, bhi);
+                    for (int k = 0; k < 3; k++) { lo[s][k] = fminf(lo[s][k], blo[k]); hi[s][k] = fmaxf(hi[s][k], bhi[k]); }
                     continue;
                 }
+                V3 q0, q1, q2;
+                refit_corners(tris_obj, objects, (size_t)t, q0, q1, q2);
+                const V3 qq[3] = {q0, q1, q2};
                 for (int c = 0; c < 3; c++) {
-                    const F4 P = c == 0 ? A : tris_obj[3 * (size_t)t + c];
-                    const V3 w = xf_point_rn(m, v3(P.x, P.y, P.z));
-                    lo[s][0] = fminf(lo[s][0], w.x); lo[s][1] = fminf(lo[s][1], w.y); lo[s][2] = fminf(lo[s][2], w.z);
-                    hi[s][0] = fmaxf(hi[s][0], w.x); hi[s][1] = fmaxf(hi[s][1], w.y); hi[s][2] = fmaxf(hi[s][2], w.z);
+                    lo[s][0] = fminf(lo[s][0], qq[c].x); lo[s][1] = fminf(lo[s][1], qq[c].y); lo[s][2] = fminf(lo[s][2], qq[c].z);
+                    hi[s][0] = fmaxf(hi[s][0], qq[c].x); hi[s][1] = fmaxf(hi[s][1], qq[c].y); hi[s][2] = fmaxf(hi[s][2], qq[c].z);
                 }
             }
             used |= 1u << s;
@@ -1072,6 +1082,16 @@ int ptb_add_pointset(ptb_ctx* c, const ptb_pointset* ps, const ptb_xform* xf, in
     if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
     PTB_GUARD(c, {
         const int id = c->host.add_pointset(ps, xf, flags, c->err);
+        if (id < 0) return id;
+        if (out_id) *out_id = id;
+        return PTB_OK;
+    })
+}
+int ptb_add_yarns(ptb_ctx* c, const ptb_yarns* y, const ptb_xform* xf, int flags, int* out_id) {
+    if (!c) return PTB_ERR_INVALID;
+    if (c->committed) { c->err = "scene already committed"; return PTB_ERR_STATE; }
+    PTB_GUARD(c, {
+        const int id = c->host.add_yarns(y, xf, flags, c->err);
         if (id < 0) return id;
         if (out_id) *out_id = id;
         return PTB_OK;

@@ -17,8 +17,9 @@ struct Bvh8Stats {
     int half_c = 0;                        // the scene's half grid (ptb_bvh8.h half_grid_c), SceneDev::half_c
     std::vector<uint32_t> level_start;     // nodes are emitted breadth first: level l is [level_start[l], level_start[l + 1]) (refit walks them bottom-up)
 };
-// verts9: 9 floats per triangle (world space).  leaf_order[k] = input index of the k-th stored triangle.
-void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& nodes, std::vector<uint32_t>& leaf_order, Bvh8Stats& stats);
+// verts9: 9 floats per triangle (world space).  leaf_order[k] = input index of the k-th stored triangle.  boxes6 (or null): lo[3], hi[3]
+// per triangle, used instead of the triangle's own bounds where lo[0] <= hi[0] (NaN = no override).
+void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& nodes, std::vector<uint32_t>& leaf_order, Bvh8Stats& stats, const float* boxes6 = nullptr);
 
 struct HostTex {
     float mult[3] = {1, 1, 1};
@@ -38,6 +39,7 @@ struct HostObject {
     std::vector<float> vertices, normals, uvs, tangents;   // tangents: per vertex
     std::vector<int32_t> tri;              // n x 10
     std::vector<float> pt_pos, pt_nrm, pt_rad, pt_col;     // point set (PointSet::vertices / normals / radius / colors)
+    std::vector<float> yarn_a, yarn_b, yarn_r;             // yarns (Yarns::cyls[i]->A / B / R)
     float trans[12], inv_trans[12], rot[9];
     KeyTrack keys[3];                      // PTB_KEY_SCALE / _TRANSLATION / _ROTATION (Geometry.h:318-320)
 };
@@ -88,6 +90,7 @@ struct HostScene {
     int add_cylinder(const float A[3], const float B[3], float R, const ptb_xform* xf, int flags);
     int add_mesh(const ptb_mesh* m, const ptb_xform* xf, int flags, std::string& err);
     int add_pointset(const ptb_pointset* p, const ptb_xform* xf, int flags, std::string& err);
+    int add_yarns(const ptb_yarns* y, const ptb_xform* xf, int flags, std::string& err);
     int set_group_material(int obj, int group, const ptb_material* m, std::string& err);
     int flatten(FlatScene& out, std::string& err);
     // Scene::prepare_render at another frame for an already flattened scene: every object's matrices (build_matrix(current_frame)) and
@@ -112,8 +115,8 @@ inline void scene_header(SceneDev& sc, FlatScene& f) {
     for (size_t i = 0; i < f.objects.size(); i++) {
         ObjectDev& o = f.objects[i];
         if (o.flags & FLAG_GHOST) sc.has_ghost = 1;
-        if (o.type == OBJ_POINTSET || o.type == OBJ_CYLINDER) sc.has_exotic = 1;   // kernels with the Cylinder / PointSet code
-        if (o.type == OBJ_MESH || o.type == OBJ_POINTSET) continue;
+        if (o.type == OBJ_POINTSET || o.type == OBJ_CYLINDER || o.type == OBJ_YARNS) sc.has_exotic = 1;   // kernels with the Cylinder / PointSet / Yarns code
+        if (o.type == OBJ_MESH || o.type == OBJ_POINTSET || o.type == OBJ_YARNS) continue;
         if (sc.n_inline < PTB_INLINE_ANALYTIC) {
             AnalyticDev& a = sc.analytic[sc.n_inline++];
             a.type = o.type | ((o.flags & FLAG_GHOST) ? PTB_ANALYTIC_GHOST : 0); a.id = (int32_t)i; a.R2 = o.R2;

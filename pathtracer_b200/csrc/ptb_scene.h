@@ -16,7 +16,7 @@
 
 namespace ptb {
 
-enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2, OBJ_CYLINDER = 3, OBJ_POINTSET = 4 };
+enum { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_PLANE = 2, OBJ_CYLINDER = 3, OBJ_POINTSET = 4, OBJ_YARNS = 5 };
 enum { FLAG_MIRROR = 1, FLAG_FLIP = 2, FLAG_FLAT = 4, FLAG_GHOST = 8, FLAG_DISPLAY_EDGES = 16, FLAG_NOT_INLINE = 1 << 16 };
 // A point-set disc sits in the BVH8 as the triangle circumscribed about it (in its plane, inscribed radius 1.1 r): every ray that can
 // hit the disc hits that triangle's interior, the threshold in its e1.w is +inf, so k_trace classifies it "left for k_exact" like a
@@ -32,6 +32,41 @@ PTB_HD void disc_cover_triangle(V3 c, V3 n, float r, V3& v0, V3& v1, V3& v2) {
     v2 = c + R * (0.8660254f * u - 0.5f * w);
 }
 #define PTB_GROUP_DISC (-2)   /* TriUV::group of a point-set disc (its TriShade holds normal, colour, centre, radius) */
+// A yarn segment (an open Cylinder of a Yarns object) sits in the BVH8 as the EIGHT triangles of a prism around it (equilateral cross-
+// section of inscribed radius 1.1 r, the ends 0.1 r beyond A and B): a ray that meets the tube between its end planes is inside the prism
+// there, so it crosses the prism's boundary before (entering) or after (leaving: a ray that starts inside).  Like the disc's triangle
+// these are always "left for k_exact" (e1.w = +inf).  The face a ray leaves through may lie beyond a nearer hit although the tube
+// itself does not, so (a) their e2.w = 0 switches the `t < t_best` cut of the fast test off and (b) all eight enter the BVH8 with the
+// TUBE's box (yarn_box), not their own: a ray reaches them whenever it can reach the tube.  idx 0..5: the three side faces, 6 / 7: the ends.
+#define PTB_YARN_COVER 8
+PTB_HD void yarn_cover_triangle(V3 a, V3 b, float r, int idx, V3& v0, V3& v1, V3& v2) {
+    const V3 ab = b - a;
+    const float l = sqrtf(norm2(ab));
+    const V3 z = l > 0.f ? ab / l : v3(0, 0, 1);
+    const V3 h = fabsf(z.x) < 0.57f ? v3(1, 0, 0) : (fabsf(z.y) < 0.57f ? v3(0, 1, 0) : v3(0, 0, 1));
+    const V3 u = normalize(cross(z, h)), w = cross(z, u);
+    const float slack = 2e-6f * fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(b.x))), fmaxf(fabsf(b.y), fabsf(b.z))) + 1e-3f * r;
+    const float R = 2.2f * r + 2.f * slack, pad = 0.1f * r + slack;
+    const V3 a2 = a - pad * z, b2 = b + pad * z;
+    const V3 c0 = R * w, c1 = R * (-0.8660254f * u - 0.5f * w), c2 = R * (0.8660254f * u - 0.5f * w);
+    if (idx >= 6) {
+        const V3 e = idx == 6 ? a2 : b2;
+        v0 = e + c0; v1 = e + c1; v2 = e + c2;
+        return;
+    }
+    const int j = idx >> 1;
+    const V3 cj = j == 0 ? c0 : (j == 1 ? c1 : c2), ck = j == 0 ? c1 : (j == 1 ? c2 : c0);
+    if (idx & 1) { v0 = b2 + cj; v1 = a2 + ck; v2 = b2 + ck; }
+    else { v0 = a2 + cj; v1 = a2 + ck; v2 = b2 + cj; }
+}
+// The box all covering triangles of a yarn segment enter the BVH8 with: the tube's own (A +- r, B +- r like Yarns::build_bbox,
+// TriangleMesh.cpp:1519-1533), with a few ulps of the coordinates of slack.
+PTB_HD void yarn_box(V3 a, V3 b, float r, float lo[3], float hi[3]) {
+    const float s = r * (1.f + 1e-3f) + 2e-6f * fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(b.x))), fmaxf(fabsf(b.y), fabsf(b.z)));
+    lo[0] = fminf(a.x, b.x) - s; lo[1] = fminf(a.y, b.y) - s; lo[2] = fminf(a.z, b.z) - s;
+    hi[0] = fmaxf(a.x, b.x) + s; hi[1] = fmaxf(a.y, b.y) + s; hi[2] = fmaxf(a.z, b.z) + s;
+}
+#define PTB_GROUP_YARN (-3)   /* TriUV::group of a yarn segment's covering triangle (its TriShade holds the axis d and the end point A) */
 enum { SLOT_KD = 1, SLOT_KS = 2, SLOT_NE = 4, SLOT_TRANSP = 8, SLOT_REFR = 16, SLOT_NORMAL = 32, SLOT_ALPHA = 64, SLOT_KSUB = 128 };
 
 struct ObjectDev {          // Object / Sphere / Plane fields the path reads (Geometry.h:240-672, 849-1217)
@@ -122,6 +157,7 @@ PTB_HD V3 xf_rot(const float* m, V3 v) {     // apply_rotation (376-382), 3x3
 }
 
 PTB_HD bool tri_exact_available(const AlphaCtx* c) { return c != nullptr && c->tris_obj != nullptr; }
+PTB_HD bool cylinder_t(const float* A, const float* D, float R2, float len, V3 o, V3 d, float& t);
 
 // Scene::intersection's ray transform (Geometry.cpp:603-605, Geometry.h:383-397) + the Triangle constructor and
 // Triangle::intersection (TriangleMesh.h:70-104) + the `localt < t` of the traversal (TriangleMesh.cpp:1197), one rounding per operation.
@@ -129,12 +165,23 @@ PTB_EXACT_LINKAGE bool tri_exact(const AlphaCtx* c, int prim, V3 o, V3 d, float 
 #if defined(__CUDA_ARCH__)
     const float4 qa = __ldg(reinterpret_cast<const float4*>(c->tris_obj) + 3 * (size_t)prim), qb = __ldg(reinterpret_cast<const float4*>(c->tris_obj) + 3 * (size_t)prim + 1),
                  qc = __ldg(reinterpret_cast<const float4*>(c->tris_obj) + 3 * (size_t)prim + 2);
-    const int obj = __float_as_int(qa.w);
+    const int obj = __float_as_int(qa.w) & 0x0fffffff;     // (bits 28..30: which covering triangle of a yarn segment, see scene_host.cpp)
 #else
     const F4 qa = c->tris_obj[3 * (size_t)prim], qb = c->tris_obj[3 * (size_t)prim + 1], qc = c->tris_obj[3 * (size_t)prim + 2];
-    const int obj = (int)f2u(qa.w);
+    const int obj = (int)(f2u(qa.w) & 0x0fffffffu);
 #endif
     const float* m = c->objects[obj].inv_trans;
+    if (c->objects[obj].type == OBJ_YARNS) {
+        // cyls[i]->intersection (Geometry.h:740-766) on the object-space ray + the `localt < t` of Yarns::intersection (TriangleMesh.cpp:1711):
+        // A = end point, B.w = radius, C = unit axis d and length
+        const V3 dl = xf_dir(m, d), ol = xf_point(m, o);
+        const float A3[3] = {qa.x, qa.y, qa.z}, D3[3] = {qc.x, qc.y, qc.z};
+        float tt;
+        if (!cylinder_t(A3, D3, qb.w * qb.w, qc.w, ol, dl, tt)) return false;
+        if (!(tt < tbest)) return false;
+        t = tt; b1 = 0; b2 = 0;
+        return true;
+    }
     if (c->objects[obj].type == OBJ_POINTSET) {
         // Disk::intersection (Geometry.h:1110-1118) on the object-space ray (xf_dir / xf_point are the reference's own expressions;
         // this path is not compared bit for bit): A = centre, B.xyz = normal, B.w = radius
@@ -361,6 +408,17 @@ PTB_HD void surface_from_hit(const SceneDev& sc, V3 o, V3 d, const Hit& hit, int
         const TriShade ts = sc.tri_shade[id];
         s.object = tu.object_has_uv & 0x7fffffff;
         obp = &sc.objects[s.object];
+        if (EXOTIC && tu.group == PTB_GROUP_YARN) {
+            // ---- the tail of cyls[i]->intersection (Geometry.h:756-763) on the segment's OWN default material: n0 = axis d, n1 = A ----
+            const V3 dl = xf_dir(obp->inv_trans, d), ol = xf_point(obp->inv_trans, o);
+            const V3 Pl = ol + hit.t * dl;
+            const V3 a0 = v3(ts.n1[0], ts.n1[1], ts.n1[2]), ax = v3(ts.n0[0], ts.n0[1], ts.n0[2]);
+            const V3 proj = a0 + dot(Pl - a0, ax) * ax;
+            s.Kd = v3(1, 1, 1); s.Ks = v3(0, 0, 0); s.Ne = v3(1, 1, 1); s.transp = false; s.refr_index = 1.3f; s.Ke = v3(0, 0, 0); s.Ksub = v3(0, 0, 0);
+            s.P = xf_point(obp->trans, Pl);
+            s.N = fast_normalize(xf_rot(obp->rot, Pl - proj));      // never flipped: the segment's flip_normals, not the Yarns object's
+            return;
+        }
         if (EXOTIC && tu.group == PTB_GROUP_DISC) {
             // ---- PointSet::intersection's tail (PointSet.cpp:192-217): n0 = normal, t0 = colour, n1 = centre, n2[0] = radius ----
             const V3 dl = xf_dir(obp->inv_trans, d), ol = xf_point(obp->inv_trans, o);

@@ -78,6 +78,21 @@ int HostScene::add_pointset(const ptb_pointset* p, const ptb_xform* xf, int flag
     return (int)objects.size() - 1;
 }
 
+// `new Yarns(file)` after its constructor (TriangleMesh.h:268-290): cyls[i] = Cylinder(A, B, R); Object(): rotation_center = 0
+int HostScene::add_yarns(const ptb_yarns* y, const ptb_xform* xf, int flags, std::string& err) {
+    if (!y || !y->A || !y->B || !y->R || y->n <= 0) { err = "add_yarns: segment end points and radii are needed"; return PTB_ERR_INVALID; }
+    if ((int64_t)y->n * PTB_YARN_COVER >= (int64_t)1 << 28) { err = "add_yarns: too many segments"; return PTB_ERR_UNSUPPORTED; }
+    HostObject o;
+    o.type = OBJ_YARNS; o.flags = flags;
+    const size_t n = (size_t)y->n;
+    o.yarn_a.assign(y->A, y->A + 3 * n); o.yarn_b.assign(y->B, y->B + 3 * n); o.yarn_r.assign(y->R, y->R + n);
+    for (size_t i = 0; i < n; i++) if (!(o.yarn_r[i] >= 0.f)) { err = "add_yarns: negative or NaN radius"; return PTB_ERR_INVALID; }
+    const float zero[3] = {0, 0, 0};
+    take_xform(o, xf, zero);
+    objects.push_back(std::move(o));
+    return (int)objects.size() - 1;
+}
+
 static inline V3 V(const std::vector<float>& a, int i) { return v3(a[3 * (size_t)i], a[3 * (size_t)i + 1], a[3 * (size_t)i + 2]); }
 
 int HostScene::add_mesh(const ptb_mesh* m, const ptb_xform* xf, int flags, std::string& err) {
@@ -327,6 +342,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
         out.objects.push_back(d);
         if (o.type == OBJ_MESH) n_tri += (int64_t)o.tri.size() / 10;
         if (o.type == OBJ_POINTSET) n_tri += (int64_t)o.pt_rad.size();
+        if (o.type == OBJ_YARNS) n_tri += (int64_t)o.yarn_r.size() * PTB_YARN_COVER;
     }
     if (out.texels.size() >= (size_t)4294967295u) { err = "commit: texture pool exceeds 2^32 floats"; return PTB_ERR_UNSUPPORTED; }
     if (out.materials.empty()) out.materials.emplace_back();  // keep pointers valid
@@ -357,6 +373,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
     struct Src { int obj; int tri; uint8_t alpha; };
     std::vector<float> verts9(9 * (size_t)n_tri);
     std::vector<Src> src(n_tri);
+    std::vector<float> boxes6;      // only with yarns in the scene: the box a covering triangle enters the BVH with (NaN: its own)
     if (n_tri > 0) {
         static const bool classify = !(getenv("PTB_ALPHA_CLASSIFY") && atoi(getenv("PTB_ALPHA_CLASSIFY")) == 0);   // experiments: 0 = test every alpha-mapped triangle
         int64_t w = 0;
@@ -374,6 +391,25 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
                     v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p1.x; v[4] = p1.y; v[5] = p1.z; v[6] = p2.x; v[7] = p2.y; v[8] = p2.z;
                     src[w].obj = oi; src[w].tri = (int)i; src[w].alpha = ALPHA_OPAQUE;
                     w++;
+                }
+                continue;
+            }
+            if (o.type == OBJ_YARNS) {
+                // a yarn segment enters the BVH as the eight triangles of a prism around it (yarn_cover_triangle, ptb_scene.h)
+                const float sc_ = placement_at(o, current_frame).scale;
+                for (size_t i = 0; i < o.yarn_r.size(); i++) {
+                    const V3 aw = xf_point(o.trans, v3(o.yarn_a[3 * i], o.yarn_a[3 * i + 1], o.yarn_a[3 * i + 2]));
+                    const V3 bw = xf_point(o.trans, v3(o.yarn_b[3 * i], o.yarn_b[3 * i + 1], o.yarn_b[3 * i + 2]));
+                    if (boxes6.empty()) boxes6.assign(6 * (size_t)n_tri, NAN);
+                    for (int f = 0; f < PTB_YARN_COVER; f++) {
+                        yarn_box(aw, bw, o.yarn_r[i] * fabsf(sc_), &boxes6[6 * (size_t)w], &boxes6[6 * (size_t)w + 3]);
+                        V3 p0, p1, p2;
+                        yarn_cover_triangle(aw, bw, o.yarn_r[i] * fabsf(sc_), f, p0, p1, p2);
+                        float* v = &verts9[9 * (size_t)w];
+                        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p1.x; v[4] = p1.y; v[5] = p1.z; v[6] = p2.x; v[7] = p2.y; v[8] = p2.z;
+                        src[w].obj = oi; src[w].tri = (int)(i * PTB_YARN_COVER + f); src[w].alpha = ALPHA_OPAQUE;
+                        w++;
+                    }
                 }
                 continue;
             }
@@ -413,7 +449,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
     if (n_tri > 0) {
         auto t0 = std::chrono::steady_clock::now();
         std::vector<uint32_t> order;
-        build_bvh8(verts9.data(), n_tri, out.nodes, order, out.bvh);
+        build_bvh8(verts9.data(), n_tri, out.nodes, order, out.bvh, boxes6.empty() ? nullptr : boxes6.data());
         out.ms_bvh = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         out.tris.resize(3 * (size_t)n_tri); out.tris_obj.resize(3 * (size_t)n_tri); out.tri_uv.resize(n_tri); out.tri_shade.resize(n_tri);
 #pragma omp parallel for schedule(static)
@@ -427,7 +463,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
                 const float* v = &verts9[9 * (size_t)in];                                   // the covering triangle; e1.w = +inf: always left for k_exact
                 q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = u2f(fl); out.tris[3 * (size_t)k] = q;
                 q.x = v[3] - v[0]; q.y = v[4] - v[1]; q.z = v[5] - v[2]; q.w = INFINITY; out.tris[3 * (size_t)k + 1] = q;
-                q.x = v[6] - v[0]; q.y = v[7] - v[1]; q.z = v[8] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 2] = q;
+                q.x = v[6] - v[0]; q.y = v[7] - v[1]; q.z = v[8] - v[2]; q.w = PTB_TRI_T_CUT; out.tris[3 * (size_t)k + 2] = q;
                 q.x = o.pt_pos[3 * i]; q.y = o.pt_pos[3 * i + 1]; q.z = o.pt_pos[3 * i + 2]; q.w = u2f((uint32_t)src[in].obj); out.tris_obj[3 * (size_t)k] = q;
                 q.x = o.pt_nrm[3 * i]; q.y = o.pt_nrm[3 * i + 1]; q.z = o.pt_nrm[3 * i + 2]; q.w = o.pt_rad[i]; out.tris_obj[3 * (size_t)k + 1] = q;
                 q.x = q.y = q.z = q.w = 0; out.tris_obj[3 * (size_t)k + 2] = q;
@@ -440,6 +476,29 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
                     ts.t0[c] = o.pt_col.empty() ? 0.5f : o.pt_col[3 * i + c];
                 }
                 ts.n2[0] = o.pt_rad[i];
+                ts.orig = (int32_t)i;
+                out.tri_shade[k] = ts;
+                continue;
+            }
+            if (o.type == OBJ_YARNS) {
+                const size_t i = (size_t)src[in].tri / PTB_YARN_COVER, face = (size_t)src[in].tri % PTB_YARN_COVER;
+                const uint32_t fl = PTB_TRI_FLAG_DISC | ((o.flags & FLAG_GHOST) ? PTB_TRI_FLAG_GHOST : 0u);    // "decided by k_exact", like a disc
+                F4 q;
+                const float* v = &verts9[9 * (size_t)in];                                   // e1.w = +inf: always left for k_exact; e2.w = 0: no t cut
+                q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = u2f(fl); out.tris[3 * (size_t)k] = q;
+                q.x = v[3] - v[0]; q.y = v[4] - v[1]; q.z = v[5] - v[2]; q.w = INFINITY; out.tris[3 * (size_t)k + 1] = q;
+                q.x = v[6] - v[0]; q.y = v[7] - v[1]; q.z = v[8] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 2] = q;
+                // Cylinder(A, B, R) (Geometry.h:734-738): d = (B - A).getNormalized(), len = sqrt((B - A).getNorm2())
+                const V3 A = v3(o.yarn_a[3 * i], o.yarn_a[3 * i + 1], o.yarn_a[3 * i + 2]), B = v3(o.yarn_b[3 * i], o.yarn_b[3 * i + 1], o.yarn_b[3 * i + 2]);
+                const V3 d = normalize(B - A);
+                q.x = A.x; q.y = A.y; q.z = A.z; q.w = u2f((uint32_t)src[in].obj | ((uint32_t)face << 28)); out.tris_obj[3 * (size_t)k] = q;
+                q.x = B.x; q.y = B.y; q.z = B.z; q.w = o.yarn_r[i]; out.tris_obj[3 * (size_t)k + 1] = q;
+                q.x = d.x; q.y = d.y; q.z = d.z; q.w = sqrtf(norm2(B - A)); out.tris_obj[3 * (size_t)k + 2] = q;
+                TriUV tu; memset(&tu, 0, sizeof(tu));
+                tu.group = PTB_GROUP_YARN; tu.object_has_uv = src[in].obj;
+                out.tri_uv[k] = tu;
+                TriShade ts; memset(&ts, 0, sizeof(ts));
+                ts.n0[0] = d.x; ts.n0[1] = d.y; ts.n0[2] = d.z; ts.n1[0] = A.x; ts.n1[1] = A.y; ts.n1[2] = A.z;
                 ts.orig = (int32_t)i;
                 out.tri_shade[k] = ts;
                 continue;
@@ -458,7 +517,7 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
             q.x = v[3] - v[0]; q.y = v[4] - v[1]; q.z = v[5] - v[2];
             q.w = (flags & PTB_TRI_FLAG_ALPHA) ? INFINITY : PTB_EDGE_EPS;     // see tri_test_classify (ptb_bvh8.h)
             out.tris[3 * (size_t)k + 1] = q;
-            q.x = v[6] - v[0]; q.y = v[7] - v[1]; q.z = v[8] - v[2]; q.w = 0; out.tris[3 * (size_t)k + 2] = q;
+            q.x = v[6] - v[0]; q.y = v[7] - v[1]; q.z = v[8] - v[2]; q.w = PTB_TRI_T_CUT; out.tris[3 * (size_t)k + 2] = q;   // see tri_test_classify: the fast test's t cut
             for (int c = 0; c < 3; c++) {      // what Triangle(vertices[vtxi], vertices[vtxj], vertices[vtxk]) is built from (TriangleMesh.cpp:812-815)
                 const V3 pv = V(o.vertices, t[c]);
                 q.x = pv.x; q.y = pv.y; q.z = pv.z; q.w = c == 0 ? u2f((uint32_t)src[in].obj) : 0.f;

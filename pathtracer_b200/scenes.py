@@ -9,7 +9,7 @@ import math
 
 import numpy as np
 
-from .api import Cylinder, Plane, PointSet, Raytracer, Sphere, Texture, TriMesh
+from .api import Cylinder, Plane, PointSet, Raytracer, Sphere, Texture, TriMesh, Yarns
 
 
 def displaced_torus(nv):
@@ -199,6 +199,43 @@ def config_points(lib, W=128, H=128, spp=8, nv=40, device=0, display_edges=False
     small.max_translation = np.array([-22, -20, 10], np.float32)
     rt.s.addObject(small)
     rt.s.addObject(Sphere((17, -21.3, 14), 6).set_material(0, **phong((.3, .8, .3), 0.3, 50.0)))
+    return rt
+
+
+def weave_segments(n_warp=6, n_weft=6, seg=20, radius=0.028):
+    """A plain-weave patch in the unit square of the xz plane as yarn segments (what Yarns::cyls holds): `n_warp` curves along x and
+    `n_weft` along z, each passing over and under the ones it crosses; radii alternate per yarn."""
+    A, B, R = [], [], []
+    amp = 1.1 * radius
+    for fam, n_own, n_cross in ((0, n_warp, n_weft), (1, n_weft, n_warp)):
+        for k in range(n_own):
+            s = np.linspace(-0.5, 0.5, seg + 1)
+            off = (k + 0.5) / n_own - 0.5
+            phase = np.pi * (k + fam)
+            y = amp * np.cos(np.pi * n_cross * (s + 0.5) + phase)
+            pts = np.stack([s, y, np.full_like(s, off)], -1) if fam == 0 else np.stack([np.full_like(s, off), y, s], -1)
+            A.append(pts[:-1]); B.append(pts[1:])
+            R.append(np.full(seg, radius * (1.0 if k % 2 == 0 else 0.8)))
+    return np.concatenate(A).astype(np.float32), np.concatenate(B).astype(np.float32), np.concatenate(R).astype(np.float32)
+
+
+def config_yarns(lib, W=128, H=128, spp=8, seg=20, device=0):
+    """Yarns objects (TriangleMesh.h:265-312): a tilted, scaled weave of yarn segments over the ground, a second, mirror-flagged
+    coarse one, next to a sphere that casts and receives shadows with them."""
+    rt = base(lib, W, H, spp, device=device)
+    # (the sphere first: an object tested after the yarns would reset the picking query's triangle id whenever the ray meets it at
+    #  all, nearer or not: Sphere::intersection writes triangle_id = -1, Geometry.h:990)
+    rt.s.addObject(Sphere((-17, -21.3, 14), 6).set_material(0, **phong((.3, .8, .3), 0.3, 50.0)))
+    y = Yarns(*weave_segments(6, 6, seg))
+    y.scale = 34.0
+    y.mat_rotation = _rot(0.9, 0.5)
+    y.max_translation = np.array([-3, -12, 4], np.float32)
+    rt.s.addObject(y)
+    small = Yarns(*weave_segments(3, 2, max(4, seg // 3), radius=0.06), mirror=True)
+    small.scale = 14.0
+    small.mat_rotation = _rot(0.2, 1.1)
+    small.max_translation = np.array([20, -19, 12], np.float32)
+    rt.s.addObject(small)
     return rt
 
 

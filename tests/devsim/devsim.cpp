@@ -43,6 +43,7 @@ int ptb_add_sphere(ptb_ctx* c, const float O[3], float R, const ptb_xform* xf, i
 int ptb_add_plane(ptb_ctx* c, const float A[3], const float N[3], const ptb_xform* xf, int flags, int* id) { int i = c->host.add_plane(A, N, xf, flags); if (id) *id = i; return PTB_OK; }
 int ptb_add_cylinder(ptb_ctx* c, const float A[3], const float B[3], float R, const ptb_xform* xf, int flags, int* id) { int i = c->host.add_cylinder(A, B, R, xf, flags); if (id) *id = i; return PTB_OK; }
 int ptb_add_pointset(ptb_ctx* c, const ptb_pointset* p, const ptb_xform* xf, int flags, int* id) { int i = c->host.add_pointset(p, xf, flags, c->err); if (i < 0) return i; if (id) *id = i; return PTB_OK; }
+int ptb_add_yarns(ptb_ctx* c, const ptb_yarns* y, const ptb_xform* xf, int flags, int* id) { int i = c->host.add_yarns(y, xf, flags, c->err); if (i < 0) return i; if (id) *id = i; return PTB_OK; }
 int ptb_add_mesh(ptb_ctx* c, const ptb_mesh* m, const ptb_xform* xf, int flags, int* id) { int i = c->host.add_mesh(m, xf, flags, c->err); if (i < 0) return i; if (id) *id = i; return PTB_OK; }
 int ptb_set_group_material(ptb_ctx* c, int obj, int group, const ptb_material* m) { return c->host.set_group_material(obj, group, m, c->err); }
 int ptb_set_brdf(ptb_ctx* c, int obj, int kind, int merl) { c->host.objects[obj].brdf = kind; c->host.objects[obj].merl = merl; return PTB_OK; }

@@ -12,7 +12,8 @@ SCENES = {
     "NGAN": lambda L, **kw: scenes.config_ngan(L, 48, 48, 2, **kw),
     "CYL": lambda L, **kw: scenes.config_cyl(L, 48, 48, 2, **kw),
     "PTS": lambda L, **kw: scenes.config_points(L, 48, 48, 2, nv=24, **kw),                        # PointSet discs (PointSet.cpp)
-    "PTS_EDGES": lambda L, **kw: scenes.config_points(L, 48, 48, 2, nv=16, display_edges=True, **kw),       # Cylinder objects (Geometry.h:731-846)     # Phong / Ngan material presets (mainApp.cpp:1499-1597)
+    "PTS_EDGES": lambda L, **kw: scenes.config_points(L, 48, 48, 2, nv=16, display_edges=True, **kw),
+    "YARN": lambda L, **kw: scenes.config_yarns(L, 48, 48, 2, seg=12, **kw),                       # Yarns (TriangleMesh.h:265-312, TriangleMesh.cpp:1519-1737)
 }
 
 # getColor's branching modes: background photograph, ghost objects, participating medium

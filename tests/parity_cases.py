@@ -12,7 +12,7 @@ Tolerances (float32 paths; the oracle and the CUDA path draw the same pcg32 numb
 import numpy as np
 
 from pathtracer_b200 import _abi, scenes
-from pathtracer_b200.api import Plane, Sphere, Texture, TriMesh
+from pathtracer_b200.api import Plane, Sphere, Texture, TriMesh, Yarns
 
 ID_AGREE = 0.9999
 FRAC_1SPP = 0.005
@@ -61,6 +61,29 @@ def case_scene(test_lib, oracle_lib, mk, nrays=None, frac=FRAC_1SPP, agree=ID_AG
     assert b.stats["samples"] == a.stats["samples"]
     d = np.abs(a.image.astype(int) - b.image.astype(int))
     assert np.mean(d > 1) <= 2 * frac
+    a.close(); b.close()
+
+
+def yarn_inside_scene(lib, W=64, H=64, spp=2):
+    """A fat yarn segment seen by a camera that sits between the tube and the prism that covers it in the BVH8, inside a small sphere:
+    every primary ray meets the tube (t = 0.1 .. 0.5) before the sphere's inner side (t = 1) and leaves the covering prism only
+    beyond it (t > 4).  The covering faces must therefore not be cut at the nearest hit so far (their e2.w = 0, ptb_scene.h)."""
+    rt = scenes.base(lib, W, H, spp)
+    rt.s.addObject(Sphere((0, 0, 2.1), 1.0).set_material(0, **scenes.phong((.3, .8, .3), 0.3, 50.0)))
+    rt.s.addObject(Yarns([[-10, 0, 0], [-4, 0.5, -6]], [[10, 0, 0], [-3, 2, -9]], [2.0, 0.7]))
+    rt.cam.position = np.array([0, 0, 2.1], np.float32)
+    rt.cam.direction = np.array([0, 0, -1], np.float32)
+    rt.cam.up = np.array([0, 1, 0], np.float32)
+    rt.cam.aperture = np.float32(0.0)
+    return rt
+
+
+def case_yarn_from_inside(test_lib, oracle_lib):
+    a, b = yarn_inside_scene(oracle_lib).commit(), yarn_inside_scene(test_lib).commit()
+    oa, ta, da = a.primary_ids()
+    assert (oa == 4).mean() > 0.9 and (ta[oa == 4] == 0).all() and da[oa == 4].max() < 0.9, "the scene must show the tube in front of the sphere"
+    check_ids(b, a, need_mesh=False)
+    check_images(b.render_image_nopreviz().copy(), a.render_image_nopreviz().copy())
     a.close(); b.close()
 
 
