@@ -73,6 +73,14 @@ int  ptb_meshfile_get(const ptb_meshfile*, ptb_meshfile_info* out);
 int  ptb_meshfile_group_name(const ptb_meshfile*, int group, char name[PTB_PATH_MAX]);
 int  ptb_meshfile_group_slot(const ptb_meshfile*, int group, int kind, ptb_slot* out);
 
+/* ---- .yarn files ---------------------------------------------------------------------------------------- */
+/* replaces: the reader inside `Yarns::Yarns(const char* filename)` (TriangleMesh.h:268-288): `nbyarns`, then per yarn `nbsegments`
+ * followed by that many points "x y z"; consecutive points of a yarn, times 50, become the end points of one segment of radius 0.1.
+ * Returns malloc'ed n x 3 / n x 3 / n arrays ready for ptb_add_yarns (free with ptb_yarnfile_free), in file order.  A count that
+ * the file does not honour is an error here (the reference's fscanf loop would push whatever the last conversion left). */
+int  ptb_yarnfile_read(const char* path, float** A, float** B, float** R, int32_t* n_segments);
+void ptb_yarnfile_free(void* p);
+
 /* ---- .scn files ----------------------------------------------------------------------------------------- */
 #define PTB_SCN_MESH      0
 #define PTB_SCN_SPHERE    1

@@ -622,6 +622,24 @@ int ref_texture_load(const char* path, int kind, float** values, int32_t* W, int
     return PTB_OK;
 }
 
+// `new Yarns(file)`: its constructor reads the file and builds its BVH, which reorders `cyls`; the segments come back in THAT order
+// (tests compare them as a set).  The constructor opens with "r+" and does not check the result: probe first.
+int ref_yarnfile_read(const char* path, float** A, float** B, float** R, int32_t* n_segments) {
+    FILE* probe = fopen(path, "r+");
+    if (!probe) return PTB_ERR_INVALID;
+    fclose(probe);
+    Yarns* y = new Yarns(path);
+    const size_t n = y->cyls.size();
+    *A = (float*)malloc(3 * n * sizeof(float)); *B = (float*)malloc(3 * n * sizeof(float)); *R = (float*)malloc(n * sizeof(float));
+    for (size_t i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) { (*A)[3 * i + k] = y->cyls[i]->A[k]; (*B)[3 * i + k] = y->cyls[i]->B[k]; }
+        (*R)[i] = y->cyls[i]->R;
+    }
+    *n_segments = (int32_t)n;
+    return PTB_OK;
+}
+void ref_yarnfile_free(void* p) { free(p); }
+
 int ref_meshfile_read(const char* path, int load_textures, void** out) {
     ref_meshfile_t* m = new ref_meshfile_t();
     m->g = new TriMesh();

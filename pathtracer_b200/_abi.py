@@ -146,7 +146,7 @@ class ScnObject(C.Structure):
 
 # every symbol include/ptb_sceneio.h declares
 SCENEIO_SYMBOLS = ["sceneio_last_error", "image_load", "image_free", "texture_load", "meshfile_read", "meshfile_free", "meshfile_get",
-                   "meshfile_group_name", "meshfile_group_slot", "scn_load", "scn_free", "scn_get_header", "scn_get_object", "scn_get_slot", "scn_get_keyframes",
+                   "meshfile_group_name", "meshfile_group_slot", "yarnfile_read", "yarnfile_free", "scn_load", "scn_free", "scn_get_header", "scn_get_object", "scn_get_slot", "scn_get_keyframes",
                    "scn_save", "load_scene"]
 
 
@@ -169,6 +169,8 @@ class SceneIO:
             "meshfile_get": (C.c_int, [vp, C.POINTER(MeshfileInfo)]),
             "meshfile_group_name": (C.c_int, [vp, C.c_int, C.c_char_p]),
             "meshfile_group_slot": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(Slot)]),
+            "yarnfile_read": (C.c_int, [C.c_char_p, C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_fp), ip32]),
+            "yarnfile_free": (None, [vp]),
             "scn_load": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(vp)]),
             "scn_free": (None, [vp]),
             "scn_get_header": (C.c_int, [vp, C.POINTER(ScnHeader)]),

@@ -248,15 +248,15 @@ class Yarns(Object):
     def from_file(cls, path):
         """`new Yarns(file)` (TriangleMesh.h:268-290): `nbyarns`, then per yarn `nbsegments` and that many points; consecutive points
         times 50 are joined by cylinders of radius 0.1."""
-        tok = open(path).read().split()
-        pos, A, B = 1, [], []
-        for _ in range(int(tok[0])):
-            n = int(tok[pos]); pos += 1
-            pts = np.array(tok[pos:pos + 3 * n], np.float32).reshape(n, 3) * np.float32(50.0)
-            pos += 3 * n
-            A.append(pts[:-1]); B.append(pts[1:])
-        A, B = np.concatenate(A), np.concatenate(B)
-        return cls(A, B, np.full(len(A), 0.1, np.float32))
+        io = _io()
+        fp = C.POINTER(C.c_float)
+        a, b, r, n = fp(), fp(), fp(), C.c_int32()
+        io.check(io.yarnfile_read(str(path).encode(), C.byref(a), C.byref(b), C.byref(r), C.byref(n)))
+        A, B = np.ctypeslib.as_array(a, shape=(n.value, 3)).copy(), np.ctypeslib.as_array(b, shape=(n.value, 3)).copy()
+        R = np.ctypeslib.as_array(r, shape=(n.value,)).copy()
+        for p in (a, b, r):
+            io.yarnfile_free(p)
+        return cls(A, B, R)
 
 
 class TriMesh(Object):

@@ -826,6 +826,44 @@ int ptb_texture_load(const char* path, int kind, float** values, int32_t* W, int
     } PTB_IO_CATCH
 }
 
+// Yarns::Yarns(filename) (TriangleMesh.h:268-288): "%u\n" counts and "%f %f %f\n" points are whitespace-separated tokens to fscanf
+int ptb_yarnfile_read(const char* path, float** A, float** B, float** R, int32_t* n_segments) {
+    try {
+    if (!path || !A || !B || !R || !n_segments) return fail(PTB_ERR_INVALID, "yarnfile_read: null argument");
+    std::vector<uint8_t> buf;
+    if (!read_file(path, buf)) return fail(PTB_ERR_INVALID, std::string("yarnfile_read: cannot read ") + path);
+    buf.push_back(0);
+    const char* p = reinterpret_cast<const char*>(buf.data());
+    auto next_uint = [&](long& v) { char* e; v = strtol(p, &e, 10); if (e == p || v < 0) return false; p = e; return true; };
+    auto next_float = [&](float& v) { char* e; v = strtof(p, &e); if (e == p) return false; p = e; return true; };
+    long nbyarns;
+    if (!next_uint(nbyarns)) return fail(PTB_ERR_INVALID, "yarnfile_read: no yarn count");
+    std::vector<float> a, b;
+    for (long y = 0; y < nbyarns; y++) {
+        long nbpoints;
+        if (!next_uint(nbpoints)) return fail(PTB_ERR_INVALID, "yarnfile_read: a yarn without its point count");
+        float prev[3] = {0, 0, 0};
+        for (long j = 0; j < nbpoints; j++) {
+            float q[3];
+            if (!next_float(q[0]) || !next_float(q[1]) || !next_float(q[2])) return fail(PTB_ERR_INVALID, "yarnfile_read: fewer points than announced");
+            for (int k = 0; k < 3; k++) q[k] *= 50.f;                                   // Vector(x, y, z) * 50.f
+            if (j > 0) { a.insert(a.end(), prev, prev + 3); b.insert(b.end(), q, q + 3); }
+            memcpy(prev, q, sizeof q);
+        }
+        if (a.size() / 3 > (size_t)(1 << 25)) return fail(PTB_ERR_UNSUPPORTED, "yarnfile_read: more than 2^25 segments");
+    }
+    const size_t n = a.size() / 3;
+    if (n == 0) return fail(PTB_ERR_INVALID, "yarnfile_read: no segment in the file");
+    *A = (float*)malloc(3 * n * sizeof(float)); *B = (float*)malloc(3 * n * sizeof(float)); *R = (float*)malloc(n * sizeof(float));
+    if (!*A || !*B || !*R) { free(*A); free(*B); free(*R); return fail(PTB_ERR_NOMEM, "yarnfile_read: out of memory"); }
+    memcpy(*A, a.data(), 3 * n * sizeof(float)); memcpy(*B, b.data(), 3 * n * sizeof(float));
+    for (size_t i = 0; i < n; i++) (*R)[i] = 0.1f;
+    *n_segments = (int32_t)n;
+    return PTB_OK;
+    } PTB_IO_CATCH
+}
+void ptb_yarnfile_free(void* p) { free(p); }
+
 int ptb_meshfile_read(const char* path, int load_textures, ptb_meshfile** out) {
     try {
     if (!path || !out) return fail(PTB_ERR_INVALID, "meshfile_read: null argument");

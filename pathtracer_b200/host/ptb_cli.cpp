@@ -43,7 +43,7 @@ int main(int argc, char** argv) {
         argv += 2; argc -= 2;
     }
     if (n_gpus < 1 || n_gpus > 64) { std::fprintf(stderr, "ptb_cli: --gpus must be 1..64\n"); return 2; }
-    if (argc < 3) { std::fprintf(stderr, "usage: %s <scene.scn|C1|torus> <out.ppm> [W H spp nv]   (PTB_FRAME=<n> renders frame n of a key-framed .scn)\n", argv[0]); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: %s <scene.scn|curves.yarn|C1|torus> <out.ppm> [W H spp nv]   (PTB_FRAME=<n> renders frame n of a key-framed .scn)\n", argv[0]); return 2; }
     try {
         std::vector<int> devices;
         for (int i = 0; i < n_gpus; i++) devices.push_back(i);
@@ -65,7 +65,9 @@ int main(int argc, char** argv) {
             m.set(PTB_SLOT_KD, Texture(kd)).set(PTB_SLOT_KS, Texture(ks)).set(PTB_SLOT_NE, Texture(ne)).set(PTB_SLOT_TRANSP, Texture(1.f)).set(PTB_SLOT_REFR, Texture(1.3f));
             return m;
         };
-        if (!std::strcmp(argv[1], "C1")) {
+        if (len > 5 && !std::strcmp(argv[1] + len - 5, ".yarn")) {
+            rt.s.addObject(std::make_shared<Yarns>(argv[1]));       // a dropped .yarn file: added as it is (mainApp.cpp:2413-2416)
+        } else if (!std::strcmp(argv[1], "C1")) {
             auto s1 = std::make_shared<Sphere>(Vector(0, -17.3f, 0), 10.f); s1->materials.push_back(phong(Vector(.8f, .3f, .3f), 0.f, 1.f));
             auto s2 = std::make_shared<Sphere>(Vector(-15, -20.3f, 5), 7.f); s2->materials.push_back(phong(Vector(.3f, .8f, .3f), .3f, 50.f));
             rt.s.addObject(s1); rt.s.addObject(s2);

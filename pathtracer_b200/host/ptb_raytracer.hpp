@@ -69,7 +69,7 @@ struct Material {                // one slot index of Object::textures / specula
     }
 };
 
-enum ObjectType { OT_TRIMESH, OT_SPHERE, OT_PLANE, OT_POINTSET, OT_CYLINDER };   // Geometry.h:29
+enum ObjectType { OT_TRIMESH, OT_SPHERE, OT_PLANE, OT_POINTSET, OT_CYLINDER, OT_YARNS };   // Geometry.h:29
 
 struct Object {                  // Geometry.h:240-672
     ObjectType type;
@@ -123,6 +123,17 @@ struct PointSet : Object {       // PointSet.h as it stands after init: one disc
 struct Cylinder : Object {       // Geometry.h:731-846
     Vector A, B; float R;
     Cylinder(const Vector& a, const Vector& b, float r) : Object(OT_CYLINDER), A(a), B(b), R(r) {}
+};
+struct Yarns : Object {          // TriangleMesh.h:265-312: `cyls` as three flat arrays (segment i = Cylinder(A[i], B[i], R[i]))
+    std::vector<float> A, B, R;  // x3, x3, x1
+    Yarns() : Object(OT_YARNS) { rotation_center = Vector(0, 0, 0); }
+    explicit Yarns(const char* filename) : Object(OT_YARNS) {      // Yarns::Yarns(filename): points times 50, radius 0.1
+        rotation_center = Vector(0, 0, 0);
+        float *a = nullptr, *b = nullptr, *r = nullptr; int32_t n = 0;
+        if (ptb_yarnfile_read(filename, &a, &b, &r, &n) != PTB_OK) throw Error(std::string("Yarns: ") + ptb_sceneio_last_error());
+        A.assign(a, a + 3 * (size_t)n); B.assign(b, b + 3 * (size_t)n); R.assign(r, r + n);
+        ptb_yarnfile_free(a); ptb_yarnfile_free(b); ptb_yarnfile_free(r);
+    }
 };
 struct TriMesh : Object {        // arrays as a reader fills them (TriangleMesh.cpp:240-569), before init's processing
     std::vector<float> vertices, normals, uvs;   // x3, x3, x2
@@ -217,6 +228,12 @@ public:
                 ck(ptb_add_pointset(ctx_, &d, &xf, flags | (ps.display_edges ? PTB_OBJ_DISPLAY_EDGES : 0), &id));
             }
             else if (o.type == OT_CYLINDER) { auto& cy = static_cast<Cylinder&>(o); ck(ptb_add_cylinder(ctx_, cy.A.v, cy.B.v, cy.R, &xf, flags, &id)); }
+            else if (o.type == OT_YARNS) {
+                auto& ys = static_cast<Yarns&>(o);
+                ptb_yarns d;
+                d.A = ys.A.data(); d.B = ys.B.data(); d.R = ys.R.data(); d.n = (int32_t)ys.R.size();
+                ck(ptb_add_yarns(ctx_, &d, &xf, flags, &id));
+            }
             else {
                 auto& g = static_cast<TriMesh&>(o);
                 ptb_mesh m;

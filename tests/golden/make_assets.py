@@ -225,9 +225,26 @@ def old_scene():
     open(os.path.join(OUT, "old.scn"), "w").write(head + "".join(objs) + "fog_density: 0.000000\nfog_type: 0\n")
 
 
+def yarns():
+    """A .yarn file as Yarns::Yarns(filename) reads it (TriangleMesh.h:268-288): yarn count, then per yarn a point count and the
+    points (times 50 in the reader).  Three yarns: a helix, a straight two-point one and a zig-zag; mixed separators and exponents."""
+    lines = ["3"]
+    t = np.linspace(0, 4 * math.pi, 17)
+    lines.append(str(len(t)))
+    lines += [f"{0.1 * math.cos(a):.6f} {0.02 * a - 0.5:.6f} {0.1 * math.sin(a):.6f}" for a in t]      # (y = -0.5 .. -0.25: in the default view)
+    lines += ["2", "-2.5e-1 -0.4 1E-1", "0.25\t-0.35   -0.1"]
+    lines.append("5")
+    lines += [f"{-0.2 + 0.1 * k} {-0.3 + 0.05 * (k % 2)} {0.02 * k}" for k in range(5)]
+    open(os.path.join(OUT, "weave.yarn"), "w").write("\n".join(lines) + "\n")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--yarns-only" in __import__("sys").argv:
+        yarns()
+        raise SystemExit(0)
     images()
     meshes()
     scenes()
+    yarns()
     print(sorted(os.listdir(OUT)))

@@ -64,6 +64,8 @@ def sceneio_golden(R):
             for key in ("vertices", "normals", "uvs", "vertex_colors", "tri"):
                 out[f"mesh/{n}/{lt}/{key}"] = d[key]
             meta[f"mesh/{n}/{lt}"] = {"n_groups": d["n_groups"], "groups": d["groups"], "slots": {str(g): {str(k): v for k, v in per.items()} for g, per in d["slots"].items()}}
+        for n in sio.YARNS:
+            out[f"yarn/{n}"] = sio.dump_yarn(RIO, n)
         for n in sio.SCENES:
             meta[f"scn/{n}"] = sio.dump_scn(RIO, n)
         for n in sio.RENDER_SCENES:
@@ -100,6 +102,9 @@ def main():
     R = ref_lib()
     assert R is not None, "oracle/_ref is not built (needs /root/reference)"
     only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]      # --only=NGAN,C1: just these scene fixtures
+    if "--sceneio-only" in sys.argv:
+        sceneio_golden(R)
+        return
     if not only:
         sceneio_golden(R)
         modes_golden(R)

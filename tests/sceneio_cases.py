@@ -13,6 +13,7 @@ ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ass
 IMAGES = ["checker.png", "grey.png", "pal.png", "rgba.png", "grey16.png", "bumps.bmp", "bumps8.bmp", "alpha.pgm", "tint.ppm", "sky.tga", "sky_rle.tga", "grey.tga"]
 TEXTURES = [("checker.png", 0), ("bumps.bmp", 1), ("alpha.pgm", 0), ("grey16.png", 1)]
 MESHES = [("relief.obj", 0), ("relief.obj", 1), ("sheet.obj", 1), ("tetra.obj", 1), ("octa.off", 0)]
+YARNS = ["weave.yarn"]
 SCENES = ["full.scn", "forms.scn", "old.scn"]
 RENDER_SCENES = ["full.scn", "old.scn"]
 
@@ -46,6 +47,18 @@ def dump_texture(io, name, kind):
     a = np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
     io.image_free(p)
     return a
+
+
+def dump_yarn(io, name):
+    """-> (n, 7) rows A, B, R sorted lexicographically (the reference hands its segments back in the order its BVH build left)"""
+    fp = C.POINTER(C.c_float)
+    a, b, r, n = fp(), fp(), fp(), C.c_int32()
+    io.check(io.yarnfile_read(name.encode(), C.byref(a), C.byref(b), C.byref(r), C.byref(n)))
+    rows = np.concatenate([np.ctypeslib.as_array(a, shape=(n.value, 3)), np.ctypeslib.as_array(b, shape=(n.value, 3)),
+                           np.ctypeslib.as_array(r, shape=(n.value, 1))], 1).astype(np.float32, copy=True)
+    for p in (a, b, r):
+        io.yarnfile_free(p)
+    return rows[np.lexsort(rows.T[::-1])]
 
 
 def _slot(sl):

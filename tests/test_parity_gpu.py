@@ -115,7 +115,7 @@ def test_animation_refit_gpu(gpu, port):
 
 
 def test_refit_moves_point_sets_and_cylinders_too(gpu, port):
-    """Discs and analytic cylinders follow their key-framed object matrices through the re-pose like triangles do."""
+    """Discs, analytic cylinders and yarn segments follow their key-framed object matrices through the re-pose like triangles do."""
     def mk(L, frame):
         rt = scenes.config_points(L, 64, 64, 2, nv=20)
         ps = rt.s.objects[3]
@@ -129,6 +129,13 @@ def test_refit_moves_point_sets_and_cylinders_too(gpu, port):
         cy.mat_rotation = scenes._rot(0.5, 0.0)
         cy.add_keyframe(6)
         rt.s.addObject(cy)
+        ya = scenes.Yarns(*scenes.weave_segments(3, 3, 8, radius=0.05))
+        ya.scale, ya.max_translation = 16.0, np.array([14, -18, 18], np.float32)
+        ya.add_keyframe(0)
+        ya.scale, ya.mat_rotation = 20.0, scenes._rot(0.7, 0.4)
+        ya.max_translation = np.array([10, -14, 14], np.float32)
+        ya.add_keyframe(6)
+        rt.s.addObject(ya)
         rt.s.current_frame = frame
         return rt
     rt = mk(gpu, 0).commit()
@@ -570,6 +577,16 @@ def test_cpp_cli_renders_like_the_python_mirror(gpu, port, tmp_path):
         ref = py_torus(preset)
         assert (np.abs(_read_ppm(out).astype(int) - ref.astype(int)) > 1).mean() < 2e-3, preset
     plain = _read_ppm(out)
+    # a .yarn file, added to the default scene as the GUI adds a dropped one (mainApp.cpp:2413-2416)
+    yarn = os.path.join(sio.ASSETS, "weave.yarn")
+    out = str(tmp_path / "y.ppm")
+    r = subprocess.run([cli, yarn, out, "96", "64", "4"], capture_output=True, text=True)      # (sub-pixel tubes: every hit is an edge case)
+    assert r.returncode == 0, r.stderr
+    q = mk(gpu)
+    q.s.addObject(api.Yarns.from_file(yarn))
+    q.commit().render_image_nopreviz()
+    assert (q.primary_ids()[0] == 3).mean() > 0.01, "the yarns must be in view"
+    assert (np.abs(_read_ppm(out).astype(int) - q.image.astype(int)) > 1).mean() < 2e-3
     n = torch.cuda.device_count()
     if n >= 2:
         out2 = str(tmp_path / "t2.ppm")

@@ -69,6 +69,16 @@ def test_mesh_readers_match_reference(io, gold, name, lt):
     assert _norm({str(g): {str(k): v for k, v in per.items()} for g, per in d["slots"].items()}) == meta["slots"]
 
 
+@pytest.mark.parametrize("name", sio.YARNS)
+def test_yarn_reader_matches_reference(io, gold, name):
+    """Yarns::Yarns(filename) (TriangleMesh.h:268-288): the same segments, bit for bit (as a set: the reference's constructor reorders them)."""
+    with sio.in_assets():
+        got = sio.dump_yarn(io, name)
+    want = gold[0][f"yarn/{name}"]
+    assert got.shape == want.shape == (16 + 1 + 4, 7) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (got[:, 6] == np.float32(0.1)).all()
+
+
 def test_obj_reader_details(io):
     """What the fixture is built to exercise, stated explicitly (independent of the golden file)."""
     with sio.in_assets():
@@ -165,6 +175,16 @@ def test_malformed_files_are_errors_not_crashes(io, tmp_path):
     f.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvn 0 0 1\nf -3/-2/-1 -2/-1/-1 -1/-2/-1\n")      # in range: fine
     assert io.meshfile_read(str(f).encode(), 0, C.byref(h)) == 0
     io.meshfile_free(h)
+    # .yarn files whose counts the points do not honour, and one without a segment
+    fp = C.POINTER(C.c_float)
+    a, b, r, n = fp(), fp(), fp(), C.c_int32()
+    f = tmp_path / "short.yarn"; f.write_text("2\n3\n0 0 0\n1 0 0\n1 1 0\n4\n0 0 1\n")
+    assert io.yarnfile_read(str(f).encode(), C.byref(a), C.byref(b), C.byref(r), C.byref(n)) == -1 and b"fewer points" in io.sceneio_last_error()
+    f.write_text("1\n1\n0 0 0\n")
+    assert io.yarnfile_read(str(f).encode(), C.byref(a), C.byref(b), C.byref(r), C.byref(n)) == -1 and b"no segment" in io.sceneio_last_error()
+    f.write_text("two yarns\n")
+    assert io.yarnfile_read(str(f).encode(), C.byref(a), C.byref(b), C.byref(r), C.byref(n)) == -1
+    assert io.yarnfile_read(str(tmp_path / "absent.yarn").encode(), C.byref(a), C.byref(b), C.byref(r), C.byref(n)) == -1
 
 
 def _scn_with_modes(tmp_path):
@@ -287,6 +307,8 @@ def test_live_reference_readers_agree(io, ref):
             assert all(np.array_equal(a[k], b[k]) if isinstance(a[k], np.ndarray) else a[k] == b[k] for k in a), n
         for n in sio.SCENES:
             assert sio.dump_scn(io, n) == sio.dump_scn(rio, n), n
+        for n in sio.YARNS:
+            assert np.array_equal(sio.dump_yarn(io, n), sio.dump_yarn(rio, n)), n
 
 
 # ---- GPU: the product end to end from a file ------------------------------------------------------------------------------------
