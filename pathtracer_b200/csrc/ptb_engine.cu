@@ -481,11 +481,6 @@ __global__ void __launch_bounds__(128) k_splat(FrameDev f, PoolDev p, F4* accum)
 // the roundings of the host's xf_point, and the node boxes are recomputed bottom-up, one launch per level (nodes are stored breadth
 // first), with the builder's conservative quantisation (bvh8_build.cpp).  The reference re-poses by changing the matrices only (its BVH
 // is in object space); here the re-pose costs one pass over the triangles and the nodes: well under a millisecond per million triangles.
-__device__ __forceinline__ V3 xf_point_rn(const float* m, V3 v) {
-    return v3(add_rn(add_rn(add_rn(mul_rn(m[0], v.x), mul_rn(m[1], v.y)), mul_rn(m[2], v.z)), m[3]),
-              add_rn(add_rn(add_rn(mul_rn(m[4], v.x), mul_rn(m[5], v.y)), mul_rn(m[6], v.z)), m[7]),
-              add_rn(add_rn(add_rn(mul_rn(m[8], v.x), mul_rn(m[9], v.y)), mul_rn(m[10], v.z)), m[11]));
-}
 // world-space corners of stored triangle `t` at the objects' current matrices: a mesh triangle's own corners, the covering triangle of a
 // point-set disc (centre A, normal B.xyz, radius B.w) or one of the covering triangles of a yarn segment (A, B, radius B.w; which one in
 // bits 28..30 of A.w)

@@ -157,7 +157,38 @@ PTB_HD V3 xf_rot(const float* m, V3 v) {     // apply_rotation (376-382), 3x3
 }
 
 PTB_HD bool tri_exact_available(const AlphaCtx* c) { return c != nullptr && c->tris_obj != nullptr; }
-PTB_HD bool cylinder_t(const float* A, const float* D, float R2, float len, V3 o, V3 d, float& t);
+// apply_inverse_rotation_scaling / apply_(inverse_)transformation (Geometry.h:362-397) with one rounding per operation, in the reference's order
+PTB_HD V3 xf_dir_rn(const float* m, V3 d) {
+    return v3(add_rn(add_rn(mul_rn(m[0], d.x), mul_rn(m[1], d.y)), mul_rn(m[2], d.z)), add_rn(add_rn(mul_rn(m[4], d.x), mul_rn(m[5], d.y)), mul_rn(m[6], d.z)),
+              add_rn(add_rn(mul_rn(m[8], d.x), mul_rn(m[9], d.y)), mul_rn(m[10], d.z)));
+}
+PTB_HD V3 xf_point_rn(const float* m, V3 v) {
+    return v3(add_rn(add_rn(add_rn(mul_rn(m[0], v.x), mul_rn(m[1], v.y)), mul_rn(m[2], v.z)), m[3]),
+              add_rn(add_rn(add_rn(mul_rn(m[4], v.x), mul_rn(m[5], v.y)), mul_rn(m[6], v.z)), m[7]),
+              add_rn(add_rn(add_rn(mul_rn(m[8], v.x), mul_rn(m[9], v.y)), mul_rn(m[10], v.z)), m[11]));
+}
+// Cylinder::intersection (Geometry.h:740-754) in the reference's own arithmetic, one rounding per operation.  For a thin yarn far from the
+// ray origin `delta = b*b - 4*a*c` cancels five digits: an FMA anywhere in it moves t by 1e-6 relative, which is 1e-4 of the tube's
+// radius and hence of the radial shading normal.  (The analytic Cylinder objects, radius of the order of their distance, keep cylinder_t.)
+PTB_HD bool cylinder_t_rn(V3 a0, V3 ax, float R, float len, V3 o, V3 d, float& t) {
+    const V3 X = sub3_rn(d, scale_rn(dot_rn(d, ax), ax));
+    const V3 oa = sub3_rn(o, a0);
+    const V3 Y = sub3_rn(oa, scale_rn(dot_rn(oa, ax), ax));
+    const float a = dot_rn(X, X);
+    const float b = mul_rn(2.f, dot_rn(X, Y));
+    const float c = sub_rn(dot_rn(Y, Y), mul_rn(R, R));
+    const float delta = sub_rn(mul_rn(b, b), mul_rn(mul_rn(4.f, a), c));
+    if (delta < 0) return false;
+    const float sdelta = sqrt_rn(delta);
+    const float t2 = div_rn(add_rn(-b, sdelta), mul_rn(2.f, a));
+    if (t2 < 0) return false;
+    const float t1 = div_rn(sub_rn(-b, sdelta), mul_rn(2.f, a));
+    t = (t1 > 0) ? t1 : t2;
+    const V3 P = add3_rn(o, scale_rn(t, d));
+    const float dP = dot_rn(sub3_rn(P, a0), ax);
+    if (dP < 0 || dP > len) return false;
+    return true;
+}
 
 // Scene::intersection's ray transform (Geometry.cpp:603-605, Geometry.h:383-397) + the Triangle constructor and
 // Triangle::intersection (TriangleMesh.h:70-104) + the `localt < t` of the traversal (TriangleMesh.cpp:1197), one rounding per operation.
@@ -174,10 +205,8 @@ PTB_EXACT_LINKAGE bool tri_exact(const AlphaCtx* c, int prim, V3 o, V3 d, float 
     if (c->objects[obj].type == OBJ_YARNS) {
         // cyls[i]->intersection (Geometry.h:740-766) on the object-space ray + the `localt < t` of Yarns::intersection (TriangleMesh.cpp:1711):
         // A = end point, B.w = radius, C = unit axis d and length
-        const V3 dl = xf_dir(m, d), ol = xf_point(m, o);
-        const float A3[3] = {qa.x, qa.y, qa.z}, D3[3] = {qc.x, qc.y, qc.z};
         float tt;
-        if (!cylinder_t(A3, D3, qb.w * qb.w, qc.w, ol, dl, tt)) return false;
+        if (!cylinder_t_rn(v3(qa.x, qa.y, qa.z), v3(qc.x, qc.y, qc.z), qb.w, qc.w, xf_point_rn(m, o), xf_dir_rn(m, d), tt)) return false;
         if (!(tt < tbest)) return false;
         t = tt; b1 = 0; b2 = 0;
         return true;
@@ -195,11 +224,7 @@ PTB_EXACT_LINKAGE bool tri_exact(const AlphaCtx* c, int prim, V3 o, V3 d, float 
         t = tt; b1 = 0; b2 = 0;
         return true;
     }
-    const V3 dl = v3(add_rn(add_rn(mul_rn(m[0], d.x), mul_rn(m[1], d.y)), mul_rn(m[2], d.z)), add_rn(add_rn(mul_rn(m[4], d.x), mul_rn(m[5], d.y)), mul_rn(m[6], d.z)),
-                     add_rn(add_rn(mul_rn(m[8], d.x), mul_rn(m[9], d.y)), mul_rn(m[10], d.z)));
-    const V3 ol = v3(add_rn(add_rn(add_rn(mul_rn(m[0], o.x), mul_rn(m[1], o.y)), mul_rn(m[2], o.z)), m[3]),
-                     add_rn(add_rn(add_rn(mul_rn(m[4], o.x), mul_rn(m[5], o.y)), mul_rn(m[6], o.z)), m[7]),
-                     add_rn(add_rn(add_rn(mul_rn(m[8], o.x), mul_rn(m[9], o.y)), mul_rn(m[10], o.z)), m[11]));
+    const V3 dl = xf_dir_rn(m, d), ol = xf_point_rn(m, o);
     const V3 A = v3(qa.x, qa.y, qa.z);
     const V3 u = sub3_rn(v3(qb.x, qb.y, qb.z), A), v = sub3_rn(v3(qc.x, qc.y, qc.z), A);
     const V3 N = cross_rn(u, v);
@@ -410,13 +435,14 @@ PTB_HD void surface_from_hit(const SceneDev& sc, V3 o, V3 d, const Hit& hit, int
         obp = &sc.objects[s.object];
         if (EXOTIC && tu.group == PTB_GROUP_YARN) {
             // ---- the tail of cyls[i]->intersection (Geometry.h:756-763) on the segment's OWN default material: n0 = axis d, n1 = A ----
-            const V3 dl = xf_dir(obp->inv_trans, d), ol = xf_point(obp->inv_trans, o);
-            const V3 Pl = ol + hit.t * dl;
+            // (one rounding per operation: the radial normal is the small difference of two points far from the origin)
+            const V3 dl = xf_dir_rn(obp->inv_trans, d), ol = xf_point_rn(obp->inv_trans, o);
+            const V3 Pl = add3_rn(ol, scale_rn(hit.t, dl));
             const V3 a0 = v3(ts.n1[0], ts.n1[1], ts.n1[2]), ax = v3(ts.n0[0], ts.n0[1], ts.n0[2]);
-            const V3 proj = a0 + dot(Pl - a0, ax) * ax;
+            const V3 proj = add3_rn(a0, scale_rn(dot_rn(sub3_rn(Pl, a0), ax), ax));
             s.Kd = v3(1, 1, 1); s.Ks = v3(0, 0, 0); s.Ne = v3(1, 1, 1); s.transp = false; s.refr_index = 1.3f; s.Ke = v3(0, 0, 0); s.Ksub = v3(0, 0, 0);
             s.P = xf_point(obp->trans, Pl);
-            s.N = fast_normalize(xf_rot(obp->rot, Pl - proj));      // never flipped: the segment's flip_normals, not the Yarns object's
+            s.N = fast_normalize(xf_rot(obp->rot, sub3_rn(Pl, proj)));      // never flipped: the segment's flip_normals, not the Yarns object's
             return;
         }
         if (EXOTIC && tu.group == PTB_GROUP_DISC) {
