@@ -87,6 +87,27 @@ def case_yarn_from_inside(test_lib, oracle_lib):
     a.close(); b.close()
 
 
+def yarn_cloth_scene(lib, W=512, H=512, spp=1, n=120, seg=300, radius=0.003):
+    """A cloth of 2 n yarns x `seg` segments (72,000 by default) of the reference's own proportions (its reader gives radius 0.1 to
+    curves of extent 50: 2e-3; here 0.12 at distance 50).  Thinner yarns are not a parity case: `delta = b*b - 4*a*c` of
+    Cylinder::intersection cancels log10((distance / radius)^2) digits, so within a few per cent of a thin tube's silhouette the
+    REFERENCE's answer is rounding noise that its own tight boxes then cull or keep (measured: 99.998 % of the primary ids agree
+    at radius 0.18, 99.994 % at 0.12, 99.97 % at 0.064)."""
+    rt = scenes.base(lib, W, H, spp)
+    y = Yarns(*scenes.weave_segments(n, n, seg, radius=radius))
+    y.scale, y.mat_rotation, y.max_translation = 40.0, scenes._rot(1.0, 0.4), np.array([0, -14, 0], np.float32)
+    rt.s.addObject(y)
+    return rt
+
+
+def case_yarn_cloth(test_lib, oracle_lib, W=512, H=512):
+    a, b = yarn_cloth_scene(oracle_lib, W, H).commit(), yarn_cloth_scene(test_lib, W, H).commit()
+    assert (a.primary_ids()[0] == 3).mean() > 0.5, "the cloth must fill the view"
+    check_ids(b, a, need_mesh=False)
+    check_images(b.render_image_nopreviz().copy(), a.render_image_nopreviz().copy())
+    a.close(); b.close()
+
+
 def case_branch_scene(test_lib, oracle_lib, mk, frac=FRAC_1SPP, gold=None):
     """getColor's branching modes (fog, ghost objects, background photograph).  Same per-contribution pcg32 streams on both
     sides (oracle/build_ref.py patch 7), so the images are compared at equal seed like the linear scenes.  Ray counters are

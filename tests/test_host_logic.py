@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
 from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_triangle_soup, case_passes_and_shards,
-                          case_progressive, case_scene, case_yarn_from_inside, check_ids)
+                          case_progressive, case_scene, case_yarn_cloth, case_yarn_from_inside, check_ids)
 
 from pathtracer_b200 import _abi, scenes
 
@@ -36,6 +36,10 @@ def test_edge_cases_devsim(devsim, port, variant):
 
 def test_yarn_seen_from_inside_its_covering_prism_devsim(devsim, port):
     case_yarn_from_inside(devsim, port)
+
+
+def test_yarn_cloth_of_72000_segments_devsim(devsim, port):
+    case_yarn_cloth(devsim, port, 256, 256)
 
 
 def test_progressive_devsim(devsim, port):

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
 from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_node_test_half, case_triangle_soup, case_passes_and_shards,
-                          case_progressive, case_scene, case_yarn_from_inside, check_ids, check_images)
+                          case_progressive, case_scene, case_yarn_cloth, case_yarn_from_inside, check_ids, check_images)
 
 from pathtracer_b200 import _abi, scenes
 
@@ -215,6 +215,10 @@ def test_edge_cases_gpu(gpu, port, variant):
 
 def test_yarn_seen_from_inside_its_covering_prism_gpu(gpu, port):
     case_yarn_from_inside(gpu, port)
+
+
+def test_yarn_cloth_of_72000_segments_gpu(gpu, port):
+    case_yarn_cloth(gpu, port)
 
 
 def test_progressive_gpu(gpu, port):
