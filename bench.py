@@ -305,6 +305,10 @@ def main():
                 dist.all_reduce(est, op=dist.ReduceOp.MAX)
             steps = max(steps, min(6, int(2.0 / max(float(est[0]), 1e-3))))
         rt.nrays = full_spp
+        if brief and world > 1:
+            # the first full-spp sharded step after short ones ran 8 % (C3) to 20 % (C5) slower than the ones after it at N = 8
+            # (profiles/r02aa: `value` below `e2e`, which is measured later in the same process): one untimed full step first
+            rt.render_resident()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()

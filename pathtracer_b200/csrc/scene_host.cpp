@@ -369,6 +369,8 @@ int HostScene::flatten(FlatScene& out, std::string& err) {
     if (out.merl.empty()) out.merl.push_back(0.f);
 
     // ---- world-space triangle soup over all meshes ----
+    // (k_trace hands a candidate to k_exact as triangle index | flags << 28, ptb_engine.cu)
+    if (n_tri >= (int64_t)1 << 28) { err = "commit: more than 2^28 triangles (discs and yarn faces included)"; return PTB_ERR_UNSUPPORTED; }
     out.n_tri_scene = n_tri;
     struct Src { int obj; int tri; uint8_t alpha; };
     std::vector<float> verts9(9 * (size_t)n_tri);
