@@ -104,7 +104,17 @@ def case_yarn_cloth(test_lib, oracle_lib, W=512, H=512):
     a, b = yarn_cloth_scene(oracle_lib, W, H).commit(), yarn_cloth_scene(test_lib, W, H).commit()
     assert (a.primary_ids()[0] == 3).mean() > 0.5, "the cloth must fill the view"
     check_ids(b, a, need_mesh=False)
+    # direct light only: camera rays are bit-identical on both sides, so the usual equal-seed bound holds (measured 0.15 % on the GPU)
+    a.nb_bounces = b.nb_bounces = 1
     check_images(b.render_image_nopreviz().copy(), a.render_image_nopreviz().copy())
+    # full depth: a bounced ray differs in its last bits between the two implementations, and for such a ray the REFERENCE's
+    # hit-or-miss near the silhouette of a far, thin tube is a coin toss (the docstring above); the flips are unbiased, so the image
+    # means and the ray counters still agree closely while single pixels do not (measured on the GPU, profiles/r02ae_yarn_cloth.txt:
+    # 1.7 % of the pixels off by more than 1e-3 at radius 0.12, 1.0 % at 0.18, 0.4 % at 0.36, 0.13 % at 0.8; means within 5e-5)
+    a.nb_bounces = b.nb_bounces = 5
+    check_images(b.render_image_nopreviz().copy(), a.render_image_nopreviz().copy(), frac=0.05, mean_rel=5e-4)
+    for k in ("rays_closest", "rays_shadow"):
+        assert abs(a.stats[k] - b.stats[k]) <= 0.001 * a.stats[k], k
     a.close(); b.close()
 
 
