@@ -68,11 +68,12 @@ struct Builder {
     void build(int64_t node, int64_t b, int64_t e, int depth);
 };
 
-constexpr int NBINS = 16;
+constexpr int NBINS_MAX = 64;
 // builder knobs (environment overrides are for experiments only; the defaults are what ships)
 static float env_f(const char* n, float d) { const char* v = getenv(n); return v ? (float)atof(v) : d; }
 static const float C_TRAV = env_f("PTB_BVH_CTRAV", 0.25f);   // binary nodes mostly vanish in the collapse
 static const int MAX_LEAF = (int)env_f("PTB_BVH_MAXLEAF", 3.f);
+static const int NBINS = std::min(NBINS_MAX, std::max(4, (int)env_f("PTB_BVH_NBINS", 16.f)));   // SAH bins per axis
 static const int COLLAPSE_DP = (int)env_f("PTB_BVH_COLLAPSE_DP", 1.f);   // 0: greedy surface-area collapse of a binary tree with <= 3-triangle leaves
 static const float C_NODE = env_f("PTB_BVH_CNODE", 1.f), C_PRIM = env_f("PTB_BVH_CPRIM", 0.5f);   // measured (profiles/r01m): 0.5 beats 0.3 and 0.15 on C2 and C3
 
@@ -124,7 +125,7 @@ void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
     for (int ax = 0; ax < 3; ax++) {
         const float lo = cb.lo[ax], ext = cb.hi[ax] - cb.lo[ax];
         if (!(ext > 0)) continue;
-        Box bb[NBINS]; int64_t bc[NBINS];
+        Box bb[NBINS_MAX]; int64_t bc[NBINS_MAX];
         for (int k = 0; k < NBINS; k++) { bb[k].reset(); bc[k] = 0; }
         const float scale = NBINS / ext;
         for (int64_t i = b; i < e; i++) {
@@ -133,7 +134,7 @@ void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
             k = k < 0 ? 0 : (k >= NBINS ? NBINS - 1 : k);
             bb[k].grow(pbox[p]); bc[k]++;
         }
-        float ra[NBINS]; int64_t rc[NBINS];
+        float ra[NBINS_MAX]; int64_t rc[NBINS_MAX];
         Box acc; acc.reset(); int64_t c = 0;
         for (int k = NBINS - 1; k > 0; k--) { acc.grow(bb[k]); c += bc[k]; ra[k] = acc.area(); rc[k] = c; }
         acc.reset(); c = 0;
