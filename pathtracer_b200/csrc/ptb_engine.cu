@@ -59,6 +59,25 @@ using namespace ptb;
 #ifndef PTB_SMEM_STACK
 #define PTB_SMEM_STACK 0   /* entries of k_trace's traversal stack held in shared memory (A/B: profiles/r02a_ab_smem_stack.txt) */
 #endif
+// L1 policy of k_trace's two gathers (A/B): nodes are re-read by every ray of a warp and by its neighbours (the top levels by everybody),
+// a triangle is read by the few rays that reach its leaf.  PTB_LD_TRI: 1 = triangles do not allocate in L1, 2 = evict first;
+// PTB_LD_NODE: 1 = nodes evict last.  0 = plain read-only loads (__ldg).
+#if !defined(PTB_LD_TRI)
+#define PTB_LD_TRI 0
+#endif
+#if !defined(PTB_LD_NODE)
+#define PTB_LD_NODE 0
+#endif
+__device__ __forceinline__ float4 ld_hint(const float4* q, int hint) {
+    float4 v;
+    if (hint == 1) asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q));
+    else if (hint == 2) asm("ld.global.nc.L1::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q));
+    else if (hint == 3) asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q));
+    else v = __ldg(q);
+    return v;
+}
+#define PTB_LDN(q) ld_hint((q), PTB_LD_NODE ? 3 : 0)
+#define PTB_LDT(q) ld_hint((q), PTB_LD_TRI)
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) k_rpp(float* rpp, int n) {
@@ -162,11 +181,11 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                     F4 o, d;
                     float tmax;
                     bool ok = true;
-                    if (ANY_HIT) { entry = qi; o = p.sh_o[qi]; d = p.sh_d[qi]; tmax = o.w; }
+                    if (ANY_HIT) { entry = qi; o = pool_ld(&p.sh_o[qi]); d = pool_ld(&p.sh_d[qi]); tmax = o.w; }
                     else {
                         item = queue ? queue[qi] : qi;
                         ok = p.pixel[item] != 0xffffffffu;
-                        o = p.ray_o[item]; d = p.ray_d[item]; tmax = p.hit[item].x;
+                        o = pool_ld(&p.ray_o[item]); d = pool_ld(&p.ray_d[item]); tmax = p.hit[item].x;
                     }
                     if (ok) {
                         r = ray_prep(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
@@ -205,13 +224,13 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                 if (PTB_EDGE_EPS_ON && ANY_HIT && nd) { /* k_exact delivers or settles */ }
                 else if (ANY_HIT && BRANCH) shadow_settle_branch(p, (int)entry, item, false);
                 else if (ANY_HIT) {   // unoccluded: deliver the deferred direct term (Raytracer.cpp:545-566)
-                    const F4 c = p.sh_c[entry];
-                    F4 L = p.radiance[item];
+                    const F4 c = pool_ld(&p.sh_c[entry]);
+                    F4 L = pool_ld(&p.radiance[item]);
                     L.x += c.x; L.y += c.y; L.z += c.z;
-                    p.radiance[item] = L;
+                    pool_st(&p.radiance[item], L);
                 } else if (hprim >= 0) {
                     F4 q; q.x = tbest; q.y = hb1; q.z = hb2; q.w = u2f((uint32_t)hprim);
-                    p.hit[item] = q;
+                    pool_st(&p.hit[item], q);
                 }
                 live = false;
             }
@@ -240,7 +259,7 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
             if (ngroup.y > 0x00ffffffu) PTB_STK_PUSH(ngroup);
             const uint32_t rel = popcount32(hits_imask & ~(0xffffffffu << slot));
             const float4* np = reinterpret_cast<const float4*>(nodes) + (size_t)(child_base + rel) * 5;
-            const float4 l0 = __ldg(np), l1 = __ldg(np + 1), l2 = __ldg(np + 2), l3 = __ldg(np + 3), l4 = __ldg(np + 4);
+            const float4 l0 = PTB_LDN(np), l1 = PTB_LDN(np + 1), l2 = PTB_LDN(np + 2), l3 = PTB_LDN(np + 3), l4 = PTB_LDN(np + 4);
             F4 n0, n1, n2, n3, n4;
             n0.x = l0.x; n0.y = l0.y; n0.z = l0.z; n0.w = l0.w; n1.x = l1.x; n1.y = l1.y; n1.z = l1.z; n1.w = l1.w;
             n2.x = l2.x; n2.y = l2.y; n2.z = l2.z; n2.w = l2.w; n3.x = l3.x; n3.y = l3.y; n3.z = l3.z; n3.w = l3.w;
@@ -270,7 +289,7 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                     tgroup.y &= ~(1u << ti);
                     const uint32_t prim = tgroup.x + popcount32(tvalid & ~(0xffffffffu << ti));
                     const float4* tp = reinterpret_cast<const float4*>(tris) + (size_t)prim * 3;
-                    const float4 l0 = __ldg(tp), l1 = __ldg(tp + 1), l2 = __ldg(tp + 2);
+                    const float4 l0 = PTB_LDT(tp), l1 = PTB_LDT(tp + 1), l2 = PTB_LDT(tp + 2);
                     F4 a, b, c;
                     a.x = l0.x; a.y = l0.y; a.z = l0.z; a.w = l0.w; b.x = l1.x; b.y = l1.y; b.z = l1.z; b.w = l1.w;
                     c.x = l2.x; c.y = l2.y; c.z = l2.z; c.w = l2.w;
@@ -409,7 +428,7 @@ __global__ void __launch_bounds__(PTB_SHADE_BLOCK, (MINB * 128) / PTB_SHADE_BLOC
     bc = __shfl_sync(0xffffffffu, bc, 0); bs = __shfl_sync(0xffffffffu, bs, 0);
     const uint32_t below = (1u << lane) - 1u;
     if (out.cont) next_queue[bc + __popc(mc & below)] = (uint32_t)path;
-    if (out.shadow) { const uint32_t si = bs + __popc(ms & below); p.sh_o[si] = out.sh_o; p.sh_d[si] = out.sh_d; p.sh_c[si] = out.sh_c; }
+    if (out.shadow) { const uint32_t si = bs + __popc(ms & below); pool_st(&p.sh_o[si], out.sh_o); pool_st(&p.sh_d[si], out.sh_d); pool_st(&p.sh_c[si], out.sh_c); }
 }
 
 // Branching renders (fog, ghost objects, background photograph): one getColor loop iteration per queue entry; side branches

@@ -556,6 +556,31 @@ struct PoolDev {
     U2* defer_rays;         // queue of the rays that left some: {path slot or shadow entry, how many}
 };
 
+// Cache policy of the path pool (A/B: -DPTB_POOL_STREAM=1).  The pool is a stream: every kernel of a bounce reads and rewrites
+// 100-200 bytes per path, gigabytes per launch, nothing of it is reused inside a kernel, while the gathers of the same kernels (BVH
+// nodes, triangles, per-triangle attributes, texels: 60-200 MB per scene) are what the 126 MB L2 should hold on to.  With the flag the
+// pool's 16-byte loads / stores carry the streaming hint (ld.global.cs / st.global.cs: first in line for eviction).
+#if !defined(PTB_POOL_STREAM)
+#define PTB_POOL_STREAM 0
+#endif
+PTB_HD F4 pool_ld(const F4* q) {
+#if defined(__CUDA_ARCH__) && PTB_POOL_STREAM
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(q));
+    F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+#else
+    return *q;
+#endif
+}
+PTB_HD void pool_st(F4* q, const F4& v) {
+#if defined(__CUDA_ARCH__) && PTB_POOL_STREAM
+    __stcs(reinterpret_cast<float4*>(q), make_float4(v.x, v.y, v.z, v.w));
+#else
+    *q = v;
+#endif
+}
+
+
 struct FrameDev {     // per-render constants (Raytracer fields + prepare_render results)
     CameraDev cam;
     FilterDev filter;
@@ -667,14 +692,14 @@ PTB_HD void raygen_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pa
     V3 o, d;
     camera_ray(f.cam, i, j, dx, dy, ax, ay, o, d);
     F4 q;
-    q.x = o.x; q.y = o.y; q.z = o.z; q.w = 0; p.ray_o[path] = q;
-    q.x = d.x; q.y = d.y; q.z = d.z; q.w = 0; p.ray_d[path] = q;
-    q.x = 1; q.y = 1; q.z = 1; q.w = u2f(pack_state(f.nb_bounces, true)); p.weight[path] = q;
-    q.x = 0; q.y = 0; q.z = 0; q.w = 0; p.radiance[path] = q;
+    q.x = o.x; q.y = o.y; q.z = o.z; q.w = 0; pool_st(&p.ray_o[path], q);
+    q.x = d.x; q.y = d.y; q.z = d.z; q.w = 0; pool_st(&p.ray_d[path], q);
+    q.x = 1; q.y = 1; q.z = 1; q.w = u2f(pack_state(f.nb_bounces, true)); pool_st(&p.weight[path], q);
+    q.x = 0; q.y = 0; q.z = 0; q.w = 0; pool_st(&p.radiance[path], q);
     if (f.accum_albedo) { p.aov_n[path] = q; p.aov_kd[path] = q; }   // `Vector normal, albedo;` start at zero (Vector.h:45) and stay there on a miss
     float ta; int32_t ida;
     analytic_closest<EXOTIC>(sc, o, d, ta, ida);        // the analytic half of Scene::intersection rides with the ray producer
-    q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
+    q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); pool_st(&p.hit[path], q);
     p.rng[path] = e.state;
     p.pixel[path] = pix;
     if (p.root) p.root[path] = (uint32_t)path;
@@ -739,17 +764,17 @@ PTB_HD bool shade_terminal_one(const SceneDev& sc, PoolDev& p, int path) {
 template <bool MERL, bool AOV = false, bool EXOTIC = true>
 PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int path, ShadeOut& out) {
     out.cont = false; out.shadow = false; out.shadow_query = false;
-    const F4 hq = p.hit[path];
+    const F4 hq = pool_ld(&p.hit[path]);
     const int32_t id = (int32_t)f2u(hq.w);
     if (id == PTB_HIT_MISS) return;                                  // Raytracer.cpp:654-657
-    const F4 oq = p.ray_o[path], dq = p.ray_d[path], wq = p.weight[path];
+    const F4 oq = pool_ld(&p.ray_o[path]), dq = pool_ld(&p.ray_d[path]), wq = pool_ld(&p.weight[path]);
     const V3 ro = v3(oq.x, oq.y, oq.z), rd = v3(dq.x, dq.y, dq.z);
     const V3 w = v3(wq.x, wq.y, wq.z);
     const uint32_t st = f2u(wq.w);
     const int depth = (int)(st & 0xffffu);
     const bool show_lights = (st & 0x10000u) != 0;
     Hit hit; hit.t = hq.x; hit.b1 = hq.y; hit.b2 = hq.z; hit.prim = id;
-    F4 Lq = p.radiance[path];
+    F4 Lq = pool_ld(&p.radiance[path]);
     if (AOV && depth == f.nb_bounces) {
         Surface s0;
         surface_from_hit<EXOTIC>(sc, ro, rd, hit, id, s0);
@@ -760,7 +785,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
     if (id == hit_id_analytic(0)) {                                  // the light, Raytracer.cpp:303-316
         const float lp = show_lights ? sc.lightPower : 0.f;
         Lq.x += w.x * lp; Lq.y += w.y * lp; Lq.z += w.z * lp;
-        p.radiance[path] = Lq;
+        pool_st(&p.radiance[path], Lq);
         return;
     }
     if (id == hit_id_analytic(1) && !sc.has_envmap) return;          // dome without a map: Ke = 0
@@ -769,7 +794,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
     if (s.object == 1) {                                             // env dome, Raytracer.cpp:275-301
         const V3 c = (w * sc.envmap_intensity) * s.Ke;
         Lq.x += c.x; Lq.y += c.y; Lq.z += c.z;
-        p.radiance[path] = Lq;
+        pool_st(&p.radiance[path], Lq);
         return;
     }
     const ObjectDev& ob = sc.objects[s.object];
@@ -838,7 +863,7 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
                         out.sh_c.x = c.x; out.sh_c.y = c.y; out.sh_c.z = c.z; out.sh_c.w = 0;
                     } else {
                         Lq.x += c.x; Lq.y += c.y; Lq.z += c.z;
-                        p.radiance[path] = Lq;
+                        pool_st(&p.radiance[path], Lq);
                     }
                 }
             } else {
@@ -876,12 +901,12 @@ PTB_HD void shade_one(const SceneDev& sc, const FrameDev& f, PoolDev& p, int pat
     if (ndepth == 0 || norm2(nw) < 0.01f * 0.01f) return;
     // NaN weights fall through `<` like the reference; keep tracing them as it does
     F4 q;
-    q.x = no.x; q.y = no.y; q.z = no.z; q.w = 0; p.ray_o[path] = q;
-    q.x = nd.x; q.y = nd.y; q.z = nd.z; q.w = 0; p.ray_d[path] = q;
-    q.x = nw.x; q.y = nw.y; q.z = nw.z; q.w = u2f(pack_state(ndepth, nshow)); p.weight[path] = q;
+    q.x = no.x; q.y = no.y; q.z = no.z; q.w = 0; pool_st(&p.ray_o[path], q);
+    q.x = nd.x; q.y = nd.y; q.z = nd.z; q.w = 0; pool_st(&p.ray_d[path], q);
+    q.x = nw.x; q.y = nw.y; q.z = nw.z; q.w = u2f(pack_state(ndepth, nshow)); pool_st(&p.weight[path], q);
     float ta; int32_t ida;
     analytic_closest<EXOTIC>(sc, no, nd, ta, ida);
-    q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); p.hit[path] = q;
+    q.x = ta; q.y = 0; q.z = 0; q.w = u2f((uint32_t)ida); pool_st(&p.hit[path], q);
     out.cont = true;
 }
 
@@ -1354,7 +1379,7 @@ PTB_HD void splat_pixel(const FrameDev& f, const PoolDev& p, int ps, F4* accum, 
         F4 c, a, n;
         c.x = c.y = c.z = c.w = 0; a = c; n = c;
         for (int s = 0; s < f.spp_pass; s++) {
-            const F4 L = p.radiance[ps * f.spp_pass + s];
+            const F4 L = pool_ld(&p.radiance[ps * f.spp_pass + s]);
             c.x += L.x; c.y += L.y; c.z += L.z; c.w += 1.f;
             if (f.accum_albedo) {
                 const F4 ka = p.aov_kd[ps * f.spp_pass + s], kn = p.aov_n[ps * f.spp_pass + s];
@@ -1368,7 +1393,7 @@ PTB_HD void splat_pixel(const FrameDev& f, const PoolDev& p, int ps, F4* accum, 
     }
     if (f.lowres) {                                      // Raytracer.cpp:1508-1510: every sample adds colour/256 to its 16x16 block
         float r = 0, g = 0, b = 0;
-        for (int s = 0; s < f.spp_pass; s++) { const F4 L = p.radiance[ps * f.spp_pass + s]; r += L.x * (1.f / 256.f); g += L.y * (1.f / 256.f); b += L.z * (1.f / 256.f); }
+        for (int s = 0; s < f.spp_pass; s++) { const F4 L = pool_ld(&p.radiance[ps * f.spp_pass + s]); r += L.x * (1.f / 256.f); g += L.y * (1.f / 256.f); b += L.z * (1.f / 256.f); }
         float* q = f.lowres + ((size_t)(f.lowresH - i / 16 - 1) * f.lowresW + j / 16) * 3;
 #if defined(__CUDA_ARCH__)
         atomicAdd(q, r); atomicAdd(q + 1, g); atomicAdd(q + 2, b);
@@ -1384,7 +1409,7 @@ PTB_HD void splat_pixel(const FrameDev& f, const PoolDev& p, int ps, F4* accum, 
             Pcg32 e = pcg32_for_sample(pix, (uint32_t)(f.k0 + s), f.seed);
             const float dx = pcg32_uniform(e) - 0.5f;
             const float dy = pcg32_uniform(e) - 0.5f;
-            const F4 L = p.radiance[ps * f.spp_pass + s];
+            const F4 L = pool_ld(&p.radiance[ps * f.spp_pass + s]);
 #pragma unroll
             for (int a = 0; a < 3; a++)
 #pragma unroll
@@ -1407,7 +1432,7 @@ PTB_HD void splat_pixel(const FrameDev& f, const PoolDev& p, int ps, F4* accum, 
             Pcg32 e = pcg32_for_sample(pix, (uint32_t)(f.k0 + s), f.seed);
             const float dx = pcg32_uniform(e) - 0.5f;
             const float dy = pcg32_uniform(e) - 0.5f;
-            const F4 L = p.radiance[ps * f.spp_pass + s];
+            const F4 L = pool_ld(&p.radiance[ps * f.spp_pass + s]);
             for (int i2 = bmin_i; i2 <= bmax_i; i2++)
                 for (int j2 = bmin_j; j2 <= bmax_j; j2++) {
                     const float w = filter_weight(f.filter, denom1, i2, j2, i, j, dx, dy);
