@@ -607,22 +607,16 @@ def test_ngan_preset_scene_vs_oracle_and_golden(gpu, port):
 @pytest.mark.parametrize("name", ["C2", "C3"])
 def test_full_size_equal_seed_parity(gpu, port, name):
     """BASELINE.json configs[1] and [2] at their full triangle counts and resolutions, 1 spp: primary-hit triangle ids (the north
-    star's criterion, >= 99.99 %) and the fixed-seed single-sample image against the oracle on the same seeded input.
-    C3 puts 2.5 M triangles under 2.07 M pixels with a checker alpha map inside the traversal: measured 293 differing pixels
-    (99.9859 %), of which 152 report the OTHER triangle of a shared edge at the same distance (a tie both tests accept; the
-    reference keeps whichever its binary BVH meets first) and 141 are silhouette / alpha-texel-border rays where the world-space
-    Moller-Trumbore test and the reference's object-space plane + Gram test round differently.  So C3 asserts >= 99.98 % exact ids
-    and >= 99.99 % hit agreement when an equal-distance tie on the same object counts as the same hit."""
+    star's criterion, >= 99.99 %, asserted literally) and the fixed-seed single-sample image against the oracle on the same seeded
+    input.  C3 puts 2.5 M triangles under 2.07 M pixels with a checker alpha map inside the traversal.  Round 1 measured 293
+    differing pixels there (99.9859 %: 152 equal-distance ties on shared edges, 141 silhouette / alpha-border rays where the
+    world-space Moller-Trumbore test and the reference's object-space plane + Gram test round differently) and relaxed the bound;
+    since round 2 a ray within 5e-4 (barycentric) of an edge and every alpha-tested hit are decided by the reference's own arithmetic
+    (tri_exact): 5 differing pixels of 2,073,600 (99.9998 %, profiles/r02d_c3_ids.txt), 1 on C2."""
     mk = lambda L: scenes.CONFIGS[name](L, spp=1)
     a, b = mk(port).commit(), mk(gpu).commit()
     assert b.scene_info()["n_triangles"] == {"C2": 1000000, "C3": 2502724}[name]
-    if name == "C3":
-        check_ids(b, a, agree=0.9998)
-        (oa, ta, da), (ob, tb, db) = a.primary_ids(), b.primary_ids()
-        tie = (oa == ob) & (ta != tb) & (np.abs(da - db) <= 1e-5 * np.abs(da))
-        assert (((oa == ob) & (ta == tb)) | tie).mean() >= 0.9999
-    else:
-        check_ids(b, a)
+    check_ids(b, a)
     ia, ib = a.render_image_nopreviz().copy(), b.render_image_nopreviz().copy()
     check_images(ib, ia, frac=FRAC_FULL)
     for k in ("rays_closest", "rays_shadow"):
