@@ -7,6 +7,7 @@
 // Queues are index lists compacted with warp ballots + one atomic per warp (k_shade); every kernel reads
 // its element count from device memory, so the host never waits for a count.
 // There is no CPU implementation behind this ABI: a missing device or a failed launch is an error code.
+#include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -379,6 +380,36 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool want) {
     if ((int)lane == leader) base = atomicAdd(counter, __popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// EXPERIMENT (PTB_SORT_QUEUE=1|2, one pass pipeline): how much would `k_trace` gain from a coherent bounce queue?  The queue of a bounce
+// >= 1 is sorted by {direction octant, Morton code of the origin on a 512^3 grid} (1) or {Morton code, octant} (2) with a separate
+// radix sort before the traversal kernel; the sort's own time is not part of the kernel's.  An upper bound for what binning the queue
+// inside k_shade's append could buy (VERDICT round 1, item 3 ii); measured in profiles/r02aj_ab_sorted_queue.txt.
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {   // 9 bits -> every third bit
+    v &= 0x1ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void __launch_bounds__(256) k_queue_keys(PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count, int n, uint32_t* keys, int mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t key = 0xffffffffu;
+    if ((uint32_t)i < *count) {
+        const uint32_t item = queue[i];
+        const F4 o = p.ray_o[item], d = p.ray_d[item];
+        const uint32_t oct = (d.x < 0 ? 4u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 1u : 0u);
+        const float sc_ = 512.f / 160.f;
+        const uint32_t qx = (uint32_t)fminf(fmaxf((o.x + 80.f) * sc_, 0.f), 511.f), qy = (uint32_t)fminf(fmaxf((o.y + 80.f) * sc_, 0.f), 511.f),
+                       qz = (uint32_t)fminf(fmaxf((o.z + 80.f) * sc_, 0.f), 511.f);
+        const uint32_t m = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+        key = mode == 2 ? ((m << 3) | oct) : ((oct << 27) | m);
+        key &= 0x7fffffffu;
+    }
+    keys[i] = key;
 }
 
 // Shades the terminal hits of a bounce (miss / light / dome) and compacts the surface hits into `out_queue` for k_shade.
@@ -757,6 +788,9 @@ struct ptb_ctx {
     uint32_t* d_queue[2] = {nullptr, nullptr};
     uint32_t* d_queue_surf = nullptr;          // the surface hits of the current bounce (k_sort_hits -> k_shade)
     bool sort_hits = false;                    // PTB_OPT_SORT_HITS (measured r01k: slower)
+    int sort_queue = 0;                        // PTB_SORT_QUEUE experiment (k_queue_keys): 0 off, 1 octant-major, 2 origin-major
+    uint32_t *d_sort_keys = nullptr, *d_sort_keys2 = nullptr, *d_sort_vals = nullptr;
+    void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0; int sort_cap = 0;
     uint32_t* d_counters = nullptr;
     unsigned long long* d_totals = nullptr;
     float* d_rpp = nullptr;
@@ -828,6 +862,8 @@ static void free_pool(ptb_ctx* c) {
     for (void* p : ptrs) if (p) cudaFree(p);
     memset(&c->pool, 0, sizeof(c->pool));
     c->d_queue[0] = c->d_queue[1] = nullptr; c->d_queue_surf = nullptr;
+    cudaFree(c->d_sort_keys); cudaFree(c->d_sort_keys2); cudaFree(c->d_sort_vals); cudaFree(c->d_sort_tmp);     // (the PTB_SORT_QUEUE experiment's buffers)
+    c->d_sort_keys = c->d_sort_keys2 = c->d_sort_vals = nullptr; c->d_sort_tmp = nullptr; c->sort_cap = 0;
     c->pool_cap = 0;
 }
 
@@ -1030,6 +1066,7 @@ int ptb_create(int device_id, ptb_ctx** out) {
     if (const char* e = getenv("PTB_SHADE_MINB_MERL")) c->shade_minb_merl = atoi(e);
     if (const char* e = getenv("PTB_PIPES")) c->n_pipes = std::max(1, std::min(atoi(e), PTB_MAX_PIPES));
     if (const char* e = getenv("PTB_SORT_HITS")) c->sort_hits = atoi(e) != 0;   // experiments: 0 = k_shade sees every hit
+    if (const char* e = getenv("PTB_SORT_QUEUE")) c->sort_queue = atoi(e);
     memset(&c->pool, 0, sizeof(c->pool));
     memset(&c->sc, 0, sizeof(c->sc));
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1441,6 +1478,21 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
                     const bool mesh = c->sc.has_mesh != 0;
                     // persistent grid: as many blocks as are resident at once, but no more than the queue can feed
                     const unsigned gt = (unsigned)std::max(1, std::min<int>(n_pipes > 1 ? c->trace_blocks_piped : c->trace_blocks, (n_paths + 127) / 128));
+                    if (mesh && c->sort_queue && b >= 1 && n_pipes == 1) {     // experiment: a coherent queue for this bounce (untimed)
+                        if (c->sort_cap < n_paths) {
+                            cudaFree(c->d_sort_keys); cudaFree(c->d_sort_keys2); cudaFree(c->d_sort_vals); cudaFree(c->d_sort_tmp);
+                            CK(cudaMalloc((void**)&c->d_sort_keys, (size_t)n_paths * 4)); CK(cudaMalloc((void**)&c->d_sort_keys2, (size_t)n_paths * 4));
+                            CK(cudaMalloc((void**)&c->d_sort_vals, (size_t)n_paths * 4));
+                            c->sort_tmp_bytes = 0;
+                            cub::DeviceRadixSort::SortPairs(nullptr, c->sort_tmp_bytes, c->d_sort_keys, c->d_sort_keys2, c->d_sort_vals, c->d_sort_vals, n_paths, 0, 32, ps);
+                            CK(cudaMalloc(&c->d_sort_tmp, c->sort_tmp_bytes));
+                            c->sort_cap = n_paths;
+                        }
+                        k_queue_keys<<<g256, 256, 0, ps>>>(pp, q, cnt, n_paths, c->d_sort_keys, c->sort_queue);
+                        size_t tb = c->sort_tmp_bytes;
+                        cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tb, c->d_sort_keys, c->d_sort_keys2, q, c->d_sort_vals, n_paths, 0, 32, ps);
+                        CK(cudaMemcpyAsync(const_cast<uint32_t*>(q), c->d_sort_vals, (size_t)n_paths * 4, cudaMemcpyDeviceToDevice, ps));
+                    }
                     if (mesh) {
                         lt.begin(1 | (b << 8), ps);
                         if (c->count_traversal) k_trace<false, true><<<gt, 128, 0, ps>>>(c->sc, pp, q, cnt, n_paths, pc + PTB_CNT_CUR + 2 * b, c->d_totals, c->refill_below, c->tri_den, c->tri_min_pct, pc + PTB_CNT_DEFER + 2 * b);
