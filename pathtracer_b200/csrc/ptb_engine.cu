@@ -50,7 +50,7 @@ using namespace ptb;
 #define PTB_N_COUNTERS (8 * (PTB_MAX_BOUNCES + 1) + 3)
 #define PTB_DEFER_K 4    /* candidates a ray can leave for k_exact; a ray with more is re-traced there with the immediate exact test */
 // 64-bit totals: 0 closest rays, 1 shadow rays, 2/3 node visits / triangle tests of the closest-hit trace, 4/5 of the any-hit trace
-#define PTB_N_TOTALS 6
+#define PTB_N_TOTALS 10   /* 0-1 rays, 2-5 node visits / triangle tests (closest, any hit), 6-9 triangle-phase warp iterations and their packed minimum (COUNT kernels) */
 #define PTB_BRANCH_MAX_LEVELS 512
 #define PTB_MAX_PIPES 4
 #ifndef PTB_TRACE_MINB
@@ -163,6 +163,7 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
     int sp = 0;
     ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
     uint32_t cn = 0, ct = 0;
+    uint32_t w_iters = 0, w_ideal = 0;   // COUNT: triangle-phase iterations of this warp, and how few would do if its tests were packed 32 to an iteration
     r.o = r.d = r.idir = v3(0, 0, 0); r.oct_inv4 = 0;
 #if PTB_NODE_HALF
     RaySlopes rs; rs.x = rs.y = rs.z = 0;
@@ -284,7 +285,9 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
         const int live_n = __popc(__ballot_sync(FULL, live));
         // (when no live lane can do anything else, every live lane holds triangles and the quorum is met: tri_min_pct <= 100)
         if (tm != 0 && __popc(tm) * 100 >= tri_min_pct * live_n) {
+            uint32_t phase_tests = 0;
             do {
+                if (COUNT) { w_iters++; phase_tests += (uint32_t)__popc(tm); }
                 if (live && tgroup.y != 0) {
                     const uint32_t ti = highest_bit(tgroup.y);
                     tgroup.y &= ~(1u << ti);
@@ -314,11 +317,13 @@ SceneDev sc, PoolDev p, const uint32_t* __restrict__ queue, const uint32_t* __re
                 }
                 tm = __ballot_sync(FULL, live && tgroup.y != 0);
             } while (__popc(tm) * tri_den >= live_n && tm != 0);
+            if (COUNT) w_ideal += (phase_tests + 31u) >> 5;
         }
     }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) { cn += __shfl_down_sync(FULL, cn, o); ct += __shfl_down_sync(FULL, ct, o); }
         if (lane == 0 && (cn | ct)) { atomicAdd(&totals[ANY_HIT ? 4 : 2], (unsigned long long)cn); atomicAdd(&totals[ANY_HIT ? 5 : 3], (unsigned long long)ct); }
+        if (lane == 0 && w_iters) { atomicAdd(&totals[ANY_HIT ? 8 : 6], (unsigned long long)w_iters); atomicAdd(&totals[ANY_HIT ? 9 : 7], (unsigned long long)w_ideal); }
     }
 }
 
@@ -1561,6 +1566,12 @@ static int render_passes(ptb_ctx* c, FrameDev f, int nrays, F4* d_rgbw, ptb_stat
             cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]);
             kt.ms[c->ev_kind[i] & 0xff] += ms;
             kt.launches[c->ev_kind[i] & 0xff]++;
+        }
+        if (getenv("PTB_DEBUG_TRI") && t[6]) {   // triangle phase of k_trace (COUNT kernels): warp iterations, lanes per iteration, packed minimum
+            fprintf(stderr, "[ptb] triangle phase, closest: %llu tests in %llu warp iterations (%.1f lanes each), %llu if packed 32 to an iteration (%.1f %% fewer)\n", t[3], t[6],
+                    (double)t[3] / (double)t[6], t[7], 100.0 * (1.0 - (double)t[7] / (double)t[6]));
+            if (t[8]) fprintf(stderr, "[ptb] triangle phase, any hit: %llu tests in %llu warp iterations (%.1f lanes each), %llu if packed (%.1f %% fewer)\n", t[5], t[8], (double)t[5] / (double)t[8], t[9],
+                              100.0 * (1.0 - (double)t[9] / (double)t[8]));
         }
         if (getenv("PTB_DEBUG_BOUNCES")) {   // per-bounce launch times of the LAST pass + its queue lengths (diagnostics only)
             uint32_t cnt[PTB_N_COUNTERS];
