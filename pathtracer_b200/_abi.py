@@ -10,6 +10,7 @@ import ctypes as C
 import numpy as np
 
 OK = 0
+ERR_INVALID, ERR_STATE, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 SLOT_KD, SLOT_KS, SLOT_NE, SLOT_TRANSP, SLOT_REFR, SLOT_NORMAL, SLOT_ALPHA, SLOT_KSUB = (1 << i for i in range(8))
 OBJ_MIRROR, OBJ_FLIP_NORMALS, OBJ_FLAT_NORMALS, OBJ_GHOST, OBJ_DISPLAY_EDGES = 1, 2, 4, 8, 16
 BRDF_PHONG, BRDF_MERL = 0, 1

@@ -502,6 +502,18 @@ def case_errors(test_lib):
     except _abi.PtbError:
         raised = True
     assert raised, "an empty mesh is rejected"
+    # yarns: missing arrays, no segment, a negative or NaN radius are refused at the boundary
+    ctx = C.c_void_p()
+    test_lib.check(test_lib.create(0, C.byref(ctx)))
+    a = np.zeros((2, 3), np.float32); b = np.ones((2, 3), np.float32)
+    for desc in (_abi.YarnsDesc(None, None, None, 2), _abi.YarnsDesc(_abi.fptr(a), _abi.fptr(b), _abi.fptr(np.array([.1, .1], np.float32)), 0),
+                 _abi.YarnsDesc(_abi.fptr(a), _abi.fptr(b), _abi.fptr(np.array([.1, -1], np.float32)), 2),
+                 _abi.YarnsDesc(_abi.fptr(a), _abi.fptr(b), _abi.fptr(np.array([np.nan, .1], np.float32)), 2)):
+        assert test_lib.add_yarns(ctx, C.byref(desc), None, 0, None) == _abi.ERR_INVALID
+    oid = C.c_int(-1)
+    ok = _abi.YarnsDesc(_abi.fptr(a), _abi.fptr(b), _abi.fptr(np.array([.1, .2], np.float32)), 2)
+    assert test_lib.add_yarns(ctx, C.byref(ok), None, 0, C.byref(oid)) == _abi.OK and oid.value == 0
+    test_lib.destroy(ctx)
 
 
 # ---- the other two renderers of the reference over the same integrator -------------------------------------------------
