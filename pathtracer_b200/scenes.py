@@ -326,6 +326,36 @@ def config_fog(lib, W=128, H=128, spp=16, nv=24, device=0, fog_type=0, phase=0, 
     return rt
 
 
+def config_exotic_modes(lib, W=128, H=128, spp=16, device=0, mode="fog"):
+    """The branching modes of getColor over the primitives of row f4: yarns, a point set and a cylinder in a height-exponential fog
+    (mode "fog"), or as / next to ghost objects over a ghost ground plane with a background photograph (mode "ghost": the yarns
+    and the cylinder are ghosts, so shadow rays pass through them and every hit on them spawns the straight-through ray)."""
+    ghost = mode == "ghost"
+    rt = base(lib, W, H, spp, device=device)
+    rt.s.addObject(Sphere((-17, -21.3, 14), 6).set_material(0, **phong((.3, .8, .3), 0.3, 50.0)))
+    y = Yarns(*weave_segments(5, 5, 10))
+    y.scale, y.mat_rotation, y.max_translation = 30.0, _rot(0.9, 0.5), np.array([-3, -13, 4], np.float32)
+    y.ghost = ghost
+    rt.s.addObject(y)
+    ps = PointSet(*torus_points(14))
+    ps.set_material(0, **phong((.5, .5, .5), (.15, .15, .15), 40.0))
+    ps.scale, ps.mat_rotation = 14.0, _rot(0.3, 0.9)
+    ps.max_translation = np.array([19, -20, 10], np.float32)
+    rt.s.addObject(ps)
+    cy = Cylinder((2, -27.3, 22), (6, -15, 20), 2.0).set_material(0, **phong((.9, .5, .2), 0.2, 30.0))
+    cy.ghost = ghost
+    rt.s.addObject(cy)
+    if ghost:
+        rt.s.objects[2].ghost = True
+        rt.s.objects[2].set_material(0, **phong((.7, .7, .7), 0.0, 1.0))
+        rt.s.background_values = photo_background()
+    else:
+        s = rt.s
+        s.fog_density, s.fog_absorption, s.fog_density_decay, s.fog_absorption_decay = 0.3, 0.3, 0.05, 0.05
+        s.fog_type, s.fog_phase_type, s.phase_aniso = 1, 1, 0.4
+    return rt
+
+
 def config_sss(lib, W=128, H=128, spp=16, nv=24, device=0, mixed=True):
     """Subsurface scattering (Raytracer.cpp:318-406) on a torus: Ksub drives the below-surface random walk step; a second,
     ordinary Phong torus and a mirror sphere share the scene when `mixed`."""

@@ -26,6 +26,8 @@ BRANCH_SCENES = {
     "FOG_U1": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=0, phase=1, mesh=False, **kw),
     "FOG_E1": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=1, phase=1, **kw),
     "FOG_E2": lambda L, **kw: scenes.config_fog(L, 48, 48, 2, fog_type=1, phase=2, **kw),
+    "FOG_EXOTIC": lambda L, **kw: scenes.config_exotic_modes(L, 48, 48, 2, mode="fog", **kw),        # yarns, discs and a cylinder in the medium
+    "GHOST_EXOTIC": lambda L, **kw: scenes.config_exotic_modes(L, 48, 48, 2, mode="ghost", **kw),    # ghost yarns / cylinder over a ghost ground + photograph
 }
 # key-framed placement at several frames: before the first key, between keys (Slerp), on a key, after the last
 ANIM_SCENES = {f"ANIM_F{fr}": (lambda L, fr=fr, **kw: scenes.config_anim(L, 48, 48, 2, frame=fr, **kw)) for fr in (0, 3, 5, 8, 12)}
