@@ -527,7 +527,12 @@ def mode_scene(L, W=56, H=40, spp=6):
     return rt
 
 
-def case_progressive(test_lib, oracle_lib, frac=FRAC_1SPP):
+def mode_scene_exotic(L, W=56, H=40, spp=6):
+    """The same ragged frame over the primitives of row f4 (yarns, a point set, a cylinder) on the linear path."""
+    return scenes.config_exotic_modes(L, W, H, spp, mode="plain")
+
+
+def case_progressive(test_lib, oracle_lib, frac=FRAC_1SPP, mode_scene=mode_scene):
     """Raytracer::render_image: un-normalised sums, weight sums, the /max(count,1) display image, the 16x16 low-resolution preview;
     stopping after k passes; and sums == nopreviz sums (same per-(pixel,sample) streams)."""
     a, b = mode_scene(oracle_lib).commit(), mode_scene(test_lib).commit()
@@ -550,7 +555,7 @@ def case_progressive(test_lib, oracle_lib, frac=FRAC_1SPP):
     a.close(); b.close()
 
 
-def case_denoiser_inputs(test_lib, oracle_lib, frac=FRAC_1SPP):
+def case_denoiser_inputs(test_lib, oracle_lib, frac=FRAC_1SPP, mode_scene=mode_scene):
     """render_image_nopreviz with has_denoiser: unsplatted means, first-hit albedo, the reference's `normalImage`, and the first-hit normals."""
     a, b = mode_scene(oracle_lib).commit(), mode_scene(test_lib).commit()
     a.render_denoiser_inputs(); b.render_denoiser_inputs()

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
 from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_triangle_soup, case_passes_and_shards,
-                          case_progressive, case_scene, case_yarn_cloth, case_yarn_from_inside, check_ids)
+                          case_progressive, case_scene, mode_scene_exotic, case_yarn_cloth, case_yarn_from_inside, check_ids)
 
 from pathtracer_b200 import _abi, scenes
 
@@ -48,6 +48,11 @@ def test_progressive_devsim(devsim, port):
 
 def test_denoiser_inputs_devsim(devsim, port):
     case_denoiser_inputs(devsim, port)
+
+
+def test_progressive_and_denoiser_inputs_over_yarns_discs_cylinders_devsim(devsim, port):
+    case_progressive(devsim, port, mode_scene=mode_scene_exotic)
+    case_denoiser_inputs(devsim, port, mode_scene=mode_scene_exotic)
 
 
 def test_converged_devsim(devsim, port):

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 from golden_scenes import ANIM_SCENES, BRANCH_SCENES, SCENES
 from parity_cases import (EDGE_VARIANTS, case_branch_converged, case_branch_errors, case_branch_passes, case_branch_scene, case_converged, case_sss_converged, case_denoiser_inputs, case_edge, case_errors, case_kats, case_merl_index_fast, case_node_test_half, case_triangle_soup, case_passes_and_shards,
-                          case_progressive, case_scene, case_yarn_cloth, case_yarn_from_inside, check_ids, check_images)
+                          case_progressive, case_scene, mode_scene_exotic, case_yarn_cloth, case_yarn_from_inside, check_ids, check_images)
 
 from pathtracer_b200 import _abi, scenes
 
@@ -227,6 +227,11 @@ def test_progressive_gpu(gpu, port):
 
 def test_denoiser_inputs_gpu(gpu, port):
     case_denoiser_inputs(gpu, port)
+
+
+def test_progressive_and_denoiser_inputs_over_yarns_discs_cylinders_gpu(gpu, port):
+    case_progressive(gpu, port, mode_scene=mode_scene_exotic)
+    case_denoiser_inputs(gpu, port, mode_scene=mode_scene_exotic)
 
 
 def test_converged_gpu(gpu, port):
