@@ -330,7 +330,7 @@ def config_exotic_modes(lib, W=128, H=128, spp=16, device=0, mode="fog"):
     """The branching modes of getColor over the primitives of row f4: yarns, a point set and a cylinder in a height-exponential fog
     (mode "fog"), or as / next to ghost objects over a ghost ground plane with a background photograph (mode "ghost": the yarns
     and the cylinder are ghosts, so shadow rays pass through them and every hit on them spawns the straight-through ray); mode
-    "plain" is the same content on the linear path."""
+    "plain" is the same content on the linear path, mode "merl" gives the three of them the measured BRDF of C4."""
     ghost = mode == "ghost"
     rt = base(lib, W, H, spp, device=device)
     rt.s.addObject(Sphere((-17, -21.3, 14), 6).set_material(0, **phong((.3, .8, .3), 0.3, 50.0)))
@@ -350,6 +350,11 @@ def config_exotic_modes(lib, W=128, H=128, spp=16, device=0, mode="fog"):
         rt.s.objects[2].ghost = True
         rt.s.objects[2].set_material(0, **phong((.7, .7, .7), 0.0, 1.0))
         rt.s.background_values = photo_background()
+    elif mode == "merl":      # the BRDF is the OBJECT's: measured (IsoMERLBRDF) yarns, discs and cylinder, with depth of field
+        rt.cam.aperture, rt.cam.focus_distance = np.float32(0.6), np.float32(50)
+        table = merl_table()
+        for o in (y, ps, cy):
+            o.brdf = ("merl", table)
     elif mode == "fog":
         s = rt.s
         s.fog_density, s.fog_absorption, s.fog_density_decay, s.fog_absorption_decay = 0.3, 0.3, 0.05, 0.05

@@ -14,6 +14,7 @@ SCENES = {
     "PTS": lambda L, **kw: scenes.config_points(L, 48, 48, 2, nv=24, **kw),                        # PointSet discs (PointSet.cpp)
     "PTS_EDGES": lambda L, **kw: scenes.config_points(L, 48, 48, 2, nv=16, display_edges=True, **kw),
     "YARN": lambda L, **kw: scenes.config_yarns(L, 48, 48, 2, seg=12, **kw),                       # Yarns (TriangleMesh.h:265-312, TriangleMesh.cpp:1519-1737)
+    "MERL_EXOTIC": lambda L, **kw: scenes.config_exotic_modes(L, 48, 48, 2, mode="merl", **kw),     # IsoMERLBRDF on yarns, discs and a cylinder, thin lens
 }
 
 # getColor's branching modes: background photograph, ghost objects, participating medium
