@@ -70,7 +70,9 @@ def yarn_inside_scene(lib, W=64, H=64, spp=2):
     beyond it (t > 4).  The covering faces must therefore not be cut at the nearest hit so far (their e2.w = 0, ptb_scene.h)."""
     rt = scenes.base(lib, W, H, spp)
     rt.s.addObject(Sphere((0, 0, 2.1), 1.0).set_material(0, **scenes.phong((.3, .8, .3), 0.3, 50.0)))
-    rt.s.addObject(Yarns([[-10, 0, 0], [-4, 0.5, -6]], [[10, 0, 0], [-3, 2, -9]], [2.0, 0.7]))
+    # (the third segment has no length: its axis is 0 / 0 and Cylinder::intersection answers t = NaN, which never wins `localt < t`;
+    #  the fourth has no radius: the reference can only graze its axis; both must stay harmless on every side)
+    rt.s.addObject(Yarns([[-10, 0, 0], [-4, 0.5, -6], [1, 1, -3], [-2, -1, -4]], [[10, 0, 0], [-3, 2, -9], [1, 1, -3], [2, -1, -4]], [2.0, 0.7, 0.5, 0.0]))
     rt.cam.position = np.array([0, 0, 2.1], np.float32)
     rt.cam.direction = np.array([0, 0, -1], np.float32)
     rt.cam.up = np.array([0, 1, 0], np.float32)
