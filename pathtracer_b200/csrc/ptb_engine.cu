@@ -1010,12 +1010,15 @@ static int refit_device(ptb_ctx* c, FlatScene& f, const HostScene& host) {
     int rc = scene_modes(sc, host, c->err);
     sc.background = bg;
     if (rc) return rc;
-    CK(cudaEventRecord(c->ev0, c->stream));
-    CK(cudaMemcpyAsync(const_cast<ObjectDev*>(sc.objects), f.objects.data(), f.objects.size() * sizeof(ObjectDev), cudaMemcpyHostToDevice, c->stream));
     const size_t n_tri = (size_t)(c->bytes_tris / (3 * (int64_t)sizeof(F4)));
-    if (sc.has_mesh && n_tri > 0) {
+    const bool mesh = sc.has_mesh && n_tri > 0;
+    if (mesh) {   // (the first re-pose of a context allocates the per-node boxes: not part of the measured device time)
         if (!sc.tris_obj) { c->err = "refit: the scene was committed without object-space triangles"; return PTB_ERR_STATE; }
         if ((rc = grow(c, &c->d_node_box, &c->node_box_n, 2 * (int64_t)f.bvh.n_nodes + 1))) return rc;
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemcpyAsync(const_cast<ObjectDev*>(sc.objects), f.objects.data(), f.objects.size() * sizeof(ObjectDev), cudaMemcpyHostToDevice, c->stream));
+    if (mesh) {
         uint32_t* outgrown = reinterpret_cast<uint32_t*>(c->d_node_box + 2 * (size_t)f.bvh.n_nodes);      // one flag behind the boxes
         CK(cudaMemsetAsync(outgrown, 0, sizeof(uint32_t), c->stream));
         k_refit_tris<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(sc.tris_obj, sc.objects, const_cast<F4*>(sc.tris), n_tri);
@@ -1025,6 +1028,7 @@ static int refit_device(ptb_ctx* c, FlatScene& f, const HostScene& host) {
             if (count) k_refit_level<<<(count + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<Node8*>(const_cast<F4*>(sc.nodes)), c->d_node_box, sc.tris_obj, sc.objects, first, count, sc.half_c, outgrown);
         }
         CK(cudaGetLastError());
+        CK(cudaEventRecord(c->ev1, c->stream));      // device time of the re-pose: upload of the object table, triangles, node boxes (no host round trip inside)
         uint32_t flag = 0;
         CK(cudaMemcpyAsync(&flag, outgrown, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -1033,8 +1037,7 @@ static int refit_device(ptb_ctx* c, FlatScene& f, const HostScene& host) {
             c->err = "refit: the re-posed scene is more than 16x larger than the committed one (the half grid of the BVH8 cannot hold its cells); commit it at this frame instead";
             return PTB_ERR_UNSUPPORTED;
         }
-    }
-    CK(cudaEventRecord(c->ev1, c->stream));
+    } else CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
