@@ -69,6 +69,7 @@ struct Builder {
 };
 
 constexpr int NBINS_MAX = 64;
+constexpr int64_t PAR_NODE = 1 << 18;      // nodes with at least this many primitives run their passes in chunks (tasks)
 // builder knobs (environment overrides are for experiments only; the defaults are what ships)
 static float env_f(const char* n, float d) { const char* v = getenv(n); return v ? (float)atof(v) : d; }
 static const float C_TRAV = env_f("PTB_BVH_CTRAV", 0.25f);   // binary nodes mostly vanish in the collapse
@@ -111,29 +112,72 @@ void Builder::build(int64_t node, int64_t b, int64_t e, int depth) {
     BNode& nd = nodes[node];
     Box box, cb;
     box.reset(); cb.reset();
+    const int64_t cnt = e - b;
+    // The two passes over a node's primitives (bounds, SAH bins) of the few nodes at the top of the tree, which no sibling task can
+    // overlap with, are cut into chunks that run as tasks; minima, maxima and counts merge exactly, so the tree is the serial one.
+    const int n_chunks = cnt >= PAR_NODE ? (int)std::min<int64_t>(64, cnt / (PAR_NODE / 4)) : 1;
+    if (n_chunks > 1) {
+        std::vector<Box> cbx(2 * (size_t)n_chunks);
+        for (int c = 0; c < n_chunks; c++) {
+#pragma omp task default(shared) firstprivate(c)
+            {
+                const int64_t i0 = b + cnt * c / n_chunks, i1 = b + cnt * (c + 1) / n_chunks;
+                Box x, y; x.reset(); y.reset();
+                for (int64_t i = i0; i < i1; i++) { x.grow(pbox[idx[i]]); y.grow(&pcen[3 * (size_t)idx[i]]); }
+                cbx[2 * (size_t)c] = x; cbx[2 * (size_t)c + 1] = y;
+            }
+        }
+#pragma omp taskwait
+        for (int c = 0; c < n_chunks; c++) { box.grow(cbx[2 * (size_t)c]); cb.grow(cbx[2 * (size_t)c + 1]); }
+    } else
     for (int64_t i = b; i < e; i++) { box.grow(pbox[idx[i]]); cb.grow(&pcen[3 * (size_t)idx[i]]); }
     nd.box = box;
-    const int64_t cnt = e - b;
     nd.sfirst = (int32_t)b; nd.scount = (int32_t)cnt;
     const int MAX_LEAF = max_leaf;
     auto make_leaf = [&]() { nd.left = nd.right = -1; nd.first = (int32_t)b; nd.count = (int32_t)cnt; if (!dp.empty()) solve(node); };
     if (cnt == 1) { make_leaf(); return; }
 
-    // binned SAH over the three axes
+    // binned SAH over the three axes: ONE pass over the node's primitives fills the bins of all three (the boxes are reached through
+    // the index array, a cache miss each: three passes were three misses per primitive)
     float best_cost = INFINITY;
     int best_axis = -1, best_bin = -1;
+    struct Bins { Box bb[3][NBINS_MAX]; int64_t bc[3][NBINS_MAX]; };
+    float lo3[3], scale3[3];
+    bool use[3];
     for (int ax = 0; ax < 3; ax++) {
-        const float lo = cb.lo[ax], ext = cb.hi[ax] - cb.lo[ax];
-        if (!(ext > 0)) continue;
-        Box bb[NBINS_MAX]; int64_t bc[NBINS_MAX];
-        for (int k = 0; k < NBINS; k++) { bb[k].reset(); bc[k] = 0; }
-        const float scale = NBINS / ext;
-        for (int64_t i = b; i < e; i++) {
+        const float ext = cb.hi[ax] - cb.lo[ax];
+        use[ax] = ext > 0;
+        lo3[ax] = cb.lo[ax]; scale3[ax] = use[ax] ? NBINS / ext : 0.f;
+    }
+    auto bin_range = [&](Bins& q, int64_t i0, int64_t i1) {
+        for (int ax = 0; ax < 3; ax++) for (int k = 0; k < NBINS; k++) { q.bb[ax][k].reset(); q.bc[ax][k] = 0; }
+        for (int64_t i = i0; i < i1; i++) {
             const uint32_t p = idx[i];
-            int k = (int)((pcen[3 * (size_t)p + ax] - lo) * scale);
-            k = k < 0 ? 0 : (k >= NBINS ? NBINS - 1 : k);
-            bb[k].grow(pbox[p]); bc[k]++;
+            const Box& pb = pbox[p];
+            const float* pc = &pcen[3 * (size_t)p];
+            for (int ax = 0; ax < 3; ax++) {
+                if (!use[ax]) continue;
+                int k = (int)((pc[ax] - lo3[ax]) * scale3[ax]);
+                k = k < 0 ? 0 : (k >= NBINS ? NBINS - 1 : k);
+                q.bb[ax][k].grow(pb); q.bc[ax][k]++;
+            }
         }
+    };
+    Bins bins;      // 6 KB of stack per level of the recursion
+    if (n_chunks > 1) {
+        std::vector<Bins> part((size_t)n_chunks);
+        for (int c = 0; c < n_chunks; c++) {
+#pragma omp task default(shared) firstprivate(c)
+            bin_range(part[(size_t)c], b + cnt * c / n_chunks, b + cnt * (c + 1) / n_chunks);
+        }
+#pragma omp taskwait
+        for (int ax = 0; ax < 3; ax++) for (int k = 0; k < NBINS; k++) { bins.bb[ax][k].reset(); bins.bc[ax][k] = 0; }
+        for (int c = 0; c < n_chunks; c++)
+            for (int ax = 0; ax < 3; ax++) for (int k = 0; k < NBINS; k++) { if (part[(size_t)c].bc[ax][k]) bins.bb[ax][k].grow(part[(size_t)c].bb[ax][k]); bins.bc[ax][k] += part[(size_t)c].bc[ax][k]; }
+    } else bin_range(bins, b, e);
+    for (int ax = 0; ax < 3; ax++) {
+        if (!use[ax]) continue;
+        const Box* bb = bins.bb[ax]; const int64_t* bc = bins.bc[ax];
         float ra[NBINS_MAX]; int64_t rc[NBINS_MAX];
         Box acc; acc.reset(); int64_t c = 0;
         for (int k = NBINS - 1; k > 0; k--) { acc.grow(bb[k]); c += bc[k]; ra[k] = acc.area(); rc[k] = c; }
@@ -221,13 +265,23 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
     }
 
     // ---- collapse to 8-wide, breadth first so that a node's internal children are contiguous ----
-    struct Work { int32_t bnode; uint32_t wide; int depth; };
-    std::vector<Work> queue;
-    out_nodes.reserve((size_t)n_tri / 3 + 16);
-    leaf_order.reserve(n_tri);
-    out_nodes.emplace_back();
-    queue.push_back({0, 0, 1});
-    size_t head = 0;
+    // Level by level (the emission order is breadth first, so the nodes of one level are consecutive): (A) every node of the level
+    // picks its children, slots and counts, in parallel; (B) a serial prefix sum hands out the indices of the internal children and
+    // the first triangle of each node, in the order a node-by-node loop would; (C) the nodes are quantised and written, in parallel.
+    struct Item {
+        int32_t bnode; uint32_t wide;
+        int32_t ch[8]; bool ch_leaf[8]; int nc; int slot_child[8];
+        Box nb;
+        uint32_t n_internal, n_tris, child_base, tri_base;
+    };
+    std::vector<Item> level, next;
+    out_nodes.assign(1, Node8());
+    leaf_order.assign((size_t)n_tri, 0u);
+    {
+        Item root; memset(&root, 0, sizeof(root));
+        root.bnode = 0; root.wide = 0;
+        level.push_back(root);
+    }
     {   // the half grid of the scene (ptb_bvh8.h half_grid_c): fixed by the root box, whose cells are the largest of the tree
         const Box& rb = B.nodes[0].box;
         int e_root = -100;
@@ -236,125 +290,156 @@ void build_bvh8(const float* verts9, int64_t n_tri, std::vector<Node8>& out_node
         stats.half_c = half_grid_c(e_root);
     }
     const int e_lo = PTB_HALF_E_LO - stats.half_c;
-    while (head < queue.size()) {
-        const Work w = queue[head++];
-        if (w.depth > stats.depth) stats.level_start.push_back(w.wide);     // breadth-first emission: the first node of a new level
-        stats.depth = std::max(stats.depth, w.depth);
-        int32_t ch[8]; bool ch_leaf[8]; int nc = 0;
-        const BNode& root = B.nodes[w.bnode];
-        if (!B.dp.empty()) {
-            // children of the wide node rooted at w.bnode: follow the recorded decisions
-            struct Item { int32_t n; int i; };
-            Item st[16]; int sp = 0;
-            if (root.count > 0 || root.scount <= 3) { ch[nc] = w.bnode; ch_leaf[nc++] = true; }   // a tiny mesh: the root holds one leaf
-            else {
-                const int k = B.dp[w.bnode].k8;
-                st[sp++] = {root.right, 8 - k}; st[sp++] = {root.left, k};
+    uint64_t tri_running = 0;
+    int64_t leaves = 0;
+    for (int depth = 1; !level.empty(); depth++) {
+        stats.level_start.push_back(level[0].wide);     // breadth-first emission: the first node of this level
+        stats.depth = depth;
+        const int64_t n_items = (int64_t)level.size();
+        // ---- (A) children, node box, slots
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int64_t it_ = 0; it_ < n_items; it_++) {
+            Item& w = level[(size_t)it_];
+            int32_t* ch = w.ch; bool* ch_leaf = w.ch_leaf; int nc = 0;
+            const BNode& root = B.nodes[w.bnode];
+            if (!B.dp.empty()) {
+                // children of the wide node rooted at w.bnode: follow the recorded decisions
+                struct It { int32_t n; int i; };
+                It st[16]; int sp = 0;
+                if (root.count > 0 || root.scount <= 3) { ch[nc] = w.bnode; ch_leaf[nc++] = true; }   // a tiny mesh: the root holds one leaf
+                else {
+                    const int k = B.dp[w.bnode].k8;
+                    st[sp++] = {root.right, 8 - k}; st[sp++] = {root.left, k};
+                }
+                while (sp > 0) {
+                    const It it = st[--sp];
+                    const BNode& m = B.nodes[it.n];
+                    if (m.count > 0) { ch[nc] = it.n; ch_leaf[nc++] = true; continue; }
+                    if (it.i == 1) { ch[nc] = it.n; ch_leaf[nc++] = B.dp[it.n].d[0] == 0; continue; }
+                    const int k = B.dp[it.n].d[it.i - 1];
+                    if (k == 0) st[sp++] = {it.n, it.i - 1};
+                    else { st[sp++] = {m.right, it.i - k}; st[sp++] = {m.left, k}; }
+                }
+            } else {
+                if (root.count > 0) ch[nc++] = w.bnode;           // a leaf root: one leaf child
+                else { ch[nc++] = root.left; ch[nc++] = root.right; }
+                while (nc < 8) {
+                    int best = -1; float best_area = -1.f;
+                    for (int i = 0; i < nc; i++) {
+                        const BNode& c = B.nodes[ch[i]];
+                        if (c.count > 0) continue;
+                        const float a = c.box.area();
+                        if (a > best_area) { best_area = a; best = i; }
+                    }
+                    if (best < 0) break;
+                    const BNode& c = B.nodes[ch[best]];
+                    ch[best] = c.left; ch[nc++] = c.right;
+                }
+                for (int i = 0; i < nc; i++) ch_leaf[i] = B.nodes[ch[i]].count > 0;
             }
-            while (sp > 0) {
-                const Item it = st[--sp];
-                const BNode& m = B.nodes[it.n];
-                if (m.count > 0) { ch[nc] = it.n; ch_leaf[nc++] = true; continue; }
-                if (it.i == 1) { ch[nc] = it.n; ch_leaf[nc++] = B.dp[it.n].d[0] == 0; continue; }
-                const int k = B.dp[it.n].d[it.i - 1];
-                if (k == 0) st[sp++] = {it.n, it.i - 1};
-                else { st[sp++] = {m.right, it.i - k}; st[sp++] = {m.left, k}; }
-            }
-        } else {
-        if (root.count > 0) ch[nc++] = w.bnode;           // a leaf root: one leaf child
-        else { ch[nc++] = root.left; ch[nc++] = root.right; }
-        while (nc < 8) {
-            int best = -1; float best_area = -1.f;
+            w.nc = nc;
+            Box nb; nb.reset();
+            for (int i = 0; i < nc; i++) nb.grow(B.nodes[ch[i]].box);
+            w.nb = nb;
+            // slot s prefers the child lying towards corner s (bit2=+x, bit1=+y, bit0=+z)
+            float ncx[3]; for (int k = 0; k < 3; k++) ncx[k] = 0.5f * (nb.lo[k] + nb.hi[k]);
+            float cost[8][8];
             for (int i = 0; i < nc; i++) {
+                const Box& cbx = B.nodes[ch[i]].box;
+                float off[3]; for (int k = 0; k < 3; k++) off[k] = 0.5f * (cbx.lo[k] + cbx.hi[k]) - ncx[k];
+                for (int s = 0; s < 8; s++)
+                    cost[i][s] = ((s & 4) ? off[0] : -off[0]) + ((s & 2) ? off[1] : -off[1]) + ((s & 1) ? off[2] : -off[2]);
+            }
+            int* slot_child = w.slot_child; for (int s = 0; s < 8; s++) slot_child[s] = -1;
+            bool child_done[8] = {false, false, false, false, false, false, false, false};
+            for (int it = 0; it < nc; it++) {
+                float bestc = -INFINITY; int bi = -1, bs = -1;
+                for (int i = 0; i < nc; i++) {
+                    if (child_done[i]) continue;
+                    for (int s = 0; s < 8; s++) {
+                        if (slot_child[s] >= 0) continue;
+                        if (cost[i][s] > bestc) { bestc = cost[i][s]; bi = i; bs = s; }
+                    }
+                }
+                slot_child[bs] = bi; child_done[bi] = true;
+            }
+            uint32_t ni = 0, nt = 0;
+            for (int s = 0; s < 8; s++) {
+                const int i = slot_child[s];
+                if (i < 0) continue;
+                if (ch_leaf[i]) nt += (uint32_t)B.nodes[ch[i]].scount; else ni++;
+            }
+            w.n_internal = ni; w.n_tris = nt;
+        }
+        // ---- (B) indices, in node order; the next level's nodes in slot order
+        next.clear();
+        uint64_t node_running = out_nodes.size();
+        for (int64_t it_ = 0; it_ < n_items; it_++) {
+            Item& w = level[(size_t)it_];
+            w.child_base = (uint32_t)node_running; w.tri_base = (uint32_t)tri_running;
+            for (int s = 0; s < 8; s++) {
+                const int i = w.slot_child[s];
+                if (i < 0 || w.ch_leaf[i]) continue;
+                Item c; c.bnode = w.ch[i]; c.wide = (uint32_t)node_running++;
+                next.push_back(c);
+            }
+            tri_running += w.n_tris;
+        }
+        out_nodes.resize((size_t)node_running);
+        // ---- (C) quantise and write
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : leaves)
+        for (int64_t it_ = 0; it_ < n_items; it_++) {
+            const Item& w = level[(size_t)it_];
+            const int32_t* ch = w.ch; const bool* ch_leaf = w.ch_leaf; const int* slot_child = w.slot_child;
+            const Box& nb = w.nb;
+            Node8 nd;
+            memset(&nd, 0, sizeof(nd));
+            nd.ex = exponent_byte(nb.hi[0] - nb.lo[0], node_coord_slack(nb.lo[0], nb.hi[0]), e_lo);
+            nd.ey = exponent_byte(nb.hi[1] - nb.lo[1], node_coord_slack(nb.lo[1], nb.hi[1]), e_lo);
+            nd.ez = exponent_byte(nb.hi[2] - nb.lo[2], node_coord_slack(nb.lo[2], nb.hi[2]), e_lo);
+            nd.hx = half_exp_byte((int)nd.ex - 127, stats.half_c); nd.hy = half_exp_byte((int)nd.ey - 127, stats.half_c); nd.hz = half_exp_byte((int)nd.ez - 127, stats.half_c);
+            const float cell[3] = {std::ldexp(1.f, (int)nd.ex - 127), std::ldexp(1.f, (int)nd.ey - 127), std::ldexp(1.f, (int)nd.ez - 127)};
+            // conservative slack: 4e-3 of a cell (covers the rounding of the traversal's folded plane bias in either form of
+            // ptb_bvh8.h planes4) plus a few ulps of the coordinate
+            float eps[3], p[3];
+            for (int k = 0; k < 3; k++) {
+                eps[k] = cell[k] * 4e-3f + node_coord_slack(nb.lo[k], nb.hi[k]);
+                p[k] = nb.lo[k] - eps[k];
+            }
+            nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
+            nd.child_base = w.child_base;
+            nd.tri_base = w.tri_base;
+            uint32_t tri_off = 0, valid24 = 0;
+            for (int s = 0; s < 8; s++) {
+                const int i = slot_child[s];
+                if (i < 0) continue;
                 const BNode& c = B.nodes[ch[i]];
-                if (c.count > 0) continue;
-                const float a = c.box.area();
-                if (a > best_area) { best_area = a; best = i; }
-            }
-            if (best < 0) break;
-            const BNode& c = B.nodes[ch[best]];
-            ch[best] = c.left; ch[nc++] = c.right;
-        }
-        for (int i = 0; i < nc; i++) ch_leaf[i] = B.nodes[ch[i]].count > 0;
-        }
-        // node box
-        Box nb; nb.reset();
-        for (int i = 0; i < nc; i++) nb.grow(B.nodes[ch[i]].box);
-        // ---- assign children to slots: slot s prefers the child lying towards corner s (bit2=+x, bit1=+y, bit0=+z)
-        float ncx[3]; for (int k = 0; k < 3; k++) ncx[k] = 0.5f * (nb.lo[k] + nb.hi[k]);
-        float cost[8][8];
-        for (int i = 0; i < nc; i++) {
-            const Box& cbx = B.nodes[ch[i]].box;
-            float off[3]; for (int k = 0; k < 3; k++) off[k] = 0.5f * (cbx.lo[k] + cbx.hi[k]) - ncx[k];
-            for (int s = 0; s < 8; s++)
-                cost[i][s] = ((s & 4) ? off[0] : -off[0]) + ((s & 2) ? off[1] : -off[1]) + ((s & 1) ? off[2] : -off[2]);
-        }
-        int slot_child[8]; for (int s = 0; s < 8; s++) slot_child[s] = -1;
-        bool child_done[8] = {false, false, false, false, false, false, false, false};
-        for (int it = 0; it < nc; it++) {
-            float bestc = -INFINITY; int bi = -1, bs = -1;
-            for (int i = 0; i < nc; i++) {
-                if (child_done[i]) continue;
-                for (int s = 0; s < 8; s++) {
-                    if (slot_child[s] >= 0) continue;
-                    if (cost[i][s] > bestc) { bestc = cost[i][s]; bi = i; bs = s; }
+                uint8_t* ql[3] = {nd.qlox, nd.qloy, nd.qloz};
+                uint8_t* qh[3] = {nd.qhix, nd.qhiy, nd.qhiz};
+                for (int k = 0; k < 3; k++) {
+                    float lo = std::floor((c.box.lo[k] - eps[k] - p[k]) / cell[k]);
+                    float hi = std::ceil((c.box.hi[k] + eps[k] - p[k]) / cell[k]);
+                    lo = std::min(std::max(lo, 0.f), 255.f);
+                    hi = std::min(std::max(hi, 0.f), 255.f);
+                    ql[k][s] = (uint8_t)lo; qh[k][s] = (uint8_t)hi;
+                }
+                if (ch_leaf[i]) {
+                    const uint32_t unary = (c.scount == 1) ? 1u : (c.scount == 2 ? 3u : 7u);
+                    valid24 |= unary << (3 * s);
+                    for (int t = 0; t < c.scount; t++) leaf_order[(size_t)w.tri_base + tri_off + (uint32_t)t] = B.idx[c.sfirst + t];
+                    tri_off += (uint32_t)c.scount;
+                    leaves++;
+                } else {
+                    nd.imask |= (uint8_t)(1u << s);
                 }
             }
-            slot_child[bs] = bi; child_done[bi] = true;
+            nd.valid24[0] = (uint8_t)(valid24 & 0xffu); nd.valid24[1] = (uint8_t)((valid24 >> 8) & 0xffu); nd.valid24[2] = (uint8_t)((valid24 >> 16) & 0xffu);
+            out_nodes[w.wide] = nd;
         }
-        // ---- emit
-        Node8 nd;
-        memset(&nd, 0, sizeof(nd));
-        nd.ex = exponent_byte(nb.hi[0] - nb.lo[0], node_coord_slack(nb.lo[0], nb.hi[0]), e_lo);
-        nd.ey = exponent_byte(nb.hi[1] - nb.lo[1], node_coord_slack(nb.lo[1], nb.hi[1]), e_lo);
-        nd.ez = exponent_byte(nb.hi[2] - nb.lo[2], node_coord_slack(nb.lo[2], nb.hi[2]), e_lo);
-        nd.hx = half_exp_byte((int)nd.ex - 127, stats.half_c); nd.hy = half_exp_byte((int)nd.ey - 127, stats.half_c); nd.hz = half_exp_byte((int)nd.ez - 127, stats.half_c);
-        const float cell[3] = {std::ldexp(1.f, (int)nd.ex - 127), std::ldexp(1.f, (int)nd.ey - 127), std::ldexp(1.f, (int)nd.ez - 127)};
-        // conservative slack: 4e-3 of a cell (covers the rounding of the traversal's folded plane bias in either form of
-        // ptb_bvh8.h planes4) plus a few ulps of the coordinate
-        float eps[3], p[3];
-        for (int k = 0; k < 3; k++) {
-            eps[k] = cell[k] * 4e-3f + node_coord_slack(nb.lo[k], nb.hi[k]);
-            p[k] = nb.lo[k] - eps[k];
-        }
-        nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
-        nd.child_base = (uint32_t)out_nodes.size();
-        nd.tri_base = (uint32_t)leaf_order.size();
-        uint32_t n_internal = 0, tri_off = 0, valid24 = 0;
-        for (int s = 0; s < 8; s++) {
-            const int i = slot_child[s];
-            if (i < 0) continue;
-            const BNode& c = B.nodes[ch[i]];
-            uint8_t* ql[3] = {nd.qlox, nd.qloy, nd.qloz};
-            uint8_t* qh[3] = {nd.qhix, nd.qhiy, nd.qhiz};
-            for (int k = 0; k < 3; k++) {
-                float lo = std::floor((c.box.lo[k] - eps[k] - p[k]) / cell[k]);
-                float hi = std::ceil((c.box.hi[k] + eps[k] - p[k]) / cell[k]);
-                lo = std::min(std::max(lo, 0.f), 255.f);
-                hi = std::min(std::max(hi, 0.f), 255.f);
-                ql[k][s] = (uint8_t)lo; qh[k][s] = (uint8_t)hi;
-            }
-            if (ch_leaf[i]) {
-                const uint32_t unary = (c.scount == 1) ? 1u : (c.scount == 2 ? 3u : 7u);
-                valid24 |= unary << (3 * s);
-                for (int t = 0; t < c.scount; t++) leaf_order.push_back(B.idx[c.sfirst + t]);
-                tri_off += (uint32_t)c.scount;
-                stats.leaves++;
-            } else {
-                nd.imask |= (uint8_t)(1u << s);
-                n_internal++;
-            }
-        }
-        nd.valid24[0] = (uint8_t)(valid24 & 0xffu); nd.valid24[1] = (uint8_t)((valid24 >> 8) & 0xffu); nd.valid24[2] = (uint8_t)((valid24 >> 16) & 0xffu);
-        // allocate the internal children contiguously, in slot order
-        for (int s = 0; s < 8; s++) {
-            const int i = slot_child[s];
-            if (i < 0 || ch_leaf[i]) continue;
-            queue.push_back({ch[i], (uint32_t)out_nodes.size(), w.depth + 1});
-            out_nodes.emplace_back();
-        }
-        out_nodes[w.wide] = nd;
+        level.swap(next);
     }
+    stats.leaves = leaves;
+    leaf_order.resize((size_t)tri_running);
     stats.n_nodes = (int64_t)out_nodes.size();
     stats.level_start.push_back((uint32_t)out_nodes.size());
     stats.n_binary_nodes = B.n_nodes.load();
